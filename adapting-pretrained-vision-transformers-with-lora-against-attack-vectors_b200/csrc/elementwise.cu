@@ -1,0 +1,433 @@
+// HBM-bound kernels of the attack step: LayerNorm forward/backward (warp-shuffle reductions, 16-byte
+// vector accesses), classifier head + cross-entropy + its backward, and the fused PGD/FGSM pixel kernels
+// (sign step + L-inf projection + [0,1] clamp + ImageNet renormalisation + im2col, one pass).
+//
+// Reference call sites replaced: torch LayerNorm (HF modeling_vit.py:325-326,333,340,455), classifier
+// (HF:613,642), F.cross_entropy (whitebox_attacks.py:29), normalisation (whitebox_attacks.py:26),
+// the FGSM tail (whitebox_attacks.py:32-38) and the torchattacks PGD loop body.
+#include "vitatk_internal.h"
+
+namespace vitatk {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ void unpack8(const uint4& q, float* f) {
+  const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(p[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 q;
+  __nv_bfloat162* p = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return q;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, CH = cols / 256 sixteen-byte chunks per lane
+// ------------------------------------------------------------------------------------------------
+template <int CH>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, bf16* __restrict__ y,
+                                                     float2* __restrict__ stats, int rows, float eps) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  constexpr int COLS = CH * 256;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * COLS);
+  float v[CH][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    unpack8(__ldg(xr + lane + 32 * i), v[i]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[i][j];
+  }
+  const float mean = warp_sum(s) * (1.f / COLS);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < CH; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float d = v[i][j] - mean;
+      q += d * d;
+    }
+  const float rstd = rsqrtf(warp_sum(q) * (1.f / COLS) + eps);
+  uint4* yr = reinterpret_cast<uint4*>(y + static_cast<size_t>(row) * COLS);
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    const int c = (lane + 32 * i) * 8;
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * gg[j] + bb[j];
+    yr[lane + 32 * i] = pack8(o);
+  }
+  if (lane == 0) stats[row] = make_float2(mean, rstd);
+}
+
+template <int CH>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                     const float2* __restrict__ stats, const float* __restrict__ gamma,
+                                                     const bf16* __restrict__ dres, bf16* __restrict__ dx, int rows) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  constexpr int COLS = CH * 256;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * COLS);
+  const uint4* dyr = reinterpret_cast<const uint4*>(dy + static_cast<size_t>(row) * COLS);
+  const float2 st = stats[row];
+  float xh[CH][8], gd[CH][8];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    const int c = (lane + 32 * i) * 8;
+    float xv[8], dv[8];
+    unpack8(__ldg(xr + lane + 32 * i), xv);
+    unpack8(__ldg(dyr + lane + 32 * i), dv);
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      xh[i][j] = (xv[j] - st.x) * st.y;
+      gd[i][j] = dv[j] * gg[j];
+      s1 += gd[i][j];
+      s2 += gd[i][j] * xh[i][j];
+    }
+  }
+  const float m1 = warp_sum(s1) * (1.f / COLS);
+  const float m2 = warp_sum(s2) * (1.f / COLS);
+  uint4* dxr = reinterpret_cast<uint4*>(dx + static_cast<size_t>(row) * COLS);
+  const uint4* rr = dres ? reinterpret_cast<const uint4*>(dres + static_cast<size_t>(row) * COLS) : nullptr;
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    float o[8];
+    float r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (rr) unpack8(__ldg(rr + lane + 32 * i), r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = r[j] + st.y * (gd[i][j] - m1 - xh[i][j] * m2);
+    dxr[lane + 32 * i] = pack8(o);
+  }
+}
+
+int layernorm_fwd(const bf16* x, const float* gamma, const float* beta, bf16* y, float2* stats, int rows, int cols,
+                  float eps, cudaStream_t stream) {
+  const int grid = (rows + 7) / 8;
+  switch (cols) {
+    case 768: ln_fwd_kernel<3><<<grid, 256, 0, stream>>>(x, gamma, beta, y, stats, rows, eps); break;
+    case 1024: ln_fwd_kernel<4><<<grid, 256, 0, stream>>>(x, gamma, beta, y, stats, rows, eps); break;
+    case 512: ln_fwd_kernel<2><<<grid, 256, 0, stream>>>(x, gamma, beta, y, stats, rows, eps); break;
+    case 256: ln_fwd_kernel<1><<<grid, 256, 0, stream>>>(x, gamma, beta, y, stats, rows, eps); break;
+    default: set_error("layernorm_fwd: cols=%d unsupported", cols); return 1;
+  }
+  VITATK_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int layernorm_bwd(const bf16* dy, const bf16* x, const float2* stats, const float* gamma, const bf16* dres,
+                  bf16* dx_out, int rows, int cols, cudaStream_t stream) {
+  const int grid = (rows + 7) / 8;
+  switch (cols) {
+    case 768: ln_bwd_kernel<3><<<grid, 256, 0, stream>>>(dy, x, stats, gamma, dres, dx_out, rows); break;
+    case 1024: ln_bwd_kernel<4><<<grid, 256, 0, stream>>>(dy, x, stats, gamma, dres, dx_out, rows); break;
+    case 512: ln_bwd_kernel<2><<<grid, 256, 0, stream>>>(dy, x, stats, gamma, dres, dx_out, rows); break;
+    case 256: ln_bwd_kernel<1><<<grid, 256, 0, stream>>>(dy, x, stats, gamma, dres, dx_out, rows); break;
+    default: set_error("layernorm_bwd: cols=%d unsupported", cols); return 1;
+  }
+  VITATK_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// classifier head: final LN on the CLS row + Linear + softmax-CE (+ backward to the hidden state)
+// one CTA (256 threads) per image
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int i = 0; i < static_cast<int>(blockDim.x >> 5); ++i) t += red[i];
+  return t;
+}
+
+__global__ void __launch_bounds__(256) head_kernel(const bf16* __restrict__ h, const float* __restrict__ gamma,
+                                                   const float* __restrict__ beta, const float* __restrict__ Wc,
+                                                   const float* __restrict__ bc, const int64_t* __restrict__ labels,
+                                                   float* __restrict__ logits, float* __restrict__ loss,
+                                                   bf16* __restrict__ dh, int tokens, int dim, int classes, float eps,
+                                                   float grad_scale) {
+  extern __shared__ float hs[];
+  float* xn = hs;              // [dim] normalised (x-mean)*rstd
+  float* yv = xn + dim;        // [dim] LN output
+  float* dyv = yv + dim;       // [dim] grad wrt LN output
+  float* lg = dyv + dim;       // [classes]
+  __shared__ float red[8];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const bf16* row = h + static_cast<size_t>(b) * tokens * dim;
+  float s = 0.f;
+  for (int k = tid; k < dim; k += blockDim.x) {
+    const float v = __bfloat162float(row[k]);
+    xn[k] = v;
+    s += v;
+  }
+  const float mean = block_sum(s, red) / dim;
+  float q = 0.f;
+  for (int k = tid; k < dim; k += blockDim.x) {
+    const float d = xn[k] - mean;
+    q += d * d;
+  }
+  const float rstd = rsqrtf(block_sum(q, red) / dim + eps);
+  for (int k = tid; k < dim; k += blockDim.x) {
+    const float xh = (xn[k] - mean) * rstd;
+    xn[k] = xh;
+    yv[k] = xh * gamma[k] + beta[k];
+  }
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+  for (int c = warp; c < classes; c += nw) {
+    float acc = 0.f;
+    for (int k = lane; k < dim; k += 32) acc += yv[k] * __ldg(Wc + static_cast<size_t>(c) * dim + k);
+    acc = warp_sum(acc);
+    if (lane == 0) lg[c] = acc + bc[c];
+  }
+  __syncthreads();
+  // softmax-CE (every thread redundantly: classes is tiny)
+  float mx = -INFINITY;
+  for (int c = 0; c < classes; ++c) mx = fmaxf(mx, lg[c]);
+  float se = 0.f;
+  for (int c = 0; c < classes; ++c) se += expf(lg[c] - mx);
+  const float lse = mx + logf(se);
+  const int y = labels ? static_cast<int>(labels[b]) : -1;
+  if (tid < classes) logits[static_cast<size_t>(b) * classes + tid] = lg[tid];
+  for (int c = tid + blockDim.x; c < classes; c += blockDim.x) logits[static_cast<size_t>(b) * classes + c] = lg[c];
+  if (tid == 0 && loss && y >= 0) loss[b] = lse - lg[y];
+  if (dh == nullptr) return;
+  // dlogits = (softmax - onehot) * grad_scale ; dy = Wc^T dlogits
+  for (int k = tid; k < dim; k += blockDim.x) {
+    float acc = 0.f;
+    for (int c = 0; c < classes; ++c) {
+      const float p = expf(lg[c] - lse) - (c == y ? 1.f : 0.f);
+      acc += p * __ldg(Wc + static_cast<size_t>(c) * dim + k);
+    }
+    dyv[k] = acc * grad_scale;
+  }
+  __syncthreads();
+  float s1 = 0.f, s2 = 0.f;
+  for (int k = tid; k < dim; k += blockDim.x) {
+    const float gd = dyv[k] * gamma[k];
+    s1 += gd;
+    s2 += gd * xn[k];
+  }
+  const float m1 = block_sum(s1, red) / dim;
+  const float m2 = block_sum(s2, red) / dim;
+  bf16* drow = dh + static_cast<size_t>(b) * tokens * dim;
+  for (int k = tid; k < dim; k += blockDim.x)
+    drow[k] = __float2bfloat16(rstd * (dyv[k] * gamma[k] - m1 - xn[k] * m2));
+  // every other token of this image receives zero gradient from the head
+  uint4* z = reinterpret_cast<uint4*>(drow + dim);
+  const int nz = (tokens - 1) * dim / 8;
+  for (int i = tid; i < nz; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+}
+
+int head_fwd_bwd(const bf16* h, const float* gamma, const float* beta, const float* Wc, const float* bc,
+                 const int64_t* labels, float* logits, float* loss, bf16* dh, int batch, int tokens, int dim,
+                 int classes, float eps, float grad_scale, cudaStream_t stream) {
+  if (dim % 8 != 0 || classes > 4096) {
+    set_error("head_fwd_bwd: dim=%d classes=%d unsupported", dim, classes);
+    return 1;
+  }
+  const size_t smem = (3 * dim + classes) * sizeof(float);
+  head_kernel<<<batch, 256, smem, stream>>>(h, gamma, beta, Wc, bc, labels, logits, loss, dh, tokens, dim, classes, eps,
+                                            grad_scale);
+  VITATK_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pixel kernels. Image NCHW fp32 [B,3,224,224]; im2col matrix bf16 [B*197, 768]:
+//   row = b*197 + 1 + (y/16)*14 + x/16 (row b*197 is the CLS slot, all zero), col = c*256 + (y%16)*16 + x%16
+// (the flattening of the HF patch conv weight [768,3,16,16], HF modeling_vit.py:151,166).
+// One thread = 8 consecutive pixels of one image row = one 16-byte bf16 chunk of the im2col matrix.
+// ------------------------------------------------------------------------------------------------
+static constexpr int IMG = 224, PATCH = 16, GRID_P = 14, TOK = 197, PDIM = 768;
+
+__device__ __forceinline__ size_t cols_offset(int b, int c, int y, int x8) {
+  const int x = x8 * 8;
+  const int rowi = b * TOK + 1 + (y >> 4) * GRID_P + (x >> 4);
+  return static_cast<size_t>(rowi) * PDIM + c * 256 + (y & 15) * 16 + (x & 15);
+}
+__device__ __forceinline__ void decode_idx(long long idx, int& b, int& c, int& y, int& x8) {
+  x8 = static_cast<int>(idx % 28);
+  idx /= 28;
+  y = static_cast<int>(idx % IMG);
+  idx /= IMG;
+  c = static_cast<int>(idx % 3);
+  b = static_cast<int>(idx / 3);
+}
+__device__ __forceinline__ float u01_hash(uint64_t seed, uint64_t ctr) {
+  // splitmix64 finaliser on (seed, counter): stateless, independent of launch geometry / GPU count
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (ctr + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return static_cast<float>(z >> 40) * (1.0f / 16777216.0f);
+}
+
+__global__ void __launch_bounds__(256) pgd_init_kernel(const float* __restrict__ x0, const float* __restrict__ noise,
+                                                       float* __restrict__ adv, bf16* __restrict__ cols, int batch,
+                                                       PixelNorm nrm, float eps, int use_rng, uint64_t seed,
+                                                       uint64_t image_index0) {
+  const long long total = static_cast<long long>(batch) * 3 * IMG * 28;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  int b, c, y, x8;
+  decode_idx(idx, b, c, y, x8);
+  const size_t p = (static_cast<size_t>(b * 3 + c) * IMG + y) * IMG + x8 * 8;
+  const float4 a0 = __ldg(reinterpret_cast<const float4*>(x0 + p));
+  const float4 a1 = __ldg(reinterpret_cast<const float4*>(x0 + p + 4));
+  float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+  if (noise != nullptr) {
+    const float4 n0 = __ldg(reinterpret_cast<const float4*>(noise + p));
+    const float4 n1 = __ldg(reinterpret_cast<const float4*>(noise + p + 4));
+    const float nn[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fminf(fmaxf(v[j] + nn[j], 0.f), 1.f);
+  } else if (use_rng) {
+    const uint64_t e0 = (image_index0 + b) * (3ull * IMG * IMG) + (static_cast<uint64_t>(c) * IMG + y) * IMG + x8 * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float n = (2.f * u01_hash(seed, e0 + j) - 1.f) * eps;
+      v[j] = fminf(fmaxf(v[j] + n, 0.f), 1.f);
+    }
+  }
+  *reinterpret_cast<float4*>(adv + p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(adv + p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  float o[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = (v[j] - nrm.mean[c]) * nrm.inv_std[c];
+  *reinterpret_cast<uint4*>(cols + cols_offset(b, c, y, x8)) = pack8(o);
+  // CLS slot of the im2col matrix stays zero: thread (c=0,y=0) of each 8-pixel column group clears a share
+  if (c == 0 && y < 4) {
+    // 4 rows x 28 threads = 112 threads >= 96 chunks of the 768-wide CLS row
+    const int chunk = y * 28 + x8;
+    if (chunk < PDIM / 8)
+      *reinterpret_cast<uint4*>(cols + static_cast<size_t>(b) * TOK * PDIM + chunk * 8) = make_uint4(0, 0, 0, 0);
+  }
+}
+
+__global__ void __launch_bounds__(256) pgd_update_kernel(const bf16* __restrict__ dcols, const float* __restrict__ x0,
+                                                         float* __restrict__ adv, bf16* __restrict__ cols, int batch,
+                                                         PixelNorm nrm, float eps, float alpha) {
+  const long long total = static_cast<long long>(batch) * 3 * IMG * 28;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  int b, c, y, x8;
+  decode_idx(idx, b, c, y, x8);
+  const size_t p = (static_cast<size_t>(b * 3 + c) * IMG + y) * IMG + x8 * 8;
+  const size_t co = cols_offset(b, c, y, x8);
+  float g[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(dcols + co)), g);
+  const float4 o0 = __ldg(reinterpret_cast<const float4*>(x0 + p));
+  const float4 o1 = __ldg(reinterpret_cast<const float4*>(x0 + p + 4));
+  const float4 a0 = *reinterpret_cast<const float4*>(adv + p);
+  const float4 a1 = *reinterpret_cast<const float4*>(adv + p + 4);
+  const float xo[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+  float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+  float o[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    // torchattacks order: adv + alpha*sign(g); delta = clamp(adv - x, -eps, eps); adv = clamp(x + delta, 0, 1)
+    const float sg = (g[j] > 0.f) ? 1.f : ((g[j] < 0.f) ? -1.f : 0.f);
+    const float stepped = v[j] + alpha * sg;
+    const float delta = fminf(fmaxf(stepped - xo[j], -eps), eps);
+    v[j] = fminf(fmaxf(xo[j] + delta, 0.f), 1.f);
+    o[j] = (v[j] - nrm.mean[c]) * nrm.inv_std[c];
+  }
+  *reinterpret_cast<float4*>(adv + p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(adv + p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  *reinterpret_cast<uint4*>(cols + co) = pack8(o);
+}
+
+__global__ void __launch_bounds__(256) grad_to_image_kernel(const bf16* __restrict__ dcols, float* __restrict__ grad,
+                                                            int batch, PixelNorm nrm, float scale) {
+  const long long total = static_cast<long long>(batch) * 3 * IMG * 28;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  int b, c, y, x8;
+  decode_idx(idx, b, c, y, x8);
+  const size_t p = (static_cast<size_t>(b * 3 + c) * IMG + y) * IMG + x8 * 8;
+  float g[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(dcols + cols_offset(b, c, y, x8))), g);
+  const float k = nrm.inv_std[c] * scale;
+  *reinterpret_cast<float4*>(grad + p) = make_float4(g[0] * k, g[1] * k, g[2] * k, g[3] * k);
+  *reinterpret_cast<float4*>(grad + p + 4) = make_float4(g[4] * k, g[5] * k, g[6] * k, g[7] * k);
+}
+
+__global__ void count_correct_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, int batch,
+                                     int classes, unsigned long long* counts) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  int ok = 0;
+  if (b < batch) {
+    const float* l = logits + static_cast<size_t>(b) * classes;
+    int best = 0;
+    float bv = l[0];
+    for (int c = 1; c < classes; ++c)
+      if (l[c] > bv) {  // first maximum wins, like torch.argmax
+        bv = l[c];
+        best = c;
+      }
+    ok = (best == static_cast<int>(labels[b])) ? 1 : 0;
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, ok);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(counts, static_cast<unsigned long long>(__popc(m)));
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(counts + 1, static_cast<unsigned long long>(batch));
+}
+
+static inline int pixel_grid(int batch) {
+  const long long total = static_cast<long long>(batch) * 3 * IMG * 28;
+  return static_cast<int>((total + 255) / 256);
+}
+
+int pgd_init(const float* x0, const float* noise, float* adv, bf16* cols, int batch, PixelNorm nrm, float eps,
+             int use_rng, uint64_t seed, uint64_t image_index0, cudaStream_t stream) {
+  pgd_init_kernel<<<pixel_grid(batch), 256, 0, stream>>>(x0, noise, adv, cols, batch, nrm, eps, use_rng, seed,
+                                                         image_index0);
+  VITATK_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int pgd_update(const bf16* dcols, const float* x0, float* adv, bf16* cols, int batch, PixelNorm nrm, float eps,
+               float alpha, cudaStream_t stream) {
+  pgd_update_kernel<<<pixel_grid(batch), 256, 0, stream>>>(dcols, x0, adv, cols, batch, nrm, eps, alpha);
+  VITATK_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int grad_to_image(const bf16* dcols, float* grad, int batch, PixelNorm nrm, float scale, cudaStream_t stream) {
+  grad_to_image_kernel<<<pixel_grid(batch), 256, 0, stream>>>(dcols, grad, batch, nrm, scale);
+  VITATK_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int count_correct(const float* logits, const int64_t* labels, int batch, int classes, long long* counts,
+                  cudaStream_t stream) {
+  count_correct_kernel<<<(batch + 127) / 128, 128, 0, stream>>>(logits, labels, batch, classes,
+                                                                reinterpret_cast<unsigned long long*>(counts));
+  VITATK_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace vitatk

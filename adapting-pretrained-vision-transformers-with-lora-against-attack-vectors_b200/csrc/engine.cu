@@ -1,0 +1,619 @@
+// Host-side engine behind the C ABI (include/vitatk.h): weight registry, activation workspace laid out
+// for B200 HBM, per-batch GEMM plans (TMA descriptors), and the forward / input-gradient / PGD drivers.
+//
+// HBM layout (M = batch * 197 tokens, all bf16 unless noted):
+//   saved for backward, per layer l : h_in[l] [M,768], h_mid[l] [M,768], qkv[l] [M,2304], u[l] [M,3072],
+//                                     stats1[l], stats2[l] float2[M]          (~13.8 KB / token / layer)
+//   transient scratch               : cols [M,768] (normalised im2col), xn [M,768] (LN out), ao [M,768]
+//                                     (attention out), g [M,3072] (GELU out), T [M,192] (LoRA x*A^T),
+//                                     dh_a/dh_b [M,768], du [M,3072], dxn [M,768], dao [M,768], dqkv [M,2304]
+// No weight gradients exist on this path (autograd.grad w.r.t. the input only), so GEMM inputs are never
+// saved for dW; only what LN / GELU / softmax need for their Jacobians is kept.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <vector>
+
+#include "../../include/vitatk.h"
+#include "vitatk_internal.h"
+
+namespace vitatk {
+
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+static constexpr int TOKENS = 197;
+static constexpr int LORA_PAD = 64;
+
+struct LoraSite {
+  int rank = 0;
+  const bf16 *la_fwd = nullptr, *lb_fwd = nullptr, *lb_bwd = nullptr, *la_bwd = nullptr;
+};
+
+struct LayerWeights {
+  const float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
+  const bf16 *qkv_w = nullptr, *qkv_wt = nullptr, *proj_w = nullptr, *proj_wt = nullptr;
+  const bf16 *fc1_w = nullptr, *fc1_wt = nullptr, *fc2_w = nullptr, *fc2_wt = nullptr;
+  const float *qkv_b = nullptr, *proj_b = nullptr, *fc1_b = nullptr, *fc2_b = nullptr;
+  LoraSite lora[4];
+};
+
+struct LayerPlans {
+  // forward
+  GemmPlan t_qkv, qkv, t_proj, proj, t_fc1, fc1, t_fc2, fc2;
+  // backward (input gradients)
+  GemmPlan bt_fc2, bfc2, bt_fc1, bfc1, bt_proj, bproj, bt_qkv, bqkv;
+};
+
+struct PlanSet {
+  int batch = 0;
+  GemmPlan patch, bpatch;
+  std::vector<LayerPlans> layers;
+};
+
+}  // namespace vitatk
+
+using namespace vitatk;
+
+struct vitatk_engine {
+  vitatk_config cfg;
+  int num_sms = 148;
+  bool finalized = false;
+  // global weights
+  const bf16 *patch_w = nullptr, *patch_wt = nullptr;
+  const float *embed_table = nullptr, *lnf_g = nullptr, *lnf_b = nullptr, *head_w = nullptr, *head_b = nullptr;
+  std::vector<LayerWeights> lw;
+  // workspace
+  char* ws = nullptr;
+  long long ws_bytes = 0;
+  std::vector<bf16*> h;      // [layers+1]
+  std::vector<bf16*> h_mid;  // [layers]
+  std::vector<bf16*> qkv;    // [layers]
+  std::vector<bf16*> u;      // [layers]
+  std::vector<float2*> st1, st2;
+  bf16 *cols = nullptr, *xn = nullptr, *ao = nullptr, *g = nullptr, *T = nullptr;
+  bf16 *dh_a = nullptr, *dh_b = nullptr, *du = nullptr, *dxn = nullptr, *dao = nullptr, *dqkv = nullptr;
+  float *logits = nullptr, *loss = nullptr, *scratch_img = nullptr;
+  std::map<int, PlanSet*> plans;
+  long long launches = 0;
+  PixelNorm nrm;
+};
+
+namespace vitatk {
+
+static int lora_ksteps(int r) { return (r + 15) / 16; }
+
+static int build_plans(vitatk_engine* e, int batch, PlanSet** out) {
+  auto it = e->plans.find(batch);
+  if (it != e->plans.end()) {
+    *out = it->second;
+    return 0;
+  }
+  const vitatk_config& c = e->cfg;
+  const int M = batch * TOKENS, D = c.dim, F = c.mlp_dim;
+  PlanSet* ps = new PlanSet();
+  ps->batch = batch;
+  ps->layers.resize(c.layers);
+  GemmEpilogue plain = {EPI_PLAIN, nullptr, nullptr, 0, nullptr, 0};
+  // patch embedding: h[0] = cols * Wpe^T + table[m % 197]
+  {
+    GemmEpilogue ep = {EPI_ROWTABLE, nullptr, nullptr, 0, e->embed_table, TOKENS};
+    if (gemm_plan_init(&ps->patch, M, D, D, e->cols, D, e->patch_w, D, e->h[0], D, nullptr, 0, nullptr, 0, nullptr, 0, 0,
+                       0, 0, ep))
+      return 1;
+  }
+  for (int l = 0; l < c.layers; ++l) {
+    const LayerWeights& w = e->lw[l];
+    LayerPlans& p = ps->layers[l];
+    const LoraSite& sq = w.lora[VITATK_SITE_QKV];
+    const LoraSite& sp = w.lora[VITATK_SITE_PROJ];
+    const LoraSite& s1 = w.lora[VITATK_SITE_FC1];
+    const LoraSite& s2 = w.lora[VITATK_SITE_FC2];
+    // ---------------- forward ----------------
+    if (sq.rank > 0 &&
+        gemm_plan_init(&p.t_qkv, M, 3 * LORA_PAD, D, e->xn, D, sq.la_fwd, D, e->T, 3 * LORA_PAD, nullptr, 0, nullptr, 0,
+                       nullptr, 0, 0, 0, 0, plain))
+      return 1;
+    {
+      GemmEpilogue ep = {EPI_PLAIN, w.qkv_b, nullptr, 0, nullptr, 0};
+      if (gemm_plan_init(&p.qkv, M, 3 * D, D, e->xn, D, w.qkv_w, D, e->qkv[l], 3 * D, nullptr, 0, e->T, 3 * LORA_PAD,
+                         sq.lb_fwd, LORA_PAD, sq.rank > 0 ? 1 : 0, lora_ksteps(sq.rank), sq.rank > 0 ? D : 0, ep))
+        return 1;
+    }
+    if (sp.rank > 0 &&
+        gemm_plan_init(&p.t_proj, M, LORA_PAD, D, e->ao, D, sp.la_fwd, D, e->T, 3 * LORA_PAD, nullptr, 0, nullptr, 0,
+                       nullptr, 0, 0, 0, 0, plain))
+      return 1;
+    {
+      GemmEpilogue ep = {EPI_RESIDUAL, w.proj_b, e->h[l], D, nullptr, 0};
+      if (gemm_plan_init(&p.proj, M, D, D, e->ao, D, w.proj_w, D, e->h_mid[l], D, nullptr, 0, e->T, 3 * LORA_PAD,
+                         sp.lb_fwd, LORA_PAD, sp.rank > 0 ? 1 : 0, lora_ksteps(sp.rank), 0, ep))
+        return 1;
+    }
+    if (s1.rank > 0 &&
+        gemm_plan_init(&p.t_fc1, M, LORA_PAD, D, e->xn, D, s1.la_fwd, D, e->T, 3 * LORA_PAD, nullptr, 0, nullptr, 0,
+                       nullptr, 0, 0, 0, 0, plain))
+      return 1;
+    {
+      GemmEpilogue ep = {EPI_GELU_DUAL, w.fc1_b, nullptr, 0, nullptr, 0};
+      if (gemm_plan_init(&p.fc1, M, F, D, e->xn, D, w.fc1_w, D, e->u[l], F, e->g, F, e->T, 3 * LORA_PAD, s1.lb_fwd,
+                         LORA_PAD, s1.rank > 0 ? 1 : 0, lora_ksteps(s1.rank), 0, ep))
+        return 1;
+    }
+    if (s2.rank > 0 &&
+        gemm_plan_init(&p.t_fc2, M, LORA_PAD, F, e->g, F, s2.la_fwd, F, e->T, 3 * LORA_PAD, nullptr, 0, nullptr, 0,
+                       nullptr, 0, 0, 0, 0, plain))
+      return 1;
+    {
+      GemmEpilogue ep = {EPI_RESIDUAL, w.fc2_b, e->h_mid[l], D, nullptr, 0};
+      if (gemm_plan_init(&p.fc2, M, D, F, e->g, F, w.fc2_w, F, e->h[l + 1], D, nullptr, 0, e->T, 3 * LORA_PAD,
+                         s2.lb_fwd, LORA_PAD, s2.rank > 0 ? 1 : 0, lora_ksteps(s2.rank), 0, ep))
+        return 1;
+    }
+    // ---------------- backward ----------------
+    // The residual-stream gradient ping-pongs: layer l receives it in dh_in(l) and leaves dh_out(l).
+    // dh entering layer l (grad wrt h[l+1]) lives in dh_a; dh_mid in dh_b; result (grad wrt h[l]) in dh_a.
+    if (s2.rank > 0 &&
+        gemm_plan_init(&p.bt_fc2, M, LORA_PAD, D, e->dh_a, D, s2.lb_bwd, D, e->T, 3 * LORA_PAD, nullptr, 0, nullptr, 0,
+                       nullptr, 0, 0, 0, 0, plain))
+      return 1;
+    {
+      GemmEpilogue ep = {EPI_DGELU, nullptr, e->u[l], F, nullptr, 0};
+      if (gemm_plan_init(&p.bfc2, M, F, D, e->dh_a, D, w.fc2_wt, D, e->du, F, nullptr, 0, e->T, 3 * LORA_PAD, s2.la_bwd,
+                         LORA_PAD, s2.rank > 0 ? 1 : 0, lora_ksteps(s2.rank), 0, ep))
+        return 1;
+    }
+    if (s1.rank > 0 &&
+        gemm_plan_init(&p.bt_fc1, M, LORA_PAD, F, e->du, F, s1.lb_bwd, F, e->T, 3 * LORA_PAD, nullptr, 0, nullptr, 0,
+                       nullptr, 0, 0, 0, 0, plain))
+      return 1;
+    if (gemm_plan_init(&p.bfc1, M, D, F, e->du, F, w.fc1_wt, F, e->dxn, D, nullptr, 0, e->T, 3 * LORA_PAD, s1.la_bwd,
+                       LORA_PAD, s1.rank > 0 ? 1 : 0, lora_ksteps(s1.rank), 0, plain))
+      return 1;
+    if (sp.rank > 0 &&
+        gemm_plan_init(&p.bt_proj, M, LORA_PAD, D, e->dh_b, D, sp.lb_bwd, D, e->T, 3 * LORA_PAD, nullptr, 0, nullptr, 0,
+                       nullptr, 0, 0, 0, 0, plain))
+      return 1;
+    if (gemm_plan_init(&p.bproj, M, D, D, e->dh_b, D, w.proj_wt, D, e->dao, D, nullptr, 0, e->T, 3 * LORA_PAD,
+                       sp.la_bwd, LORA_PAD, sp.rank > 0 ? 1 : 0, lora_ksteps(sp.rank), 0, plain))
+      return 1;
+    if (sq.rank > 0 &&
+        gemm_plan_init(&p.bt_qkv, M, 3 * LORA_PAD, 3 * D, e->dqkv, 3 * D, sq.lb_bwd, 3 * D, e->T, 3 * LORA_PAD, nullptr,
+                       0, nullptr, 0, nullptr, 0, 0, 0, 0, plain))
+      return 1;
+    if (gemm_plan_init(&p.bqkv, M, D, 3 * D, e->dqkv, 3 * D, w.qkv_wt, 3 * D, e->dxn, D, nullptr, 0, e->T,
+                       3 * LORA_PAD, sq.la_bwd, 3 * LORA_PAD, sq.rank > 0 ? 3 : 0, lora_ksteps(sq.rank), 0, plain))
+      return 1;
+  }
+  // patch-embed input gradient: dcols = dh0 * Wpe   (written over the im2col buffer's twin)
+  if (gemm_plan_init(&ps->bpatch, M, D, D, e->dh_a, D, e->patch_wt, D, e->dxn, D, nullptr, 0, nullptr, 0, nullptr, 0, 0,
+                     0, 0, plain))
+    return 1;
+  e->plans[batch] = ps;
+  *out = ps;
+  return 0;
+}
+
+#define RUN(expr)        \
+  do {                   \
+    if (expr) return 1;  \
+    ++e->launches;       \
+  } while (0)
+
+// forward through the encoder from the im2col'd, normalised input in e->cols
+static int encoder_forward(vitatk_engine* e, PlanSet* ps, int batch, cudaStream_t s) {
+  const vitatk_config& c = e->cfg;
+  const int M = batch * TOKENS, D = c.dim;
+  RUN(gemm_launch(&ps->patch, s, e->num_sms));
+  for (int l = 0; l < c.layers; ++l) {
+    const LayerWeights& w = e->lw[l];
+    LayerPlans& p = ps->layers[l];
+    RUN(layernorm_fwd(e->h[l], w.ln1_g, w.ln1_b, e->xn, e->st1[l], M, D, c.ln_eps, s));
+    if (w.lora[VITATK_SITE_QKV].rank > 0) RUN(gemm_launch(&p.t_qkv, s, e->num_sms));
+    RUN(gemm_launch(&p.qkv, s, e->num_sms));
+    RUN(attention_fwd(e->qkv[l], e->ao, batch, TOKENS, c.heads, s));
+    if (w.lora[VITATK_SITE_PROJ].rank > 0) RUN(gemm_launch(&p.t_proj, s, e->num_sms));
+    RUN(gemm_launch(&p.proj, s, e->num_sms));
+    RUN(layernorm_fwd(e->h_mid[l], w.ln2_g, w.ln2_b, e->xn, e->st2[l], M, D, c.ln_eps, s));
+    if (w.lora[VITATK_SITE_FC1].rank > 0) RUN(gemm_launch(&p.t_fc1, s, e->num_sms));
+    RUN(gemm_launch(&p.fc1, s, e->num_sms));
+    if (w.lora[VITATK_SITE_FC2].rank > 0) RUN(gemm_launch(&p.t_fc2, s, e->num_sms));
+    RUN(gemm_launch(&p.fc2, s, e->num_sms));
+  }
+  return 0;
+}
+
+// backward from dh_a = dL/dh[layers] down to e->dxn = dL/d(cols)
+static int encoder_backward(vitatk_engine* e, PlanSet* ps, int batch, cudaStream_t s) {
+  const vitatk_config& c = e->cfg;
+  const int M = batch * TOKENS, D = c.dim;
+  for (int l = c.layers - 1; l >= 0; --l) {
+    const LayerWeights& w = e->lw[l];
+    LayerPlans& p = ps->layers[l];
+    if (w.lora[VITATK_SITE_FC2].rank > 0) RUN(gemm_launch(&p.bt_fc2, s, e->num_sms));
+    RUN(gemm_launch(&p.bfc2, s, e->num_sms));  // du = (dh W2 + lora) * gelu'(u)
+    if (w.lora[VITATK_SITE_FC1].rank > 0) RUN(gemm_launch(&p.bt_fc1, s, e->num_sms));
+    RUN(gemm_launch(&p.bfc1, s, e->num_sms));  // dxn = du W1 + lora
+    RUN(layernorm_bwd(e->dxn, e->h_mid[l], e->st2[l], w.ln2_g, e->dh_a, e->dh_b, M, D, s));  // dh_mid
+    if (w.lora[VITATK_SITE_PROJ].rank > 0) RUN(gemm_launch(&p.bt_proj, s, e->num_sms));
+    RUN(gemm_launch(&p.bproj, s, e->num_sms));  // dao = dh_mid Wp + lora
+    RUN(attention_bwd(e->qkv[l], e->dao, e->dqkv, batch, TOKENS, c.heads, s));
+    if (w.lora[VITATK_SITE_QKV].rank > 0) RUN(gemm_launch(&p.bt_qkv, s, e->num_sms));
+    RUN(gemm_launch(&p.bqkv, s, e->num_sms));  // dxn = dqkv Wqkv + lora
+    RUN(layernorm_bwd(e->dxn, e->h[l], e->st1[l], w.ln1_g, e->dh_b, e->dh_a, M, D, s));  // dh wrt h[l]
+  }
+  RUN(gemm_launch(&ps->bpatch, s, e->num_sms));  // dxn <- dL/d(cols)
+  return 0;
+}
+
+static int check_batch(vitatk_engine* e, int batch) {
+  if (!e || !e->finalized) {
+    set_error("engine not finalized");
+    return 1;
+  }
+  if (batch < 1 || batch > e->cfg.max_batch) {
+    set_error("batch %d outside [1, max_batch=%d]", batch, e->cfg.max_batch);
+    return 1;
+  }
+  return 0;
+}
+
+}  // namespace vitatk
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+const char* vitatk_last_error(void) { return last_error(); }
+int vitatk_version(void) { return 1; }
+
+int vitatk_create(const vitatk_config* cfg, vitatk_engine** out) {
+  if (!cfg || !out) {
+    set_error("vitatk_create: null argument");
+    return 1;
+  }
+  if (cfg->image_size != 224 || cfg->patch_size != 16 || cfg->dim != 768 || cfg->heads * 64 != cfg->dim ||
+      cfg->mlp_dim % 256 != 0 || cfg->layers < 1 || cfg->num_classes < 1 || cfg->max_batch < 1) {
+    set_error("vitatk_create: unsupported geometry (need image 224, patch 16, dim 768 = heads*64, mlp %% 256 == 0)");
+    return 1;
+  }
+  int dev = 0;
+  VITATK_CUDA_OK(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  VITATK_CUDA_OK(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) {
+    set_error("vitatk requires an sm_100a (B200) device; found sm_%d%d. There is no fallback path.", prop.major,
+              prop.minor);
+    return 1;
+  }
+  vitatk_engine* e = new vitatk_engine();
+  e->cfg = *cfg;
+  e->num_sms = prop.multiProcessorCount;
+  e->lw.resize(cfg->layers);
+  for (int i = 0; i < 3; ++i) {
+    e->nrm.mean[i] = cfg->mean[i];
+    e->nrm.inv_std[i] = 1.0f / cfg->std[i];
+  }
+  *out = e;
+  return 0;
+}
+
+int vitatk_destroy(vitatk_engine* e) {
+  if (!e) return 0;
+  for (auto& kv : e->plans) delete kv.second;
+  if (e->ws) cudaFree(e->ws);
+  delete e;
+  return 0;
+}
+
+int vitatk_set_tensor(vitatk_engine* e, int id, int layer, const void* p, long long nbytes) {
+  if (!e || !p) {
+    set_error("vitatk_set_tensor: null argument");
+    return 1;
+  }
+  const vitatk_config& c = e->cfg;
+  const long long D = c.dim, F = c.mlp_dim, C = c.num_classes;
+  long long want = -1;
+  LayerWeights* w = nullptr;
+  if (id >= 16) {
+    if (layer < 0 || layer >= c.layers) {
+      set_error("vitatk_set_tensor: layer %d out of range", layer);
+      return 1;
+    }
+    w = &e->lw[layer];
+  }
+  const float* pf = static_cast<const float*>(p);
+  const bf16* pb = static_cast<const bf16*>(p);
+  switch (id) {
+    case VITATK_PATCH_W: e->patch_w = pb; want = D * D * 2; break;
+    case VITATK_PATCH_WT: e->patch_wt = pb; want = D * D * 2; break;
+    case VITATK_EMBED_TABLE: e->embed_table = pf; want = TOKENS * D * 4; break;
+    case VITATK_LNF_G: e->lnf_g = pf; want = D * 4; break;
+    case VITATK_LNF_B: e->lnf_b = pf; want = D * 4; break;
+    case VITATK_HEAD_W: e->head_w = pf; want = C * D * 4; break;
+    case VITATK_HEAD_B: e->head_b = pf; want = C * 4; break;
+    case VITATK_LN1_G: w->ln1_g = pf; want = D * 4; break;
+    case VITATK_LN1_B: w->ln1_b = pf; want = D * 4; break;
+    case VITATK_LN2_G: w->ln2_g = pf; want = D * 4; break;
+    case VITATK_LN2_B: w->ln2_b = pf; want = D * 4; break;
+    case VITATK_QKV_W: w->qkv_w = pb; want = 3 * D * D * 2; break;
+    case VITATK_QKV_WT: w->qkv_wt = pb; want = 3 * D * D * 2; break;
+    case VITATK_QKV_B: w->qkv_b = pf; want = 3 * D * 4; break;
+    case VITATK_PROJ_W: w->proj_w = pb; want = D * D * 2; break;
+    case VITATK_PROJ_WT: w->proj_wt = pb; want = D * D * 2; break;
+    case VITATK_PROJ_B: w->proj_b = pf; want = D * 4; break;
+    case VITATK_FC1_W: w->fc1_w = pb; want = F * D * 2; break;
+    case VITATK_FC1_WT: w->fc1_wt = pb; want = F * D * 2; break;
+    case VITATK_FC1_B: w->fc1_b = pf; want = F * 4; break;
+    case VITATK_FC2_W: w->fc2_w = pb; want = F * D * 2; break;
+    case VITATK_FC2_WT: w->fc2_wt = pb; want = F * D * 2; break;
+    case VITATK_FC2_B: w->fc2_b = pf; want = D * 4; break;
+    default: set_error("vitatk_set_tensor: unknown tensor id %d", id); return 1;
+  }
+  if (nbytes != want) {
+    set_error("vitatk_set_tensor: id %d layer %d expects %lld bytes, got %lld", id, layer, want, nbytes);
+    return 1;
+  }
+  // weights changed -> cached TMA plans are stale
+  for (auto& kv : e->plans) delete kv.second;
+  e->plans.clear();
+  return 0;
+}
+
+int vitatk_set_lora(vitatk_engine* e, int layer, int site, int rank, const void* la_fwd, const void* lb_fwd,
+                    const void* lb_bwd, const void* la_bwd) {
+  if (!e || layer < 0 || layer >= e->cfg.layers || site < 0 || site > 3) {
+    set_error("vitatk_set_lora: bad layer/site");
+    return 1;
+  }
+  if (rank < 0 || rank > LORA_PAD) {
+    set_error("vitatk_set_lora: rank %d unsupported (0..%d)", rank, LORA_PAD);
+    return 1;
+  }
+  if (rank > 0 && (!la_fwd || !lb_fwd || !lb_bwd || !la_bwd)) {
+    set_error("vitatk_set_lora: null adapter tensor");
+    return 1;
+  }
+  LoraSite& s = e->lw[layer].lora[site];
+  s.rank = rank;
+  s.la_fwd = static_cast<const bf16*>(la_fwd);
+  s.lb_fwd = static_cast<const bf16*>(lb_fwd);
+  s.lb_bwd = static_cast<const bf16*>(lb_bwd);
+  s.la_bwd = static_cast<const bf16*>(la_bwd);
+  for (auto& kv : e->plans) delete kv.second;
+  e->plans.clear();
+  return 0;
+}
+
+int vitatk_set_normalization(vitatk_engine* e, const float* mean3, const float* std3) {
+  if (!e || !mean3 || !std3) {
+    set_error("vitatk_set_normalization: null argument");
+    return 1;
+  }
+  for (int i = 0; i < 3; ++i) {
+    if (!(std3[i] > 0.f)) {
+      set_error("vitatk_set_normalization: std[%d] must be > 0", i);
+      return 1;
+    }
+    e->cfg.mean[i] = mean3[i];
+    e->cfg.std[i] = std3[i];
+    e->nrm.mean[i] = mean3[i];
+    e->nrm.inv_std[i] = 1.0f / std3[i];
+  }
+  return 0;
+}
+
+long long vitatk_workspace_bytes(const vitatk_engine* e) { return e ? e->ws_bytes : 0; }
+long long vitatk_launch_count(const vitatk_engine* e) { return e ? e->launches : 0; }
+
+int vitatk_finalize(vitatk_engine* e) {
+  if (!e) {
+    set_error("vitatk_finalize: null engine");
+    return 1;
+  }
+  if (e->finalized) return 0;
+  const vitatk_config& c = e->cfg;
+  if (!e->patch_w || !e->patch_wt || !e->embed_table || !e->lnf_g || !e->lnf_b || !e->head_w || !e->head_b) {
+    set_error("vitatk_finalize: a global tensor is missing");
+    return 1;
+  }
+  for (int l = 0; l < c.layers; ++l) {
+    const LayerWeights& w = e->lw[l];
+    if (!w.ln1_g || !w.ln1_b || !w.ln2_g || !w.ln2_b || !w.qkv_w || !w.qkv_wt || !w.qkv_b || !w.proj_w || !w.proj_wt ||
+        !w.proj_b || !w.fc1_w || !w.fc1_wt || !w.fc1_b || !w.fc2_w || !w.fc2_wt || !w.fc2_b) {
+      set_error("vitatk_finalize: layer %d has a missing tensor", l);
+      return 1;
+    }
+  }
+  const long long Mmax = static_cast<long long>(c.max_batch) * TOKENS;
+  const long long D = c.dim, F = c.mlp_dim;
+  auto al = [](long long b) { return (b + 1023) / 1024 * 1024; };
+  const long long sz_d = al(Mmax * D * 2), sz_3d = al(Mmax * 3 * D * 2), sz_f = al(Mmax * F * 2);
+  const long long sz_st = al(Mmax * 8), sz_t = al(Mmax * 3 * LORA_PAD * 2);
+  const long long sz_img = al(static_cast<long long>(c.max_batch) * 3 * 224 * 224 * 4);
+  long long total = 0;
+  total += (c.layers + 1) * sz_d;                       // h
+  total += c.layers * (sz_d + sz_3d + sz_f + 2 * sz_st);  // h_mid, qkv, u, stats
+  total += 3 * sz_d + sz_f + sz_t;                      // cols, xn, ao, g, T
+  total += 4 * sz_d + sz_f + sz_3d;                     // dh_a, dh_b, dxn, dao, du, dqkv
+  total += al(static_cast<long long>(c.max_batch) * c.num_classes * 4) + al(c.max_batch * 4) + sz_img;
+  VITATK_CUDA_OK(cudaMalloc(&e->ws, total));
+  VITATK_CUDA_OK(cudaMemset(e->ws, 0, total));
+  e->ws_bytes = total;
+  char* p = e->ws;
+  auto take = [&](long long b) {
+    char* r = p;
+    p += b;
+    return r;
+  };
+  e->h.resize(c.layers + 1);
+  e->h_mid.resize(c.layers);
+  e->qkv.resize(c.layers);
+  e->u.resize(c.layers);
+  e->st1.resize(c.layers);
+  e->st2.resize(c.layers);
+  for (int l = 0; l <= c.layers; ++l) e->h[l] = reinterpret_cast<bf16*>(take(sz_d));
+  for (int l = 0; l < c.layers; ++l) {
+    e->h_mid[l] = reinterpret_cast<bf16*>(take(sz_d));
+    e->qkv[l] = reinterpret_cast<bf16*>(take(sz_3d));
+    e->u[l] = reinterpret_cast<bf16*>(take(sz_f));
+    e->st1[l] = reinterpret_cast<float2*>(take(sz_st));
+    e->st2[l] = reinterpret_cast<float2*>(take(sz_st));
+  }
+  e->cols = reinterpret_cast<bf16*>(take(sz_d));
+  e->xn = reinterpret_cast<bf16*>(take(sz_d));
+  e->ao = reinterpret_cast<bf16*>(take(sz_d));
+  e->g = reinterpret_cast<bf16*>(take(sz_f));
+  e->T = reinterpret_cast<bf16*>(take(sz_t));
+  e->dh_a = reinterpret_cast<bf16*>(take(sz_d));
+  e->dh_b = reinterpret_cast<bf16*>(take(sz_d));
+  e->dxn = reinterpret_cast<bf16*>(take(sz_d));
+  e->dao = reinterpret_cast<bf16*>(take(sz_d));
+  e->du = reinterpret_cast<bf16*>(take(sz_f));
+  e->dqkv = reinterpret_cast<bf16*>(take(sz_3d));
+  e->logits = reinterpret_cast<float*>(take(al(static_cast<long long>(c.max_batch) * c.num_classes * 4)));
+  e->loss = reinterpret_cast<float*>(take(al(c.max_batch * 4)));
+  e->scratch_img = reinterpret_cast<float*>(take(sz_img));
+  e->finalized = true;
+  return 0;
+}
+
+int vitatk_forward(vitatk_engine* e, const float* images, int batch, float* logits_out, void* stream) {
+  if (check_batch(e, batch)) return 1;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  PlanSet* ps = nullptr;
+  if (build_plans(e, batch, &ps)) return 1;
+  const vitatk_config& c = e->cfg;
+  RUN(pgd_init(images, nullptr, e->scratch_img, e->cols, batch, e->nrm, 0.f, 0, 0, 0, s));
+  if (encoder_forward(e, ps, batch, s)) return 1;
+  RUN(head_fwd_bwd(e->h[c.layers], e->lnf_g, e->lnf_b, e->head_w, e->head_b, nullptr, logits_out, nullptr, nullptr,
+                   batch, TOKENS, c.dim, c.num_classes, c.ln_eps, 0.f, s));
+  return 0;
+}
+
+int vitatk_input_grad(vitatk_engine* e, const float* images, const int64_t* labels, int batch, float* grad_out,
+                      float* logits_out, float* loss_out, void* stream) {
+  if (check_batch(e, batch)) return 1;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  PlanSet* ps = nullptr;
+  if (build_plans(e, batch, &ps)) return 1;
+  const vitatk_config& c = e->cfg;
+  RUN(pgd_init(images, nullptr, e->scratch_img, e->cols, batch, e->nrm, 0.f, 0, 0, 0, s));
+  if (encoder_forward(e, ps, batch, s)) return 1;
+  // internal gradient is of the SUM of per-image CE (keeps magnitudes independent of batch / sharding);
+  // the 1/B of the reference's mean reduction (whitebox_attacks.py:29) is applied when materialising.
+  RUN(head_fwd_bwd(e->h[c.layers], e->lnf_g, e->lnf_b, e->head_w, e->head_b, labels, logits_out ? logits_out : e->logits,
+                   loss_out ? loss_out : e->loss, e->dh_a, batch, TOKENS, c.dim, c.num_classes, c.ln_eps, 1.0f, s));
+  if (encoder_backward(e, ps, batch, s)) return 1;
+  RUN(grad_to_image(e->dxn, grad_out, batch, e->nrm, 1.0f / batch, s));
+  return 0;
+}
+
+int vitatk_attack(vitatk_engine* e, const float* images, const int64_t* labels, int batch, float eps, float alpha,
+                  int steps, int start, const float* noise, uint64_t seed, uint64_t image_index0, float* adv,
+                  void* stream) {
+  if (check_batch(e, batch)) return 1;
+  if (steps < 1 || !images || !labels || !adv || images == adv) {
+    set_error("vitatk_attack: bad arguments (steps>=1, non-null, adv must not alias images)");
+    return 1;
+  }
+  if (start == VITATK_START_NOISE && !noise) {
+    set_error("vitatk_attack: start=NOISE needs noise_dev");
+    return 1;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  PlanSet* ps = nullptr;
+  if (build_plans(e, batch, &ps)) return 1;
+  const vitatk_config& c = e->cfg;
+  RUN(pgd_init(images, start == VITATK_START_NOISE ? noise : nullptr, adv, e->cols, batch, e->nrm, eps,
+               start == VITATK_START_RNG ? 1 : 0, seed, image_index0, s));
+  for (int it = 0; it < steps; ++it) {
+    if (encoder_forward(e, ps, batch, s)) return 1;
+    RUN(head_fwd_bwd(e->h[c.layers], e->lnf_g, e->lnf_b, e->head_w, e->head_b, labels, e->logits, e->loss, e->dh_a,
+                     batch, TOKENS, c.dim, c.num_classes, c.ln_eps, 1.0f, s));
+    if (encoder_backward(e, ps, batch, s)) return 1;
+    RUN(pgd_update(e->dxn, images, adv, e->cols, batch, e->nrm, eps, alpha, s));
+  }
+  return 0;
+}
+
+int vitatk_count_correct(vitatk_engine* e, const float* images, const int64_t* labels, int batch, long long* counts,
+                         void* stream) {
+  if (vitatk_forward(e, images, batch, e->logits, stream)) return 1;
+  RUN(count_correct(e->logits, labels, batch, e->cfg.num_classes, counts, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+// ------------------------------- kernel-level entry points -------------------------------
+int vitatk_k_gemm(int M, int N, int K, const void* A, int lda, const void* B, int ldb, void* out, int ldo, void* out2,
+                  int ldo2, const void* T, int ldt, const void* LB, int ldlb, int lora_nkb, int lora_ksteps_,
+                  int lora_group_cols, int epi_mode, const float* bias, const void* res, int ld_res, const float* table,
+                  int table_rows, int use_simt, void* stream) {
+  GemmPlan p;
+  GemmEpilogue ep = {epi_mode, bias, static_cast<const bf16*>(res), ld_res, table, table_rows};
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (use_simt) {
+    p.M = M; p.N = N; p.K = K; p.BN = 0;
+    p.lora_nkb = lora_nkb; p.lora_ksteps = lora_ksteps_; p.lora_group_cols = lora_group_cols; p.epi = ep;
+    return gemm_launch_simt(&p, static_cast<const bf16*>(A), lda, static_cast<const bf16*>(B), ldb,
+                            static_cast<bf16*>(out), ldo, static_cast<bf16*>(out2), ldo2, static_cast<const bf16*>(T),
+                            ldt, static_cast<const bf16*>(LB), ldlb, s);
+  }
+  if (gemm_plan_init(&p, M, N, K, static_cast<const bf16*>(A), lda, static_cast<const bf16*>(B), ldb,
+                     static_cast<bf16*>(out), ldo, static_cast<bf16*>(out2), ldo2, static_cast<const bf16*>(T), ldt,
+                     static_cast<const bf16*>(LB), ldlb, lora_nkb, lora_ksteps_, lora_group_cols, ep))
+    return 1;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return gemm_launch(&p, s, sms);
+}
+int vitatk_k_attention_fwd(const void* qkv, void* out, int batch, int tokens, int heads, void* stream) {
+  return attention_fwd(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), batch, tokens, heads,
+                       static_cast<cudaStream_t>(stream));
+}
+int vitatk_k_attention_bwd(const void* qkv, const void* dout, void* dqkv, int batch, int tokens, int heads,
+                           void* stream) {
+  return attention_bwd(static_cast<const bf16*>(qkv), static_cast<const bf16*>(dout), static_cast<bf16*>(dqkv), batch,
+                       tokens, heads, static_cast<cudaStream_t>(stream));
+}
+int vitatk_k_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* stats, int rows,
+                           int cols, float eps, void* stream) {
+  return layernorm_fwd(static_cast<const bf16*>(x), gamma, beta, static_cast<bf16*>(y),
+                       reinterpret_cast<float2*>(stats), rows, cols, eps, static_cast<cudaStream_t>(stream));
+}
+int vitatk_k_layernorm_bwd(const void* dy, const void* x, const float* stats, const float* gamma, const void* dres,
+                           void* dx, int rows, int cols, void* stream) {
+  return layernorm_bwd(static_cast<const bf16*>(dy), static_cast<const bf16*>(x),
+                       reinterpret_cast<const float2*>(stats), gamma, static_cast<const bf16*>(dres),
+                       static_cast<bf16*>(dx), rows, cols, static_cast<cudaStream_t>(stream));
+}
+static PixelNorm make_norm(const float* mean3, const float* std3) {
+  PixelNorm n;
+  for (int i = 0; i < 3; ++i) {
+    n.mean[i] = mean3[i];
+    n.inv_std[i] = 1.0f / std3[i];
+  }
+  return n;
+}
+int vitatk_k_pgd_update(const void* dcols, const float* x0, float* adv, void* cols, int batch, const float* mean3,
+                        const float* std3, float eps, float alpha, void* stream) {
+  return pgd_update(static_cast<const bf16*>(dcols), x0, adv, static_cast<bf16*>(cols), batch, make_norm(mean3, std3),
+                    eps, alpha, static_cast<cudaStream_t>(stream));
+}
+int vitatk_k_pgd_init(const float* x0, const float* noise, float* adv, void* cols, int batch, const float* mean3,
+                      const float* std3, float eps, int use_rng, uint64_t seed, uint64_t image_index0, void* stream) {
+  return pgd_init(x0, noise, adv, static_cast<bf16*>(cols), batch, make_norm(mean3, std3), eps, use_rng, seed,
+                  image_index0, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

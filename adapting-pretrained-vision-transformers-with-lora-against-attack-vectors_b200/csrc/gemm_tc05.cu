@@ -1,0 +1,463 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a with the LoRA product and the
+// bias / residual / GELU / GELU' / row-table epilogues fused into the accumulator tile.
+//
+//   out[M,N] = epi( A[M,K] * B[N,K]^T + T[M,64*nkb] * LB[N,64*nkb]^T )
+//
+// Replaces (reference call sites): every nn.Linear of HF ViTLayer (HF modeling_vit.py:216-218,262,
+// 290-298,305-311) plus the peft LoRA branch configured at train_loras.py:79-95, forward and
+// input-gradient backward (dX = dY*W + s*(dY*B)*A).
+//
+// Structure (one CTA per SM, 192 threads):
+//   warps 0-3 : epilogue   TMEM -> registers (tcgen05.ld) -> fused math -> swizzled smem -> TMA store
+//   warp  4   : TMA producer (cp.async.bulk.tensor, 128B swizzle, mbarrier complete_tx); owns TMEM alloc
+//   warp  5   : MMA issuer   (one thread, tcgen05.mma cta_group::1 kind::f16, M=128 N=BN K=16)
+// Pipelines: smem ring full/empty (TMA <-> MMA), TMEM accumulator double buffer full/empty
+// (MMA <-> epilogue), static persistent tile scheduler (tile = blockIdx.x + i*gridDim.x).
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "ptx.cuh"
+#include "vitatk_internal.h"
+
+namespace vitatk {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
+static constexpr int NUM_EPI_WARPS = 4;
+static constexpr int GEMM_THREADS = 192;
+static constexpr int STAGE_OUT_BYTES = 32 * 128;  // one warp's 32-row x 64-col bf16 store tile
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+  static constexpr int OUT_BYTES = NUM_EPI_WARPS * 2 * STAGE_OUT_BYTES;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + OUT_BYTES + BAR_BYTES;
+};
+
+struct GemmKernelArgs {
+  int M, N, K;
+  int lora_nkb, lora_ksteps, lora_group_cols;
+  GemmEpilogue epi;
+};
+
+__device__ __forceinline__ float gelu_exact(float u) { return 0.5f * u * (1.0f + erff(u * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad(float u) {
+  const float cdf = 0.5f * (1.0f + erff(u * 0.70710678118654752f));
+  const float pdf = 0.3989422804014327f * __expf(-0.5f * u * u);
+  return cdf + u * pdf;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void unpack_bf16x8(const uint4& q, float* f) {
+  const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(p[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmLA, const __grid_constant__ CUtensorMap tmLB,
+                 const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
+                 const GemmKernelArgs args) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024 B alignment: required by the 128B swizzle pattern shared by TMA and the UMMA descriptors
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_stage = smem;
+  uint8_t* smem_out = smem + STAGES * Cfg::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_out + Cfg::OUT_BYTES);
+  uint64_t* full_bar = bars;                   // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;         // [STAGES]
+  uint64_t* tmem_full = bars + 2 * STAGES;     // [2]
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int tiles_m = (args.M + BM - 1) / BM;
+  const int tiles_n = args.N / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int main_kb = args.K / BK;
+  const int num_kb = main_kb + args.lora_nkb;
+
+  if (warp == 5 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(&tmem_full[b], 1);
+      ptx::mbar_init(&tmem_empty[b], NUM_EPI_WARPS);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 4) {
+    if (lane == 0) {
+      ptx::prefetch_tmap(&tmA);
+      ptx::prefetch_tmap(&tmB);
+      ptx::prefetch_tmap(&tmOut);
+      if (args.lora_nkb > 0) {
+        ptx::prefetch_tmap(&tmLA);
+        ptx::prefetch_tmap(&tmLB);
+      }
+    }
+    ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    // ================================= TMA producer =================================
+    if (lane == 0) {
+      uint32_t cnt = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * BM;
+        const int n0 = (tile % tiles_n) * BN;
+        const int tcol0 = args.lora_group_cols > 0 ? (n0 / args.lora_group_cols) * BK : 0;
+        for (int kb = 0; kb < num_kb; ++kb, ++cnt) {
+          const int s = cnt % STAGES;
+          const uint32_t ph = (cnt / STAGES) & 1;
+          ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem_stage + s * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          ptx::mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+          if (kb < main_kb) {
+            ptx::tma_load_2d(sa, &tmA, &full_bar[s], kb * BK, m0);
+            ptx::tma_load_2d(sb, &tmB, &full_bar[s], kb * BK, n0);
+          } else {
+            const int j = kb - main_kb;
+            ptx::tma_load_2d(sa, &tmLA, &full_bar[s], tcol0 + j * BK, m0);
+            ptx::tma_load_2d(sb, &tmLB, &full_bar[s], j * BK, n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ================================= MMA issuer =================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN);
+      uint32_t cnt = 0;
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t buf = it & 1;
+        const uint32_t use = it >> 1;
+        ptx::mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);  // epilogue has drained this accumulator
+        ptx::tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + buf * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++cnt) {
+          const int s = cnt % STAGES;
+          const uint32_t ph = (cnt / STAGES) & 1;
+          ptx::mbar_wait(&full_bar[s], ph);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem_stage + s * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::A_BYTES;
+          const uint64_t adesc = ptx::make_smem_desc_sw128(sa);
+          const uint64_t bdesc = ptx::make_smem_desc_sw128(sb);
+          const int ksteps = kb < main_kb ? (BK / 16) : args.lora_ksteps;
+          for (int k = 0; k < ksteps; ++k) {
+            // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr>>4) field
+            ptx::umma_bf16(tmem_acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty_bar[s]);  // smem slot reusable once these MMAs retire
+        }
+        ptx::umma_commit(&tmem_full[buf]);  // accumulator complete
+      }
+    }
+  } else {
+    // ================================= epilogue warps 0..3 =================================
+    uint8_t* my_out = smem_out + warp * 2 * STAGE_OUT_BYTES;
+    const GemmEpilogue epi = args.epi;
+    uint32_t it = 0;
+    uint32_t store_idx = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m0 = (tile / tiles_n) * BM;
+      const int n0 = (tile % tiles_n) * BN;
+      const uint32_t buf = it & 1;
+      const uint32_t use = it >> 1;
+      ptx::mbar_wait(&tmem_full[buf], use & 1);
+      ptx::tc_fence_after();
+      const int row = m0 + warp * 32 + lane;
+      const bool row_ok = row < args.M;
+      const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + buf * BN;
+
+#pragma unroll 1
+      for (int c = 0; c < BN / 64; ++c) {
+        uint32_t packed[32];   // 64 bf16 of the primary output
+        uint32_t packed2[32];  // 64 bf16 of the secondary output (GELU_DUAL only)
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(taddr_row + c * 64 + half * 32, r);
+          ptx::tmem_ld_wait();
+          const int ncol = n0 + c * 64 + half * 32;
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          if (epi.bias != nullptr) {
+            const float4* bp = reinterpret_cast<const float4*>(epi.bias + ncol);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 b = __ldg(bp + i);
+              v[4 * i] += b.x;
+              v[4 * i + 1] += b.y;
+              v[4 * i + 2] += b.z;
+              v[4 * i + 3] += b.w;
+            }
+          }
+          if (epi.mode == EPI_RESIDUAL || epi.mode == EPI_DGELU) {
+            if (row_ok) {
+              const uint4* rp = reinterpret_cast<const uint4*>(epi.res + static_cast<size_t>(row) * epi.ld_res + ncol);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const uint4 q = __ldg(rp + i);
+                float f[8];
+                unpack_bf16x8(q, f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  if (epi.mode == EPI_RESIDUAL) v[8 * i + j] += f[j];
+                  else v[8 * i + j] *= gelu_grad(f[j]);
+                }
+              }
+            }
+          } else if (epi.mode == EPI_ROWTABLE) {
+            if (row_ok) {
+              const float4* tp = reinterpret_cast<const float4*>(
+                  epi.table + static_cast<size_t>(row % epi.table_rows) * args.N + ncol);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 b = __ldg(tp + i);
+                v[4 * i] += b.x;
+                v[4 * i + 1] += b.y;
+                v[4 * i + 2] += b.z;
+                v[4 * i + 3] += b.w;
+              }
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) packed[half * 16 + i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+          if (epi.mode == EPI_GELU_DUAL) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              packed2[half * 16 + i] = pack_bf16x2(gelu_exact(v[2 * i]), gelu_exact(v[2 * i + 1]));
+          }
+        }
+        // ---- registers -> swizzled smem -> TMA store (per-warp 32x64 tile, double buffered) ----
+        const int nstores = (epi.mode == EPI_GELU_DUAL) ? 2 : 1;
+        for (int o = 0; o < nstores; ++o) {
+          uint8_t* stage = my_out + (store_idx & 1) * STAGE_OUT_BYTES;
+          ++store_idx;
+          if (lane == 0) ptx::tma_store_wait_read<1>();  // the buffer used two stores ago is free
+          __syncwarp();
+          const uint32_t* src = (o == 0) ? packed : packed2;
+          const uint32_t row_base = ptx::smem_u32(stage) + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t addr = row_base + ((j ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(src[4 * j]), "r"(src[4 * j + 1]),
+                         "r"(src[4 * j + 2]), "r"(src[4 * j + 3])
+                         : "memory");
+          }
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_store_2d(o == 0 ? &tmOut : &tmOut2, stage, n0 + c * 64, m0 + warp * 32);
+            ptx::tma_store_commit();
+          }
+        }
+      }
+      // all tcgen05.ld of this accumulator have completed (wait::ld above) -> hand it back to the MMA warp
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty[buf]);
+    }
+    if (lane == 0) ptx::tma_store_wait_all<0>();
+    __syncwarp();
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// scalar reference kernel (tests only): same math, one thread per output element
+// ---------------------------------------------------------------------------------------------
+__global__ void gemm_simt_kernel(GemmKernelArgs args, const bf16* A, int lda, const bf16* B, int ldb, bf16* out,
+                                 int ldo, bf16* out2, int ldo2, const bf16* T, int ldt, const bf16* LB, int ldlb) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y;
+  if (n >= args.N || m >= args.M) return;
+  float acc = 0.f;
+  for (int k = 0; k < args.K; ++k)
+    acc += __bfloat162float(A[(size_t)m * lda + k]) * __bfloat162float(B[(size_t)n * ldb + k]);
+  if (args.lora_nkb > 0) {
+    const int tcol0 = args.lora_group_cols > 0 ? (n / args.lora_group_cols) * 64 : 0;
+    for (int j = 0; j < args.lora_nkb; ++j)
+      for (int k = 0; k < args.lora_ksteps * 16; ++k)
+        acc += __bfloat162float(T[(size_t)m * ldt + tcol0 + j * 64 + k]) *
+               __bfloat162float(LB[(size_t)n * ldlb + j * 64 + k]);
+  }
+  const GemmEpilogue& e = args.epi;
+  if (e.bias) acc += e.bias[n];
+  if (e.mode == EPI_RESIDUAL) acc += __bfloat162float(e.res[(size_t)m * e.ld_res + n]);
+  if (e.mode == EPI_DGELU) acc *= gelu_grad(__bfloat162float(e.res[(size_t)m * e.ld_res + n]));
+  if (e.mode == EPI_ROWTABLE) acc += e.table[(size_t)(m % e.table_rows) * args.N + n];
+  out[(size_t)m * ldo + n] = __float2bfloat16(acc);
+  if (e.mode == EPI_GELU_DUAL) out2[(size_t)m * ldo2 + n] = __float2bfloat16(gelu_exact(acc));
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || p == nullptr) {
+    set_error("cudaGetDriverEntryPoint(cuTensorMapEncodeTiled) failed: %s", cudaGetErrorString(e));
+    return nullptr;
+  }
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// 2D bf16 row-major tensor [rows, cols] with leading dimension ld (elements); box = [box_cols, box_rows]
+static int make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                        uint32_t box_cols, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return 1;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || ((ld * 2) & 15)) {
+    set_error("tensor map: base %p / ld %llu not 16-byte aligned", base, (unsigned long long)ld);
+    return 1;
+  }
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box=%ux%u", (int)r,
+              (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_cols, box_rows);
+    return 1;
+  }
+  return 0;
+}
+
+int gemm_plan_init(GemmPlan* p, int M, int N, int K, const bf16* A, int lda, const bf16* B, int ldb, bf16* out,
+                   int ldo, bf16* out2, int ldo2, const bf16* T, int ldt, const bf16* LB, int ldlb, int lora_nkb,
+                   int lora_ksteps, int lora_group_cols, GemmEpilogue epi) {
+  if (K % BK != 0 || N % 64 != 0 || M <= 0) {
+    set_error("gemm_plan_init: unsupported shape M=%d N=%d K=%d (K%%64, N%%64 must be 0)", M, N, K);
+    return 1;
+  }
+  p->M = M;
+  p->N = N;
+  p->K = K;
+  p->BN = (N % 256 == 0) ? 256 : (N % 128 == 0 ? 128 : 64);
+  p->lora_nkb = lora_nkb;
+  p->lora_ksteps = lora_ksteps;
+  p->lora_group_cols = lora_group_cols;
+  p->epi = epi;
+  if (lora_group_cols > 0 && lora_group_cols % p->BN != 0) {
+    set_error("gemm_plan_init: lora_group_cols %d not a multiple of BN %d", lora_group_cols, p->BN);
+    return 1;
+  }
+  if (make_tmap_2d(&p->tmA, A, M, K, lda, BK, BM)) return 1;
+  if (make_tmap_2d(&p->tmB, B, N, K, ldb, BK, p->BN)) return 1;
+  if (make_tmap_2d(&p->tmOut, out, M, N, ldo, 64, 32)) return 1;
+  if (out2) {
+    if (make_tmap_2d(&p->tmOut2, out2, M, N, ldo2, 64, 32)) return 1;
+  } else {
+    p->tmOut2 = p->tmOut;
+  }
+  if (lora_nkb > 0) {
+    const int tcols = lora_group_cols > 0 ? (N / lora_group_cols) * 64 : lora_nkb * 64;
+    if (make_tmap_2d(&p->tmLA, T, M, tcols, ldt, BK, BM)) return 1;
+    if (make_tmap_2d(&p->tmLB, LB, N, lora_nkb * 64, ldlb, BK, p->BN)) return 1;
+  } else {
+    p->tmLA = p->tmA;
+    p->tmLB = p->tmB;
+  }
+  return 0;
+}
+
+template <int BN>
+static int launch_bn(const GemmPlan* p, cudaStream_t stream, int num_sms) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VITATK_CUDA_OK(cudaFuncSetAttribute(gemm_tc05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = ((p->M + BM - 1) / BM) * (p->N / BN);
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  GemmKernelArgs a;
+  a.M = p->M;
+  a.N = p->N;
+  a.K = p->K;
+  a.lora_nkb = p->lora_nkb;
+  a.lora_ksteps = p->lora_ksteps;
+  a.lora_group_cols = p->lora_group_cols;
+  a.epi = p->epi;
+  gemm_tc05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(p->tmA, p->tmB, p->tmLA, p->tmLB, p->tmOut,
+                                                                      p->tmOut2, a);
+  VITATK_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int gemm_launch(const GemmPlan* p, cudaStream_t stream, int num_sms) {
+  switch (p->BN) {
+    case 256: return launch_bn<256>(p, stream, num_sms);
+    case 128: return launch_bn<128>(p, stream, num_sms);
+    case 64: return launch_bn<64>(p, stream, num_sms);
+  }
+  set_error("gemm_launch: bad BN %d", p->BN);
+  return 1;
+}
+
+int gemm_launch_simt(const GemmPlan* p, const bf16* A, int lda, const bf16* B, int ldb, bf16* out, int ldo,
+                     bf16* out2, int ldo2, const bf16* T, int ldt, const bf16* LB, int ldlb, cudaStream_t stream) {
+  GemmKernelArgs a;
+  a.M = p->M;
+  a.N = p->N;
+  a.K = p->K;
+  a.lora_nkb = p->lora_nkb;
+  a.lora_ksteps = p->lora_ksteps;
+  a.lora_group_cols = p->lora_group_cols;
+  a.epi = p->epi;
+  dim3 grid((p->N + 127) / 128, p->M);
+  gemm_simt_kernel<<<grid, 128, 0, stream>>>(a, A, lda, B, ldb, out, ldo, out2, ldo2, T, ldt, LB, ldlb);
+  VITATK_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace vitatk

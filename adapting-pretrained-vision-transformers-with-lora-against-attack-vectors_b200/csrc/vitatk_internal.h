@@ -1,0 +1,109 @@
+// Internal declarations shared by the kernels and the host-side engine (not part of the C ABI).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vitatk {
+
+typedef __nv_bfloat16 bf16;
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing (no C++ exceptions cross the ABI)
+// ---------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+const char* last_error();
+#define VITATK_CUDA_OK(expr)                                                              \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      ::vitatk::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return 1;                                                                           \
+    }                                                                                     \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// tcgen05 GEMM:  out[M,N] = epi( A[M,K] * B[N,K]^T  +  T[M,64*nkb] * LB[N,64*nkb]^T )
+// All operands bf16 row-major with the reduction dimension contiguous (K-major), fp32 accumulate
+// in TMEM.  The second product is the rank-r LoRA term: T = x*A_lora^T (precomputed, bf16) and
+// LB = s*B_lora zero-padded to 64 columns; it is issued as extra k-blocks of the same accumulator
+// so the adapter lands in the W*x tile before the epilogue reads it.
+// ---------------------------------------------------------------------------------------------
+enum EpiMode : int {
+  EPI_PLAIN = 0,      // out = acc (+ bias)
+  EPI_RESIDUAL = 1,   // out = acc + bias + res
+  EPI_GELU_DUAL = 2,  // out = u = acc + bias ; out2 = gelu(u)          (fc1 forward)
+  EPI_DGELU = 3,      // out = acc * gelu'(res)                          (fc2 backward -> dU)
+  EPI_ROWTABLE = 4    // out = acc + table[m % table_rows][n]            (patch embed: bias+pos / cls+pos)
+};
+
+struct GemmEpilogue {
+  int mode;
+  const float* bias;    // [N] fp32 or null
+  const bf16* res;      // [M, ld_res] residual (EPI_RESIDUAL) or saved pre-activation (EPI_DGELU)
+  int ld_res;
+  const float* table;   // [table_rows, N] fp32 (EPI_ROWTABLE)
+  int table_rows;
+};
+
+struct GemmPlan {
+  // shapes
+  int M, N, K;
+  int BN;               // 64, 128 or 256
+  int lora_nkb;         // extra 64-wide k-blocks (0 = no adapter)
+  int lora_ksteps;      // UMMA k-steps (16 each) issued per extra k-block = ceil(r/16)
+  int lora_group_cols;  // >0: T column offset = (n0 / lora_group_cols) * 64  (fused q|k|v forward)
+  GemmEpilogue epi;
+  // tensor maps (built once per plan)
+  CUtensorMap tmA, tmB, tmLA, tmLB, tmOut, tmOut2;
+};
+
+// Build the TMA descriptors of a plan. Pointers may be null when the feature is unused.
+int gemm_plan_init(GemmPlan* p, int M, int N, int K, const bf16* A, int lda, const bf16* B, int ldb,
+                   bf16* out, int ldo, bf16* out2, int ldo2, const bf16* T, int ldt, const bf16* LB, int ldlb,
+                   int lora_nkb, int lora_ksteps, int lora_group_cols, GemmEpilogue epi);
+int gemm_launch(const GemmPlan* p, cudaStream_t stream, int num_sms);
+// Scalar CUDA-core GEMM with identical semantics; used by tests to cross-check the tcgen05 kernel.
+int gemm_launch_simt(const GemmPlan* p, const bf16* A, int lda, const bf16* B, int ldb, bf16* out, int ldo,
+                     bf16* out2, int ldo2, const bf16* T, int ldt, const bf16* LB, int ldlb, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------------
+// attention (softmax(QK^T/sqrt(d))V per (image, head)), qkv packed [M, 3*D] token-major
+// ---------------------------------------------------------------------------------------------
+int attention_fwd(const bf16* qkv, bf16* out, int batch, int tokens, int heads, cudaStream_t stream);
+int attention_bwd(const bf16* qkv, const bf16* dout, bf16* dqkv, int batch, int tokens, int heads,
+                  cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm / head / PGD kernels (HBM-bound)
+// ---------------------------------------------------------------------------------------------
+int layernorm_fwd(const bf16* x, const float* gamma, const float* beta, bf16* y, float2* stats, int rows,
+                  int cols, float eps, cudaStream_t stream);
+// dx_out = dres + LN_backward(dy) ; x is the saved LN input, stats = (mean, rstd)
+int layernorm_bwd(const bf16* dy, const bf16* x, const float2* stats, const float* gamma, const bf16* dres,
+                  bf16* dx_out, int rows, int cols, cudaStream_t stream);
+// final LN on CLS rows + classifier + softmax-CE; writes logits, per-image loss, and (optionally) the
+// gradient wrt the final hidden state (non-CLS rows zero-filled).
+int head_fwd_bwd(const bf16* h, const float* gamma, const float* beta, const float* Wc, const float* bc,
+                 const int64_t* labels, float* logits, float* loss, bf16* dh, int batch, int tokens, int dim,
+                 int classes, float eps, float grad_scale, cudaStream_t stream);
+
+struct PixelNorm {
+  float mean[3];
+  float inv_std[3];
+};
+// adv <- clamp(x0 + noise, 0, 1) (noise may be null; or counter-based U(-eps,eps) when seed_enable),
+// and writes the normalised im2col rows of adv (bf16) for the patch-embed GEMM.
+int pgd_init(const float* x0, const float* noise, float* adv, bf16* cols, int batch, PixelNorm nrm, float eps,
+             int use_rng, uint64_t seed, uint64_t image_index0, cudaStream_t stream);
+// one fused PGD update: sign step + Linf projection + [0,1] clamp + renormalised im2col for the next step
+int pgd_update(const bf16* dcols, const float* x0, float* adv, bf16* cols, int batch, PixelNorm nrm,
+               float eps, float alpha, cudaStream_t stream);
+// materialise dL/dx (fp32 NCHW) from the im2col-layout gradient
+int grad_to_image(const bf16* dcols, float* grad, int batch, PixelNorm nrm, float scale, cudaStream_t stream);
+// counts[0] += #(argmax(logits)==label), counts[1] += batch
+int count_correct(const float* logits, const int64_t* labels, int batch, int classes, long long* counts,
+                  cudaStream_t stream);
+
+}  // namespace vitatk

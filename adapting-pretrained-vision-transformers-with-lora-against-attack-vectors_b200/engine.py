@@ -1,0 +1,325 @@
+"""Python host for the C-ABI engine: packs an HF ViT (+ LoRA adapters) into the engine's bf16 layout and
+drives forward / input-gradient / FGSM / PGD through ``libvitatk.so``.
+
+PyTorch is used for device memory, streams and one-off weight packing only; every per-step operation is a
+hand-written sm_100a kernel behind the C ABI.  There is no CPU or eager fallback.
+
+Weights in (reference formats):
+  * HF state-dict keys ``vit.embeddings.*``, ``vit.encoder.layer.{i}.*``, ``vit.layernorm.*``,
+    ``classifier.*`` (whitebox_attacks.py:92-94, Utils.py:84-90)
+  * LoRA adapters found on the module tree as objects carrying ``lora_A`` / ``lora_B`` (peft's
+    ``lora.Linear`` with ``scaling[adapter]``, train_loras.py:79-95; or the oracle's ``LoraLinear``), or
+    passed explicitly as ``{module_name: [(A, B, scale), ...]}``; several adapters on one Linear are
+    concatenated along the rank (un-merged equivalent of eval_compose.py:102-114).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+IMAGENET_MEAN = (0.485, 0.456, 0.406)  # Utils.py:92-93
+IMAGENET_STD = (0.229, 0.224, 0.225)
+LORA_PAD = 64
+TOKENS = 197
+
+# tensor ids (include/vitatk.h)
+T_PATCH_W, T_PATCH_WT, T_EMBED, T_LNF_G, T_LNF_B, T_HEAD_W, T_HEAD_B = 0, 1, 2, 3, 4, 5, 6
+T_LN1_G, T_LN1_B, T_QKV_W, T_QKV_WT, T_QKV_B, T_PROJ_W, T_PROJ_WT, T_PROJ_B = 16, 17, 18, 19, 20, 21, 22, 23
+T_LN2_G, T_LN2_B, T_FC1_W, T_FC1_WT, T_FC1_B, T_FC2_W, T_FC2_WT, T_FC2_B = 24, 25, 26, 27, 28, 29, 30, 31
+SITE_QKV, SITE_PROJ, SITE_FC1, SITE_FC2 = 0, 1, 2, 3
+
+Adapter = Tuple[torch.Tensor, torch.Tensor, float]  # (A [r,in], B [out,r], scale)
+
+
+def _strip(name: str) -> str:
+    """Remove wrapper prefixes (LogitsModel.model, peft base_model.model, DDP module) from a key."""
+    while not (name.startswith("vit.") or name.startswith("classifier.")):
+        for pre in ("base_model.", "model.", "module."):
+            if name.startswith(pre):
+                name = name[len(pre):]
+                break
+        else:
+            break
+    return name
+
+
+def collect_adapters(model: torch.nn.Module) -> Dict[str, List[Adapter]]:
+    """Find LoRA-wrapped Linears on the module tree -> {linear name: [(A, B, scale)]}."""
+    found: Dict[str, List[Adapter]] = {}
+    for name, mod in model.named_modules():
+        if not (hasattr(mod, "lora_A") and hasattr(mod, "lora_B")):
+            continue
+        key = _strip(name)
+        la, lb = mod.lora_A, mod.lora_B
+        if isinstance(la, (torch.nn.ModuleDict, dict)):  # peft: one entry per adapter name
+            scaling = getattr(mod, "scaling", {})
+            for ad in la.keys():
+                found.setdefault(key, []).append(
+                    (la[ad].weight.detach(), lb[ad].weight.detach(), float(scaling.get(ad, 1.0))))
+        else:  # oracle.LoraLinear-style: plain parameters + .scale
+            found.setdefault(key, []).append((la.detach(), lb.detach(), float(getattr(mod, "scale", 1.0))))
+    return found
+
+
+def normalise_state_dict(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """Drop wrapper prefixes / LoRA entries so keys match the plain HF ViT names.  peft's SEQ_CLS wrapper
+    keeps two classifiers (train_loras.py:84): the trained ``modules_to_save`` copy wins over the original."""
+    import re
+
+    out: Dict[str, torch.Tensor] = {}
+    saved: Dict[str, torch.Tensor] = {}
+    for k, v in sd.items():
+        k = _strip(k)
+        if "lora_" in k:
+            continue
+        k = k.replace(".base_layer.", ".").replace(".base.", ".")
+        m = re.match(r"(.*)\.modules_to_save\.[^.]+\.(.*)", k)
+        if m:
+            saved[m.group(1) + "." + m.group(2)] = v
+            continue
+        k = k.replace(".original_module.", ".")
+        out[k] = v
+    out.update(saved)
+    return out
+
+
+class Engine:
+    """One engine per (model, device).  Mirrors what ``model.to(device).eval()`` is to the reference loop."""
+
+    def __init__(self, model: Optional[torch.nn.Module] = None, state_dict: Optional[Dict[str, torch.Tensor]] = None,
+                 adapters: Optional[Dict[str, Sequence[Adapter]]] = None, max_batch: int = 256,
+                 mean: Sequence[float] = IMAGENET_MEAN, std: Sequence[float] = IMAGENET_STD,
+                 device: Optional[torch.device] = None, ln_eps: Optional[float] = None):
+        if not torch.cuda.is_available():
+            raise _lib.VitatkError("vitatk needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        if model is not None:
+            sd = model.state_dict()
+            found = collect_adapters(model)
+            if adapters:
+                for k, v in adapters.items():
+                    found.setdefault(k, []).extend(v)
+            adapters = found
+            cfg = getattr(model, "config", None)
+            if ln_eps is None and cfg is not None:
+                ln_eps = float(getattr(cfg, "layer_norm_eps", 1e-12))
+        elif state_dict is not None:
+            sd = state_dict
+        else:
+            raise ValueError("Engine needs a model or a state_dict")
+        sd = normalise_state_dict(sd)
+        self.adapters = {k: list(v) for k, v in (adapters or {}).items()}
+        self.ln_eps = 1e-12 if ln_eps is None else ln_eps
+        self.dim = sd["vit.embeddings.cls_token"].shape[-1]
+        self.layers = 1 + max(int(k.split(".")[3]) for k in sd if k.startswith("vit.encoder.layer."))
+        self.mlp_dim = sd["vit.encoder.layer.0.intermediate.dense.weight"].shape[0]
+        self.num_classes = sd["classifier.weight"].shape[0]
+        self.heads = self.dim // 64
+        self.max_batch = int(max_batch)
+        self.mean, self.std = tuple(float(m) for m in mean), tuple(float(s) for s in std)
+        self._keep: List[torch.Tensor] = []  # device buffers the engine borrows
+        self._h = C.c_void_p()
+        cfg = _lib.Config(224, 16, self.dim, self.heads, self.layers, self.mlp_dim, self.num_classes, self.max_batch,
+                          self.ln_eps, (C.c_float * 3)(*self.mean), (C.c_float * 3)(*self.std))
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.vitatk_create(C.byref(cfg), C.byref(self._h)), "vitatk_create")
+            self._upload(sd)
+            _lib.check(self.lib.vitatk_finalize(self._h), "vitatk_finalize")
+
+    # ------------------------------------------------------------------ weight packing
+    def _dev(self, t: torch.Tensor, dtype) -> torch.Tensor:
+        t = t.detach().to(device=self.device, dtype=dtype).contiguous()
+        self._keep.append(t)
+        return t
+
+    def _set(self, tid: int, layer: int, t: torch.Tensor, dtype) -> None:
+        t = self._dev(t, dtype)
+        _lib.check(self.lib.vitatk_set_tensor(self._h, tid, layer, t.data_ptr(), t.numel() * t.element_size()),
+                   f"vitatk_set_tensor({tid}, layer {layer})")
+
+    def _upload(self, sd: Dict[str, torch.Tensor]) -> None:
+        bf, f32 = torch.bfloat16, torch.float32
+        D = self.dim
+        g = lambda k: sd[k].detach().to(self.device, torch.float32)  # noqa: E731
+        pw = g("vit.embeddings.patch_embeddings.projection.weight").reshape(D, -1)
+        if pw.shape[1] != 768:
+            raise _lib.VitatkError("patch embedding must be 3x16x16")
+        self._set(T_PATCH_W, 0, pw, bf)
+        self._set(T_PATCH_WT, 0, pw.t(), bf)
+        pos = g("vit.embeddings.position_embeddings").reshape(-1, D)
+        if pos.shape[0] != TOKENS:
+            raise _lib.VitatkError(f"expected {TOKENS} position embeddings, got {pos.shape[0]}")
+        table = pos.clone()
+        table[0] += g("vit.embeddings.cls_token").reshape(D)
+        table[1:] += g("vit.embeddings.patch_embeddings.projection.bias")
+        self._set(T_EMBED, 0, table, f32)
+        self._set(T_LNF_G, 0, g("vit.layernorm.weight"), f32)
+        self._set(T_LNF_B, 0, g("vit.layernorm.bias"), f32)
+        self._set(T_HEAD_W, 0, g("classifier.weight"), f32)
+        self._set(T_HEAD_B, 0, g("classifier.bias"), f32)
+        for l in range(self.layers):
+            p = f"vit.encoder.layer.{l}."
+            self._set(T_LN1_G, l, g(p + "layernorm_before.weight"), f32)
+            self._set(T_LN1_B, l, g(p + "layernorm_before.bias"), f32)
+            self._set(T_LN2_G, l, g(p + "layernorm_after.weight"), f32)
+            self._set(T_LN2_B, l, g(p + "layernorm_after.bias"), f32)
+            a = p + "attention.attention."
+            wqkv = torch.cat([g(a + "query.weight"), g(a + "key.weight"), g(a + "value.weight")], 0)
+            bqkv = torch.cat([g(a + "query.bias"), g(a + "key.bias"), g(a + "value.bias")], 0)
+            self._set(T_QKV_W, l, wqkv, bf)
+            self._set(T_QKV_WT, l, wqkv.t(), bf)
+            self._set(T_QKV_B, l, bqkv, f32)
+            for (w_id, wt_id, b_id, key) in ((T_PROJ_W, T_PROJ_WT, T_PROJ_B, "attention.output.dense"),
+                                             (T_FC1_W, T_FC1_WT, T_FC1_B, "intermediate.dense"),
+                                             (T_FC2_W, T_FC2_WT, T_FC2_B, "output.dense")):
+                w = g(p + key + ".weight")
+                self._set(w_id, l, w, bf)
+                self._set(wt_id, l, w.t(), bf)
+                self._set(b_id, l, g(p + key + ".bias"), f32)
+            self._upload_lora(l, p)
+
+    def _site_adapters(self, names: Sequence[str]) -> List[List[Adapter]]:
+        return [list(self.adapters.get(n, [])) for n in names]
+
+    def _upload_lora(self, l: int, p: str) -> None:
+        a = p + "attention.attention."
+        sites = (
+            (SITE_QKV, [a + "query", a + "key", a + "value"], self.dim, self.dim),
+            (SITE_PROJ, [p + "attention.output.dense"], self.dim, self.dim),
+            (SITE_FC1, [p + "intermediate.dense"], self.dim, self.mlp_dim),
+            (SITE_FC2, [p + "output.dense"], self.mlp_dim, self.dim),
+        )
+        for site, names, n_in, n_out in sites:
+            groups = self._site_adapters(names)
+            if not any(groups):
+                continue
+            G = len(names)
+            la_fwd = torch.zeros(LORA_PAD * G, n_in, device=self.device)
+            lb_fwd = torch.zeros(n_out * G, LORA_PAD, device=self.device)
+            lb_bwd = torch.zeros(LORA_PAD * G, n_out * G, device=self.device)
+            la_bwd = torch.zeros(n_in, LORA_PAD * G, device=self.device)
+            rmax = 0
+            for gi, ads in enumerate(groups):
+                r0 = 0
+                for (A, B, s) in ads:
+                    A = A.to(self.device, torch.float32)
+                    B = B.to(self.device, torch.float32)
+                    r = A.shape[0]
+                    if A.shape != (r, n_in) or B.shape != (n_out, r):
+                        raise _lib.VitatkError(f"adapter shape mismatch on {names[gi]}: A {tuple(A.shape)} B {tuple(B.shape)}")
+                    if r0 + r > LORA_PAD:
+                        raise _lib.VitatkError(f"total LoRA rank on {names[gi]} exceeds {LORA_PAD}")
+                    la_fwd[LORA_PAD * gi + r0: LORA_PAD * gi + r0 + r] = A
+                    lb_fwd[n_out * gi: n_out * (gi + 1), r0: r0 + r] = s * B
+                    lb_bwd[LORA_PAD * gi + r0: LORA_PAD * gi + r0 + r, n_out * gi: n_out * (gi + 1)] = B.t()
+                    la_bwd[:, LORA_PAD * gi + r0: LORA_PAD * gi + r0 + r] = s * A.t()
+                    r0 += r
+                rmax = max(rmax, r0)
+            bufs = [self._dev(t, torch.bfloat16) for t in (la_fwd, lb_fwd, lb_bwd, la_bwd)]
+            _lib.check(self.lib.vitatk_set_lora(self._h, l, site, rmax, *[b.data_ptr() for b in bufs]),
+                       f"vitatk_set_lora(layer {l}, site {site})")
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _img(self, x: torch.Tensor) -> torch.Tensor:
+        if x.dim() != 4 or tuple(x.shape[1:]) != (3, 224, 224):
+            raise ValueError(f"expected images [B,3,224,224], got {tuple(x.shape)}")
+        if x.shape[0] > self.max_batch:
+            raise ValueError(f"batch {x.shape[0]} > max_batch {self.max_batch}")
+        if x.device != self.device or x.dtype != torch.float32 or not x.is_contiguous():
+            x = x.detach().to(self.device, torch.float32).contiguous()
+        return x
+
+    def _lab(self, y: torch.Tensor, b: int) -> torch.Tensor:
+        if y.shape != (b,):
+            raise ValueError(f"expected labels [{b}], got {tuple(y.shape)}")
+        if y.device != self.device or y.dtype != torch.int64 or not y.is_contiguous():
+            y = y.detach().to(self.device, torch.int64).contiguous()
+        return y
+
+    def set_normalization(self, mean: Sequence[float], std: Sequence[float]) -> None:
+        self.mean, self.std = tuple(float(m) for m in mean), tuple(float(s) for s in std)
+        _lib.check(self.lib.vitatk_set_normalization(self._h, (C.c_float * 3)(*self.mean), (C.c_float * 3)(*self.std)),
+                   "vitatk_set_normalization")
+
+    @property
+    def workspace_bytes(self) -> int:
+        return int(self.lib.vitatk_workspace_bytes(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.vitatk_launch_count(self._h))
+
+    # ------------------------------------------------------------------ hot path
+    def logits(self, images: torch.Tensor) -> torch.Tensor:
+        x = self._img(images)
+        out = torch.empty(x.shape[0], self.num_classes, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.vitatk_forward(self._h, x.data_ptr(), x.shape[0], out.data_ptr(), self._stream()),
+                       "vitatk_forward")
+        return out
+
+    def input_grad(self, images: torch.Tensor, labels: torch.Tensor):
+        """(grad [B,3,224,224] of mean CE, logits [B,C], per-image loss [B])."""
+        x = self._img(images)
+        y = self._lab(labels, x.shape[0])
+        grad = torch.empty_like(x)
+        logits = torch.empty(x.shape[0], self.num_classes, device=self.device, dtype=torch.float32)
+        loss = torch.empty(x.shape[0], device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.vitatk_input_grad(self._h, x.data_ptr(), y.data_ptr(), x.shape[0], grad.data_ptr(),
+                                                  logits.data_ptr(), loss.data_ptr(), self._stream()),
+                       "vitatk_input_grad")
+        return grad, logits, loss
+
+    def attack(self, images: torch.Tensor, labels: torch.Tensor, eps: float, alpha: float, steps: int,
+               start: str = "none", noise: Optional[torch.Tensor] = None, seed: int = 0, image_index0: int = 0,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        x = self._img(images)
+        y = self._lab(labels, x.shape[0])
+        mode = {"none": 0, "rng": 1, "noise": 2}[start]
+        nptr = None
+        if mode == 2:
+            if noise is None:
+                raise ValueError("start='noise' needs a noise tensor")
+            noise = self._img(noise)
+            nptr = noise.data_ptr()
+        adv = out if out is not None else torch.empty_like(x)
+        if adv.data_ptr() == x.data_ptr():
+            raise ValueError("out must not alias images (the reference does not mutate its input)")
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.vitatk_attack(self._h, x.data_ptr(), y.data_ptr(), x.shape[0], float(eps), float(alpha),
+                                              int(steps), mode, nptr, int(seed), int(image_index0), adv.data_ptr(),
+                                              self._stream()), "vitatk_attack")
+        return adv
+
+    def count_correct(self, images: torch.Tensor, labels: torch.Tensor, counts: Optional[torch.Tensor] = None):
+        """counts (int64[2] on device) += (#top-1 correct, #images) — train_loras.py:56-76."""
+        x = self._img(images)
+        y = self._lab(labels, x.shape[0])
+        if counts is None:
+            counts = torch.zeros(2, device=self.device, dtype=torch.int64)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.vitatk_count_correct(self._h, x.data_ptr(), y.data_ptr(), x.shape[0], counts.data_ptr(),
+                                                     self._stream()), "vitatk_count_correct")
+        return counts
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            torch.cuda.synchronize(self.device)
+            self.lib.vitatk_destroy(self._h)
+            self._h = C.c_void_p()
+            self._keep.clear()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

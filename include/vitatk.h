@@ -1,0 +1,151 @@
+/* vitatk — C ABI of the B200-native white-box attack engine (libvitatk.so).
+ *
+ * The reference has no FFI of its own: its boundary is the Python call surface of
+ * whitebox_attacks.py.  Each entry point below names the reference interface it replaces
+ * (file:line in rneddojr/Adapting-Pretrained-Vision-Transformers-with-LoRA-against-Attack-Vectors;
+ * "HF:" = transformers/models/vit/modeling_vit.py).  INTEGRATION.md shows the ctypes binding a
+ * maintainer would add to the reference scripts.
+ *
+ * Conventions: plain pointers and sizes only (no torch types).  Every pointer named *_dev is a CUDA
+ * device pointer owned by the caller; the engine owns only its workspace.  Every call enqueues on the
+ * given cudaStream_t (passed as void*) and returns 0 on success, non-zero on failure with a message in
+ * vitatk_last_error().  No hidden host synchronisation in the step loop.  One engine per device; an
+ * engine is not thread-safe (the reference loop is single-threaded, whitebox_attacks.py:157-173).
+ */
+#ifndef VITATK_H_
+#define VITATK_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vitatk_engine vitatk_engine;
+
+/* Model geometry = Utils.py:84-90 create_vit_model -> HF ViTConfig defaults (ViT-B/16). */
+typedef struct vitatk_config {
+  int image_size;   /* 224 */
+  int patch_size;   /* 16  */
+  int dim;          /* 768 */
+  int heads;        /* 12  */
+  int layers;       /* 12  */
+  int mlp_dim;      /* 3072 */
+  int num_classes;  /* e.g. 21 */
+  int max_batch;    /* largest batch any later call will pass */
+  float ln_eps;     /* 1e-12 (HF:layer_norm_eps) */
+  float mean[3];    /* Utils.py:92-93 get_normalization */
+  float std[3];
+} vitatk_config;
+
+/* Tensor ids for vitatk_set_tensor.  bf16 matrices are row-major [out, in] ("W") or its transpose
+ * [in, out] ("WT", used by the input-gradient GEMMs); fp32 for vectors/tables. */
+enum vitatk_tensor_id {
+  /* global (layer argument ignored) */
+  VITATK_PATCH_W = 0,    /* bf16 [768, 768]  conv weight flattened [out, c*256+ky*16+kx]   (HF:151) */
+  VITATK_PATCH_WT = 1,   /* bf16 [768, 768]  its transpose */
+  VITATK_EMBED_TABLE = 2,/* fp32 [197, 768]  row0 = cls+pos[0]; row t = conv bias + pos[t]  (HF:117-124) */
+  VITATK_LNF_G = 3,      /* fp32 [768] final LayerNorm (HF:455) */
+  VITATK_LNF_B = 4,
+  VITATK_HEAD_W = 5,     /* fp32 [C, 768] classifier (HF:613) */
+  VITATK_HEAD_B = 6,     /* fp32 [C] */
+  /* per layer */
+  VITATK_LN1_G = 16, VITATK_LN1_B = 17,      /* fp32 [768]  layernorm_before (HF:325) */
+  VITATK_QKV_W = 18,     /* bf16 [2304, 768]  cat(query, key, value).weight (HF:216-218) */
+  VITATK_QKV_WT = 19,    /* bf16 [768, 2304] */
+  VITATK_QKV_B = 20,     /* fp32 [2304] */
+  VITATK_PROJ_W = 21,    /* bf16 [768, 768]  attention.output.dense (HF:262) */
+  VITATK_PROJ_WT = 22,
+  VITATK_PROJ_B = 23,
+  VITATK_LN2_G = 24, VITATK_LN2_B = 25,      /* layernorm_after (HF:326) */
+  VITATK_FC1_W = 26,     /* bf16 [3072, 768]  intermediate.dense (HF:290) */
+  VITATK_FC1_WT = 27,    /* bf16 [768, 3072] */
+  VITATK_FC1_B = 28,
+  VITATK_FC2_W = 29,     /* bf16 [768, 3072]  output.dense (HF:305) */
+  VITATK_FC2_WT = 30,    /* bf16 [3072, 768] */
+  VITATK_FC2_B = 31
+};
+
+/* Adapter sites for vitatk_set_lora (train_loras.py:79-95 target_modules; q,k,v share one fused site). */
+enum vitatk_lora_site { VITATK_SITE_QKV = 0, VITATK_SITE_PROJ = 1, VITATK_SITE_FC1 = 2, VITATK_SITE_FC2 = 3 };
+
+const char* vitatk_last_error(void);
+int vitatk_version(void);
+
+/* replaces: create_vit_model(...).to(device) (whitebox_attacks.py:92) — allocates nothing big yet */
+int vitatk_create(const vitatk_config* cfg, vitatk_engine** out);
+int vitatk_destroy(vitatk_engine* e);
+
+/* replaces: model.load_state_dict(torch.load(path)) (whitebox_attacks.py:94).  The pointer is borrowed:
+ * the caller keeps the buffer alive for the life of the engine.  nbytes is checked against the shape. */
+int vitatk_set_tensor(vitatk_engine* e, int tensor_id, int layer, const void* dev_ptr, long long nbytes);
+
+/* replaces: PeftModel.from_pretrained / get_peft_model (train_loras.py:83-92,419).  rank == 0 removes
+ * the adapter.  G = 3 for the fused QKV site (q|k|v groups), 1 otherwise; in/out are the Linear's dims.
+ *   la_fwd  bf16 [64*G, in]    rows 64g..64g+r = A_g, rest zero           (T = x A^T)
+ *   lb_fwd  bf16 [out, 64]     cols 0..r = (alpha/r) * B (row n of its group), rest zero
+ *   lb_bwd  bf16 [64*G, out]   rows 64g..64g+r = B_g^T on group g's columns, zero elsewhere
+ *   la_bwd  bf16 [in, 64*G]    cols 64g..64g+r = (alpha/r) * A_g^T, rest zero */
+int vitatk_set_lora(vitatk_engine* e, int layer, int site, int rank, const void* la_fwd_dev, const void* lb_fwd_dev,
+                    const void* lb_bwd_dev, const void* la_bwd_dev);
+
+/* replaces: attack.set_normalization_used(mean, std) (whitebox_attacks.py:169) and the in-graph
+ * (x - mean) / std of whitebox_attacks.py:26 / patch_attack.py:23-25.  Host pointers to 3 floats each. */
+int vitatk_set_normalization(vitatk_engine* e, const float* mean3, const float* std3);
+
+/* allocates the activation workspace for max_batch and validates that every tensor is present */
+int vitatk_finalize(vitatk_engine* e);
+long long vitatk_workspace_bytes(const vitatk_engine* e);
+
+/* replaces: logits = get_model_output(model((x - mean) / std)) (whitebox_attacks.py:26-28).
+ * images_dev fp32 [B,3,224,224] in [0,1]; logits_dev fp32 [B, C]. */
+int vitatk_forward(vitatk_engine* e, const float* images_dev, int batch, float* logits_dev, void* stream);
+
+/* replaces: F.cross_entropy(logits, labels); loss.backward(); perturbed.grad (whitebox_attacks.py:29-32).
+ * grad_dev fp32 [B,3,224,224] = d(mean CE)/d(images); logits_dev / loss_dev (per-image CE) optional. */
+int vitatk_input_grad(vitatk_engine* e, const float* images_dev, const int64_t* labels_dev, int batch,
+                      float* grad_dev, float* logits_dev, float* loss_dev, void* stream);
+
+/* replaces: batched_fgsm_attack (whitebox_attacks.py:22-38) when steps == 1, alpha == eps, start == NONE,
+ * and torchattacks.PGD.__call__ (whitebox_attacks.py:112-113,168-170) otherwise.
+ *   start: 0 = none, 1 = counter-based U(-eps,eps) from (seed, image_index0 + b), 2 = caller noise_dev
+ *   adv_dev fp32 [B,3,224,224] receives the adversarial images (must not alias images_dev).
+ * Every iteration is: im2col'd normalised input -> ViT forward -> CE -> input gradient -> one fused
+ * sign-step / projection / clamp / renormalise kernel. */
+#define VITATK_START_NONE 0
+#define VITATK_START_RNG 1
+#define VITATK_START_NOISE 2
+int vitatk_attack(vitatk_engine* e, const float* images_dev, const int64_t* labels_dev, int batch, float eps,
+                  float alpha, int steps, int start, const float* noise_dev, uint64_t seed, uint64_t image_index0,
+                  float* adv_dev, void* stream);
+
+/* replaces: test_model top-1 counting (train_loras.py:56-76). counts_dev int64[2] += {correct, total}. */
+int vitatk_count_correct(vitatk_engine* e, const float* images_dev, const int64_t* labels_dev, int batch,
+                         long long* counts_dev, void* stream);
+
+/* number of kernels the engine enqueued since creation (bench.py reports the per-step delta) */
+long long vitatk_launch_count(const vitatk_engine* e);
+
+/* ---- kernel-level entry points (used by tests/ and bench.py's roofline leg) ---- */
+int vitatk_k_gemm(int M, int N, int K, const void* A_dev, int lda, const void* B_dev, int ldb, void* out_dev,
+                  int ldo, void* out2_dev, int ldo2, const void* T_dev, int ldt, const void* LB_dev, int ldlb,
+                  int lora_nkb, int lora_ksteps, int lora_group_cols, int epi_mode, const float* bias_dev,
+                  const void* res_dev, int ld_res, const float* table_dev, int table_rows, int use_simt,
+                  void* stream);
+int vitatk_k_attention_fwd(const void* qkv_dev, void* out_dev, int batch, int tokens, int heads, void* stream);
+int vitatk_k_attention_bwd(const void* qkv_dev, const void* dout_dev, void* dqkv_dev, int batch, int tokens,
+                           int heads, void* stream);
+int vitatk_k_layernorm_fwd(const void* x_dev, const float* gamma_dev, const float* beta_dev, void* y_dev,
+                           float* stats_dev, int rows, int cols, float eps, void* stream);
+int vitatk_k_layernorm_bwd(const void* dy_dev, const void* x_dev, const float* stats_dev, const float* gamma_dev,
+                           const void* dres_dev, void* dx_dev, int rows, int cols, void* stream);
+int vitatk_k_pgd_update(const void* dcols_dev, const float* x0_dev, float* adv_dev, void* cols_dev, int batch,
+                        const float* mean3, const float* std3, float eps, float alpha, void* stream);
+int vitatk_k_pgd_init(const float* x0_dev, const float* noise_dev, float* adv_dev, void* cols_dev, int batch,
+                      const float* mean3, const float* std3, float eps, int use_rng, uint64_t seed,
+                      uint64_t image_index0, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VITATK_H_ */

@@ -1,0 +1,125 @@
+"""CPU: host-side logic, C-ABI surface, and the world_size-2 count exchange over gloo."""
+import os
+import re
+import socket
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from vitatk import _lib
+
+    header = open(os.path.join(ROOT, "include", "vitatk.h")).read()
+    declared = set(re.findall(r"\b(vitatk_[a-z_0-9]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.vitatk_version() == 1
+
+
+def test_no_gpu_fails_loudly():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from vitatk import _lib
+    from vitatk.engine import Engine
+
+    with pytest.raises(_lib.VitatkError):
+        Engine(state_dict={})
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "adapting-pretrained-vision-transformers-with-lora-against-attack-vectors_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_shard_range_partitions():
+    from vitatk.dist import shard_range
+
+    for n in (0, 1, 7, 256, 2049):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for (a, b), (c, d) in zip(spans, spans[1:]):
+                assert b == c
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(4, 2, 2)
+
+
+def test_state_dict_normalisation_and_adapter_discovery():
+    from oracle import fixtures as fx
+    from vitatk.attacks import LogitsModel, NormalizedModel, _unwrap
+    from vitatk.engine import collect_adapters, normalise_state_dict
+
+    m = fx.make_model(lora=True)
+    wrapped = NormalizedModel(LogitsModel(m), [0.5, 0.5, 0.5], [0.25, 0.25, 0.25])
+    core, mean, std = _unwrap(wrapped)
+    assert core is m and mean == [0.5] * 3 and std == [0.25] * 3
+    sd = normalise_state_dict(wrapped.state_dict())
+    assert "vit.encoder.layer.0.attention.attention.query.weight" in sd
+    assert "vit.encoder.layer.11.output.dense.bias" in sd
+    assert not any("lora" in k for k in sd)
+    ad = collect_adapters(wrapped)
+    assert len(ad) == 12 * 6
+    A, B, s = ad["vit.encoder.layer.3.intermediate.dense"][0]
+    assert A.shape == (8, 768) and B.shape == (3072, 8) and s == 2.0
+    # peft-style key layout (base_layer / modules_to_save)
+    fake = {"base_model.model.vit.encoder.layer.0.attention.attention.query.base_layer.weight": torch.zeros(1),
+            "base_model.model.vit.encoder.layer.0.attention.attention.query.lora_A.default.weight": torch.zeros(1),
+            "base_model.model.classifier.original_module.weight": torch.zeros(1),
+            "base_model.model.classifier.modules_to_save.default.weight": torch.ones(1)}
+    out = normalise_state_dict(fake)
+    assert set(out) == {"vit.encoder.layer.0.attention.attention.query.weight", "classifier.weight"}
+    assert float(out["classifier.weight"]) == 1.0  # trained copy wins (train_loras.py:84 SEQ_CLS)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    sys_path = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    import sys
+
+    sys.path.insert(0, sys_path)
+    from vitatk.dist import allreduce_counts, shard_range
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    lo, hi = shard_range(101, rank, world)
+    labels = torch.arange(101)[lo:hi]
+    counts = torch.tensor([int((labels % 2 == 0).sum()), int((labels % 3 == 0).sum()), hi - lo], dtype=torch.int64)
+    allreduce_counts(counts)
+    q.put((rank, counts.tolist()))
+    dist.destroy_process_group()
+
+
+def test_count_allreduce_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=120) for _ in ps]
+    for p in ps:
+        p.join(60)
+        assert p.exitcode == 0
+    want = [51, 34, 101]
+    for _, c in res:
+        assert c == want

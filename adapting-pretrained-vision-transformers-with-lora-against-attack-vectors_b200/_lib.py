@@ -76,7 +76,7 @@ EXPORTS = [
     "vitatk_set_normalization", "vitatk_finalize", "vitatk_workspace_bytes", "vitatk_forward", "vitatk_input_grad",
     "vitatk_attack", "vitatk_count_correct", "vitatk_launch_count", "vitatk_k_gemm", "vitatk_k_attention_fwd",
     "vitatk_k_attention_bwd", "vitatk_k_layernorm_fwd", "vitatk_k_layernorm_bwd", "vitatk_k_pgd_update",
-    "vitatk_k_pgd_init",
+    "vitatk_k_pgd_init", "vitatk_profile_begin", "vitatk_profile_end",
 ]
 
 
@@ -118,6 +118,8 @@ def load() -> C.CDLL:
     lib.vitatk_input_grad.argtypes = [vp, vp, vp, i, vp, vp, vp, vp]
     lib.vitatk_attack.argtypes = [vp, vp, vp, i, f, f, i, i, vp, u64, u64, vp, vp]
     lib.vitatk_count_correct.argtypes = [vp, vp, vp, i, vp, vp]
+    lib.vitatk_profile_begin.argtypes = [vp]
+    lib.vitatk_profile_end.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(ll)]
     lib.vitatk_k_gemm.argtypes = [i, i, i, vp, i, vp, i, vp, i, vp, i, vp, i, vp, i, i, i, i, i, vp, vp, i, vp, i, i, vp]
     lib.vitatk_k_attention_fwd.argtypes = [vp, vp, i, i, i, vp]
     lib.vitatk_k_attention_bwd.argtypes = [vp, vp, vp, i, i, i, vp]

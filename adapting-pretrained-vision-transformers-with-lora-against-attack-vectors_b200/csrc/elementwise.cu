@@ -289,6 +289,17 @@ __device__ __forceinline__ float u01_hash(uint64_t seed, uint64_t ctr) {
   return static_cast<float>(z >> 40) * (1.0f / 16777216.0f);
 }
 
+
+// Strict L-inf ball: the reference arithmetic adv = clamp(x0 + delta, 0, 1) can leave fl32(adv - x0) a few
+// ulps of eps outside [-eps, eps] (x0 + delta is rounded at the ulp of adv, ~6e-8, eps's ulp is ~2e-9).
+// BASELINE's gate is ||adv - x0||_inf <= eps exactly, so move adv one ulp towards x0 when that happens.
+__device__ __forceinline__ float enforce_ball(float adv, float x0, float eps) {
+  const float d = adv - x0;
+  if (d > eps) adv = __uint_as_float(__float_as_uint(adv) - 1u);        // adv > x0 >= 0: one ulp down
+  else if (d < -eps) adv = __uint_as_float(__float_as_uint(adv) + 1u);  // 0 <= adv < x0: one ulp up
+  return adv;
+}
+
 __global__ void __launch_bounds__(256) pgd_init_kernel(const float* __restrict__ x0, const float* __restrict__ noise,
                                                        float* __restrict__ adv, bf16* __restrict__ cols, int batch,
                                                        PixelNorm nrm, float eps, int use_rng, uint64_t seed,
@@ -307,13 +318,13 @@ __global__ void __launch_bounds__(256) pgd_init_kernel(const float* __restrict__
     const float4 n1 = __ldg(reinterpret_cast<const float4*>(noise + p + 4));
     const float nn[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = fminf(fmaxf(v[j] + nn[j], 0.f), 1.f);
+    for (int j = 0; j < 8; ++j) v[j] = enforce_ball(fminf(fmaxf(v[j] + nn[j], 0.f), 1.f), v[j], eps);
   } else if (use_rng) {
     const uint64_t e0 = (image_index0 + b) * (3ull * IMG * IMG) + (static_cast<uint64_t>(c) * IMG + y) * IMG + x8 * 8;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float n = (2.f * u01_hash(seed, e0 + j) - 1.f) * eps;
-      v[j] = fminf(fmaxf(v[j] + n, 0.f), 1.f);
+      v[j] = enforce_ball(fminf(fmaxf(v[j] + n, 0.f), 1.f), v[j], eps);
     }
   }
   *reinterpret_cast<float4*>(adv + p) = make_float4(v[0], v[1], v[2], v[3]);
@@ -356,7 +367,7 @@ __global__ void __launch_bounds__(256) pgd_update_kernel(const bf16* __restrict_
     const float sg = (g[j] > 0.f) ? 1.f : ((g[j] < 0.f) ? -1.f : 0.f);
     const float stepped = v[j] + alpha * sg;
     const float delta = fminf(fmaxf(stepped - xo[j], -eps), eps);
-    v[j] = fminf(fmaxf(xo[j] + delta, 0.f), 1.f);
+    v[j] = enforce_ball(fminf(fmaxf(xo[j] + delta, 0.f), 1.f), xo[j], eps);
     o[j] = (v[j] - nrm.mean[c]) * nrm.inv_std[c];
   }
   *reinterpret_cast<float4*>(adv + p) = make_float4(v[0], v[1], v[2], v[3]);

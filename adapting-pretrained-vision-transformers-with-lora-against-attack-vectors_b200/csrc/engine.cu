@@ -85,6 +85,11 @@ struct vitatk_engine {
   std::map<int, PlanSet*> plans;
   long long launches = 0;
   PixelNorm nrm;
+  // optional per-launch CUDA-event timing (bench.py's roofline leg; off in the timed region)
+  bool prof = false;
+  struct ProfRec { int cat; double flops; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof_recs;
+  std::vector<cudaEvent_t> prof_pool;
 };
 
 namespace vitatk {
@@ -202,31 +207,61 @@ static int build_plans(vitatk_engine* e, int batch, PlanSet** out) {
   return 0;
 }
 
-#define RUN(expr)        \
-  do {                   \
-    if (expr) return 1;  \
-    ++e->launches;       \
+enum ProfCat { CAT_GEMM = 0, CAT_GEMM_LORA_T = 1, CAT_ATTN_FWD = 2, CAT_ATTN_BWD = 3, CAT_LN = 4, CAT_HEAD = 5,
+               CAT_PIXEL = 6, CAT_COUNT = 8 };
+
+static cudaEvent_t prof_event(vitatk_engine* e) {
+  cudaEvent_t ev;
+  if (!e->prof_pool.empty()) {
+    ev = e->prof_pool.back();
+    e->prof_pool.pop_back();
+    return ev;
+  }
+  cudaEventCreate(&ev);
+  return ev;
+}
+static double plan_flops(const GemmPlan* p) {
+  return 2.0 * p->M * p->N * (static_cast<double>(p->K) + 16.0 * p->lora_ksteps * p->lora_nkb);
+}
+
+// launch one kernel; with profiling on, bracket it with events on the launching stream
+#define RUNC(cat, flops, expr)                                   \
+  do {                                                           \
+    cudaEvent_t _a = nullptr, _b = nullptr;                      \
+    if (e->prof) {                                               \
+      _a = prof_event(e);                                        \
+      _b = prof_event(e);                                        \
+      cudaEventRecord(_a, s);                                    \
+    }                                                            \
+    if (expr) return 1;                                          \
+    ++e->launches;                                               \
+    if (e->prof) {                                               \
+      cudaEventRecord(_b, s);                                    \
+      e->prof_recs.push_back({(cat), (flops), _a, _b});          \
+    }                                                            \
   } while (0)
+#define RUN_GEMM(plan) RUNC(CAT_GEMM, plan_flops(plan), gemm_launch((plan), s, e->num_sms))
+#define RUN_GEMM_T(plan) RUNC(CAT_GEMM_LORA_T, plan_flops(plan), gemm_launch((plan), s, e->num_sms))
 
 // forward through the encoder from the im2col'd, normalised input in e->cols
 static int encoder_forward(vitatk_engine* e, PlanSet* ps, int batch, cudaStream_t s) {
   const vitatk_config& c = e->cfg;
   const int M = batch * TOKENS, D = c.dim;
-  RUN(gemm_launch(&ps->patch, s, e->num_sms));
+  RUN_GEMM(&ps->patch);
   for (int l = 0; l < c.layers; ++l) {
     const LayerWeights& w = e->lw[l];
     LayerPlans& p = ps->layers[l];
-    RUN(layernorm_fwd(e->h[l], w.ln1_g, w.ln1_b, e->xn, e->st1[l], M, D, c.ln_eps, s));
-    if (w.lora[VITATK_SITE_QKV].rank > 0) RUN(gemm_launch(&p.t_qkv, s, e->num_sms));
-    RUN(gemm_launch(&p.qkv, s, e->num_sms));
-    RUN(attention_fwd(e->qkv[l], e->ao, batch, TOKENS, c.heads, s));
-    if (w.lora[VITATK_SITE_PROJ].rank > 0) RUN(gemm_launch(&p.t_proj, s, e->num_sms));
-    RUN(gemm_launch(&p.proj, s, e->num_sms));
-    RUN(layernorm_fwd(e->h_mid[l], w.ln2_g, w.ln2_b, e->xn, e->st2[l], M, D, c.ln_eps, s));
-    if (w.lora[VITATK_SITE_FC1].rank > 0) RUN(gemm_launch(&p.t_fc1, s, e->num_sms));
-    RUN(gemm_launch(&p.fc1, s, e->num_sms));
-    if (w.lora[VITATK_SITE_FC2].rank > 0) RUN(gemm_launch(&p.t_fc2, s, e->num_sms));
-    RUN(gemm_launch(&p.fc2, s, e->num_sms));
+    RUNC(CAT_LN, 0, layernorm_fwd(e->h[l], w.ln1_g, w.ln1_b, e->xn, e->st1[l], M, D, c.ln_eps, s));
+    if (w.lora[VITATK_SITE_QKV].rank > 0) RUN_GEMM_T(&p.t_qkv);
+    RUN_GEMM(&p.qkv);
+    RUNC(CAT_ATTN_FWD, 4.0 * batch * c.heads * TOKENS * TOKENS * 64, attention_fwd(e->qkv[l], e->ao, batch, TOKENS, c.heads, s));
+    if (w.lora[VITATK_SITE_PROJ].rank > 0) RUN_GEMM_T(&p.t_proj);
+    RUN_GEMM(&p.proj);
+    RUNC(CAT_LN, 0, layernorm_fwd(e->h_mid[l], w.ln2_g, w.ln2_b, e->xn, e->st2[l], M, D, c.ln_eps, s));
+    if (w.lora[VITATK_SITE_FC1].rank > 0) RUN_GEMM_T(&p.t_fc1);
+    RUN_GEMM(&p.fc1);
+    if (w.lora[VITATK_SITE_FC2].rank > 0) RUN_GEMM_T(&p.t_fc2);
+    RUN_GEMM(&p.fc2);
   }
   return 0;
 }
@@ -238,19 +273,19 @@ static int encoder_backward(vitatk_engine* e, PlanSet* ps, int batch, cudaStream
   for (int l = c.layers - 1; l >= 0; --l) {
     const LayerWeights& w = e->lw[l];
     LayerPlans& p = ps->layers[l];
-    if (w.lora[VITATK_SITE_FC2].rank > 0) RUN(gemm_launch(&p.bt_fc2, s, e->num_sms));
-    RUN(gemm_launch(&p.bfc2, s, e->num_sms));  // du = (dh W2 + lora) * gelu'(u)
-    if (w.lora[VITATK_SITE_FC1].rank > 0) RUN(gemm_launch(&p.bt_fc1, s, e->num_sms));
-    RUN(gemm_launch(&p.bfc1, s, e->num_sms));  // dxn = du W1 + lora
-    RUN(layernorm_bwd(e->dxn, e->h_mid[l], e->st2[l], w.ln2_g, e->dh_a, e->dh_b, M, D, s));  // dh_mid
-    if (w.lora[VITATK_SITE_PROJ].rank > 0) RUN(gemm_launch(&p.bt_proj, s, e->num_sms));
-    RUN(gemm_launch(&p.bproj, s, e->num_sms));  // dao = dh_mid Wp + lora
-    RUN(attention_bwd(e->qkv[l], e->dao, e->dqkv, batch, TOKENS, c.heads, s));
-    if (w.lora[VITATK_SITE_QKV].rank > 0) RUN(gemm_launch(&p.bt_qkv, s, e->num_sms));
-    RUN(gemm_launch(&p.bqkv, s, e->num_sms));  // dxn = dqkv Wqkv + lora
-    RUN(layernorm_bwd(e->dxn, e->h[l], e->st1[l], w.ln1_g, e->dh_b, e->dh_a, M, D, s));  // dh wrt h[l]
+    if (w.lora[VITATK_SITE_FC2].rank > 0) RUN_GEMM_T(&p.bt_fc2);
+    RUN_GEMM(&p.bfc2);  // du = (dh W2 + lora) * gelu'(u)
+    if (w.lora[VITATK_SITE_FC1].rank > 0) RUN_GEMM_T(&p.bt_fc1);
+    RUN_GEMM(&p.bfc1);  // dxn = du W1 + lora
+    RUNC(CAT_LN, 0, layernorm_bwd(e->dxn, e->h_mid[l], e->st2[l], w.ln2_g, e->dh_a, e->dh_b, M, D, s));  // dh_mid
+    if (w.lora[VITATK_SITE_PROJ].rank > 0) RUN_GEMM_T(&p.bt_proj);
+    RUN_GEMM(&p.bproj);  // dao = dh_mid Wp + lora
+    RUNC(CAT_ATTN_BWD, 8.0 * batch * c.heads * TOKENS * TOKENS * 64, attention_bwd(e->qkv[l], e->dao, e->dqkv, batch, TOKENS, c.heads, s));
+    if (w.lora[VITATK_SITE_QKV].rank > 0) RUN_GEMM_T(&p.bt_qkv);
+    RUN_GEMM(&p.bqkv);  // dxn = dqkv Wqkv + lora
+    RUNC(CAT_LN, 0, layernorm_bwd(e->dxn, e->h[l], e->st1[l], w.ln1_g, e->dh_b, e->dh_a, M, D, s));  // dh wrt h[l]
   }
-  RUN(gemm_launch(&ps->bpatch, s, e->num_sms));  // dxn <- dL/d(cols)
+  RUN_GEMM(&ps->bpatch);  // dxn <- dL/d(cols)
   return 0;
 }
 
@@ -412,6 +447,40 @@ int vitatk_set_normalization(vitatk_engine* e, const float* mean3, const float* 
   return 0;
 }
 
+int vitatk_profile_begin(vitatk_engine* e) {
+  if (!e) {
+    set_error("vitatk_profile_begin: null engine");
+    return 1;
+  }
+  e->prof = true;
+  return 0;
+}
+
+int vitatk_profile_end(vitatk_engine* e, double* ms_by_cat, double* flops_by_cat, long long* launches_by_cat) {
+  if (!e || !ms_by_cat || !flops_by_cat || !launches_by_cat) {
+    set_error("vitatk_profile_end: null argument");
+    return 1;
+  }
+  e->prof = false;
+  for (int i = 0; i < CAT_COUNT; ++i) {
+    ms_by_cat[i] = 0;
+    flops_by_cat[i] = 0;
+    launches_by_cat[i] = 0;
+  }
+  for (auto& r : e->prof_recs) {
+    VITATK_CUDA_OK(cudaEventSynchronize(r.b));
+    float ms = 0.f;
+    VITATK_CUDA_OK(cudaEventElapsedTime(&ms, r.a, r.b));
+    ms_by_cat[r.cat] += ms;
+    flops_by_cat[r.cat] += r.flops;
+    launches_by_cat[r.cat] += 1;
+    e->prof_pool.push_back(r.a);
+    e->prof_pool.push_back(r.b);
+  }
+  e->prof_recs.clear();
+  return 0;
+}
+
 long long vitatk_workspace_bytes(const vitatk_engine* e) { return e ? e->ws_bytes : 0; }
 long long vitatk_launch_count(const vitatk_engine* e) { return e ? e->launches : 0; }
 
@@ -493,9 +562,9 @@ int vitatk_forward(vitatk_engine* e, const float* images, int batch, float* logi
   PlanSet* ps = nullptr;
   if (build_plans(e, batch, &ps)) return 1;
   const vitatk_config& c = e->cfg;
-  RUN(pgd_init(images, nullptr, e->scratch_img, e->cols, batch, e->nrm, 0.f, 0, 0, 0, s));
+  RUNC(CAT_PIXEL, 0, pgd_init(images, nullptr, e->scratch_img, e->cols, batch, e->nrm, 0.f, 0, 0, 0, s));
   if (encoder_forward(e, ps, batch, s)) return 1;
-  RUN(head_fwd_bwd(e->h[c.layers], e->lnf_g, e->lnf_b, e->head_w, e->head_b, nullptr, logits_out, nullptr, nullptr,
+  RUNC(CAT_HEAD, 0, head_fwd_bwd(e->h[c.layers], e->lnf_g, e->lnf_b, e->head_w, e->head_b, nullptr, logits_out, nullptr, nullptr,
                    batch, TOKENS, c.dim, c.num_classes, c.ln_eps, 0.f, s));
   return 0;
 }
@@ -507,14 +576,14 @@ int vitatk_input_grad(vitatk_engine* e, const float* images, const int64_t* labe
   PlanSet* ps = nullptr;
   if (build_plans(e, batch, &ps)) return 1;
   const vitatk_config& c = e->cfg;
-  RUN(pgd_init(images, nullptr, e->scratch_img, e->cols, batch, e->nrm, 0.f, 0, 0, 0, s));
+  RUNC(CAT_PIXEL, 0, pgd_init(images, nullptr, e->scratch_img, e->cols, batch, e->nrm, 0.f, 0, 0, 0, s));
   if (encoder_forward(e, ps, batch, s)) return 1;
   // internal gradient is of the SUM of per-image CE (keeps magnitudes independent of batch / sharding);
   // the 1/B of the reference's mean reduction (whitebox_attacks.py:29) is applied when materialising.
-  RUN(head_fwd_bwd(e->h[c.layers], e->lnf_g, e->lnf_b, e->head_w, e->head_b, labels, logits_out ? logits_out : e->logits,
+  RUNC(CAT_HEAD, 0, head_fwd_bwd(e->h[c.layers], e->lnf_g, e->lnf_b, e->head_w, e->head_b, labels, logits_out ? logits_out : e->logits,
                    loss_out ? loss_out : e->loss, e->dh_a, batch, TOKENS, c.dim, c.num_classes, c.ln_eps, 1.0f, s));
   if (encoder_backward(e, ps, batch, s)) return 1;
-  RUN(grad_to_image(e->dxn, grad_out, batch, e->nrm, 1.0f / batch, s));
+  RUNC(CAT_PIXEL, 0, grad_to_image(e->dxn, grad_out, batch, e->nrm, 1.0f / batch, s));
   return 0;
 }
 
@@ -534,14 +603,14 @@ int vitatk_attack(vitatk_engine* e, const float* images, const int64_t* labels, 
   PlanSet* ps = nullptr;
   if (build_plans(e, batch, &ps)) return 1;
   const vitatk_config& c = e->cfg;
-  RUN(pgd_init(images, start == VITATK_START_NOISE ? noise : nullptr, adv, e->cols, batch, e->nrm, eps,
+  RUNC(CAT_PIXEL, 0, pgd_init(images, start == VITATK_START_NOISE ? noise : nullptr, adv, e->cols, batch, e->nrm, eps,
                start == VITATK_START_RNG ? 1 : 0, seed, image_index0, s));
   for (int it = 0; it < steps; ++it) {
     if (encoder_forward(e, ps, batch, s)) return 1;
-    RUN(head_fwd_bwd(e->h[c.layers], e->lnf_g, e->lnf_b, e->head_w, e->head_b, labels, e->logits, e->loss, e->dh_a,
+    RUNC(CAT_HEAD, 0, head_fwd_bwd(e->h[c.layers], e->lnf_g, e->lnf_b, e->head_w, e->head_b, labels, e->logits, e->loss, e->dh_a,
                      batch, TOKENS, c.dim, c.num_classes, c.ln_eps, 1.0f, s));
     if (encoder_backward(e, ps, batch, s)) return 1;
-    RUN(pgd_update(e->dxn, images, adv, e->cols, batch, e->nrm, eps, alpha, s));
+    RUNC(CAT_PIXEL, 0, pgd_update(e->dxn, images, adv, e->cols, batch, e->nrm, eps, alpha, s));
   }
   return 0;
 }
@@ -549,7 +618,8 @@ int vitatk_attack(vitatk_engine* e, const float* images, const int64_t* labels, 
 int vitatk_count_correct(vitatk_engine* e, const float* images, const int64_t* labels, int batch, long long* counts,
                          void* stream) {
   if (vitatk_forward(e, images, batch, e->logits, stream)) return 1;
-  RUN(count_correct(e->logits, labels, batch, e->cfg.num_classes, counts, static_cast<cudaStream_t>(stream)));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  RUNC(CAT_HEAD, 0, count_correct(e->logits, labels, batch, e->cfg.num_classes, counts, s));
   return 0;
 }
 

@@ -155,7 +155,7 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
-  d |= static_cast<uint64_t>(0) << 16;             // LBO (ignored)
+  d |= static_cast<uint64_t>(1) << 16;             // LBO = 16 B (canonical value; unused by swizzled K-major)
   d |= static_cast<uint64_t>(1024 >> 4) << 32;     // SBO = 1024 B
   d |= static_cast<uint64_t>(1) << 46;             // descriptor version (Blackwell)
   d |= static_cast<uint64_t>(2) << 61;             // SWIZZLE_128B

@@ -311,6 +311,17 @@ class Engine:
                                                      self._stream()), "vitatk_count_correct")
         return counts
 
+    PROFILE_CATEGORIES = ("gemm_tc05", "gemm_lora_t", "attention_fwd", "attention_bwd", "layernorm", "head", "pixel")
+
+    def profile_begin(self) -> None:
+        _lib.check(self.lib.vitatk_profile_begin(self._h), "vitatk_profile_begin")
+
+    def profile_end(self) -> Dict[str, Dict[str, float]]:
+        """{category: {ms, flops, launches}} for everything enqueued since profile_begin()."""
+        ms, fl, n = (C.c_double * 8)(), (C.c_double * 8)(), (C.c_longlong * 8)()
+        _lib.check(self.lib.vitatk_profile_end(self._h, ms, fl, n), "vitatk_profile_end")
+        return {c: {"ms": ms[i], "flops": fl[i], "launches": int(n[i])} for i, c in enumerate(self.PROFILE_CATEGORIES)}
+
     def close(self) -> None:
         if getattr(self, "_h", None) is not None and self._h.value:
             torch.cuda.synchronize(self.device)

@@ -126,6 +126,14 @@ int vitatk_count_correct(vitatk_engine* e, const float* images_dev, const int64_
 /* number of kernels the engine enqueued since creation (bench.py reports the per-step delta) */
 long long vitatk_launch_count(const vitatk_engine* e);
 
+/* Per-launch CUDA-event timing for bench.py's roofline leg (never on inside a timed region).  Between
+ * begin and end every kernel the engine enqueues is bracketed by events on its stream; end() waits for
+ * them and returns, per category, the summed duration (ms), algorithmic FLOPs and launch count.
+ * Categories: 0 GEMM (tcgen05), 1 LoRA x*A^T GEMM, 2 attention fwd, 3 attention bwd, 4 LayerNorm,
+ * 5 head/CE/count, 6 pixel kernels (PGD init/update, gradient materialisation); arrays have 8 entries. */
+int vitatk_profile_begin(vitatk_engine* e);
+int vitatk_profile_end(vitatk_engine* e, double* ms_by_cat, double* flops_by_cat, long long* launches_by_cat);
+
 /* ---- kernel-level entry points (used by tests/ and bench.py's roofline leg) ---- */
 int vitatk_k_gemm(int M, int N, int K, const void* A_dev, int lda, const void* B_dev, int ldb, void* out_dev,
                   int ldo, void* out2_dev, int ldo2, const void* T_dev, int ldt, const void* LB_dev, int ldlb,

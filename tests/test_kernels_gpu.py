@@ -1,0 +1,281 @@
+"""GPU: every hand-written kernel against a plain PyTorch fp32 reference of the same op, through the C ABI."""
+import ctypes as C
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+EPI_PLAIN, EPI_RESIDUAL, EPI_GELU_DUAL, EPI_DGELU, EPI_ROWTABLE = 0, 1, 2, 3, 4
+
+
+def _s():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _gelu(u):
+    return 0.5 * u * (1 + torch.erf(u / math.sqrt(2)))
+
+
+def _dgelu(u):
+    return 0.5 * (1 + torch.erf(u / math.sqrt(2))) + u * torch.exp(-0.5 * u * u) / math.sqrt(2 * math.pi)
+
+
+def run_gemm(lib, A, B, epi=EPI_PLAIN, bias=None, res=None, table=None, T=None, LB=None, nkb=0, ksteps=0,
+             group_cols=0, simt=False):
+    from vitatk import _lib
+
+    M, K = A.shape
+    N = B.shape[0]
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    out2 = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16) if epi == EPI_GELU_DUAL else None
+    rc = lib.vitatk_k_gemm(M, N, K, _p(A), A.stride(0), _p(B), B.stride(0), _p(out), N, _p(out2), N, _p(T),
+                           0 if T is None else T.stride(0), _p(LB), 0 if LB is None else LB.stride(0), nkb, ksteps,
+                           group_cols, epi, _p(bias), _p(res), 0 if res is None else res.stride(0), _p(table),
+                           0 if table is None else table.shape[0], 1 if simt else 0, _s())
+    _lib.check(rc, "vitatk_k_gemm")
+    torch.cuda.synchronize()
+    return out, out2
+
+
+def ref_gemm(A, B, epi, bias, res, table, T, LB, nkb, ksteps, group_cols):
+    acc = A.float() @ B.float().t()
+    if nkb:
+        N = B.shape[0]
+        r = ksteps * 16
+        for j in range(nkb):
+            if group_cols:
+                for g in range(N // group_cols):
+                    acc[:, g * group_cols:(g + 1) * group_cols] += (
+                        T[:, g * 64 + j * 64: g * 64 + j * 64 + r].float()
+                        @ LB[g * group_cols:(g + 1) * group_cols, j * 64: j * 64 + r].float().t())
+            else:
+                acc += T[:, j * 64: j * 64 + r].float() @ LB[:, j * 64: j * 64 + r].float().t()
+    if bias is not None:
+        acc = acc + bias
+    out2 = None
+    if epi == EPI_RESIDUAL:
+        acc = acc + res.float()
+    elif epi == EPI_DGELU:
+        acc = acc * _dgelu(res.float())
+    elif epi == EPI_ROWTABLE:
+        rows = torch.arange(A.shape[0], device=A.device) % table.shape[0]
+        acc = acc + table[rows]
+    elif epi == EPI_GELU_DUAL:
+        out2 = _gelu(acc)
+    return acc, out2
+
+
+def check_close(got, want, what):
+    got = got.float()
+    assert torch.isfinite(got).all(), f"{what}: non-finite output"
+    scale = want.abs().max().item() + 1e-6
+    err = (got - want).abs()
+    tol = 1e-2 * want.abs() + 4e-3 * scale  # bf16 output rounding (2^-8 relative) + accumulation order
+    bad = (err > tol).float().mean().item()
+    assert bad == 0.0, f"{what}: {bad:.4%} elements out of tolerance, max err {err.max().item():.4g} (scale {scale:.3g})"
+
+
+def check_rel(got, want, what, rel_l2, rel_max):
+    got = got.float()
+    assert torch.isfinite(got).all(), f"{what}: non-finite output"
+    l2 = float((got - want).norm() / (want.norm() + 1e-12))
+    mx = float((got - want).abs().max() / (want.abs().max() + 1e-12))
+    assert l2 < rel_l2 and mx < rel_max, f"{what}: rel l2 {l2:.4g} (<{rel_l2}), rel max {mx:.4g} (<{rel_max})"
+
+
+GEMM_CASES = [
+    # M, N, K, epi, lora(nkb, r, group_cols)
+    (128, 256, 64, EPI_PLAIN, (0, 0, 0)),
+    (128, 256, 768, EPI_PLAIN, (0, 0, 0)),
+    (1576, 768, 768, EPI_PLAIN, (0, 0, 0)),       # config-1 token count (8*197), ragged last M tile
+    (1576, 2304, 768, EPI_PLAIN, (1, 8, 768)),    # fused q|k|v forward with three adapters
+    (1576, 768, 768, EPI_RESIDUAL, (1, 8, 0)),    # proj forward
+    (1576, 3072, 768, EPI_GELU_DUAL, (1, 16, 0)),  # fc1 forward
+    (1576, 768, 3072, EPI_RESIDUAL, (1, 32, 0)),  # fc2 forward
+    (1576, 3072, 768, EPI_DGELU, (1, 8, 0)),      # fc2 backward
+    (1576, 768, 2304, EPI_PLAIN, (3, 8, 0)),      # qkv backward: three extra k-blocks
+    (1576, 768, 768, EPI_ROWTABLE, (0, 0, 0)),    # patch embed
+    (1576, 192, 768, EPI_PLAIN, (0, 0, 0)),       # LoRA T = x A^T (BN = 64)
+    (1576, 64, 3072, EPI_PLAIN, (0, 0, 0)),
+    (197, 128, 128, EPI_PLAIN, (0, 0, 0)),        # BN = 128 path, single image
+    (50432, 768, 768, EPI_RESIDUAL, (1, 8, 0)),   # full BASELINE size (256*197): many tiles per CTA
+]
+
+
+@pytest.mark.parametrize("M,N,K,epi,lora", GEMM_CASES)
+def test_gemm_tc05_vs_torch(lib, M, N, K, epi, lora):
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K + epi)
+    rn = lambda *s: torch.randn(*s, device="cuda", generator=g)  # noqa: E731
+    A = rn(M, K).to(torch.bfloat16)
+    B = (rn(N, K) / math.sqrt(K)).to(torch.bfloat16)
+    bias = rn(N) * 0.1 if epi in (EPI_PLAIN, EPI_RESIDUAL, EPI_GELU_DUAL) and N != 192 else None
+    res = rn(M, N).to(torch.bfloat16) if epi in (EPI_RESIDUAL, EPI_DGELU) else None
+    table = rn(197, N) if epi == EPI_ROWTABLE else None
+    nkb, r, gc = lora
+    T = LB = None
+    ksteps = 0
+    if nkb:
+        ksteps = (r + 15) // 16
+        tcols = (N // gc) * 64 if gc else nkb * 64
+        T = torch.zeros(M, tcols, device="cuda")
+        LB = torch.zeros(N, nkb * 64, device="cuda")
+        for j in range(tcols // 64):
+            T[:, j * 64: j * 64 + r] = rn(M, r)
+        for j in range(nkb):
+            LB[:, j * 64: j * 64 + r] = rn(N, r) * 0.1
+        # columns beyond r inside an issued k-step must be zero (the engine pads with zeros)
+        T, LB = T.to(torch.bfloat16), LB.to(torch.bfloat16)
+    out, out2 = run_gemm(lib, A, B, epi, bias, res, table, T, LB, nkb, ksteps, gc)
+    want, want2 = ref_gemm(A, B, epi, bias, res, table, T, LB, nkb, ksteps, gc)
+    check_close(out, want, f"gemm {M}x{N}x{K} epi{epi}")
+    if epi == EPI_GELU_DUAL:
+        check_close(out2, want2, "gelu output")
+    if M <= 2000:  # cross-check with the scalar CUDA-core kernel (bit-level agreement is not expected)
+        s_out, s_out2 = run_gemm(lib, A, B, epi, bias, res, table, T, LB, nkb, ksteps, gc, simt=True)
+        check_close(s_out, want, "simt gemm")
+
+
+def test_gemm_rejects_bad_shapes(lib):
+    from vitatk import _lib
+
+    A = torch.zeros(8, 100, device="cuda", dtype=torch.bfloat16)
+    B = torch.zeros(64, 100, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(_lib.VitatkError):
+        run_gemm(lib, A, B)
+
+
+@pytest.mark.parametrize("batch,tokens", [(1, 197), (3, 197), (2, 50), (1, 208), (2, 1)])
+def test_attention_fwd_bwd_vs_torch(lib, batch, tokens):
+    from vitatk import _lib
+
+    heads, D = 12, 768
+    g = torch.Generator(device="cuda").manual_seed(batch * 100 + tokens)
+    qkv = (torch.randn(batch * tokens, 3 * D, device="cuda", generator=g) * 1.5).to(torch.bfloat16)
+    dout = torch.randn(batch * tokens, D, device="cuda", generator=g).to(torch.bfloat16)
+    out = torch.full((batch * tokens, D), float("nan"), device="cuda", dtype=torch.bfloat16)
+    dqkv = torch.full((batch * tokens, 3 * D), float("nan"), device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.vitatk_k_attention_fwd(_p(qkv), _p(out), batch, tokens, heads, _s()), "attention_fwd")
+    _lib.check(lib.vitatk_k_attention_bwd(_p(qkv), _p(dout), _p(dqkv), batch, tokens, heads, _s()), "attention_bwd")
+    torch.cuda.synchronize()
+    x = qkv.float().reshape(batch, tokens, 3, heads, 64).permute(2, 0, 3, 1, 4).requires_grad_(True)  # [3,B,H,T,d]
+    q, k, v = x[0], x[1], x[2]
+    p = torch.softmax(q @ k.transpose(-1, -2) / 8.0, dim=-1)
+    o = (p @ v).permute(0, 2, 1, 3).reshape(batch * tokens, D)
+    (gx,) = torch.autograd.grad(o, x, dout.float())
+    gref = gx.permute(1, 3, 0, 2, 4).reshape(batch * tokens, 3 * D)
+    # probabilities and dS are rounded to bf16 before the second GEMM of each chain (fp32 accumulate)
+    check_rel(out, o.detach(), "attention out", 8e-3, 2e-2)
+    check_rel(dqkv, gref, "attention dqkv", 1.5e-2, 3e-2)
+
+
+@pytest.mark.parametrize("rows", [1, 8, 197, 1576, 50432])
+def test_layernorm_fwd_bwd_vs_torch(lib, rows):
+    from vitatk import _lib
+
+    cols = 768
+    g = torch.Generator(device="cuda").manual_seed(rows)
+    x = (torch.randn(rows, cols, device="cuda", generator=g) * 2 + 0.5).to(torch.bfloat16)
+    gamma = 1 + 0.1 * torch.randn(cols, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(cols, device="cuda", generator=g)
+    dy = torch.randn(rows, cols, device="cuda", generator=g).to(torch.bfloat16)
+    dres = torch.randn(rows, cols, device="cuda", generator=g).to(torch.bfloat16)
+    y = torch.empty_like(x)
+    stats = torch.empty(rows, 2, device="cuda")
+    dx = torch.empty_like(x)
+    _lib.check(lib.vitatk_k_layernorm_fwd(_p(x), _p(gamma), _p(beta), _p(y), _p(stats), rows, cols, 1e-12, _s()), "ln_fwd")
+    _lib.check(lib.vitatk_k_layernorm_bwd(_p(dy), _p(x), _p(stats), _p(gamma), _p(dres), _p(dx), rows, cols, _s()), "ln_bwd")
+    torch.cuda.synchronize()
+    xf = x.float().requires_grad_(True)
+    yr = torch.nn.functional.layer_norm(xf, (cols,), gamma, beta, eps=1e-12)
+    (gx,) = torch.autograd.grad(yr, xf, dy.float())
+    check_close(y, yr.detach(), "ln y")
+    check_close(dx, gx + dres.float(), "ln dx")
+    torch.testing.assert_close(stats[:, 0], x.float().mean(-1), rtol=1e-4, atol=1e-4)
+
+
+def _cols_from_image(img, mean, std):
+    """torch restatement of the im2col layout: [B,3,224,224] -> [B*197, 768] with zero CLS rows."""
+    B = img.shape[0]
+    m = torch.tensor(mean, device=img.device).view(1, 3, 1, 1)
+    s = torch.tensor(std, device=img.device).view(1, 3, 1, 1)
+    xn = (img - m) * (1.0 / s)
+    patches = xn.reshape(B, 3, 14, 16, 14, 16).permute(0, 2, 4, 1, 3, 5).reshape(B, 196, 768)
+    return torch.cat([torch.zeros(B, 1, 768, device=img.device), patches], 1).reshape(B * 197, 768)
+
+
+def _image_from_cols(cols, B):
+    return cols.reshape(B, 197, 768)[:, 1:].reshape(B, 14, 14, 3, 16, 16).permute(0, 3, 1, 4, 2, 5).reshape(B, 3, 224, 224)
+
+
+def enforce_ball(adv, x0, eps):
+    """torch restatement of the kernel's strict-ball rule (one ulp towards x0 when fl32(adv-x0) leaves the ball)."""
+    e = torch.tensor(eps, dtype=torch.float32, device=adv.device)
+    d = adv - x0
+    adv = torch.where(d > e, torch.nextafter(adv, adv - 1), adv)
+    return torch.where(d < -e, torch.nextafter(adv, adv + 1), adv)
+
+
+@pytest.mark.parametrize("batch", [1, 3, 8])
+def test_pgd_init_and_update_bit_exact(lib, batch):
+    from vitatk import _lib
+
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    eps, alpha = 8 / 255, 2 / 255
+    g = torch.Generator(device="cuda").manual_seed(batch)
+    x0 = torch.rand(batch, 3, 224, 224, device="cuda", generator=g)
+    noise = torch.empty_like(x0).uniform_(-eps, eps, generator=g)
+    adv = torch.empty_like(x0)
+    cols = torch.full((batch * 197, 768), float("nan"), device="cuda", dtype=torch.bfloat16)
+    mean_c, std_c = (C.c_float * 3)(*mean), (C.c_float * 3)(*std)
+    _lib.check(lib.vitatk_k_pgd_init(_p(x0), _p(noise), _p(adv), _p(cols), batch, mean_c, std_c, eps, 0, 0, 0, _s()), "init")
+    torch.cuda.synchronize()
+    raw = torch.clamp(x0 + noise, 0, 1)
+    want_adv = enforce_ball(raw, x0, eps)
+    assert torch.equal(adv, want_adv)
+    assert float((adv - raw).abs().max()) <= 6e-8  # at most one ulp away from the torchattacks arithmetic
+    want_cols = _cols_from_image(want_adv, mean, std)
+    assert (cols.float() - want_cols).abs().max() <= 2e-2  # bf16 rounding of values up to ~2.7
+    assert torch.equal(cols.reshape(batch, 197, 768)[:, 0], torch.zeros(batch, 768, device="cuda", dtype=torch.bfloat16))
+    # update: gradient given in im2col layout
+    gimg = torch.randn(batch, 3, 224, 224, device="cuda", generator=g)
+    gimg[:, :, ::7, ::5] = 0.0  # exact zeros must not move the pixel (torch.sign(0) == 0)
+    dcols = _cols_from_image(gimg, (0, 0, 0), (1, 1, 1)).to(torch.bfloat16)
+    gimg_b = _image_from_cols(dcols.float(), batch)
+    adv_in = adv.clone()
+    _lib.check(lib.vitatk_k_pgd_update(_p(dcols), _p(x0), _p(adv), _p(cols), batch, mean_c, std_c, eps, alpha, _s()), "update")
+    torch.cuda.synchronize()
+    stepped = adv_in + alpha * gimg_b.sign()
+    delta = torch.clamp(stepped - x0, min=-eps, max=eps)
+    raw = torch.clamp(x0 + delta, 0, 1)
+    want = enforce_ball(raw, x0, eps)
+    assert torch.equal(adv, want)  # bit-exact fp32: same operation order as the oracle / torchattacks
+    assert float((adv - raw).abs().max()) <= 6e-8 and float((adv != raw).float().mean()) < 0.05
+    assert float((adv - x0).abs().max()) <= float(torch.tensor(eps, dtype=torch.float32))  # exactly inside the ball
+    assert float(adv.min()) >= 0 and float(adv.max()) <= 1
+    assert (cols.float() - _cols_from_image(want, mean, std)).abs().max() <= 2e-2
+
+
+def test_pgd_init_rng_is_counter_based(lib):
+    from vitatk import _lib
+
+    mean_c, std_c = (C.c_float * 3)(0, 0, 0), (C.c_float * 3)(1, 1, 1)
+    eps = 8 / 255
+    x0 = torch.full((4, 3, 224, 224), 0.5, device="cuda")
+    a = torch.empty_like(x0)
+    b = torch.empty_like(x0[:2])
+    cols = torch.empty(4 * 197, 768, device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.vitatk_k_pgd_init(_p(x0), None, _p(a), _p(cols), 4, mean_c, std_c, eps, 1, 123, 10, _s()), "init")
+    # images 12,13 generated alone (as another rank would) must equal rows 2,3 of the 4-image call
+    _lib.check(lib.vitatk_k_pgd_init(_p(x0), None, _p(b), _p(cols), 2, mean_c, std_c, eps, 1, 123, 12, _s()), "init")
+    torch.cuda.synchronize()
+    assert torch.equal(a[2:], b)
+    d = a - 0.5
+    assert float(d.abs().max()) <= float(torch.tensor(eps, dtype=torch.float32))
+    assert abs(float(d.mean())) < 1e-4 and float(d.std()) == pytest.approx(eps / math.sqrt(3), rel=0.02)
+    assert not torch.equal(a[0], a[1])

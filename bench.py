@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py — PGD-10 adversarial images / second on LoRA ViT-B/16, batch 256 per GPU (BASELINE.json configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's engine (torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port), rank 0 only
+
+A "step" is one full PGD-10 attack (eps 8/255, alpha 2/255, random start) on one batch of 256 synthetic
+224x224 images per GPU = 10 x (ViT forward + input-gradient backward + fused update).  One JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+EPS, ALPHA, PGD_STEPS, BATCH, CLASSES, RANK_R = 8 / 255, 2 / 255, 10, 256, 21, 8
+METRIC = "PGD-10 adv images/sec, LoRA ViT-B/16 bs256, 1/2/4/8 B200; tensor-pipe util"
+UNIT = "adv_images/s"
+
+
+def algorithmic_gflop_per_image_step(r=RANK_R):
+    """dense-contraction FLOPs of one PGD step for one image (no dW, no recompute counted)."""
+    T, D, F, L = 197, 768, 3072, 12
+    lin = 2 * T * (3 * D * D + D * D + 2 * D * F)            # qkv, proj, fc1, fc2
+    att = 4 * T * T * D                                        # QK^T + PV over 12 heads
+    patch = 2 * 196 * D * D
+    lora = 2 * T * r * ((D + D) * 3 + (D + D) + (D + F) + (F + D))
+    fwd = patch + L * (lin + att)
+    bwd = patch + L * (lin + 2 * att)
+    return (fwd + bwd + 2 * L * lora) / 1e9
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index, self.proc, self.path = gpu_index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        rows = []
+        for line in open(self.path):
+            f = [v.strip() for v in line.split(",")]
+            if len(f) >= 8:
+                rows.append(f)
+        os.unlink(self.path)
+        sm = sorted(float(r[1]) for r in rows if r[1].replace(".", "").isdigit())
+        if sm:
+            out["sm_mhz"] = sm[len(sm) // 2]
+            out["sm_max_mhz"] = float(rows[0][2])
+            out["power_w_max"] = max(float(r[3]) for r in rows if r[3].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        out["reasons"] = [n for i, n in enumerate(names) if any(r[4 + i].lower().startswith("active") for r in rows)]
+        out["samples"] = len(rows)
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port of the reference's PyTorch attack on the host cores
+# ---------------------------------------------------------------------------------------------------------
+def cpu_reference_run(steps, warmup, sample_batch):
+    """Time `steps` PGD-10 attacks of `sample_batch` images each with the oracle (fp32 torch, all host threads)."""
+    import torch
+
+    from oracle import vit_oracle as vo
+    from vitatk import synthetic
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = synthetic.random_vit(CLASSES, seed=0)
+    adapters = synthetic.random_adapters(model, r=RANK_R, seed=0)
+    vo.attach_lora(model, r=RANK_R, alpha=16.0, targets=vo.ALL_TARGETS, seed=0)
+    with torch.no_grad():
+        for name, mod in model.named_modules():
+            if isinstance(mod, vo.LoraLinear):
+                A, B, _ = adapters[name][0]
+                mod.lora_A.copy_(A)
+                mod.lora_B.copy_(B)
+    x, y = synthetic.images_and_labels(sample_batch, 0, CLASSES, seed=0)
+    g = torch.Generator().manual_seed(1)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        vo.pgd(model, x, y, eps=EPS, alpha=ALPHA, steps=PGD_STEPS, random_start=True, generator=g)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    total = sum(times)
+    return {"value": sample_batch * len(times) / total, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{len(times)} x PGD-10 on {sample_batch} images (fp32 torch CPU oracle of whitebox_attacks.py "
+                      f"+ torchattacks-PGD restatement), {total:.1f} s, {warmup} warm-up"}, total / max(len(times), 1)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    per_step_budget = 150.0 / max(args.steps + args.warmup, 1)
+    sample = 8 if per_step_budget > 30 else (4 if per_step_budget > 12 else 2)
+    base, sec_per_step = cpu_reference_run(args.steps, args.warmup, sample)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "PGD-10 eps=8/255 alpha=2/255 random-start, LoRA(r=8; q,k,v,proj,fc1,fc2) ViT-B/16, "
+                               "21 classes, 224x224; reference arm = bounded CPU sample", "sample_batch": sample},
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------------
+# this repo's arm
+# ---------------------------------------------------------------------------------------------------------
+def run_engine(args):
+    import torch
+    import torch.distributed as dist
+
+    import vitatk
+    from vitatk import synthetic
+    from vitatk.dist import allreduce_counts
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    batch = args.batch
+    idx0 = rank * batch  # weak scaling: every rank attacks its own 256 independent images, no data-path collective
+
+    model = synthetic.random_vit(CLASSES, seed=0)
+    adapters = synthetic.random_adapters(model, r=RANK_R, seed=0)
+    eng = vitatk.Engine(model=model, adapters=adapters, max_batch=batch, device=dev)
+    x_host, y_host = synthetic.images_and_labels(batch, idx0, CLASSES, seed=0, pin=True)
+    x, y = x_host.to(dev), y_host.to(dev)
+    adv = torch.empty_like(x)
+    adv_host = torch.empty_like(x_host).pin_memory()
+
+    def step(i):
+        eng.attack(x, y, EPS, ALPHA, PGD_STEPS, start="rng", seed=1234 + i, image_index0=idx0, out=adv)
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for i in range(args.warmup):
+        step(i)
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    launches = eng.launch_count - l0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end through the public API: pinned host -> device, attack, adversarial images -> host ----
+    def e2e_step(i):
+        xd = x_host.to(dev, non_blocking=True)
+        yd = y_host.to(dev, non_blocking=True)
+        a = eng.attack(xd, yd, EPS, ALPHA, PGD_STEPS, start="rng", seed=1234 + i, image_index0=idx0, out=adv)
+        adv_host.copy_(a, non_blocking=True)
+
+    e2e_step(0)
+    sync_all()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(args.steps):
+        e2e_step(i)
+    f1.record()
+    sync_all()
+    ms_e2e = f0.elapsed_time(f1)
+
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)  # max over ranks, device-timed
+    ms, ms_e2e = float(t[0]), float(t[1])
+
+    # ---- robust accuracy: the one real exchange of the path (3 x int64 all-reduce over NCCL / NVLink) ----
+    y_clean = eng.logits(x).argmax(-1)  # self-labels so clean accuracy is 100 % and the number is informative
+    step(0)
+    eng.attack(x, y_clean, EPS, ALPHA, PGD_STEPS, start="rng", seed=99, image_index0=idx0, out=adv)
+    c = eng.count_correct(x, y_clean)
+    r = eng.count_correct(adv, y_clean)
+    counts = allreduce_counts(torch.stack([c[0], r[0], c[1]]))
+    linf = float((adv - x).abs().max())
+
+    # ---- roofline leg: one profiled step (events around every launch, outside the timed region) ----
+    prof = None
+    if rank == 0:
+        torch.cuda.synchronize(dev)
+        eng.profile_begin()
+        step(0)
+        prof = eng.profile_end()
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    peaks, peaks_kind = measured_peaks()
+    imgs = batch * world * args.steps
+    value = imgs / (ms / 1e3)
+    gemm = prof["gemm_tc05"]
+    gemm_tflops = gemm["flops"] / (gemm["ms"] / 1e3) / 1e12
+    peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
+    total_prof_ms = sum(v["ms"] for v in prof.values())
+    gflop_img = algorithmic_gflop_per_image_step() * PGD_STEPS
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "PGD-10 eps=8/255 alpha=2/255 random-start on LoRA(r=8; q,k,v,proj,fc1,fc2) ViT-B/16, "
+                               "21 classes, batch 256 per GPU, 224x224 (BASELINE configs[1])",
+                   "global_batch": batch * world, "parallelism": f"dp{world} (independent images, no data-path collective)",
+                   "l2": "inputs larger than L2 (154 MB images, ~11 GB activations per step)"},
+        "clocks": clocks,
+        "e2e": {"value": imgs / (ms_e2e / 1e3), "unit": UNIT,
+                "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8, "d2h_bytes_per_step": adv_host.numel() * 4},
+        "gpu_launches": launches,
+        "roofline": {"bound": "tensor", "achieved": gemm_tflops, "peak": peak, "unit": "TFLOP/s",
+                     "frac": gemm_tflops / peak, "traffic": None,
+                     "kernel": "gemm_tc05_kernel (all main GEMM launches of one PGD-10 step, CUDA events per launch)",
+                     "peak_kind": f"{peaks_kind} sustained cuBLAS bf16",
+                     "kernel_share_of_step": gemm["ms"] / total_prof_ms,
+                     "whole_step_tensor_frac": value / world * gflop_img * 1e9 / 1e12 / peak},
+        "breakdown_ms_per_step": {k: round(v["ms"], 3) for k, v in prof.items()},
+        "breakdown_launches": {k: v["launches"] for k, v in prof.items()},
+        "robust": {"clean_correct": int(counts[0]), "robust_correct": int(counts[1]), "total": int(counts[2]),
+                   "linf": linf, "eps_f32": float(torch.tensor(EPS, dtype=torch.float32))},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        base, _ = cpu_reference_run(steps=1, warmup=0, sample_batch=4)
+        line["cpu_baseline"] = base
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH, help="images per GPU (BASELINE: 256)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "engine":
+        args.warmup = 3  # timing rules: W >= 3
+    if args.impl == "reference":
+        return run_reference(args)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun (the driver launches torchrun itself)
+        import socket
+
+        s = socket.socket()
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+        s.close()
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    return run_engine(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -2,7 +2,7 @@
 // for B200 HBM, per-batch GEMM plans (TMA descriptors), and the forward / input-gradient / PGD drivers.
 //
 // HBM layout (M = batch * 197 tokens, all bf16 unless noted):
-//   saved for backward, per layer l : h_in[l] [M,768], h_mid[l] [M,768], qkv[l] [M,2304], u[l] [M,3072],
+//   saved for backward, per layer l : h_in[l] [M,768], h_mid[l] [M,768], qkv[l] [M,2304], u[l] = gelu'(fc1) [M,3072],
 //                                     stats1[l], stats2[l] float2[M]          (~13.8 KB / token / layer)
 //   transient scratch               : cols [M,768] (normalised im2col), xn [M,768] (LN out), ao [M,768]
 //                                     (attention out), g [M,3072] (GELU out), T [M,192] (LoRA x*A^T),
@@ -149,7 +149,7 @@ static int build_plans(vitatk_engine* e, int batch, PlanSet** out) {
       return 1;
     {
       GemmEpilogue ep = {EPI_GELU_DUAL, w.fc1_b, nullptr, 0, nullptr, 0};
-      if (gemm_plan_init(&p.fc1, M, F, D, e->xn, D, w.fc1_w, D, e->u[l], F, e->g, F, e->T, 3 * LORA_PAD, s1.lb_fwd,
+      if (gemm_plan_init(&p.fc1, M, F, D, e->xn, D, w.fc1_w, D, e->g, F, e->u[l], F, e->T, 3 * LORA_PAD, s1.lb_fwd,
                          LORA_PAD, s1.rank > 0 ? 1 : 0, lora_ksteps(s1.rank), 0, ep))
         return 1;
     }
@@ -171,7 +171,7 @@ static int build_plans(vitatk_engine* e, int batch, PlanSet** out) {
                        nullptr, 0, 0, 0, 0, plain))
       return 1;
     {
-      GemmEpilogue ep = {EPI_DGELU, nullptr, e->u[l], F, nullptr, 0};
+      GemmEpilogue ep = {EPI_MUL, nullptr, e->u[l], F, nullptr, 0};
       if (gemm_plan_init(&p.bfc2, M, F, D, e->dh_a, D, w.fc2_wt, D, e->du, F, nullptr, 0, e->T, 3 * LORA_PAD, s2.la_bwd,
                          LORA_PAD, s2.rank > 0 ? 1 : 0, lora_ksteps(s2.rank), 0, ep))
         return 1;
@@ -274,7 +274,7 @@ static int encoder_backward(vitatk_engine* e, PlanSet* ps, int batch, cudaStream
     const LayerWeights& w = e->lw[l];
     LayerPlans& p = ps->layers[l];
     if (w.lora[VITATK_SITE_FC2].rank > 0) RUN_GEMM_T(&p.bt_fc2);
-    RUN_GEMM(&p.bfc2);  // du = (dh W2 + lora) * gelu'(u)
+    RUN_GEMM(&p.bfc2);  // du = (dh W2 + lora) * gelu'(u)   (u[l] holds gelu'(u), written by fc1's epilogue)
     if (w.lora[VITATK_SITE_FC1].rank > 0) RUN_GEMM_T(&p.bt_fc1);
     RUN_GEMM(&p.bfc1);  // dxn = du W1 + lora
     RUNC(CAT_LN, 0, layernorm_bwd(e->dxn, e->h_mid[l], e->st2[l], w.ln2_g, e->dh_a, e->dh_b, M, D, s));  // dh_mid

@@ -7,10 +7,12 @@
 // 290-298,305-311) plus the peft LoRA branch configured at train_loras.py:79-95, forward and
 // input-gradient backward (dX = dY*W + s*(dY*B)*A).
 //
-// Structure (one CTA per SM, 192 threads):
-//   warps 0-3 : epilogue   TMEM -> registers (tcgen05.ld) -> fused math -> swizzled smem -> TMA store
-//   warp  4   : TMA producer (cp.async.bulk.tensor, 128B swizzle, mbarrier complete_tx); owns TMEM alloc
-//   warp  5   : MMA issuer   (one thread, tcgen05.mma cta_group::1 kind::f16, M=128 N=BN K=16)
+// Structure (one CTA per SM, 320 threads):
+//   warps 0-7 : epilogue   TMEM -> registers (tcgen05.ld) -> fused math -> swizzled smem -> TMA store
+//               (two warps per TMEM lane quarter, each taking one column half of the tile; residual /
+//               multiplier rows are software-pipelined one 32-column chunk ahead in registers)
+//   warp  8   : TMA producer (cp.async.bulk.tensor, 128B swizzle, mbarrier complete_tx); owns TMEM alloc
+//   warp  9   : MMA issuer   (one thread, tcgen05.mma cta_group::1 kind::f16, M=128 N=BN K=16)
 // Pipelines: smem ring full/empty (TMA <-> MMA), TMEM accumulator double buffer full/empty
 // (MMA <-> epilogue), static persistent tile scheduler (tile = blockIdx.x + i*gridDim.x).
 #include <stdarg.h>
@@ -23,9 +25,12 @@ namespace vitatk {
 
 static constexpr int BM = 128;
 static constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
-static constexpr int NUM_EPI_WARPS = 4;
-static constexpr int GEMM_THREADS = 192;
-static constexpr int STAGE_OUT_BYTES = 32 * 128;  // one warp's 32-row x 64-col bf16 store tile
+static constexpr int NUM_EPI_WARPS = 8;
+static constexpr int TMA_WARP = 8;
+static constexpr int MMA_WARP = 9;
+static constexpr int GEMM_THREADS = 320;
+static constexpr int CHUNK = 32;                  // epilogue column granule = one tcgen05.ld.32x32b.x32
+static constexpr int STAGE_OUT_BYTES = 32 * 64;   // one warp's 32-row x 32-col bf16 store tile (64 B swizzle)
 
 template <int BN>
 struct GemmCfg {
@@ -45,10 +50,28 @@ struct GemmKernelArgs {
   GemmEpilogue epi;
 };
 
+// Exact-erf GELU and its derivative from ONE exponential and ONE reciprocal (Abramowitz-Stegun 7.1.26,
+// |erf error| < 1.5e-7, far below the bf16 output resolution):
+//   x = |u|/sqrt2, t = 1/(1+p x), e = exp(-x^2) = exp(-u^2/2), erfc(x) = poly(t) e
+//   Phi(u) = u<0 ? erfc/2 : 1 - erfc/2 ;  gelu = u Phi ;  gelu' = Phi + u e / sqrt(2 pi)
+__device__ __forceinline__ void gelu_and_grad(float u, float& g, float& d) {
+  const float ax = fabsf(u) * 0.70710678118654752f;
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * ax * ax));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float half_erfc = 0.5f * p * t * e;
+  const float phi = u < 0.f ? half_erfc : 1.0f - half_erfc;
+  g = u * phi;
+  d = fmaf(u * e, 0.3989422804014327f, phi);
+}
 __device__ __forceinline__ float gelu_exact(float u) { return 0.5f * u * (1.0f + erff(u * 0.70710678118654752f)); }
 __device__ __forceinline__ float gelu_grad(float u) {
   const float cdf = 0.5f * (1.0f + erff(u * 0.70710678118654752f));
-  const float pdf = 0.3989422804014327f * __expf(-0.5f * u * u);
+  const float pdf = 0.3989422804014327f * expf(-0.5f * u * u);
   return cdf + u * pdf;
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -62,6 +85,27 @@ __device__ __forceinline__ void unpack_bf16x8(const uint4& q, float* f) {
     float2 t = __bfloat1622float2(p[i]);
     f[2 * i] = t.x;
     f[2 * i + 1] = t.y;
+  }
+}
+// one warp: 32 rows x 32 bf16 columns from registers -> 64B-swizzled smem tile -> TMA store
+__device__ __forceinline__ void stage_and_store(uint8_t* stage, const uint32_t (&src)[16], const CUtensorMap* tm, int c0,
+                                                int c1, int lane) {
+  if (lane == 0) ptx::tma_store_wait_read<1>();  // the buffer used two stores ago has been read out
+  __syncwarp();
+  const uint32_t row_base = ptx::smem_u32(stage) + lane * 64;
+  const uint32_t sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t addr = row_base + ((j ^ sw) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(src[4 * j]), "r"(src[4 * j + 1]),
+                 "r"(src[4 * j + 2]), "r"(src[4 * j + 3])
+                 : "memory");
+  }
+  ptx::fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    ptx::tma_store_2d(tm, stage, c0, c1);
+    ptx::tma_store_commit();
   }
 }
 
@@ -94,7 +138,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int main_kb = args.K / BK;
   const int num_kb = main_kb + args.lora_nkb;
 
-  if (warp == 5 && lane == 0) {
+  if (warp == MMA_WARP && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
@@ -105,7 +149,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     ptx::fence_mbar_init();
   }
-  if (warp == 4) {
+  if (warp == TMA_WARP) {
     if (lane == 0) {
       ptx::prefetch_tmap(&tmA);
       ptx::prefetch_tmap(&tmB);
@@ -123,7 +167,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == TMA_WARP) {
     // ================================= TMA producer =================================
     if (lane == 0) {
       uint32_t cnt = 0;
@@ -149,7 +193,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == MMA_WARP) {
     // ================================= MMA issuer =================================
     if (lane == 0) {
       constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN);
@@ -181,11 +225,30 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else {
-    // ================================= epilogue warps 0..3 =================================
+    // ================================= epilogue warps 0..7 =================================
+    // warp w owns TMEM lanes 32*(w%4).. (hardware rule) and column half w/4 of every tile.
+    const int q = warp & 3;
+    const int hsel = warp >> 2;
+    constexpr int CPW = BN / (2 * CHUNK);  // 32-column chunks per warp per tile
     uint8_t* my_out = smem_out + warp * 2 * STAGE_OUT_BYTES;
     const GemmEpilogue epi = args.epi;
+    const bool has_aux = (epi.mode == EPI_RESIDUAL || epi.mode == EPI_MUL);
     uint32_t it = 0;
     uint32_t store_idx = 0;
+    uint4 aux_next[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) aux_next[i] = make_uint4(0, 0, 0, 0);
+    // prefetch the aux (residual / multiplier) rows of the first chunk before the accumulator is ready
+    if (has_aux && static_cast<int>(blockIdx.x) < num_tiles) {
+      const int m0 = (blockIdx.x / tiles_n) * BM, n0 = (blockIdx.x % tiles_n) * BN;
+      const int row = m0 + q * 32 + lane;
+      if (row < args.M) {
+        const uint4* rp = reinterpret_cast<const uint4*>(epi.res + static_cast<size_t>(row) * epi.ld_res + n0 +
+                                                         hsel * CPW * CHUNK);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) aux_next[i] = __ldg(rp + i);
+      }
+    }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m0 = (tile / tiles_n) * BM;
       const int n0 = (tile % tiles_n) * BN;
@@ -193,94 +256,95 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t use = it >> 1;
       ptx::mbar_wait(&tmem_full[buf], use & 1);
       ptx::tc_fence_after();
-      const int row = m0 + warp * 32 + lane;
+      const int row = m0 + q * 32 + lane;
       const bool row_ok = row < args.M;
-      const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + buf * BN;
+      const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN;
 
 #pragma unroll 1
-      for (int c = 0; c < BN / 64; ++c) {
-        uint32_t packed[32];   // 64 bf16 of the primary output
-        uint32_t packed2[32];  // 64 bf16 of the secondary output (GELU_DUAL only)
+      for (int i = 0; i < CPW; ++i) {
+        const int c = hsel * CPW + i;
+        const int ncol = n0 + c * CHUNK;
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(taddr_row + c * CHUNK, r);
+        uint4 aux[4];
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32b_x32(taddr_row + c * 64 + half * 32, r);
-          ptx::tmem_ld_wait();
-          const int ncol = n0 + c * 64 + half * 32;
-          float v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-          if (epi.bias != nullptr) {
-            const float4* bp = reinterpret_cast<const float4*>(epi.bias + ncol);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 b = __ldg(bp + i);
-              v[4 * i] += b.x;
-              v[4 * i + 1] += b.y;
-              v[4 * i + 2] += b.z;
-              v[4 * i + 3] += b.w;
-            }
+        for (int j = 0; j < 4; ++j) aux[j] = aux_next[j];
+        if (has_aux) {
+          // software pipeline: fetch the next chunk's aux rows (possibly of the next tile) while this one computes
+          int nrow = row, ncol_next = ncol + CHUNK;
+          bool ok = row_ok;
+          if (i + 1 == CPW) {
+            const int nt = tile + gridDim.x;
+            ok = nt < num_tiles;
+            nrow = (nt / tiles_n) * BM + q * 32 + lane;
+            ncol_next = (nt % tiles_n) * BN + hsel * CPW * CHUNK;
+            ok = ok && nrow < args.M;
           }
-          if (epi.mode == EPI_RESIDUAL || epi.mode == EPI_DGELU) {
-            if (row_ok) {
-              const uint4* rp = reinterpret_cast<const uint4*>(epi.res + static_cast<size_t>(row) * epi.ld_res + ncol);
+          if (ok) {
+            const uint4* rp = reinterpret_cast<const uint4*>(epi.res + static_cast<size_t>(nrow) * epi.ld_res + ncol_next);
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const uint4 q = __ldg(rp + i);
-                float f[8];
-                unpack_bf16x8(q, f);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  if (epi.mode == EPI_RESIDUAL) v[8 * i + j] += f[j];
-                  else v[8 * i + j] *= gelu_grad(f[j]);
-                }
-              }
-            }
-          } else if (epi.mode == EPI_ROWTABLE) {
-            if (row_ok) {
-              const float4* tp = reinterpret_cast<const float4*>(
-                  epi.table + static_cast<size_t>(row % epi.table_rows) * args.N + ncol);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float4 b = __ldg(tp + i);
-                v[4 * i] += b.x;
-                v[4 * i + 1] += b.y;
-                v[4 * i + 2] += b.z;
-                v[4 * i + 3] += b.w;
-              }
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < 16; ++i) packed[half * 16 + i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
-          if (epi.mode == EPI_GELU_DUAL) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              packed2[half * 16 + i] = pack_bf16x2(gelu_exact(v[2 * i]), gelu_exact(v[2 * i + 1]));
+            for (int j = 0; j < 4; ++j) aux_next[j] = __ldg(rp + j);
           }
         }
-        // ---- registers -> swizzled smem -> TMA store (per-warp 32x64 tile, double buffered) ----
-        const int nstores = (epi.mode == EPI_GELU_DUAL) ? 2 : 1;
-        for (int o = 0; o < nstores; ++o) {
-          uint8_t* stage = my_out + (store_idx & 1) * STAGE_OUT_BYTES;
-          ++store_idx;
-          if (lane == 0) ptx::tma_store_wait_read<1>();  // the buffer used two stores ago is free
-          __syncwarp();
-          const uint32_t* src = (o == 0) ? packed : packed2;
-          const uint32_t row_base = ptx::smem_u32(stage) + lane * 128;
+        ptx::tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (epi.bias != nullptr) {
+          const float4* bp = reinterpret_cast<const float4*>(epi.bias + ncol);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const uint32_t addr = row_base + ((j ^ (lane & 7)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(src[4 * j]), "r"(src[4 * j + 1]),
-                         "r"(src[4 * j + 2]), "r"(src[4 * j + 3])
-                         : "memory");
-          }
-          ptx::fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            ptx::tma_store_2d(o == 0 ? &tmOut : &tmOut2, stage, n0 + c * 64, m0 + warp * 32);
-            ptx::tma_store_commit();
+            const float4 b = __ldg(bp + j);
+            v[4 * j] += b.x;
+            v[4 * j + 1] += b.y;
+            v[4 * j + 2] += b.z;
+            v[4 * j + 3] += b.w;
           }
         }
+        if (has_aux) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float f[8];
+            unpack_bf16x8(aux[j], f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              if (epi.mode == EPI_RESIDUAL) v[8 * j + k] += f[k];
+              else v[8 * j + k] *= f[k];
+            }
+          }
+        } else if (epi.mode == EPI_ROWTABLE) {
+          if (row_ok) {
+            const float4* tp = reinterpret_cast<const float4*>(
+                epi.table + static_cast<size_t>(row % epi.table_rows) * args.N + ncol);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = __ldg(tp + j);
+              v[4 * j] += b.x;
+              v[4 * j + 1] += b.y;
+              v[4 * j + 2] += b.z;
+              v[4 * j + 3] += b.w;
+            }
+          }
+        }
+        uint32_t packed[16];
+        if (epi.mode == EPI_GELU_DUAL) {
+          uint32_t packed2[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float g0, d0, g1, d1;
+            gelu_and_grad(v[2 * j], g0, d0);
+            gelu_and_grad(v[2 * j + 1], g1, d1);
+            packed[j] = pack_bf16x2(g0, g1);
+            packed2[j] = pack_bf16x2(d0, d1);
+          }
+          stage_and_store(my_out + (store_idx & 1) * STAGE_OUT_BYTES, packed2, &tmOut2, ncol, m0 + q * 32, lane);
+          ++store_idx;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) packed[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+        }
+        stage_and_store(my_out + (store_idx & 1) * STAGE_OUT_BYTES, packed, &tmOut, ncol, m0 + q * 32, lane);
+        ++store_idx;
       }
       // all tcgen05.ld of this accumulator have completed (wait::ld above) -> hand it back to the MMA warp
       ptx::tc_fence_before();
@@ -293,7 +357,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == TMA_WARP) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
@@ -320,10 +384,14 @@ __global__ void gemm_simt_kernel(GemmKernelArgs args, const bf16* A, int lda, co
   const GemmEpilogue& e = args.epi;
   if (e.bias) acc += e.bias[n];
   if (e.mode == EPI_RESIDUAL) acc += __bfloat162float(e.res[(size_t)m * e.ld_res + n]);
-  if (e.mode == EPI_DGELU) acc *= gelu_grad(__bfloat162float(e.res[(size_t)m * e.ld_res + n]));
+  if (e.mode == EPI_MUL) acc *= __bfloat162float(e.res[(size_t)m * e.ld_res + n]);
   if (e.mode == EPI_ROWTABLE) acc += e.table[(size_t)(m % e.table_rows) * args.N + n];
-  out[(size_t)m * ldo + n] = __float2bfloat16(acc);
-  if (e.mode == EPI_GELU_DUAL) out2[(size_t)m * ldo2 + n] = __float2bfloat16(gelu_exact(acc));
+  if (e.mode == EPI_GELU_DUAL) {
+    out[(size_t)m * ldo + n] = __float2bfloat16(gelu_exact(acc));
+    out2[(size_t)m * ldo2 + n] = __float2bfloat16(gelu_grad(acc));
+  } else {
+    out[(size_t)m * ldo + n] = __float2bfloat16(acc);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -349,7 +417,7 @@ static EncodeTiledFn get_encode_fn() {
 
 // 2D bf16 row-major tensor [rows, cols] with leading dimension ld (elements); box = [box_cols, box_rows]
 static int make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
-                        uint32_t box_cols, uint32_t box_rows) {
+                        uint32_t box_cols, uint32_t box_rows, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return 1;
   if ((reinterpret_cast<uintptr_t>(base) & 15) || ((ld * 2) & 15)) {
@@ -361,7 +429,7 @@ static int make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box=%ux%u", (int)r,
@@ -392,9 +460,9 @@ int gemm_plan_init(GemmPlan* p, int M, int N, int K, const bf16* A, int lda, con
   }
   if (make_tmap_2d(&p->tmA, A, M, K, lda, BK, BM)) return 1;
   if (make_tmap_2d(&p->tmB, B, N, K, ldb, BK, p->BN)) return 1;
-  if (make_tmap_2d(&p->tmOut, out, M, N, ldo, 64, 32)) return 1;
+  if (make_tmap_2d(&p->tmOut, out, M, N, ldo, CHUNK, 32, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
   if (out2) {
-    if (make_tmap_2d(&p->tmOut2, out2, M, N, ldo2, 64, 32)) return 1;
+    if (make_tmap_2d(&p->tmOut2, out2, M, N, ldo2, CHUNK, 32, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
   } else {
     p->tmOut2 = p->tmOut;
   }

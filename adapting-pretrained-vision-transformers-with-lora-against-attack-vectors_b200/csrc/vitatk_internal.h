@@ -33,15 +33,15 @@ const char* last_error();
 enum EpiMode : int {
   EPI_PLAIN = 0,      // out = acc (+ bias)
   EPI_RESIDUAL = 1,   // out = acc + bias + res
-  EPI_GELU_DUAL = 2,  // out = u = acc + bias ; out2 = gelu(u)          (fc1 forward)
-  EPI_DGELU = 3,      // out = acc * gelu'(res)                          (fc2 backward -> dU)
+  EPI_GELU_DUAL = 2,  // u = acc + bias ; out = gelu(u) ; out2 = gelu'(u)   (fc1 forward; gelu' is what backward needs)
+  EPI_MUL = 3,        // out = acc * res                                  (fc2 backward: dU = dG * gelu'(u))
   EPI_ROWTABLE = 4    // out = acc + table[m % table_rows][n]            (patch embed: bias+pos / cls+pos)
 };
 
 struct GemmEpilogue {
   int mode;
   const float* bias;    // [N] fp32 or null
-  const bf16* res;      // [M, ld_res] residual (EPI_RESIDUAL) or saved pre-activation (EPI_DGELU)
+  const bf16* res;      // [M, ld_res] residual (EPI_RESIDUAL) or saved gelu'(u) multiplier (EPI_MUL)
   int ld_res;
   const float* table;   // [table_rows, N] fp32 (EPI_ROWTABLE)
   int table_rows;

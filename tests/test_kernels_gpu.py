@@ -7,7 +7,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-EPI_PLAIN, EPI_RESIDUAL, EPI_GELU_DUAL, EPI_DGELU, EPI_ROWTABLE = 0, 1, 2, 3, 4
+EPI_PLAIN, EPI_RESIDUAL, EPI_GELU_DUAL, EPI_MUL, EPI_ROWTABLE = 0, 1, 2, 3, 4
 
 
 def _s():
@@ -61,13 +61,13 @@ def ref_gemm(A, B, epi, bias, res, table, T, LB, nkb, ksteps, group_cols):
     out2 = None
     if epi == EPI_RESIDUAL:
         acc = acc + res.float()
-    elif epi == EPI_DGELU:
-        acc = acc * _dgelu(res.float())
+    elif epi == EPI_MUL:
+        acc = acc * res.float()
     elif epi == EPI_ROWTABLE:
         rows = torch.arange(A.shape[0], device=A.device) % table.shape[0]
         acc = acc + table[rows]
     elif epi == EPI_GELU_DUAL:
-        out2 = _gelu(acc)
+        acc, out2 = _gelu(acc), _dgelu(acc)
     return acc, out2
 
 
@@ -98,13 +98,16 @@ GEMM_CASES = [
     (1576, 768, 768, EPI_RESIDUAL, (1, 8, 0)),    # proj forward
     (1576, 3072, 768, EPI_GELU_DUAL, (1, 16, 0)),  # fc1 forward
     (1576, 768, 3072, EPI_RESIDUAL, (1, 32, 0)),  # fc2 forward
-    (1576, 3072, 768, EPI_DGELU, (1, 8, 0)),      # fc2 backward
+    (1576, 3072, 768, EPI_MUL, (1, 8, 0)),        # fc2 backward (dU = dG * gelu')
     (1576, 768, 2304, EPI_PLAIN, (3, 8, 0)),      # qkv backward: three extra k-blocks
     (1576, 768, 768, EPI_ROWTABLE, (0, 0, 0)),    # patch embed
     (1576, 192, 768, EPI_PLAIN, (0, 0, 0)),       # LoRA T = x A^T (BN = 64)
     (1576, 64, 3072, EPI_PLAIN, (0, 0, 0)),
     (197, 128, 128, EPI_PLAIN, (0, 0, 0)),        # BN = 128 path, single image
     (50432, 768, 768, EPI_RESIDUAL, (1, 8, 0)),   # full BASELINE size (256*197): many tiles per CTA
+    (50432, 3072, 768, EPI_GELU_DUAL, (1, 8, 0)),
+    (50432, 3072, 768, EPI_MUL, (1, 8, 0)),
+    (25216, 2304, 768, EPI_PLAIN, (1, 8, 768)),
 ]
 
 
@@ -115,7 +118,7 @@ def test_gemm_tc05_vs_torch(lib, M, N, K, epi, lora):
     A = rn(M, K).to(torch.bfloat16)
     B = (rn(N, K) / math.sqrt(K)).to(torch.bfloat16)
     bias = rn(N) * 0.1 if epi in (EPI_PLAIN, EPI_RESIDUAL, EPI_GELU_DUAL) and N != 192 else None
-    res = rn(M, N).to(torch.bfloat16) if epi in (EPI_RESIDUAL, EPI_DGELU) else None
+    res = rn(M, N).to(torch.bfloat16) if epi in (EPI_RESIDUAL, EPI_MUL) else None
     table = rn(197, N) if epi == EPI_ROWTABLE else None
     nkb, r, gc = lora
     T = LB = None
@@ -135,10 +138,12 @@ def test_gemm_tc05_vs_torch(lib, M, N, K, epi, lora):
     want, want2 = ref_gemm(A, B, epi, bias, res, table, T, LB, nkb, ksteps, gc)
     check_close(out, want, f"gemm {M}x{N}x{K} epi{epi}")
     if epi == EPI_GELU_DUAL:
-        check_close(out2, want2, "gelu output")
+        check_close(out2, want2, "gelu' output")
     if M <= 2000:  # cross-check with the scalar CUDA-core kernel (bit-level agreement is not expected)
         s_out, s_out2 = run_gemm(lib, A, B, epi, bias, res, table, T, LB, nkb, ksteps, gc, simt=True)
         check_close(s_out, want, "simt gemm")
+        if epi == EPI_GELU_DUAL:
+            check_close(s_out2, want2, "simt gelu'")
 
 
 def test_gemm_rejects_bad_shapes(lib):

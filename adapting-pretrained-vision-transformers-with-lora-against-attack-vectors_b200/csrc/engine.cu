@@ -57,6 +57,7 @@ struct PlanSet {
   int batch = 0;
   GemmPlan patch, bpatch;
   std::vector<LayerPlans> layers;
+  std::vector<AttnFwdPlan> attn_fwd;
 };
 
 }  // namespace vitatk
@@ -107,6 +108,7 @@ static int build_plans(vitatk_engine* e, int batch, PlanSet** out) {
   PlanSet* ps = new PlanSet();
   ps->batch = batch;
   ps->layers.resize(c.layers);
+  ps->attn_fwd.resize(c.layers);
   GemmEpilogue plain = {EPI_PLAIN, nullptr, nullptr, 0, nullptr, 0};
   // patch embedding: h[0] = cols * Wpe^T + table[m % 197]
   {
@@ -123,6 +125,7 @@ static int build_plans(vitatk_engine* e, int batch, PlanSet** out) {
     const LoraSite& s1 = w.lora[VITATK_SITE_FC1];
     const LoraSite& s2 = w.lora[VITATK_SITE_FC2];
     // ---------------- forward ----------------
+    if (attention_fwd_plan_init(&ps->attn_fwd[l], e->qkv[l], e->ao, nullptr, batch, TOKENS, c.heads)) return 1;
     if (sq.rank > 0 &&
         gemm_plan_init(&p.t_qkv, M, 3 * LORA_PAD, D, e->xn, D, sq.la_fwd, D, e->T, 3 * LORA_PAD, nullptr, 0, nullptr, 0,
                        nullptr, 0, 0, 0, 0, plain))
@@ -254,7 +257,7 @@ static int encoder_forward(vitatk_engine* e, PlanSet* ps, int batch, cudaStream_
     RUNC(CAT_LN, 0, layernorm_fwd(e->h[l], w.ln1_g, w.ln1_b, e->xn, e->st1[l], M, D, c.ln_eps, s));
     if (w.lora[VITATK_SITE_QKV].rank > 0) RUN_GEMM_T(&p.t_qkv);
     RUN_GEMM(&p.qkv);
-    RUNC(CAT_ATTN_FWD, 4.0 * batch * c.heads * TOKENS * TOKENS * 64, attention_fwd(e->qkv[l], e->ao, batch, TOKENS, c.heads, s));
+    RUNC(CAT_ATTN_FWD, 4.0 * batch * c.heads * TOKENS * TOKENS * 64, attention_fwd_tc05(&ps->attn_fwd[l], s));
     if (w.lora[VITATK_SITE_PROJ].rank > 0) RUN_GEMM_T(&p.t_proj);
     RUN_GEMM(&p.proj);
     RUNC(CAT_LN, 0, layernorm_fwd(e->h_mid[l], w.ln2_g, w.ln2_b, e->xn, e->st2[l], M, D, c.ln_eps, s));
@@ -650,6 +653,12 @@ int vitatk_k_gemm(int M, int N, int K, const void* A, int lda, const void* B, in
 int vitatk_k_attention_fwd(const void* qkv, void* out, int batch, int tokens, int heads, void* stream) {
   return attention_fwd(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), batch, tokens, heads,
                        static_cast<cudaStream_t>(stream));
+}
+int vitatk_k_attention_fwd_tc05(const void* qkv, void* out, float* lse2, int batch, int tokens, int heads, void* stream) {
+  AttnFwdPlan p;
+  if (attention_fwd_plan_init(&p, static_cast<const bf16*>(qkv), static_cast<bf16*>(out), lse2, batch, tokens, heads))
+    return 1;
+  return attention_fwd_tc05(&p, static_cast<cudaStream_t>(stream));
 }
 int vitatk_k_attention_bwd(const void* qkv, const void* dout, void* dqkv, int batch, int tokens, int heads,
                            void* stream) {

@@ -34,7 +34,7 @@ static constexpr int STAGE_OUT_BYTES = 32 * 64;   // one warp's 32-row x 32-col 
 
 template <int BN>
 struct GemmCfg {
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 192 ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -439,6 +439,31 @@ static int make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64
   return 0;
 }
 
+// 3D bf16 tensor [d2][d1][d0] (d0 contiguous) with byte strides s1 (between d1 rows) and s2 (between d2 slabs);
+// box = [b0, b1, 1], 128B swizzle, out-of-bounds elements read as zero.
+int make_tmap_3d(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1_bytes,
+                 uint64_t s2_bytes, uint32_t b0, uint32_t b1) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return 1;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (s1_bytes & 15) || (s2_bytes & 15)) {
+    set_error("tensor map 3d: base/strides not 16-byte aligned");
+    return 1;
+  }
+  cuuint64_t gdim[3] = {d0, d1, d2};
+  cuuint64_t gstride[2] = {s1_bytes, s2_bytes};
+  cuuint32_t box[3] = {b0, b1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(3d) failed (%d) dims=%llu,%llu,%llu box=%u,%u", (int)r, (unsigned long long)d0,
+              (unsigned long long)d1, (unsigned long long)d2, b0, b1);
+    return 1;
+  }
+  return 0;
+}
+
 int gemm_plan_init(GemmPlan* p, int M, int N, int K, const bf16* A, int lda, const bf16* B, int ldb, bf16* out,
                    int ldo, bf16* out2, int ldo2, const bf16* T, int ldt, const bf16* LB, int ldlb, int lora_nkb,
                    int lora_ksteps, int lora_group_cols, GemmEpilogue epi) {
@@ -449,7 +474,7 @@ int gemm_plan_init(GemmPlan* p, int M, int N, int K, const bf16* A, int lda, con
   p->M = M;
   p->N = N;
   p->K = K;
-  p->BN = (N % 256 == 0) ? 256 : (N % 128 == 0 ? 128 : 64);
+  p->BN = (N % 256 == 0) ? 256 : (N % 192 == 0 ? 192 : (N % 128 == 0 ? 128 : 64));
   p->lora_nkb = lora_nkb;
   p->lora_ksteps = lora_ksteps;
   p->lora_group_cols = lora_group_cols;
@@ -505,6 +530,7 @@ static int launch_bn(const GemmPlan* p, cudaStream_t stream, int num_sms) {
 int gemm_launch(const GemmPlan* p, cudaStream_t stream, int num_sms) {
   switch (p->BN) {
     case 256: return launch_bn<256>(p, stream, num_sms);
+    case 192: return launch_bn<192>(p, stream, num_sms);
     case 128: return launch_bn<128>(p, stream, num_sms);
     case 64: return launch_bn<64>(p, stream, num_sms);
   }

@@ -68,9 +68,23 @@ int gemm_launch(const GemmPlan* p, cudaStream_t stream, int num_sms);
 int gemm_launch_simt(const GemmPlan* p, const bf16* A, int lda, const bf16* B, int ldb, bf16* out, int ldo,
                      bf16* out2, int ldo2, const bf16* T, int ldt, const bf16* LB, int ldlb, cudaStream_t stream);
 
+int make_tmap_3d(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1_bytes,
+                 uint64_t s2_bytes, uint32_t b0, uint32_t b1);
+
 // ---------------------------------------------------------------------------------------------
 // attention (softmax(QK^T/sqrt(d))V per (image, head)), qkv packed [M, 3*D] token-major
 // ---------------------------------------------------------------------------------------------
+// tcgen05 forward: S = QK^T and O = PV on the 5th-gen tensor cores, P kept in TMEM as the A operand.
+struct AttnFwdPlan {
+  int batch, tokens, heads;
+  const bf16* qkv;
+  bf16* out;
+  float* lse2;  // [batch*heads, 208] log2-domain logsumexp per query (for the backward), may be null
+  CUtensorMap tmQ, tmKV;
+};
+int attention_fwd_plan_init(AttnFwdPlan* p, const bf16* qkv, bf16* out, float* lse2, int batch, int tokens, int heads);
+int attention_fwd_tc05(const AttnFwdPlan* p, cudaStream_t stream);
+// mma.sync forward (round-1 first version, kept for cross-checking the tcgen05 kernel in tests)
 int attention_fwd(const bf16* qkv, bf16* out, int batch, int tokens, int heads, cudaStream_t stream);
 int attention_bwd(const bf16* qkv, const bf16* dout, bf16* dqkv, int batch, int tokens, int heads,
                   cudaStream_t stream);

@@ -141,6 +141,9 @@ int vitatk_k_gemm(int M, int N, int K, const void* A_dev, int lda, const void* B
                   const void* res_dev, int ld_res, const float* table_dev, int table_rows, int use_simt,
                   void* stream);
 int vitatk_k_attention_fwd(const void* qkv_dev, void* out_dev, int batch, int tokens, int heads, void* stream);
+/* tcgen05 forward (the engine's path); lse2_dev (optional) receives [batch*heads, 208] log2-domain logsumexp */
+int vitatk_k_attention_fwd_tc05(const void* qkv_dev, void* out_dev, float* lse2_dev, int batch, int tokens, int heads,
+                                void* stream);
 int vitatk_k_attention_bwd(const void* qkv_dev, const void* dout_dev, void* dqkv_dev, int batch, int tokens,
                            int heads, void* stream);
 int vitatk_k_layernorm_fwd(const void* x_dev, const float* gamma_dev, const float* beta_dev, void* y_dev,

@@ -155,7 +155,7 @@ def test_gemm_rejects_bad_shapes(lib):
         run_gemm(lib, A, B)
 
 
-@pytest.mark.parametrize("batch,tokens", [(1, 197), (3, 197), (2, 50), (1, 208), (2, 1)])
+@pytest.mark.parametrize("batch,tokens", [(1, 197), (3, 197), (2, 50), (1, 208), (2, 1), (2, 128), (64, 197)])
 def test_attention_fwd_bwd_vs_torch(lib, batch, tokens):
     from vitatk import _lib
 
@@ -165,7 +165,10 @@ def test_attention_fwd_bwd_vs_torch(lib, batch, tokens):
     dout = torch.randn(batch * tokens, D, device="cuda", generator=g).to(torch.bfloat16)
     out = torch.full((batch * tokens, D), float("nan"), device="cuda", dtype=torch.bfloat16)
     dqkv = torch.full((batch * tokens, 3 * D), float("nan"), device="cuda", dtype=torch.bfloat16)
+    out_tc = torch.full((batch * tokens, D), float("nan"), device="cuda", dtype=torch.bfloat16)
+    lse2 = torch.zeros(batch * heads, 208, device="cuda")
     _lib.check(lib.vitatk_k_attention_fwd(_p(qkv), _p(out), batch, tokens, heads, _s()), "attention_fwd")
+    _lib.check(lib.vitatk_k_attention_fwd_tc05(_p(qkv), _p(out_tc), _p(lse2), batch, tokens, heads, _s()), "attention_fwd_tc05")
     _lib.check(lib.vitatk_k_attention_bwd(_p(qkv), _p(dout), _p(dqkv), batch, tokens, heads, _s()), "attention_bwd")
     torch.cuda.synchronize()
     x = qkv.float().reshape(batch, tokens, 3, heads, 64).permute(2, 0, 3, 1, 4).requires_grad_(True)  # [3,B,H,T,d]
@@ -176,6 +179,10 @@ def test_attention_fwd_bwd_vs_torch(lib, batch, tokens):
     gref = gx.permute(1, 3, 0, 2, 4).reshape(batch * tokens, 3 * D)
     # probabilities and dS are rounded to bf16 before the second GEMM of each chain (fp32 accumulate)
     check_rel(out, o.detach(), "attention out", 8e-3, 2e-2)
+    check_rel(out_tc, o.detach(), "attention out (tcgen05)", 8e-3, 2e-2)
+    s_ref = (q @ k.transpose(-1, -2) / 8.0).detach()
+    lse_ref = torch.logsumexp(s_ref, -1).reshape(batch * heads, tokens) * 1.4426950408889634
+    torch.testing.assert_close(lse2[:, :tokens], lse_ref, rtol=1e-3, atol=2e-3)
     check_rel(dqkv, gref, "attention dqkv", 1.5e-2, 3e-2)
 
 

@@ -77,6 +77,7 @@ EXPORTS = [
     "vitatk_attack", "vitatk_count_correct", "vitatk_launch_count", "vitatk_k_gemm", "vitatk_k_attention_fwd",
     "vitatk_k_attention_bwd", "vitatk_k_layernorm_fwd", "vitatk_k_layernorm_bwd", "vitatk_k_pgd_update",
     "vitatk_k_pgd_init", "vitatk_profile_begin", "vitatk_profile_end", "vitatk_k_attention_fwd_tc05",
+    "vitatk_k_attention_bwd_tc05",
 ]
 
 
@@ -123,6 +124,7 @@ def load() -> C.CDLL:
     lib.vitatk_k_gemm.argtypes = [i, i, i, vp, i, vp, i, vp, i, vp, i, vp, i, vp, i, i, i, i, i, vp, vp, i, vp, i, i, vp]
     lib.vitatk_k_attention_fwd.argtypes = [vp, vp, i, i, i, vp]
     lib.vitatk_k_attention_fwd_tc05.argtypes = [vp, vp, vp, i, i, i, vp]
+    lib.vitatk_k_attention_bwd_tc05.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, vp]
     lib.vitatk_k_attention_bwd.argtypes = [vp, vp, vp, i, i, i, vp]
     lib.vitatk_k_layernorm_fwd.argtypes = [vp, vp, vp, vp, vp, i, i, f, vp]
     lib.vitatk_k_layernorm_bwd.argtypes = [vp, vp, vp, vp, vp, vp, i, i, vp]

@@ -4,8 +4,8 @@
 // HBM layout (M = batch * 197 tokens, all bf16 unless noted):
 //   saved for backward, per layer l : h_in[l] [M,768], h_mid[l] [M,768], qkv[l] [M,2304], u[l] = gelu'(fc1) [M,3072],
 //                                     stats1[l], stats2[l] float2[M]          (~13.8 KB / token / layer)
-//   transient scratch               : cols [M,768] (normalised im2col), xn [M,768] (LN out), ao [M,768]
-//                                     (attention out), g [M,3072] (GELU out), T [M,192] (LoRA x*A^T),
+//                                     ao[l] [M,768] (attention out), lse2[l] float[B*12*208]
+//   transient scratch               : cols [M,768] (normalised im2col), xn [M,768] (LN out), g [M,3072] (GELU out), T [M,192] (LoRA x*A^T),
 //                                     dh_a/dh_b [M,768], du [M,3072], dxn [M,768], dao [M,768], dqkv [M,2304]
 // No weight gradients exist on this path (autograd.grad w.r.t. the input only), so GEMM inputs are never
 // saved for dW; only what LN / GELU / softmax need for their Jacobians is kept.
@@ -58,6 +58,7 @@ struct PlanSet {
   GemmPlan patch, bpatch;
   std::vector<LayerPlans> layers;
   std::vector<AttnFwdPlan> attn_fwd;
+  std::vector<AttnBwdPlan> attn_bwd;
 };
 
 }  // namespace vitatk
@@ -80,7 +81,10 @@ struct vitatk_engine {
   std::vector<bf16*> qkv;    // [layers]
   std::vector<bf16*> u;      // [layers]
   std::vector<float2*> st1, st2;
-  bf16 *cols = nullptr, *xn = nullptr, *ao = nullptr, *g = nullptr, *T = nullptr;
+  std::vector<bf16*> ao;     // [layers] attention output (saved: delta = rowsum(dO o O) in the backward)
+  std::vector<float*> lse2;  // [layers] log2-domain logsumexp per (image, head, query)
+  float* delta = nullptr;
+  bf16 *cols = nullptr, *xn = nullptr, *g = nullptr, *T = nullptr;
   bf16 *dh_a = nullptr, *dh_b = nullptr, *du = nullptr, *dxn = nullptr, *dao = nullptr, *dqkv = nullptr;
   float *logits = nullptr, *loss = nullptr, *scratch_img = nullptr;
   std::map<int, PlanSet*> plans;
@@ -109,6 +113,7 @@ static int build_plans(vitatk_engine* e, int batch, PlanSet** out) {
   ps->batch = batch;
   ps->layers.resize(c.layers);
   ps->attn_fwd.resize(c.layers);
+  ps->attn_bwd.resize(c.layers);
   GemmEpilogue plain = {EPI_PLAIN, nullptr, nullptr, 0, nullptr, 0};
   // patch embedding: h[0] = cols * Wpe^T + table[m % 197]
   {
@@ -125,7 +130,10 @@ static int build_plans(vitatk_engine* e, int batch, PlanSet** out) {
     const LoraSite& s1 = w.lora[VITATK_SITE_FC1];
     const LoraSite& s2 = w.lora[VITATK_SITE_FC2];
     // ---------------- forward ----------------
-    if (attention_fwd_plan_init(&ps->attn_fwd[l], e->qkv[l], e->ao, nullptr, batch, TOKENS, c.heads)) return 1;
+    if (attention_fwd_plan_init(&ps->attn_fwd[l], e->qkv[l], e->ao[l], e->lse2[l], batch, TOKENS, c.heads)) return 1;
+    if (attention_bwd_plan_init(&ps->attn_bwd[l], e->qkv[l], e->dao, e->ao[l], e->lse2[l], e->delta, e->dqkv, batch,
+                                TOKENS, c.heads))
+      return 1;
     if (sq.rank > 0 &&
         gemm_plan_init(&p.t_qkv, M, 3 * LORA_PAD, D, e->xn, D, sq.la_fwd, D, e->T, 3 * LORA_PAD, nullptr, 0, nullptr, 0,
                        nullptr, 0, 0, 0, 0, plain))
@@ -137,12 +145,12 @@ static int build_plans(vitatk_engine* e, int batch, PlanSet** out) {
         return 1;
     }
     if (sp.rank > 0 &&
-        gemm_plan_init(&p.t_proj, M, LORA_PAD, D, e->ao, D, sp.la_fwd, D, e->T, 3 * LORA_PAD, nullptr, 0, nullptr, 0,
+        gemm_plan_init(&p.t_proj, M, LORA_PAD, D, e->ao[l], D, sp.la_fwd, D, e->T, 3 * LORA_PAD, nullptr, 0, nullptr, 0,
                        nullptr, 0, 0, 0, 0, plain))
       return 1;
     {
       GemmEpilogue ep = {EPI_RESIDUAL, w.proj_b, e->h[l], D, nullptr, 0};
-      if (gemm_plan_init(&p.proj, M, D, D, e->ao, D, w.proj_w, D, e->h_mid[l], D, nullptr, 0, e->T, 3 * LORA_PAD,
+      if (gemm_plan_init(&p.proj, M, D, D, e->ao[l], D, w.proj_w, D, e->h_mid[l], D, nullptr, 0, e->T, 3 * LORA_PAD,
                          sp.lb_fwd, LORA_PAD, sp.rank > 0 ? 1 : 0, lora_ksteps(sp.rank), 0, ep))
         return 1;
     }
@@ -283,7 +291,7 @@ static int encoder_backward(vitatk_engine* e, PlanSet* ps, int batch, cudaStream
     RUNC(CAT_LN, 0, layernorm_bwd(e->dxn, e->h_mid[l], e->st2[l], w.ln2_g, e->dh_a, e->dh_b, M, D, s));  // dh_mid
     if (w.lora[VITATK_SITE_PROJ].rank > 0) RUN_GEMM_T(&p.bt_proj);
     RUN_GEMM(&p.bproj);  // dao = dh_mid Wp + lora
-    RUNC(CAT_ATTN_BWD, 8.0 * batch * c.heads * TOKENS * TOKENS * 64, attention_bwd(e->qkv[l], e->dao, e->dqkv, batch, TOKENS, c.heads, s));
+    RUNC(CAT_ATTN_BWD, 8.0 * batch * c.heads * TOKENS * TOKENS * 64, attention_bwd_tc05(&ps->attn_bwd[l], s));
     if (w.lora[VITATK_SITE_QKV].rank > 0) RUN_GEMM_T(&p.bt_qkv);
     RUN_GEMM(&p.bqkv);  // dxn = dqkv Wqkv + lora
     RUNC(CAT_LN, 0, layernorm_bwd(e->dxn, e->h[l], e->st1[l], w.ln1_g, e->dh_b, e->dh_a, M, D, s));  // dh wrt h[l]
@@ -515,7 +523,9 @@ int vitatk_finalize(vitatk_engine* e) {
   long long total = 0;
   total += (c.layers + 1) * sz_d;                       // h
   total += c.layers * (sz_d + sz_3d + sz_f + 2 * sz_st);  // h_mid, qkv, u, stats
-  total += 3 * sz_d + sz_f + sz_t;                      // cols, xn, ao, g, T
+  const long long sz_lse = al(static_cast<long long>(c.max_batch) * c.heads * 208 * 4);
+  total += 2 * sz_d + sz_f + sz_t;                      // cols, xn, g, T
+  total += c.layers * (sz_d + sz_lse) + sz_lse;         // ao, lse2 per layer; delta
   total += 4 * sz_d + sz_f + sz_3d;                     // dh_a, dh_b, dxn, dao, du, dqkv
   total += al(static_cast<long long>(c.max_batch) * c.num_classes * 4) + al(c.max_batch * 4) + sz_img;
   VITATK_CUDA_OK(cudaMalloc(&e->ws, total));
@@ -533,6 +543,8 @@ int vitatk_finalize(vitatk_engine* e) {
   e->u.resize(c.layers);
   e->st1.resize(c.layers);
   e->st2.resize(c.layers);
+  e->ao.resize(c.layers);
+  e->lse2.resize(c.layers);
   for (int l = 0; l <= c.layers; ++l) e->h[l] = reinterpret_cast<bf16*>(take(sz_d));
   for (int l = 0; l < c.layers; ++l) {
     e->h_mid[l] = reinterpret_cast<bf16*>(take(sz_d));
@@ -540,10 +552,12 @@ int vitatk_finalize(vitatk_engine* e) {
     e->u[l] = reinterpret_cast<bf16*>(take(sz_f));
     e->st1[l] = reinterpret_cast<float2*>(take(sz_st));
     e->st2[l] = reinterpret_cast<float2*>(take(sz_st));
+    e->ao[l] = reinterpret_cast<bf16*>(take(sz_d));
+    e->lse2[l] = reinterpret_cast<float*>(take(sz_lse));
   }
+  e->delta = reinterpret_cast<float*>(take(sz_lse));
   e->cols = reinterpret_cast<bf16*>(take(sz_d));
   e->xn = reinterpret_cast<bf16*>(take(sz_d));
-  e->ao = reinterpret_cast<bf16*>(take(sz_d));
   e->g = reinterpret_cast<bf16*>(take(sz_f));
   e->T = reinterpret_cast<bf16*>(take(sz_t));
   e->dh_a = reinterpret_cast<bf16*>(take(sz_d));
@@ -659,6 +673,14 @@ int vitatk_k_attention_fwd_tc05(const void* qkv, void* out, float* lse2, int bat
   if (attention_fwd_plan_init(&p, static_cast<const bf16*>(qkv), static_cast<bf16*>(out), lse2, batch, tokens, heads))
     return 1;
   return attention_fwd_tc05(&p, static_cast<cudaStream_t>(stream));
+}
+int vitatk_k_attention_bwd_tc05(const void* qkv, const void* dout, const void* o, const float* lse2, float* delta,
+                                void* dqkv, int batch, int tokens, int heads, void* stream) {
+  AttnBwdPlan p;
+  if (attention_bwd_plan_init(&p, static_cast<const bf16*>(qkv), static_cast<const bf16*>(dout),
+                              static_cast<const bf16*>(o), lse2, delta, static_cast<bf16*>(dqkv), batch, tokens, heads))
+    return 1;
+  return attention_bwd_tc05(&p, static_cast<cudaStream_t>(stream));
 }
 int vitatk_k_attention_bwd(const void* qkv, const void* dout, void* dqkv, int batch, int tokens, int heads,
                            void* stream) {

@@ -84,6 +84,18 @@ struct AttnFwdPlan {
 };
 int attention_fwd_plan_init(AttnFwdPlan* p, const bf16* qkv, bf16* out, float* lse2, int batch, int tokens, int heads);
 int attention_fwd_tc05(const AttnFwdPlan* p, cudaStream_t stream);
+// tcgen05 backward: dQ kernel (also produces delta) then dK/dV kernel; lse2 comes from the forward.
+struct AttnBwdPlan {
+  int batch, tokens, heads;
+  const bf16 *dout, *o;
+  const float* lse2;
+  float* delta;  // [batch*heads, 208] scratch
+  bf16* dqkv;
+  CUtensorMap tmQKV128, tmQKV208, tmDO128, tmDO208;
+};
+int attention_bwd_plan_init(AttnBwdPlan* p, const bf16* qkv, const bf16* dout, const bf16* o, const float* lse2,
+                            float* delta, bf16* dqkv, int batch, int tokens, int heads);
+int attention_bwd_tc05(const AttnBwdPlan* p, cudaStream_t stream);
 // mma.sync forward (round-1 first version, kept for cross-checking the tcgen05 kernel in tests)
 int attention_fwd(const bf16* qkv, bf16* out, int batch, int tokens, int heads, cudaStream_t stream);
 int attention_bwd(const bf16* qkv, const bf16* dout, bf16* dqkv, int batch, int tokens, int heads,

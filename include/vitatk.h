@@ -144,6 +144,10 @@ int vitatk_k_attention_fwd(const void* qkv_dev, void* out_dev, int batch, int to
 /* tcgen05 forward (the engine's path); lse2_dev (optional) receives [batch*heads, 208] log2-domain logsumexp */
 int vitatk_k_attention_fwd_tc05(const void* qkv_dev, void* out_dev, float* lse2_dev, int batch, int tokens, int heads,
                                 void* stream);
+/* tcgen05 backward (the engine's path): needs the forward's output o_dev and lse2_dev; delta_dev is a zero-
+ * initialised [batch*heads, 208] fp32 scratch; dqkv_dev [batch*tokens, 3*D] receives dq | dk | dv */
+int vitatk_k_attention_bwd_tc05(const void* qkv_dev, const void* dout_dev, const void* o_dev, const float* lse2_dev,
+                                float* delta_dev, void* dqkv_dev, int batch, int tokens, int heads, void* stream);
 int vitatk_k_attention_bwd(const void* qkv_dev, const void* dout_dev, void* dqkv_dev, int batch, int tokens,
                            int heads, void* stream);
 int vitatk_k_layernorm_fwd(const void* x_dev, const float* gamma_dev, const float* beta_dev, void* y_dev,

@@ -170,6 +170,10 @@ def test_attention_fwd_bwd_vs_torch(lib, batch, tokens):
     _lib.check(lib.vitatk_k_attention_fwd(_p(qkv), _p(out), batch, tokens, heads, _s()), "attention_fwd")
     _lib.check(lib.vitatk_k_attention_fwd_tc05(_p(qkv), _p(out_tc), _p(lse2), batch, tokens, heads, _s()), "attention_fwd_tc05")
     _lib.check(lib.vitatk_k_attention_bwd(_p(qkv), _p(dout), _p(dqkv), batch, tokens, heads, _s()), "attention_bwd")
+    dqkv_tc = torch.full((batch * tokens, 3 * D), float("nan"), device="cuda", dtype=torch.bfloat16)
+    delta = torch.zeros(batch * heads, 208, device="cuda")
+    _lib.check(lib.vitatk_k_attention_bwd_tc05(_p(qkv), _p(dout), _p(out_tc), _p(lse2), _p(delta), _p(dqkv_tc), batch,
+                                               tokens, heads, _s()), "attention_bwd_tc05")
     torch.cuda.synchronize()
     x = qkv.float().reshape(batch, tokens, 3, heads, 64).permute(2, 0, 3, 1, 4).requires_grad_(True)  # [3,B,H,T,d]
     q, k, v = x[0], x[1], x[2]
@@ -184,6 +188,9 @@ def test_attention_fwd_bwd_vs_torch(lib, batch, tokens):
     lse_ref = torch.logsumexp(s_ref, -1).reshape(batch * heads, tokens) * 1.4426950408889634
     torch.testing.assert_close(lse2[:, :tokens], lse_ref, rtol=1e-3, atol=2e-3)
     check_rel(dqkv, gref, "attention dqkv", 1.5e-2, 3e-2)
+    check_rel(dqkv_tc, gref, "attention dqkv (tcgen05)", 1.5e-2, 3e-2)
+    dref = (dout.float() * o.detach()).reshape(batch, tokens, heads, 64).sum(-1).permute(0, 2, 1).reshape(batch * heads, tokens)
+    check_rel(delta[:, :tokens], dref, "attention delta", 1e-2, 3e-2)  # o is bf16-rounded in the kernel's input
 
 
 @pytest.mark.parametrize("rows", [1, 8, 197, 1576, 50432])

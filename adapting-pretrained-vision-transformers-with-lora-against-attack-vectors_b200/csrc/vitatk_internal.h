@@ -80,7 +80,7 @@ struct AttnFwdPlan {
   const bf16* qkv;
   bf16* out;
   float* lse2;  // [batch*heads, 208] log2-domain logsumexp per query (for the backward), may be null
-  CUtensorMap tmQ, tmKV;
+  CUtensorMap tmQ, tmKV, tmO;
 };
 int attention_fwd_plan_init(AttnFwdPlan* p, const bf16* qkv, bf16* out, float* lse2, int batch, int tokens, int heads);
 int attention_fwd_tc05(const AttnFwdPlan* p, cudaStream_t stream);
@@ -91,7 +91,7 @@ struct AttnBwdPlan {
   const float* lse2;
   float* delta;  // [batch*heads, 208] scratch
   bf16* dqkv;
-  CUtensorMap tmQKV128, tmQKV208, tmDO128, tmDO208;
+  CUtensorMap tmQKV128, tmQKV208, tmDO128, tmDO208, tmDqkv;
 };
 int attention_bwd_plan_init(AttnBwdPlan* p, const bf16* qkv, const bf16* dout, const bf16* o, const float* lse2,
                             float* delta, bf16* dqkv, int batch, int tokens, int heads);

@@ -14,7 +14,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libvitatk.so")
 INCLUDE_DIR = os.path.join(os.path.dirname(PKG_DIR), "include")
-SOURCES = ["gemm_tc05.cu", "attention.cu", "attention_tc05.cu", "elementwise.cu", "engine.cu"]
+SOURCES = ["gemm_tc05.cu", "attention.cu", "attention_tc05.cu", "attention_bwd_fused.cu", "elementwise.cu", "engine.cu"]
 HEADERS = ["ptx.cuh", "vitatk_internal.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -77,7 +77,7 @@ EXPORTS = [
     "vitatk_attack", "vitatk_count_correct", "vitatk_launch_count", "vitatk_k_gemm", "vitatk_k_attention_fwd",
     "vitatk_k_attention_bwd", "vitatk_k_layernorm_fwd", "vitatk_k_layernorm_bwd", "vitatk_k_pgd_update",
     "vitatk_k_pgd_init", "vitatk_profile_begin", "vitatk_profile_end", "vitatk_k_attention_fwd_tc05",
-    "vitatk_k_attention_bwd_tc05",
+    "vitatk_k_attention_bwd_tc05", "vitatk_k_attention_bwd_fused",
 ]
 
 
@@ -125,6 +125,7 @@ def load() -> C.CDLL:
     lib.vitatk_k_attention_fwd.argtypes = [vp, vp, i, i, i, vp]
     lib.vitatk_k_attention_fwd_tc05.argtypes = [vp, vp, vp, i, i, i, vp]
     lib.vitatk_k_attention_bwd_tc05.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, vp]
+    lib.vitatk_k_attention_bwd_fused.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, vp]
     lib.vitatk_k_attention_bwd.argtypes = [vp, vp, vp, i, i, i, vp]
     lib.vitatk_k_layernorm_fwd.argtypes = [vp, vp, vp, vp, vp, i, i, f, vp]
     lib.vitatk_k_layernorm_bwd.argtypes = [vp, vp, vp, vp, vp, vp, i, i, vp]

@@ -609,7 +609,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__
 }
 
 // delta[b,h,i] = sum_d dO[i, h*64+d] * O[i, h*64+d]   (one warp per token row, 8 lanes per head)
-__global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ o,
+__global__ void __launch_bounds__(256) attn_delta_kernel_2k(const bf16* __restrict__ dout, const bf16* __restrict__ o,
                                                          float* __restrict__ delta, int rows, int tokens, int heads) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -635,6 +635,13 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict_
   }
 }
 
+int attention_delta(const AttnBwdPlan* p, cudaStream_t stream) {
+  const int rows = p->batch * p->tokens;
+  attn_delta_kernel_2k<<<(rows + 7) / 8, 256, 0, stream>>>(p->dout, p->o, p->delta, rows, p->tokens, p->heads);
+  VITATK_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int attention_bwd_plan_init(AttnBwdPlan* p, const bf16* qkv, const bf16* dout, const bf16* o, const float* lse2,
                             float* delta, bf16* dqkv, int batch, int tokens, int heads) {
   if (tokens < 1 || tokens > A_TPAD) {
@@ -655,6 +662,7 @@ int attention_bwd_plan_init(AttnBwdPlan* p, const bf16* qkv, const bf16* dout, c
   if (make_tmap_3d(&p->tmDO128, dout, ldo, tokens, batch, ldo * 2, ldo * 2 * tokens, A_HD, 128)) return 1;
   if (make_tmap_3d(&p->tmDO208, dout, ldo, tokens, batch, ldo * 2, ldo * 2 * tokens, A_HD, A_TPAD)) return 1;
   if (make_tmap_3d(&p->tmDqkv, dqkv, ld, tokens, batch, ld * 2, ld * 2 * tokens, A_HD, 32)) return 1;
+  if (make_tmap_3d(&p->tmDqkv32, dqkv, ld, tokens, batch, ld * 2, ld * 2 * tokens, 32, 32, 64)) return 1;
   return 0;
 }
 
@@ -684,7 +692,7 @@ int attention_bwd_tc05(const AttnBwdPlan* p, cudaStream_t stream) {
     const char* e = getenv("VITATK_ATTN_DBG");
     dbg = e ? atoi(e) : 0;
   }
-  attn_delta_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(p->dout, p->o, p->delta, rows, p->tokens, p->heads);
+  attn_delta_kernel_2k<<<(rows + 7) / 8, 256, 0, stream>>>(p->dout, p->o, p->delta, rows, p->tokens, p->heads);
   VITATK_CUDA_OK(cudaGetLastError());
   // dQ: A0 = Q tile, A1 = dO tile, B0 = K, B1 = V
   attn_bwd_kernel<0><<<grid, B_THREADS, B_SMEM, stream>>>(p->tmQKV128, p->tmDO128, p->tmQKV208, p->tmQKV208, p->tmDqkv, 0, 0, D,

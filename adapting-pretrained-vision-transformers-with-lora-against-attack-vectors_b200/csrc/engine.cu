@@ -11,6 +11,7 @@
 // saved for dW; only what LN / GELU / softmax need for their Jacobians is kept.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -91,6 +92,7 @@ struct vitatk_engine {
   long long launches = 0;
   PixelNorm nrm;
   // optional per-launch CUDA-event timing (bench.py's roofline leg; off in the timed region)
+  bool attn_bwd_two_kernel = false;  // VITATK_ATTN_BWD=2k selects the older dQ + dK/dV kernel pair
   bool prof = false;
   struct ProfRec { int cat; double flops; cudaEvent_t a, b; };
   std::vector<ProfRec> prof_recs;
@@ -218,8 +220,10 @@ static int build_plans(vitatk_engine* e, int batch, PlanSet** out) {
   return 0;
 }
 
-enum ProfCat { CAT_GEMM = 0, CAT_GEMM_LORA_T = 1, CAT_ATTN_FWD = 2, CAT_ATTN_BWD = 3, CAT_LN = 4, CAT_HEAD = 5,
-               CAT_PIXEL = 6, CAT_COUNT = 8 };
+// one profiling category per kernel role (include/vitatk.h lists them in this order)
+enum ProfCat { CAT_PATCH = 0, CAT_QKV, CAT_PROJ, CAT_FC1, CAT_FC2, CAT_BFC2, CAT_BFC1, CAT_BPROJ, CAT_BQKV, CAT_BPATCH,
+               CAT_T_QKV, CAT_T_PROJ, CAT_T_FC1, CAT_T_FC2, CAT_BT_FC2, CAT_BT_FC1, CAT_BT_PROJ, CAT_BT_QKV,
+               CAT_ATTN_FWD, CAT_ATTN_BWD, CAT_LN_FWD, CAT_LN_BWD, CAT_HEAD, CAT_PIXEL, CAT_COUNT = 32 };
 
 static cudaEvent_t prof_event(vitatk_engine* e) {
   cudaEvent_t ev;
@@ -251,28 +255,27 @@ static double plan_flops(const GemmPlan* p) {
       e->prof_recs.push_back({(cat), (flops), _a, _b});          \
     }                                                            \
   } while (0)
-#define RUN_GEMM(plan) RUNC(CAT_GEMM, plan_flops(plan), gemm_launch((plan), s, e->num_sms))
-#define RUN_GEMM_T(plan) RUNC(CAT_GEMM_LORA_T, plan_flops(plan), gemm_launch((plan), s, e->num_sms))
+#define RUN_GEMM(cat, plan) RUNC(cat, plan_flops(plan), gemm_launch((plan), s, e->num_sms))
 
 // forward through the encoder from the im2col'd, normalised input in e->cols
 static int encoder_forward(vitatk_engine* e, PlanSet* ps, int batch, cudaStream_t s) {
   const vitatk_config& c = e->cfg;
   const int M = batch * TOKENS, D = c.dim;
-  RUN_GEMM(&ps->patch);
+  RUN_GEMM(CAT_PATCH, &ps->patch);
   for (int l = 0; l < c.layers; ++l) {
     const LayerWeights& w = e->lw[l];
     LayerPlans& p = ps->layers[l];
-    RUNC(CAT_LN, 0, layernorm_fwd(e->h[l], w.ln1_g, w.ln1_b, e->xn, e->st1[l], M, D, c.ln_eps, s));
-    if (w.lora[VITATK_SITE_QKV].rank > 0) RUN_GEMM_T(&p.t_qkv);
-    RUN_GEMM(&p.qkv);
+    RUNC(CAT_LN_FWD, 0, layernorm_fwd(e->h[l], w.ln1_g, w.ln1_b, e->xn, e->st1[l], M, D, c.ln_eps, s));
+    if (w.lora[VITATK_SITE_QKV].rank > 0) RUN_GEMM(CAT_T_QKV, &p.t_qkv);
+    RUN_GEMM(CAT_QKV, &p.qkv);
     RUNC(CAT_ATTN_FWD, 4.0 * batch * c.heads * TOKENS * TOKENS * 64, attention_fwd_tc05(&ps->attn_fwd[l], s));
-    if (w.lora[VITATK_SITE_PROJ].rank > 0) RUN_GEMM_T(&p.t_proj);
-    RUN_GEMM(&p.proj);
-    RUNC(CAT_LN, 0, layernorm_fwd(e->h_mid[l], w.ln2_g, w.ln2_b, e->xn, e->st2[l], M, D, c.ln_eps, s));
-    if (w.lora[VITATK_SITE_FC1].rank > 0) RUN_GEMM_T(&p.t_fc1);
-    RUN_GEMM(&p.fc1);
-    if (w.lora[VITATK_SITE_FC2].rank > 0) RUN_GEMM_T(&p.t_fc2);
-    RUN_GEMM(&p.fc2);
+    if (w.lora[VITATK_SITE_PROJ].rank > 0) RUN_GEMM(CAT_T_PROJ, &p.t_proj);
+    RUN_GEMM(CAT_PROJ, &p.proj);
+    RUNC(CAT_LN_FWD, 0, layernorm_fwd(e->h_mid[l], w.ln2_g, w.ln2_b, e->xn, e->st2[l], M, D, c.ln_eps, s));
+    if (w.lora[VITATK_SITE_FC1].rank > 0) RUN_GEMM(CAT_T_FC1, &p.t_fc1);
+    RUN_GEMM(CAT_FC1, &p.fc1);
+    if (w.lora[VITATK_SITE_FC2].rank > 0) RUN_GEMM(CAT_T_FC2, &p.t_fc2);
+    RUN_GEMM(CAT_FC2, &p.fc2);
   }
   return 0;
 }
@@ -284,19 +287,20 @@ static int encoder_backward(vitatk_engine* e, PlanSet* ps, int batch, cudaStream
   for (int l = c.layers - 1; l >= 0; --l) {
     const LayerWeights& w = e->lw[l];
     LayerPlans& p = ps->layers[l];
-    if (w.lora[VITATK_SITE_FC2].rank > 0) RUN_GEMM_T(&p.bt_fc2);
-    RUN_GEMM(&p.bfc2);  // du = (dh W2 + lora) * gelu'(u)   (u[l] holds gelu'(u), written by fc1's epilogue)
-    if (w.lora[VITATK_SITE_FC1].rank > 0) RUN_GEMM_T(&p.bt_fc1);
-    RUN_GEMM(&p.bfc1);  // dxn = du W1 + lora
-    RUNC(CAT_LN, 0, layernorm_bwd(e->dxn, e->h_mid[l], e->st2[l], w.ln2_g, e->dh_a, e->dh_b, M, D, s));  // dh_mid
-    if (w.lora[VITATK_SITE_PROJ].rank > 0) RUN_GEMM_T(&p.bt_proj);
-    RUN_GEMM(&p.bproj);  // dao = dh_mid Wp + lora
-    RUNC(CAT_ATTN_BWD, 8.0 * batch * c.heads * TOKENS * TOKENS * 64, attention_bwd_tc05(&ps->attn_bwd[l], s));
-    if (w.lora[VITATK_SITE_QKV].rank > 0) RUN_GEMM_T(&p.bt_qkv);
-    RUN_GEMM(&p.bqkv);  // dxn = dqkv Wqkv + lora
-    RUNC(CAT_LN, 0, layernorm_bwd(e->dxn, e->h[l], e->st1[l], w.ln1_g, e->dh_b, e->dh_a, M, D, s));  // dh wrt h[l]
+    if (w.lora[VITATK_SITE_FC2].rank > 0) RUN_GEMM(CAT_BT_FC2, &p.bt_fc2);
+    RUN_GEMM(CAT_BFC2, &p.bfc2);  // du = (dh W2 + lora) * gelu'(u)   (u[l] holds gelu'(u), written by fc1's epilogue)
+    if (w.lora[VITATK_SITE_FC1].rank > 0) RUN_GEMM(CAT_BT_FC1, &p.bt_fc1);
+    RUN_GEMM(CAT_BFC1, &p.bfc1);  // dxn = du W1 + lora
+    RUNC(CAT_LN_BWD, 0, layernorm_bwd(e->dxn, e->h_mid[l], e->st2[l], w.ln2_g, e->dh_a, e->dh_b, M, D, s));  // dh_mid
+    if (w.lora[VITATK_SITE_PROJ].rank > 0) RUN_GEMM(CAT_BT_PROJ, &p.bt_proj);
+    RUN_GEMM(CAT_BPROJ, &p.bproj);  // dao = dh_mid Wp + lora
+    RUNC(CAT_ATTN_BWD, 8.0 * batch * c.heads * TOKENS * TOKENS * 64,
+         e->attn_bwd_two_kernel ? attention_bwd_tc05(&ps->attn_bwd[l], s) : attention_bwd_fused(&ps->attn_bwd[l], s));
+    if (w.lora[VITATK_SITE_QKV].rank > 0) RUN_GEMM(CAT_BT_QKV, &p.bt_qkv);
+    RUN_GEMM(CAT_BQKV, &p.bqkv);  // dxn = dqkv Wqkv + lora
+    RUNC(CAT_LN_BWD, 0, layernorm_bwd(e->dxn, e->h[l], e->st1[l], w.ln1_g, e->dh_b, e->dh_a, M, D, s));  // dh wrt h[l]
   }
-  RUN_GEMM(&ps->bpatch);  // dxn <- dL/d(cols)
+  RUN_GEMM(CAT_BPATCH, &ps->bpatch);  // dxn <- dL/d(cols)
   return 0;
 }
 
@@ -344,6 +348,10 @@ int vitatk_create(const vitatk_config* cfg, vitatk_engine** out) {
   vitatk_engine* e = new vitatk_engine();
   e->cfg = *cfg;
   e->num_sms = prop.multiProcessorCount;
+  {
+    const char* v = getenv("VITATK_ATTN_BWD");
+    e->attn_bwd_two_kernel = v && strcmp(v, "2k") == 0;
+  }
   e->lw.resize(cfg->layers);
   for (int i = 0; i < 3; ++i) {
     e->nrm.mean[i] = cfg->mean[i];
@@ -681,6 +689,14 @@ int vitatk_k_attention_bwd_tc05(const void* qkv, const void* dout, const void* o
                               static_cast<const bf16*>(o), lse2, delta, static_cast<bf16*>(dqkv), batch, tokens, heads))
     return 1;
   return attention_bwd_tc05(&p, static_cast<cudaStream_t>(stream));
+}
+int vitatk_k_attention_bwd_fused(const void* qkv, const void* dout, const void* o, const float* lse2, float* delta,
+                                 void* dqkv, int batch, int tokens, int heads, void* stream) {
+  AttnBwdPlan p;
+  if (attention_bwd_plan_init(&p, static_cast<const bf16*>(qkv), static_cast<const bf16*>(dout),
+                              static_cast<const bf16*>(o), lse2, delta, static_cast<bf16*>(dqkv), batch, tokens, heads))
+    return 1;
+  return attention_bwd_fused(&p, static_cast<cudaStream_t>(stream));
 }
 int vitatk_k_attention_bwd(const void* qkv, const void* dout, void* dqkv, int batch, int tokens, int heads,
                            void* stream) {

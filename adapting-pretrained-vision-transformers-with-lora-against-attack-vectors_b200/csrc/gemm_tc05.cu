@@ -17,6 +17,7 @@
 // (MMA <-> epilogue), static persistent tile scheduler (tile = blockIdx.x + i*gridDim.x).
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "ptx.cuh"
 #include "vitatk_internal.h"
@@ -48,6 +49,8 @@ struct GemmKernelArgs {
   int M, N, K;
   int lora_nkb, lora_ksteps, lora_group_cols;
   GemmEpilogue epi;
+  int dbg;  // timing experiments (DBG instantiation only, VITATK_GEMM_DBG): 1 no aux loads, 2 no stores,
+            // 4 no TMA loads after the first ring fill, 8 no MMA issue, 16 epilogue skips TMEM reads and math
 };
 
 // Exact-erf GELU and its derivative from ONE exponential and ONE reciprocal (Abramowitz-Stegun 7.1.26,
@@ -109,7 +112,7 @@ __device__ __forceinline__ void stage_and_store(uint8_t* stage, const uint32_t (
   }
 }
 
-template <int BN>
+template <int BN, bool DBG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmLA, const __grid_constant__ CUtensorMap tmLB,
@@ -181,6 +184,10 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           ptx::mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem_stage + s * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
+          if (DBG && (args.dbg & 4) && cnt >= STAGES) {
+            ptx::mbar_arrive(&full_bar[s]);
+            continue;
+          }
           ptx::mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
           if (kb < main_kb) {
             ptx::tma_load_2d(sa, &tmA, &full_bar[s], kb * BK, m0);
@@ -215,7 +222,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint64_t adesc = ptx::make_smem_desc_sw128(sa);
           const uint64_t bdesc = ptx::make_smem_desc_sw128(sb);
           const int ksteps = kb < main_kb ? (BK / 16) : args.lora_ksteps;
-          for (int k = 0; k < ksteps; ++k) {
+          for (int k = 0; k < ((DBG && (args.dbg & 8)) ? 0 : ksteps); ++k) {
             // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr>>4) field
             ptx::umma_bf16(tmem_acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
@@ -232,7 +239,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     constexpr int CPW = BN / (2 * CHUNK);  // 32-column chunks per warp per tile
     uint8_t* my_out = smem_out + warp * 2 * STAGE_OUT_BYTES;
     const GemmEpilogue epi = args.epi;
-    const bool has_aux = (epi.mode == EPI_RESIDUAL || epi.mode == EPI_MUL);
+    const bool has_aux = (epi.mode == EPI_RESIDUAL || epi.mode == EPI_MUL) && !(DBG && (args.dbg & 1));
     uint32_t it = 0;
     uint32_t store_idx = 0;
     uint4 aux_next[4];
@@ -261,7 +268,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN;
 
 #pragma unroll 1
-      for (int i = 0; i < CPW; ++i) {
+      for (int i = 0; i < ((DBG && (args.dbg & 16)) ? 0 : CPW); ++i) {
         const int c = hsel * CPW + i;
         const int ncol = n0 + c * CHUNK;
         uint32_t r[32];
@@ -337,13 +344,17 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             packed[j] = pack_bf16x2(g0, g1);
             packed2[j] = pack_bf16x2(d0, d1);
           }
-          stage_and_store(my_out + (store_idx & 1) * STAGE_OUT_BYTES, packed2, &tmOut2, ncol, m0 + q * 32, lane);
+          if (!(DBG && (args.dbg & 2)))
+            stage_and_store(my_out + (store_idx & 1) * STAGE_OUT_BYTES, packed2, &tmOut2, ncol, m0 + q * 32, lane);
           ++store_idx;
         } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j) packed[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
         }
-        stage_and_store(my_out + (store_idx & 1) * STAGE_OUT_BYTES, packed, &tmOut, ncol, m0 + q * 32, lane);
+        if (!(DBG && (args.dbg & 2)))
+          stage_and_store(my_out + (store_idx & 1) * STAGE_OUT_BYTES, packed, &tmOut, ncol, m0 + q * 32, lane);
+        else if (packed[3] == 0x12345678u && packed[7] == 0x9abcdef0u)
+          tmem_slot[1] = packed[5];  // keep the math alive when stores are disabled
         ++store_idx;
       }
       // all tcgen05.ld of this accumulator have completed (wait::ld above) -> hand it back to the MMA warp
@@ -440,9 +451,9 @@ static int make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64
 }
 
 // 3D bf16 tensor [d2][d1][d0] (d0 contiguous) with byte strides s1 (between d1 rows) and s2 (between d2 slabs);
-// box = [b0, b1, 1], 128B swizzle, out-of-bounds elements read as zero.
+// box = [b0, b1, 1], 128B (default) or 64B swizzle, out-of-bounds elements read as zero / are not written.
 int make_tmap_3d(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1_bytes,
-                 uint64_t s2_bytes, uint32_t b0, uint32_t b1) {
+                 uint64_t s2_bytes, uint32_t b0, uint32_t b1, int swizzle_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return 1;
   if ((reinterpret_cast<uintptr_t>(base) & 15) || (s1_bytes & 15) || (s2_bytes & 15)) {
@@ -454,8 +465,9 @@ int make_tmap_3d(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1, ui
   cuuint32_t box[3] = {b0, b1, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(3d) failed (%d) dims=%llu,%llu,%llu box=%u,%u", (int)r, (unsigned long long)d0,
               (unsigned long long)d1, (unsigned long long)d2, b0, b1);
@@ -502,12 +514,23 @@ int gemm_plan_init(GemmPlan* p, int M, int N, int K, const bf16* A, int lda, con
   return 0;
 }
 
+static int gemm_dbg_flags() {
+  static int dbg = -1;
+  if (dbg < 0) {
+    const char* e = getenv("VITATK_GEMM_DBG");
+    dbg = e ? atoi(e) : 0;
+  }
+  return dbg;
+}
+
 template <int BN>
 static int launch_bn(const GemmPlan* p, cudaStream_t stream, int num_sms) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    VITATK_CUDA_OK(cudaFuncSetAttribute(gemm_tc05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    VITATK_CUDA_OK(cudaFuncSetAttribute(gemm_tc05_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Cfg::SMEM_BYTES));
+    VITATK_CUDA_OK(cudaFuncSetAttribute(gemm_tc05_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::SMEM_BYTES));
     attr_set = true;
   }
@@ -521,8 +544,13 @@ static int launch_bn(const GemmPlan* p, cudaStream_t stream, int num_sms) {
   a.lora_ksteps = p->lora_ksteps;
   a.lora_group_cols = p->lora_group_cols;
   a.epi = p->epi;
-  gemm_tc05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(p->tmA, p->tmB, p->tmLA, p->tmLB, p->tmOut,
-                                                                      p->tmOut2, a);
+  a.dbg = gemm_dbg_flags();
+  if (a.dbg)
+    gemm_tc05_kernel<BN, true><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(p->tmA, p->tmB, p->tmLA, p->tmLB,
+                                                                              p->tmOut, p->tmOut2, a);
+  else
+    gemm_tc05_kernel<BN, false><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(p->tmA, p->tmB, p->tmLA, p->tmLB,
+                                                                               p->tmOut, p->tmOut2, a);
   VITATK_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -548,6 +576,7 @@ int gemm_launch_simt(const GemmPlan* p, const bf16* A, int lda, const bf16* B, i
   a.lora_ksteps = p->lora_ksteps;
   a.lora_group_cols = p->lora_group_cols;
   a.epi = p->epi;
+  a.dbg = 0;
   dim3 grid((p->N + 127) / 128, p->M);
   gemm_simt_kernel<<<grid, 128, 0, stream>>>(a, A, lda, B, ldb, out, ldo, out2, ldo2, T, ldt, LB, ldlb);
   VITATK_CUDA_OK(cudaGetLastError());

@@ -69,7 +69,7 @@ int gemm_launch_simt(const GemmPlan* p, const bf16* A, int lda, const bf16* B, i
                      bf16* out2, int ldo2, const bf16* T, int ldt, const bf16* LB, int ldlb, cudaStream_t stream);
 
 int make_tmap_3d(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1_bytes,
-                 uint64_t s2_bytes, uint32_t b0, uint32_t b1);
+                 uint64_t s2_bytes, uint32_t b0, uint32_t b1, int swizzle_bytes = 128);
 
 // ---------------------------------------------------------------------------------------------
 // attention (softmax(QK^T/sqrt(d))V per (image, head)), qkv packed [M, 3*D] token-major
@@ -92,10 +92,12 @@ struct AttnBwdPlan {
   float* delta;  // [batch*heads, 208] scratch
   bf16* dqkv;
   CUtensorMap tmQKV128, tmQKV208, tmDO128, tmDO208, tmDqkv;
+  CUtensorMap tmDqkv32;  // 32-column x 32-row store boxes, 64B swizzle (fused kernel)
 };
 int attention_bwd_plan_init(AttnBwdPlan* p, const bf16* qkv, const bf16* dout, const bf16* o, const float* lse2,
                             float* delta, bf16* dqkv, int batch, int tokens, int heads);
-int attention_bwd_tc05(const AttnBwdPlan* p, cudaStream_t stream);
+int attention_bwd_tc05(const AttnBwdPlan* p, cudaStream_t stream);        // two-kernel version (dQ, then dK/dV)
+int attention_bwd_fused(const AttnBwdPlan* p, cudaStream_t stream);       // single-pass version (engine default)
 // mma.sync forward (round-1 first version, kept for cross-checking the tcgen05 kernel in tests)
 int attention_fwd(const bf16* qkv, bf16* out, int batch, int tokens, int heads, cudaStream_t stream);
 int attention_bwd(const bf16* qkv, const bf16* dout, bf16* dqkv, int batch, int tokens, int heads,

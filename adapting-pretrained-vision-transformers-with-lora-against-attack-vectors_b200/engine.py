@@ -311,16 +311,27 @@ class Engine:
                                                      self._stream()), "vitatk_count_correct")
         return counts
 
-    PROFILE_CATEGORIES = ("gemm_tc05", "gemm_lora_t", "attention_fwd", "attention_bwd", "layernorm", "head", "pixel")
+    PROFILE_CATEGORIES = ("patch", "qkv", "proj", "fc1", "fc2", "bfc2", "bfc1", "bproj", "bqkv", "bpatch",
+                          "t_qkv", "t_proj", "t_fc1", "t_fc2", "bt_fc2", "bt_fc1", "bt_proj", "bt_qkv",
+                          "attention_fwd", "attention_bwd", "layernorm_fwd", "layernorm_bwd", "head", "pixel")
+    PROFILE_GROUPS = {"gemm_tc05": PROFILE_CATEGORIES[0:10], "gemm_lora_t": PROFILE_CATEGORIES[10:18],
+                      "attention_fwd": ("attention_fwd",), "attention_bwd": ("attention_bwd",),
+                      "layernorm": ("layernorm_fwd", "layernorm_bwd"), "head": ("head",), "pixel": ("pixel",)}
 
     def profile_begin(self) -> None:
         _lib.check(self.lib.vitatk_profile_begin(self._h), "vitatk_profile_begin")
 
-    def profile_end(self) -> Dict[str, Dict[str, float]]:
-        """{category: {ms, flops, launches}} for everything enqueued since profile_begin()."""
-        ms, fl, n = (C.c_double * 8)(), (C.c_double * 8)(), (C.c_longlong * 8)()
+    def profile_end(self, grouped: bool = True) -> Dict[str, Dict[str, float]]:
+        """{category: {ms, flops, launches}} for everything enqueued since profile_begin(); ``grouped`` sums the
+        per-role categories into gemm_tc05 / gemm_lora_t / attention_* / layernorm / head / pixel."""
+        ms, fl, n = (C.c_double * 32)(), (C.c_double * 32)(), (C.c_longlong * 32)()
         _lib.check(self.lib.vitatk_profile_end(self._h, ms, fl, n), "vitatk_profile_end")
-        return {c: {"ms": ms[i], "flops": fl[i], "launches": int(n[i])} for i, c in enumerate(self.PROFILE_CATEGORIES)}
+        fine = {c: {"ms": ms[i], "flops": fl[i], "launches": int(n[i])} for i, c in enumerate(self.PROFILE_CATEGORIES)}
+        self.last_profile_detail = fine
+        if not grouped:
+            return fine
+        return {g: {k: sum(fine[c][k] for c in cats) for k in ("ms", "flops", "launches")}
+                for g, cats in self.PROFILE_GROUPS.items()}
 
     def close(self) -> None:
         if getattr(self, "_h", None) is not None and self._h.value:

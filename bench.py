@@ -275,6 +275,8 @@ def run_engine(args):
                      "whole_step_tensor_frac": value / world * gflop_img * 1e9 / 1e12 / peak},
         "breakdown_ms_per_step": {k: round(v["ms"], 3) for k, v in prof.items()},
         "breakdown_launches": {k: v["launches"] for k, v in prof.items()},
+        "breakdown_detail": {k: [round(v["ms"], 3), round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 1) if v["flops"] else 0]
+                             for k, v in eng.last_profile_detail.items() if v["launches"]},
         "robust": {"clean_correct": int(counts[0]), "robust_correct": int(counts[1]), "total": int(counts[2]),
                    "linf": linf, "eps_f32": float(torch.tensor(EPS, dtype=torch.float32))},
     }

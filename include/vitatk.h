@@ -129,8 +129,10 @@ long long vitatk_launch_count(const vitatk_engine* e);
 /* Per-launch CUDA-event timing for bench.py's roofline leg (never on inside a timed region).  Between
  * begin and end every kernel the engine enqueues is bracketed by events on its stream; end() waits for
  * them and returns, per category, the summed duration (ms), algorithmic FLOPs and launch count.
- * Categories: 0 GEMM (tcgen05), 1 LoRA x*A^T GEMM, 2 attention fwd, 3 attention bwd, 4 LayerNorm,
- * 5 head/CE/count, 6 pixel kernels (PGD init/update, gradient materialisation); arrays have 8 entries. */
+ * Categories (arrays have 32 entries): 0 patch-embed GEMM, 1 qkv, 2 proj, 3 fc1, 4 fc2, 5 fc2-bwd, 6 fc1-bwd,
+ * 7 proj-bwd, 8 qkv-bwd, 9 patch-bwd, 10-13 LoRA x*A^T GEMMs (qkv, proj, fc1, fc2), 14-17 LoRA dY*B GEMMs (fc2, fc1,
+ * proj, qkv), 18 attention fwd, 19 attention bwd, 20 LayerNorm fwd, 21 LayerNorm bwd, 22 head/CE/count,
+ * 23 pixel kernels (PGD init/update, gradient materialisation). */
 int vitatk_profile_begin(vitatk_engine* e);
 int vitatk_profile_end(vitatk_engine* e, double* ms_by_cat, double* flops_by_cat, long long* launches_by_cat);
 
@@ -144,10 +146,13 @@ int vitatk_k_attention_fwd(const void* qkv_dev, void* out_dev, int batch, int to
 /* tcgen05 forward (the engine's path); lse2_dev (optional) receives [batch*heads, 208] log2-domain logsumexp */
 int vitatk_k_attention_fwd_tc05(const void* qkv_dev, void* out_dev, float* lse2_dev, int batch, int tokens, int heads,
                                 void* stream);
-/* tcgen05 backward (the engine's path): needs the forward's output o_dev and lse2_dev; delta_dev is a zero-
+/* tcgen05 backward, two-kernel version (dQ, then dK/dV): needs the forward's output o_dev and lse2_dev; delta_dev is a zero-
  * initialised [batch*heads, 208] fp32 scratch; dqkv_dev [batch*tokens, 3*D] receives dq | dk | dv */
 int vitatk_k_attention_bwd_tc05(const void* qkv_dev, const void* dout_dev, const void* o_dev, const float* lse2_dev,
                                 float* delta_dev, void* dqkv_dev, int batch, int tokens, int heads, void* stream);
+/* single-pass tcgen05 backward (the engine's path; same arguments as the two-kernel version above) */
+int vitatk_k_attention_bwd_fused(const void* qkv_dev, const void* dout_dev, const void* o_dev, const float* lse2_dev,
+                                 float* delta_dev, void* dqkv_dev, int batch, int tokens, int heads, void* stream);
 int vitatk_k_attention_bwd(const void* qkv_dev, const void* dout_dev, void* dqkv_dev, int batch, int tokens,
                            int heads, void* stream);
 int vitatk_k_layernorm_fwd(const void* x_dev, const float* gamma_dev, const float* beta_dev, void* y_dev,

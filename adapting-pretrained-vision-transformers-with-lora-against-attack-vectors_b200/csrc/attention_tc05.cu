@@ -114,22 +114,24 @@ attn_fwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const uint32_t tmem = *tmem_slot;
 
   if (warp == A_TMA_WARP) {
-    if (lane == 0) {
+    {
+      const uint32_t leader = ptx::elect_leader();
       int n = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++n) {
         const int st = n & 1;
         const int b = item / heads, h = item % heads;
         ptx::mbar_wait(&load_empty[st], ((n >> 1) & 1) ^ 1);
         uint8_t* Qs = smem + st * A_STAGE_BYTES;
-        ptx::mbar_arrive_expect_tx(&load_full[st], A_STAGE_BYTES);
-        ptx::tma_load_3d(Qs, &tmQ, &load_full[st], h * A_HD, 0, b);
-        ptx::tma_load_3d(Qs + 128 * 128, &tmQ, &load_full[st], h * A_HD, 128, b);
-        ptx::tma_load_3d(Qs + Q_BYTES, &tmKV, &load_full[st], D + h * A_HD, 0, b);
-        ptx::tma_load_3d(Qs + Q_BYTES + KV_BYTES, &tmKV, &load_full[st], 2 * D + h * A_HD, 0, b);
+        ptx::mbar_arrive_expect_tx_p(leader, &load_full[st], A_STAGE_BYTES);
+        ptx::tma_load_3d_p(leader, Qs, &tmQ, &load_full[st], h * A_HD, 0, b);
+        ptx::tma_load_3d_p(leader, Qs + 128 * 128, &tmQ, &load_full[st], h * A_HD, 128, b);
+        ptx::tma_load_3d_p(leader, Qs + Q_BYTES, &tmKV, &load_full[st], D + h * A_HD, 0, b);
+        ptx::tma_load_3d_p(leader, Qs + Q_BYTES + KV_BYTES, &tmKV, &load_full[st], 2 * D + h * A_HD, 0, b);
       }
     }
   } else if (warp == A_MMA_WARP) {
-    if (lane == 0) {
+    {
+      const uint32_t leader = ptx::elect_leader();
       constexpr uint32_t idesc_s = ptx::make_idesc_bf16(128, A_TPAD);
       constexpr uint32_t idesc_pv = ptx::make_idesc_bf16(128, A_HD) | ptx::IDESC_B_MN_MAJOR;
       int n = 0;
@@ -146,8 +148,8 @@ attn_fwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           const uint64_t qdesc = ptx::make_smem_desc_sw128(qs + t * 128 * 128);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            ptx::umma_bf16(tmem + t * A_TILE_COLS, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k > 0 ? 1u : 0u);
-          ptx::umma_commit(&s_full[t]);
+            ptx::umma_bf16_p(leader, tmem + t * A_TILE_COLS, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+          ptx::umma_commit_p(leader, &s_full[t]);
         }
         for (int t = 0; t < ntiles; ++t) {
           ptx::mbar_wait(&p_full[t], par);
@@ -155,10 +157,10 @@ attn_fwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           const uint32_t tt = tmem + t * A_TILE_COLS;
 #pragma unroll 1
           for (int ks = 0; ks < A_TPAD / 16; ++ks)  // 16 keys per step: 8 TMEM columns of P, 16 rows (2 KB) of V
-            ptx::umma_bf16_ts(tt + A_O_COL, tt + ks * 8, vdesc + ks * (2048 >> 4), idesc_pv, ks > 0 ? 1u : 0u);
-          ptx::umma_commit(&o_full[t]);
+            ptx::umma_bf16_ts_p(leader, tt + A_O_COL, tt + ks * 8, vdesc + ks * (2048 >> 4), idesc_pv, ks > 0 ? 1u : 0u);
+          ptx::umma_commit_p(leader, &o_full[t]);
         }
-        ptx::umma_commit(&load_empty[st]);  // every MMA reading this stage has retired
+        ptx::umma_commit_p(leader, &load_empty[st]);  // every MMA reading this stage has retired
       }
     }
   } else {

@@ -171,65 +171,66 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == TMA_WARP) {
-    // ================================= TMA producer =================================
-    if (lane == 0) {
-      uint32_t cnt = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / tiles_n) * BM;
-        const int n0 = (tile % tiles_n) * BN;
-        const int tcol0 = args.lora_group_cols > 0 ? (n0 / args.lora_group_cols) * BK : 0;
-        for (int kb = 0; kb < num_kb; ++kb, ++cnt) {
-          const int s = cnt % STAGES;
-          const uint32_t ph = (cnt / STAGES) & 1;
-          ptx::mbar_wait(&empty_bar[s], ph ^ 1);
-          uint8_t* sa = smem_stage + s * Cfg::STAGE_BYTES;
-          uint8_t* sb = sa + Cfg::A_BYTES;
-          if (DBG && (args.dbg & 4) && cnt >= STAGES) {
-            ptx::mbar_arrive(&full_bar[s]);
-            continue;
-          }
-          ptx::mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-          if (kb < main_kb) {
-            ptx::tma_load_2d(sa, &tmA, &full_bar[s], kb * BK, m0);
-            ptx::tma_load_2d(sb, &tmB, &full_bar[s], kb * BK, n0);
-          } else {
-            const int j = kb - main_kb;
-            ptx::tma_load_2d(sa, &tmLA, &full_bar[s], tcol0 + j * BK, m0);
-            ptx::tma_load_2d(sb, &tmLB, &full_bar[s], j * BK, n0);
-          }
+    // ================================= TMA producer (converged warp, elected lane issues) =================================
+    const uint32_t leader = ptx::elect_leader();
+    uint32_t cnt = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / tiles_n) * BM;
+      const int n0 = (tile % tiles_n) * BN;
+      const int tcol0 = args.lora_group_cols > 0 ? (n0 / args.lora_group_cols) * BK : 0;
+      for (int kb = 0; kb < num_kb; ++kb, ++cnt) {
+        const int s = cnt % STAGES;
+        const uint32_t ph = (cnt / STAGES) & 1;
+        ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* sa = smem_stage + s * Cfg::STAGE_BYTES;
+        uint8_t* sb = sa + Cfg::A_BYTES;
+        if (DBG && (args.dbg & 4) && cnt >= STAGES) {
+          ptx::mbar_arrive_p(leader, &full_bar[s]);
+          continue;
+        }
+        ptx::mbar_arrive_expect_tx_p(leader, &full_bar[s], Cfg::STAGE_BYTES);
+        if (kb < main_kb) {
+          ptx::tma_load_2d_p(leader, sa, &tmA, &full_bar[s], kb * BK, m0);
+          ptx::tma_load_2d_p(leader, sb, &tmB, &full_bar[s], kb * BK, n0);
+        } else {
+          const int j = kb - main_kb;
+          ptx::tma_load_2d_p(leader, sa, &tmLA, &full_bar[s], tcol0 + j * BK, m0);
+          ptx::tma_load_2d_p(leader, sb, &tmLB, &full_bar[s], j * BK, n0);
         }
       }
     }
   } else if (warp == MMA_WARP) {
-    // ================================= MMA issuer =================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN);
-      uint32_t cnt = 0;
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const uint32_t buf = it & 1;
-        const uint32_t use = it >> 1;
-        ptx::mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);  // epilogue has drained this accumulator
+    // ================================= MMA issuer (converged warp, elected lane issues) =================================
+    const uint32_t leader = ptx::elect_leader();
+    constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN);
+    uint32_t cnt = 0;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const uint32_t buf = it & 1;
+      const uint32_t use = it >> 1;
+      ptx::mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);  // epilogue has drained this accumulator
+      ptx::tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + buf * BN;
+      for (int kb = 0; kb < num_kb; ++kb, ++cnt) {
+        const int s = cnt % STAGES;
+        const uint32_t ph = (cnt / STAGES) & 1;
+        ptx::mbar_wait(&full_bar[s], ph);
         ptx::tc_fence_after();
-        const uint32_t tmem_acc = tmem_base + buf * BN;
-        for (int kb = 0; kb < num_kb; ++kb, ++cnt) {
-          const int s = cnt % STAGES;
-          const uint32_t ph = (cnt / STAGES) & 1;
-          ptx::mbar_wait(&full_bar[s], ph);
-          ptx::tc_fence_after();
-          const uint32_t sa = ptx::smem_u32(smem_stage + s * Cfg::STAGE_BYTES);
-          const uint32_t sb = sa + Cfg::A_BYTES;
-          const uint64_t adesc = ptx::make_smem_desc_sw128(sa);
-          const uint64_t bdesc = ptx::make_smem_desc_sw128(sb);
-          const int ksteps = kb < main_kb ? (BK / 16) : args.lora_ksteps;
-          for (int k = 0; k < ((DBG && (args.dbg & 8)) ? 0 : ksteps); ++k) {
-            // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr>>4) field
-            ptx::umma_bf16(tmem_acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          }
-          ptx::umma_commit(&empty_bar[s]);  // smem slot reusable once these MMAs retire
+        const uint32_t sa = ptx::smem_u32(smem_stage + s * Cfg::STAGE_BYTES);
+        const uint32_t sb = sa + Cfg::A_BYTES;
+        const uint64_t adesc = ptx::make_smem_desc_sw128(sa);
+        const uint64_t bdesc = ptx::make_smem_desc_sw128(sb);
+        if (kb < main_kb && !(DBG && (args.dbg & 8))) {
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)  // +16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in (addr>>4)
+            ptx::umma_bf16_p(leader, tmem_acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        } else if (!(DBG && (args.dbg & 8))) {
+          for (int k = 0; k < args.lora_ksteps; ++k)
+            ptx::umma_bf16_p(leader, tmem_acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
         }
-        ptx::umma_commit(&tmem_full[buf]);  // accumulator complete
+        ptx::umma_commit_p(leader, &empty_bar[s]);  // smem slot reusable once these MMAs retire
       }
+      ptx::umma_commit_p(leader, &tmem_full[buf]);  // accumulator complete
     }
   } else {
     // ================================= epilogue warps 0..7 =================================

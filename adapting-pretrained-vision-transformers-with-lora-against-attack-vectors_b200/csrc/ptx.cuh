@@ -196,6 +196,111 @@ __device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ----------------------------------------------------------------------------------------------
+// Converged-warp issue.  Measured on B200 (scripts/micro/mma_rate.cu): a tcgen05.mma inside an `if (lane == 0)` region
+// costs 130-175 clk per instruction because the compiler wraps it in an ELECT / BRA.U.ANY loop; issued from a fully
+// converged warp under a predicate it costs 51 clk (N=64) to 123 clk (N=256, the tensor-pipe rate).  So the producer
+// and MMA warps run their loops with all 32 lanes and pass `leader` (1 in exactly one lane, from elect_leader()).
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t elect_leader() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred px;\n\t"
+      "elect.sync _|px, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred;
+}
+__device__ __forceinline__ void umma_bf16_p(uint32_t leader, uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ts_p(uint32_t leader, uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_p(uint32_t leader, uint64_t* bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_p(uint32_t leader, uint64_t* bar, uint32_t bytes) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %2, 0;\n\t"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(bytes), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_p(uint32_t leader, uint64_t* bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q mbarrier.arrive.shared::cta.b64 _, [%0];\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_p(uint32_t leader, void* smem_dst, const void* tmap, uint64_t* bar, int c0,
+                                              int c1) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t"
+      "}\n" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_p(uint32_t leader, void* smem_dst, const void* tmap, uint64_t* bar, int c0,
+                                              int c1, int c2) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %6, 0;\n\t"
+      "@q cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n\t"
+      "}\n" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d_p(uint32_t leader, void* smem_dst, const void* gsrc, uint32_t bytes,
+                                               uint64_t* bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %4, 0;\n\t"
+      "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t"
+      "}\n" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar)), "r"(leader)
+      : "memory");
+}
+
+// ----------------------------------------------------------------------------------------------
 // UMMA descriptors (PTX ISA "tcgen05 shared memory descriptor" / "instruction descriptor")
 // ----------------------------------------------------------------------------------------------
 // K-major operand tile, 128-byte swizzle: rows are 128 B apart, 8-row groups (one swizzle atom) are

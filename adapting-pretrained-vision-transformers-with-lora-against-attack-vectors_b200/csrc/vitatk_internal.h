@@ -98,6 +98,7 @@ int attention_bwd_plan_init(AttnBwdPlan* p, const bf16* qkv, const bf16* dout, c
                             float* delta, bf16* dqkv, int batch, int tokens, int heads);
 int attention_bwd_tc05(const AttnBwdPlan* p, cudaStream_t stream);        // two-kernel version (dQ, then dK/dV)
 int attention_bwd_fused(const AttnBwdPlan* p, cudaStream_t stream);       // single-pass version (engine default)
+int attention_bwd_set_trace(long long* dev_buf);                          // timing experiments only
 // mma.sync forward (round-1 first version, kept for cross-checking the tcgen05 kernel in tests)
 int attention_fwd(const bf16* qkv, bf16* out, int batch, int tokens, int heads, cudaStream_t stream);
 int attention_bwd(const bf16* qkv, const bf16* dout, bf16* dqkv, int batch, int tokens, int heads,

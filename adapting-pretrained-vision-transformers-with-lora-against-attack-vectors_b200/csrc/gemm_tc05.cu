@@ -32,15 +32,21 @@ static constexpr int MMA_WARP = 9;
 static constexpr int GEMM_THREADS = 320;
 static constexpr int CHUNK = 32;                  // epilogue column granule = one tcgen05.ld.32x32b.x32
 static constexpr int STAGE_OUT_BYTES = 32 * 64;   // one warp's 32-row x 32-col bf16 store tile (64 B swizzle)
+static constexpr int SLAB_BYTES = 128 * 128;      // pair kernel: 128-row x 64-col bf16 slab (128 B swizzle)
 
-template <int BN>
+// TWO = CTA-pair variant (cta_group::2): the pair computes a 256 x BN tile, each CTA stages its 128 rows of A and
+// HALF of the B tile per k-block (32 KB instead of 48 KB at BN = 256), which is what relieves the L2 -> SM operand path.
+template <int BN, bool TWO = false>
 struct GemmCfg {
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 192 ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_ROWS = TWO ? BN / 2 : BN;
+  static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = TWO ? 5 : ((BN == 256) ? 4 : (BN == 192 ? 4 : (BN == 128 ? 6 : 8)));
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
-  static constexpr int OUT_BYTES = NUM_EPI_WARPS * 2 * STAGE_OUT_BYTES;
+  // epilogue staging: single kernel = 2 x (32 rows x 32 cols) per warp; pair kernel = 2 column groups x 2 slabs of
+  // (128 rows x 64 cols, 128B swizzle) shared by the four warps of a group
+  static constexpr int OUT_BYTES = TWO ? 2 * 2 * SLAB_BYTES : NUM_EPI_WARPS * 2 * STAGE_OUT_BYTES;
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + OUT_BYTES + BAR_BYTES;
 };
@@ -112,13 +118,18 @@ __device__ __forceinline__ void stage_and_store(uint8_t* stage, const uint32_t (
   }
 }
 
-template <int BN, bool DBG>
+template <int BN, bool DBG, bool TWO>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmLA, const __grid_constant__ CUtensorMap tmLB,
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
-                 const GemmKernelArgs args) {
-  using Cfg = GemmCfg<BN>;
+                 const __grid_constant__ CUtensorMap tmAux, const GemmKernelArgs args) {
+  using Cfg = GemmCfg<BN, TWO>;
+  // CTA pair: rank 0 is the leader (issues the M = 256 MMAs); unit = CTA (single) or cluster (pair)
+  const uint32_t rank = TWO ? ptx::cluster_ctarank() : 0u;
+  const int unit = TWO ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int num_units = TWO ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  constexpr int TILE_M = TWO ? 2 * BM : BM;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   // 1024 B alignment: required by the 128B swizzle pattern shared by TMA and the UMMA descriptors
@@ -131,11 +142,12 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tmem_full = bars + 2 * STAGES;     // [2]
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* aux_bar = bars + 2 * STAGES + 5;   // [2 groups][2 slabs] residual / multiplier slab landed (pair kernel)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int tiles_m = (args.M + BM - 1) / BM;
+  const int tiles_m = (args.M + TILE_M - 1) / TILE_M;
   const int tiles_n = args.N / BN;
   const int num_tiles = tiles_m * tiles_n;
   const int main_kb = args.K / BK;
@@ -143,13 +155,14 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == MMA_WARP && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&full_bar[s], 1);  // pair: the leader's producer expects the bytes of BOTH CTAs' loads
       ptx::mbar_init(&empty_bar[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(&tmem_full[b], 1);
-      ptx::mbar_init(&tmem_empty[b], NUM_EPI_WARPS);
+      ptx::mbar_init(&tmem_empty[b], TWO ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS);  // pair: both CTAs' epilogue warps
     }
+    for (int i = 0; i < 4; ++i) ptx::mbar_init(&aux_bar[i], 1);
     ptx::fence_mbar_init();
   }
   if (warp == TMA_WARP) {
@@ -157,16 +170,23 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       ptx::prefetch_tmap(&tmA);
       ptx::prefetch_tmap(&tmB);
       ptx::prefetch_tmap(&tmOut);
+      if (TWO && (args.epi.mode == EPI_RESIDUAL || args.epi.mode == EPI_MUL)) ptx::prefetch_tmap(&tmAux);
       if (args.lora_nkb > 0) {
         ptx::prefetch_tmap(&tmLA);
         ptx::prefetch_tmap(&tmLB);
       }
     }
-    ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    ptx::tmem_relinquish();
+    if constexpr (TWO) {
+      ptx::tmem_alloc_2cta(tmem_slot, Cfg::TMEM_COLS);
+      ptx::tmem_relinquish_2cta();
+    } else {
+      ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (TWO) ptx::cluster_sync();  // barrier inits of both CTAs are visible before any remote arrive / TMA signal
+  else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -174,9 +194,10 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ================================= TMA producer (converged warp, elected lane issues) =================================
     const uint32_t leader = ptx::elect_leader();
     uint32_t cnt = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / tiles_n) * BM;
+    for (int tile = unit; tile < num_tiles; tile += num_units) {
+      const int m0 = (tile / tiles_n) * TILE_M + static_cast<int>(rank) * BM;        // this CTA's 128 rows of A
       const int n0 = (tile % tiles_n) * BN;
+      const int nb0 = n0 + static_cast<int>(rank) * Cfg::B_ROWS;                     // pair: this CTA's half of B
       const int tcol0 = args.lora_group_cols > 0 ? (n0 / args.lora_group_cols) * BK : 0;
       for (int kb = 0; kb < num_kb; ++kb, ++cnt) {
         const int s = cnt % STAGES;
@@ -184,54 +205,260 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         ptx::mbar_wait(&empty_bar[s], ph ^ 1);
         uint8_t* sa = smem_stage + s * Cfg::STAGE_BYTES;
         uint8_t* sb = sa + Cfg::A_BYTES;
-        if (DBG && (args.dbg & 4) && cnt >= STAGES) {
-          ptx::mbar_arrive_p(leader, &full_bar[s]);
-          continue;
-        }
-        ptx::mbar_arrive_expect_tx_p(leader, &full_bar[s], Cfg::STAGE_BYTES);
-        if (kb < main_kb) {
-          ptx::tma_load_2d_p(leader, sa, &tmA, &full_bar[s], kb * BK, m0);
-          ptx::tma_load_2d_p(leader, sb, &tmB, &full_bar[s], kb * BK, n0);
+        if constexpr (TWO) {
+          const uint32_t fb = ptx::mapa_shared(ptx::smem_u32(&full_bar[s]), 0);  // the leader CTA's full barrier
+          if (DBG && (args.dbg & 4) && cnt >= STAGES) {
+            if (rank == 0) ptx::mbar_arrive_p(leader, &full_bar[s]);
+            continue;
+          }
+          // Only the leader arrives (no remote round trip per k-block).  The peer's complete_tx may land first: the
+          // tx-count is signed and the phase cannot complete before the leader's pending arrival.
+          if (rank == 0) ptx::mbar_arrive_expect_tx_p(leader, &full_bar[s], 2 * Cfg::STAGE_BYTES);
+          if (kb < main_kb) {
+            ptx::tma_load_2d_2cta_p(leader, sa, &tmA, fb, kb * BK, m0);
+            ptx::tma_load_2d_2cta_p(leader, sb, &tmB, fb, kb * BK, nb0);
+          } else {
+            const int j = kb - main_kb;
+            ptx::tma_load_2d_2cta_p(leader, sa, &tmLA, fb, tcol0 + j * BK, m0);
+            ptx::tma_load_2d_2cta_p(leader, sb, &tmLB, fb, j * BK, nb0);
+          }
         } else {
-          const int j = kb - main_kb;
-          ptx::tma_load_2d_p(leader, sa, &tmLA, &full_bar[s], tcol0 + j * BK, m0);
-          ptx::tma_load_2d_p(leader, sb, &tmLB, &full_bar[s], j * BK, n0);
+          if (DBG && (args.dbg & 4) && cnt >= STAGES) {
+            ptx::mbar_arrive_p(leader, &full_bar[s]);
+            continue;
+          }
+          ptx::mbar_arrive_expect_tx_p(leader, &full_bar[s], Cfg::STAGE_BYTES);
+          if (kb < main_kb) {
+            ptx::tma_load_2d_p(leader, sa, &tmA, &full_bar[s], kb * BK, m0);
+            ptx::tma_load_2d_p(leader, sb, &tmB, &full_bar[s], kb * BK, n0);
+          } else {
+            const int j = kb - main_kb;
+            ptx::tma_load_2d_p(leader, sa, &tmLA, &full_bar[s], tcol0 + j * BK, m0);
+            ptx::tma_load_2d_p(leader, sb, &tmLB, &full_bar[s], j * BK, n0);
+          }
         }
       }
     }
   } else if (warp == MMA_WARP) {
     // ================================= MMA issuer (converged warp, elected lane issues) =================================
     const uint32_t leader = ptx::elect_leader();
-    constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN);
+    constexpr uint32_t idesc = ptx::make_idesc_bf16(TILE_M, BN);
     uint32_t cnt = 0;
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    if (!TWO || rank == 0) {
+      for (int tile = unit; tile < num_tiles; tile += num_units, ++it) {
+        const uint32_t buf = it & 1;
+        const uint32_t use = it >> 1;
+        // the epilogue warps (of both CTAs of a pair) have drained this accumulator
+        ptx::mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + buf * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++cnt) {
+          const int s = cnt % STAGES;
+          const uint32_t ph = (cnt / STAGES) & 1;
+          ptx::mbar_wait(&full_bar[s], ph);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem_stage + s * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::A_BYTES;
+          const uint64_t adesc = ptx::make_smem_desc_sw128(sa);
+          const uint64_t bdesc = ptx::make_smem_desc_sw128(sb);
+          const int ksteps = (kb < main_kb) ? BK / 16 : args.lora_ksteps;
+          if (!(DBG && (args.dbg & 8))) {
+            if (ksteps == BK / 16) {
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) {  // +16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in (addr>>4)
+                if constexpr (TWO)
+                  ptx::umma_bf16_2cta_p(leader, tmem_acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                else
+                  ptx::umma_bf16_p(leader, tmem_acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              }
+            } else {
+              for (int k = 0; k < ksteps; ++k) {
+                if constexpr (TWO)
+                  ptx::umma_bf16_2cta_p(leader, tmem_acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                else
+                  ptx::umma_bf16_p(leader, tmem_acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              }
+            }
+          }
+          // smem slot reusable (in both CTAs of a pair) once these MMAs retire
+          if constexpr (TWO) ptx::umma_commit_2cta_mc_p(leader, &empty_bar[s], 3);
+          else ptx::umma_commit_p(leader, &empty_bar[s]);
+        }
+        // accumulator complete
+        if constexpr (TWO) ptx::umma_commit_2cta_mc_p(leader, &tmem_full[buf], 3);
+        else ptx::umma_commit_p(leader, &tmem_full[buf]);
+      }
+    }
+  } else if constexpr (TWO) {
+    // ================================= slab epilogue (pair kernel), warps 0..7 =================================
+    // Column group g = warp / 4 owns columns [128 g, 128 g + 128) of the tile as two 64-column slabs; its four warps
+    // (TMEM lane quarters) fill one 128-row x 64-column slab in 128B-swizzled smem and ONE thread issues ONE TMA store
+    // per slab (4 per tile instead of 32 small ones, full 128-byte lines).  Residual / multiplier slabs are TMA-loaded
+    // into the same buffer one slab ahead and combined in place, so no strided per-lane global loads remain.
+    const int q = warp & 3;
+    const int g = warp >> 2;
+    const int trow = q * 32 + lane;  // row inside this CTA's 128-row block
+    const bool issuer = (q == 0) && (lane == 0);
+    const uint32_t gbuf = ptx::smem_u32(smem_out) + g * 2 * SLAB_BYTES;
+    uint64_t* aux_full = aux_bar + g * 2;
+    const uint32_t bar_id = 1 + g;
+    const uint32_t swz = trow & 7;
+    const GemmEpilogue epi = args.epi;
+    const bool has_aux = (epi.mode == EPI_RESIDUAL || epi.mode == EPI_MUL);
+    const bool no_store = DBG && (args.dbg & 2);
+    const uint32_t tmem_empty_remote = ptx::mapa_shared(ptx::smem_u32(&tmem_empty[0]), 0);  // the leader's barrier
+    uint32_t it = 0;
+    uint32_t c = 0;  // slabs this group has produced; slab c uses buffer c & 1
+    auto group_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory"); };
+    auto issue_aux = [&](uint32_t cc, int tile_, int sl_) {  // issuer thread only
+      const int am0 = (tile_ / tiles_n) * TILE_M + static_cast<int>(rank) * BM;
+      const int acol = (tile_ % tiles_n) * BN + g * 128 + sl_ * 64;
+      const uint32_t b = cc & 1;
+      ptx::mbar_arrive_expect_tx(&aux_full[b], SLAB_BYTES);
+      ptx::tma_load_2d(smem_out + g * 2 * SLAB_BYTES + b * SLAB_BYTES, &tmAux, &aux_full[b], acol, am0);
+    };
+    // write one packed 64-column row (32 registers) of this thread into slab buffer b
+    auto write_row = [&](uint32_t b, const uint32_t (&pk)[32]) {
+      const uint32_t rowaddr = gbuf + b * SLAB_BYTES + trow * 128;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t addr = rowaddr + ((j ^ swz) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * j]), "r"(pk[4 * j + 1]),
+                     "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
+                     : "memory");
+      }
+    };
+    // hand a filled slab to the TMA store engine (all four warps call; one thread issues)
+    auto store_slab = [&](uint32_t b, const CUtensorMap* tm, int col, int row0) {
+      ptx::fence_proxy_async_smem();
+      group_sync();
+      if (issuer && !no_store) {
+        ptx::tma_store_2d(tm, smem_out + g * 2 * SLAB_BYTES + b * SLAB_BYTES, col, row0);
+        ptx::tma_store_commit();
+      }
+    };
+    if (has_aux && issuer && unit < num_tiles) issue_aux(0, unit, 0);
+    for (int tile = unit; tile < num_tiles; tile += num_units, ++it) {
+      const int m0 = (tile / tiles_n) * TILE_M + static_cast<int>(rank) * BM;
+      const int n0 = (tile % tiles_n) * BN;
       const uint32_t buf = it & 1;
       const uint32_t use = it >> 1;
-      ptx::mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);  // epilogue has drained this accumulator
+      ptx::mbar_wait(&tmem_full[buf], use & 1);
       ptx::tc_fence_after();
-      const uint32_t tmem_acc = tmem_base + buf * BN;
-      for (int kb = 0; kb < num_kb; ++kb, ++cnt) {
-        const int s = cnt % STAGES;
-        const uint32_t ph = (cnt / STAGES) & 1;
-        ptx::mbar_wait(&full_bar[s], ph);
-        ptx::tc_fence_after();
-        const uint32_t sa = ptx::smem_u32(smem_stage + s * Cfg::STAGE_BYTES);
-        const uint32_t sb = sa + Cfg::A_BYTES;
-        const uint64_t adesc = ptx::make_smem_desc_sw128(sa);
-        const uint64_t bdesc = ptx::make_smem_desc_sw128(sb);
-        if (kb < main_kb && !(DBG && (args.dbg & 8))) {
+      const int row = m0 + trow;
+      const bool row_ok = row < args.M;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + g * 128;
+#pragma unroll 1
+      for (int sl = 0; sl < 2; ++sl) {
+        const int ncol = n0 + g * 128 + sl * 64;
+        float v[64];
+        if (!(DBG && (args.dbg & 16))) {
+          uint32_t r0[32], r1[32];
+          ptx::tmem_ld_32x32b_x32(taddr + sl * 64, r0);
+          ptx::tmem_ld_32x32b_x32(taddr + sl * 64 + 32, r1);
+          ptx::tmem_ld_wait();
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)  // +16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in (addr>>4)
-            ptx::umma_bf16_p(leader, tmem_acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-        } else if (!(DBG && (args.dbg & 8))) {
-          for (int k = 0; k < args.lora_ksteps; ++k)
-            ptx::umma_bf16_p(leader, tmem_acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int j = 0; j < 32; ++j) {
+            v[j] = __uint_as_float(r0[j]);
+            v[32 + j] = __uint_as_float(r1[j]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 64; ++j) v[j] = 0.f;
         }
-        ptx::umma_commit_p(leader, &empty_bar[s]);  // smem slot reusable once these MMAs retire
+        if (sl == 1) {  // every tcgen05.ld of this accumulator has completed -> hand it back to the MMA warp
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive_cluster(tmem_empty_remote + buf * 8);
+        }
+        if (epi.bias != nullptr) {
+          const float4* bp = reinterpret_cast<const float4*>(epi.bias + ncol);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float4 b = __ldg(bp + j);
+            v[4 * j] += b.x;
+            v[4 * j + 1] += b.y;
+            v[4 * j + 2] += b.z;
+            v[4 * j + 3] += b.w;
+          }
+        }
+        if (epi.mode == EPI_ROWTABLE && row_ok) {
+          const float4* tp =
+              reinterpret_cast<const float4*>(epi.table + static_cast<size_t>(row % epi.table_rows) * args.N + ncol);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float4 b = __ldg(tp + j);
+            v[4 * j] += b.x;
+            v[4 * j + 1] += b.y;
+            v[4 * j + 2] += b.z;
+            v[4 * j + 3] += b.w;
+          }
+        }
+        uint32_t pk[32];
+        if (epi.mode == EPI_GELU_DUAL) {
+          uint32_t pk2[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float g0, d0, g1, d1;
+            gelu_and_grad(v[2 * j], g0, d0);
+            gelu_and_grad(v[2 * j + 1], g1, d1);
+            pk[j] = pack_bf16x2(g0, g1);
+            pk2[j] = pack_bf16x2(d0, d1);
+          }
+          // two slabs per column slab: gelu(u) -> out, gelu'(u) -> out2
+          const uint32_t b0 = c & 1;
+          if (issuer) ptx::tma_store_wait_read<1>();  // the store that last used buffer b0 has read it out
+          group_sync();
+          write_row(b0, pk);
+          store_slab(b0, &tmOut, ncol, m0);
+          if (issuer) ptx::tma_store_wait_read<1>();
+          group_sync();
+          write_row(b0 ^ 1, pk2);
+          store_slab(b0 ^ 1, &tmOut2, ncol, m0);
+          c += 2;
+        } else if (has_aux) {
+          const uint32_t b = c & 1;
+          ptx::mbar_wait(&aux_full[b], (c >> 1) & 1);  // residual / multiplier slab landed (=> the buffer was free)
+          const uint32_t rowaddr = gbuf + b * SLAB_BYTES + trow * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint4 a;
+            const uint32_t addr = rowaddr + ((j ^ swz) << 4);
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(addr));
+            float f[8];
+            unpack_bf16x8(a, f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              if (epi.mode == EPI_RESIDUAL) v[8 * j + k] += f[k];
+              else v[8 * j + k] *= f[k];
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+          write_row(b, pk);  // in place: each thread only ever touches its own row of the slab
+          store_slab(b, &tmOut, ncol, m0);
+          ++c;
+          if (issuer) {
+            // the other buffer's last store has been read out -> fetch the next slab's residual / multiplier into it
+            ptx::tma_store_wait_read<1>();
+            if (sl == 0) issue_aux(c, tile, 1);
+            else if (tile + num_units < num_tiles) issue_aux(c, tile + num_units, 0);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+          const uint32_t b = c & 1;
+          if (issuer) ptx::tma_store_wait_read<1>();
+          group_sync();
+          write_row(b, pk);
+          store_slab(b, &tmOut, ncol, m0);
+          ++c;
+        }
       }
-      ptx::umma_commit_p(leader, &tmem_full[buf]);  // accumulator complete
     }
+    if (issuer) ptx::tma_store_wait_all<0>();
+    __syncwarp();
   } else {
     // ================================= epilogue warps 0..7 =================================
     // warp w owns TMEM lanes 32*(w%4).. (hardware rule) and column half w/4 of every tile.
@@ -247,8 +474,9 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
     for (int i = 0; i < 4; ++i) aux_next[i] = make_uint4(0, 0, 0, 0);
     // prefetch the aux (residual / multiplier) rows of the first chunk before the accumulator is ready
-    if (has_aux && static_cast<int>(blockIdx.x) < num_tiles) {
-      const int m0 = (blockIdx.x / tiles_n) * BM, n0 = (blockIdx.x % tiles_n) * BN;
+    const uint32_t tmem_empty_remote = TWO ? ptx::mapa_shared(ptx::smem_u32(&tmem_empty[0]), 0) : 0u;  // leader's barrier
+    if (has_aux && unit < num_tiles) {
+      const int m0 = (unit / tiles_n) * TILE_M + static_cast<int>(rank) * BM, n0 = (unit % tiles_n) * BN;
       const int row = m0 + q * 32 + lane;
       if (row < args.M) {
         const uint4* rp = reinterpret_cast<const uint4*>(epi.res + static_cast<size_t>(row) * epi.ld_res + n0 +
@@ -257,8 +485,8 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int i = 0; i < 4; ++i) aux_next[i] = __ldg(rp + i);
       }
     }
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int m0 = (tile / tiles_n) * BM;
+    for (int tile = unit; tile < num_tiles; tile += num_units, ++it) {
+      const int m0 = (tile / tiles_n) * TILE_M + static_cast<int>(rank) * BM;
       const int n0 = (tile % tiles_n) * BN;
       const uint32_t buf = it & 1;
       const uint32_t use = it >> 1;
@@ -282,9 +510,9 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           int nrow = row, ncol_next = ncol + CHUNK;
           bool ok = row_ok;
           if (i + 1 == CPW) {
-            const int nt = tile + gridDim.x;
+            const int nt = tile + num_units;
             ok = nt < num_tiles;
-            nrow = (nt / tiles_n) * BM + q * 32 + lane;
+            nrow = (nt / tiles_n) * TILE_M + static_cast<int>(rank) * BM + q * 32 + lane;
             ncol_next = (nt % tiles_n) * BN + hsel * CPW * CHUNK;
             ok = ok && nrow < args.M;
           }
@@ -361,17 +589,22 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // all tcgen05.ld of this accumulator have completed (wait::ld above) -> hand it back to the MMA warp
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tmem_empty[buf]);
+      if (lane == 0) {
+        if constexpr (TWO) ptx::mbar_arrive_cluster(tmem_empty_remote + buf * 8);
+        else ptx::mbar_arrive(&tmem_empty[buf]);
+      }
     }
     if (lane == 0) ptx::tma_store_wait_all<0>();
     __syncwarp();
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (TWO) ptx::cluster_sync();  // the peer's smem / TMEM stay valid until the leader's last MMA retired
+  else __syncthreads();
   if (warp == TMA_WARP) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if constexpr (TWO) ptx::tmem_dealloc_2cta(tmem_base, Cfg::TMEM_COLS);
+    else ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -477,6 +710,15 @@ int make_tmap_3d(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1, ui
   return 0;
 }
 
+static bool gemm_two_cta_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VITATK_GEMM_2CTA");  // "0" selects the single-CTA kernel for every shape
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 int gemm_plan_init(GemmPlan* p, int M, int N, int K, const bf16* A, int lda, const bf16* B, int ldb, bf16* out,
                    int ldo, bf16* out2, int ldo2, const bf16* T, int ldt, const bf16* LB, int ldlb, int lora_nkb,
                    int lora_ksteps, int lora_group_cols, GemmEpilogue epi) {
@@ -497,17 +739,27 @@ int gemm_plan_init(GemmPlan* p, int M, int N, int K, const bf16* A, int lda, con
     return 1;
   }
   if (make_tmap_2d(&p->tmA, A, M, K, lda, BK, BM)) return 1;
-  if (make_tmap_2d(&p->tmB, B, N, K, ldb, BK, p->BN)) return 1;
-  if (make_tmap_2d(&p->tmOut, out, M, N, ldo, CHUNK, 32, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+  p->two_cta = (p->BN == 256 && gemm_two_cta_enabled()) ? 1 : 0;
+  const int b_rows = p->two_cta ? p->BN / 2 : p->BN;
+  if (make_tmap_2d(&p->tmB, B, N, K, ldb, BK, b_rows)) return 1;
+  // store boxes: pair kernel = 64-col x 128-row slabs (128B swizzle); single kernel = 32 x 32 chunks (64B swizzle)
+  const uint32_t obc = p->two_cta ? 64 : CHUNK, obr = p->two_cta ? 128 : 32;
+  const CUtensorMapSwizzle osw = p->two_cta ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  if (make_tmap_2d(&p->tmOut, out, M, N, ldo, obc, obr, osw)) return 1;
   if (out2) {
-    if (make_tmap_2d(&p->tmOut2, out2, M, N, ldo2, CHUNK, 32, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+    if (make_tmap_2d(&p->tmOut2, out2, M, N, ldo2, obc, obr, osw)) return 1;
   } else {
     p->tmOut2 = p->tmOut;
+  }
+  if (p->two_cta && (epi.mode == EPI_RESIDUAL || epi.mode == EPI_MUL)) {
+    if (make_tmap_2d(&p->tmAux, epi.res, M, N, epi.ld_res, 64, 128)) return 1;
+  } else {
+    p->tmAux = p->tmOut;
   }
   if (lora_nkb > 0) {
     const int tcols = lora_group_cols > 0 ? (N / lora_group_cols) * 64 : lora_nkb * 64;
     if (make_tmap_2d(&p->tmLA, T, M, tcols, ldt, BK, BM)) return 1;
-    if (make_tmap_2d(&p->tmLB, LB, N, lora_nkb * 64, ldlb, BK, p->BN)) return 1;
+    if (make_tmap_2d(&p->tmLB, LB, N, lora_nkb * 64, ldlb, BK, b_rows)) return 1;
   } else {
     p->tmLA = p->tmA;
     p->tmLB = p->tmB;
@@ -524,19 +776,21 @@ static int gemm_dbg_flags() {
   return dbg;
 }
 
-template <int BN>
+template <int BN, bool TWO>
 static int launch_bn(const GemmPlan* p, cudaStream_t stream, int num_sms) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, TWO>;
   static bool attr_set = false;
   if (!attr_set) {
-    VITATK_CUDA_OK(cudaFuncSetAttribute(gemm_tc05_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    VITATK_CUDA_OK(cudaFuncSetAttribute(gemm_tc05_kernel<BN, false, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::SMEM_BYTES));
-    VITATK_CUDA_OK(cudaFuncSetAttribute(gemm_tc05_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    VITATK_CUDA_OK(cudaFuncSetAttribute(gemm_tc05_kernel<BN, true, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  const int tiles = ((p->M + BM - 1) / BM) * (p->N / BN);
-  const int grid = tiles < num_sms ? tiles : num_sms;
+  const int tile_m = TWO ? 2 * BM : BM;
+  const int tiles = ((p->M + tile_m - 1) / tile_m) * (p->N / BN);
+  const int max_units = TWO ? num_sms / 2 : num_sms;
+  const int units = tiles < max_units ? tiles : max_units;
   GemmKernelArgs a;
   a.M = p->M;
   a.N = p->N;
@@ -546,22 +800,33 @@ static int launch_bn(const GemmPlan* p, cudaStream_t stream, int num_sms) {
   a.lora_group_cols = p->lora_group_cols;
   a.epi = p->epi;
   a.dbg = gemm_dbg_flags();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(TWO ? 2 * units : units, 1, 1);
+  cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = TWO ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   if (a.dbg)
-    gemm_tc05_kernel<BN, true><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(p->tmA, p->tmB, p->tmLA, p->tmLB,
-                                                                              p->tmOut, p->tmOut2, a);
+    VITATK_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc05_kernel<BN, true, TWO>, p->tmA, p->tmB, p->tmLA, p->tmLB, p->tmOut,
+                                      p->tmOut2, p->tmAux, a));
   else
-    gemm_tc05_kernel<BN, false><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(p->tmA, p->tmB, p->tmLA, p->tmLB,
-                                                                               p->tmOut, p->tmOut2, a);
-  VITATK_CUDA_OK(cudaGetLastError());
+    VITATK_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc05_kernel<BN, false, TWO>, p->tmA, p->tmB, p->tmLA, p->tmLB, p->tmOut,
+                                      p->tmOut2, p->tmAux, a));
   return 0;
 }
 
 int gemm_launch(const GemmPlan* p, cudaStream_t stream, int num_sms) {
   switch (p->BN) {
-    case 256: return launch_bn<256>(p, stream, num_sms);
-    case 192: return launch_bn<192>(p, stream, num_sms);
-    case 128: return launch_bn<128>(p, stream, num_sms);
-    case 64: return launch_bn<64>(p, stream, num_sms);
+    case 256: return p->two_cta ? launch_bn<256, true>(p, stream, num_sms) : launch_bn<256, false>(p, stream, num_sms);
+    case 192: return launch_bn<192, false>(p, stream, num_sms);
+    case 128: return launch_bn<128, false>(p, stream, num_sms);
+    case 64: return launch_bn<64, false>(p, stream, num_sms);
   }
   set_error("gemm_launch: bad BN %d", p->BN);
   return 1;

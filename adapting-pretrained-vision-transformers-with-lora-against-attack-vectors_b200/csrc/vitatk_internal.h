@@ -50,13 +50,15 @@ struct GemmEpilogue {
 struct GemmPlan {
   // shapes
   int M, N, K;
-  int BN;               // 64, 128 or 256
+  int BN;               // 64, 128, 192 or 256
+  int two_cta;          // 1: CTA-pair kernel (cta_group::2, 256-row tiles, half of B per CTA); BN = 256 only
   int lora_nkb;         // extra 64-wide k-blocks (0 = no adapter)
   int lora_ksteps;      // UMMA k-steps (16 each) issued per extra k-block = ceil(r/16)
   int lora_group_cols;  // >0: T column offset = (n0 / lora_group_cols) * 64  (fused q|k|v forward)
   GemmEpilogue epi;
   // tensor maps (built once per plan)
   CUtensorMap tmA, tmB, tmLA, tmLB, tmOut, tmOut2;
+  CUtensorMap tmAux;    // residual / multiplier tensor as 64-col x 128-row slabs (pair kernel only)
 };
 
 // Build the TMA descriptors of a plan. Pointers may be null when the feature is unused.

@@ -536,7 +536,7 @@ int attention_bwd_set_trace(long long* dev_buf) {
   return 0;
 }
 
-int attention_bwd_fused(const AttnBwdPlan* p, cudaStream_t stream) {
+int attention_bwd_fused(const AttnBwdPlan* p, cudaStream_t stream, bool compute_delta) {
   static bool attr = false;
   if (!attr) {
     VITATK_CUDA_OK(cudaFuncSetAttribute(attn_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM));
@@ -553,7 +553,7 @@ int attention_bwd_fused(const AttnBwdPlan* p, cudaStream_t stream) {
     const char* e = getenv("VITATK_ATTN_DBG");
     dbg = e ? atoi(e) : 0;
   }
-  if (!(dbg & 16) && attention_delta(p, stream)) return 1;
+  if (compute_delta && !(dbg & 16) && attention_delta(p, stream)) return 1;
   attn_bwd_fused_kernel<<<items < sms ? items : sms, F_THREADS, F_SMEM, stream>>>(
       p->tmQKV128, p->tmQKV208, p->tmDO208, p->tmDqkv32, p->lse2, p->delta, p->tokens, p->heads, items, sl2, scale,
       dbg);

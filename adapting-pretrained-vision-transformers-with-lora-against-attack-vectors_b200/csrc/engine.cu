@@ -93,6 +93,7 @@ struct vitatk_engine {
   PixelNorm nrm;
   // optional per-launch CUDA-event timing (bench.py's roofline leg; off in the timed region)
   bool attn_bwd_two_kernel = false;  // VITATK_ATTN_BWD=2k selects the older dQ + dK/dV kernel pair
+  bool fuse_delta = false;           // delta comes out of the proj-backward GEMM epilogue (pair kernel) instead of a kernel
   bool prof = false;
   struct ProfRec { int cat; double flops; cudaEvent_t a, b; };
   std::vector<ProfRec> prof_recs;
@@ -116,7 +117,7 @@ static int build_plans(vitatk_engine* e, int batch, PlanSet** out) {
   ps->layers.resize(c.layers);
   ps->attn_fwd.resize(c.layers);
   ps->attn_bwd.resize(c.layers);
-  GemmEpilogue plain = {EPI_PLAIN, nullptr, nullptr, 0, nullptr, 0};
+  GemmEpilogue plain = {EPI_PLAIN, nullptr, nullptr, 0, nullptr, 0, nullptr, 0, 0};
   // patch embedding: h[0] = cols * Wpe^T + table[m % 197]
   {
     GemmEpilogue ep = {EPI_ROWTABLE, nullptr, nullptr, 0, e->embed_table, TOKENS};
@@ -200,9 +201,22 @@ static int build_plans(vitatk_engine* e, int batch, PlanSet** out) {
         gemm_plan_init(&p.bt_proj, M, LORA_PAD, D, e->dh_b, D, sp.lb_bwd, D, e->T, 3 * LORA_PAD, nullptr, 0, nullptr, 0,
                        nullptr, 0, 0, 0, 0, plain))
       return 1;
-    if (gemm_plan_init(&p.bproj, M, D, D, e->dh_b, D, w.proj_wt, D, e->dao, D, nullptr, 0, e->T, 3 * LORA_PAD,
-                       sp.la_bwd, LORA_PAD, sp.rank > 0 ? 1 : 0, lora_ksteps(sp.rank), 0, plain))
-      return 1;
+    {
+      // proj backward also produces attention's delta = rowsum(dO o O) per (image, head, query): one 64-column slab of
+      // the output is one head, so the pair kernel's slab epilogue gets it for free (replaces a 154 MB pass)
+      GemmEpilogue ep = plain;
+      if (e->fuse_delta) {
+        ep.mode = EPI_ROWDOT;
+        ep.res = e->ao[l];
+        ep.ld_res = D;
+        ep.rowdot = e->delta;
+        ep.rowdot_rows = TOKENS;
+        ep.rowdot_pad = 208;
+      }
+      if (gemm_plan_init(&p.bproj, M, D, D, e->dh_b, D, w.proj_wt, D, e->dao, D, nullptr, 0, e->T, 3 * LORA_PAD,
+                         sp.la_bwd, LORA_PAD, sp.rank > 0 ? 1 : 0, lora_ksteps(sp.rank), 0, ep))
+        return 1;
+    }
     if (sq.rank > 0 &&
         gemm_plan_init(&p.bt_qkv, M, 3 * LORA_PAD, 3 * D, e->dqkv, 3 * D, sq.lb_bwd, 3 * D, e->T, 3 * LORA_PAD, nullptr,
                        0, nullptr, 0, nullptr, 0, 0, 0, 0, plain))
@@ -295,7 +309,8 @@ static int encoder_backward(vitatk_engine* e, PlanSet* ps, int batch, cudaStream
     if (w.lora[VITATK_SITE_PROJ].rank > 0) RUN_GEMM(CAT_BT_PROJ, &p.bt_proj);
     RUN_GEMM(CAT_BPROJ, &p.bproj);  // dao = dh_mid Wp + lora
     RUNC(CAT_ATTN_BWD, 8.0 * batch * c.heads * TOKENS * TOKENS * 64,
-         e->attn_bwd_two_kernel ? attention_bwd_tc05(&ps->attn_bwd[l], s) : attention_bwd_fused(&ps->attn_bwd[l], s));
+         e->attn_bwd_two_kernel ? attention_bwd_tc05(&ps->attn_bwd[l], s)
+                                : attention_bwd_fused(&ps->attn_bwd[l], s, !e->fuse_delta));
     if (w.lora[VITATK_SITE_QKV].rank > 0) RUN_GEMM(CAT_BT_QKV, &p.bt_qkv);
     RUN_GEMM(CAT_BQKV, &p.bqkv);  // dxn = dqkv Wqkv + lora
     RUNC(CAT_LN_BWD, 0, layernorm_bwd(e->dxn, e->h[l], e->st1[l], w.ln1_g, e->dh_b, e->dh_a, M, D, s));  // dh wrt h[l]
@@ -351,6 +366,9 @@ int vitatk_create(const vitatk_config* cfg, vitatk_engine** out) {
   {
     const char* v = getenv("VITATK_ATTN_BWD");
     e->attn_bwd_two_kernel = v && strcmp(v, "2k") == 0;
+    const char* g2 = getenv("VITATK_GEMM_2CTA");
+    const char* fd = getenv("VITATK_FUSE_DELTA");
+    e->fuse_delta = !e->attn_bwd_two_kernel && !(g2 && g2[0] == '0') && !(fd && fd[0] == '0') && cfg->dim % 256 == 0;
   }
   e->lw.resize(cfg->layers);
   for (int i = 0; i < 3; ++i) {
@@ -652,9 +670,10 @@ int vitatk_count_correct(vitatk_engine* e, const float* images, const int64_t* l
 int vitatk_k_gemm(int M, int N, int K, const void* A, int lda, const void* B, int ldb, void* out, int ldo, void* out2,
                   int ldo2, const void* T, int ldt, const void* LB, int ldlb, int lora_nkb, int lora_ksteps_,
                   int lora_group_cols, int epi_mode, const float* bias, const void* res, int ld_res, const float* table,
-                  int table_rows, int use_simt, void* stream) {
+                  int table_rows, float* rowdot, int rowdot_rows, int rowdot_pad, int use_simt, void* stream) {
   GemmPlan p;
-  GemmEpilogue ep = {epi_mode, bias, static_cast<const bf16*>(res), ld_res, table, table_rows};
+  GemmEpilogue ep = {epi_mode, bias, static_cast<const bf16*>(res), ld_res, table, table_rows, rowdot, rowdot_rows,
+                     rowdot_pad};
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (use_simt) {
     p.M = M; p.N = N; p.K = K; p.BN = 0;
@@ -696,7 +715,7 @@ int vitatk_k_attention_bwd_fused(const void* qkv, const void* dout, const void* 
   if (attention_bwd_plan_init(&p, static_cast<const bf16*>(qkv), static_cast<const bf16*>(dout),
                               static_cast<const bf16*>(o), lse2, delta, static_cast<bf16*>(dqkv), batch, tokens, heads))
     return 1;
-  return attention_bwd_fused(&p, static_cast<cudaStream_t>(stream));
+  return attention_bwd_fused(&p, static_cast<cudaStream_t>(stream), true);
 }
 int vitatk_k_attention_bwd_trace(long long* dev_buf) { return attention_bwd_set_trace(dev_buf); }
 int vitatk_k_attention_bwd(const void* qkv, const void* dout, void* dqkv, int batch, int tokens, int heads,

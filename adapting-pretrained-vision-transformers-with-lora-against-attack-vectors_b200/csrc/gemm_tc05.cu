@@ -170,7 +170,8 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       ptx::prefetch_tmap(&tmA);
       ptx::prefetch_tmap(&tmB);
       ptx::prefetch_tmap(&tmOut);
-      if (TWO && (args.epi.mode == EPI_RESIDUAL || args.epi.mode == EPI_MUL)) ptx::prefetch_tmap(&tmAux);
+      if (TWO && (args.epi.mode == EPI_RESIDUAL || args.epi.mode == EPI_MUL || args.epi.mode == EPI_ROWDOT))
+        ptx::prefetch_tmap(&tmAux);
       if (args.lora_nkb > 0) {
         ptx::prefetch_tmap(&tmLA);
         ptx::prefetch_tmap(&tmLB);
@@ -305,7 +306,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t bar_id = 1 + g;
     const uint32_t swz = trow & 7;
     const GemmEpilogue epi = args.epi;
-    const bool has_aux = (epi.mode == EPI_RESIDUAL || epi.mode == EPI_MUL);
+    const bool has_aux = (epi.mode == EPI_RESIDUAL || epi.mode == EPI_MUL || epi.mode == EPI_ROWDOT);
     const bool no_store = DBG && (args.dbg & 2);
     const uint32_t tmem_empty_remote = ptx::mapa_shared(ptx::smem_u32(&tmem_empty[0]), 0);  // the leader's barrier
     uint32_t it = 0;
@@ -421,6 +422,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t b = c & 1;
           ptx::mbar_wait(&aux_full[b], (c >> 1) & 1);  // residual / multiplier slab landed (=> the buffer was free)
           const uint32_t rowaddr = gbuf + b * SLAB_BYTES + trow * 128;
+          float dot = 0.f;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             uint4 a;
@@ -428,14 +430,31 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(addr));
             float f[8];
             unpack_bf16x8(a, f);
+            if (epi.mode == EPI_ROWDOT) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              if (epi.mode == EPI_RESIDUAL) v[8 * j + k] += f[k];
-              else v[8 * j + k] *= f[k];
+              for (int k = 0; k < 4; ++k) {
+                pk[4 * j + k] = pack_bf16x2(v[8 * j + 2 * k], v[8 * j + 2 * k + 1]);
+                // the consumer reads the bf16-rounded values, so the dot product uses them too
+                const float lo = __uint_as_float(pk[4 * j + k] << 16), hi = __uint_as_float(pk[4 * j + k] & 0xffff0000u);
+                dot = fmaf(lo, f[2 * k], dot);
+                dot = fmaf(hi, f[2 * k + 1], dot);
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                if (epi.mode == EPI_RESIDUAL) v[8 * j + k] += f[k];
+                else v[8 * j + k] *= f[k];
+              }
             }
           }
+          if (epi.mode == EPI_ROWDOT) {
+            if (row_ok)
+              epi.rowdot[(static_cast<size_t>(row / epi.rowdot_rows) * (args.N >> 6) + (ncol >> 6)) * epi.rowdot_pad +
+                         row % epi.rowdot_rows] = dot;
+          } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+            for (int j = 0; j < 32; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+          }
           write_row(b, pk);  // in place: each thread only ever touches its own row of the slab
           store_slab(b, &tmOut, ncol, m0);
           ++c;
@@ -631,6 +650,9 @@ __global__ void gemm_simt_kernel(GemmKernelArgs args, const bf16* A, int lda, co
   if (e.mode == EPI_RESIDUAL) acc += __bfloat162float(e.res[(size_t)m * e.ld_res + n]);
   if (e.mode == EPI_MUL) acc *= __bfloat162float(e.res[(size_t)m * e.ld_res + n]);
   if (e.mode == EPI_ROWTABLE) acc += e.table[(size_t)(m % e.table_rows) * args.N + n];
+  if (e.mode == EPI_ROWDOT)  // side buffer must be zeroed by the caller
+    atomicAdd(&e.rowdot[((size_t)(m / e.rowdot_rows) * (args.N >> 6) + (n >> 6)) * e.rowdot_pad + m % e.rowdot_rows],
+              __bfloat162float(__float2bfloat16(acc)) * __bfloat162float(e.res[(size_t)m * e.ld_res + n]));
   if (e.mode == EPI_GELU_DUAL) {
     out[(size_t)m * ldo + n] = __float2bfloat16(gelu_exact(acc));
     out2[(size_t)m * ldo2 + n] = __float2bfloat16(gelu_grad(acc));
@@ -751,7 +773,11 @@ int gemm_plan_init(GemmPlan* p, int M, int N, int K, const bf16* A, int lda, con
   } else {
     p->tmOut2 = p->tmOut;
   }
-  if (p->two_cta && (epi.mode == EPI_RESIDUAL || epi.mode == EPI_MUL)) {
+  if (epi.mode == EPI_ROWDOT && (!p->two_cta || !epi.rowdot || epi.rowdot_rows <= 0)) {
+    set_error("gemm_plan_init: EPI_ROWDOT needs the pair kernel (N %% 256 == 0, VITATK_GEMM_2CTA != 0) and a side buffer");
+    return 1;
+  }
+  if (p->two_cta && (epi.mode == EPI_RESIDUAL || epi.mode == EPI_MUL || epi.mode == EPI_ROWDOT)) {
     if (make_tmap_2d(&p->tmAux, epi.res, M, N, epi.ld_res, 64, 128)) return 1;
   } else {
     p->tmAux = p->tmOut;

@@ -35,7 +35,9 @@ enum EpiMode : int {
   EPI_RESIDUAL = 1,   // out = acc + bias + res
   EPI_GELU_DUAL = 2,  // u = acc + bias ; out = gelu(u) ; out2 = gelu'(u)   (fc1 forward; gelu' is what backward needs)
   EPI_MUL = 3,        // out = acc * res                                  (fc2 backward: dU = dG * gelu'(u))
-  EPI_ROWTABLE = 4    // out = acc + table[m % table_rows][n]            (patch embed: bias+pos / cls+pos)
+  EPI_ROWTABLE = 4,   // out = acc + table[m % table_rows][n]            (patch embed: bias+pos / cls+pos)
+  EPI_ROWDOT = 5      // out = acc ; rowdot[(m / rows) * (N/64) + n/64][m % rows] = sum over the 64-column slab of
+                      // bf16(out) * res   (proj backward: attention's delta = rowsum(dO o O) per head; pair kernel only)
 };
 
 struct GemmEpilogue {
@@ -45,6 +47,9 @@ struct GemmEpilogue {
   int ld_res;
   const float* table;   // [table_rows, N] fp32 (EPI_ROWTABLE)
   int table_rows;
+  float* rowdot;        // EPI_ROWDOT side output, [(M / rowdot_rows) * (N / 64), rowdot_pad] fp32
+  int rowdot_rows;      // rows per group (tokens per image)
+  int rowdot_pad;       // row pitch of the side output (208)
 };
 
 struct GemmPlan {
@@ -99,7 +104,8 @@ struct AttnBwdPlan {
 int attention_bwd_plan_init(AttnBwdPlan* p, const bf16* qkv, const bf16* dout, const bf16* o, const float* lse2,
                             float* delta, bf16* dqkv, int batch, int tokens, int heads);
 int attention_bwd_tc05(const AttnBwdPlan* p, cudaStream_t stream);        // two-kernel version (dQ, then dK/dV)
-int attention_bwd_fused(const AttnBwdPlan* p, cudaStream_t stream);       // single-pass version (engine default)
+// single-pass version (engine default); compute_delta = false when delta was already produced (EPI_ROWDOT GEMM)
+int attention_bwd_fused(const AttnBwdPlan* p, cudaStream_t stream, bool compute_delta);
 int attention_bwd_set_trace(long long* dev_buf);                          // timing experiments only
 // mma.sync forward (round-1 first version, kept for cross-checking the tcgen05 kernel in tests)
 int attention_fwd(const bf16* qkv, bf16* out, int batch, int tokens, int heads, cudaStream_t stream);

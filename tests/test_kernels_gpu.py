@@ -7,7 +7,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-EPI_PLAIN, EPI_RESIDUAL, EPI_GELU_DUAL, EPI_MUL, EPI_ROWTABLE = 0, 1, 2, 3, 4
+EPI_PLAIN, EPI_RESIDUAL, EPI_GELU_DUAL, EPI_MUL, EPI_ROWTABLE, EPI_ROWDOT = 0, 1, 2, 3, 4, 5
 
 
 def _s():
@@ -27,7 +27,7 @@ def _dgelu(u):
 
 
 def run_gemm(lib, A, B, epi=EPI_PLAIN, bias=None, res=None, table=None, T=None, LB=None, nkb=0, ksteps=0,
-             group_cols=0, simt=False):
+             group_cols=0, simt=False, rowdot=None, rowdot_rows=0):
     from vitatk import _lib
 
     M, K = A.shape
@@ -37,7 +37,8 @@ def run_gemm(lib, A, B, epi=EPI_PLAIN, bias=None, res=None, table=None, T=None, 
     rc = lib.vitatk_k_gemm(M, N, K, _p(A), A.stride(0), _p(B), B.stride(0), _p(out), N, _p(out2), N, _p(T),
                            0 if T is None else T.stride(0), _p(LB), 0 if LB is None else LB.stride(0), nkb, ksteps,
                            group_cols, epi, _p(bias), _p(res), 0 if res is None else res.stride(0), _p(table),
-                           0 if table is None else table.shape[0], 1 if simt else 0, _s())
+                           0 if table is None else table.shape[0], _p(rowdot), rowdot_rows,
+                           0 if rowdot is None else rowdot.shape[1], 1 if simt else 0, _s())
     _lib.check(rc, "vitatk_k_gemm")
     torch.cuda.synchronize()
     return out, out2
@@ -144,6 +145,27 @@ def test_gemm_tc05_vs_torch(lib, M, N, K, epi, lora):
         check_close(s_out, want, "simt gemm")
         if epi == EPI_GELU_DUAL:
             check_close(s_out2, want2, "simt gelu'")
+
+
+@pytest.mark.parametrize("images,tokens", [(8, 197), (3, 50), (256, 197)])
+def test_gemm_rowdot_epilogue(lib, images, tokens):
+    """proj backward with the fused attention delta: out = A B^T (+ LoRA), side[b*12 + h, i] = sum_64 bf16(out) * res."""
+    M, N, K = images * tokens, 768, 768
+    g = torch.Generator(device="cuda").manual_seed(images)
+    rn = lambda *s: torch.randn(*s, device="cuda", generator=g)  # noqa: E731
+    A = rn(M, K).to(torch.bfloat16)
+    B = (rn(N, K) / math.sqrt(K)).to(torch.bfloat16)
+    res = rn(M, N).to(torch.bfloat16)
+    T = torch.zeros(M, 64, device="cuda")
+    LB = torch.zeros(N, 64, device="cuda")
+    T[:, :8], LB[:, :8] = rn(M, 8), rn(N, 8) * 0.1
+    T, LB = T.to(torch.bfloat16), LB.to(torch.bfloat16)
+    side = torch.full((images * 12, 208), float("nan"), device="cuda")
+    out, _ = run_gemm(lib, A, B, EPI_ROWDOT, None, res, None, T, LB, 1, 1, 0, rowdot=side, rowdot_rows=tokens)
+    want, _ = ref_gemm(A, B, EPI_PLAIN, None, None, None, T, LB, 1, 1, 0)
+    check_close(out, want, "rowdot gemm out")
+    dref = (out.float() * res.float()).reshape(images, tokens, 12, 64).sum(-1).permute(0, 2, 1).reshape(images * 12, tokens)
+    torch.testing.assert_close(side[:, :tokens], dref, rtol=2e-3, atol=2e-3)
 
 
 def test_gemm_rejects_bad_shapes(lib):

@@ -36,6 +36,24 @@ def algorithmic_gflop_per_image_step(r=RANK_R):
     return (fwd + bwd + 2 * L * lora) / 1e9
 
 
+def ncu_traffic_per_launch(kernel_prefix="gemm_tc05_kernel<256"):
+    """dram read+write bytes per launch of the dominant kernel from the newest committed ncu launch list
+    (profiles/*_launches_summary.json, made by scripts/ncu_launch_summary.py); None if no profile is present."""
+    import glob
+
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_launches_summary.json")))
+    if not files:
+        return None, None
+    try:
+        d = json.load(open(files[-1]))["kernels"]
+        for name, k in d.items():
+            if name.startswith(kernel_prefix):
+                return (k["dram_read_mb_per_launch"] + k["dram_write_mb_per_launch"]) * 1e6, os.path.basename(files[-1])
+    except Exception:
+        pass
+    return None, None
+
+
 def measured_peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
@@ -255,6 +273,7 @@ def run_engine(args):
     peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
     total_prof_ms = sum(v["ms"] for v in prof.values())
     gflop_img = algorithmic_gflop_per_image_step() * PGD_STEPS
+    traffic, traffic_src = ncu_traffic_per_launch()
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -268,7 +287,9 @@ def run_engine(args):
                 "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8, "d2h_bytes_per_step": adv_host.numel() * 4},
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "achieved": gemm_tflops, "peak": peak, "unit": "TFLOP/s",
-                     "frac": gemm_tflops / peak, "traffic": None,
+                     "frac": gemm_tflops / peak, "traffic": traffic, "traffic_source": traffic_src,
+                     "algorithmic_flops_per_launch": gemm["flops"] / max(gemm["launches"], 1),
+                     "avg_launch_us": gemm["ms"] * 1e3 / max(gemm["launches"], 1),
                      "kernel": "gemm_tc05_kernel (all main GEMM launches of one PGD-10 step, CUDA events per launch)",
                      "peak_kind": f"{peaks_kind} sustained cuBLAS bf16",
                      "kernel_share_of_step": gemm["ms"] / total_prof_ms,

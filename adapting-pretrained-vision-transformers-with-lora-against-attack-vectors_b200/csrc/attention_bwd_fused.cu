@@ -173,6 +173,8 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_
   const uint32_t tmem = *tmem_slot;
   const int my_items =
       (num_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == F_TMA_WARP) {
     // ======================================= TMA producer (converged warp) =======================================
@@ -554,10 +556,9 @@ int attention_bwd_fused(const AttnBwdPlan* p, cudaStream_t stream, bool compute_
     dbg = e ? atoi(e) : 0;
   }
   if (compute_delta && !(dbg & 16) && attention_delta(p, stream)) return 1;
-  attn_bwd_fused_kernel<<<items < sms ? items : sms, F_THREADS, F_SMEM, stream>>>(
-      p->tmQKV128, p->tmQKV208, p->tmDO208, p->tmDqkv32, p->lse2, p->delta, p->tokens, p->heads, items, sl2, scale,
-      dbg);
-  VITATK_CUDA_OK(cudaGetLastError());
+  VITATK_CUDA_OK(launch_pdl(attn_bwd_fused_kernel, dim3(items < sms ? items : sms), dim3(F_THREADS), F_SMEM, stream, 1,
+                            p->tmQKV128, p->tmQKV208, p->tmDO208, p->tmDqkv32, p->lse2, p->delta, p->tokens, p->heads,
+                            items, sl2, scale, dbg));
   return 0;
 }
 

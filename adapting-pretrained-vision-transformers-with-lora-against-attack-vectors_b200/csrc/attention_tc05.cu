@@ -112,6 +112,8 @@ attn_fwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == A_TMA_WARP) {
     {
@@ -287,9 +289,8 @@ int attention_fwd_tc05(const AttnFwdPlan* p, cudaStream_t stream) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int items = p->batch * p->heads;
-  attn_fwd_tc05_kernel<<<items < sms ? items : sms, A_THREADS, A_SMEM, stream>>>(p->tmQ, p->tmKV, p->tmO, p->lse2,
-                                                                                p->tokens, p->heads, items, sl2);
-  VITATK_CUDA_OK(cudaGetLastError());
+  VITATK_CUDA_OK(launch_pdl(attn_fwd_tc05_kernel, dim3(items < sms ? items : sms), dim3(A_THREADS), A_SMEM, stream, 1,
+                            p->tmQ, p->tmKV, p->tmO, p->lse2, p->tokens, p->heads, items, sl2));
   return 0;
 }
 

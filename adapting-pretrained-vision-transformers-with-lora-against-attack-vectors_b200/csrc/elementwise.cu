@@ -38,6 +38,8 @@ template <int CH>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, bf16* __restrict__ y,
                                                      float2* __restrict__ stats, int rows, float eps) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -83,6 +85,8 @@ template <int CH>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                                                      const float2* __restrict__ stats, const float* __restrict__ gamma,
                                                      const bf16* __restrict__ dres, bf16* __restrict__ dx, int rows) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -128,10 +132,10 @@ int layernorm_fwd(const bf16* x, const float* gamma, const float* beta, bf16* y,
                   float eps, cudaStream_t stream) {
   const int grid = (rows + 7) / 8;
   switch (cols) {
-    case 768: ln_fwd_kernel<3><<<grid, 256, 0, stream>>>(x, gamma, beta, y, stats, rows, eps); break;
-    case 1024: ln_fwd_kernel<4><<<grid, 256, 0, stream>>>(x, gamma, beta, y, stats, rows, eps); break;
-    case 512: ln_fwd_kernel<2><<<grid, 256, 0, stream>>>(x, gamma, beta, y, stats, rows, eps); break;
-    case 256: ln_fwd_kernel<1><<<grid, 256, 0, stream>>>(x, gamma, beta, y, stats, rows, eps); break;
+    case 768: VITATK_CUDA_OK(launch_pdl(ln_fwd_kernel<3>, dim3(grid), dim3(256), 0, stream, 1, x, gamma, beta, y, stats, rows, eps)); break;
+    case 1024: VITATK_CUDA_OK(launch_pdl(ln_fwd_kernel<4>, dim3(grid), dim3(256), 0, stream, 1, x, gamma, beta, y, stats, rows, eps)); break;
+    case 512: VITATK_CUDA_OK(launch_pdl(ln_fwd_kernel<2>, dim3(grid), dim3(256), 0, stream, 1, x, gamma, beta, y, stats, rows, eps)); break;
+    case 256: VITATK_CUDA_OK(launch_pdl(ln_fwd_kernel<1>, dim3(grid), dim3(256), 0, stream, 1, x, gamma, beta, y, stats, rows, eps)); break;
     default: set_error("layernorm_fwd: cols=%d unsupported", cols); return 1;
   }
   VITATK_CUDA_OK(cudaGetLastError());
@@ -142,10 +146,10 @@ int layernorm_bwd(const bf16* dy, const bf16* x, const float2* stats, const floa
                   bf16* dx_out, int rows, int cols, cudaStream_t stream) {
   const int grid = (rows + 7) / 8;
   switch (cols) {
-    case 768: ln_bwd_kernel<3><<<grid, 256, 0, stream>>>(dy, x, stats, gamma, dres, dx_out, rows); break;
-    case 1024: ln_bwd_kernel<4><<<grid, 256, 0, stream>>>(dy, x, stats, gamma, dres, dx_out, rows); break;
-    case 512: ln_bwd_kernel<2><<<grid, 256, 0, stream>>>(dy, x, stats, gamma, dres, dx_out, rows); break;
-    case 256: ln_bwd_kernel<1><<<grid, 256, 0, stream>>>(dy, x, stats, gamma, dres, dx_out, rows); break;
+    case 768: VITATK_CUDA_OK(launch_pdl(ln_bwd_kernel<3>, dim3(grid), dim3(256), 0, stream, 1, dy, x, stats, gamma, dres, dx_out, rows)); break;
+    case 1024: VITATK_CUDA_OK(launch_pdl(ln_bwd_kernel<4>, dim3(grid), dim3(256), 0, stream, 1, dy, x, stats, gamma, dres, dx_out, rows)); break;
+    case 512: VITATK_CUDA_OK(launch_pdl(ln_bwd_kernel<2>, dim3(grid), dim3(256), 0, stream, 1, dy, x, stats, gamma, dres, dx_out, rows)); break;
+    case 256: VITATK_CUDA_OK(launch_pdl(ln_bwd_kernel<1>, dim3(grid), dim3(256), 0, stream, 1, dy, x, stats, gamma, dres, dx_out, rows)); break;
     default: set_error("layernorm_bwd: cols=%d unsupported", cols); return 1;
   }
   VITATK_CUDA_OK(cudaGetLastError());
@@ -172,6 +176,8 @@ __global__ void __launch_bounds__(256) head_kernel(const bf16* __restrict__ h, c
                                                    float* __restrict__ logits, float* __restrict__ loss,
                                                    bf16* __restrict__ dh, int tokens, int dim, int classes, float eps,
                                                    float grad_scale) {
+  pdl_wait();
+  pdl_launch_dependents();
   extern __shared__ float hs[];
   float* xn = hs;              // [dim] normalised (x-mean)*rstd
   float* yv = xn + dim;        // [dim] LN output
@@ -253,9 +259,8 @@ int head_fwd_bwd(const bf16* h, const float* gamma, const float* beta, const flo
     return 1;
   }
   const size_t smem = (3 * dim + classes) * sizeof(float);
-  head_kernel<<<batch, 256, smem, stream>>>(h, gamma, beta, Wc, bc, labels, logits, loss, dh, tokens, dim, classes, eps,
-                                            grad_scale);
-  VITATK_CUDA_OK(cudaGetLastError());
+  VITATK_CUDA_OK(launch_pdl(head_kernel, dim3(batch), dim3(256), smem, stream, 1, h, gamma, beta, Wc, bc, labels, logits,
+                            loss, dh, tokens, dim, classes, eps, grad_scale));
   return 0;
 }
 
@@ -345,6 +350,8 @@ __global__ void __launch_bounds__(256) pgd_init_kernel(const float* __restrict__
 __global__ void __launch_bounds__(256) pgd_update_kernel(const bf16* __restrict__ dcols, const float* __restrict__ x0,
                                                          float* __restrict__ adv, bf16* __restrict__ cols, int batch,
                                                          PixelNorm nrm, float eps, float alpha) {
+  pdl_wait();
+  pdl_launch_dependents();
   const long long total = static_cast<long long>(batch) * 3 * IMG * 28;
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= total) return;
@@ -424,8 +431,8 @@ int pgd_init(const float* x0, const float* noise, float* adv, bf16* cols, int ba
 }
 int pgd_update(const bf16* dcols, const float* x0, float* adv, bf16* cols, int batch, PixelNorm nrm, float eps,
                float alpha, cudaStream_t stream) {
-  pgd_update_kernel<<<pixel_grid(batch), 256, 0, stream>>>(dcols, x0, adv, cols, batch, nrm, eps, alpha);
-  VITATK_CUDA_OK(cudaGetLastError());
+  VITATK_CUDA_OK(launch_pdl(pgd_update_kernel, dim3(pixel_grid(batch)), dim3(256), 0, stream, 1, dcols, x0, adv, cols,
+                            batch, nrm, eps, alpha));
   return 0;
 }
 int grad_to_image(const bf16* dcols, float* grad, int batch, PixelNorm nrm, float scale, cudaStream_t stream) {

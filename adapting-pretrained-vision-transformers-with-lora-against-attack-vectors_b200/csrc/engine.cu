@@ -31,6 +31,15 @@ void set_error(const char* fmt, ...) {
 }
 const char* last_error() { return g_err; }
 
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VITATK_PDL");  // measured on B200: no gain (937.8 vs 941.6 adv img/s), so opt-in
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 static constexpr int TOKENS = 197;
 static constexpr int LORA_PAD = 64;
 

@@ -190,6 +190,8 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();               // everything above overlapped the previous kernel; global memory is touched only below
+  pdl_launch_dependents();
 
   if (warp == TMA_WARP) {
     // ================================= TMA producer (converged warp, elected lane issues) =================================
@@ -826,24 +828,13 @@ static int launch_bn(const GemmPlan* p, cudaStream_t stream, int num_sms) {
   a.lora_group_cols = p->lora_group_cols;
   a.epi = p->epi;
   a.dbg = gemm_dbg_flags();
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(TWO ? 2 * units : units, 1, 1);
-  cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
-  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = TWO ? 2 : 1;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  const dim3 grid(TWO ? 2 * units : units, 1, 1), block(GEMM_THREADS, 1, 1);
   if (a.dbg)
-    VITATK_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc05_kernel<BN, true, TWO>, p->tmA, p->tmB, p->tmLA, p->tmLB, p->tmOut,
-                                      p->tmOut2, p->tmAux, a));
+    VITATK_CUDA_OK(launch_pdl(gemm_tc05_kernel<BN, true, TWO>, grid, block, Cfg::SMEM_BYTES, stream, TWO ? 2 : 1, p->tmA,
+                              p->tmB, p->tmLA, p->tmLB, p->tmOut, p->tmOut2, p->tmAux, a));
   else
-    VITATK_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc05_kernel<BN, false, TWO>, p->tmA, p->tmB, p->tmLA, p->tmLB, p->tmOut,
-                                      p->tmOut2, p->tmAux, a));
+    VITATK_CUDA_OK(launch_pdl(gemm_tc05_kernel<BN, false, TWO>, grid, block, Cfg::SMEM_BYTES, stream, TWO ? 2 : 1, p->tmA,
+                              p->tmB, p->tmLA, p->tmLB, p->tmOut, p->tmOut2, p->tmAux, a));
   return 0;
 }
 

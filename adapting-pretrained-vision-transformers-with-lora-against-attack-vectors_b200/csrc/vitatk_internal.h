@@ -24,6 +24,46 @@ const char* last_error();
   } while (0)
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch: the hot-path kernels are launched with programmatic stream serialization, call
+// pdl_wait() before their first global-memory access (the previous kernel in the stream has then completed and its
+// writes are visible) and pdl_launch_dependents() right after, so the NEXT kernel's launch latency and prologue
+// (barrier init, TMEM allocation, descriptor prefetch) overlap this kernel's execution / tail.  Measured on B200 it
+// changes nothing for this workload (the ~2700 launches per PGD-10 step are already queued ahead of the GPU), so the
+// launch attribute is opt-in: VITATK_PDL=1.  Without the attribute griddepcontrol.* are no-ops.
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              int cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// ---------------------------------------------------------------------------------------------
 // tcgen05 GEMM:  out[M,N] = epi( A[M,K] * B[N,K]^T  +  T[M,64*nkb] * LB[N,64*nkb]^T )
 // All operands bf16 row-major with the reduction dimension contiguous (K-major), fp32 accumulate
 // in TMEM.  The second product is the rank-r LoRA term: T = x*A_lora^T (precomputed, bf16) and

@@ -29,6 +29,23 @@ static constexpr int A_STAGE_BYTES = Q_BYTES + 2 * KV_BYTES;
 static constexpr int A_OUT_OFF = 2 * A_STAGE_BYTES;          // 8 warps x 4 KB output staging
 static constexpr int A_SMEM = 1024 + 2 * A_STAGE_BYTES + 8 * 4096 + 256;
 
+// optional in-kernel timeline of the forward kernel (timing experiments only, VITATK_ATTN_DBG & 32): CTA 0 records
+// (event, unit, clock) triples into a device buffer set with attention_fwd_set_trace()
+__device__ long long* g_fwd_trace = nullptr;
+__device__ __forceinline__ void ftrace(int slot0, int& idx, int ev, int u) {
+  if (g_fwd_trace != nullptr && blockIdx.x == 0 && idx < 680) {
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t));
+    g_fwd_trace[(slot0 + idx) * 2] = (static_cast<long long>(ev) << 32) | static_cast<unsigned>(u);
+    g_fwd_trace[(slot0 + idx) * 2 + 1] = t;
+    ++idx;
+  }
+}
+#define FTR(slot0, ev, u) do { if (trace_on) ftrace(slot0, tr_idx, ev, u); } while (0)
+
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  return fmaxf(a, fmaxf(b, c));  // (the 3-input max.f32 / FMNMX3 form measured slower on B200)
+}
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -71,7 +88,8 @@ __device__ __forceinline__ void stage_store_64(uint8_t* stage, const uint32_t (&
 __global__ void __launch_bounds__(A_THREADS, 1)
 attn_fwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                      const __grid_constant__ CUtensorMap tmO, float* __restrict__ lse2, int tokens, int heads,
-                     int num_items, float sl2) {
+                     int num_items, float sl2, int trace_on) {
+  int tr_idx = 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A_OUT_OFF + 8 * 4096);
@@ -136,34 +154,45 @@ attn_fwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const uint32_t leader = ptx::elect_leader();
       constexpr uint32_t idesc_s = ptx::make_idesc_bf16(128, A_TPAD);
       constexpr uint32_t idesc_pv = ptx::make_idesc_bf16(128, A_HD) | ptx::IDESC_B_MN_MAJOR;
-      int n = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++n) {
-        const int st = n & 1;
-        const uint32_t par = n & 1;
+      // Work units are (head, query tile) pairs; S of unit u is issued BEFORE P*V of unit u - 1, so the two TMEM slots
+      // run half a period out of phase: while one tile's softmax owns the MUFU pipe, the other tile's S / P*V MMAs and
+      // read-out proceed (the previous in-order S,S,PV,PV schedule kept both tiles in lockstep: ~8.5K clk per head).
+      const int my_items =
+          (num_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+      const int units = my_items * ntiles;
+      auto issue_pv = [&](int v) {
+        const int n = v / ntiles, t = v - n * ntiles, st = n & 1;
+        const uint32_t qs = ptx::smem_u32(smem + st * A_STAGE_BYTES);
+        const uint64_t vdesc = ptx::make_smem_desc_mn_sw128(qs + Q_BYTES + KV_BYTES, 1024);
+        ptx::mbar_wait(&p_full[t], n & 1);
+        ptx::tc_fence_after();
+        FTR(0, 4, v);
+        const uint32_t tt = tmem + t * A_TILE_COLS;
+#pragma unroll
+        for (int ks = 0; ks < A_TPAD / 16; ++ks)  // 16 keys per step: 8 TMEM columns of P, 16 rows (2 KB) of V
+          ptx::umma_bf16_ts_p(leader, tt + A_O_COL, tt + ks * 8, vdesc + ks * (2048 >> 4), idesc_pv, ks > 0 ? 1u : 0u);
+        ptx::umma_commit_p(leader, &o_full[t]);
+        FTR(0, 5, v);
+        if (t == ntiles - 1) ptx::umma_commit_p(leader, &load_empty[st]);  // every MMA reading this stage has retired
+      };
+      for (int u = 0; u < units; ++u) {
+        const int n = u / ntiles, t = u - n * ntiles, st = n & 1;
         const uint32_t qs = ptx::smem_u32(smem + st * A_STAGE_BYTES);
         const uint64_t kdesc = ptx::make_smem_desc_sw128(qs + Q_BYTES);
-        const uint64_t vdesc = ptx::make_smem_desc_mn_sw128(qs + Q_BYTES + KV_BYTES, 1024);
-        ptx::mbar_wait(&load_full[st], (n >> 1) & 1);
-        for (int t = 0; t < ntiles; ++t) {
-          ptx::mbar_wait(&tmem_free[t], par ^ 1);  // previous head's O of this tile has been read out
-          ptx::tc_fence_after();
-          const uint64_t qdesc = ptx::make_smem_desc_sw128(qs + t * 128 * 128);
+        FTR(0, 1, u);
+        if (t == 0) ptx::mbar_wait(&load_full[st], (n >> 1) & 1);
+        ptx::mbar_wait(&tmem_free[t], (n & 1) ^ 1);  // previous head's O of this tile has been read out
+        ptx::tc_fence_after();
+        FTR(0, 2, u);
+        const uint64_t qdesc = ptx::make_smem_desc_sw128(qs + t * 128 * 128);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            ptx::umma_bf16_p(leader, tmem + t * A_TILE_COLS, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k > 0 ? 1u : 0u);
-          ptx::umma_commit_p(leader, &s_full[t]);
-        }
-        for (int t = 0; t < ntiles; ++t) {
-          ptx::mbar_wait(&p_full[t], par);
-          ptx::tc_fence_after();
-          const uint32_t tt = tmem + t * A_TILE_COLS;
-#pragma unroll 1
-          for (int ks = 0; ks < A_TPAD / 16; ++ks)  // 16 keys per step: 8 TMEM columns of P, 16 rows (2 KB) of V
-            ptx::umma_bf16_ts_p(leader, tt + A_O_COL, tt + ks * 8, vdesc + ks * (2048 >> 4), idesc_pv, ks > 0 ? 1u : 0u);
-          ptx::umma_commit_p(leader, &o_full[t]);
-        }
-        ptx::umma_commit_p(leader, &load_empty[st]);  // every MMA reading this stage has retired
+        for (int k = 0; k < 4; ++k)
+          ptx::umma_bf16_p(leader, tmem + t * A_TILE_COLS, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+        ptx::umma_commit_p(leader, &s_full[t]);
+        FTR(0, 3, u);
+        if (u > 0) issue_pv(u - 1);
       }
+      if (units > 0) issue_pv(units - 1);
     }
   } else {
     const int t = warp >> 2;        // query tile of this warp group
@@ -176,36 +205,70 @@ attn_fwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++n) {
         const uint32_t par = n & 1;
         const int b = item / heads, h = item % heads;
+        const int tslot = (w4 == 0 && lane == 0) ? 680 * (1 + t) : -1;
         ptx::mbar_wait(&s_full[t], par);
         ptx::tc_fence_after();
+        if (tslot >= 0) FTR(tslot, 11, 2 * n + t);
         float inv_sum = 0.f, lse = 0.f;
         if (warp_active) {
+          // pass 1 (row max): the 208 score columns are read in two batches (4 + 3 chunks of 32) so only two TMEM
+          // round trips are exposed instead of seven
           float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-          for (int c = 0; c < 7; ++c) {
-            uint32_t r[32];
-            ptx::tmem_ld_32x32b_x32(lane_addr + c * 32, r);
+          {
+            uint32_t r0[32], r1[32], r2[32], r3[32];
+            ptx::tmem_ld_32x32b_x32(lane_addr, r0);
+            ptx::tmem_ld_32x32b_x32(lane_addr + 32, r1);
+            ptx::tmem_ld_32x32b_x32(lane_addr + 64, r2);
+            ptx::tmem_ld_32x32b_x32(lane_addr + 96, r3);
             ptx::tmem_ld_wait();
-            const int limit = tokens - c * 32;
-            if (limit >= 32) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              mx0 = max3(mx0, __uint_as_float(r0[j]), __uint_as_float(r1[j]));
+              mx1 = max3(mx1, __uint_as_float(r0[j + 1]), __uint_as_float(r1[j + 1]));
+            }
+            if (tokens >= 128) {
 #pragma unroll
               for (int j = 0; j < 32; j += 2) {
-                mx0 = fmaxf(mx0, __uint_as_float(r[j]));
-                mx1 = fmaxf(mx1, __uint_as_float(r[j + 1]));
+                mx0 = max3(mx0, __uint_as_float(r2[j]), __uint_as_float(r3[j]));
+                mx1 = max3(mx1, __uint_as_float(r2[j + 1]), __uint_as_float(r3[j + 1]));
               }
             } else {
+              // fewer than 128 keys: redo the first four chunks with per-column limits
+              mx0 = mx1 = -INFINITY;
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < limit) mx0 = fmaxf(mx0, __uint_as_float(r[j]));
+              for (int j = 0; j < 32; ++j) {
+                if (j < tokens) mx0 = fmaxf(mx0, __uint_as_float(r0[j]));
+                if (32 + j < tokens) mx0 = fmaxf(mx0, __uint_as_float(r1[j]));
+                if (64 + j < tokens) mx0 = fmaxf(mx0, __uint_as_float(r2[j]));
+                if (96 + j < tokens) mx0 = fmaxf(mx0, __uint_as_float(r3[j]));
+              }
+            }
+          }
+          if (tokens > 128) {
+            uint32_t r0[32], r1[32], r2[32];
+            ptx::tmem_ld_32x32b_x32(lane_addr + 128, r0);
+            ptx::tmem_ld_32x32b_x32(lane_addr + 160, r1);
+            ptx::tmem_ld_32x32b_x32(lane_addr + 192, r2);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (128 + j < tokens) mx0 = fmaxf(mx0, __uint_as_float(r0[j]));
+              if (160 + j < tokens) mx1 = fmaxf(mx1, __uint_as_float(r1[j]));
+              if (192 + j < tokens) mx0 = fmaxf(mx0, __uint_as_float(r2[j]));
             }
           }
           const float m2 = fmaxf(mx0, mx1) * sl2;
+          if (tslot >= 0) FTR(tslot, 12, 2 * n + t);
+          // pass 2 (exp, row sum, bf16 P written over S): chunk c + 1 is in flight while chunk c is processed
           float sum0 = 0.f, sum1 = 0.f;
+          uint32_t ra[32], rb[32];
+          ptx::tmem_ld_32x32b_x32(lane_addr, ra);
 #pragma unroll
           for (int c = 0; c < 7; ++c) {
-            uint32_t r[32];
-            ptx::tmem_ld_32x32b_x32(lane_addr + c * 32, r);
+            uint32_t(&r)[32] = (c & 1) ? rb : ra;
+            uint32_t(&rn)[32] = (c & 1) ? ra : rb;
             ptx::tmem_ld_wait();
+            if (c + 1 < 7) ptx::tmem_ld_32x32b_x32(lane_addr + (c + 1) * 32, rn);
             const int limit = tokens - c * 32;
             uint32_t pk[16];
 #pragma unroll
@@ -231,8 +294,10 @@ attn_fwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&p_full[t]);
+        if (tslot >= 0) FTR(tslot, 13, 2 * n + t);
         ptx::mbar_wait(&o_full[t], par);
         ptx::tc_fence_after();
+        if (tslot >= 0) FTR(tslot, 14, 2 * n + t);
         if (warp_active) {
           uint32_t o0[32], o1[32];
           ptx::tmem_ld_32x32b_x32(lane_addr + A_O_COL, o0);
@@ -243,9 +308,12 @@ attn_fwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             if (lse2) lse2[static_cast<size_t>(item) * A_TPAD + i] = lse;
           }
         }
+        // (releasing the slot before the store was measured SLOWER, 143 vs 102 us: it lets the two tiles' MUFU-bound
+        // softmax phases drift into lockstep again)
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&tmem_free[t]);
+        if (tslot >= 0) FTR(tslot, 15, 2 * n + t);
       }
       if (lane == 0) ptx::tma_store_wait_all<0>();
       __syncwarp();
@@ -278,6 +346,11 @@ int attention_fwd_plan_init(AttnFwdPlan* p, const bf16* qkv, bf16* out, float* l
   return 0;
 }
 
+int attention_fwd_set_trace(long long* dev_buf) {
+  VITATK_CUDA_OK(cudaMemcpyToSymbol(g_fwd_trace, &dev_buf, sizeof(dev_buf)));
+  return 0;
+}
+
 int attention_fwd_tc05(const AttnFwdPlan* p, cudaStream_t stream) {
   static bool attr = false;
   if (!attr) {
@@ -285,12 +358,17 @@ int attention_fwd_tc05(const AttnFwdPlan* p, cudaStream_t stream) {
     attr = true;
   }
   const float sl2 = 1.4426950408889634f / sqrtf(static_cast<float>(A_HD));
+  static int trace_on = -1;
+  if (trace_on < 0) {
+    const char* e = getenv("VITATK_ATTN_DBG");
+    trace_on = (e && (atoi(e) & 32)) ? 1 : 0;
+  }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int items = p->batch * p->heads;
   VITATK_CUDA_OK(launch_pdl(attn_fwd_tc05_kernel, dim3(items < sms ? items : sms), dim3(A_THREADS), A_SMEM, stream, 1,
-                            p->tmQ, p->tmKV, p->tmO, p->lse2, p->tokens, p->heads, items, sl2));
+                            p->tmQ, p->tmKV, p->tmO, p->lse2, p->tokens, p->heads, items, sl2, trace_on));
   return 0;
 }
 

@@ -147,6 +147,7 @@ int attention_bwd_tc05(const AttnBwdPlan* p, cudaStream_t stream);        // two
 // single-pass version (engine default); compute_delta = false when delta was already produced (EPI_ROWDOT GEMM)
 int attention_bwd_fused(const AttnBwdPlan* p, cudaStream_t stream, bool compute_delta);
 int attention_bwd_set_trace(long long* dev_buf);                          // timing experiments only
+int attention_fwd_set_trace(long long* dev_buf);                          // timing experiments only
 // mma.sync forward (round-1 first version, kept for cross-checking the tcgen05 kernel in tests)
 int attention_fwd(const bf16* qkv, bf16* out, int batch, int tokens, int heads, cudaStream_t stream);
 int attention_bwd(const bf16* qkv, const bf16* dout, bf16* dqkv, int batch, int tokens, int heads,

@@ -1,5 +1,4 @@
 mkdir -p gpurun_out
 timeout 180 python -m pytest tests/test_kernels_gpu.py -x -q -k "attention" > gpurun_out/t_attn.log 2>&1; echo "attn rc=$?"
 tail -4 gpurun_out/t_attn.log
-for d in 0 16 17 20 24; do VITATK_ATTN_DBG=$d timeout 120 python scripts/attn_time.py 2>&1 | tail -2; done
-timeout 120 python scripts/attn_trace.py > gpurun_out/attn_trace.txt 2>&1
+timeout 120 python scripts/attn_time.py 2>&1 | tail -2

@@ -153,6 +153,10 @@ int vitatk_k_attention_bwd_tc05(const void* qkv_dev, const void* dout_dev, const
 /* single-pass tcgen05 backward (the engine's path; same arguments as the two-kernel version above) */
 int vitatk_k_attention_bwd_fused(const void* qkv_dev, const void* dout_dev, const void* o_dev, const float* lse2_dev,
                                  float* delta_dev, void* dqkv_dev, int batch, int tokens, int heads, void* stream);
+/* timing experiments: device buffer of 4096 int64 receiving CTA 0's (event, step, clock64) timeline when
+ * VITATK_ATTN_DBG has bit 32 set (scripts/attn_trace.py, scripts/attn_fwd_trace.py); null switches it off */
+int vitatk_k_attention_bwd_trace(long long* trace_dev);
+int vitatk_k_attention_fwd_trace(long long* trace_dev);
 int vitatk_k_attention_bwd(const void* qkv_dev, const void* dout_dev, void* dqkv_dev, int batch, int tokens,
                            int heads, void* stream);
 int vitatk_k_layernorm_fwd(const void* x_dev, const float* gamma_dev, const float* beta_dev, void* y_dev,

@@ -78,7 +78,7 @@ EXPORTS = [
     "vitatk_k_attention_bwd", "vitatk_k_layernorm_fwd", "vitatk_k_layernorm_bwd", "vitatk_k_pgd_update",
     "vitatk_k_pgd_init", "vitatk_profile_begin", "vitatk_profile_end", "vitatk_k_attention_fwd_tc05",
     "vitatk_k_attention_bwd_tc05", "vitatk_k_attention_bwd_fused", "vitatk_k_attention_bwd_trace",
-    "vitatk_k_attention_fwd_trace",
+    "vitatk_k_attention_fwd_trace", "vitatk_k_layernorm_fwd_t", "vitatk_k_layernorm_bwd_t",
 ]
 
 
@@ -132,6 +132,8 @@ def load() -> C.CDLL:
     lib.vitatk_k_attention_bwd.argtypes = [vp, vp, vp, i, i, i, vp]
     lib.vitatk_k_layernorm_fwd.argtypes = [vp, vp, vp, vp, vp, i, i, f, vp]
     lib.vitatk_k_layernorm_bwd.argtypes = [vp, vp, vp, vp, vp, vp, i, i, vp]
+    lib.vitatk_k_layernorm_fwd_t.argtypes = [vp, vp, vp, vp, vp, i, i, f, vp, i, i, vp, i, vp]
+    lib.vitatk_k_layernorm_bwd_t.argtypes = [vp, vp, vp, vp, vp, vp, i, i, vp, i, i, vp, i, vp]
     lib.vitatk_k_pgd_update.argtypes = [vp, vp, vp, vp, i, C.POINTER(f), C.POINTER(f), f, f, vp]
     lib.vitatk_k_pgd_init.argtypes = [vp, vp, vp, vp, i, C.POINTER(f), C.POINTER(f), f, i, u64, u64, vp]
     for name in EXPORTS:

@@ -102,6 +102,7 @@ struct vitatk_engine {
   PixelNorm nrm;
   // optional per-launch CUDA-event timing (bench.py's roofline leg; off in the timed region)
   bool attn_bwd_two_kernel = false;  // VITATK_ATTN_BWD=2k selects the older dQ + dK/dV kernel pair
+  bool fuse_ln_t = false;            // LayerNorm kernels also produce the LoRA x*A^T of the site they feed
   bool fuse_delta = false;           // delta comes out of the proj-backward GEMM epilogue (pair kernel) instead of a kernel
   bool prof = false;
   struct ProfRec { int cat; double flops; cudaEvent_t a, b; };
@@ -288,14 +289,28 @@ static int encoder_forward(vitatk_engine* e, PlanSet* ps, int batch, cudaStream_
   for (int l = 0; l < c.layers; ++l) {
     const LayerWeights& w = e->lw[l];
     LayerPlans& p = ps->layers[l];
-    RUNC(CAT_LN_FWD, 0, layernorm_fwd(e->h[l], w.ln1_g, w.ln1_b, e->xn, e->st1[l], M, D, c.ln_eps, s));
-    if (w.lora[VITATK_SITE_QKV].rank > 0) RUN_GEMM(CAT_T_QKV, &p.t_qkv);
+    const int rq = w.lora[VITATK_SITE_QKV].rank, r1 = w.lora[VITATK_SITE_FC1].rank;
+    // Legacy mma.sync is slow on sm_100 (measured: +14 us per launch with one 8-column tile of T, +72 us with three),
+    // so the fusion only pays for single-tile sites (it replaces a 23 us skinny GEMM); the 3-adapter q|k|v site keeps
+    // its own GEMM.
+    const bool ln1_t = e->fuse_ln_t && rq > 0 && 3 * ((rq + 7) / 8) <= 1;
+    const bool ln2_t = e->fuse_ln_t && r1 > 0 && r1 <= 8;
+    if (ln1_t)
+      RUNC(CAT_LN_FWD, 0, layernorm_fwd_t(e->h[l], w.ln1_g, w.ln1_b, e->xn, e->st1[l], M, D, c.ln_eps,
+                                          w.lora[VITATK_SITE_QKV].la_fwd, 3, rq, e->T, 3 * LORA_PAD, s));
+    else
+      RUNC(CAT_LN_FWD, 0, layernorm_fwd(e->h[l], w.ln1_g, w.ln1_b, e->xn, e->st1[l], M, D, c.ln_eps, s));
+    if (rq > 0 && !ln1_t) RUN_GEMM(CAT_T_QKV, &p.t_qkv);
     RUN_GEMM(CAT_QKV, &p.qkv);
     RUNC(CAT_ATTN_FWD, 4.0 * batch * c.heads * TOKENS * TOKENS * 64, attention_fwd_tc05(&ps->attn_fwd[l], s));
     if (w.lora[VITATK_SITE_PROJ].rank > 0) RUN_GEMM(CAT_T_PROJ, &p.t_proj);
     RUN_GEMM(CAT_PROJ, &p.proj);
-    RUNC(CAT_LN_FWD, 0, layernorm_fwd(e->h_mid[l], w.ln2_g, w.ln2_b, e->xn, e->st2[l], M, D, c.ln_eps, s));
-    if (w.lora[VITATK_SITE_FC1].rank > 0) RUN_GEMM(CAT_T_FC1, &p.t_fc1);
+    if (ln2_t)
+      RUNC(CAT_LN_FWD, 0, layernorm_fwd_t(e->h_mid[l], w.ln2_g, w.ln2_b, e->xn, e->st2[l], M, D, c.ln_eps,
+                                          w.lora[VITATK_SITE_FC1].la_fwd, 1, r1, e->T, 3 * LORA_PAD, s));
+    else
+      RUNC(CAT_LN_FWD, 0, layernorm_fwd(e->h_mid[l], w.ln2_g, w.ln2_b, e->xn, e->st2[l], M, D, c.ln_eps, s));
+    if (r1 > 0 && !ln2_t) RUN_GEMM(CAT_T_FC1, &p.t_fc1);
     RUN_GEMM(CAT_FC1, &p.fc1);
     if (w.lora[VITATK_SITE_FC2].rank > 0) RUN_GEMM(CAT_T_FC2, &p.t_fc2);
     RUN_GEMM(CAT_FC2, &p.fc2);
@@ -307,22 +322,38 @@ static int encoder_forward(vitatk_engine* e, PlanSet* ps, int batch, cudaStream_
 static int encoder_backward(vitatk_engine* e, PlanSet* ps, int batch, cudaStream_t s) {
   const vitatk_config& c = e->cfg;
   const int M = batch * TOKENS, D = c.dim;
+  bool t_fc2_ready = false;
   for (int l = c.layers - 1; l >= 0; --l) {
     const LayerWeights& w = e->lw[l];
     LayerPlans& p = ps->layers[l];
-    if (w.lora[VITATK_SITE_FC2].rank > 0) RUN_GEMM(CAT_BT_FC2, &p.bt_fc2);
+    // dh_a * B_fc2 was already produced by the LayerNorm backward of the layer above (not for the top layer: dh_a
+    // comes from the head there)
+    if (w.lora[VITATK_SITE_FC2].rank > 0 && !t_fc2_ready) RUN_GEMM(CAT_BT_FC2, &p.bt_fc2);
     RUN_GEMM(CAT_BFC2, &p.bfc2);  // du = (dh W2 + lora) * gelu'(u)   (u[l] holds gelu'(u), written by fc1's epilogue)
     if (w.lora[VITATK_SITE_FC1].rank > 0) RUN_GEMM(CAT_BT_FC1, &p.bt_fc1);
     RUN_GEMM(CAT_BFC1, &p.bfc1);  // dxn = du W1 + lora
-    RUNC(CAT_LN_BWD, 0, layernorm_bwd(e->dxn, e->h_mid[l], e->st2[l], w.ln2_g, e->dh_a, e->dh_b, M, D, s));  // dh_mid
-    if (w.lora[VITATK_SITE_PROJ].rank > 0) RUN_GEMM(CAT_BT_PROJ, &p.bt_proj);
+    const int rp = w.lora[VITATK_SITE_PROJ].rank;
+    const bool ln2b_t = e->fuse_ln_t && rp > 0 && rp <= 8;
+    if (ln2b_t)  // dh_mid, and its LoRA projection dh_mid * B_proj for the proj backward GEMM
+      RUNC(CAT_LN_BWD, 0, layernorm_bwd_t(e->dxn, e->h_mid[l], e->st2[l], w.ln2_g, e->dh_a, e->dh_b, M, D,
+                                          w.lora[VITATK_SITE_PROJ].lb_bwd, 1, rp, e->T, 3 * LORA_PAD, s));
+    else
+      RUNC(CAT_LN_BWD, 0, layernorm_bwd(e->dxn, e->h_mid[l], e->st2[l], w.ln2_g, e->dh_a, e->dh_b, M, D, s));  // dh_mid
+    if (rp > 0 && !ln2b_t) RUN_GEMM(CAT_BT_PROJ, &p.bt_proj);
     RUN_GEMM(CAT_BPROJ, &p.bproj);  // dao = dh_mid Wp + lora
     RUNC(CAT_ATTN_BWD, 8.0 * batch * c.heads * TOKENS * TOKENS * 64,
          e->attn_bwd_two_kernel ? attention_bwd_tc05(&ps->attn_bwd[l], s)
                                 : attention_bwd_fused(&ps->attn_bwd[l], s, !e->fuse_delta));
     if (w.lora[VITATK_SITE_QKV].rank > 0) RUN_GEMM(CAT_BT_QKV, &p.bt_qkv);
     RUN_GEMM(CAT_BQKV, &p.bqkv);  // dxn = dqkv Wqkv + lora
-    RUNC(CAT_LN_BWD, 0, layernorm_bwd(e->dxn, e->h[l], e->st1[l], w.ln1_g, e->dh_b, e->dh_a, M, D, s));  // dh wrt h[l]
+    // dh wrt h[l]; with fusion also dh * B_fc2 of the layer below (consumed first thing in its backward)
+    const int r2n = l > 0 ? e->lw[l - 1].lora[VITATK_SITE_FC2].rank : 0;
+    t_fc2_ready = e->fuse_ln_t && r2n > 0 && r2n <= 8;
+    if (t_fc2_ready)
+      RUNC(CAT_LN_BWD, 0, layernorm_bwd_t(e->dxn, e->h[l], e->st1[l], w.ln1_g, e->dh_b, e->dh_a, M, D,
+                                          e->lw[l - 1].lora[VITATK_SITE_FC2].lb_bwd, 1, r2n, e->T, 3 * LORA_PAD, s));
+    else
+      RUNC(CAT_LN_BWD, 0, layernorm_bwd(e->dxn, e->h[l], e->st1[l], w.ln1_g, e->dh_b, e->dh_a, M, D, s));
   }
   RUN_GEMM(CAT_BPATCH, &ps->bpatch);  // dxn <- dL/d(cols)
   return 0;
@@ -377,6 +408,10 @@ int vitatk_create(const vitatk_config* cfg, vitatk_engine** out) {
     e->attn_bwd_two_kernel = v && strcmp(v, "2k") == 0;
     const char* g2 = getenv("VITATK_GEMM_2CTA");
     const char* fd = getenv("VITATK_FUSE_DELTA");
+    const char* flt = getenv("VITATK_FUSE_LN_T");
+    // opt-in: measured perf-neutral on B200 (skinny GEMMs -8 ms, LayerNorm kernels +8 ms per PGD-10 step: the legacy
+    // mma.sync the LN kernels use for the projection is slow on sm_100)
+    e->fuse_ln_t = flt && flt[0] == '1' && cfg->dim == 768;
     e->fuse_delta = !e->attn_bwd_two_kernel && !(g2 && g2[0] == '0') && !(fd && fd[0] == '0') && cfg->dim % 256 == 0;
   }
   e->lw.resize(cfg->layers);
@@ -743,6 +778,20 @@ int vitatk_k_layernorm_bwd(const void* dy, const void* x, const float* stats, co
   return layernorm_bwd(static_cast<const bf16*>(dy), static_cast<const bf16*>(x),
                        reinterpret_cast<const float2*>(stats), gamma, static_cast<const bf16*>(dres),
                        static_cast<bf16*>(dx), rows, cols, static_cast<cudaStream_t>(stream));
+}
+int vitatk_k_layernorm_fwd_t(const void* x, const float* gamma, const float* beta, void* y, float* stats, int rows,
+                             int cols, float eps, const void* lora, int groups, int rank, void* T, int ldt, void* stream) {
+  return layernorm_fwd_t(static_cast<const bf16*>(x), gamma, beta, static_cast<bf16*>(y), reinterpret_cast<float2*>(stats),
+                         rows, cols, eps, static_cast<const bf16*>(lora), groups, rank, static_cast<bf16*>(T), ldt,
+                         static_cast<cudaStream_t>(stream));
+}
+int vitatk_k_layernorm_bwd_t(const void* dy, const void* x, const float* stats, const float* gamma, const void* dres,
+                             void* dx, int rows, int cols, const void* lora, int groups, int rank, void* T, int ldt,
+                             void* stream) {
+  return layernorm_bwd_t(static_cast<const bf16*>(dy), static_cast<const bf16*>(x), reinterpret_cast<const float2*>(stats),
+                         gamma, static_cast<const bf16*>(dres), static_cast<bf16*>(dx), rows, cols,
+                         static_cast<const bf16*>(lora), groups, rank, static_cast<bf16*>(T), ldt,
+                         static_cast<cudaStream_t>(stream));
 }
 static PixelNorm make_norm(const float* mean3, const float* std3) {
   PixelNorm n;

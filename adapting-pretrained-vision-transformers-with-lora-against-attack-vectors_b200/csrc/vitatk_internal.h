@@ -161,6 +161,12 @@ int layernorm_fwd(const bf16* x, const float* gamma, const float* beta, bf16* y,
 // dx_out = dres + LN_backward(dy) ; x is the saved LN input, stats = (mean, rstd)
 int layernorm_bwd(const bf16* dy, const bf16* x, const float2* stats, const float* gamma, const bf16* dres,
                   bf16* dx_out, int rows, int cols, cudaStream_t stream);
+// Variants that also write the LoRA down-projection of their output: T[row, 64 g + j] = out[row, :] . lora[64 g + j, :]
+// for g < groups, j < ceil8(rank) (lora: bf16 [64 * groups, cols], rows >= rank zero; groups * ceil(rank/8) <= 6; cols 768)
+int layernorm_fwd_t(const bf16* x, const float* gamma, const float* beta, bf16* y, float2* stats, int rows, int cols,
+                    float eps, const bf16* lora, int groups, int rank, bf16* T, int ldt, cudaStream_t stream);
+int layernorm_bwd_t(const bf16* dy, const bf16* x, const float2* stats, const float* gamma, const bf16* dres, bf16* dx_out,
+                    int rows, int cols, const bf16* lora, int groups, int rank, bf16* T, int ldt, cudaStream_t stream);
 // final LN on CLS rows + classifier + softmax-CE; writes logits, per-image loss, and (optionally) the
 // gradient wrt the final hidden state (non-CLS rows zero-filled).
 int head_fwd_bwd(const bf16* h, const float* gamma, const float* beta, const float* Wc, const float* bc,

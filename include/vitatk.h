@@ -163,6 +163,14 @@ int vitatk_k_layernorm_fwd(const void* x_dev, const float* gamma_dev, const floa
                            float* stats_dev, int rows, int cols, float eps, void* stream);
 int vitatk_k_layernorm_bwd(const void* dy_dev, const void* x_dev, const float* stats_dev, const float* gamma_dev,
                            const void* dres_dev, void* dx_dev, int rows, int cols, void* stream);
+/* LayerNorm variants that also write T[row, 64 g + j] = out[row, :] . lora[64 g + j, :] (the LoRA x*A^T of the site the
+ * output feeds; lora bf16 [64 * groups, cols], rows >= rank zero; cols must be 768, groups * ceil(rank / 8) <= 6) */
+int vitatk_k_layernorm_fwd_t(const void* x_dev, const float* gamma_dev, const float* beta_dev, void* y_dev,
+                             float* stats_dev, int rows, int cols, float eps, const void* lora_dev, int groups, int rank,
+                             void* T_dev, int ldt, void* stream);
+int vitatk_k_layernorm_bwd_t(const void* dy_dev, const void* x_dev, const float* stats_dev, const float* gamma_dev,
+                             const void* dres_dev, void* dx_dev, int rows, int cols, const void* lora_dev, int groups,
+                             int rank, void* T_dev, int ldt, void* stream);
 int vitatk_k_pgd_update(const void* dcols_dev, const float* x0_dev, float* adv_dev, void* cols_dev, int batch,
                         const float* mean3, const float* std3, float eps, float alpha, void* stream);
 int vitatk_k_pgd_init(const float* x0_dev, const float* noise_dev, float* adv_dev, void* cols_dev, int batch,

@@ -249,6 +249,49 @@ def test_layernorm_fwd_bwd_vs_torch(lib, rows):
     torch.testing.assert_close(stats[:, 0], x.float().mean(-1), rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize("rows,groups,rank", [(197, 1, 8), (1576, 3, 8), (1000, 1, 16), (50432, 3, 8)])
+def test_layernorm_with_lora_projection(lib, rows, groups, rank):
+    """LN forward / backward variants that also emit T = out * A^T for the LoRA site the output feeds."""
+    from vitatk import _lib
+
+    cols = 768
+    g = torch.Generator(device="cuda").manual_seed(rows + rank)
+    x = (torch.randn(rows, cols, device="cuda", generator=g) * 2 + 0.5).to(torch.bfloat16)
+    gamma = 1 + 0.1 * torch.randn(cols, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(cols, device="cuda", generator=g)
+    dy = torch.randn(rows, cols, device="cuda", generator=g).to(torch.bfloat16)
+    dres = torch.randn(rows, cols, device="cuda", generator=g).to(torch.bfloat16)
+    lora = torch.zeros(64 * groups, cols, device="cuda")
+    for gi in range(groups):
+        lora[64 * gi: 64 * gi + rank] = torch.randn(rank, cols, device="cuda", generator=g) / math.sqrt(cols)
+    lora = lora.to(torch.bfloat16)
+    y, y0 = torch.empty_like(x), torch.empty_like(x)
+    stats, stats0 = torch.empty(rows, 2, device="cuda"), torch.empty(rows, 2, device="cuda")
+    dx, dx0 = torch.empty_like(x), torch.empty_like(x)
+    T = torch.full((rows, 192), 7.0, device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.vitatk_k_layernorm_fwd(_p(x), _p(gamma), _p(beta), _p(y0), _p(stats0), rows, cols, 1e-12, _s()), "ln")
+    _lib.check(lib.vitatk_k_layernorm_fwd_t(_p(x), _p(gamma), _p(beta), _p(y), _p(stats), rows, cols, 1e-12, _p(lora),
+                                            groups, rank, _p(T), 192, _s()), "ln_fwd_t")
+    torch.cuda.synchronize()
+    assert torch.equal(y, y0) and torch.equal(stats, stats0)  # same arithmetic as the plain kernel
+    r8 = (rank + 7) // 8 * 8
+    for gi in range(groups):
+        want = y.float() @ lora[64 * gi: 64 * gi + r8].float().t()
+        got = T[:, 64 * gi: 64 * gi + r8].float()
+        assert (got - want).abs().max() <= 1e-2 * want.abs().max() + 1e-3, (gi, (got - want).abs().max())
+        assert torch.equal(T[:, 64 * gi + r8: 64 * (gi + 1)], torch.full_like(T[:, 64 * gi + r8: 64 * (gi + 1)], 7.0))
+    T.fill_(7.0)
+    _lib.check(lib.vitatk_k_layernorm_bwd(_p(dy), _p(x), _p(stats), _p(gamma), _p(dres), _p(dx0), rows, cols, _s()), "lnb")
+    _lib.check(lib.vitatk_k_layernorm_bwd_t(_p(dy), _p(x), _p(stats), _p(gamma), _p(dres), _p(dx), rows, cols, _p(lora),
+                                            groups, rank, _p(T), 192, _s()), "ln_bwd_t")
+    torch.cuda.synchronize()
+    assert torch.equal(dx, dx0)
+    for gi in range(groups):
+        want = dx.float() @ lora[64 * gi: 64 * gi + r8].float().t()
+        got = T[:, 64 * gi: 64 * gi + r8].float()
+        assert (got - want).abs().max() <= 1e-2 * want.abs().max() + 1e-3, (gi, (got - want).abs().max())
+
+
 def _cols_from_image(img, mean, std):
     """torch restatement of the im2col layout: [B,3,224,224] -> [B*197, 768] with zero CLS rows."""
     B = img.shape[0]

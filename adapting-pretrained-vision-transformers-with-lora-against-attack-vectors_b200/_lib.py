@@ -122,7 +122,7 @@ def load() -> C.CDLL:
     lib.vitatk_count_correct.argtypes = [vp, vp, vp, i, vp, vp]
     lib.vitatk_profile_begin.argtypes = [vp]
     lib.vitatk_profile_end.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(ll)]
-    lib.vitatk_k_gemm.argtypes = [i, i, i, vp, i, vp, i, vp, i, vp, i, vp, i, vp, i, i, i, i, i, vp, vp, i, vp, i, vp, i, i, i, vp]
+    lib.vitatk_k_gemm.argtypes = [i, i, i, vp, i, vp, i, vp, i, vp, i, vp, i, vp, i, i, i, i, i, vp, vp, i, vp, i, vp, i, i, vp, vp, i, vp]
     lib.vitatk_k_attention_fwd.argtypes = [vp, vp, i, i, i, vp]
     lib.vitatk_k_attention_fwd_tc05.argtypes = [vp, vp, vp, i, i, i, vp]
     lib.vitatk_k_attention_bwd_tc05.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, vp]
@@ -132,6 +132,7 @@ def load() -> C.CDLL:
     lib.vitatk_k_attention_bwd.argtypes = [vp, vp, vp, i, i, i, vp]
     lib.vitatk_k_layernorm_fwd.argtypes = [vp, vp, vp, vp, vp, i, i, f, vp]
     lib.vitatk_k_layernorm_bwd.argtypes = [vp, vp, vp, vp, vp, vp, i, i, vp]
+    lib.vitatk_k_layernorm_stats.argtypes = [vp, vp, i, i, f, vp]
     lib.vitatk_k_layernorm_fwd_t.argtypes = [vp, vp, vp, vp, vp, i, i, f, vp, i, i, vp, i, vp]
     lib.vitatk_k_layernorm_bwd_t.argtypes = [vp, vp, vp, vp, vp, vp, i, i, vp, i, i, vp, i, vp]
     lib.vitatk_k_pgd_update.argtypes = [vp, vp, vp, vp, i, C.POINTER(f), C.POINTER(f), f, f, vp]

@@ -82,6 +82,37 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x,
 }
 
 template <int CH>
+__global__ void __launch_bounds__(256) ln_stats_kernel(const bf16* __restrict__ x, float2* __restrict__ stats, int rows,
+                                                       float eps) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  constexpr int COLS = CH * 256;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * COLS);
+  float v[CH][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    unpack8(__ldg(xr + lane + 32 * i), v[i]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[i][j];
+  }
+  const float mean = warp_sum(s) * (1.f / COLS);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < CH; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float d = v[i][j] - mean;
+      q += d * d;
+    }
+  const float rstd = rsqrtf(warp_sum(q) * (1.f / COLS) + eps);
+  if (lane == 0) stats[row] = make_float2(mean, rstd);
+}
+
+template <int CH>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                                                      const float2* __restrict__ stats, const float* __restrict__ gamma,
                                                      const bf16* __restrict__ dres, bf16* __restrict__ dx, int rows) {
@@ -377,6 +408,18 @@ int layernorm_fwd(const bf16* x, const float* gamma, const float* beta, bf16* y,
     default: set_error("layernorm_fwd: cols=%d unsupported", cols); return 1;
   }
   VITATK_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int layernorm_stats(const bf16* x, float2* stats, int rows, int cols, float eps, cudaStream_t stream) {
+  const int grid = (rows + 7) / 8;
+  switch (cols) {
+    case 768: VITATK_CUDA_OK(launch_pdl(ln_stats_kernel<3>, dim3(grid), dim3(256), 0, stream, 1, x, stats, rows, eps)); break;
+    case 1024: VITATK_CUDA_OK(launch_pdl(ln_stats_kernel<4>, dim3(grid), dim3(256), 0, stream, 1, x, stats, rows, eps)); break;
+    case 512: VITATK_CUDA_OK(launch_pdl(ln_stats_kernel<2>, dim3(grid), dim3(256), 0, stream, 1, x, stats, rows, eps)); break;
+    case 256: VITATK_CUDA_OK(launch_pdl(ln_stats_kernel<1>, dim3(grid), dim3(256), 0, stream, 1, x, stats, rows, eps)); break;
+    default: set_error("layernorm_stats: cols=%d unsupported", cols); return 1;
+  }
   return 0;
 }
 

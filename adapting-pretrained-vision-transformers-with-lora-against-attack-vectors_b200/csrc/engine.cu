@@ -53,6 +53,9 @@ struct LayerWeights {
   const bf16 *qkv_w = nullptr, *qkv_wt = nullptr, *proj_w = nullptr, *proj_wt = nullptr;
   const bf16 *fc1_w = nullptr, *fc1_wt = nullptr, *fc2_w = nullptr, *fc2_wt = nullptr;
   const float *qkv_b = nullptr, *proj_b = nullptr, *fc1_b = nullptr, *fc2_b = nullptr;
+  // LayerNorm folded into the qkv / fc1 GEMMs (both set => this layer runs folded): qkv_w / fc1_w then hold gamma o W,
+  // qkv_b / fc1_b hold c2 = W beta + LoRA(beta) + b, the QKV / FC1 adapter la_fwd holds gamma o A, and these hold c1
+  const float *qkv_c1 = nullptr, *fc1_c1 = nullptr;
   LoraSite lora[4];
 };
 
@@ -127,7 +130,8 @@ static int build_plans(vitatk_engine* e, int batch, PlanSet** out) {
   ps->layers.resize(c.layers);
   ps->attn_fwd.resize(c.layers);
   ps->attn_bwd.resize(c.layers);
-  GemmEpilogue plain = {EPI_PLAIN, nullptr, nullptr, 0, nullptr, 0, nullptr, 0, 0};
+  GemmEpilogue plain = {};
+  plain.mode = EPI_PLAIN;
   // patch embedding: h[0] = cols * Wpe^T + table[m % 197]
   {
     GemmEpilogue ep = {EPI_ROWTABLE, nullptr, nullptr, 0, e->embed_table, TOKENS};
@@ -142,18 +146,26 @@ static int build_plans(vitatk_engine* e, int batch, PlanSet** out) {
     const LoraSite& sp = w.lora[VITATK_SITE_PROJ];
     const LoraSite& s1 = w.lora[VITATK_SITE_FC1];
     const LoraSite& s2 = w.lora[VITATK_SITE_FC2];
+    const bool fold = w.qkv_c1 != nullptr && w.fc1_c1 != nullptr;  // LayerNorm folded into the qkv / fc1 GEMMs
+    const bf16* a_ln1 = fold ? e->h[l] : e->xn;
+    const bf16* a_ln2 = fold ? e->h_mid[l] : e->xn;
     // ---------------- forward ----------------
     if (attention_fwd_plan_init(&ps->attn_fwd[l], e->qkv[l], e->ao[l], e->lse2[l], batch, TOKENS, c.heads)) return 1;
     if (attention_bwd_plan_init(&ps->attn_bwd[l], e->qkv[l], e->dao, e->ao[l], e->lse2[l], e->delta, e->dqkv, batch,
                                 TOKENS, c.heads))
       return 1;
     if (sq.rank > 0 &&
-        gemm_plan_init(&p.t_qkv, M, 3 * LORA_PAD, D, e->xn, D, sq.la_fwd, D, e->T, 3 * LORA_PAD, nullptr, 0, nullptr, 0,
+        gemm_plan_init(&p.t_qkv, M, 3 * LORA_PAD, D, a_ln1, D, sq.la_fwd, D, e->T, 3 * LORA_PAD, nullptr, 0, nullptr, 0,
                        nullptr, 0, 0, 0, 0, plain))
       return 1;
     {
-      GemmEpilogue ep = {EPI_PLAIN, w.qkv_b, nullptr, 0, nullptr, 0};
-      if (gemm_plan_init(&p.qkv, M, 3 * D, D, e->xn, D, w.qkv_w, D, e->qkv[l], 3 * D, nullptr, 0, e->T, 3 * LORA_PAD,
+      GemmEpilogue ep = plain;
+      ep.bias = w.qkv_b;
+      if (fold) {
+        ep.row_stats = e->st1[l];
+        ep.c1 = w.qkv_c1;
+      }
+      if (gemm_plan_init(&p.qkv, M, 3 * D, D, a_ln1, D, w.qkv_w, D, e->qkv[l], 3 * D, nullptr, 0, e->T, 3 * LORA_PAD,
                          sq.lb_fwd, LORA_PAD, sq.rank > 0 ? 1 : 0, lora_ksteps(sq.rank), sq.rank > 0 ? D : 0, ep))
         return 1;
     }
@@ -168,12 +180,18 @@ static int build_plans(vitatk_engine* e, int batch, PlanSet** out) {
         return 1;
     }
     if (s1.rank > 0 &&
-        gemm_plan_init(&p.t_fc1, M, LORA_PAD, D, e->xn, D, s1.la_fwd, D, e->T, 3 * LORA_PAD, nullptr, 0, nullptr, 0,
+        gemm_plan_init(&p.t_fc1, M, LORA_PAD, D, a_ln2, D, s1.la_fwd, D, e->T, 3 * LORA_PAD, nullptr, 0, nullptr, 0,
                        nullptr, 0, 0, 0, 0, plain))
       return 1;
     {
-      GemmEpilogue ep = {EPI_GELU_DUAL, w.fc1_b, nullptr, 0, nullptr, 0};
-      if (gemm_plan_init(&p.fc1, M, F, D, e->xn, D, w.fc1_w, D, e->g, F, e->u[l], F, e->T, 3 * LORA_PAD, s1.lb_fwd,
+      GemmEpilogue ep = plain;
+      ep.mode = EPI_GELU_DUAL;
+      ep.bias = w.fc1_b;
+      if (fold) {
+        ep.row_stats = e->st2[l];
+        ep.c1 = w.fc1_c1;
+      }
+      if (gemm_plan_init(&p.fc1, M, F, D, a_ln2, D, w.fc1_w, D, e->g, F, e->u[l], F, e->T, 3 * LORA_PAD, s1.lb_fwd,
                          LORA_PAD, s1.rank > 0 ? 1 : 0, lora_ksteps(s1.rank), 0, ep))
         return 1;
     }
@@ -290,12 +308,15 @@ static int encoder_forward(vitatk_engine* e, PlanSet* ps, int batch, cudaStream_
     const LayerWeights& w = e->lw[l];
     LayerPlans& p = ps->layers[l];
     const int rq = w.lora[VITATK_SITE_QKV].rank, r1 = w.lora[VITATK_SITE_FC1].rank;
+    const bool fold = w.qkv_c1 != nullptr && w.fc1_c1 != nullptr;
     // Legacy mma.sync is slow on sm_100 (measured: +14 us per launch with one 8-column tile of T, +72 us with three),
     // so the fusion only pays for single-tile sites (it replaces a 23 us skinny GEMM); the 3-adapter q|k|v site keeps
     // its own GEMM.
-    const bool ln1_t = e->fuse_ln_t && rq > 0 && 3 * ((rq + 7) / 8) <= 1;
-    const bool ln2_t = e->fuse_ln_t && r1 > 0 && r1 <= 8;
-    if (ln1_t)
+    const bool ln1_t = !fold && e->fuse_ln_t && rq > 0 && 3 * ((rq + 7) / 8) <= 1;
+    const bool ln2_t = !fold && e->fuse_ln_t && r1 > 0 && r1 <= 8;
+    if (fold)  // only (mean, rstd): the normalisation itself happens in the qkv GEMM's epilogue
+      RUNC(CAT_LN_FWD, 0, layernorm_stats(e->h[l], e->st1[l], M, D, c.ln_eps, s));
+    else if (ln1_t)
       RUNC(CAT_LN_FWD, 0, layernorm_fwd_t(e->h[l], w.ln1_g, w.ln1_b, e->xn, e->st1[l], M, D, c.ln_eps,
                                           w.lora[VITATK_SITE_QKV].la_fwd, 3, rq, e->T, 3 * LORA_PAD, s));
     else
@@ -305,7 +326,9 @@ static int encoder_forward(vitatk_engine* e, PlanSet* ps, int batch, cudaStream_
     RUNC(CAT_ATTN_FWD, 4.0 * batch * c.heads * TOKENS * TOKENS * 64, attention_fwd_tc05(&ps->attn_fwd[l], s));
     if (w.lora[VITATK_SITE_PROJ].rank > 0) RUN_GEMM(CAT_T_PROJ, &p.t_proj);
     RUN_GEMM(CAT_PROJ, &p.proj);
-    if (ln2_t)
+    if (fold)
+      RUNC(CAT_LN_FWD, 0, layernorm_stats(e->h_mid[l], e->st2[l], M, D, c.ln_eps, s));
+    else if (ln2_t)
       RUNC(CAT_LN_FWD, 0, layernorm_fwd_t(e->h_mid[l], w.ln2_g, w.ln2_b, e->xn, e->st2[l], M, D, c.ln_eps,
                                           w.lora[VITATK_SITE_FC1].la_fwd, 1, r1, e->T, 3 * LORA_PAD, s));
     else
@@ -473,6 +496,8 @@ int vitatk_set_tensor(vitatk_engine* e, int id, int layer, const void* p, long l
     case VITATK_FC2_W: w->fc2_w = pb; want = F * D * 2; break;
     case VITATK_FC2_WT: w->fc2_wt = pb; want = F * D * 2; break;
     case VITATK_FC2_B: w->fc2_b = pf; want = D * 4; break;
+    case VITATK_QKV_C1: w->qkv_c1 = pf; want = 3 * D * 4; break;
+    case VITATK_FC1_C1: w->fc1_c1 = pf; want = F * 4; break;
     default: set_error("vitatk_set_tensor: unknown tensor id %d", id); return 1;
   }
   if (nbytes != want) {
@@ -714,10 +739,21 @@ int vitatk_count_correct(vitatk_engine* e, const float* images, const int64_t* l
 int vitatk_k_gemm(int M, int N, int K, const void* A, int lda, const void* B, int ldb, void* out, int ldo, void* out2,
                   int ldo2, const void* T, int ldt, const void* LB, int ldlb, int lora_nkb, int lora_ksteps_,
                   int lora_group_cols, int epi_mode, const float* bias, const void* res, int ld_res, const float* table,
-                  int table_rows, float* rowdot, int rowdot_rows, int rowdot_pad, int use_simt, void* stream) {
+                  int table_rows, float* rowdot, int rowdot_rows, int rowdot_pad, const float* row_stats, const float* c1,
+                  int use_simt, void* stream) {
   GemmPlan p;
-  GemmEpilogue ep = {epi_mode, bias, static_cast<const bf16*>(res), ld_res, table, table_rows, rowdot, rowdot_rows,
-                     rowdot_pad};
+  GemmEpilogue ep = {};
+  ep.mode = epi_mode;
+  ep.bias = bias;
+  ep.res = static_cast<const bf16*>(res);
+  ep.ld_res = ld_res;
+  ep.table = table;
+  ep.table_rows = table_rows;
+  ep.rowdot = rowdot;
+  ep.rowdot_rows = rowdot_rows;
+  ep.rowdot_pad = rowdot_pad;
+  ep.row_stats = reinterpret_cast<const float2*>(row_stats);
+  ep.c1 = c1;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (use_simt) {
     p.M = M; p.N = N; p.K = K; p.BN = 0;
@@ -791,6 +827,10 @@ int vitatk_k_layernorm_bwd_t(const void* dy, const void* x, const float* stats, 
   return layernorm_bwd_t(static_cast<const bf16*>(dy), static_cast<const bf16*>(x), reinterpret_cast<const float2*>(stats),
                          gamma, static_cast<const bf16*>(dres), static_cast<bf16*>(dx), rows, cols,
                          static_cast<const bf16*>(lora), groups, rank, static_cast<bf16*>(T), ldt,
+                         static_cast<cudaStream_t>(stream));
+}
+int vitatk_k_layernorm_stats(const void* x, float* stats, int rows, int cols, float eps, void* stream) {
+  return layernorm_stats(static_cast<const bf16*>(x), reinterpret_cast<float2*>(stats), rows, cols, eps,
                          static_cast<cudaStream_t>(stream));
 }
 static PixelNorm make_norm(const float* mean3, const float* std3) {

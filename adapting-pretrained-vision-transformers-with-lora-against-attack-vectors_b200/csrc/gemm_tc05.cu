@@ -419,6 +419,19 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive_cluster(tmem_empty_remote + buf * 8);
         }
+        if (epi.row_stats != nullptr) {  // LayerNorm folded into this GEMM: acc <- rstd * (acc - mean * c1[n])
+          const float2 st = row_ok ? __ldg(epi.row_stats + row) : make_float2(0.f, 1.f);
+          const float nm = -st.x * st.y;
+          const float4* cp = reinterpret_cast<const float4*>(epi.c1 + ncol);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float4 c = __ldg(cp + j);
+            v[4 * j] = fmaf(v[4 * j], st.y, nm * c.x);
+            v[4 * j + 1] = fmaf(v[4 * j + 1], st.y, nm * c.y);
+            v[4 * j + 2] = fmaf(v[4 * j + 2], st.y, nm * c.z);
+            v[4 * j + 3] = fmaf(v[4 * j + 3], st.y, nm * c.w);
+          }
+        }
         if (epi.bias != nullptr && !(DBG && (args.dbg & 64))) {
           const float4* bp = reinterpret_cast<const float4*>(epi.bias + ncol);
 #pragma unroll
@@ -599,6 +612,19 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (epi.row_stats != nullptr) {  // LayerNorm folded into this GEMM
+          const float2 st = row_ok ? __ldg(epi.row_stats + row) : make_float2(0.f, 1.f);
+          const float nm = -st.x * st.y;
+          const float4* cp = reinterpret_cast<const float4*>(epi.c1 + ncol);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 c = __ldg(cp + j);
+            v[4 * j] = fmaf(v[4 * j], st.y, nm * c.x);
+            v[4 * j + 1] = fmaf(v[4 * j + 1], st.y, nm * c.y);
+            v[4 * j + 2] = fmaf(v[4 * j + 2], st.y, nm * c.z);
+            v[4 * j + 3] = fmaf(v[4 * j + 3], st.y, nm * c.w);
+          }
+        }
         if (epi.bias != nullptr) {
           const float4* bp = reinterpret_cast<const float4*>(epi.bias + ncol);
 #pragma unroll
@@ -700,6 +726,7 @@ __global__ void gemm_simt_kernel(GemmKernelArgs args, const bf16* A, int lda, co
                __bfloat162float(LB[(size_t)n * ldlb + j * 64 + k]);
   }
   const GemmEpilogue& e = args.epi;
+  if (e.row_stats) acc = e.row_stats[m].y * (acc - e.row_stats[m].x * e.c1[n]);
   if (e.bias) acc += e.bias[n];
   if (e.mode == EPI_RESIDUAL) acc += __bfloat162float(e.res[(size_t)m * e.ld_res + n]);
   if (e.mode == EPI_MUL) acc *= __bfloat162float(e.res[(size_t)m * e.ld_res + n]);

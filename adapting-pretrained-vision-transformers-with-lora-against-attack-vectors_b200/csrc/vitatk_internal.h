@@ -87,6 +87,11 @@ struct GemmEpilogue {
   int ld_res;
   const float* table;   // [table_rows, N] fp32 (EPI_ROWTABLE)
   int table_rows;
+  // LayerNorm folded into the GEMM (any mode): the A operand is the RAW LayerNorm input h, B holds gamma o W, and the
+  // epilogue first applies acc <- rstd[m] * (acc - mean[m] * c1[n]) (c1[n] = sum_k of the effective folded weight row,
+  // LoRA included); the beta / bias part arrives through `bias`.  row_stats = (mean, rstd) per row, null = off.
+  const float2* row_stats;
+  const float* c1;
   float* rowdot;        // EPI_ROWDOT side output, [(M / rowdot_rows) * (N / 64), rowdot_pad] fp32
   int rowdot_rows;      // rows per group (tokens per image)
   int rowdot_pad;       // row pitch of the side output (208)
@@ -156,6 +161,8 @@ int attention_bwd(const bf16* qkv, const bf16* dout, bf16* dqkv, int batch, int 
 // ---------------------------------------------------------------------------------------------
 // LayerNorm / head / PGD kernels (HBM-bound)
 // ---------------------------------------------------------------------------------------------
+// (mean, rstd) per row only: the read-only half of LayerNorm, for consumers that fold the normalisation into a GEMM
+int layernorm_stats(const bf16* x, float2* stats, int rows, int cols, float eps, cudaStream_t stream);
 int layernorm_fwd(const bf16* x, const float* gamma, const float* beta, bf16* y, float2* stats, int rows,
                   int cols, float eps, cudaStream_t stream);
 // dx_out = dres + LN_backward(dy) ; x is the saved LN input, stats = (mean, rstd)

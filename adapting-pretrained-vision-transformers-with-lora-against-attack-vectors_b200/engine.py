@@ -30,6 +30,7 @@ TOKENS = 197
 T_PATCH_W, T_PATCH_WT, T_EMBED, T_LNF_G, T_LNF_B, T_HEAD_W, T_HEAD_B = 0, 1, 2, 3, 4, 5, 6
 T_LN1_G, T_LN1_B, T_QKV_W, T_QKV_WT, T_QKV_B, T_PROJ_W, T_PROJ_WT, T_PROJ_B = 16, 17, 18, 19, 20, 21, 22, 23
 T_LN2_G, T_LN2_B, T_FC1_W, T_FC1_WT, T_FC1_B, T_FC2_W, T_FC2_WT, T_FC2_B = 24, 25, 26, 27, 28, 29, 30, 31
+T_QKV_C1, T_FC1_C1 = 32, 33
 SITE_QKV, SITE_PROJ, SITE_FC1, SITE_FC2 = 0, 1, 2, 3
 
 Adapter = Tuple[torch.Tensor, torch.Tensor, float]  # (A [r,in], B [out,r], scale)
@@ -97,6 +98,9 @@ class Engine:
         if not torch.cuda.is_available():
             raise _lib.VitatkError("vitatk needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
+        # LayerNorm folded into the qkv / fc1 GEMMs: LN(h) W^T = rstd (h (gamma o W)^T - mean c1) + c2
+        import os as _os
+        self.ln_fold = _os.environ.get("VITATK_LN_FOLD", "1") != "0"
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         if model is not None:
             sd = model.state_dict()
@@ -171,22 +175,46 @@ class Engine:
             a = p + "attention.attention."
             wqkv = torch.cat([g(a + "query.weight"), g(a + "key.weight"), g(a + "value.weight")], 0)
             bqkv = torch.cat([g(a + "query.bias"), g(a + "key.bias"), g(a + "value.bias")], 0)
-            self._set(T_QKV_W, l, wqkv, bf)
+            wfc1, bfc1 = g(p + "intermediate.dense.weight"), g(p + "intermediate.dense.bias")
+            g1, b1 = g(p + "layernorm_before.weight"), g(p + "layernorm_before.bias")
+            g2, b2 = g(p + "layernorm_after.weight"), g(p + "layernorm_after.bias")
+            fold = self.ln_fold and self.dim == 768
+            # forward operands of the two LayerNorm-fed GEMMs: folded = gamma o W (the backward keeps the plain W^T)
+            wqkv_f = (wqkv * g1[None, :]) if fold else wqkv
+            wfc1_f = (wfc1 * g2[None, :]) if fold else wfc1
+            self._set(T_QKV_W, l, wqkv_f, bf)
             self._set(T_QKV_WT, l, wqkv.t(), bf)
-            self._set(T_QKV_B, l, bqkv, f32)
+            self._set(T_FC1_W, l, wfc1_f, bf)
+            self._set(T_FC1_WT, l, wfc1.t(), bf)
             for (w_id, wt_id, b_id, key) in ((T_PROJ_W, T_PROJ_WT, T_PROJ_B, "attention.output.dense"),
-                                             (T_FC1_W, T_FC1_WT, T_FC1_B, "intermediate.dense"),
                                              (T_FC2_W, T_FC2_WT, T_FC2_B, "output.dense")):
                 w = g(p + key + ".weight")
                 self._set(w_id, l, w, bf)
                 self._set(wt_id, l, w.t(), bf)
                 self._set(b_id, l, g(p + key + ".bias"), f32)
-            self._upload_lora(l, p)
+            lora_c = self._upload_lora(l, p, {SITE_QKV: (g1, b1), SITE_FC1: (g2, b2)} if fold else {})
+            if fold:
+                # c1[n] = sum_k of the bf16 operands the tensor cores really see (+ the adapter's share), c2 in fp32
+                zc = (0.0, 0.0)
+                c1q = wqkv_f.to(bf).float().sum(1) + lora_c.get(SITE_QKV, zc)[0]
+                c2q = bqkv + wqkv @ b1 + lora_c.get(SITE_QKV, zc)[1]
+                c1f = wfc1_f.to(bf).float().sum(1) + lora_c.get(SITE_FC1, zc)[0]
+                c2f = bfc1 + wfc1 @ b2 + lora_c.get(SITE_FC1, zc)[1]
+                self._set(T_QKV_B, l, c2q, f32)
+                self._set(T_FC1_B, l, c2f, f32)
+                self._set(T_QKV_C1, l, c1q, f32)
+                self._set(T_FC1_C1, l, c1f, f32)
+            else:
+                self._set(T_QKV_B, l, bqkv, f32)
+                self._set(T_FC1_B, l, bfc1, f32)
 
     def _site_adapters(self, names: Sequence[str]) -> List[List[Adapter]]:
         return [list(self.adapters.get(n, [])) for n in names]
 
-    def _upload_lora(self, l: int, p: str) -> None:
+    def _upload_lora(self, l: int, p: str, fold: Dict[int, Tuple[torch.Tensor, torch.Tensor]]):
+        """Pack and register the adapters of layer ``l``.  ``fold`` maps a site to the (gamma, beta) of the LayerNorm
+        feeding it when that LayerNorm is folded into the site's GEMM: the forward down-projection then runs on the raw
+        LayerNorm input with gamma o A, and the adapter's share of the c1 / c2 epilogue vectors is returned per site."""
         a = p + "attention.attention."
         sites = (
             (SITE_QKV, [a + "query", a + "key", a + "value"], self.dim, self.dim),
@@ -194,15 +222,18 @@ class Engine:
             (SITE_FC1, [p + "intermediate.dense"], self.dim, self.mlp_dim),
             (SITE_FC2, [p + "output.dense"], self.mlp_dim, self.dim),
         )
+        shares = {}
         for site, names, n_in, n_out in sites:
             groups = self._site_adapters(names)
             if not any(groups):
                 continue
             G = len(names)
+            gamma, beta = fold.get(site, (None, None))
             la_fwd = torch.zeros(LORA_PAD * G, n_in, device=self.device)
             lb_fwd = torch.zeros(n_out * G, LORA_PAD, device=self.device)
             lb_bwd = torch.zeros(LORA_PAD * G, n_out * G, device=self.device)
             la_bwd = torch.zeros(n_in, LORA_PAD * G, device=self.device)
+            c2 = torch.zeros(n_out * G, device=self.device)
             rmax = 0
             for gi, ads in enumerate(groups):
                 r0 = 0
@@ -214,15 +245,24 @@ class Engine:
                         raise _lib.VitatkError(f"adapter shape mismatch on {names[gi]}: A {tuple(A.shape)} B {tuple(B.shape)}")
                     if r0 + r > LORA_PAD:
                         raise _lib.VitatkError(f"total LoRA rank on {names[gi]} exceeds {LORA_PAD}")
-                    la_fwd[LORA_PAD * gi + r0: LORA_PAD * gi + r0 + r] = A
+                    la_fwd[LORA_PAD * gi + r0: LORA_PAD * gi + r0 + r] = A if gamma is None else A * gamma[None, :]
                     lb_fwd[n_out * gi: n_out * (gi + 1), r0: r0 + r] = s * B
                     lb_bwd[LORA_PAD * gi + r0: LORA_PAD * gi + r0 + r, n_out * gi: n_out * (gi + 1)] = B.t()
                     la_bwd[:, LORA_PAD * gi + r0: LORA_PAD * gi + r0 + r] = s * A.t()
+                    if gamma is not None:
+                        c2[n_out * gi: n_out * (gi + 1)] += s * (B @ (A @ beta))
                     r0 += r
                 rmax = max(rmax, r0)
             bufs = [self._dev(t, torch.bfloat16) for t in (la_fwd, lb_fwd, lb_bwd, la_bwd)]
             _lib.check(self.lib.vitatk_set_lora(self._h, l, site, rmax, *[b.data_ptr() for b in bufs]),
                        f"vitatk_set_lora(layer {l}, site {site})")
+            if gamma is not None:
+                # c1 share from the bf16 operands: row n of group gi sees sum_j lb_fwd[n, j] * sum_k la_fwd[64 gi + j, k]
+                a_sum = bufs[0].float().sum(1).reshape(G, LORA_PAD)
+                lb = bufs[1].float().reshape(G, n_out, LORA_PAD)
+                c1 = torch.einsum("gnj,gj->gn", lb, a_sum).reshape(-1)
+                shares[site] = (c1, c2)
+        return shares
 
     # ------------------------------------------------------------------ helpers
     def _stream(self) -> int:

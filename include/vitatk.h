@@ -63,7 +63,13 @@ enum vitatk_tensor_id {
   VITATK_FC1_B = 28,
   VITATK_FC2_W = 29,     /* bf16 [768, 3072]  output.dense (HF:305) */
   VITATK_FC2_WT = 30,    /* bf16 [3072, 768] */
-  VITATK_FC2_B = 31
+  VITATK_FC2_B = 31,
+  /* Optional: LayerNorm folded into the qkv / fc1 GEMMs, LN(h) W^T = rstd (h (gamma o W)^T - mean c1) + c2.  When a layer
+   * has BOTH c1 vectors set it runs folded and the caller must have passed: QKV_W / FC1_W = gamma o W (the transposes
+   * QKV_WT / FC1_WT stay un-folded: the backward needs W), QKV_B / FC1_B = c2 = W beta + s B (A beta) + b, the QKV / FC1
+   * adapter la_fwd = gamma o A, and c1[n] = sum_k (gamma o W)[n,k] + sum_j lb_fwd[n,j] sum_k (gamma o A)[j,k]. */
+  VITATK_QKV_C1 = 32,    /* fp32 [2304] */
+  VITATK_FC1_C1 = 33     /* fp32 [3072] */
 };
 
 /* Adapter sites for vitatk_set_lora (train_loras.py:79-95 target_modules; q,k,v share one fused site). */
@@ -141,7 +147,8 @@ int vitatk_k_gemm(int M, int N, int K, const void* A_dev, int lda, const void* B
                   int ldo, void* out2_dev, int ldo2, const void* T_dev, int ldt, const void* LB_dev, int ldlb,
                   int lora_nkb, int lora_ksteps, int lora_group_cols, int epi_mode, const float* bias_dev,
                   const void* res_dev, int ld_res, const float* table_dev, int table_rows, float* rowdot_dev,
-                  int rowdot_rows, int rowdot_pad, int use_simt, void* stream);
+                  int rowdot_rows, int rowdot_pad, const float* row_stats_dev, const float* c1_dev, int use_simt,
+                  void* stream);
 int vitatk_k_attention_fwd(const void* qkv_dev, void* out_dev, int batch, int tokens, int heads, void* stream);
 /* tcgen05 forward (the engine's path); lse2_dev (optional) receives [batch*heads, 208] log2-domain logsumexp */
 int vitatk_k_attention_fwd_tc05(const void* qkv_dev, void* out_dev, float* lse2_dev, int batch, int tokens, int heads,
@@ -161,6 +168,8 @@ int vitatk_k_attention_bwd(const void* qkv_dev, const void* dout_dev, void* dqkv
                            int heads, void* stream);
 int vitatk_k_layernorm_fwd(const void* x_dev, const float* gamma_dev, const float* beta_dev, void* y_dev,
                            float* stats_dev, int rows, int cols, float eps, void* stream);
+/* (mean, rstd) per row only (stats_dev fp32 [rows, 2]) */
+int vitatk_k_layernorm_stats(const void* x_dev, float* stats_dev, int rows, int cols, float eps, void* stream);
 int vitatk_k_layernorm_bwd(const void* dy_dev, const void* x_dev, const float* stats_dev, const float* gamma_dev,
                            const void* dres_dev, void* dx_dev, int rows, int cols, void* stream);
 /* LayerNorm variants that also write T[row, 64 g + j] = out[row, :] . lora[64 g + j, :] (the LoRA x*A^T of the site the

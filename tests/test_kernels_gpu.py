@@ -27,7 +27,7 @@ def _dgelu(u):
 
 
 def run_gemm(lib, A, B, epi=EPI_PLAIN, bias=None, res=None, table=None, T=None, LB=None, nkb=0, ksteps=0,
-             group_cols=0, simt=False, rowdot=None, rowdot_rows=0):
+             group_cols=0, simt=False, rowdot=None, rowdot_rows=0, row_stats=None, c1=None):
     from vitatk import _lib
 
     M, K = A.shape
@@ -38,7 +38,7 @@ def run_gemm(lib, A, B, epi=EPI_PLAIN, bias=None, res=None, table=None, T=None, 
                            0 if T is None else T.stride(0), _p(LB), 0 if LB is None else LB.stride(0), nkb, ksteps,
                            group_cols, epi, _p(bias), _p(res), 0 if res is None else res.stride(0), _p(table),
                            0 if table is None else table.shape[0], _p(rowdot), rowdot_rows,
-                           0 if rowdot is None else rowdot.shape[1], 1 if simt else 0, _s())
+                           0 if rowdot is None else rowdot.shape[1], _p(row_stats), _p(c1), 1 if simt else 0, _s())
     _lib.check(rc, "vitatk_k_gemm")
     torch.cuda.synchronize()
     return out, out2
@@ -166,6 +166,37 @@ def test_gemm_rowdot_epilogue(lib, images, tokens):
     check_close(out, want, "rowdot gemm out")
     dref = (out.float() * res.float()).reshape(images, tokens, 12, 64).sum(-1).permute(0, 2, 1).reshape(images * 12, tokens)
     torch.testing.assert_close(side[:, :tokens], dref, rtol=2e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize("M,N,epi", [(1576, 2304, EPI_PLAIN), (1576, 3072, EPI_GELU_DUAL), (50432, 2304, EPI_PLAIN),
+                                     (1576, 192, EPI_PLAIN)])
+def test_gemm_layernorm_fold(lib, M, N, epi):
+    """LN folded into the GEMM: A = raw h, B = gamma o W, epilogue rstd (acc - mean c1) + c2 == LN(h) W^T + b."""
+    from vitatk import _lib
+
+    K = 768
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    rn = lambda *s: torch.randn(*s, device="cuda", generator=g)  # noqa: E731
+    h = (rn(M, K) * 2 + 0.7).to(torch.bfloat16)
+    gamma, beta = 1 + 0.1 * rn(K), 0.1 * rn(K)
+    W = rn(N, K) / math.sqrt(K)
+    b = rn(N) * 0.1
+    Wf = (W * gamma[None, :]).to(torch.bfloat16)
+    c1 = Wf.float().sum(1)
+    c2 = b + W @ beta
+    stats = torch.empty(M, 2, device="cuda")
+    _lib.check(lib.vitatk_k_layernorm_stats(_p(h), _p(stats), M, K, 1e-12, _s()), "ln_stats")
+    out, out2 = run_gemm(lib, h, Wf, epi, c2.contiguous(), row_stats=stats, c1=c1.contiguous())
+    ref = torch.nn.functional.layer_norm(h.float(), (K,), gamma, beta, eps=1e-12) @ W.t() + b
+    if epi == EPI_GELU_DUAL:
+        check_close(out, _gelu(ref), "ln-fold gelu")
+        check_close(out2, _dgelu(ref), "ln-fold gelu'")
+    else:
+        check_close(out, ref, "ln-fold gemm")
+    torch.testing.assert_close(stats[:, 0], h.float().mean(-1), rtol=1e-4, atol=1e-4)
+    if M <= 2000:
+        s_out, _ = run_gemm(lib, h, Wf, epi, c2.contiguous(), row_stats=stats, c1=c1.contiguous(), simt=True)
+        check_close(s_out, _gelu(ref) if epi == EPI_GELU_DUAL else ref, "ln-fold simt")
 
 
 def test_gemm_rejects_bad_shapes(lib):

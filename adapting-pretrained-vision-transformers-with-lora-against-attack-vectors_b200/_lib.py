@@ -78,7 +78,7 @@ EXPORTS = [
     "vitatk_k_attention_bwd", "vitatk_k_layernorm_fwd", "vitatk_k_layernorm_bwd", "vitatk_k_pgd_update",
     "vitatk_k_pgd_init", "vitatk_profile_begin", "vitatk_profile_end", "vitatk_k_attention_fwd_tc05",
     "vitatk_k_attention_bwd_tc05", "vitatk_k_attention_bwd_fused", "vitatk_k_attention_bwd_trace",
-    "vitatk_k_attention_fwd_trace", "vitatk_k_layernorm_fwd_t", "vitatk_k_layernorm_bwd_t",
+    "vitatk_k_attention_fwd_trace", "vitatk_k_layernorm_fwd_t", "vitatk_k_layernorm_bwd_t", "vitatk_k_layernorm_stats",
 ]
 
 
@@ -122,7 +122,7 @@ def load() -> C.CDLL:
     lib.vitatk_count_correct.argtypes = [vp, vp, vp, i, vp, vp]
     lib.vitatk_profile_begin.argtypes = [vp]
     lib.vitatk_profile_end.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(ll)]
-    lib.vitatk_k_gemm.argtypes = [i, i, i, vp, i, vp, i, vp, i, vp, i, vp, i, vp, i, i, i, i, i, vp, vp, i, vp, i, vp, i, i, vp, vp, i, vp]
+    lib.vitatk_k_gemm.argtypes = [i, i, i, vp, i, vp, i, vp, i, vp, i, vp, i, vp, i, i, i, i, i, vp, vp, i, vp, i, vp, i, i, vp, vp, vp, f, i, vp]
     lib.vitatk_k_attention_fwd.argtypes = [vp, vp, i, i, i, vp]
     lib.vitatk_k_attention_fwd_tc05.argtypes = [vp, vp, vp, i, i, i, vp]
     lib.vitatk_k_attention_bwd_tc05.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, vp]

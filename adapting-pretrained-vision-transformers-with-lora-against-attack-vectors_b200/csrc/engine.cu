@@ -105,6 +105,7 @@ struct vitatk_engine {
   PixelNorm nrm;
   // optional per-launch CUDA-event timing (bench.py's roofline leg; off in the timed region)
   bool attn_bwd_two_kernel = false;  // VITATK_ATTN_BWD=2k selects the older dQ + dK/dV kernel pair
+  bool fuse_stats = true;            // folded LayerNorm: (mean, rstd) come out of the skinny LoRA GEMM (VITATK_FUSE_STATS=0: stats kernel)
   bool fuse_ln_t = false;            // LayerNorm kernels also produce the LoRA x*A^T of the site they feed
   bool fuse_delta = false;           // delta comes out of the proj-backward GEMM epilogue (pair kernel) instead of a kernel
   bool prof = false;
@@ -154,10 +155,17 @@ static int build_plans(vitatk_engine* e, int batch, PlanSet** out) {
     if (attention_bwd_plan_init(&ps->attn_bwd[l], e->qkv[l], e->dao, e->ao[l], e->lse2[l], e->delta, e->dqkv, batch,
                                 TOKENS, c.heads))
       return 1;
-    if (sq.rank > 0 &&
-        gemm_plan_init(&p.t_qkv, M, 3 * LORA_PAD, D, a_ln1, D, sq.la_fwd, D, e->T, 3 * LORA_PAD, nullptr, 0, nullptr, 0,
-                       nullptr, 0, 0, 0, 0, plain))
-      return 1;
+    {
+      GemmEpilogue ep = plain;
+      if (fold && e->fuse_stats) {  // the skinny GEMM streams h anyway: it also produces LN1's (mean, rstd)
+        ep.stats_out = e->st1[l];
+        ep.stats_eps = c.ln_eps;
+      }
+      if (sq.rank > 0 &&
+          gemm_plan_init(&p.t_qkv, M, 3 * LORA_PAD, D, a_ln1, D, sq.la_fwd, D, e->T, 3 * LORA_PAD, nullptr, 0, nullptr, 0,
+                         nullptr, 0, 0, 0, 0, ep))
+        return 1;
+    }
     {
       GemmEpilogue ep = plain;
       ep.bias = w.qkv_b;
@@ -179,10 +187,17 @@ static int build_plans(vitatk_engine* e, int batch, PlanSet** out) {
                          sp.lb_fwd, LORA_PAD, sp.rank > 0 ? 1 : 0, lora_ksteps(sp.rank), 0, ep))
         return 1;
     }
-    if (s1.rank > 0 &&
-        gemm_plan_init(&p.t_fc1, M, LORA_PAD, D, a_ln2, D, s1.la_fwd, D, e->T, 3 * LORA_PAD, nullptr, 0, nullptr, 0,
-                       nullptr, 0, 0, 0, 0, plain))
-      return 1;
+    {
+      GemmEpilogue ep = plain;
+      if (fold && e->fuse_stats) {
+        ep.stats_out = e->st2[l];
+        ep.stats_eps = c.ln_eps;
+      }
+      if (s1.rank > 0 &&
+          gemm_plan_init(&p.t_fc1, M, LORA_PAD, D, a_ln2, D, s1.la_fwd, D, e->T, 3 * LORA_PAD, nullptr, 0, nullptr, 0,
+                         nullptr, 0, 0, 0, 0, ep))
+        return 1;
+    }
     {
       GemmEpilogue ep = plain;
       ep.mode = EPI_GELU_DUAL;
@@ -314,9 +329,9 @@ static int encoder_forward(vitatk_engine* e, PlanSet* ps, int batch, cudaStream_
     // its own GEMM.
     const bool ln1_t = !fold && e->fuse_ln_t && rq > 0 && 3 * ((rq + 7) / 8) <= 1;
     const bool ln2_t = !fold && e->fuse_ln_t && r1 > 0 && r1 <= 8;
-    if (fold)  // only (mean, rstd): the normalisation itself happens in the qkv GEMM's epilogue
-      RUNC(CAT_LN_FWD, 0, layernorm_stats(e->h[l], e->st1[l], M, D, c.ln_eps, s));
-    else if (ln1_t)
+    if (fold) {  // only (mean, rstd): the normalisation itself happens in the qkv GEMM's epilogue
+      if (!(rq > 0 && p.t_qkv.epi.stats_out)) RUNC(CAT_LN_FWD, 0, layernorm_stats(e->h[l], e->st1[l], M, D, c.ln_eps, s));
+    } else if (ln1_t)
       RUNC(CAT_LN_FWD, 0, layernorm_fwd_t(e->h[l], w.ln1_g, w.ln1_b, e->xn, e->st1[l], M, D, c.ln_eps,
                                           w.lora[VITATK_SITE_QKV].la_fwd, 3, rq, e->T, 3 * LORA_PAD, s));
     else
@@ -326,9 +341,10 @@ static int encoder_forward(vitatk_engine* e, PlanSet* ps, int batch, cudaStream_
     RUNC(CAT_ATTN_FWD, 4.0 * batch * c.heads * TOKENS * TOKENS * 64, attention_fwd_tc05(&ps->attn_fwd[l], s));
     if (w.lora[VITATK_SITE_PROJ].rank > 0) RUN_GEMM(CAT_T_PROJ, &p.t_proj);
     RUN_GEMM(CAT_PROJ, &p.proj);
-    if (fold)
-      RUNC(CAT_LN_FWD, 0, layernorm_stats(e->h_mid[l], e->st2[l], M, D, c.ln_eps, s));
-    else if (ln2_t)
+    if (fold) {
+      if (!(r1 > 0 && p.t_fc1.epi.stats_out))
+        RUNC(CAT_LN_FWD, 0, layernorm_stats(e->h_mid[l], e->st2[l], M, D, c.ln_eps, s));
+    } else if (ln2_t)
       RUNC(CAT_LN_FWD, 0, layernorm_fwd_t(e->h_mid[l], w.ln2_g, w.ln2_b, e->xn, e->st2[l], M, D, c.ln_eps,
                                           w.lora[VITATK_SITE_FC1].la_fwd, 1, r1, e->T, 3 * LORA_PAD, s));
     else
@@ -431,6 +447,8 @@ int vitatk_create(const vitatk_config* cfg, vitatk_engine** out) {
     e->attn_bwd_two_kernel = v && strcmp(v, "2k") == 0;
     const char* g2 = getenv("VITATK_GEMM_2CTA");
     const char* fd = getenv("VITATK_FUSE_DELTA");
+    const char* fs = getenv("VITATK_FUSE_STATS");
+    e->fuse_stats = !(fs && fs[0] == '0');
     const char* flt = getenv("VITATK_FUSE_LN_T");
     // opt-in: measured perf-neutral on B200 (skinny GEMMs -8 ms, LayerNorm kernels +8 ms per PGD-10 step: the legacy
     // mma.sync the LN kernels use for the projection is slow on sm_100)
@@ -740,7 +758,7 @@ int vitatk_k_gemm(int M, int N, int K, const void* A, int lda, const void* B, in
                   int ldo2, const void* T, int ldt, const void* LB, int ldlb, int lora_nkb, int lora_ksteps_,
                   int lora_group_cols, int epi_mode, const float* bias, const void* res, int ld_res, const float* table,
                   int table_rows, float* rowdot, int rowdot_rows, int rowdot_pad, const float* row_stats, const float* c1,
-                  int use_simt, void* stream) {
+                  float* stats_out, float stats_eps, int use_simt, void* stream) {
   GemmPlan p;
   GemmEpilogue ep = {};
   ep.mode = epi_mode;
@@ -754,6 +772,8 @@ int vitatk_k_gemm(int M, int N, int K, const void* A, int lda, const void* B, in
   ep.rowdot_pad = rowdot_pad;
   ep.row_stats = reinterpret_cast<const float2*>(row_stats);
   ep.c1 = c1;
+  ep.stats_out = reinterpret_cast<float2*>(stats_out);
+  ep.stats_eps = stats_eps;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (use_simt) {
     p.M = M; p.N = N; p.K = K; p.BN = 0;

@@ -193,7 +193,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == MMA_WARP && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       ptx::mbar_init(&full_bar[s], 1);  // pair: the leader's producer expects the bytes of BOTH CTAs' loads
-      ptx::mbar_init(&empty_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], (!TWO && args.epi.stats_out != nullptr) ? 5 : 1);  // + the four row-statistics warps
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(&tmem_full[b], 1);
@@ -571,11 +571,46 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int i = 0; i < 4; ++i) aux_next[i] = __ldg(rp + i);
       }
     }
+    uint32_t scnt = 0;  // k-block counter of the row-statistics warps (same sequence as the producer's)
     for (int tile = unit; tile < num_tiles; tile += num_units, ++it) {
       const int m0 = (tile / tiles_n) * TILE_M + static_cast<int>(rank) * BM;
       const int n0 = (tile % tiles_n) * BN;
       const uint32_t buf = it & 1;
       const uint32_t use = it >> 1;
+      if (!TWO && epi.stats_out != nullptr && hsel == 0) {
+        // LayerNorm statistics of this tile's 128 A rows, read from the operand stages as they land (thread = row).
+        // Shifted accumulation (d = x - x[0]) keeps the single-pass variance well conditioned when |mean| >> std.
+        const int srow = q * 32 + lane;
+        float shift = 0.f, sd = 0.f, sdd = 0.f;
+        for (int kb = 0; kb < num_kb; ++kb, ++scnt) {
+          const int s = scnt % STAGES;
+          ptx::mbar_wait(&full_bar[s], (scnt / STAGES) & 1);
+          if (kb < main_kb) {
+            const uint32_t rowaddr = ptx::smem_u32(smem_stage + s * Cfg::STAGE_BYTES) + srow * 128;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              uint4 a;
+              const uint32_t addr = rowaddr + ((c ^ (srow & 7)) << 4);
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(addr));
+              float f[8];
+              unpack_bf16x8(a, f);
+              if (kb == 0 && c == 0) shift = f[0];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const float d = f[k] - shift;
+                sd += d;
+                sdd = fmaf(d, d, sdd);
+              }
+            }
+          }
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&empty_bar[s]);
+        }
+        const float inv_k = 1.0f / static_cast<float>(args.K);
+        const float md = sd * inv_k;
+        const float var = fmaxf(sdd * inv_k - md * md, 0.f);
+        if (m0 + srow < args.M) epi.stats_out[m0 + srow] = make_float2(shift + md, rsqrtf(var + epi.stats_eps));
+      }
       ptx::mbar_wait(&tmem_full[buf], use & 1);
       ptx::tc_fence_after();
       const int row = m0 + q * 32 + lane;
@@ -853,6 +888,10 @@ int gemm_plan_init(GemmPlan* p, int M, int N, int K, const bf16* A, int lda, con
     if (make_tmap_2d(&p->tmOut2, out2, M, N, ldo2, obc, obr, osw)) return 1;
   } else {
     p->tmOut2 = p->tmOut;
+  }
+  if (epi.stats_out && (p->two_cta || N != p->BN || lora_nkb != 0)) {
+    set_error("gemm_plan_init: row statistics need the single-CTA kernel with one N-tile and no LoRA k-blocks");
+    return 1;
   }
   if (epi.mode == EPI_ROWDOT && (!p->two_cta || !epi.rowdot || epi.rowdot_rows <= 0)) {
     set_error("gemm_plan_init: EPI_ROWDOT needs the pair kernel (N %% 256 == 0, VITATK_GEMM_2CTA != 0) and a side buffer");

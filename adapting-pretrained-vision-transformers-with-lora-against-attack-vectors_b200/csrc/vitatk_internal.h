@@ -92,6 +92,11 @@ struct GemmEpilogue {
   // LoRA included); the beta / bias part arrives through `bias`.  row_stats = (mean, rstd) per row, null = off.
   const float2* row_stats;
   const float* c1;
+  // Single-CTA kernel with one N-tile (the skinny x*A^T GEMMs): while the rows of A stream through shared memory, four
+  // otherwise idle epilogue warps also compute the LayerNorm statistics (mean, rstd) of every A row over the full K
+  // and write them here -- the folded LayerNorm then needs no separate pass over h at all.  null = off.
+  float2* stats_out;
+  float stats_eps;
   float* rowdot;        // EPI_ROWDOT side output, [(M / rowdot_rows) * (N / 64), rowdot_pad] fp32
   int rowdot_rows;      // rows per group (tokens per image)
   int rowdot_pad;       // row pitch of the side output (208)

@@ -147,8 +147,8 @@ int vitatk_k_gemm(int M, int N, int K, const void* A_dev, int lda, const void* B
                   int ldo, void* out2_dev, int ldo2, const void* T_dev, int ldt, const void* LB_dev, int ldlb,
                   int lora_nkb, int lora_ksteps, int lora_group_cols, int epi_mode, const float* bias_dev,
                   const void* res_dev, int ld_res, const float* table_dev, int table_rows, float* rowdot_dev,
-                  int rowdot_rows, int rowdot_pad, const float* row_stats_dev, const float* c1_dev, int use_simt,
-                  void* stream);
+                  int rowdot_rows, int rowdot_pad, const float* row_stats_dev, const float* c1_dev, float* stats_out_dev,
+                  float stats_eps, int use_simt, void* stream);
 int vitatk_k_attention_fwd(const void* qkv_dev, void* out_dev, int batch, int tokens, int heads, void* stream);
 /* tcgen05 forward (the engine's path); lse2_dev (optional) receives [batch*heads, 208] log2-domain logsumexp */
 int vitatk_k_attention_fwd_tc05(const void* qkv_dev, void* out_dev, float* lse2_dev, int batch, int tokens, int heads,

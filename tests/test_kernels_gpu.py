@@ -27,7 +27,7 @@ def _dgelu(u):
 
 
 def run_gemm(lib, A, B, epi=EPI_PLAIN, bias=None, res=None, table=None, T=None, LB=None, nkb=0, ksteps=0,
-             group_cols=0, simt=False, rowdot=None, rowdot_rows=0, row_stats=None, c1=None):
+             group_cols=0, simt=False, rowdot=None, rowdot_rows=0, row_stats=None, c1=None, stats_out=None):
     from vitatk import _lib
 
     M, K = A.shape
@@ -38,7 +38,8 @@ def run_gemm(lib, A, B, epi=EPI_PLAIN, bias=None, res=None, table=None, T=None, 
                            0 if T is None else T.stride(0), _p(LB), 0 if LB is None else LB.stride(0), nkb, ksteps,
                            group_cols, epi, _p(bias), _p(res), 0 if res is None else res.stride(0), _p(table),
                            0 if table is None else table.shape[0], _p(rowdot), rowdot_rows,
-                           0 if rowdot is None else rowdot.shape[1], _p(row_stats), _p(c1), 1 if simt else 0, _s())
+                           0 if rowdot is None else rowdot.shape[1], _p(row_stats), _p(c1), _p(stats_out), 1e-12,
+                           1 if simt else 0, _s())
     _lib.check(rc, "vitatk_k_gemm")
     torch.cuda.synchronize()
     return out, out2
@@ -197,6 +198,23 @@ def test_gemm_layernorm_fold(lib, M, N, epi):
     if M <= 2000:
         s_out, _ = run_gemm(lib, h, Wf, epi, c2.contiguous(), row_stats=stats, c1=c1.contiguous(), simt=True)
         check_close(s_out, _gelu(ref) if epi == EPI_GELU_DUAL else ref, "ln-fold simt")
+
+
+@pytest.mark.parametrize("M,N", [(197, 64), (1576, 192), (50432, 64), (50432, 192)])
+def test_skinny_gemm_also_emits_layernorm_stats(lib, M, N):
+    """The x*A^T GEMM computes (mean, rstd) of every A row on the side (folded LayerNorm needs no pass of its own)."""
+    K = 768
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    rn = lambda *s: torch.randn(*s, device="cuda", generator=g)  # noqa: E731
+    A = (rn(M, K) * 2 + 3.0 * rn(M, 1)).to(torch.bfloat16)  # rows with |mean| up to several std
+    B = (rn(N, K) / math.sqrt(K)).to(torch.bfloat16)
+    stats = torch.full((M, 2), float("nan"), device="cuda")
+    out, _ = run_gemm(lib, A, B, stats_out=stats)
+    want, _ = ref_gemm(A, B, EPI_PLAIN, None, None, None, None, None, 0, 0, 0)
+    check_close(out, want, "skinny gemm with stats")
+    af = A.float()
+    torch.testing.assert_close(stats[:, 0], af.mean(-1), rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(stats[:, 1], torch.rsqrt(af.var(-1, unbiased=False) + 1e-12), rtol=2e-4, atol=1e-5)
 
 
 def test_gemm_rejects_bad_shapes(lib):

@@ -221,19 +221,44 @@ def run_engine(args):
     launches = eng.launch_count - l0
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- end to end through the public API: pinned host -> device, attack, adversarial images -> host ----
-    def e2e_step(i):
-        xd = x_host.to(dev, non_blocking=True)
-        yd = y_host.to(dev, non_blocking=True)
-        a = eng.attack(xd, yd, EPS, ALPHA, PGD_STEPS, start="rng", seed=1234 + i, image_index0=idx0, out=adv)
-        adv_host.copy_(a, non_blocking=True)
+    # ---- end to end through the public API: EVERY step uploads its batch from pinned host memory and reads its
+    # adversarial batch back; as a user of the drop-in would, the copies run on their own streams so that the upload of
+    # batch i+1 and the download of batch i-1 overlap the attack on batch i (double-buffered device tensors) ----
+    comp = torch.cuda.current_stream(dev)
+    s_h2d, s_d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    xd = [torch.empty_like(x) for _ in range(2)]
+    yd = [torch.empty_like(y) for _ in range(2)]
+    advd = [torch.empty_like(x) for _ in range(2)]
+    adv_hosts = [adv_host, torch.empty_like(x_host).pin_memory()]
+    ev_up = [torch.cuda.Event() for _ in range(2)]
+    ev_done = [torch.cuda.Event() for _ in range(2)]
+    ev_down = [torch.cuda.Event() for _ in range(2)]
 
-    e2e_step(0)
+    def e2e_run(n):
+        for i in range(n):
+            b = i & 1
+            with torch.cuda.stream(s_h2d):
+                if i >= 2:
+                    s_h2d.wait_event(ev_done[b])  # the attack that read xd[b] two steps ago has finished
+                xd[b].copy_(x_host, non_blocking=True)
+                yd[b].copy_(y_host, non_blocking=True)
+                ev_up[b].record(s_h2d)
+            comp.wait_event(ev_up[b])
+            if i >= 2:
+                comp.wait_event(ev_down[b])  # advd[b] of two steps ago has been read back
+            eng.attack(xd[b], yd[b], EPS, ALPHA, PGD_STEPS, start="rng", seed=1234 + i, image_index0=idx0, out=advd[b])
+            ev_done[b].record(comp)
+            with torch.cuda.stream(s_d2h):
+                s_d2h.wait_event(ev_done[b])
+                adv_hosts[b].copy_(advd[b], non_blocking=True)
+                ev_down[b].record(s_d2h)
+        comp.wait_stream(s_d2h)
+
+    e2e_run(2)
     sync_all()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    for i in range(args.steps):
-        e2e_step(i)
+    e2e_run(args.steps)
     f1.record()
     sync_all()
     ms_e2e = f0.elapsed_time(f1)

@@ -54,6 +54,14 @@ def ncu_traffic_per_launch(kernel_prefix="gemm_tc05_kernel<256"):
     return None, None
 
 
+def workload_config(world, batch):
+    """The `config` object of the JSON line (identical for this repo's arm and the reference arm)."""
+    return {"workload": "PGD-10 eps=8/255 alpha=2/255 random-start on LoRA(r=8; q,k,v,proj,fc1,fc2) ViT-B/16, "
+                        "21 classes, batch 256 per GPU, 224x224 (BASELINE configs[1])",
+            "global_batch": batch * world, "parallelism": f"dp{world} (independent images, no data-path collective)",
+            "l2": "inputs larger than L2 (154 MB images, ~11 GB activations per step)"}
+
+
 def measured_peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
@@ -153,8 +161,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "PGD-10 eps=8/255 alpha=2/255 random-start, LoRA(r=8; q,k,v,proj,fc1,fc2) ViT-B/16, "
-                               "21 classes, 224x224; reference arm = bounded CPU sample", "sample_batch": sample},
+        "config": dict(workload_config(max(args.gpus, 1), args.batch), reference_sample_batch=sample),
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -303,10 +310,7 @@ def run_engine(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "PGD-10 eps=8/255 alpha=2/255 random-start on LoRA(r=8; q,k,v,proj,fc1,fc2) ViT-B/16, "
-                               "21 classes, batch 256 per GPU, 224x224 (BASELINE configs[1])",
-                   "global_batch": batch * world, "parallelism": f"dp{world} (independent images, no data-path collective)",
-                   "l2": "inputs larger than L2 (154 MB images, ~11 GB activations per step)"},
+        "config": workload_config(world, batch),
         "clocks": clocks,
         "e2e": {"value": imgs / (ms_e2e / 1e3), "unit": UNIT,
                 "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8, "d2h_bytes_per_step": adv_host.numel() * 4},

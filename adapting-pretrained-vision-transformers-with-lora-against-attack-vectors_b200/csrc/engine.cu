@@ -105,6 +105,7 @@ struct vitatk_engine {
   PixelNorm nrm;
   // optional per-launch CUDA-event timing (bench.py's roofline leg; off in the timed region)
   bool attn_bwd_two_kernel = false;  // VITATK_ATTN_BWD=2k selects the older dQ + dK/dV kernel pair
+  bool zigzag = true;                // skinny LoRA GEMMs walk M last-to-first (VITATK_ZIGZAG=0: first-to-last)
   bool fuse_stats = true;            // folded LayerNorm: (mean, rstd) come out of the skinny LoRA GEMM (VITATK_FUSE_STATS=0: stats kernel)
   bool fuse_ln_t = false;            // LayerNorm kernels also produce the LoRA x*A^T of the site they feed
   bool fuse_delta = false;           // delta comes out of the proj-backward GEMM epilogue (pair kernel) instead of a kernel
@@ -272,6 +273,13 @@ static int build_plans(vitatk_engine* e, int batch, PlanSet** out) {
   if (gemm_plan_init(&ps->bpatch, M, D, D, e->dh_a, D, e->patch_wt, D, e->dxn, D, nullptr, 0, nullptr, 0, nullptr, 0, 0,
                      0, 0, plain))
     return 1;
+  if (e->zigzag) {
+    // the skinny x*A^T GEMMs read what the previous kernel has just written front to back: walk it back to front so the
+    // tail that is still in L2 is consumed first (the main GEMM that follows reads front to back again)
+    for (auto& p : ps->layers)
+      for (GemmPlan* g : {&p.t_qkv, &p.t_proj, &p.t_fc1, &p.t_fc2, &p.bt_fc2, &p.bt_fc1, &p.bt_proj, &p.bt_qkv})
+        g->reverse_m = 1;
+  }
   e->plans[batch] = ps;
   *out = ps;
   return 0;
@@ -447,6 +455,8 @@ int vitatk_create(const vitatk_config* cfg, vitatk_engine** out) {
     e->attn_bwd_two_kernel = v && strcmp(v, "2k") == 0;
     const char* g2 = getenv("VITATK_GEMM_2CTA");
     const char* fd = getenv("VITATK_FUSE_DELTA");
+    const char* zz = getenv("VITATK_ZIGZAG");
+    e->zigzag = !(zz && zz[0] == '0');
     const char* fs = getenv("VITATK_FUSE_STATS");
     e->fuse_stats = !(fs && fs[0] == '0');
     const char* flt = getenv("VITATK_FUSE_LN_T");

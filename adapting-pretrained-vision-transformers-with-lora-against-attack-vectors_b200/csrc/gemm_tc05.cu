@@ -58,6 +58,8 @@ struct GemmKernelArgs {
   int M, N, K;
   int lora_nkb, lora_ksteps, lora_group_cols;
   GemmEpilogue epi;
+  int reverse_m;  // 1: walk the M-blocks from the last to the first (the input was just written in ascending order by the
+                  // previous kernel, so its tail is still in L2)
   int gelu_f32;  // 1: fp32 Abramowitz-Stegun GELU in the epilogue (VITATK_GELU=f32), 0: packed-half path
   int dbg;  // timing experiments (DBG instantiation only, VITATK_GEMM_DBG): 1 no aux loads, 2 no stores,
             // 4 no TMA loads after the first ring fill, 8 no MMA issue, 16 epilogue skips TMEM reads and math
@@ -189,6 +191,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int num_tiles = tiles_m * tiles_n;
   const int main_kb = args.K / BK;
   const int num_kb = main_kb + args.lora_nkb;
+  auto mblock = [&](int tile_) { return args.reverse_m ? tiles_m - 1 - tile_ / tiles_n : tile_ / tiles_n; };
 
   if (warp == MMA_WARP && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -235,7 +238,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t leader = ptx::elect_leader();
     uint32_t cnt = 0;
     for (int tile = unit; tile < num_tiles; tile += num_units) {
-      const int m0 = (tile / tiles_n) * TILE_M + static_cast<int>(rank) * BM;        // this CTA's 128 rows of A
+      const int m0 = mblock(tile) * TILE_M + static_cast<int>(rank) * BM;              // this CTA's 128 rows of A
       const int n0 = (tile % tiles_n) * BN;
       const int nb0 = n0 + static_cast<int>(rank) * Cfg::B_ROWS;                     // pair: this CTA's half of B
       const int tcol0 = args.lora_group_cols > 0 ? (n0 / args.lora_group_cols) * BK : 0;
@@ -355,7 +358,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
     };
     auto issue_aux = [&](uint32_t cc, int tile_, int sl_) {  // issuer thread only
-      const int am0 = (tile_ / tiles_n) * TILE_M + static_cast<int>(rank) * BM;
+      const int am0 = mblock(tile_) * TILE_M + static_cast<int>(rank) * BM;
       const int acol = (tile_ % tiles_n) * BN + g * 128 + sl_ * 64;
       const uint32_t b = cc & 1;
       ptx::mbar_arrive_expect_tx(&aux_full[b], SLAB_BYTES);
@@ -387,7 +390,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     };
     if (has_aux && issuer && unit < num_tiles) issue_aux(0, unit, 0);
     for (int tile = unit; tile < num_tiles; tile += num_units, ++it) {
-      const int m0 = (tile / tiles_n) * TILE_M + static_cast<int>(rank) * BM;
+      const int m0 = mblock(tile) * TILE_M + static_cast<int>(rank) * BM;
       const int n0 = (tile % tiles_n) * BN;
       const uint32_t buf = it & 1;
       const uint32_t use = it >> 1;
@@ -562,7 +565,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // prefetch the aux (residual / multiplier) rows of the first chunk before the accumulator is ready
     const uint32_t tmem_empty_remote = TWO ? ptx::mapa_shared(ptx::smem_u32(&tmem_empty[0]), 0) : 0u;  // leader's barrier
     if (has_aux && unit < num_tiles) {
-      const int m0 = (unit / tiles_n) * TILE_M + static_cast<int>(rank) * BM, n0 = (unit % tiles_n) * BN;
+      const int m0 = mblock(unit) * TILE_M + static_cast<int>(rank) * BM, n0 = (unit % tiles_n) * BN;
       const int row = m0 + q * 32 + lane;
       if (row < args.M) {
         const uint4* rp = reinterpret_cast<const uint4*>(epi.res + static_cast<size_t>(row) * epi.ld_res + n0 +
@@ -573,7 +576,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     uint32_t scnt = 0;  // k-block counter of the row-statistics warps (same sequence as the producer's)
     for (int tile = unit; tile < num_tiles; tile += num_units, ++it) {
-      const int m0 = (tile / tiles_n) * TILE_M + static_cast<int>(rank) * BM;
+      const int m0 = mblock(tile) * TILE_M + static_cast<int>(rank) * BM;
       const int n0 = (tile % tiles_n) * BN;
       const uint32_t buf = it & 1;
       const uint32_t use = it >> 1;
@@ -633,7 +636,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (i + 1 == CPW) {
             const int nt = tile + num_units;
             ok = nt < num_tiles;
-            nrow = (nt / tiles_n) * TILE_M + static_cast<int>(rank) * BM + q * 32 + lane;
+            nrow = mblock(nt) * TILE_M + static_cast<int>(rank) * BM + q * 32 + lane;
             ncol_next = (nt % tiles_n) * BN + hsel * CPW * CHUNK;
             ok = ok && nrow < args.M;
           }
@@ -872,6 +875,7 @@ int gemm_plan_init(GemmPlan* p, int M, int N, int K, const bf16* A, int lda, con
   p->lora_ksteps = lora_ksteps;
   p->lora_group_cols = lora_group_cols;
   p->epi = epi;
+  p->reverse_m = 0;
   if (lora_group_cols > 0 && lora_group_cols % p->BN != 0) {
     set_error("gemm_plan_init: lora_group_cols %d not a multiple of BN %d", lora_group_cols, p->BN);
     return 1;
@@ -956,6 +960,7 @@ static int launch_bn(const GemmPlan* p, cudaStream_t stream, int num_sms) {
   a.epi = p->epi;
   a.dbg = gemm_dbg_flags();
   a.gelu_f32 = gemm_gelu_f32();
+  a.reverse_m = p->reverse_m;
   const dim3 grid(TWO ? 2 * units : units, 1, 1), block(GEMM_THREADS, 1, 1);
   if (a.dbg)
     VITATK_CUDA_OK(launch_pdl(gemm_tc05_kernel<BN, true, TWO>, grid, block, Cfg::SMEM_BYTES, stream, TWO ? 2 : 1, p->tmA,
@@ -988,6 +993,7 @@ int gemm_launch_simt(const GemmPlan* p, const bf16* A, int lda, const bf16* B, i
   a.lora_group_cols = p->lora_group_cols;
   a.epi = p->epi;
   a.dbg = 0;
+  a.reverse_m = 0;
   a.gelu_f32 = 1;
   dim3 grid((p->N + 127) / 128, p->M);
   gemm_simt_kernel<<<grid, 128, 0, stream>>>(a, A, lda, B, ldb, out, ldo, out2, ldo2, T, ldt, LB, ldlb);

@@ -106,6 +106,7 @@ struct GemmPlan {
   // shapes
   int M, N, K;
   int BN;               // 64, 128, 192 or 256
+  int reverse_m;        // 1: M-blocks are processed last-to-first (set by the engine on the skinny LoRA GEMMs)
   int two_cta;          // 1: CTA-pair kernel (cta_group::2, 256-row tiles, half of B per CTA); BN = 256 only
   int lora_nkb;         // extra 64-wide k-blocks (0 = no adapter)
   int lora_ksteps;      // UMMA k-steps (16 each) issued per extra k-block = ceil(r/16)

@@ -88,6 +88,28 @@ def normalise_state_dict(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]
     return out
 
 
+def fold_layernorm_into_linear(W: torch.Tensor, b: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
+                               adapters: Sequence[Adapter] = (), round_to=None):
+    """Host-side algebra of the folded LayerNorm, for ONE Linear fed by LN(gamma, beta):
+
+        LN(h) W^T + sum_a s_a B_a (A_a LN(h)) + b  ==  rstd * (h Wf^T + sum_a (h Af_a^T) (s_a B_a)^T - mean * c1) + c2
+
+    Returns (Wf = gamma o W, [Af_a = gamma o A_a], c1, c2).  ``round_to`` (e.g. torch.bfloat16) makes c1 the row sums of
+    the ROUNDED operands the tensor cores will see, which is what cancels exactly against the accumulator.  Pure tensor
+    math (CPU or GPU); ``Engine._upload`` applies the same formulas on the packed buffers."""
+    rd = (lambda t: t.to(round_to).to(t.dtype)) if round_to is not None else (lambda t: t)
+    Wf = W * gamma[None, :]
+    c1 = rd(Wf).sum(1)
+    c2 = b + W @ beta
+    Afs = []
+    for (A, B, s) in adapters:
+        Af = A * gamma[None, :]
+        Afs.append(Af)
+        c1 = c1 + rd(s * B) @ rd(Af).sum(1)
+        c2 = c2 + s * (B @ (A @ beta))
+    return Wf, Afs, c1, c2
+
+
 class Engine:
     """One engine per (model, device).  Mirrors what ``model.to(device).eval()`` is to the reference loop."""
 

@@ -123,3 +123,30 @@ def test_count_allreduce_world2_gloo():
     want = [51, 34, 101]
     for _, c in res:
         assert c == want
+
+
+def test_layernorm_fold_algebra():
+    """CPU: the folded-LayerNorm packing (gamma o W, gamma o A, c1, c2) reproduces LN -> Linear (+ LoRA) exactly."""
+    import torch
+
+    from vitatk.engine import fold_layernorm_into_linear
+
+    g = torch.Generator().manual_seed(0)
+    rn = lambda *s: torch.randn(*s, generator=g, dtype=torch.float64)  # noqa: E731
+    M, K, N, r = 37, 96, 40, 8
+    h = rn(M, K) * 2 + 3 * rn(M, 1)  # rows with |mean| well above the spread
+    gamma, beta = 1 + 0.2 * rn(K), 0.3 * rn(K)
+    W, b = rn(N, K) / K ** 0.5, rn(N) * 0.1
+    ads = [(rn(r, K) / K ** 0.5, rn(N, r) * 0.05, 2.0), (rn(4, K) / K ** 0.5, rn(N, 4) * 0.05, 0.5)]
+    xn = torch.nn.functional.layer_norm(h, (K,), gamma, beta, eps=1e-12)
+    want = xn @ W.t() + b + sum(s * (xn @ A.t()) @ B.t() for (A, B, s) in ads)
+    Wf, Afs, c1, c2 = fold_layernorm_into_linear(W, b, gamma, beta, ads)
+    mean = h.mean(-1, keepdim=True)
+    rstd = torch.rsqrt(h.var(-1, unbiased=False, keepdim=True) + 1e-12)
+    acc = h @ Wf.t() + sum((h @ Af.t()) @ (s * B).t() for Af, (A, B, s) in zip(Afs, ads))
+    got = rstd * (acc - mean * c1[None, :]) + c2[None, :]
+    torch.testing.assert_close(got, want, rtol=1e-9, atol=1e-9)
+    # with bf16-rounded operands, c1 must be the row sums of the ROUNDED operands (that is what cancels the mean term)
+    Wb = Wf.float().to(torch.bfloat16).double()
+    _, _, c1b, _ = fold_layernorm_into_linear(W.float(), b.float(), gamma.float(), beta.float(), [], round_to=torch.bfloat16)
+    torch.testing.assert_close(c1b.double(), Wb.sum(1), rtol=1e-5, atol=1e-5)

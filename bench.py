@@ -173,7 +173,24 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------------
 # this repo's arm
 # ---------------------------------------------------------------------------------------------------------
+class StdoutToStderr:
+    """Route everything written to fd 1 (NCCL prints its version banner there) to stderr, so that stdout carries exactly
+    one line: the JSON result printed through `emit`."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        print(text, flush=True)
+        os.dup2(2, 1)
+
+
 def run_engine(args):
+    out = StdoutToStderr()
     import torch
     import torch.distributed as dist
 
@@ -333,7 +350,7 @@ def run_engine(args):
     if world == 1 and not args.no_cpu_baseline:
         base, _ = cpu_reference_run(steps=1, warmup=0, sample_batch=4)
         line["cpu_baseline"] = base
-    print(json.dumps(line), flush=True)
+    out.emit(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -73,7 +73,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 # symbols include/vitatk.h declares; tests check the .so exports every one of them
 EXPORTS = [
     "vitatk_last_error", "vitatk_version", "vitatk_create", "vitatk_destroy", "vitatk_set_tensor", "vitatk_set_lora",
-    "vitatk_set_normalization", "vitatk_finalize", "vitatk_workspace_bytes", "vitatk_forward", "vitatk_input_grad",
+    "vitatk_set_normalization", "vitatk_finalize", "vitatk_workspace_bytes", "vitatk_forward", "vitatk_input_grad", "vitatk_vjp", "vitatk_png_roundtrip",
     "vitatk_attack", "vitatk_count_correct", "vitatk_launch_count", "vitatk_k_gemm", "vitatk_k_attention_fwd",
     "vitatk_k_attention_bwd", "vitatk_k_layernorm_fwd", "vitatk_k_layernorm_bwd", "vitatk_k_pgd_update",
     "vitatk_k_pgd_init", "vitatk_profile_begin", "vitatk_profile_end", "vitatk_k_attention_fwd_tc05",
@@ -118,6 +118,8 @@ def load() -> C.CDLL:
     lib.vitatk_launch_count.restype = ll
     lib.vitatk_forward.argtypes = [vp, vp, i, vp, vp]
     lib.vitatk_input_grad.argtypes = [vp, vp, vp, i, vp, vp, vp, vp]
+    lib.vitatk_vjp.argtypes = [vp, vp, vp, i, vp, vp, vp]
+    lib.vitatk_png_roundtrip.argtypes = [vp, i, vp, vp, vp]
     lib.vitatk_attack.argtypes = [vp, vp, vp, i, f, f, i, i, vp, u64, u64, vp, vp]
     lib.vitatk_count_correct.argtypes = [vp, vp, vp, i, vp, vp]
     lib.vitatk_profile_begin.argtypes = [vp]

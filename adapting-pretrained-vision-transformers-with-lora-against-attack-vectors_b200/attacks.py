@@ -98,6 +98,48 @@ def compile_model(model: torch.nn.Module, max_batch: int = 256, device=None, for
     return eng
 
 
+class _EngineLogits(torch.autograd.Function):
+    """logits = engine(images) with d/d images supplied by the engine's backward kernels (``vitatk_vjp``)."""
+
+    @staticmethod
+    def forward(ctx, images, eng):
+        ctx.eng = eng
+        ctx.save_for_backward(images)
+        return eng.logits(images).to(images.device)
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        (images,) = ctx.saved_tensors
+        grad, _ = ctx.eng.vjp(images, dlogits)
+        return grad.to(images.device), None
+
+
+class EngineModule(torch.nn.Module):
+    """``nn.Module`` face of an engine, differentiable with respect to its input: what ART's
+    ``PyTorchClassifier(model=NormalizedModel(LogitsModel(model), mean, std), ...)`` (patch_attack.py:50-57) or
+    ``SignConstrainedModel`` (rp2_attack.py:25-30) need in order to run their patch / EOT optimisation on the engine:
+
+        classifier = PyTorchClassifier(model=EngineModule(normalized_model), clip_values=(0, 1), loss=CE, ...)
+
+    ``forward(x)`` takes [0,1] images (normalisation read from a wrapped ``NormalizedModel`` or given here) and returns
+    logits; ``backward`` runs the engine's forward + input-gradient kernels for whatever cotangent autograd supplies, so
+    any loss on the logits works (targeted / untargeted CE, ART's sign-constrained variants).  Parameters receive no
+    gradient (weights are frozen on the attack path)."""
+
+    def __init__(self, model, mean=None, std=None, max_batch: int = 256):
+        super().__init__()
+        self._wrapped = [model]  # not registered: the engine owns packed copies of the weights
+        self._max_batch = max_batch
+        _, m, s = _unwrap(model)
+        self._mean = _as_list(mean, (0.0, 0.0, 0.0)) if mean is not None else (m if m is not None else [0.0] * 3)
+        self._std = _as_list(std, (1.0, 1.0, 1.0)) if std is not None else (s if s is not None else [1.0] * 3)
+
+    def forward(self, x):
+        eng = compile_model(self._wrapped[0], max_batch=max(self._max_batch, int(x.shape[0])))
+        eng.set_normalization(self._mean, self._std)
+        return _EngineLogits.apply(x, eng)
+
+
 def _as_list(t, default):
     if t is None:
         return list(default)

@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(256) head_kernel(const bf16* __restrict__ h, c
                                                    const float* __restrict__ bc, const int64_t* __restrict__ labels,
                                                    float* __restrict__ logits, float* __restrict__ loss,
                                                    bf16* __restrict__ dh, int tokens, int dim, int classes, float eps,
-                                                   float grad_scale) {
+                                                   float grad_scale, const float* __restrict__ dlogits) {
   pdl_wait();
   pdl_launch_dependents();
   extern __shared__ float hs[];
@@ -505,13 +505,14 @@ __global__ void __launch_bounds__(256) head_kernel(const bf16* __restrict__ h, c
   for (int c = tid + blockDim.x; c < classes; c += blockDim.x) logits[static_cast<size_t>(b) * classes + c] = lg[c];
   if (tid == 0 && loss && y >= 0) loss[b] = lse - lg[y];
   if (dh == nullptr) return;
-  // dlogits = (softmax - onehot) * grad_scale ; dy = Wc^T dlogits
+  // dlogits = (softmax - onehot) * grad_scale, or the caller's cotangent (vector-Jacobian product); dy = Wc^T dlogits
+  __syncthreads();
+  for (int c = tid; c < classes; c += blockDim.x)
+    lg[c] = dlogits ? dlogits[static_cast<size_t>(b) * classes + c] : expf(lg[c] - lse) - (c == y ? 1.f : 0.f);
+  __syncthreads();
   for (int k = tid; k < dim; k += blockDim.x) {
     float acc = 0.f;
-    for (int c = 0; c < classes; ++c) {
-      const float p = expf(lg[c] - lse) - (c == y ? 1.f : 0.f);
-      acc += p * __ldg(Wc + static_cast<size_t>(c) * dim + k);
-    }
+    for (int c = 0; c < classes; ++c) acc += lg[c] * __ldg(Wc + static_cast<size_t>(c) * dim + k);
     dyv[k] = acc * grad_scale;
   }
   __syncthreads();
@@ -534,14 +535,14 @@ __global__ void __launch_bounds__(256) head_kernel(const bf16* __restrict__ h, c
 
 int head_fwd_bwd(const bf16* h, const float* gamma, const float* beta, const float* Wc, const float* bc,
                  const int64_t* labels, float* logits, float* loss, bf16* dh, int batch, int tokens, int dim,
-                 int classes, float eps, float grad_scale, cudaStream_t stream) {
+                 int classes, float eps, float grad_scale, cudaStream_t stream, const float* dlogits) {
   if (dim % 8 != 0 || classes > 4096) {
     set_error("head_fwd_bwd: dim=%d classes=%d unsupported", dim, classes);
     return 1;
   }
   const size_t smem = (3 * dim + classes) * sizeof(float);
   VITATK_CUDA_OK(launch_pdl(head_kernel, dim3(batch), dim3(256), smem, stream, 1, h, gamma, beta, Wc, bc, labels, logits,
-                            loss, dh, tokens, dim, classes, eps, grad_scale));
+                            loss, dh, tokens, dim, classes, eps, grad_scale, dlogits));
   return 0;
 }
 
@@ -716,6 +717,53 @@ int pgd_update(const bf16* dcols, const float* x0, float* adv, bf16* cols, int b
                             batch, nrm, eps, alpha));
   return 0;
 }
+// Utils.py:106-113 save_images (clamp to [0,1], *255, truncate to uint8) followed by what re-loading the PNG with ToTensor
+// gives back (/255): the pixel values the reference's evaluation scripts actually see (train_loras.py:56-76 reads the
+// saved files).  HBM-bound: 4 B read + 4 B write (+ 1 B for the optional uint8 HWC copy) per pixel-channel.
+__global__ void __launch_bounds__(256) png_roundtrip_kernel(const float4* __restrict__ in, float4* __restrict__ out,
+                                                            size_t n4) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float4 v = __ldg(in + i);
+    float4 o;
+    o.x = __fdiv_rn(static_cast<float>(__float2uint_rz(__fmul_rn(fminf(fmaxf(v.x, 0.f), 1.f), 255.f))), 255.f);
+    o.y = __fdiv_rn(static_cast<float>(__float2uint_rz(__fmul_rn(fminf(fmaxf(v.y, 0.f), 1.f), 255.f))), 255.f);
+    o.z = __fdiv_rn(static_cast<float>(__float2uint_rz(__fmul_rn(fminf(fmaxf(v.z, 0.f), 1.f), 255.f))), 255.f);
+    o.w = __fdiv_rn(static_cast<float>(__float2uint_rz(__fmul_rn(fminf(fmaxf(v.w, 0.f), 1.f), 255.f))), 255.f);
+    out[i] = o;
+  }
+}
+
+// uint8 HWC image the reference hands to PIL (Utils.py:111-113): [B,224,224,3] from NCHW fp32
+__global__ void __launch_bounds__(256) to_uint8_hwc_kernel(const float* __restrict__ in, uint8_t* __restrict__ out,
+                                                           int batch) {
+  const size_t total = static_cast<size_t>(batch) * 224 * 224;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t b = i / (224 * 224), px = i % (224 * 224);
+    const float* src = in + b * 3 * 224 * 224 + px;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = fminf(fmaxf(__ldg(src + c * 224 * 224), 0.f), 1.f);
+      out[i * 3 + c] = static_cast<uint8_t>(__float2uint_rz(__fmul_rn(v, 255.f)));
+    }
+  }
+}
+
+int png_roundtrip(const float* images, float* out, uint8_t* u8_hwc, int batch, cudaStream_t stream) {
+  const size_t n = static_cast<size_t>(batch) * 3 * 224 * 224;
+  if (out) {
+    png_roundtrip_kernel<<<pixel_grid(batch), 256, 0, stream>>>(reinterpret_cast<const float4*>(images),
+                                                                reinterpret_cast<float4*>(out), n / 4);
+    VITATK_CUDA_OK(cudaGetLastError());
+  }
+  if (u8_hwc) {
+    to_uint8_hwc_kernel<<<pixel_grid(batch), 256, 0, stream>>>(images, u8_hwc, batch);
+    VITATK_CUDA_OK(cudaGetLastError());
+  }
+  return 0;
+}
+
 int grad_to_image(const bf16* dcols, float* grad, int batch, PixelNorm nrm, float scale, cudaStream_t stream) {
   grad_to_image_kernel<<<pixel_grid(batch), 256, 0, stream>>>(dcols, grad, batch, nrm, scale);
   VITATK_CUDA_OK(cudaGetLastError());

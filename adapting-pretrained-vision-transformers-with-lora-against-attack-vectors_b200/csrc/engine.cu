@@ -727,6 +727,26 @@ int vitatk_input_grad(vitatk_engine* e, const float* images, const int64_t* labe
   return 0;
 }
 
+int vitatk_vjp(vitatk_engine* e, const float* images, const float* dlogits, int batch, float* grad_out, float* logits_out,
+               void* stream) {
+  if (check_batch(e, batch)) return 1;
+  if (!images || !dlogits || !grad_out) {
+    set_error("vitatk_vjp: images, dlogits and grad must be non-null");
+    return 1;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  PlanSet* ps = nullptr;
+  if (build_plans(e, batch, &ps)) return 1;
+  const vitatk_config& c = e->cfg;
+  RUNC(CAT_PIXEL, 0, pgd_init(images, nullptr, e->scratch_img, e->cols, batch, e->nrm, 0.f, 0, 0, 0, s));
+  if (encoder_forward(e, ps, batch, s)) return 1;
+  RUNC(CAT_HEAD, 0, head_fwd_bwd(e->h[c.layers], e->lnf_g, e->lnf_b, e->head_w, e->head_b, nullptr, logits_out ? logits_out : e->logits,
+                   nullptr, e->dh_a, batch, TOKENS, c.dim, c.num_classes, c.ln_eps, 1.0f, s, dlogits));
+  if (encoder_backward(e, ps, batch, s)) return 1;
+  RUNC(CAT_PIXEL, 0, grad_to_image(e->dxn, grad_out, batch, e->nrm, 1.0f, s));
+  return 0;
+}
+
 int vitatk_attack(vitatk_engine* e, const float* images, const int64_t* labels, int batch, float eps, float alpha,
                   int steps, int start, const float* noise, uint64_t seed, uint64_t image_index0, float* adv,
                   void* stream) {
@@ -761,6 +781,14 @@ int vitatk_count_correct(vitatk_engine* e, const float* images, const int64_t* l
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   RUNC(CAT_HEAD, 0, count_correct(e->logits, labels, batch, e->cfg.num_classes, counts, s));
   return 0;
+}
+
+int vitatk_png_roundtrip(const float* images, int batch, float* out, unsigned char* u8_hwc, void* stream) {
+  if (!images || batch < 1 || (!out && !u8_hwc)) {
+    set_error("vitatk_png_roundtrip: need images, batch >= 1 and at least one output");
+    return 1;
+  }
+  return png_roundtrip(images, out, u8_hwc, batch, static_cast<cudaStream_t>(stream));
 }
 
 // ------------------------------- kernel-level entry points -------------------------------

@@ -181,10 +181,11 @@ int layernorm_fwd_t(const bf16* x, const float* gamma, const float* beta, bf16* 
 int layernorm_bwd_t(const bf16* dy, const bf16* x, const float2* stats, const float* gamma, const bf16* dres, bf16* dx_out,
                     int rows, int cols, const bf16* lora, int groups, int rank, bf16* T, int ldt, cudaStream_t stream);
 // final LN on CLS rows + classifier + softmax-CE; writes logits, per-image loss, and (optionally) the
-// gradient wrt the final hidden state (non-CLS rows zero-filled).
+// gradient wrt the final hidden state (non-CLS rows zero-filled).  dlogits == nullptr: the cotangent is
+// softmax - onehot (cross-entropy); otherwise the caller's [batch, classes] fp32 cotangent (vector-Jacobian product).
 int head_fwd_bwd(const bf16* h, const float* gamma, const float* beta, const float* Wc, const float* bc,
                  const int64_t* labels, float* logits, float* loss, bf16* dh, int batch, int tokens, int dim,
-                 int classes, float eps, float grad_scale, cudaStream_t stream);
+                 int classes, float eps, float grad_scale, cudaStream_t stream, const float* dlogits = nullptr);
 
 struct PixelNorm {
   float mean[3];
@@ -199,6 +200,8 @@ int pgd_update(const bf16* dcols, const float* x0, float* adv, bf16* cols, int b
                float eps, float alpha, cudaStream_t stream);
 // materialise dL/dx (fp32 NCHW) from the im2col-layout gradient
 int grad_to_image(const bf16* dcols, float* grad, int batch, PixelNorm nrm, float scale, cudaStream_t stream);
+// save_images + reload (Utils.py:106-113): out fp32 NCHW = trunc(clamp(x)*255)/255 and / or the uint8 HWC image itself
+int png_roundtrip(const float* images, float* out, uint8_t* u8_hwc, int batch, cudaStream_t stream);
 // counts[0] += #(argmax(logits)==label), counts[1] += batch
 int count_correct(const float* logits, const int64_t* labels, int batch, int classes, long long* counts,
                   cudaStream_t stream);

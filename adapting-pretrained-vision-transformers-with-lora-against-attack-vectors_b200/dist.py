@@ -31,14 +31,19 @@ def allreduce_counts(counts: torch.Tensor) -> torch.Tensor:
     return counts
 
 
-def robust_accuracy_counts(engine, attack_fn, images: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+def robust_accuracy_counts(engine, attack_fn, images: torch.Tensor, labels: torch.Tensor,
+                           png_roundtrip: bool = False) -> torch.Tensor:
     """int64[3] = (clean-correct, robust-correct, total) over ALL ranks for this rank's shard of images.
 
-    ``attack_fn(images, labels) -> adv``.  Mirrors train_loras.py:56-76 (top-1 on adversarial inputs)."""
+    ``attack_fn(images, labels) -> adv``.  Mirrors train_loras.py:56-76 (top-1 on adversarial inputs).  The reference
+    evaluates the adversarial images after they went through ``save_images`` (uint8 truncation, Utils.py:106-113) and
+    were re-loaded; ``png_roundtrip=True`` applies exactly that quantisation on the device before counting."""
     c = torch.zeros(2, device=engine.device, dtype=torch.int64)
     r = torch.zeros(2, device=engine.device, dtype=torch.int64)
     engine.count_correct(images, labels, c)
     adv = attack_fn(images, labels)
+    if png_roundtrip:
+        adv = engine.png_roundtrip(adv)
     engine.count_correct(adv, labels, r)
     out = torch.stack([c[0], r[0], c[1]])
     return allreduce_counts(out)

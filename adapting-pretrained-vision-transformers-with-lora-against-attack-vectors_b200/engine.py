@@ -116,7 +116,8 @@ class Engine:
     def __init__(self, model: Optional[torch.nn.Module] = None, state_dict: Optional[Dict[str, torch.Tensor]] = None,
                  adapters: Optional[Dict[str, Sequence[Adapter]]] = None, max_batch: int = 256,
                  mean: Sequence[float] = IMAGENET_MEAN, std: Sequence[float] = IMAGENET_STD,
-                 device: Optional[torch.device] = None, ln_eps: Optional[float] = None):
+                 device: Optional[torch.device] = None, ln_eps: Optional[float] = None,
+                 merge_lora: Optional[bool] = None):
         if not torch.cuda.is_available():
             raise _lib.VitatkError("vitatk needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -139,6 +140,15 @@ class Engine:
         else:
             raise ValueError("Engine needs a model or a state_dict")
         sd = normalise_state_dict(sd)
+        # merge_lora: W <- W + s B A before packing (peft's merge_and_unload, eval_compose.py:108-110) instead of running
+        # the adapters un-merged through the fused LoRA k-blocks; the default keeps them un-merged (north-star design)
+        if merge_lora is None:
+            merge_lora = _os.environ.get("VITATK_LORA_MERGE", "0") == "1"
+        self.merged_lora = bool(merge_lora and adapters)
+        if self.merged_lora:
+            from .adapters import merge_into_state_dict
+            sd = merge_into_state_dict(sd, adapters)
+            adapters = {}
         self.adapters = {k: list(v) for k, v in (adapters or {}).items()}
         self.ln_eps = 1e-12 if ln_eps is None else ln_eps
         self.dim = sd["vit.embeddings.cls_token"].shape[-1]
@@ -341,6 +351,20 @@ class Engine:
                        "vitatk_input_grad")
         return grad, logits, loss
 
+    def vjp(self, images: torch.Tensor, dlogits: torch.Tensor):
+        """(grad [B,3,224,224] = dlogits^T . d logits / d images, logits [B,C]) for an arbitrary cotangent on the logits:
+        what autograd / ART's ``loss_gradient`` need (patch_attack.py:50-57, rp2_attack.py:37-60)."""
+        x = self._img(images)
+        if tuple(dlogits.shape) != (x.shape[0], self.num_classes):
+            raise ValueError(f"expected dlogits [{x.shape[0]},{self.num_classes}], got {tuple(dlogits.shape)}")
+        d = dlogits.detach().to(self.device, torch.float32).contiguous()
+        grad = torch.empty_like(x)
+        logits = torch.empty(x.shape[0], self.num_classes, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.vitatk_vjp(self._h, x.data_ptr(), d.data_ptr(), x.shape[0], grad.data_ptr(),
+                                           logits.data_ptr(), self._stream()), "vitatk_vjp")
+        return grad, logits
+
     def attack(self, images: torch.Tensor, labels: torch.Tensor, eps: float, alpha: float, steps: int,
                start: str = "none", noise: Optional[torch.Tensor] = None, seed: int = 0, image_index0: int = 0,
                out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -372,6 +396,21 @@ class Engine:
             _lib.check(self.lib.vitatk_count_correct(self._h, x.data_ptr(), y.data_ptr(), x.shape[0], counts.data_ptr(),
                                                      self._stream()), "vitatk_count_correct")
         return counts
+
+    def png_roundtrip(self, images: torch.Tensor, uint8: bool = False) -> torch.Tensor:
+        """What the reference's evaluation sees after ``save_images`` + reload (Utils.py:106-113): fp32
+        trunc(clamp(x)*255)/255, or with ``uint8=True`` the [B,224,224,3] uint8 array handed to PIL."""
+        x = self._img(images)
+        with torch.cuda.device(self.device):
+            if uint8:
+                out = torch.empty(x.shape[0], 224, 224, 3, device=self.device, dtype=torch.uint8)
+                _lib.check(self.lib.vitatk_png_roundtrip(x.data_ptr(), x.shape[0], None, out.data_ptr(), self._stream()),
+                           "vitatk_png_roundtrip")
+            else:
+                out = torch.empty_like(x)
+                _lib.check(self.lib.vitatk_png_roundtrip(x.data_ptr(), x.shape[0], out.data_ptr(), None, self._stream()),
+                           "vitatk_png_roundtrip")
+        return out
 
     PROFILE_CATEGORIES = ("patch", "qkv", "proj", "fc1", "fc2", "bfc2", "bfc1", "bproj", "bqkv", "bpatch",
                           "t_qkv", "t_proj", "t_fc1", "t_fc2", "bt_fc2", "bt_fc1", "bt_proj", "bt_qkv",

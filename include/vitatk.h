@@ -112,6 +112,13 @@ int vitatk_forward(vitatk_engine* e, const float* images_dev, int batch, float* 
 int vitatk_input_grad(vitatk_engine* e, const float* images_dev, const int64_t* labels_dev, int batch,
                       float* grad_dev, float* logits_dev, float* loss_dev, void* stream);
 
+/* replaces: the backward pass ART's PyTorchClassifier / autograd drive through NormalizedModel / SignConstrainedModel
+ * (patch_attack.py:16-25,50-57, rp2_attack.py:25-30,37-60): grad_dev fp32 [B,3,224,224] = dlogits^T . d logits / d images
+ * for a caller-supplied cotangent dlogits_dev fp32 [B, C] (any loss on the logits).  Runs forward + backward; logits_dev
+ * optional. */
+int vitatk_vjp(vitatk_engine* e, const float* images_dev, const float* dlogits_dev, int batch, float* grad_dev,
+               float* logits_dev, void* stream);
+
 /* replaces: batched_fgsm_attack (whitebox_attacks.py:22-38) when steps == 1, alpha == eps, start == NONE,
  * and torchattacks.PGD.__call__ (whitebox_attacks.py:112-113,168-170) otherwise.
  *   start: 0 = none, 1 = counter-based U(-eps,eps) from (seed, image_index0 + b), 2 = caller noise_dev
@@ -128,6 +135,12 @@ int vitatk_attack(vitatk_engine* e, const float* images_dev, const int64_t* labe
 /* replaces: test_model top-1 counting (train_loras.py:56-76). counts_dev int64[2] += {correct, total}. */
 int vitatk_count_correct(vitatk_engine* e, const float* images_dev, const int64_t* labels_dev, int batch,
                          long long* counts_dev, void* stream);
+
+/* replaces: save_images (Utils.py:106-113: clamp, *255, truncate to uint8, PNG) + re-loading the file with ToTensor,
+ * i.e. the pixel values train_loras.py:56-76 / eval_compose.py:16-59 really evaluate.  out_dev fp32 [B,3,224,224] =
+ * trunc(clamp(x,0,1)*255)/255 (may alias images_dev) and / or u8_hwc_dev uint8 [B,224,224,3] (what PIL receives);
+ * either may be NULL.  Needs no engine. */
+int vitatk_png_roundtrip(const float* images_dev, int batch, float* out_dev, unsigned char* u8_hwc_dev, void* stream);
 
 /* number of kernels the engine enqueued since creation (bench.py reports the per-step delta) */
 long long vitatk_launch_count(const vitatk_engine* e);

@@ -196,3 +196,82 @@ def test_robust_accuracy_counts(setup, golden):
     atk.set_normalization_used(vo.IMAGENET_MEAN, vo.IMAGENET_STD)
     counts = robust_accuracy_counts(eng, atk, x, y2).tolist()
     assert counts == golden["lora_counts_selflabel_pgd3"].tolist() == [4, 0, 4]
+
+
+def test_vjp_with_arbitrary_cotangent_vs_oracle_autograd(setup):
+    """vitatk_vjp: d(sum(dlogits * logits))/d images for a random cotangent (what ART / autograd feed the backward)."""
+    m, eng = setup["lora"]
+    x = setup["x"]
+    gen = torch.Generator(device="cpu").manual_seed(5)
+    d = torch.randn(x.shape[0], eng.num_classes, generator=gen).cuda()
+    g, logits = eng.vjp(x, d)
+    xr = x.clone().requires_grad_(True)
+    mean = torch.tensor(eng.mean, device="cuda").view(1, 3, 1, 1)
+    std = torch.tensor(eng.std, device="cuda").view(1, 3, 1, 1)
+    ol = m((xr - mean) / std)
+    ol = ol.logits if hasattr(ol, "logits") else ol
+    (og,) = torch.autograd.grad((ol * d).sum(), xr)
+    assert rel(logits, ol.detach()) < RTOL_LOGITS
+    assert rel(g, og) < RTOL_GRAD, rel(g, og)
+    assert cos(g, og) > MIN_COS
+    # the cross-entropy cotangent through the generic path reproduces input_grad (same kernels, same order)
+    y = setup["y"]
+    p = torch.softmax(logits, 1)
+    p[torch.arange(x.shape[0]), y] -= 1.0
+    g_ce, _, _ = eng.input_grad(x, y)
+    g2, _ = eng.vjp(x, p / x.shape[0])
+    assert rel(g2, g_ce) < 2e-2
+
+
+def test_engine_module_is_differentiable_like_the_wrapped_model(setup):
+    """EngineModule(NormalizedModel(LogitsModel(model))) under autograd == ART's loss_gradient on the reference wrapper
+    (patch_attack.py:16-25,50-57): loss.backward() fills x.grad through the engine."""
+    import vitatk
+    from oracle import fixtures as fx
+
+    m, _ = setup["lora"]
+    x, y = setup["x"], setup["y"]
+    wrapped = vitatk.NormalizedModel(vitatk.LogitsModel(m), fx.MEAN if hasattr(fx, "MEAN") else vitatk.engine.IMAGENET_MEAN,
+                                     fx.STD if hasattr(fx, "STD") else vitatk.engine.IMAGENET_STD)
+    mod = vitatk.EngineModule(wrapped, max_batch=8)
+    xe = x.clone().requires_grad_(True)
+    loss = torch.nn.functional.cross_entropy(mod(xe), y)
+    loss.backward()
+    xr = x.clone().requires_grad_(True)
+    rloss = torch.nn.functional.cross_entropy(wrapped(xr), y)
+    rloss.backward()
+    assert abs(float(loss) - float(rloss)) < 2e-2 * abs(float(rloss))
+    assert rel(xe.grad, xr.grad) < RTOL_GRAD
+    assert cos(xe.grad, xr.grad) > MIN_COS
+
+
+def test_adapter_directories_stacked_and_merged(adapter_dirs):
+    """base checkpoint + two peft adapter directories, un-merged (stacked ranks 8 + 4) and merged
+    (eval_compose.py:102-114), both against the fp32 oracle of the merged model."""
+    import vitatk
+    from oracle import fixtures as fx
+    from oracle import vit_oracle as vo
+
+    base, dirs = adapter_dirs
+    x, y = fx.make_inputs()
+    sd_m, _ = vitatk.compose(base.state_dict(), dirs, mode="merge")
+    ref = fx.make_model(lora=False)
+    ref.load_state_dict(sd_m)
+    ref.cuda()
+    x, y = x.cuda(), y.cuda()
+    oloss, ologits, og = vo.input_grad(ref, x, y)
+    for mode in ("stack", "merge"):
+        eng = vitatk.load_engine(base.state_dict(), dirs, mode=mode, max_batch=8, device="cuda")
+        g, logits, loss = eng.input_grad(x, y)
+        assert rel(logits, ologits) < RTOL_LOGITS, (mode, rel(logits, ologits))
+        assert rel(g, og) < RTOL_GRAD, (mode, rel(g, og))
+        assert cos(g, og) > MIN_COS
+        eng.close()
+    # merge_lora=True on a LoRA-wrapped module == its un-merged engine within bf16 rounding of the merged weights
+    m = fx.make_model(lora=True)
+    e1 = vitatk.Engine(model=m, max_batch=8, device="cuda")
+    e2 = vitatk.Engine(model=m, max_batch=8, device="cuda", merge_lora=True)
+    assert e2.merged_lora and not e1.merged_lora
+    assert rel(e2.logits(x), e1.logits(x)) < RTOL_LOGITS
+    e1.close()
+    e2.close()

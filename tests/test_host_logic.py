@@ -150,3 +150,75 @@ def test_layernorm_fold_algebra():
     Wb = Wf.float().to(torch.bfloat16).double()
     _, _, c1b, _ = fold_layernorm_into_linear(W.float(), b.float(), gamma.float(), beta.float(), [], round_to=torch.bfloat16)
     torch.testing.assert_close(c1b.double(), Wb.sum(1), rtol=1e-5, atol=1e-5)
+
+
+def test_peft_adapter_directory_round_trip(tmp_path, adapter_dirs):
+    """adapter_config.json + adapter_model.safetensors (train_loras.py:398-421) parse back to the same pairs / scale."""
+    import json
+
+    from vitatk.adapters import find_lora_adapters, read_adapter
+
+    _, dirs = adapter_dirs
+    ad = read_adapter(dirs[0])
+    assert ad.rank == 8 and len(ad.lora) == 6 * 12  # q,k,v,proj,fc1,fc2 on 12 layers
+    name = "vit.encoder.layer.3.attention.attention.query"
+    A, B, s = ad.lora[name]
+    assert A.shape == (8, 768) and B.shape == (768, 8) and s == pytest.approx(2.0)
+    assert set(ad.saved) == {"classifier.weight", "classifier.bias"}
+    cfg = json.load(open(os.path.join(dirs[0], "adapter_config.json")))
+    assert cfg["peft_type"] == "LORA" and cfg["r"] == 8 and cfg["modules_to_save"] == ["classifier"]
+    ad2 = read_adapter(dirs[1])
+    assert ad2.rank == 4 and len(ad2.lora) == 2 * 12 and ad2.lora[name][2] == pytest.approx(4.0)
+    # peft's own key spellings: adapter name inside lora_X / modules_to_save wrappers
+    from safetensors.torch import load_file, save_file
+    t = load_file(os.path.join(dirs[1], "adapter_model.safetensors"))
+    t2 = {}
+    for k, v in t.items():
+        k = k.replace(".lora_A.weight", ".lora_A.default.weight").replace("classifier.", "classifier.modules_to_save.default.")
+        t2[k] = v
+    t2["base_model.model.classifier.original_module.weight"] = torch.zeros(21, 768)
+    save_file(t2, os.path.join(dirs[1], "adapter_model.safetensors"))
+    ad3 = read_adapter(dirs[1])
+    assert set(ad3.lora) == set(ad2.lora) and set(ad3.saved) == set(ad2.saved)
+    assert torch.equal(ad3.saved["classifier.weight"], ad2.saved["classifier.weight"])
+    # eval_compose.py:197-208 path convention
+    root = str(tmp_path)
+    assert find_lora_adapters(root, ["atk0", "atk1", "missing"], 8) == {"atk0": dirs[0]}
+    assert find_lora_adapters(root, ["atk1"], 4) == {"atk1": dirs[1]}
+
+
+def test_adapter_composition_stack_equals_merge(adapter_dirs):
+    """eval_compose.py:102-114: sequential merge_and_unload == the un-merged stack of the same adapters (fp32 oracle)."""
+    from oracle import fixtures as fx
+    from oracle import vit_oracle as vo
+    from vitatk.adapters import compose
+
+    base, dirs = adapter_dirs
+    sd_m, none = compose(base.state_dict(), dirs, mode="merge")
+    sd_s, stacked = compose(base.state_dict(), dirs, mode="stack")
+    assert none == {} and len(stacked["vit.encoder.layer.0.attention.attention.query"]) == 2
+    assert len(stacked["vit.encoder.layer.0.output.dense"]) == 1
+    merged = fx.make_model(lora=False)
+    merged.load_state_dict(sd_m)
+    x, _ = fx.make_inputs(batch=2)
+    with torch.no_grad():
+        lm = vo.logits_of(merged, x)
+        # un-merged: hooks add s B (A x) of every stacked pair to the plain Linear's output
+        plain = fx.make_model(lora=False)
+        plain.load_state_dict(sd_s)
+        mods = dict(plain.named_modules())
+        hooks = []
+        for name, pairs in stacked.items():
+            def hook(mod, inp, out, pairs=pairs):
+                for (A, B, s) in pairs:
+                    out = out + s * torch.nn.functional.linear(torch.nn.functional.linear(inp[0], A), B)
+                return out
+            hooks.append(mods[name].register_forward_hook(hook))
+        ls = vo.logits_of(plain, x)
+        lb = vo.logits_of(base, x)
+    assert torch.allclose(lm, ls, rtol=1e-4, atol=1e-4)
+    assert not torch.allclose(lm, lb, rtol=1e-2, atol=1e-2)  # the adapters (and the last classifier) do change the function
+    # the classifier of the LAST adapter survives in both modes
+    from vitatk.adapters import read_adapter
+    last = read_adapter(dirs[1]).saved["classifier.weight"]
+    assert torch.equal(sd_m["classifier.weight"], last) and torch.equal(sd_s["classifier.weight"], last)

@@ -421,3 +421,26 @@ def test_pgd_init_rng_is_counter_based(lib):
     assert float(d.abs().max()) <= float(torch.tensor(eps, dtype=torch.float32))
     assert abs(float(d.mean())) < 1e-4 and float(d.std()) == pytest.approx(eps / math.sqrt(3), rel=0.02)
     assert not torch.equal(a[0], a[1])
+
+
+def test_png_roundtrip_bit_exact_vs_oracle(lib):
+    """Utils.py:106-113 save_images quantisation: bit-exact against the oracle (integer work), incl. out-of-range input."""
+    import ctypes as C
+
+    from oracle import vit_oracle as vo
+
+    g = torch.Generator().manual_seed(11)
+    x = torch.rand(3, 3, 224, 224, generator=g) * 1.2 - 0.1   # some values outside [0,1]
+    x[0, 0, 0, :8] = torch.tensor([0.0, 1.0, 0.5, 1 / 255, 254.9999 / 255, 2 / 255 - 1e-8, -3.0, 7.0])
+    xd = x.cuda()
+    out = torch.empty_like(xd)
+    u8 = torch.empty(3, 224, 224, 3, device="cuda", dtype=torch.uint8)
+    stream = torch.cuda.current_stream().cuda_stream
+    assert lib.vitatk_png_roundtrip(xd.data_ptr(), 3, out.data_ptr(), u8.data_ptr(), stream) == 0
+    ref = vo.png_roundtrip(x)
+    assert torch.equal(out.cpu(), ref)
+    ref_u8 = (torch.clamp(x, 0, 1).permute(0, 2, 3, 1) * 255).to(torch.uint8)
+    assert torch.equal(u8.cpu(), ref_u8)
+    assert lib.vitatk_png_roundtrip(xd.data_ptr(), 3, xd.data_ptr(), None, stream) == 0  # in place
+    assert torch.equal(xd.cpu(), ref)
+    assert lib.vitatk_png_roundtrip(xd.data_ptr(), 3, None, None, stream) != 0

@@ -14,6 +14,7 @@ __path__.append(PACKAGE_DIR)
 
 from .attacks import (  # noqa: E402,F401
     FGSM,
+    EngineModule,
     PGD,
     LogitsModel,
     NormalizedModel,
@@ -23,3 +24,11 @@ from .attacks import (  # noqa: E402,F401
     get_model_output,
 )
 from .engine import Engine  # noqa: E402,F401
+from .adapters import (  # noqa: E402,F401
+    PeftAdapter,
+    compose,
+    find_lora_adapters,
+    load_engine,
+    read_adapter,
+    write_adapter,
+)

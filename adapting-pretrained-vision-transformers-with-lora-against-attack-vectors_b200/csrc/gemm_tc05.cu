@@ -29,10 +29,10 @@ namespace vitatk {
 
 static constexpr int BM = 128;
 static constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
-static constexpr int NUM_EPI_WARPS = 8;
-static constexpr int TMA_WARP = 8;
-static constexpr int MMA_WARP = 9;
-static constexpr int GEMM_THREADS = 320;
+static constexpr int NUM_EPI_WARPS = 8;  // single-CTA kernel and pair kernel with EW == 1; the pair kernel with EW == 2 has 16
+// warp roles: epilogue warps 0..NEPI-1, then the TMA producer warp, then the MMA issuer warp
+__host__ __device__ constexpr int gemm_epi_warps(bool two, int ew) { return (two && ew == 2) ? 16 : NUM_EPI_WARPS; }
+__host__ __device__ constexpr int gemm_threads(bool two, int ew) { return (gemm_epi_warps(two, ew) + 2) * 32; }
 static constexpr int CHUNK = 32;                  // epilogue column granule = one tcgen05.ld.32x32b.x32
 static constexpr int STAGE_OUT_BYTES = 32 * 64;   // one warp's 32-row x 32-col bf16 store tile (64 B swizzle)
 static constexpr int SLAB_BYTES = 128 * 128;      // pair kernel: 128-row x 64-col bf16 slab (128 B swizzle)
@@ -60,7 +60,8 @@ struct GemmKernelArgs {
   GemmEpilogue epi;
   int reverse_m;  // 1: walk the M-blocks from the last to the first (the input was just written in ascending order by the
                   // previous kernel, so its tail is still in L2)
-  int gelu_f32;  // 1: fp32 Abramowitz-Stegun GELU in the epilogue (VITATK_GELU=f32), 0: packed-half path
+  int gelu_f32;  // GELU in the pair epilogue: 2 fp32 2^P fit (default), 1 fp32 Abramowitz-Stegun (VITATK_GELU=f32),
+                 // 0 packed half (VITATK_GELU=h2)
   int dbg;  // timing experiments (DBG instantiation only, VITATK_GEMM_DBG): 1 no aux loads, 2 no stores,
             // 4 no TMA loads after the first ring fill, 8 no MMA issue, 16 epilogue skips TMEM reads and math
 };
@@ -83,39 +84,25 @@ __device__ __forceinline__ void gelu_and_grad(float u, float& g, float& d) {
   g = u * phi;
   d = fmaf(u * e, 0.3989422804014327f, phi);
 }
+// fp32 variant of the 2^P fit below: 12 FMA/ALU-pipe instructions + 2 MUFU.EX2 per element and NO f16 conversions.
+// On B200 HFMA2 issues at half the FFMA rate (scripts/micro/alu_rate.cu: 64 vs 125 lanes/clk/SM) and ex2.f16x2 is two
+// MUFU ops, so packed half buys no throughput; in fp32 the same degree-4 fit is also more accurate
+// (|gelu error| <= 9.2e-5, |gelu' error| <= 7.2e-4 over [-8, 8]).
+__device__ __forceinline__ void gelu_and_grad_p(float u, float& g, float& d) {
+  const float ax = fminf(fabsf(u), 4.25f);
+  float p = fmaf(0.00238781f, ax, -0.03508832f);
+  p = fmaf(p, ax, -0.48539043f);
+  p = fmaf(p, ax, -1.13599843f);
+  p = fmaf(p, ax, -1.00205332f);
+  float e, pb;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(p));                                    // Phi(-|u|) < 0.5
+  const float hm = 0.5f - e;
+  const float phi = 0.5f + __uint_as_float(__float_as_uint(hm) | (__float_as_uint(u) & 0x80000000u));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pb) : "f"(fmaf(u * u, -0.72134752f, -1.32574806f)));  // pdf(u)
+  g = u * phi;
+  d = fmaf(u, pb, phi);
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi);
-// Packed-half variant for the GEMM epilogue (two elements per instruction, ~11.5 instructions and one MUFU per
-// element instead of ~24 and two): the fc1 epilogue is CUDA-core bound, not tensor bound (ncu: issue 44 %, tensor 45 %).
-//   Phi(-|u|) = 2^P(|u|), P = degree-4 fit of log2 Phi(-x) on [0, 4.25] (no cancellation, so small Phi keeps its
-//   relative accuracy: 1.4e-3), Phi(u) = 0.5 + copysign(0.5 - Phi(-|u|), u), pdf via a second ex2.
-// Measured against the exact functions over [-8, 8]: |gelu error| <= 2.9e-3 (0.2 bf16 ulp at that magnitude, mean
-// 4e-4), |gelu' error| <= 1.2e-3 (mean 1e-4) -- below the bf16 rounding of the stored outputs.  VITATK_GELU=f32
-// selects the fp32 Abramowitz-Stegun path above.
-__device__ __forceinline__ uint32_t h2_ex2(uint32_t x) {
-  uint32_t y;
-  asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
-  return y;
-}
-__device__ __forceinline__ void gelu_and_grad_h2(float u0, float u1, uint32_t& g_bf, uint32_t& d_bf) {
-  const __half2 h = __floats2half2_rn(u0, u1);
-  const __half2 ax = __hmin2(__habs2(h), __float2half2_rn(4.25f));
-  __half2 p = __hfma2(__float2half2_rn(0.00238781f), ax, __float2half2_rn(-0.03508832f));
-  p = __hfma2(p, ax, __float2half2_rn(-0.48539043f));
-  p = __hfma2(p, ax, __float2half2_rn(-1.13599843f));
-  p = __hfma2(p, ax, __float2half2_rn(-1.00205332f));
-  uint32_t eb = h2_ex2(*reinterpret_cast<const uint32_t*>(&p));                 // Phi(-|u|)
-  const __half2 hm = __hsub2(__float2half2_rn(0.5f), *reinterpret_cast<const __half2*>(&eb));
-  const uint32_t sg = (*reinterpret_cast<const uint32_t*>(&hm) & 0x7fff7fffu) | (*reinterpret_cast<const uint32_t*>(&h) & 0x80008000u);
-  const __half2 phi = __hadd2(__float2half2_rn(0.5f), *reinterpret_cast<const __half2*>(&sg));
-  const __half2 s2 = __hmul2(h, h);
-  const __half2 arg = __hfma2(s2, __float2half2_rn(-0.72134752f), __float2half2_rn(-1.32574806f));  // log2(1/sqrt(2 pi))
-  uint32_t pb = h2_ex2(*reinterpret_cast<const uint32_t*>(&arg));               // exp(-u^2/2) / sqrt(2 pi)
-  const __half2 g = __hmul2(h, phi);
-  const __half2 d = __hfma2(h, *reinterpret_cast<const __half2*>(&pb), phi);
-  const float2 gf = __half22float2(g), df = __half22float2(d);
-  g_bf = pack_bf16x2(gf.x, gf.y);
-  d_bf = pack_bf16x2(df.x, df.y);
-}
 __device__ __forceinline__ float gelu_exact(float u) { return 0.5f * u * (1.0f + erff(u * 0.70710678118654752f)); }
 __device__ __forceinline__ float gelu_grad(float u) {
   const float cdf = 0.5f * (1.0f + erff(u * 0.70710678118654752f));
@@ -157,8 +144,8 @@ __device__ __forceinline__ void stage_and_store(uint8_t* stage, const uint32_t (
   }
 }
 
-template <int BN, bool DBG, bool TWO>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <int BN, bool DBG, bool TWO, int EW = 1>
+__global__ void __launch_bounds__(gemm_threads(TWO, EW), 1)
 gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmLA, const __grid_constant__ CUtensorMap tmLB,
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
@@ -170,6 +157,9 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int num_units = TWO ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   constexpr int TILE_M = TWO ? 2 * BM : BM;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int NEPI = gemm_epi_warps(TWO, EW);
+  constexpr int TMA_WARP = NEPI;
+  constexpr int MMA_WARP = NEPI + 1;
   extern __shared__ uint8_t smem_raw[];
   // 1024 B alignment: required by the 128B swizzle pattern shared by TMA and the UMMA descriptors
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -200,7 +190,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(&tmem_full[b], 1);
-      ptx::mbar_init(&tmem_empty[b], TWO ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS);  // pair: both CTAs' epilogue warps
+      ptx::mbar_init(&tmem_empty[b], TWO ? 2 * NEPI : NEPI);  // pair: both CTAs' epilogue warps
     }
     for (int i = 0; i < 4; ++i) ptx::mbar_init(&aux_bar[i], 1);
     ptx::fence_mbar_init();
@@ -334,15 +324,22 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if constexpr (TWO) {
-    // ================================= slab epilogue (pair kernel), warps 0..7 =================================
-    // Column group g = warp / 4 owns columns [128 g, 128 g + 128) of the tile as two 64-column slabs; its four warps
-    // (TMEM lane quarters) fill one 128-row x 64-column slab in 128B-swizzled smem and ONE thread issues ONE TMA store
-    // per slab (4 per tile instead of 32 small ones, full 128-byte lines).  Residual / multiplier slabs are TMA-loaded
-    // into the same buffer one slab ahead and combined in place, so no strided per-lane global loads remain.
+    // ================================= slab epilogue (pair kernel), warps 0..NEPI-1 =================================
+    // Column group g owns columns [128 g, 128 g + 128) of the tile as two 64-column slabs; its warps fill one 128-row x
+    // 64-column slab in 128B-swizzled smem and ONE thread issues ONE TMA store per slab (4 per tile instead of 32 small
+    // ones, full 128-byte lines).  Residual / multiplier slabs are TMA-loaded into the same buffer one slab ahead and
+    // combined in place, so no strided per-lane global loads remain.
+    // EW = warps per TMEM lane quarter inside a group: 1 -> four warps per group, every thread owns a full 64-column
+    // slab row; 2 -> eight warps per group, warp (q, hh) owns columns [32 hh, 32 hh + 32) of the slab row (half the
+    // registers per thread and four instead of two warps per scheduler to hide the epilogue's dependent-issue latency).
+    constexpr int NC = 64 / EW;            // slab columns per thread
+    constexpr int NP = NC / 2;             // packed bf16x2 registers per thread per slab
+    constexpr int NQ = NC / 8;             // 16-byte chunks per thread per slab row
     const int q = warp & 3;
-    const int g = warp >> 2;
+    const int hh = (EW == 2) ? ((warp >> 2) & 1) : 0;
+    const int g = (EW == 2) ? (warp >> 3) : (warp >> 2);
     const int trow = q * 32 + lane;  // row inside this CTA's 128-row block
-    const bool issuer = (q == 0) && (lane == 0);
+    const bool issuer = (q == 0) && (hh == 0) && (lane == 0);
     const uint32_t gbuf = ptx::smem_u32(smem_out) + g * 2 * SLAB_BYTES;
     uint64_t* aux_full = aux_bar + g * 2;
     const uint32_t bar_id = 1 + g;
@@ -355,7 +352,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t c = 0;  // slabs this group has produced; slab c uses buffer c & 1
     auto group_sync = [&]() {
       if (DBG && (args.dbg & 128)) return;  // timing experiment: no group barriers (results are garbage)
-      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(128 * EW) : "memory");
     };
     auto issue_aux = [&](uint32_t cc, int tile_, int sl_) {  // issuer thread only
       const int am0 = mblock(tile_) * TILE_M + static_cast<int>(rank) * BM;
@@ -364,22 +361,22 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       ptx::mbar_arrive_expect_tx(&aux_full[b], SLAB_BYTES);
       ptx::tma_load_2d(smem_out + g * 2 * SLAB_BYTES + b * SLAB_BYTES, &tmAux, &aux_full[b], acol, am0);
     };
-    // write one packed 64-column row (32 registers) of this thread into slab buffer b
-    auto write_row = [&](uint32_t b, const uint32_t (&pk)[32]) {
+    // write this thread's NC packed columns of its row into slab buffer b
+    auto write_row = [&](uint32_t b, const uint32_t (&pk)[NP]) {
       if (DBG && (args.dbg & 32)) {  // timing experiment: no staging writes (keep the values alive)
-        if (pk[3] == 0x12345678u && pk[17] == 0x9abcdef0u) tmem_slot[1] = pk[5];
+        if (pk[3] == 0x12345678u && pk[NP - 1] == 0x9abcdef0u) tmem_slot[1] = pk[5];
         return;
       }
       const uint32_t rowaddr = gbuf + b * SLAB_BYTES + trow * 128;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const uint32_t addr = rowaddr + ((j ^ swz) << 4);
+      for (int j = 0; j < NQ; ++j) {
+        const uint32_t addr = rowaddr + (((hh * NQ + j) ^ swz) << 4);
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * j]), "r"(pk[4 * j + 1]),
                      "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
                      : "memory");
       }
     };
-    // hand a filled slab to the TMA store engine (all four warps call; one thread issues)
+    // hand a filled slab to the TMA store engine (all warps of the group call; one thread issues)
     auto store_slab = [&](uint32_t b, const CUtensorMap* tm, int col, int row0) {
       ptx::fence_proxy_async_smem();
       group_sync();
@@ -394,16 +391,26 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int n0 = (tile % tiles_n) * BN;
       const uint32_t buf = it & 1;
       const uint32_t use = it >> 1;
-      ptx::mbar_wait(&tmem_full[buf], use & 1);
-      ptx::tc_fence_after();
       const int row = m0 + trow;
       const bool row_ok = row < args.M;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + g * 128;
-#pragma unroll 1
+      // folded LayerNorm: this row's (mean, rstd), fetched before the accumulator is awaited
+      const float2 st = (epi.row_stats != nullptr && row_ok) ? __ldg(epi.row_stats + row) : make_float2(0.f, 1.f);
+      ptx::mbar_wait(&tmem_full[buf], use & 1);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + g * 128 + hh * NC;
+      uint32_t rn[EW == 2 ? 32 : 1];  // EW == 2: slab 1's accumulator columns, fetched together with slab 0's
+      (void)rn;
+#pragma unroll(EW == 2 ? 2 : 1)
       for (int sl = 0; sl < 2; ++sl) {
-        const int ncol = n0 + g * 128 + sl * 64;
-        float v[64];
-        if (!(DBG && (args.dbg & 16))) {
+        const int scol = n0 + g * 128 + sl * 64;  // first column of the slab (TMA coordinates)
+        const int ncol = scol + hh * NC;          // first column this thread owns
+        float v[NC];
+        bool drained = false;  // every tcgen05.ld of this accumulator has completed
+        if (DBG && (args.dbg & 16)) {
+#pragma unroll
+          for (int j = 0; j < NC; ++j) v[j] = 0.f;
+          drained = (sl == 1);
+        } else if constexpr (EW == 1) {
           uint32_t r0[32], r1[32];
           ptx::tmem_ld_32x32b_x32(taddr + sl * 64, r0);
           ptx::tmem_ld_32x32b_x32(taddr + sl * 64 + 32, r1);
@@ -411,34 +418,52 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             v[j] = __uint_as_float(r0[j]);
-            v[32 + j] = __uint_as_float(r1[j]);
+            v[NC / 2 + j] = __uint_as_float(r1[j]);
           }
+          drained = (sl == 1);
         } else {
+          // slab 1's columns are requested while slab 0 is being staged / stored (prefetch_slab1 below), so the second
+          // half of the tile starts without a TMEM round trip
+          if (sl == 0) {
+            uint32_t r0[32];
+            ptx::tmem_ld_32x32b_x32(taddr, r0);
+            ptx::tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 64; ++j) v[j] = 0.f;
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]);
+          } else {
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rn[j]);
+            drained = true;
+          }
         }
-        if (sl == 1) {  // every tcgen05.ld of this accumulator has completed -> hand it back to the MMA warp
+        // EW == 2: issue slab 1's TMEM load once slab 0's values are packed (v is dead, registers are free again)
+        auto prefetch_slab1 = [&]() {
+          if constexpr (EW == 2) {
+            if (sl == 0 && !(DBG && (args.dbg & 16))) ptx::tmem_ld_32x32b_x32(taddr + 64, rn);
+          }
+        };
+        if (drained) {  // hand the accumulator back to the MMA warp
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive_cluster(tmem_empty_remote + buf * 8);
         }
         if (epi.row_stats != nullptr) {  // LayerNorm folded into this GEMM: acc <- rstd * (acc - mean * c1[n])
-          const float2 st = row_ok ? __ldg(epi.row_stats + row) : make_float2(0.f, 1.f);
           const float nm = -st.x * st.y;
           const float4* cp = reinterpret_cast<const float4*>(epi.c1 + ncol);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float4 c = __ldg(cp + j);
-            v[4 * j] = fmaf(v[4 * j], st.y, nm * c.x);
-            v[4 * j + 1] = fmaf(v[4 * j + 1], st.y, nm * c.y);
-            v[4 * j + 2] = fmaf(v[4 * j + 2], st.y, nm * c.z);
-            v[4 * j + 3] = fmaf(v[4 * j + 3], st.y, nm * c.w);
+          for (int j = 0; j < NC / 4; ++j) {
+            const float4 cc = __ldg(cp + j);
+            v[4 * j] = fmaf(v[4 * j], st.y, nm * cc.x);
+            v[4 * j + 1] = fmaf(v[4 * j + 1], st.y, nm * cc.y);
+            v[4 * j + 2] = fmaf(v[4 * j + 2], st.y, nm * cc.z);
+            v[4 * j + 3] = fmaf(v[4 * j + 3], st.y, nm * cc.w);
           }
         }
         if (epi.bias != nullptr && !(DBG && (args.dbg & 64))) {
           const float4* bp = reinterpret_cast<const float4*>(epi.bias + ncol);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
+          for (int j = 0; j < NC / 4; ++j) {
             const float4 b = __ldg(bp + j);
             v[4 * j] += b.x;
             v[4 * j + 1] += b.y;
@@ -450,7 +475,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const float4* tp =
               reinterpret_cast<const float4*>(epi.table + static_cast<size_t>(row % epi.table_rows) * args.N + ncol);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
+          for (int j = 0; j < NC / 4; ++j) {
             const float4 b = __ldg(tp + j);
             v[4 * j] += b.x;
             v[4 * j + 1] += b.y;
@@ -458,12 +483,18 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             v[4 * j + 3] += b.w;
           }
         }
-        uint32_t pk[32];
+        uint32_t pk[NP];
         if (epi.mode == EPI_GELU_DUAL) {
-          uint32_t pk2[32];
-          if (args.gelu_f32) {
+          uint32_t pk2[NP];
+          if (DBG && (args.dbg & 256)) {  // timing experiment: no GELU math
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
+            for (int j = 0; j < NP; ++j) {
+              pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+              pk2[j] = pk[j] ^ 0x00010001u;
+            }
+          } else if (args.gelu_f32 == 1) {
+#pragma unroll
+            for (int j = 0; j < NP; ++j) {
               float g0, d0, g1, d1;
               gelu_and_grad(v[2 * j], g0, d0);
               gelu_and_grad(v[2 * j + 1], g1, d1);
@@ -472,8 +503,15 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) gelu_and_grad_h2(v[2 * j], v[2 * j + 1], pk[j], pk2[j]);
+            for (int j = 0; j < NP; ++j) {
+              float g0, d0, g1, d1;
+              gelu_and_grad_p(v[2 * j], g0, d0);
+              gelu_and_grad_p(v[2 * j + 1], g1, d1);
+              pk[j] = pack_bf16x2(g0, g1);
+              pk2[j] = pack_bf16x2(d0, d1);
+            }
           }
+          prefetch_slab1();
           // two slabs per column slab: gelu(u) -> out (buffer 0), gelu'(u) -> out2 (buffer 1); both buffers were last
           // used one column slab ago, so one wait + two group barriers cover both stores
           if (issuer) ptx::tma_store_wait_read<0>();
@@ -483,8 +521,8 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           ptx::fence_proxy_async_smem();
           group_sync();
           if (issuer && !no_store) {
-            ptx::tma_store_2d(&tmOut, smem_out + g * 2 * SLAB_BYTES, ncol, m0);
-            ptx::tma_store_2d(&tmOut2, smem_out + g * 2 * SLAB_BYTES + SLAB_BYTES, ncol, m0);
+            ptx::tma_store_2d(&tmOut, smem_out + g * 2 * SLAB_BYTES, scol, m0);
+            ptx::tma_store_2d(&tmOut2, smem_out + g * 2 * SLAB_BYTES + SLAB_BYTES, scol, m0);
             ptx::tma_store_commit();
           }
           c += 2;
@@ -494,9 +532,9 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t rowaddr = gbuf + b * SLAB_BYTES + trow * 128;
           float dot = 0.f;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < NQ; ++j) {
             uint4 a;
-            const uint32_t addr = rowaddr + ((j ^ swz) << 4);
+            const uint32_t addr = rowaddr + (((hh * NQ + j) ^ swz) << 4);
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(addr));
             float f[8];
             unpack_bf16x8(a, f);
@@ -518,15 +556,18 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
           if (epi.mode == EPI_ROWDOT) {
-            if (row_ok)
-              epi.rowdot[(static_cast<size_t>(row / epi.rowdot_rows) * (args.N >> 6) + (ncol >> 6)) * epi.rowdot_pad +
+            // one slab row = one head's 64 columns: only the EW == 1 layout holds them in one thread (the host never
+            // selects EW == 2 for this mode)
+            if (EW == 1 && row_ok)
+              epi.rowdot[(static_cast<size_t>(row / epi.rowdot_rows) * (args.N >> 6) + (scol >> 6)) * epi.rowdot_pad +
                          row % epi.rowdot_rows] = dot;
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+            for (int j = 0; j < NP; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
           }
-          write_row(b, pk);  // in place: each thread only ever touches its own row of the slab
-          store_slab(b, &tmOut, ncol, m0);
+          prefetch_slab1();
+          write_row(b, pk);  // in place: each thread only ever touches its own part of its own row of the slab
+          store_slab(b, &tmOut, scol, m0);
           ++c;
           if (issuer) {
             // the other buffer's last store has been read out -> fetch the next slab's residual / multiplier into it
@@ -536,12 +577,13 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+          for (int j = 0; j < NP; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+          prefetch_slab1();
           const uint32_t b = c & 1;
           if (issuer) ptx::tma_store_wait_read<1>();
           group_sync();
           write_row(b, pk);
-          store_slab(b, &tmOut, ncol, m0);
+          store_slab(b, &tmOut, scol, m0);
           ++c;
         }
       }
@@ -921,9 +963,18 @@ static int gemm_gelu_f32() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("VITATK_GELU");
-    v = (e && strcmp(e, "f32") == 0) ? 1 : 0;
+    v = (e && strcmp(e, "f32") == 0) ? 1 : ((e && strcmp(e, "h2") == 0) ? 0 : 2);  // default: fp32 2^P fit
   }
   return v;
+}
+
+static bool gemm_epi16_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VITATK_GEMM_EPI16");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v == 1;
 }
 
 static int gemm_dbg_flags() {
@@ -935,14 +986,14 @@ static int gemm_dbg_flags() {
   return dbg;
 }
 
-template <int BN, bool TWO>
+template <int BN, bool TWO, int EW = 1>
 static int launch_bn(const GemmPlan* p, cudaStream_t stream, int num_sms) {
   using Cfg = GemmCfg<BN, TWO>;
   static bool attr_set = false;
   if (!attr_set) {
-    VITATK_CUDA_OK(cudaFuncSetAttribute(gemm_tc05_kernel<BN, false, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    VITATK_CUDA_OK(cudaFuncSetAttribute(gemm_tc05_kernel<BN, false, TWO, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::SMEM_BYTES));
-    VITATK_CUDA_OK(cudaFuncSetAttribute(gemm_tc05_kernel<BN, true, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    VITATK_CUDA_OK(cudaFuncSetAttribute(gemm_tc05_kernel<BN, true, TWO, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::SMEM_BYTES));
     attr_set = true;
   }
@@ -961,19 +1012,25 @@ static int launch_bn(const GemmPlan* p, cudaStream_t stream, int num_sms) {
   a.dbg = gemm_dbg_flags();
   a.gelu_f32 = gemm_gelu_f32();
   a.reverse_m = p->reverse_m;
-  const dim3 grid(TWO ? 2 * units : units, 1, 1), block(GEMM_THREADS, 1, 1);
+  const dim3 grid(TWO ? 2 * units : units, 1, 1), block(gemm_threads(TWO, EW), 1, 1);
   if (a.dbg)
-    VITATK_CUDA_OK(launch_pdl(gemm_tc05_kernel<BN, true, TWO>, grid, block, Cfg::SMEM_BYTES, stream, TWO ? 2 : 1, p->tmA,
+    VITATK_CUDA_OK(launch_pdl(gemm_tc05_kernel<BN, true, TWO, EW>, grid, block, Cfg::SMEM_BYTES, stream, TWO ? 2 : 1, p->tmA,
                               p->tmB, p->tmLA, p->tmLB, p->tmOut, p->tmOut2, p->tmAux, a));
   else
-    VITATK_CUDA_OK(launch_pdl(gemm_tc05_kernel<BN, false, TWO>, grid, block, Cfg::SMEM_BYTES, stream, TWO ? 2 : 1, p->tmA,
+    VITATK_CUDA_OK(launch_pdl(gemm_tc05_kernel<BN, false, TWO, EW>, grid, block, Cfg::SMEM_BYTES, stream, TWO ? 2 : 1, p->tmA,
                               p->tmB, p->tmLA, p->tmLB, p->tmOut, p->tmOut2, p->tmAux, a));
   return 0;
 }
 
 int gemm_launch(const GemmPlan* p, cudaStream_t stream, int num_sms) {
   switch (p->BN) {
-    case 256: return p->two_cta ? launch_bn<256, true>(p, stream, num_sms) : launch_bn<256, false>(p, stream, num_sms);
+    case 256:
+      if (!p->two_cta) return launch_bn<256, false>(p, stream, num_sms);
+      // 16 epilogue warps (two per TMEM lane quarter and column group) for the short-K GEMMs, whose epilogue is as long
+      // as their main loop (measured: fc1 -7 %, qkv -4 %, proj -4 %, bfc2 -3 %); the K >= 2304 GEMMs are main-loop
+      // bound and lose ~3 % to the extra warps, and ROWDOT needs a whole slab row in one thread
+      if (gemm_epi16_enabled() && p->epi.mode != EPI_ROWDOT && p->K <= 1024) return launch_bn<256, true, 2>(p, stream, num_sms);
+      return launch_bn<256, true, 1>(p, stream, num_sms);
     case 192: return launch_bn<192, false>(p, stream, num_sms);
     case 128: return launch_bn<128, false>(p, stream, num_sms);
     case 64: return launch_bn<64, false>(p, stream, num_sms);

@@ -1,7 +1,11 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/t_gpu.log 2>&1; echo "tests rc=$?"
-tail -4 gpurun_out/t_gpu.log
+timeout 900 python -m pytest tests/test_kernels_gpu.py -x -q -m gpu -k "gemm" 2>&1 | grep -v Warning | tail -3
+for v in 0 1; do
+echo "== EPI16=$v"
+VITATK_GEMM_EPI16=$v timeout 200 python scripts/gemm_bench.py 30 proj,qkv,fc1,fc2,bfc2 2>&1 | tail -5
+VITATK_GEMM_DBG=14 VITATK_GEMM_EPI16=$v timeout 200 python scripts/gemm_bench.py 30 fc1 2>&1 | tail -1
+done
 for v in 0 1 0 1; do
-VITATK_ZIGZAG=$v timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline 2> gpurun_out/bench_ab.err | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print('ZIGZAG=$v value',round(d['value'],1),'ms/step',round(d['ms_per_step'],2), {k:round(v,1) for k,v in d['breakdown_ms_per_step'].items()}, d['robust']['clean_correct'], {k:v for k,v in d['breakdown_detail'].items() if k.startswith('t_') or k.startswith('bt_')})"
+VITATK_GEMM_EPI16=$v timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline 2> gpurun_out/ab_$v.err | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('EPI16=$v value',d['value'],'ms/step',d['ms_per_step'], {k:v[0] for k,v in d['breakdown_detail'].items() if k in ('qkv','proj','fc1','fc2','bfc2','bfc1','bqkv')})"
 done

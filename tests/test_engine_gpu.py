@@ -275,3 +275,32 @@ def test_adapter_directories_stacked_and_merged(adapter_dirs):
     assert rel(e2.logits(x), e1.logits(x)) < RTOL_LOGITS
     e1.close()
     e2.close()
+
+
+def test_full_size_batch_properties():
+    """BASELINE configs[1] size (batch 256, LoRA r=8 on six targets): size-independent properties of the attack —
+    ||delta||_inf <= eps exactly, range [0,1], bit-reproducible, every image's result independent of its batch-mates
+    (the first rows of the 256-image attack equal the same images attacked in a batch of 5), sharding-invariant RNG."""
+    import vitatk
+    from oracle import fixtures as fx
+
+    m = fx.make_model(lora=True)
+    eng = vitatk.Engine(model=m, max_batch=256, device="cuda")
+    g = torch.Generator().manual_seed(77)
+    x = torch.rand(256, 3, 224, 224, generator=g).cuda()
+    y = torch.randint(0, fx.NUM_CLASSES, (256,), generator=g).cuda()
+    eps32 = float(torch.tensor(fx.EPS, dtype=torch.float32))
+    a1 = eng.attack(x, y, fx.EPS, fx.ALPHA, 3, start="rng", seed=9)
+    a2 = eng.attack(x, y, fx.EPS, fx.ALPHA, 3, start="rng", seed=9)
+    assert torch.equal(a1, a2), "same inputs, same seed -> bit-identical adversarial images"
+    assert float((a1 - x).abs().max()) <= eps32
+    assert float(a1.min()) >= 0.0 and float(a1.max()) <= 1.0
+    assert float((a1 - x).abs().max()) > 0.5 * eps32  # the attack moved
+    # batch independence + sharding-invariant random start: images 251..255 attacked alone, keyed by their global index
+    tail = eng.attack(x[251:], y[251:], fx.EPS, fx.ALPHA, 3, start="rng", seed=9, image_index0=251)
+    assert torch.equal(tail, a1[251:])
+    head = eng.attack(x[:5], y[:5], fx.EPS, fx.ALPHA, 3, start="rng", seed=9, image_index0=0)
+    assert torch.equal(head, a1[:5])
+    # logits of the full batch equal the small-batch logits row by row
+    assert torch.equal(eng.logits(x)[100:103], eng.logits(x[100:103]))
+    eng.close()

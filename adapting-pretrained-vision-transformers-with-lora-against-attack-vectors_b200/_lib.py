@@ -77,7 +77,7 @@ EXPORTS = [
     "vitatk_attack", "vitatk_count_correct", "vitatk_launch_count", "vitatk_k_gemm", "vitatk_k_attention_fwd",
     "vitatk_k_attention_bwd", "vitatk_k_layernorm_fwd", "vitatk_k_layernorm_bwd", "vitatk_k_pgd_update",
     "vitatk_k_pgd_init", "vitatk_profile_begin", "vitatk_profile_end", "vitatk_k_attention_fwd_tc05",
-    "vitatk_k_attention_bwd_tc05", "vitatk_k_attention_bwd_fused", "vitatk_k_attention_bwd_trace",
+    "vitatk_k_attention_bwd_tc05", "vitatk_k_attention_bwd_fused", "vitatk_k_gemm_trace", "vitatk_k_attention_bwd_trace",
     "vitatk_k_attention_fwd_trace", "vitatk_k_layernorm_fwd_t", "vitatk_k_layernorm_bwd_t", "vitatk_k_layernorm_stats",
 ]
 
@@ -129,6 +129,7 @@ def load() -> C.CDLL:
     lib.vitatk_k_attention_fwd_tc05.argtypes = [vp, vp, vp, i, i, i, vp]
     lib.vitatk_k_attention_bwd_tc05.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, vp]
     lib.vitatk_k_attention_bwd_fused.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, vp]
+    lib.vitatk_k_gemm_trace.argtypes = [vp]
     lib.vitatk_k_attention_bwd_trace.argtypes = [vp]
     lib.vitatk_k_attention_fwd_trace.argtypes = [vp]
     lib.vitatk_k_attention_bwd.argtypes = [vp, vp, vp, i, i, i, vp]

@@ -855,6 +855,7 @@ int vitatk_k_attention_bwd_fused(const void* qkv, const void* dout, const void* 
     return 1;
   return attention_bwd_fused(&p, static_cast<cudaStream_t>(stream), true);
 }
+int vitatk_k_gemm_trace(long long* dev_buf) { return gemm_set_trace(dev_buf); }
 int vitatk_k_attention_bwd_trace(long long* dev_buf) { return attention_bwd_set_trace(dev_buf); }
 int vitatk_k_attention_fwd_trace(long long* dev_buf) { return attention_fwd_set_trace(dev_buf); }
 int vitatk_k_attention_bwd(const void* qkv, const void* dout, void* dqkv, int batch, int tokens, int heads,

@@ -63,7 +63,8 @@ struct GemmKernelArgs {
   int gelu_f32;  // GELU in the pair epilogue: 2 fp32 2^P fit (default), 1 fp32 Abramowitz-Stegun (VITATK_GELU=f32),
                  // 0 packed half (VITATK_GELU=h2)
   int dbg;  // timing experiments (DBG instantiation only, VITATK_GEMM_DBG): 1 no aux loads, 2 no stores,
-            // 4 no TMA loads after the first ring fill, 8 no MMA issue, 16 epilogue skips TMEM reads and math
+            // 4 no TMA loads after the first ring fill, 8 no MMA issue, 16 epilogue skips TMEM reads and math,
+            // 32 no staging writes, 64 no bias, 128 no group barriers, 256 no GELU math, 512 epilogue timeline
 };
 
 // Exact-erf GELU and its derivative from ONE exponential and ONE reciprocal (Abramowitz-Stegun 7.1.26,
@@ -143,6 +144,9 @@ __device__ __forceinline__ void stage_and_store(uint8_t* stage, const uint32_t (
     ptx::tma_store_commit();
   }
 }
+
+// in-kernel timeline (DBG instantiation, dbg & 512): CTA 0, lane 0 of epilogue warps 0 and 5 write clock64() per event
+__device__ long long* g_gemm_trace = nullptr;
 
 template <int BN, bool DBG, bool TWO, int EW = 1>
 __global__ void __launch_bounds__(gemm_threads(TWO, EW), 1)
@@ -350,6 +354,12 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t tmem_empty_remote = ptx::mapa_shared(ptx::smem_u32(&tmem_empty[0]), 0);  // the leader's barrier
     uint32_t it = 0;
     uint32_t c = 0;  // slabs this group has produced; slab c uses buffer c & 1
+    // timeline slot: [tile iteration < 24][slab][event < 12][warp 0 | warp 5]
+    auto GTR = [&](int sl_, int ev) {
+      if (DBG && (args.dbg & 512) && g_gemm_trace != nullptr && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 5) &&
+          it < 24)
+        g_gemm_trace[((it * 2 + sl_) * 12 + ev) * 2 + (warp == 0 ? 0 : 1)] = clock64();
+    };
     auto group_sync = [&]() {
       if (DBG && (args.dbg & 128)) return;  // timing experiment: no group barriers (results are garbage)
       asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(128 * EW) : "memory");
@@ -395,8 +405,16 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const bool row_ok = row < args.M;
       // folded LayerNorm: this row's (mean, rstd), fetched before the accumulator is awaited
       const float2 st = (epi.row_stats != nullptr && row_ok) ? __ldg(epi.row_stats + row) : make_float2(0.f, 1.f);
+      // the group's 128 columns of c1 / bias (4 lines each) are pulled into L1 before the accumulator is awaited: under
+      // the main loop's shared-memory traffic an L1 miss in the middle of the epilogue costs thousands of clocks
+      if (!(DBG && (args.dbg & 1024)) && q == 0 && hh == 0 && lane < 8) {
+        const float* base = (lane < 4) ? epi.c1 : epi.bias;
+        if (base != nullptr) ptx::prefetch_l1(base + n0 + g * 128 + (lane & 3) * 32);
+      }
+      GTR(0, 0);
       ptx::mbar_wait(&tmem_full[buf], use & 1);
       ptx::tc_fence_after();
+      GTR(0, 1);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + g * 128 + hh * NC;
       uint32_t rn[EW == 2 ? 32 : 1];  // EW == 2: slab 1's accumulator columns, fetched together with slab 0's
       (void)rn;
@@ -443,12 +461,16 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (sl == 0 && !(DBG && (args.dbg & 16))) ptx::tmem_ld_32x32b_x32(taddr + 64, rn);
           }
         };
+        GTR(sl, 2);
         if (drained) {  // hand the accumulator back to the MMA warp
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive_cluster(tmem_empty_remote + buf * 8);
         }
-        if (epi.row_stats != nullptr) {  // LayerNorm folded into this GEMM: acc <- rstd * (acc - mean * c1[n])
+        if (DBG && (args.dbg & 2048)) {  // timing experiment: per-row scale only, no per-column constants
+#pragma unroll
+          for (int j = 0; j < NC; ++j) v[j] *= st.y;
+        } else if (epi.row_stats != nullptr) {  // LayerNorm folded into this GEMM: acc <- rstd * (acc - mean * c1[n])
           const float nm = -st.x * st.y;
           const float4* cp = reinterpret_cast<const float4*>(epi.c1 + ncol);
 #pragma unroll
@@ -460,7 +482,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             v[4 * j + 3] = fmaf(v[4 * j + 3], st.y, nm * cc.w);
           }
         }
-        if (epi.bias != nullptr && !(DBG && (args.dbg & 64))) {
+        if (epi.bias != nullptr && !(DBG && (args.dbg & (64 | 2048)))) {
           const float4* bp = reinterpret_cast<const float4*>(epi.bias + ncol);
 #pragma unroll
           for (int j = 0; j < NC / 4; ++j) {
@@ -484,6 +506,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         uint32_t pk[NP];
+        GTR(sl, 3);
         if (epi.mode == EPI_GELU_DUAL) {
           uint32_t pk2[NP];
           if (DBG && (args.dbg & 256)) {  // timing experiment: no GELU math
@@ -512,19 +535,26 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
           prefetch_slab1();
+          GTR(sl, 4);
           // two slabs per column slab: gelu(u) -> out (buffer 0), gelu'(u) -> out2 (buffer 1); both buffers were last
           // used one column slab ago, so one wait + two group barriers cover both stores
           if (issuer) ptx::tma_store_wait_read<0>();
+          GTR(sl, 5);
           group_sync();
+          GTR(sl, 6);
           write_row(0, pk);
           write_row(1, pk2);
+          GTR(sl, 7);
           ptx::fence_proxy_async_smem();
+          GTR(sl, 8);
           group_sync();
+          GTR(sl, 9);
           if (issuer && !no_store) {
             ptx::tma_store_2d(&tmOut, smem_out + g * 2 * SLAB_BYTES, scol, m0);
             ptx::tma_store_2d(&tmOut2, smem_out + g * 2 * SLAB_BYTES + SLAB_BYTES, scol, m0);
             ptx::tma_store_commit();
           }
+          GTR(sl, 10);
           c += 2;
         } else if (has_aux) {
           const uint32_t b = c & 1;
@@ -579,11 +609,16 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < NP; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
           prefetch_slab1();
+          GTR(sl, 4);
           const uint32_t b = c & 1;
           if (issuer) ptx::tma_store_wait_read<1>();
+          GTR(sl, 5);
           group_sync();
+          GTR(sl, 6);
           write_row(b, pk);
+          GTR(sl, 7);
           store_slab(b, &tmOut, scol, m0);
+          GTR(sl, 10);
           ++c;
         }
       }
@@ -1019,6 +1054,11 @@ static int launch_bn(const GemmPlan* p, cudaStream_t stream, int num_sms) {
   else
     VITATK_CUDA_OK(launch_pdl(gemm_tc05_kernel<BN, false, TWO, EW>, grid, block, Cfg::SMEM_BYTES, stream, TWO ? 2 : 1, p->tmA,
                               p->tmB, p->tmLA, p->tmLB, p->tmOut, p->tmOut2, p->tmAux, a));
+  return 0;
+}
+
+int gemm_set_trace(long long* dev_buf) {
+  VITATK_CUDA_OK(cudaMemcpyToSymbol(g_gemm_trace, &dev_buf, sizeof(dev_buf)));
   return 0;
 }
 

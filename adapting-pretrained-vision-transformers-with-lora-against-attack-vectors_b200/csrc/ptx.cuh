@@ -69,6 +69,9 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 // ----------------------------------------------------------------------------------------------
 // TMA
 // ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void prefetch_l1(const void* gptr) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(gptr));
+}
 __device__ __forceinline__ void prefetch_tmap(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
 }
@@ -381,8 +384,11 @@ __device__ __forceinline__ void mbar_arrive_expect_tx_cluster_p(uint32_t leader,
       "r"(bytes), "r"(leader)
       : "memory");
 }
+// Arrive on an mbarrier of another CTA of the cluster.  Default semantics (.release at CTA scope): what is handed over is
+// TMEM, ordered by tcgen05.fence::before_thread_sync; a cluster-scope release turns into a full memory barrier and was
+// measured at ~2000 clk per arrival under the GEMM main loop's memory traffic (scripts/gemm_trace.py).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {  // acquire at cluster scope
   uint32_t ok;

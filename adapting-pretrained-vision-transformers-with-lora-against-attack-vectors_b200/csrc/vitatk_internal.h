@@ -157,6 +157,7 @@ int attention_bwd_plan_init(AttnBwdPlan* p, const bf16* qkv, const bf16* dout, c
 int attention_bwd_tc05(const AttnBwdPlan* p, cudaStream_t stream);        // two-kernel version (dQ, then dK/dV)
 // single-pass version (engine default); compute_delta = false when delta was already produced (EPI_ROWDOT GEMM)
 int attention_bwd_fused(const AttnBwdPlan* p, cudaStream_t stream, bool compute_delta);
+int gemm_set_trace(long long* dev_buf);
 int attention_bwd_set_trace(long long* dev_buf);                          // timing experiments only
 int attention_fwd_set_trace(long long* dev_buf);                          // timing experiments only
 // mma.sync forward (round-1 first version, kept for cross-checking the tcgen05 kernel in tests)

@@ -175,6 +175,7 @@ int vitatk_k_attention_bwd_fused(const void* qkv_dev, const void* dout_dev, cons
                                  float* delta_dev, void* dqkv_dev, int batch, int tokens, int heads, void* stream);
 /* timing experiments: device buffer of 4096 int64 receiving CTA 0's (event, step, clock64) timeline when
  * VITATK_ATTN_DBG has bit 32 set (scripts/attn_trace.py, scripts/attn_fwd_trace.py); null switches it off */
+int vitatk_k_gemm_trace(long long* dev_buf);  /* pair GEMM epilogue timeline (VITATK_GEMM_DBG & 512), scripts/gemm_trace.py */
 int vitatk_k_attention_bwd_trace(long long* trace_dev);
 int vitatk_k_attention_fwd_trace(long long* trace_dev);
 int vitatk_k_attention_bwd(const void* qkv_dev, const void* dout_dev, void* dqkv_dev, int batch, int tokens,

@@ -610,14 +610,18 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int j = 0; j < NP; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
           prefetch_slab1();
           GTR(sl, 4);
+          // One group barrier per slab: buffer c & 1 was last read by the store of slab c - 2, and the issuer only passes
+          // the barrier of slab c - 1 (below) once that store has been read out, so nobody needs to wait here.
           const uint32_t b = c & 1;
-          if (issuer) ptx::tma_store_wait_read<1>();
-          GTR(sl, 5);
-          group_sync();
-          GTR(sl, 6);
           write_row(b, pk);
           GTR(sl, 7);
-          store_slab(b, &tmOut, scol, m0);
+          ptx::fence_proxy_async_smem();
+          if (issuer) ptx::tma_store_wait_read<0>();  // store c - 1: the buffer slab c + 1 will overwrite
+          group_sync();
+          if (issuer && !no_store) {
+            ptx::tma_store_2d(&tmOut, smem_out + g * 2 * SLAB_BYTES + b * SLAB_BYTES, scol, m0);
+            ptx::tma_store_commit();
+          }
           GTR(sl, 10);
           ++c;
         }

@@ -41,14 +41,22 @@ def ncu_traffic_per_launch(kernel_prefix="gemm_tc05_kernel<256"):
     (profiles/*_launches_summary.json, made by scripts/ncu_launch_summary.py); None if no profile is present."""
     import glob
 
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_launches_summary.json")))
+    import re
+
+    def version(path):  # r01_v10_... sorts after r01_v8_...
+        return [int(n) for n in re.findall(r"\d+", os.path.basename(path))]
+
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_launches_summary.json")), key=version)
     if not files:
         return None, None
     try:
         d = json.load(open(files[-1]))["kernels"]
-        for name, k in d.items():
-            if name.startswith(kernel_prefix):
-                return (k["dram_read_mb_per_launch"] + k["dram_write_mb_per_launch"]) * 1e6, os.path.basename(files[-1])
+        # the main GEMM runs as two instantiations (8 / 16 epilogue warps): launch-weighted mean over both
+        ks = [k for name, k in d.items() if name.startswith(kernel_prefix)]
+        n = sum(k["launches"] for k in ks)
+        if n:
+            mb = sum((k["dram_read_mb_per_launch"] + k["dram_write_mb_per_launch"]) * k["launches"] for k in ks) / n
+            return mb * 1e6, os.path.basename(files[-1])
     except Exception:
         pass
     return None, None

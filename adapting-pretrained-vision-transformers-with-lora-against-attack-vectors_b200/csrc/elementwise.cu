@@ -764,6 +764,34 @@ int png_roundtrip(const float* images, float* out, uint8_t* u8_hwc, int batch, c
   return 0;
 }
 
+// One-off (finalize): copy of a LoRA up-projection lb [rows, 64] whose columns col.. carry the consumer GEMM's per-column
+// constants as bf16 hi/lo splits, so the tensor core adds them (rank-1 updates against matching columns of T):
+//   c1 != null: [c1_hi, c1_lo, c1_hi, c2_hi, c2_lo, c2_hi]   (folded LayerNorm; T holds [-mh, -mh, -ml, sh, sh, sl])
+//   c1 == null: [c2_hi, c2_lo]                               (plain bias; T holds [1, 1])
+__global__ void lora_const_columns_kernel(const bf16* __restrict__ lb, const float* __restrict__ c1,
+                                          const float* __restrict__ c2, bf16* __restrict__ out, int rows, int col) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= rows) return;
+  for (int j = 0; j < 64; ++j) out[static_cast<size_t>(n) * 64 + j] = lb[static_cast<size_t>(n) * 64 + j];
+  bf16* o = out + static_cast<size_t>(n) * 64 + col;
+  const float b = c2[n];
+  const bf16 bh = __float2bfloat16(b), bl = __float2bfloat16(b - __bfloat162float(bh));
+  if (c1 != nullptr) {
+    const float a = c1[n];
+    const bf16 ah = __float2bfloat16(a), al = __float2bfloat16(a - __bfloat162float(ah));
+    o[0] = ah; o[1] = al; o[2] = ah; o[3] = bh; o[4] = bl; o[5] = bh;
+  } else {
+    o[0] = bh; o[1] = bl;
+  }
+}
+
+int lora_const_columns(const bf16* lb, const float* c1, const float* c2, bf16* out, int rows, int col,
+                       cudaStream_t stream) {
+  lora_const_columns_kernel<<<(rows + 127) / 128, 128, 0, stream>>>(lb, c1, c2, out, rows, col);
+  VITATK_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int grad_to_image(const bf16* dcols, float* grad, int batch, PixelNorm nrm, float scale, cudaStream_t stream) {
   grad_to_image_kernel<<<pixel_grid(batch), 256, 0, stream>>>(dcols, grad, batch, nrm, scale);
   VITATK_CUDA_OK(cudaGetLastError());

@@ -46,6 +46,13 @@ static constexpr int LORA_PAD = 64;
 struct LoraSite {
   int rank = 0;
   const bf16 *la_fwd = nullptr, *lb_fwd = nullptr, *lb_bwd = nullptr, *la_bwd = nullptr;
+  // Constants through the tensor core (GemmEpilogue::stat_col): engine-owned copy of lb_fwd whose columns ccol.. carry
+  // the site's bias / LayerNorm-fold constants, and (plain-bias sites) the "bias" vector that makes the skinny GEMM
+  // write 1.0 into T's matching columns.  ccol == 0: off (the epilogue loads the constants itself).
+  int ccol = 0;
+  bool cfold = false;
+  const bf16* lbx = nullptr;
+  const float* tones = nullptr;
 };
 
 struct LayerWeights {
@@ -106,6 +113,8 @@ struct vitatk_engine {
   // optional per-launch CUDA-event timing (bench.py's roofline leg; off in the timed region)
   bool attn_bwd_two_kernel = false;  // VITATK_ATTN_BWD=2k selects the older dQ + dK/dV kernel pair
   bool zigzag = true;                // skinny LoRA GEMMs walk M last-to-first (VITATK_ZIGZAG=0: first-to-last)
+  bool tc_const = true;              // bias / fold constants as tensor-core rank-1 updates (VITATK_TC_CONST=0: epilogue loads)
+  char* cbuf = nullptr;              // backing store of the lbx / tones arrays
   bool fuse_stats = true;            // folded LayerNorm: (mean, rstd) come out of the skinny LoRA GEMM (VITATK_FUSE_STATS=0: stats kernel)
   bool fuse_ln_t = false;            // LayerNorm kernels also produce the LoRA x*A^T of the site they feed
   bool fuse_delta = false;           // delta comes out of the proj-backward GEMM epilogue (pair kernel) instead of a kernel
@@ -118,6 +127,8 @@ struct vitatk_engine {
 namespace vitatk {
 
 static int lora_ksteps(int r) { return (r + 15) / 16; }
+// forward k-steps of a site: its rank plus the constant columns the tensor core adds (6 folded, 2 plain bias)
+static int site_ksteps(const LoraSite& s) { return lora_ksteps(s.ccol > 0 ? s.ccol + (s.cfold ? 6 : 2) : s.rank); }
 
 static int build_plans(vitatk_engine* e, int batch, PlanSet** out) {
   auto it = e->plans.find(batch);
@@ -161,7 +172,9 @@ static int build_plans(vitatk_engine* e, int batch, PlanSet** out) {
       if (fold && e->fuse_stats) {  // the skinny GEMM streams h anyway: it also produces LN1's (mean, rstd)
         ep.stats_out = e->st1[l];
         ep.stats_eps = c.ln_eps;
+        if (sq.ccol > 0 && sq.cfold) ep.stat_col = sq.ccol;  // ... and the per-row factors of qkv's constants
       }
+      if (sq.ccol > 0 && !sq.cfold) ep.bias = sq.tones;
       if (sq.rank > 0 &&
           gemm_plan_init(&p.t_qkv, M, 3 * LORA_PAD, D, a_ln1, D, sq.la_fwd, D, e->T, 3 * LORA_PAD, nullptr, 0, nullptr, 0,
                          nullptr, 0, 0, 0, 0, ep))
@@ -174,18 +187,24 @@ static int build_plans(vitatk_engine* e, int batch, PlanSet** out) {
         ep.row_stats = e->st1[l];
         ep.c1 = w.qkv_c1;
       }
+      if (sq.ccol > 0) ep.bias = nullptr, ep.c1 = nullptr;  // the constants ride in the LoRA k-block
       if (gemm_plan_init(&p.qkv, M, 3 * D, D, a_ln1, D, w.qkv_w, D, e->qkv[l], 3 * D, nullptr, 0, e->T, 3 * LORA_PAD,
-                         sq.lb_fwd, LORA_PAD, sq.rank > 0 ? 1 : 0, lora_ksteps(sq.rank), sq.rank > 0 ? D : 0, ep))
+                         sq.ccol > 0 ? sq.lbx : sq.lb_fwd, LORA_PAD, sq.rank > 0 ? 1 : 0, site_ksteps(sq),
+                         sq.rank > 0 ? D : 0, ep))
         return 1;
     }
-    if (sp.rank > 0 &&
-        gemm_plan_init(&p.t_proj, M, LORA_PAD, D, e->ao[l], D, sp.la_fwd, D, e->T, 3 * LORA_PAD, nullptr, 0, nullptr, 0,
-                       nullptr, 0, 0, 0, 0, plain))
-      return 1;
     {
-      GemmEpilogue ep = {EPI_RESIDUAL, w.proj_b, e->h[l], D, nullptr, 0};
+      GemmEpilogue ep = plain;
+      if (sp.ccol > 0) ep.bias = sp.tones;  // T[:, ccol..ccol+1] = 1: proj's bias is added by the tensor core
+      if (sp.rank > 0 &&
+          gemm_plan_init(&p.t_proj, M, LORA_PAD, D, e->ao[l], D, sp.la_fwd, D, e->T, 3 * LORA_PAD, nullptr, 0, nullptr, 0,
+                         nullptr, 0, 0, 0, 0, ep))
+        return 1;
+    }
+    {
+      GemmEpilogue ep = {EPI_RESIDUAL, sp.ccol > 0 ? nullptr : w.proj_b, e->h[l], D, nullptr, 0};
       if (gemm_plan_init(&p.proj, M, D, D, e->ao[l], D, w.proj_w, D, e->h_mid[l], D, nullptr, 0, e->T, 3 * LORA_PAD,
-                         sp.lb_fwd, LORA_PAD, sp.rank > 0 ? 1 : 0, lora_ksteps(sp.rank), 0, ep))
+                         sp.ccol > 0 ? sp.lbx : sp.lb_fwd, LORA_PAD, sp.rank > 0 ? 1 : 0, site_ksteps(sp), 0, ep))
         return 1;
     }
     {
@@ -193,7 +212,9 @@ static int build_plans(vitatk_engine* e, int batch, PlanSet** out) {
       if (fold && e->fuse_stats) {
         ep.stats_out = e->st2[l];
         ep.stats_eps = c.ln_eps;
+        if (s1.ccol > 0 && s1.cfold) ep.stat_col = s1.ccol;
       }
+      if (s1.ccol > 0 && !s1.cfold) ep.bias = s1.tones;
       if (s1.rank > 0 &&
           gemm_plan_init(&p.t_fc1, M, LORA_PAD, D, a_ln2, D, s1.la_fwd, D, e->T, 3 * LORA_PAD, nullptr, 0, nullptr, 0,
                          nullptr, 0, 0, 0, 0, ep))
@@ -207,18 +228,23 @@ static int build_plans(vitatk_engine* e, int batch, PlanSet** out) {
         ep.row_stats = e->st2[l];
         ep.c1 = w.fc1_c1;
       }
-      if (gemm_plan_init(&p.fc1, M, F, D, a_ln2, D, w.fc1_w, D, e->g, F, e->u[l], F, e->T, 3 * LORA_PAD, s1.lb_fwd,
-                         LORA_PAD, s1.rank > 0 ? 1 : 0, lora_ksteps(s1.rank), 0, ep))
+      if (s1.ccol > 0) ep.bias = nullptr, ep.c1 = nullptr;
+      if (gemm_plan_init(&p.fc1, M, F, D, a_ln2, D, w.fc1_w, D, e->g, F, e->u[l], F, e->T, 3 * LORA_PAD,
+                         s1.ccol > 0 ? s1.lbx : s1.lb_fwd, LORA_PAD, s1.rank > 0 ? 1 : 0, site_ksteps(s1), 0, ep))
         return 1;
     }
-    if (s2.rank > 0 &&
-        gemm_plan_init(&p.t_fc2, M, LORA_PAD, F, e->g, F, s2.la_fwd, F, e->T, 3 * LORA_PAD, nullptr, 0, nullptr, 0,
-                       nullptr, 0, 0, 0, 0, plain))
-      return 1;
     {
-      GemmEpilogue ep = {EPI_RESIDUAL, w.fc2_b, e->h_mid[l], D, nullptr, 0};
+      GemmEpilogue ep = plain;
+      if (s2.ccol > 0) ep.bias = s2.tones;
+      if (s2.rank > 0 &&
+          gemm_plan_init(&p.t_fc2, M, LORA_PAD, F, e->g, F, s2.la_fwd, F, e->T, 3 * LORA_PAD, nullptr, 0, nullptr, 0,
+                         nullptr, 0, 0, 0, 0, ep))
+        return 1;
+    }
+    {
+      GemmEpilogue ep = {EPI_RESIDUAL, s2.ccol > 0 ? nullptr : w.fc2_b, e->h_mid[l], D, nullptr, 0};
       if (gemm_plan_init(&p.fc2, M, D, F, e->g, F, w.fc2_w, F, e->h[l + 1], D, nullptr, 0, e->T, 3 * LORA_PAD,
-                         s2.lb_fwd, LORA_PAD, s2.rank > 0 ? 1 : 0, lora_ksteps(s2.rank), 0, ep))
+                         s2.ccol > 0 ? s2.lbx : s2.lb_fwd, LORA_PAD, s2.rank > 0 ? 1 : 0, site_ksteps(s2), 0, ep))
         return 1;
     }
     // ---------------- backward ----------------
@@ -459,10 +485,13 @@ int vitatk_create(const vitatk_config* cfg, vitatk_engine** out) {
     e->zigzag = !(zz && zz[0] == '0');
     const char* fs = getenv("VITATK_FUSE_STATS");
     e->fuse_stats = !(fs && fs[0] == '0');
+    const char* tc = getenv("VITATK_TC_CONST");
+    e->tc_const = !(tc && tc[0] == '0') && !(g2 && g2[0] == '0') && cfg->dim % 256 == 0 && cfg->mlp_dim % 256 == 0;
     const char* flt = getenv("VITATK_FUSE_LN_T");
     // opt-in: measured perf-neutral on B200 (skinny GEMMs -8 ms, LayerNorm kernels +8 ms per PGD-10 step: the legacy
     // mma.sync the LN kernels use for the projection is slow on sm_100)
     e->fuse_ln_t = flt && flt[0] == '1' && cfg->dim == 768;
+    if (e->fuse_ln_t) e->tc_const = false;  // T then comes from the LayerNorm kernels, which write no constant columns
     e->fuse_delta = !e->attn_bwd_two_kernel && !(g2 && g2[0] == '0') && !(fd && fd[0] == '0') && cfg->dim % 256 == 0;
   }
   e->lw.resize(cfg->layers);
@@ -478,6 +507,7 @@ int vitatk_destroy(vitatk_engine* e) {
   if (!e) return 0;
   for (auto& kv : e->plans) delete kv.second;
   if (e->ws) cudaFree(e->ws);
+  if (e->cbuf) cudaFree(e->cbuf);
   delete e;
   return 0;
 }
@@ -692,6 +722,44 @@ int vitatk_finalize(vitatk_engine* e) {
   e->logits = reinterpret_cast<float*>(take(al(static_cast<long long>(c.max_batch) * c.num_classes * 4)));
   e->loss = reinterpret_cast<float*>(take(al(c.max_batch * 4)));
   e->scratch_img = reinterpret_cast<float*>(take(sz_img));
+  if (e->tc_const) {
+    // one engine-owned copy of every forward LoRA up-projection with the consumer's constants in spare columns
+    const int site_rows[4] = {3 * c.dim, c.dim, c.mlp_dim, c.dim};
+    long long bytes = 0;
+    for (int s = 0; s < 4; ++s) bytes += static_cast<long long>(site_rows[s]) * LORA_PAD * 2 + 3 * LORA_PAD * 4;
+    bytes *= c.layers;
+    VITATK_CUDA_OK(cudaMalloc(&e->cbuf, bytes));
+    VITATK_CUDA_OK(cudaMemset(e->cbuf, 0, bytes));
+    char* q = e->cbuf;
+    for (int l = 0; l < c.layers; ++l) {
+      LayerWeights& w = e->lw[l];
+      const bool fold = w.qkv_c1 != nullptr && w.fc1_c1 != nullptr;
+      const float* c1s[4] = {fold ? w.qkv_c1 : nullptr, nullptr, fold ? w.fc1_c1 : nullptr, nullptr};
+      const float* c2s[4] = {w.qkv_b, w.proj_b, w.fc1_b, w.fc2_b};
+      for (int s = 0; s < 4; ++s) {
+        LoraSite& ls = w.lora[s];
+        bf16* lbx = reinterpret_cast<bf16*>(q);
+        q += static_cast<long long>(site_rows[s]) * LORA_PAD * 2;
+        float* ones = reinterpret_cast<float*>(q);
+        q += 3 * LORA_PAD * 4;
+        const bool cf = c1s[s] != nullptr;
+        const int need = cf ? 6 : 2;
+        // folded sites take their per-row factors from the statistics the skinny GEMM computes in-kernel
+        if (ls.rank <= 0 || ls.rank + need > 32 || (cf && !e->fuse_stats)) continue;
+        ls.ccol = ls.rank;
+        ls.cfold = cf;
+        if (lora_const_columns(ls.lb_fwd, c1s[s], c2s[s], lbx, site_rows[s], ls.ccol, nullptr)) return 1;
+        ls.lbx = lbx;
+        if (!cf) {
+          float host_ones[3 * LORA_PAD] = {0};
+          for (int g = 0; g < 3; ++g) host_ones[g * LORA_PAD + ls.ccol] = host_ones[g * LORA_PAD + ls.ccol + 1] = 1.0f;
+          VITATK_CUDA_OK(cudaMemcpy(ones, host_ones, sizeof(host_ones), cudaMemcpyHostToDevice));
+          ls.tones = ones;
+        }
+      }
+    }
+    VITATK_CUDA_OK(cudaDeviceSynchronize());
+  }
   e->finalized = true;
   return 0;
 }

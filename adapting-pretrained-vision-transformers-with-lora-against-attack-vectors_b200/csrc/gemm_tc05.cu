@@ -51,7 +51,8 @@ struct GemmCfg {
   // (128 rows x 64 cols, 128B swizzle) shared by the four warps of a group
   static constexpr int OUT_BYTES = TWO ? 2 * 2 * SLAB_BYTES : NUM_EPI_WARPS * 2 * STAGE_OUT_BYTES;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + OUT_BYTES + BAR_BYTES;
+  static constexpr int STAT_BYTES = TWO ? 0 : BM * 8;  // single kernel: (mean, rstd) of the tile's rows, stats warps -> all
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + OUT_BYTES + BAR_BYTES + STAT_BYTES;
 };
 
 struct GemmKernelArgs {
@@ -470,6 +471,10 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (DBG && (args.dbg & 2048)) {  // timing experiment: per-row scale only, no per-column constants
 #pragma unroll
           for (int j = 0; j < NC; ++j) v[j] *= st.y;
+        } else if (epi.row_stats != nullptr && epi.c1 == nullptr) {
+          // folded LayerNorm with the constants already in the accumulator (tensor-core rank-1 updates): rstd only
+#pragma unroll
+          for (int j = 0; j < NC; ++j) v[j] *= st.y;
         } else if (epi.row_stats != nullptr) {  // LayerNorm folded into this GEMM: acc <- rstd * (acc - mean * c1[n])
           const float nm = -st.x * st.y;
           const float4* cp = reinterpret_cast<const float4*>(epi.c1 + ncol);
@@ -655,6 +660,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int i = 0; i < 4; ++i) aux_next[i] = __ldg(rp + i);
       }
     }
+    float2* stat_sm = reinterpret_cast<float2*>(smem_out + Cfg::OUT_BYTES + Cfg::BAR_BYTES);
     uint32_t scnt = 0;  // k-block counter of the row-statistics warps (same sequence as the producer's)
     for (int tile = unit; tile < num_tiles; tile += num_units, ++it) {
       const int m0 = mblock(tile) * TILE_M + static_cast<int>(rank) * BM;
@@ -693,7 +699,17 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const float inv_k = 1.0f / static_cast<float>(args.K);
         const float md = sd * inv_k;
         const float var = fmaxf(sdd * inv_k - md * md, 0.f);
-        if (m0 + srow < args.M) epi.stats_out[m0 + srow] = make_float2(shift + md, rsqrtf(var + epi.stats_eps));
+        const float2 mr = make_float2(shift + md, rsqrtf(var + epi.stats_eps));
+        if (m0 + srow < args.M) epi.stats_out[m0 + srow] = mr;
+        if (epi.stat_col > 0) stat_sm[srow] = mr;
+      }
+      float2 row_mr = make_float2(0.f, 1.f);
+      if (!TWO && epi.stats_out != nullptr && epi.stat_col > 0) {
+        // all eight epilogue warps need their row's statistics for T's constant columns; the second barrier lets the
+        // statistics warps overwrite stat_sm for the next tile
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+        row_mr = stat_sm[q * 32 + lane];
+        asm volatile("bar.sync 3, 256;" ::: "memory");
       }
       ptx::mbar_wait(&tmem_full[buf], use & 1);
       ptx::tc_fence_after();
@@ -778,6 +794,18 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               v[4 * j + 2] += b.z;
               v[4 * j + 3] += b.w;
             }
+          }
+        }
+        if (!TWO && epi.stats_out != nullptr && epi.stat_col > 0 && ((c & 1) == 0)) {
+          // first chunk of a 64-column group: columns stat_col .. stat_col + 5 become the per-row factors of the
+          // consumer's tensor-core constants (hi / lo bf16 splits keep ~16 mantissa bits)
+          const float sg = 1.0f / row_mr.y;
+          const float mh = __bfloat162float(__float2bfloat16(row_mr.x)), ml = row_mr.x - mh;
+          const float sh = __bfloat162float(__float2bfloat16(sg)), sl = sg - sh;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int k = j - epi.stat_col;
+            if (static_cast<unsigned>(k) < 6u) v[j] = (k < 2) ? -mh : ((k == 2) ? -ml : ((k < 5) ? sh : sl));
           }
         }
         uint32_t packed[16];
@@ -976,6 +1004,15 @@ int gemm_plan_init(GemmPlan* p, int M, int N, int K, const bf16* A, int lda, con
   }
   if (epi.stats_out && (p->two_cta || N != p->BN || lora_nkb != 0)) {
     set_error("gemm_plan_init: row statistics need the single-CTA kernel with one N-tile and no LoRA k-blocks");
+    return 1;
+  }
+  if (epi.stat_col != 0 && (!epi.stats_out || epi.stat_col < 1 || epi.stat_col + 6 > 32)) {
+    set_error("gemm_plan_init: stat_col %d needs stats_out and columns stat_col..stat_col+5 inside the first 32 of a group",
+              epi.stat_col);
+    return 1;
+  }
+  if (epi.row_stats && !epi.c1 && (!p->two_cta || lora_nkb == 0)) {
+    set_error("gemm_plan_init: the scale-only LayerNorm fold needs the pair kernel and a LoRA k-block carrying the constants");
     return 1;
   }
   if (epi.mode == EPI_ROWDOT && (!p->two_cta || !epi.rowdot || epi.rowdot_rows <= 0)) {

@@ -100,6 +100,14 @@ struct GemmEpilogue {
   float* rowdot;        // EPI_ROWDOT side output, [(M / rowdot_rows) * (N / 64), rowdot_pad] fp32
   int rowdot_rows;      // rows per group (tokens per image)
   int rowdot_pad;       // row pitch of the side output (208)
+  // Constants through the tensor core.  A consumer GEMM can take its per-column constants (bias, the LayerNorm-fold
+  // c1 / c2) as rank-1 updates inside its LoRA k-block instead of loading them in the epilogue: LB carries
+  // [c1_hi, c1_lo, c1_hi, c2_hi, c2_lo, c2_hi] in columns stat_col.. of every 64-column group and the producer of T
+  // (the skinny GEMM that computes stats_out) writes the matching per-row factors
+  // [-mean_hi, -mean_hi, -mean_lo, sigma_hi, sigma_hi, sigma_lo] (sigma = 1 / rstd, hi/lo = bf16 split) into T there.
+  // Producer side: stat_col > 0 (with stats_out) enables the write.  Consumer side: row_stats != null && c1 == null
+  // means "scale by rstd only".  0 = off.
+  int stat_col;
 };
 
 struct GemmPlan {
@@ -201,6 +209,9 @@ int pgd_update(const bf16* dcols, const float* x0, float* adv, bf16* cols, int b
                float eps, float alpha, cudaStream_t stream);
 // materialise dL/dx (fp32 NCHW) from the im2col-layout gradient
 int grad_to_image(const bf16* dcols, float* grad, int batch, PixelNorm nrm, float scale, cudaStream_t stream);
+// finalize-time packing of the tensor-core constant columns (GemmEpilogue::stat_col) into a copy of lb [rows, 64]
+int lora_const_columns(const bf16* lb, const float* c1, const float* c2, bf16* out, int rows, int col,
+                       cudaStream_t stream);
 // save_images + reload (Utils.py:106-113): out fp32 NCHW = trunc(clamp(x)*255)/255 and / or the uint8 HWC image itself
 int png_roundtrip(const float* images, float* out, uint8_t* u8_hwc, int batch, cudaStream_t stream);
 // counts[0] += #(argmax(logits)==label), counts[1] += batch

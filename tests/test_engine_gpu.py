@@ -304,3 +304,27 @@ def test_full_size_batch_properties():
     # logits of the full batch equal the small-batch logits row by row
     assert torch.equal(eng.logits(x)[100:103], eng.logits(x[100:103]))
     eng.close()
+
+
+def test_tensor_core_constants_match_epilogue_constants(setup, monkeypatch):
+    """Bias / LayerNorm-fold constants as rank-1 tensor-core updates (default) vs loaded in the epilogue
+    (VITATK_TC_CONST=0).  The two engines round intermediate bf16 activations differently, so they differ from each
+    other by about as much as each differs from the fp32 oracle; the check is that the tensor-core path is not less
+    accurate against the oracle than the epilogue path."""
+    import vitatk
+    from oracle import vit_oracle as vo
+
+    m, eng = setup["lora"]
+    x, y = setup["x"], setup["y"]
+    monkeypatch.setenv("VITATK_TC_CONST", "0")
+    ref = vitatk.Engine(model=m, max_batch=8, device="cuda")
+    monkeypatch.delenv("VITATK_TC_CONST")
+    _, ol, og = vo.input_grad(m, x, y)
+    g0, l0, _ = ref.input_grad(x, y)
+    g1, l1, _ = eng.input_grad(x, y)
+    e_l0, e_l1, e_g0, e_g1 = rel(l0, ol), rel(l1, ol), rel(g0, og), rel(g1, og)
+    msg = f"logits err: epilogue {e_l0:.4f} tensor-core {e_l1:.4f}; grad err: epilogue {e_g0:.4f} tensor-core {e_g1:.4f}"
+    assert e_l1 < RTOL_LOGITS and e_g1 < RTOL_GRAD, msg
+    assert e_l1 < 1.5 * e_l0 + 2e-3 and e_g1 < 1.5 * e_g0 + 2e-3, msg
+    assert rel(l1, l0) < RTOL_LOGITS and cos(g1, g0) > MIN_COS, msg
+    ref.close()

@@ -51,8 +51,7 @@ struct GemmCfg {
   // (128 rows x 64 cols, 128B swizzle) shared by the four warps of a group
   static constexpr int OUT_BYTES = TWO ? 2 * 2 * SLAB_BYTES : NUM_EPI_WARPS * 2 * STAGE_OUT_BYTES;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int STAT_BYTES = TWO ? 0 : BM * 8;  // single kernel: (mean, rstd) of the tile's rows, stats warps -> all
-  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + OUT_BYTES + BAR_BYTES + STAT_BYTES;
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + OUT_BYTES + BAR_BYTES;
 };
 
 struct GemmKernelArgs {
@@ -660,13 +659,13 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int i = 0; i < 4; ++i) aux_next[i] = __ldg(rp + i);
       }
     }
-    float2* stat_sm = reinterpret_cast<float2*>(smem_out + Cfg::OUT_BYTES + Cfg::BAR_BYTES);
     uint32_t scnt = 0;  // k-block counter of the row-statistics warps (same sequence as the producer's)
     for (int tile = unit; tile < num_tiles; tile += num_units, ++it) {
       const int m0 = mblock(tile) * TILE_M + static_cast<int>(rank) * BM;
       const int n0 = (tile % tiles_n) * BN;
       const uint32_t buf = it & 1;
       const uint32_t use = it >> 1;
+      float2 row_mr = make_float2(0.f, 1.f);
       if (!TWO && epi.stats_out != nullptr && hsel == 0) {
         // LayerNorm statistics of this tile's 128 A rows, read from the operand stages as they land (thread = row).
         // Shifted accumulation (d = x - x[0]) keeps the single-pass variance well conditioned when |mean| >> std.
@@ -701,15 +700,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const float var = fmaxf(sdd * inv_k - md * md, 0.f);
         const float2 mr = make_float2(shift + md, rsqrtf(var + epi.stats_eps));
         if (m0 + srow < args.M) epi.stats_out[m0 + srow] = mr;
-        if (epi.stat_col > 0) stat_sm[srow] = mr;
-      }
-      float2 row_mr = make_float2(0.f, 1.f);
-      if (!TWO && epi.stats_out != nullptr && epi.stat_col > 0) {
-        // all eight epilogue warps need their row's statistics for T's constant columns; the second barrier lets the
-        // statistics warps overwrite stat_sm for the next tile
-        asm volatile("bar.sync 3, 256;" ::: "memory");
-        row_mr = stat_sm[q * 32 + lane];
-        asm volatile("bar.sync 3, 256;" ::: "memory");
+        row_mr = mr;
       }
       ptx::mbar_wait(&tmem_full[buf], use & 1);
       ptx::tc_fence_after();
@@ -719,7 +710,10 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 #pragma unroll 1
       for (int i = 0; i < ((DBG && (args.dbg & 16)) ? 0 : CPW); ++i) {
-        const int c = hsel * CPW + i;
+        // T's constant columns live in the first chunk of every 64-column group: with them enabled the chunks are
+        // interleaved so that those (even) chunks all belong to the statistics warps 0..3, which hold (mean, rstd) of
+        // their rows in registers -- no exchange with warps 4..7 needed
+        const int c = (epi.stat_col > 0) ? (2 * i + hsel) : (hsel * CPW + i);
         const int ncol = n0 + c * CHUNK;
         uint32_t r[32];
         ptx::tmem_ld_32x32b_x32(taddr_row + c * CHUNK, r);
@@ -1006,9 +1000,9 @@ int gemm_plan_init(GemmPlan* p, int M, int N, int K, const bf16* A, int lda, con
     set_error("gemm_plan_init: row statistics need the single-CTA kernel with one N-tile and no LoRA k-blocks");
     return 1;
   }
-  if (epi.stat_col != 0 && (!epi.stats_out || epi.stat_col < 1 || epi.stat_col + 6 > 32)) {
-    set_error("gemm_plan_init: stat_col %d needs stats_out and columns stat_col..stat_col+5 inside the first 32 of a group",
-              epi.stat_col);
+  if (epi.stat_col != 0 && (!epi.stats_out || epi.stat_col < 1 || epi.stat_col + 6 > 32 || epi.mode != EPI_PLAIN)) {
+    set_error("gemm_plan_init: stat_col %d needs stats_out, EPI_PLAIN and columns stat_col..stat_col+5 inside the first "
+              "32 of a group", epi.stat_col);
     return 1;
   }
   if (epi.row_stats && !epi.c1 && (!p->two_cta || lora_nkb == 0)) {

@@ -21,6 +21,7 @@
 #include <string.h>
 
 #include <cuda_fp16.h>
+#include <type_traits>
 
 #include "ptx.cuh"
 #include "vitatk_internal.h"
@@ -796,10 +797,20 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const float sg = 1.0f / row_mr.y;
           const float mh = __bfloat162float(__float2bfloat16(row_mr.x)), ml = row_mr.x - mh;
           const float sh = __bfloat162float(__float2bfloat16(sg)), sl = sg - sh;
+          auto fill = [&](auto off) {  // compile-time offset: six register moves
+            constexpr int o = decltype(off)::value;
+            v[o] = -mh; v[o + 1] = -mh; v[o + 2] = -ml; v[o + 3] = sh; v[o + 4] = sh; v[o + 5] = sl;
+          };
+          switch (epi.stat_col) {  // ranks are multiples of 8 in practice
+            case 8: fill(std::integral_constant<int, 8>{}); break;
+            case 16: fill(std::integral_constant<int, 16>{}); break;
+            case 24: fill(std::integral_constant<int, 24>{}); break;
+            default:
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int k = j - epi.stat_col;
-            if (static_cast<unsigned>(k) < 6u) v[j] = (k < 2) ? -mh : ((k == 2) ? -ml : ((k < 5) ? sh : sl));
+              for (int j = 0; j < 32; ++j) {
+                const int k = j - epi.stat_col;
+                if (static_cast<unsigned>(k) < 6u) v[j] = (k < 2) ? -mh : ((k == 2) ? -ml : ((k < 5) ? sh : sl));
+              }
           }
         }
         uint32_t packed[16];

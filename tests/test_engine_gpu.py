@@ -328,3 +328,24 @@ def test_tensor_core_constants_match_epilogue_constants(setup, monkeypatch):
     assert e_l1 < 1.5 * e_l0 + 2e-3 and e_g1 < 1.5 * e_g0 + 2e-3, msg
     assert rel(l1, l0) < RTOL_LOGITS and cos(g1, g0) > MIN_COS, msg
     ref.close()
+
+
+@pytest.mark.parametrize("r", [4, 16, 28])
+def test_other_lora_ranks_vs_oracle(r):
+    """Ranks around the tensor-core-constants limits: r = 4 (generic column fill), r = 16 (constants spill into a second
+    k-step), r = 28 (r + 6 > 32: the engine falls back to epilogue-loaded constants)."""
+    import vitatk
+    from oracle import fixtures as fx
+    from oracle import vit_oracle as vo
+
+    m = fx.make_model(lora=True, r=r)
+    eng = vitatk.Engine(model=m, max_batch=4, device="cuda")
+    x, y = fx.make_inputs()
+    x, y = x.cuda(), y.cuda()
+    m.cuda()
+    g, logits, _ = eng.input_grad(x, y)
+    _, ol, og = vo.input_grad(m, x, y)
+    assert rel(logits, ol) < RTOL_LOGITS, (r, rel(logits, ol))
+    assert rel(g, og) < RTOL_GRAD, (r, rel(g, og))
+    assert cos(g, og) > MIN_COS
+    eng.close()

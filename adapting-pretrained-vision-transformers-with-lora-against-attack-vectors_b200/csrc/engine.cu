@@ -115,6 +115,7 @@ struct vitatk_engine {
   bool zigzag = true;                // skinny LoRA GEMMs walk M last-to-first (VITATK_ZIGZAG=0: first-to-last)
   bool tc_const = true;              // bias / fold constants as tensor-core rank-1 updates (VITATK_TC_CONST=0: epilogue loads)
   char* cbuf = nullptr;              // backing store of the lbx / tones arrays
+  bool const_dirty = true;           // weights / adapters changed since the constant columns were packed
   bool fuse_stats = true;            // folded LayerNorm: (mean, rstd) come out of the skinny LoRA GEMM (VITATK_FUSE_STATS=0: stats kernel)
   bool fuse_ln_t = false;            // LayerNorm kernels also produce the LoRA x*A^T of the site they feed
   bool fuse_delta = false;           // delta comes out of the proj-backward GEMM epilogue (pair kernel) instead of a kernel
@@ -126,11 +127,65 @@ struct vitatk_engine {
 
 namespace vitatk {
 
+// (Re)pack the tensor-core constant columns (LoraSite::lbx / tones) from the current weights and adapters.  Runs at the
+// first use after finalize and again after any vitatk_set_tensor / vitatk_set_lora (they mark the engine dirty).
+static int refresh_const_columns(vitatk_engine* e) {
+  const vitatk_config& c = e->cfg;
+  e->const_dirty = false;
+  for (auto& w : e->lw)
+    for (auto& ls : w.lora) ls.ccol = 0, ls.cfold = false, ls.lbx = nullptr, ls.tones = nullptr;
+  if (!e->tc_const) return 0;
+  const int site_rows[4] = {3 * c.dim, c.dim, c.mlp_dim, c.dim};
+  if (!e->cbuf) {
+    long long bytes = 0;
+    for (int s = 0; s < 4; ++s) bytes += static_cast<long long>(site_rows[s]) * LORA_PAD * 2 + 3 * LORA_PAD * 4;
+    bytes *= c.layers;
+    VITATK_CUDA_OK(cudaMalloc(&e->cbuf, bytes));
+    VITATK_CUDA_OK(cudaMemset(e->cbuf, 0, bytes));
+  }
+  VITATK_CUDA_OK(cudaDeviceSynchronize());  // nothing may still be reading the previous columns
+  char* q = e->cbuf;
+  for (int l = 0; l < c.layers; ++l) {
+    LayerWeights& w = e->lw[l];
+    const bool fold = w.qkv_c1 != nullptr && w.fc1_c1 != nullptr;
+    const float* c1s[4] = {fold ? w.qkv_c1 : nullptr, nullptr, fold ? w.fc1_c1 : nullptr, nullptr};
+    const float* c2s[4] = {w.qkv_b, w.proj_b, w.fc1_b, w.fc2_b};
+    for (int s = 0; s < 4; ++s) {
+      LoraSite& ls = w.lora[s];
+      bf16* lbx = reinterpret_cast<bf16*>(q);
+      q += static_cast<long long>(site_rows[s]) * LORA_PAD * 2;
+      float* ones = reinterpret_cast<float*>(q);
+      q += 3 * LORA_PAD * 4;
+      const bool cf = c1s[s] != nullptr;
+      const int need = cf ? 6 : 2;
+      // folded sites take their per-row factors from the statistics the skinny GEMM computes in-kernel
+      if (ls.rank <= 0 || ls.rank + need > 32 || (cf && !e->fuse_stats)) continue;
+      ls.ccol = ls.rank;
+      ls.cfold = cf;
+      if (lora_const_columns(ls.lb_fwd, c1s[s], c2s[s], lbx, site_rows[s], ls.ccol, nullptr)) return 1;
+      ls.lbx = lbx;
+      if (!cf) {
+        float host_ones[3 * LORA_PAD] = {0};
+        for (int g = 0; g < 3; ++g) host_ones[g * LORA_PAD + ls.ccol] = host_ones[g * LORA_PAD + ls.ccol + 1] = 1.0f;
+        VITATK_CUDA_OK(cudaMemcpy(ones, host_ones, sizeof(host_ones), cudaMemcpyHostToDevice));
+        ls.tones = ones;
+      }
+    }
+  }
+  VITATK_CUDA_OK(cudaDeviceSynchronize());
+  return 0;
+}
+
 static int lora_ksteps(int r) { return (r + 15) / 16; }
 // forward k-steps of a site: its rank plus the constant columns the tensor core adds (6 folded, 2 plain bias)
 static int site_ksteps(const LoraSite& s) { return lora_ksteps(s.ccol > 0 ? s.ccol + (s.cfold ? 6 : 2) : s.rank); }
 
 static int build_plans(vitatk_engine* e, int batch, PlanSet** out) {
+  if (e->const_dirty) {  // (set_tensor / set_lora already dropped the cached plans)
+    for (auto& kv : e->plans) delete kv.second;
+    e->plans.clear();
+    if (refresh_const_columns(e)) return 1;
+  }
   auto it = e->plans.find(batch);
   if (it != e->plans.end()) {
     *out = it->second;
@@ -562,9 +617,10 @@ int vitatk_set_tensor(vitatk_engine* e, int id, int layer, const void* p, long l
     set_error("vitatk_set_tensor: id %d layer %d expects %lld bytes, got %lld", id, layer, want, nbytes);
     return 1;
   }
-  // weights changed -> cached TMA plans are stale
+  // weights changed -> cached TMA plans (and the packed constant columns) are stale
   for (auto& kv : e->plans) delete kv.second;
   e->plans.clear();
+  e->const_dirty = true;
   return 0;
 }
 
@@ -590,6 +646,7 @@ int vitatk_set_lora(vitatk_engine* e, int layer, int site, int rank, const void*
   s.la_bwd = static_cast<const bf16*>(la_bwd);
   for (auto& kv : e->plans) delete kv.second;
   e->plans.clear();
+  e->const_dirty = true;
   return 0;
 }
 
@@ -722,44 +779,7 @@ int vitatk_finalize(vitatk_engine* e) {
   e->logits = reinterpret_cast<float*>(take(al(static_cast<long long>(c.max_batch) * c.num_classes * 4)));
   e->loss = reinterpret_cast<float*>(take(al(c.max_batch * 4)));
   e->scratch_img = reinterpret_cast<float*>(take(sz_img));
-  if (e->tc_const) {
-    // one engine-owned copy of every forward LoRA up-projection with the consumer's constants in spare columns
-    const int site_rows[4] = {3 * c.dim, c.dim, c.mlp_dim, c.dim};
-    long long bytes = 0;
-    for (int s = 0; s < 4; ++s) bytes += static_cast<long long>(site_rows[s]) * LORA_PAD * 2 + 3 * LORA_PAD * 4;
-    bytes *= c.layers;
-    VITATK_CUDA_OK(cudaMalloc(&e->cbuf, bytes));
-    VITATK_CUDA_OK(cudaMemset(e->cbuf, 0, bytes));
-    char* q = e->cbuf;
-    for (int l = 0; l < c.layers; ++l) {
-      LayerWeights& w = e->lw[l];
-      const bool fold = w.qkv_c1 != nullptr && w.fc1_c1 != nullptr;
-      const float* c1s[4] = {fold ? w.qkv_c1 : nullptr, nullptr, fold ? w.fc1_c1 : nullptr, nullptr};
-      const float* c2s[4] = {w.qkv_b, w.proj_b, w.fc1_b, w.fc2_b};
-      for (int s = 0; s < 4; ++s) {
-        LoraSite& ls = w.lora[s];
-        bf16* lbx = reinterpret_cast<bf16*>(q);
-        q += static_cast<long long>(site_rows[s]) * LORA_PAD * 2;
-        float* ones = reinterpret_cast<float*>(q);
-        q += 3 * LORA_PAD * 4;
-        const bool cf = c1s[s] != nullptr;
-        const int need = cf ? 6 : 2;
-        // folded sites take their per-row factors from the statistics the skinny GEMM computes in-kernel
-        if (ls.rank <= 0 || ls.rank + need > 32 || (cf && !e->fuse_stats)) continue;
-        ls.ccol = ls.rank;
-        ls.cfold = cf;
-        if (lora_const_columns(ls.lb_fwd, c1s[s], c2s[s], lbx, site_rows[s], ls.ccol, nullptr)) return 1;
-        ls.lbx = lbx;
-        if (!cf) {
-          float host_ones[3 * LORA_PAD] = {0};
-          for (int g = 0; g < 3; ++g) host_ones[g * LORA_PAD + ls.ccol] = host_ones[g * LORA_PAD + ls.ccol + 1] = 1.0f;
-          VITATK_CUDA_OK(cudaMemcpy(ones, host_ones, sizeof(host_ones), cudaMemcpyHostToDevice));
-          ls.tones = ones;
-        }
-      }
-    }
-    VITATK_CUDA_OK(cudaDeviceSynchronize());
-  }
+  e->const_dirty = true;  // the tensor-core constant columns are packed on first use (refresh_const_columns)
   e->finalized = true;
   return 0;
 }

@@ -349,3 +349,31 @@ def test_other_lora_ranks_vs_oracle(r):
     assert rel(g, og) < RTOL_GRAD, (r, rel(g, og))
     assert cos(g, og) > MIN_COS
     eng.close()
+
+
+def test_weights_can_change_after_finalize():
+    """vitatk_set_tensor after finalize (a new proj bias): cached plans AND the packed tensor-core constant columns are
+    rebuilt, so the engine matches a fresh engine built from the modified model bit for bit."""
+    import vitatk
+    from oracle import fixtures as fx
+    from vitatk import _lib
+    from vitatk.engine import T_PROJ_B
+
+    m = fx.make_model(lora=True)
+    x, _ = fx.make_inputs()
+    x = x.cuda()
+    eng = vitatk.Engine(model=m, max_batch=4, device="cuda")
+    l0 = eng.logits(x)
+    dense = m.vit.encoder.layer[0].attention.output.dense
+    lin = dense.base if hasattr(dense, "base") else dense
+    with torch.no_grad():
+        lin.bias += 0.5
+    nb = lin.bias.detach().float().cuda().contiguous()
+    _lib.check(eng.lib.vitatk_set_tensor(eng._h, T_PROJ_B, 0, nb.data_ptr(), nb.numel() * 4), "set_tensor")
+    l1 = eng.logits(x)
+    fresh = vitatk.Engine(model=m, max_batch=4, device="cuda")
+    l2 = fresh.logits(x)
+    assert torch.equal(l1, l2)
+    assert rel(l1, l0) > 1e-3
+    eng.close()
+    fresh.close()

@@ -1058,6 +1058,15 @@ static bool gemm_epi16_enabled() {
   return v == 1;
 }
 
+static int gemm_epi16_max_k() {  // VITATK_GEMM_EPI16_MAXK: largest K that still gets the 16-warp epilogue (default 1024)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VITATK_GEMM_EPI16_MAXK");
+    v = e ? atoi(e) : 1024;
+  }
+  return v;
+}
+
 static int gemm_dbg_flags() {
   static int dbg = -1;
   if (dbg < 0) {
@@ -1115,7 +1124,8 @@ int gemm_launch(const GemmPlan* p, cudaStream_t stream, int num_sms) {
       // 16 epilogue warps (two per TMEM lane quarter and column group) for the short-K GEMMs, whose epilogue is as long
       // as their main loop (measured: fc1 -7 %, qkv -4 %, proj -4 %, bfc2 -3 %); the K >= 2304 GEMMs are main-loop
       // bound and lose ~3 % to the extra warps, and ROWDOT needs a whole slab row in one thread
-      if (gemm_epi16_enabled() && p->epi.mode != EPI_ROWDOT && p->K <= 1024) return launch_bn<256, true, 2>(p, stream, num_sms);
+      if (gemm_epi16_enabled() && p->epi.mode != EPI_ROWDOT && p->K <= gemm_epi16_max_k())
+        return launch_bn<256, true, 2>(p, stream, num_sms);
       return launch_bn<256, true, 1>(p, stream, num_sms);
     case 192: return launch_bn<192, false>(p, stream, num_sms);
     case 128: return launch_bn<128, false>(p, stream, num_sms);

@@ -222,3 +222,69 @@ def test_adapter_composition_stack_equals_merge(adapter_dirs):
     from vitatk.adapters import read_adapter
     last = read_adapter(dirs[1]).saved["classifier.weight"]
     assert torch.equal(sd_m["classifier.weight"], last) and torch.equal(sd_s["classifier.weight"], last)
+
+
+def test_c_abi_header_is_plain_c():
+    """include/vitatk.h is the drop-in boundary: it must compile as C99 (no C++ or torch types in the signatures)."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    hdr = os.path.join(ROOT, "include", "vitatk.h")
+    r = subprocess.run([gcc, "-x", "c", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", hdr], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    code = re.sub(r"/\*.*?\*/", "", open(hdr).read(), flags=re.S)  # declarations only, comments stripped
+    assert "::" not in code and "Tensor" not in code and "torch" not in code.lower()
+
+
+def test_peft_adapter_config_variants(tmp_path):
+    """alpha_pattern / rank_pattern / use_rslora and the legacy adapter_model.bin are honoured; malformed adapters fail
+    loudly (peft 0.15 LoraConfig fields, train_loras.py:83-90)."""
+    import json
+
+    from vitatk.adapters import compose, read_adapter, write_adapter
+
+    g = torch.Generator().manual_seed(3)
+    q, v = "vit.encoder.layer.0.attention.attention.query", "vit.encoder.layer.0.attention.attention.value"
+    lora = {q: (torch.randn(8, 768, generator=g), torch.randn(768, 8, generator=g), 2.0),
+            v: (torch.randn(4, 768, generator=g), torch.randn(768, 4, generator=g), 4.0)}
+    d = str(tmp_path / "a")
+    with pytest.raises(ValueError):   # scales 2.0 (r=8) and 4.0 (r=4) are both alpha=16, so this is fine ...
+        write_adapter(d, {q: (lora[q][0], lora[q][1], 3.0)}, lora_alpha=16.0)   # ... but 3.0 is not 16/8
+    write_adapter(d, lora, lora_alpha=16.0)
+    cfg_path = os.path.join(d, "adapter_config.json")
+    cfg = json.load(open(cfg_path))
+    assert cfg["r"] == 4 and cfg["rank_pattern"] == {q: 8}  # smallest rank is the default, the others are overrides
+    ad = read_adapter(d)
+    assert ad.lora[q][2] == pytest.approx(2.0) and ad.lora[v][2] == pytest.approx(4.0)
+    # alpha_pattern by module-name suffix, rsLoRA scaling
+    cfg["alpha_pattern"] = {"value": 8}
+    cfg["use_rslora"] = True
+    json.dump(cfg, open(cfg_path, "w"))
+    ad = read_adapter(d)
+    assert ad.lora[q][2] == pytest.approx(16 / 8 ** 0.5) and ad.lora[v][2] == pytest.approx(8 / 4 ** 0.5)
+    # legacy torch checkpoint instead of safetensors
+    from safetensors.torch import load_file
+    st = os.path.join(d, "adapter_model.safetensors")
+    torch.save(dict(load_file(st)), os.path.join(d, "adapter_model.bin"))
+    os.remove(st)
+    ad2 = read_adapter(d)
+    assert torch.equal(ad2.lora[q][0], lora[q][0]) and torch.equal(ad2.lora[v][1], lora[v][1])
+    # failures: missing weights, unpaired A/B, non-LoRA adapter, adapter for a Linear the base model does not have
+    os.remove(os.path.join(d, "adapter_model.bin"))
+    with pytest.raises(FileNotFoundError):
+        read_adapter(d)
+    from safetensors.torch import save_file
+    save_file({f"base_model.model.{q}.lora_A.weight": lora[q][0]}, st)
+    with pytest.raises(ValueError):
+        read_adapter(d)
+    cfg["peft_type"] = "IA3"
+    json.dump(cfg, open(cfg_path, "w"))
+    with pytest.raises(ValueError):
+        read_adapter(d)
+    d2 = str(tmp_path / "b")
+    write_adapter(d2, {"vit.encoder.layer.0.nonexistent": lora[q]}, lora_alpha=16.0)
+    with pytest.raises(KeyError):
+        compose({q + ".weight": torch.zeros(768, 768)}, [d2])

@@ -226,7 +226,8 @@ def test_gemm_rejects_bad_shapes(lib):
         run_gemm(lib, A, B)
 
 
-@pytest.mark.parametrize("batch,tokens", [(1, 197), (3, 197), (2, 50), (1, 208), (2, 1), (2, 128), (2, 100), (2, 129), (2, 192), (64, 197)])
+@pytest.mark.parametrize("batch,tokens", [(1, 197), (3, 197), (2, 50), (1, 208), (2, 1), (2, 128), (2, 100), (2, 129), (2, 192), (64, 197),
+                                          (256, 197)])  # last: BASELINE configs[1] size
 def test_attention_fwd_bwd_vs_torch(lib, batch, tokens):
     from vitatk import _lib
 

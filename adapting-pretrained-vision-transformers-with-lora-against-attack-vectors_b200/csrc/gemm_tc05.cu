@@ -61,11 +61,11 @@ struct GemmKernelArgs {
   GemmEpilogue epi;
   int reverse_m;  // 1: walk the M-blocks from the last to the first (the input was just written in ascending order by the
                   // previous kernel, so its tail is still in L2)
-  int gelu_f32;  // GELU in the pair epilogue: 2 fp32 2^P fit (default), 1 fp32 Abramowitz-Stegun (VITATK_GELU=f32),
-                 // 0 packed half (VITATK_GELU=h2)
+  int gelu_f32;  // GELU in the pair epilogue: 1 = fp32 Abramowitz-Stegun (VITATK_GELU=f32), otherwise the fp32 2^P fit
   int dbg;  // timing experiments (DBG instantiation only, VITATK_GEMM_DBG): 1 no aux loads, 2 no stores,
             // 4 no TMA loads after the first ring fill, 8 no MMA issue, 16 epilogue skips TMEM reads and math,
-            // 32 no staging writes, 64 no bias, 128 no group barriers, 256 no GELU math, 512 epilogue timeline
+            // 32 no staging writes, 64 no bias, 128 no group barriers, 256 no GELU math, 512 epilogue timeline,
+            // 1024 no L1 prefetch of the epilogue constants, 2048 per-row scale only (no per-column constants)
 };
 
 // Exact-erf GELU and its derivative from ONE exponential and ONE reciprocal (Abramowitz-Stegun 7.1.26,
@@ -635,7 +635,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (issuer) ptx::tma_store_wait_all<0>();
     __syncwarp();
   } else {
-    // ================================= epilogue warps 0..7 =================================
+    // ================================= chunk epilogue (single-CTA kernel), warps 0..7 =================================
     // warp w owns TMEM lanes 32*(w%4).. (hardware rule) and column half w/4 of every tile.
     const int q = warp & 3;
     const int hsel = warp >> 2;
@@ -1044,7 +1044,7 @@ static int gemm_gelu_f32() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("VITATK_GELU");
-    v = (e && strcmp(e, "f32") == 0) ? 1 : ((e && strcmp(e, "h2") == 0) ? 0 : 2);  // default: fp32 2^P fit
+    v = (e && strcmp(e, "f32") == 0) ? 1 : 2;  // default: fp32 2^P fit
   }
   return v;
 }

@@ -125,6 +125,77 @@ def test_count_allreduce_world2_gloo():
         assert c == want
 
 
+class _ToyEngine:
+    """CPU stand-in with the engine's evaluation surface (count_correct / png_roundtrip) for the sharding tests."""
+
+    def __init__(self):
+        g = torch.Generator().manual_seed(0)
+        self.w = torch.randn(3 * 8 * 8, 5, generator=g)
+        self.device = torch.device("cpu")
+
+    def logits(self, x):
+        return x.reshape(x.shape[0], -1) @ self.w
+
+    def count_correct(self, images, labels, counts):
+        counts += torch.tensor([int((self.logits(images).argmax(-1) == labels).sum()), labels.numel()])
+        return counts
+
+    def png_roundtrip(self, x):
+        return (torch.clamp(x, 0, 1) * 255).to(torch.uint8).float() / 255
+
+    def attack(self, x, y):  # one signed step on the toy model's CE
+        xr = x.clone().requires_grad_(True)
+        torch.nn.functional.cross_entropy(self.logits(xr), y).backward()
+        return torch.clamp(x + 0.1 * xr.grad.sign(), 0, 1)
+
+
+def _toy_batch():
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(37, 3, 8, 8, generator=g)
+    y = torch.randint(0, 5, (37,), generator=g)
+    return x, y
+
+
+def _worker_robust(rank, world, port, q):
+    import sys
+
+    import torch.distributed as dist
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from vitatk.dist import robust_accuracy_counts, shard_range
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    eng = _ToyEngine()
+    x, y = _toy_batch()
+    lo, hi = shard_range(x.shape[0], rank, world)
+    out = [robust_accuracy_counts(eng, eng.attack, x[lo:hi], y[lo:hi], png_roundtrip=flag).tolist() for flag in (False, True)]
+    q.put((rank, out))
+    dist.destroy_process_group()
+
+
+def test_robust_accuracy_counts_are_sharding_invariant_world2_gloo():
+    """ranks shard the images, one all-reduce of (clean-correct, robust-correct, total); the result equals
+    the single-process count over the whole batch, with and without the uint8 PNG round trip (Utils.py:106-113)."""
+    from vitatk.dist import robust_accuracy_counts
+
+    eng = _ToyEngine()
+    x, y = _toy_batch()
+    want = [robust_accuracy_counts(eng, eng.attack, x, y, png_roundtrip=flag).tolist() for flag in (False, True)]
+    assert want[0][2] == 37 and want[0][1] <= want[0][0]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker_robust, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=120) for _ in ps]
+    for p in ps:
+        p.join(60)
+        assert p.exitcode == 0
+    for _, out in res:
+        assert out == want
+
+
 def test_layernorm_fold_algebra():
     """CPU: the folded-LayerNorm packing (gamma o W, gamma o A, c1, c2) reproduces LN -> Linear (+ LoRA) exactly."""
     import torch

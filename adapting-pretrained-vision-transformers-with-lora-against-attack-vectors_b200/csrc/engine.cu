@@ -15,6 +15,7 @@
 #include <string.h>
 
 #include <map>
+#include <memory>
 #include <vector>
 
 #include "../../include/vitatk.h"
@@ -193,7 +194,8 @@ static int build_plans(vitatk_engine* e, int batch, PlanSet** out) {
   }
   const vitatk_config& c = e->cfg;
   const int M = batch * TOKENS, D = c.dim, F = c.mlp_dim;
-  PlanSet* ps = new PlanSet();
+  std::unique_ptr<PlanSet> owner(new PlanSet());  // released into e->plans on success, freed on any early return
+  PlanSet* ps = owner.get();
   ps->batch = batch;
   ps->layers.resize(c.layers);
   ps->attn_fwd.resize(c.layers);
@@ -361,7 +363,7 @@ static int build_plans(vitatk_engine* e, int batch, PlanSet** out) {
       for (GemmPlan* g : {&p.t_qkv, &p.t_proj, &p.t_fc1, &p.t_fc2, &p.bt_fc2, &p.bt_fc1, &p.bt_proj, &p.bt_qkv})
         g->reverse_m = 1;
   }
-  e->plans[batch] = ps;
+  e->plans[batch] = owner.release();
   *out = ps;
   return 0;
 }
@@ -563,6 +565,11 @@ int vitatk_destroy(vitatk_engine* e) {
   for (auto& kv : e->plans) delete kv.second;
   if (e->ws) cudaFree(e->ws);
   if (e->cbuf) cudaFree(e->cbuf);
+  for (auto& r : e->prof_recs) {  // profiling events (bench.py's roofline leg)
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  for (cudaEvent_t ev : e->prof_pool) cudaEventDestroy(ev);
   delete e;
   return 0;
 }

@@ -53,3 +53,27 @@ def adapter_dirs(tmp_path):
         write_adapter(d, lora, saved, lora_alpha=16.0)
         dirs.append(d)
     return base, dirs
+
+
+@pytest.fixture(scope="session")
+def c_example():
+    """Compile examples/pgd_c_abi.c (plain C99, only include/vitatk.h + the CUDA runtime) against libvitatk.so."""
+    import shutil
+    import subprocess
+
+    from vitatk import _lib
+
+    gcc = shutil.which("gcc")
+    cuda = "/usr/local/cuda"
+    if gcc is None or not os.path.exists(os.path.join(cuda, "include", "cuda_runtime_api.h")):
+        pytest.skip("gcc or the CUDA runtime headers are not available")
+    if _lib.needs_build():
+        _lib.build()
+    pkg = os.path.dirname(_lib.LIB_PATH)
+    exe = os.path.join(ROOT, "examples", "pgd_c_abi")
+    cmd = [gcc, "-O2", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(cuda, "include"),
+           os.path.join(ROOT, "examples", "pgd_c_abi.c"), "-o", exe, "-L", pkg, "-lvitatk", "-L", os.path.join(cuda, "lib64"),
+           "-lcudart", "-lm", f"-Wl,-rpath,{pkg}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe

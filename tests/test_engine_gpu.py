@@ -377,3 +377,13 @@ def test_weights_can_change_after_finalize():
     assert rel(l1, l0) > 1e-3
     eng.close()
     fresh.close()
+
+
+def test_c_host_program_runs_the_attack_without_python_or_torch(c_example):
+    """examples/pgd_c_abi.c: create / set_tensor / finalize / attack / count through the C ABI from a plain C program;
+    it checks ||delta||_inf <= eps, range, determinism and batch independence itself (exit code 0 = all hold)."""
+    import subprocess
+
+    r = subprocess.run([c_example], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "OK" in r.stdout

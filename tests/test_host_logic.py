@@ -359,3 +359,7 @@ def test_peft_adapter_config_variants(tmp_path):
     write_adapter(d2, {"vit.encoder.layer.0.nonexistent": lora[q]}, lora_alpha=16.0)
     with pytest.raises(KeyError):
         compose({q + ".weight": torch.zeros(768, 768)}, [d2])
+
+
+def test_c_host_example_links_against_the_abi(c_example):
+    assert os.path.exists(c_example)

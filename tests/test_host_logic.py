@@ -363,3 +363,35 @@ def test_peft_adapter_config_variants(tmp_path):
 
 def test_c_host_example_links_against_the_abi(c_example):
     assert os.path.exists(c_example)
+
+
+def test_wrapper_peeling_and_attack_object_defaults():
+    """Host logic of the drop-in surface that needs no GPU: LogitsModel / NormalizedModel peeling (patch_attack.py:16-44),
+    torchattacks-shaped defaults, get_model_output (whitebox_attacks.py:13-19)."""
+    import vitatk
+    from vitatk.attacks import _unwrap
+
+    core = torch.nn.Linear(4, 2)
+    mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+    wrapped = vitatk.NormalizedModel(vitatk.LogitsModel(core), mean, std)
+    m, mu, sd = _unwrap(wrapped)
+    assert m is core and mu == pytest.approx(mean) and sd == pytest.approx(std)
+    m, mu, sd = _unwrap(vitatk.LogitsModel(core))
+    assert m is core and mu is None and sd is None
+
+    class Out:
+        logits = torch.ones(2, 3)
+
+    assert vitatk.get_model_output(Out()) is Out.logits
+    assert vitatk.get_model_output({"logits": 5}) == 5
+    t = torch.zeros(1)
+    assert vitatk.get_model_output(t) is t
+    atk = vitatk.PGD(wrapped, eps=8 / 255, alpha=2 / 255, steps=10, random_start=True)
+    assert list(atk._mean) == pytest.approx(mean)          # read from the NormalizedModel wrapper
+    atk2 = vitatk.PGD(core)
+    assert list(atk2._mean) == [0.0, 0.0, 0.0] and list(atk2._std) == [1.0, 1.0, 1.0]   # torchattacks default
+    atk2.set_normalization_used(mean, std)
+    assert list(atk2._std) == pytest.approx(std)
+    if not torch.cuda.is_available():
+        with pytest.raises(Exception):
+            atk(torch.rand(1, 3, 224, 224), torch.zeros(1, dtype=torch.long))      # no CPU fallback: must raise

@@ -115,13 +115,17 @@ __global__ void __launch_bounds__(256) ln_stats_kernel(const bf16* __restrict__ 
 template <int CH>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                                                      const float2* __restrict__ stats, const float* __restrict__ gamma,
-                                                     const bf16* __restrict__ dres, bf16* __restrict__ dx, int rows) {
+                                                     const bf16* __restrict__ dres, bf16* __restrict__ dx, int rows,
+                                                     int streaming) {
   pdl_wait();
   pdl_launch_dependents();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
   constexpr int COLS = CH * 256;
+  // the three inputs are read exactly once: with `streaming` they are loaded evict-first (ld.global.cs) so that they do
+  // not push the freshly written output -- which the next two kernels read -- out of L2
+  auto ld = [&](const uint4* p) { return streaming ? __ldcs(p) : __ldg(p); };
   const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * COLS);
   const uint4* dyr = reinterpret_cast<const uint4*>(dy + static_cast<size_t>(row) * COLS);
   const float2 st = stats[row];
@@ -131,8 +135,8 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
   for (int i = 0; i < CH; ++i) {
     const int c = (lane + 32 * i) * 8;
     float xv[8], dv[8];
-    unpack8(__ldg(xr + lane + 32 * i), xv);
-    unpack8(__ldg(dyr + lane + 32 * i), dv);
+    unpack8(ld(xr + lane + 32 * i), xv);
+    unpack8(ld(dyr + lane + 32 * i), dv);
     const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c));
     const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
     const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
@@ -152,7 +156,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
   for (int i = 0; i < CH; ++i) {
     float o[8];
     float r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (rr) unpack8(__ldg(rr + lane + 32 * i), r);
+    if (rr) unpack8(ld(rr + lane + 32 * i), r);
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = r[j] + st.y * (gd[i][j] - m1 - xh[i][j] * m2);
     dxr[lane + 32 * i] = pack8(o);
@@ -426,11 +430,16 @@ int layernorm_stats(const bf16* x, float2* stats, int rows, int cols, float eps,
 int layernorm_bwd(const bf16* dy, const bf16* x, const float2* stats, const float* gamma, const bf16* dres,
                   bf16* dx_out, int rows, int cols, cudaStream_t stream) {
   const int grid = (rows + 7) / 8;
+  static int streaming = -1;
+  if (streaming < 0) {
+    const char* e = getenv("VITATK_LN_STREAM");
+    streaming = (e && e[0] == '0') ? 0 : 1;
+  }
   switch (cols) {
-    case 768: VITATK_CUDA_OK(launch_pdl(ln_bwd_kernel<3>, dim3(grid), dim3(256), 0, stream, 1, dy, x, stats, gamma, dres, dx_out, rows)); break;
-    case 1024: VITATK_CUDA_OK(launch_pdl(ln_bwd_kernel<4>, dim3(grid), dim3(256), 0, stream, 1, dy, x, stats, gamma, dres, dx_out, rows)); break;
-    case 512: VITATK_CUDA_OK(launch_pdl(ln_bwd_kernel<2>, dim3(grid), dim3(256), 0, stream, 1, dy, x, stats, gamma, dres, dx_out, rows)); break;
-    case 256: VITATK_CUDA_OK(launch_pdl(ln_bwd_kernel<1>, dim3(grid), dim3(256), 0, stream, 1, dy, x, stats, gamma, dres, dx_out, rows)); break;
+    case 768: VITATK_CUDA_OK(launch_pdl(ln_bwd_kernel<3>, dim3(grid), dim3(256), 0, stream, 1, dy, x, stats, gamma, dres, dx_out, rows, streaming)); break;
+    case 1024: VITATK_CUDA_OK(launch_pdl(ln_bwd_kernel<4>, dim3(grid), dim3(256), 0, stream, 1, dy, x, stats, gamma, dres, dx_out, rows, streaming)); break;
+    case 512: VITATK_CUDA_OK(launch_pdl(ln_bwd_kernel<2>, dim3(grid), dim3(256), 0, stream, 1, dy, x, stats, gamma, dres, dx_out, rows, streaming)); break;
+    case 256: VITATK_CUDA_OK(launch_pdl(ln_bwd_kernel<1>, dim3(grid), dim3(256), 0, stream, 1, dy, x, stats, gamma, dres, dx_out, rows, streaming)); break;
     default: set_error("layernorm_bwd: cols=%d unsupported", cols); return 1;
   }
   VITATK_CUDA_OK(cudaGetLastError());

@@ -14,7 +14,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libvitatk.so")
 INCLUDE_DIR = os.path.join(os.path.dirname(PKG_DIR), "include")
-SOURCES = ["gemm_tc05.cu", "attention.cu", "attention_tc05.cu", "attention_bwd_fused.cu", "elementwise.cu", "engine.cu"]
+SOURCES = ["gemm_tc05.cu", "attention_tc05.cu", "attention_bwd_fused.cu", "elementwise.cu", "engine.cu"]
 HEADERS = ["ptx.cuh", "vitatk_internal.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -46,6 +46,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB_PATH
     nvcc = _nvcc()
+    flags = list(NVCC_FLAGS)
+    if os.environ.get("VITATK_DBG_BUILD") == "1":  # timing-experiment instantiations + in-kernel timelines (scripts/*_trace.py)
+        flags.append("-DVITATK_DBG_KERNELS")
     objdir = os.path.join(PKG_DIR, "build")
     os.makedirs(objdir, exist_ok=True)
     procs = []
@@ -53,7 +56,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
         objs.append(obj)
-        cmd = [nvcc] + NVCC_FLAGS + ["-I", INCLUDE_DIR, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc] + flags + ["-I", INCLUDE_DIR, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             print(" ".join(cmd))
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -74,11 +77,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
 EXPORTS = [
     "vitatk_last_error", "vitatk_version", "vitatk_create", "vitatk_destroy", "vitatk_set_tensor", "vitatk_set_lora",
     "vitatk_set_normalization", "vitatk_finalize", "vitatk_workspace_bytes", "vitatk_forward", "vitatk_input_grad", "vitatk_vjp", "vitatk_png_roundtrip",
-    "vitatk_attack", "vitatk_count_correct", "vitatk_launch_count", "vitatk_k_gemm", "vitatk_k_attention_fwd",
-    "vitatk_k_attention_bwd", "vitatk_k_layernorm_fwd", "vitatk_k_layernorm_bwd", "vitatk_k_pgd_update",
+    "vitatk_attack", "vitatk_count_correct", "vitatk_launch_count", "vitatk_k_gemm", "vitatk_k_layernorm_fwd", "vitatk_k_layernorm_bwd", "vitatk_k_pgd_update",
     "vitatk_k_pgd_init", "vitatk_profile_begin", "vitatk_profile_end", "vitatk_k_attention_fwd_tc05",
-    "vitatk_k_attention_bwd_tc05", "vitatk_k_attention_bwd_fused", "vitatk_k_gemm_trace", "vitatk_k_attention_bwd_trace",
-    "vitatk_k_attention_fwd_trace", "vitatk_k_layernorm_fwd_t", "vitatk_k_layernorm_bwd_t", "vitatk_k_layernorm_stats",
+    "vitatk_k_attention_bwd_fused", "vitatk_k_gemm_trace", "vitatk_k_attention_bwd_trace",
+    "vitatk_k_attention_fwd_trace", "vitatk_k_layernorm_stats",
 ]
 
 
@@ -124,20 +126,15 @@ def load() -> C.CDLL:
     lib.vitatk_count_correct.argtypes = [vp, vp, vp, i, vp, vp]
     lib.vitatk_profile_begin.argtypes = [vp]
     lib.vitatk_profile_end.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(ll)]
-    lib.vitatk_k_gemm.argtypes = [i, i, i, vp, i, vp, i, vp, i, vp, i, vp, i, vp, i, i, i, i, i, vp, vp, i, vp, i, vp, i, i, vp, vp, vp, f, i, vp]
-    lib.vitatk_k_attention_fwd.argtypes = [vp, vp, i, i, i, vp]
+    lib.vitatk_k_gemm.argtypes = [i, i, i, vp, i, vp, i, vp, i, vp, i, vp, i, vp, i, i, i, i, i, vp, vp, i, vp, i, vp, i, i, vp, vp, vp, f, vp]
     lib.vitatk_k_attention_fwd_tc05.argtypes = [vp, vp, vp, i, i, i, vp]
-    lib.vitatk_k_attention_bwd_tc05.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, vp]
     lib.vitatk_k_attention_bwd_fused.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, vp]
     lib.vitatk_k_gemm_trace.argtypes = [vp]
     lib.vitatk_k_attention_bwd_trace.argtypes = [vp]
     lib.vitatk_k_attention_fwd_trace.argtypes = [vp]
-    lib.vitatk_k_attention_bwd.argtypes = [vp, vp, vp, i, i, i, vp]
     lib.vitatk_k_layernorm_fwd.argtypes = [vp, vp, vp, vp, vp, i, i, f, vp]
     lib.vitatk_k_layernorm_bwd.argtypes = [vp, vp, vp, vp, vp, vp, i, i, vp]
     lib.vitatk_k_layernorm_stats.argtypes = [vp, vp, i, i, f, vp]
-    lib.vitatk_k_layernorm_fwd_t.argtypes = [vp, vp, vp, vp, vp, i, i, f, vp, i, i, vp, i, vp]
-    lib.vitatk_k_layernorm_bwd_t.argtypes = [vp, vp, vp, vp, vp, vp, i, i, vp, i, i, vp, i, vp]
     lib.vitatk_k_pgd_update.argtypes = [vp, vp, vp, vp, i, C.POINTER(f), C.POINTER(f), f, f, vp]
     lib.vitatk_k_pgd_init.argtypes = [vp, vp, vp, vp, i, C.POINTER(f), C.POINTER(f), f, i, u64, u64, vp]
     for name in EXPORTS:

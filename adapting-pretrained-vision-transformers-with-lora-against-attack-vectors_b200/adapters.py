@@ -80,6 +80,8 @@ def read_adapter(path: str) -> PeftAdapter:
         config = json.load(f)
     if str(config.get("peft_type", "LORA")).upper() != "LORA":
         raise ValueError(f"{path}: peft_type {config.get('peft_type')} is not LORA")
+    if config.get("use_dora"):
+        raise ValueError(f"{path}: use_dora adapters (weight-decomposed LoRA) are not supported by the engine")
     st = os.path.join(path, WEIGHTS_NAME)
     if os.path.exists(st):
         from safetensors.torch import load_file
@@ -97,7 +99,11 @@ def read_adapter(path: str) -> PeftAdapter:
         if m:
             (As if m.group(2) == "A" else Bs)[m.group(1)] = t.float().clone()  # clone: do not keep the file mapped
             continue
-        if "lora_" in k or ".original_module." in k:
+        if "lora_" in k:
+            # lora_magnitude_vector (DoRA), lora_embedding_*, lora_bias ...: silently dropping them would attack a
+            # different function than the one peft runs
+            raise ValueError(f"{path}: unsupported LoRA tensor '{key}' (only lora_A / lora_B weights are implemented)")
+        if ".original_module." in k:
             continue
         k = re.sub(r"\.modules_to_save(\.[^.]+)?\.(weight|bias)$", r".\2", k)
         ad.saved[k] = t.float().clone()

@@ -25,7 +25,7 @@ from typing import Optional, Sequence
 
 import torch
 
-from .engine import IMAGENET_MEAN, IMAGENET_STD, Engine
+from .engine import IMAGENET_MEAN, IMAGENET_STD, Engine, model_fingerprint
 
 
 def get_model_output(outputs):
@@ -82,10 +82,17 @@ def _unwrap(model):
 
 
 def compile_model(model: torch.nn.Module, max_batch: int = 256, device=None, force: bool = False) -> Engine:
-    """Pack ``model`` (frozen weights + adapters) into an engine; cached on the module object."""
+    """Pack ``model`` (frozen weights + adapters) into an engine; cached on the module object.
+
+    The cache is keyed by :func:`vitatk.engine.model_fingerprint` (parameter storage + in-place version counters + peft
+    adapter state), so fine-tuning steps, ``load_state_dict``, ``set_adapter`` / ``merge_adapter`` ... between two attacks
+    re-pack the engine instead of silently attacking stale weights.  ``invalidate(model)`` drops the cache explicitly."""
     core, mean, std = _unwrap(model)
     eng: Optional[Engine] = getattr(core, "_vitatk_engine", None)
-    if force or eng is None or eng.max_batch < max_batch:
+    fp = model_fingerprint(core)
+    if eng is not None and getattr(eng, "_h", None) is not None and not eng._h.value:
+        eng = None  # closed by the caller
+    if force or eng is None or eng.max_batch < max_batch or getattr(core, "_vitatk_fingerprint", None) != fp:
         if eng is not None:
             eng.close()
         if core.training:
@@ -93,25 +100,40 @@ def compile_model(model: torch.nn.Module, max_batch: int = 256, device=None, for
                                "whitebox_attacks.py:99; dropout is not part of the attack path)")
         eng = Engine(model=core, max_batch=max_batch, device=device)
         object.__setattr__(core, "_vitatk_engine", eng)
+        object.__setattr__(core, "_vitatk_fingerprint", fp)
     if mean is not None:
         eng.set_normalization(mean, std)
     return eng
 
 
+def invalidate(model: torch.nn.Module) -> None:
+    """Drop the engine cached on ``model`` (the next attack re-packs the weights)."""
+    core, _, _ = _unwrap(model)
+    eng = getattr(core, "_vitatk_engine", None)
+    if eng is not None:
+        eng.close()
+        object.__setattr__(core, "_vitatk_engine", None)
+        object.__setattr__(core, "_vitatk_fingerprint", None)
+
+
 class _EngineLogits(torch.autograd.Function):
-    """logits = engine(images) with d/d images supplied by the engine's backward kernels (``vitatk_vjp``)."""
+    """logits = engine(images) with d/d images supplied by the engine's backward kernels (``vitatk_vjp``).  The
+    normalisation constants travel with the autograd node: another wrapper sharing the cached engine may have changed
+    them between this node's forward and backward."""
 
     @staticmethod
-    def forward(ctx, images, eng):
-        ctx.eng = eng
+    def forward(ctx, images, eng, mean, std):
+        ctx.eng, ctx.mean, ctx.std = eng, tuple(mean), tuple(std)
         ctx.save_for_backward(images)
+        eng.set_normalization(mean, std)
         return eng.logits(images).to(images.device)
 
     @staticmethod
     def backward(ctx, dlogits):
         (images,) = ctx.saved_tensors
+        ctx.eng.set_normalization(ctx.mean, ctx.std)
         grad, _ = ctx.eng.vjp(images, dlogits)
-        return grad.to(images.device), None
+        return grad.to(images.device), None, None, None
 
 
 class EngineModule(torch.nn.Module):
@@ -136,8 +158,7 @@ class EngineModule(torch.nn.Module):
 
     def forward(self, x):
         eng = compile_model(self._wrapped[0], max_batch=max(self._max_batch, int(x.shape[0])))
-        eng.set_normalization(self._mean, self._std)
-        return _EngineLogits.apply(x, eng)
+        return _EngineLogits.apply(x, eng, self._mean, self._std)
 
 
 def _as_list(t, default):
@@ -157,9 +178,16 @@ def batched_fgsm_attack(model, images, labels, epsilon, mean, std):
 
 
 class _Attack:
-    def __init__(self, model, max_batch: int = 0):
+    def __init__(self, model, max_batch: int = 0, torchattacks_inverse_normalize: bool = False):
         self.model = model
         self._max_batch = max_batch
+        # SURVEY 8(c) hazard, OFF by default: torchattacks' ``set_normalization_used`` means "the inputs are already
+        # normalised" -- it runs the attack on x*std + mean and returns (adv - mean) / std.  Fed the reference's
+        # UN-normalised [0,1] batches (whitebox_attacks.py:129-133,169-170) the model therefore sees x + delta/std and the
+        # returned tensor is x + delta/std (clamped to [0,1] only later by save_images, Utils.py:108).  True reproduces
+        # exactly that with two element-wise host ops around the engine's loop; False keeps the FGSM-consistent meaning
+        # (normalise inside the graph, ||delta||_inf <= eps in pixel space).
+        self._inverse_normalize = bool(torchattacks_inverse_normalize)
         self._mean: Sequence[float] = (0.0, 0.0, 0.0)  # torchattacks default: model takes [0,1] input
         self._std: Sequence[float] = (1.0, 1.0, 1.0)
         _, m, s = _unwrap(model)
@@ -176,14 +204,20 @@ class _Attack:
         return eng
 
     def __call__(self, images, labels):
-        return self.forward(images, labels)
+        if not self._inverse_normalize:
+            return self.forward(images, labels)
+        mean = torch.tensor(self._mean, device=images.device, dtype=images.dtype).view(1, 3, 1, 1)
+        std = torch.tensor(self._std, device=images.device, dtype=images.dtype).view(1, 3, 1, 1)
+        shifted = torch.clamp(images * std + mean, 0, 1)  # torchattacks.Attack.inverse_normalize
+        return (self.forward(shifted, labels) - mean) / std  # torchattacks.Attack.normalize
+
 
 
 class FGSM(_Attack):
     """torchattacks.FGSM-shaped (whitebox_attacks.py:110)."""
 
-    def __init__(self, model, eps=8 / 255, max_batch: int = 0):
-        super().__init__(model, max_batch)
+    def __init__(self, model, eps=8 / 255, max_batch: int = 0, torchattacks_inverse_normalize: bool = False):
+        super().__init__(model, max_batch, torchattacks_inverse_normalize)
         self.eps = eps
 
     def forward(self, images, labels):
@@ -200,8 +234,8 @@ class PGD(_Attack):
     """
 
     def __init__(self, model, eps=8 / 255, alpha=2 / 255, steps=10, random_start=True, rng: str = "torch",
-                 seed: int = 0, max_batch: int = 0):
-        super().__init__(model, max_batch)
+                 seed: int = 0, max_batch: int = 0, torchattacks_inverse_normalize: bool = False):
+        super().__init__(model, max_batch, torchattacks_inverse_normalize)
         self.eps, self.alpha, self.steps, self.random_start = eps, alpha, steps, random_start
         self.rng, self.seed = rng, seed
 

@@ -112,8 +112,14 @@ __global__ void __launch_bounds__(F_THREADS, 1)
 attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_constant__ CUtensorMap tmQ208,
                       const __grid_constant__ CUtensorMap tmDO208, const __grid_constant__ CUtensorMap tmOut,
                       const float* __restrict__ lse2, const float* __restrict__ delta, int tokens, int heads,
-                      int num_items, float sl2, float scale, int dbg) {
-  // dbg (VITATK_ATTN_DBG, timing experiments only): 1 no accumulator read-out, 2 no element-wise math,
+                      int num_items, float sl2, float scale, int dbg_arg) {
+#ifdef VITATK_DBG_KERNELS
+  const int dbg = dbg_arg;
+#else
+  constexpr int dbg = 0;  // the product build carries no timing-experiment branches
+  (void)dbg_arg;
+#endif
+  // dbg (VITATK_ATTN_DBG with -DVITATK_DBG_KERNELS, timing experiments only): 1 no accumulator read-out, 2 no element-wise math,
   // 4 no dS^T smem tile / dK / dQ MMAs, 8 no X/Y/dV MMAs, 16 no delta, 32 timeline, 64 no statistics loads.
   // Measured (B = 256): 276 us; without the statistics loads 270; without ANY element-wise math 225 -- the kernel is
   // bound by the MMA-issue / mbarrier hand-off chain of its 64-query steps, not by the element-wise work.
@@ -543,16 +549,20 @@ int attention_delta(const AttnBwdPlan* p, cudaStream_t stream);  // attention_tc
 
 // timing experiments: device buffer of 2 * 2048 * 2 int64 receiving CTA 0's event timeline (with VITATK_ATTN_DBG & 32)
 int attention_bwd_set_trace(long long* dev_buf) {
+#ifdef VITATK_DBG_KERNELS
   VITATK_CUDA_OK(cudaMemcpyToSymbol(g_trace, &dev_buf, sizeof(dev_buf)));
   return 0;
+#else
+  (void)dev_buf;
+  set_error("attention_bwd_set_trace: build with -DVITATK_DBG_KERNELS (VITATK_DBG_BUILD=1) for the in-kernel timeline");
+  return 1;
+#endif
 }
 
 int attention_bwd_fused(const AttnBwdPlan* p, cudaStream_t stream, bool compute_delta) {
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce once;
+  if (once.need())
     VITATK_CUDA_OK(cudaFuncSetAttribute(attn_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM));
-    attr = true;
-  }
   const float scale = 1.0f / sqrtf(static_cast<float>(HD));
   const float sl2 = scale * 1.4426950408889634f;
   int dev = 0, sms = 148;

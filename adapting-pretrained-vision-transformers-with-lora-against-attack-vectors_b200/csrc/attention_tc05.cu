@@ -88,8 +88,15 @@ __device__ __forceinline__ void stage_store_64(uint8_t* stage, const uint32_t (&
 __global__ void __launch_bounds__(A_THREADS, 1)
 attn_fwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                      const __grid_constant__ CUtensorMap tmO, float* __restrict__ lse2, int tokens, int heads,
-                     int num_items, float sl2, int trace_on) {
+                     int num_items, float sl2, int trace_arg) {
+#ifdef VITATK_DBG_KERNELS
+  const int trace_on = trace_arg;
+#else
+  constexpr int trace_on = 0;  // the product build carries no timing-experiment branches
+  (void)trace_arg;
+#endif
   int tr_idx = 0;
+  (void)tr_idx;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A_OUT_OFF + 8 * 4096);
@@ -347,16 +354,20 @@ int attention_fwd_plan_init(AttnFwdPlan* p, const bf16* qkv, bf16* out, float* l
 }
 
 int attention_fwd_set_trace(long long* dev_buf) {
+#ifdef VITATK_DBG_KERNELS
   VITATK_CUDA_OK(cudaMemcpyToSymbol(g_fwd_trace, &dev_buf, sizeof(dev_buf)));
   return 0;
+#else
+  (void)dev_buf;
+  set_error("attention_fwd_set_trace: build with -DVITATK_DBG_KERNELS (VITATK_DBG_BUILD=1) for the in-kernel timeline");
+  return 1;
+#endif
 }
 
 int attention_fwd_tc05(const AttnFwdPlan* p, cudaStream_t stream) {
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce once;
+  if (once.need())
     VITATK_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A_SMEM));
-    attr = true;
-  }
   const float sl2 = 1.4426950408889634f / sqrtf(static_cast<float>(A_HD));
   static int trace_on = -1;
   if (trace_on < 0) {
@@ -374,323 +385,11 @@ int attention_fwd_tc05(const AttnFwdPlan* p, cudaStream_t stream) {
 
 
 // =================================================================================================
-// Backward (input gradients), two persistent tcgen05 kernels that never transpose through shared memory:
-//   attn_bwd_kernel<0>  work item = (image, head, 128-query tile):  S = Q K^T, dP = dO V^T  ->
-//                       dS = P o (dP - delta) / sqrt(d)  (bf16, written back to TMEM)  ->  dQ = dS K   (TS MMA)
-//   attn_bwd_kernel<1>  work item = (image, head, 128-key tile):    S^T = K Q^T, dP^T = V dO^T  ->
-//                       P^T and dS^T (bf16 in TMEM)  ->  dV = P^T dO,  dK = dS^T Q             (TS MMAs)
-//   attn_delta_kernel   delta_i = sum_d dO[i,d] O[i,d] per (image, head, query), shared by both
-// The softmax statistics come from the forward (lse2, log2 domain).  Eight element-wise warps split every tile
-// by columns (no row reductions are needed in the backward), the next item's operands are prefetched by TMA.
-// Zero-filled operand rows (>= T) make every padded row/column contribute exactly zero, so no masks are needed.
-// Replaces the autograd backward of HF attention (HF modeling_vit.py:185-193) w.r.t. q, k, v.
+// Backward-side helpers shared with attention_bwd_fused.cu: the delta kernel (only used when the proj-backward GEMM
+// epilogue does not produce delta) and the tensor maps of the fused single-pass backward.
 // =================================================================================================
-static constexpr int B_THREADS = 320;
-static constexpr int B_TMA_WARP = 8, B_MMA_WARP = 9;
-static constexpr int B_A_BYTES = 128 * 128;                               // one 128-row operand tile
-static constexpr int B_STATS_OFF = 2 * B_A_BYTES + 2 * KV_BYTES;          // lse2 row, then delta row (1 KB apart)
-static constexpr int B_STATS_BYTES = A_TPAD * 4;                          // 832
-static constexpr int B_STAGE_BYTES = B_STATS_OFF + 2048;
-static constexpr int B_TX_BYTES = 2 * B_A_BYTES + 2 * KV_BYTES + 2 * B_STATS_BYTES;
-static constexpr int B_OUT_OFF = 2 * B_STAGE_BYTES;          // 8 warps x 4 KB output staging
-static constexpr int B_SMEM = 1024 + 2 * B_STAGE_BYTES + 8 * 4096 + 256;
-// TMEM: two ping-pong buffers of 192 columns, one per 64-column sub-block of the score matrix:
-//   [0,64) X = S (or S^T) sub-block, [64,128) Y = dP (or dP^T), [128,160) bf16 operand 1, [160,192) bf16 operand 2
-// and two 64-column output accumulators that live for the whole item.
-static constexpr int B_BUFW = 192;
-static constexpr int B_ACC0 = 384, B_ACC1 = 448;
-static constexpr int B_NSB = 4;  // sub-blocks of the 208 columns: 64, 64, 64, 16
-
-__device__ __forceinline__ void store_row32(bf16* dst, const uint32_t (&a)[32]) {
-  uint4* d = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    uint32_t w[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      __nv_bfloat162 v = __floats2bfloat162_rn(__uint_as_float(a[8 * j + 2 * k]), __uint_as_float(a[8 * j + 2 * k + 1]));
-      w[k] = *reinterpret_cast<uint32_t*>(&v);
-    }
-    d[j] = make_uint4(w[0], w[1], w[2], w[3]);
-  }
-}
-
-__device__ __forceinline__ void store_row64(bf16* dst, const uint32_t (&a)[32], const uint32_t (&b)[32]) {
-  store_row32(dst, a);
-  store_row32(dst + 32, b);
-}
-
-// MODE 0 (dQ):    rows = queries.  A0 = Q tile, A1 = dO tile, B0 = K, B1 = V.
-//                 X = S = Q K^T, Y = dP = dO V^T, dS = P o (dP - delta)/sqrt(d) -> TMEM, ACC0 += dS K.
-// MODE 1 (dK,dV): rows = keys.     A0 = K tile, A1 = V tile, B0 = Q, B1 = dO.
-//                 X = S^T = K Q^T, Y = dP^T = V dO^T, P^T and dS^T -> TMEM, ACC0 (dV) += P^T dO, ACC1 (dK) += dS^T Q.
-// The 208 score columns are processed as four sub-blocks through two ping-pong TMEM buffers, so the tensor
-// cores compute sub-block g+1 / g+2 (also of the NEXT work item) while the element-wise warps are on g.
-template <int MODE>
-__global__ void __launch_bounds__(B_THREADS, 1)
-attn_bwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUtensorMap mA1,
-                const __grid_constant__ CUtensorMap mB0, const __grid_constant__ CUtensorMap mB1,
-                const __grid_constant__ CUtensorMap mOut, int cA0, int cA1, int cB0, int cB1,
-                const float* __restrict__ lse2, const float* __restrict__ delta, bf16* __restrict__ dqkv, int tokens, int heads, int ntiles, int num_items, float sl2, float scale,
-                int dbg) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B_OUT_OFF + 8 * 4096);
-  uint64_t* load_full = bars;       // [2] TMA -> MMA / element-wise
-  uint64_t* load_empty = bars + 2;  // [2] MMA -> TMA
-  uint64_t* xy_full = bars + 4;     // [2] X,Y of a sub-block complete        (MMA -> element-wise)
-  uint64_t* a_full = bars + 6;      // [2] bf16 operands written, 8 arrivals   (element-wise -> MMA)
-  uint64_t* acc_full = bars + 8;    // output accumulators complete           (MMA -> epilogue)
-  uint64_t* acc_free = bars + 9;    // accumulators read out, 8 arrivals       (epilogue -> MMA)
-  uint64_t* xy_used = bars + 10;    // [2] X,Y of a sub-block are in registers, 8 arrivals (element-wise -> MMA):
-                                    //     lets the tensor cores refill the buffer while the warps still compute
-  uint64_t* ts_done = bars + 12;    // [2] the TS MMAs that read a buffer's bf16 operands retired (MMA -> element-wise)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int D = heads * A_HD;
-
-  if (warp == B_MMA_WARP && lane == 0) {
-    for (int i = 0; i < 2; ++i) {
-      ptx::mbar_init(&load_full[i], 1);
-      ptx::mbar_init(&load_empty[i], 1);
-      ptx::mbar_init(&xy_full[i], 1);
-      ptx::mbar_init(&a_full[i], 8);
-      ptx::mbar_init(&xy_used[i], 8);
-      ptx::mbar_init(&ts_done[i], 1);
-    }
-    ptx::mbar_init(acc_full, 1);
-    ptx::mbar_init(acc_free, 8);
-    ptx::fence_mbar_init();
-  }
-  if (warp == B_TMA_WARP) {
-    if (lane == 0) {
-      ptx::prefetch_tmap(&mA0);
-      ptx::prefetch_tmap(&mA1);
-      ptx::prefetch_tmap(&mB0);
-      ptx::prefetch_tmap(&mB1);
-    }
-    __syncwarp();
-    ptx::tmem_alloc(tmem_slot, 512);
-    ptx::tmem_relinquish();
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  const int my_items = (num_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-
-  if (warp == B_TMA_WARP) {
-    if (lane == 0) {
-      for (int n = 0; n < my_items; ++n) {
-        const int item = blockIdx.x + n * gridDim.x;
-        const int st = n & 1, hd = item / ntiles, t = item % ntiles, b = hd / heads, h = hd % heads;
-        ptx::mbar_wait(&load_empty[st], ((n >> 1) & 1) ^ 1);
-        uint8_t* s0 = smem + st * B_STAGE_BYTES;
-        if ((dbg & 1) && n >= 2) {  // timing experiment: no loads after the first two items
-          ptx::mbar_arrive(&load_full[st]);
-          continue;
-        }
-        ptx::mbar_arrive_expect_tx(&load_full[st], B_TX_BYTES);
-        ptx::tma_load_3d(s0, &mA0, &load_full[st], cA0 + h * A_HD, t * 128, b);
-        ptx::tma_load_3d(s0 + B_A_BYTES, &mA1, &load_full[st], cA1 + h * A_HD, t * 128, b);
-        ptx::tma_load_3d(s0 + 2 * B_A_BYTES, &mB0, &load_full[st], cB0 + h * A_HD, 0, b);
-        ptx::tma_load_3d(s0 + 2 * B_A_BYTES + KV_BYTES, &mB1, &load_full[st], cB1 + h * A_HD, 0, b);
-        ptx::bulk_load_1d(s0 + B_STATS_OFF, lse2 + static_cast<size_t>(hd) * A_TPAD, B_STATS_BYTES, &load_full[st]);
-        ptx::bulk_load_1d(s0 + B_STATS_OFF + 1024, delta + static_cast<size_t>(hd) * A_TPAD, B_STATS_BYTES,
-                          &load_full[st]);
-      }
-    }
-  } else if (warp == B_MMA_WARP) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_64 = ptx::make_idesc_bf16(128, 64);
-      constexpr uint32_t idesc_16 = ptx::make_idesc_bf16(128, 16);
-      constexpr uint32_t idesc_o = ptx::make_idesc_bf16(128, A_HD) | ptx::IDESC_B_MN_MAJOR;
-      const int total_g = my_items * B_NSB;
-      auto issue_xy = [&](int g) {
-        const int n = g >> 2, sb = g & 3, st = n & 1;
-        if (sb == 0) ptx::mbar_wait(&load_full[st], (n >> 1) & 1);
-        const uint32_t s0 = ptx::smem_u32(smem + st * B_STAGE_BYTES);
-        const uint64_t a0 = ptx::make_smem_desc_sw128(s0);
-        const uint64_t a1 = ptx::make_smem_desc_sw128(s0 + B_A_BYTES);
-        const uint64_t b0 = ptx::make_smem_desc_sw128(s0 + 2 * B_A_BYTES + sb * 64 * 128);
-        const uint64_t b1 = ptx::make_smem_desc_sw128(s0 + 2 * B_A_BYTES + KV_BYTES + sb * 64 * 128);
-        const uint32_t buf = tmem + (g & 1) * B_BUFW;
-        const uint32_t idesc = sb < 3 ? idesc_64 : idesc_16;
-        if (!(dbg & 16)) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) ptx::umma_bf16(buf, a0 + 2 * k, b0 + 2 * k, idesc, k > 0 ? 1u : 0u);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) ptx::umma_bf16(buf + 64, a1 + 2 * k, b1 + 2 * k, idesc, k > 0 ? 1u : 0u);
-        }
-        ptx::umma_commit(&xy_full[g & 1]);
-      };
-      if (total_g > 0) issue_xy(0);
-      if (total_g > 1) issue_xy(1);
-      for (int g = 0; g < total_g; ++g) {
-        const int n = g >> 2, sb = g & 3, st = n & 1;
-        // refill this buffer's X/Y as soon as the element-wise warps hold sub-block g in registers
-        ptx::mbar_wait(&xy_used[g & 1], (g >> 1) & 1);
-        ptx::tc_fence_after();
-        if (g + 2 < total_g) issue_xy(g + 2);
-        ptx::mbar_wait(&a_full[g & 1], (g >> 1) & 1);
-        if (sb == 0) ptx::mbar_wait(acc_free, (n & 1) ^ 1);  // previous item's outputs have been read out
-        ptx::tc_fence_after();
-        const uint32_t s0 = ptx::smem_u32(smem + st * B_STAGE_BYTES);
-        const uint32_t buf = tmem + (g & 1) * B_BUFW;
-        const int ksteps = sb < 3 ? 4 : 1;
-        for (int ks = 0; ks < ((dbg & 16) ? 0 : ksteps); ++ks) {
-          const uint32_t acc = (sb > 0 || ks > 0) ? 1u : 0u;
-          const uint32_t rows = (sb * 64 + ks * 16) * 128;  // 16 reduction rows of the MN-major B operand
-          if (MODE == 0) {
-            ptx::umma_bf16_ts(tmem + B_ACC0, buf + 128 + ks * 8,
-                              ptx::make_smem_desc_mn_sw128(s0 + 2 * B_A_BYTES + rows, 1024), idesc_o, acc);
-          } else {
-            ptx::umma_bf16_ts(tmem + B_ACC0, buf + 128 + ks * 8,
-                              ptx::make_smem_desc_mn_sw128(s0 + 2 * B_A_BYTES + KV_BYTES + rows, 1024), idesc_o, acc);
-            ptx::umma_bf16_ts(tmem + B_ACC1, buf + 160 + ks * 8,
-                              ptx::make_smem_desc_mn_sw128(s0 + 2 * B_A_BYTES + rows, 1024), idesc_o, acc);
-          }
-        }
-        ptx::umma_commit(&ts_done[g & 1]);
-        if (sb == 3) {
-          ptx::umma_commit(acc_full);
-          ptx::umma_commit(&load_empty[st]);
-        }
-      }
-    }
-  } else {
-    const int w4 = warp & 3, half = warp >> 2;
-    const uint32_t lane_addr = tmem + (static_cast<uint32_t>(w4 * 32) << 16);
-    const int r = w4 * 32 + lane;
-    const float nscale = -scale;
-    for (int n = 0; n < my_items; ++n) {
-      const int item = blockIdx.x + n * gridDim.x;
-      const int st = n & 1, hd = item / ntiles, t = item % ntiles, b = hd / heads, h = hd % heads;
-      const int row = t * 128 + r;  // query (MODE 0) or key (MODE 1) index of this thread
-      (void)b;
-      const float* sl = reinterpret_cast<const float*>(smem + st * B_STAGE_BYTES + B_STATS_OFF);
-      const float* sd = sl + 256;
-      ptx::mbar_wait(&load_full[st], (n >> 1) & 1);
-      float l_row = 0.f, nds_row = 0.f;
-      if (MODE == 0 && row < A_TPAD) {
-        l_row = sl[row];
-        nds_row = sd[row] * nscale;
-      }
-#pragma unroll 1
-      for (int sb = 0; sb < B_NSB; ++sb) {
-        const int g = n * B_NSB + sb;
-        ptx::mbar_wait(&xy_full[g & 1], (g >> 1) & 1);
-        ptx::tc_fence_after();
-        const uint32_t buf = lane_addr + (g & 1) * B_BUFW;
-        if (sb < 3 || half == 0) {
-          const int coff = sb < 3 ? 32 * half : 0;
-          uint32_t x[32], y[32];
-          if (!(dbg & 8)) {
-          ptx::tmem_ld_32x32b_x32(buf + coff, x);
-          ptx::tmem_ld_32x32b_x32(buf + 64 + coff, y);
-          ptx::tmem_ld_wait();
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = y[j] = j + lane;
-          }
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&xy_used[g & 1]);
-          uint32_t o1[16], o2[16];
-          const float* cl = sl + sb * 64 + coff;  // column statistics (MODE 1)
-          const float* cd = sd + sb * 64 + coff;
-          if (dbg & 2) {  // timing experiment: no element-wise math
-#pragma unroll
-            for (int j = 0; j < 16; ++j) o1[j] = o2[j] = x[j] ^ y[j];
-          } else
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 l4, d4;
-            if (MODE == 0) {
-              l4 = make_float4(l_row, l_row, l_row, l_row);
-              d4 = make_float4(nds_row, nds_row, nds_row, nds_row);
-            } else {
-              l4 = *reinterpret_cast<const float4*>(cl + 4 * j);
-              d4 = *reinterpret_cast<const float4*>(cd + 4 * j);
-              d4.x *= nscale; d4.y *= nscale; d4.z *= nscale; d4.w *= nscale;
-            }
-            const float p0 = ex2_approx(fmaf(__uint_as_float(x[4 * j]), sl2, -l4.x));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(x[4 * j + 1]), sl2, -l4.y));
-            const float p2 = ex2_approx(fmaf(__uint_as_float(x[4 * j + 2]), sl2, -l4.z));
-            const float p3 = ex2_approx(fmaf(__uint_as_float(x[4 * j + 3]), sl2, -l4.w));
-            // dS = P * (dP - delta) * scale
-            const float e0 = p0 * fmaf(__uint_as_float(y[4 * j]), scale, d4.x);
-            const float e1 = p1 * fmaf(__uint_as_float(y[4 * j + 1]), scale, d4.y);
-            const float e2 = p2 * fmaf(__uint_as_float(y[4 * j + 2]), scale, d4.z);
-            const float e3 = p3 * fmaf(__uint_as_float(y[4 * j + 3]), scale, d4.w);
-            __nv_bfloat162 v0 = __floats2bfloat162_rn(e0, e1), v1 = __floats2bfloat162_rn(e2, e3);
-            if (MODE == 0) {
-              o1[2 * j] = *reinterpret_cast<uint32_t*>(&v0);
-              o1[2 * j + 1] = *reinterpret_cast<uint32_t*>(&v1);
-            } else {
-              __nv_bfloat162 w0 = __floats2bfloat162_rn(p0, p1), w1 = __floats2bfloat162_rn(p2, p3);
-              o1[2 * j] = *reinterpret_cast<uint32_t*>(&w0);
-              o1[2 * j + 1] = *reinterpret_cast<uint32_t*>(&w1);
-              o2[2 * j] = *reinterpret_cast<uint32_t*>(&v0);
-              o2[2 * j + 1] = *reinterpret_cast<uint32_t*>(&v1);
-            }
-          }
-          ptx::mbar_wait(&ts_done[g & 1], ((g >> 1) & 1) ^ 1);  // TS MMAs of sub-block g-2 no longer read this buffer
-          ptx::tc_fence_after();
-          if (!(dbg & 8)) {
-          ptx::tmem_st_32x32b_x16(buf + 128 + (sb < 3 ? 16 * half : 0), o1);
-          if (MODE == 1) ptx::tmem_st_32x32b_x16(buf + 160 + (sb < 3 ? 16 * half : 0), o2);
-          ptx::tmem_st_wait();
-          } else if (o1[3] == 0x12345 && o2[5] == 0x777) {
-            dqkv[0] = __float2bfloat16(1.f);
-          }
-        } else {
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&xy_used[g & 1]);
-        }
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&a_full[g & 1]);
-      }
-      // ---- epilogue: accumulators -> bf16 -> dqkv ----
-      ptx::mbar_wait(acc_full, n & 1);
-      ptx::tc_fence_after();
-      if (MODE == 0) {
-        if (half == 0) {  // dQ: 64 columns of ACC0 -> q slot
-          uint32_t a0[32], a1[32];
-          ptx::tmem_ld_32x32b_x32(lane_addr + B_ACC0, a0);
-          ptx::tmem_ld_32x32b_x32(lane_addr + B_ACC0 + 32, a1);
-          ptx::tmem_ld_wait();
-          if (!(dbg & 4))
-            stage_store_64(smem + B_OUT_OFF + warp * 4096, a0, a1, 1.0f, &mOut, h * A_HD, t * 128 + w4 * 32, b, lane);
-        }
-      } else {  // half 0: dV (ACC0) -> v slot, half 1: dK (ACC1) -> k slot
-        uint32_t a0[32], a1[32];
-        const uint32_t col = half == 0 ? B_ACC0 : B_ACC1;
-        ptx::tmem_ld_32x32b_x32(lane_addr + col, a0);
-        ptx::tmem_ld_32x32b_x32(lane_addr + col + 32, a1);
-        ptx::tmem_ld_wait();
-        if (!(dbg & 4))
-          stage_store_64(smem + B_OUT_OFF + warp * 4096, a0, a1, 1.0f, &mOut, (half == 0 ? 2 * D : D) + h * A_HD,
-                         t * 128 + w4 * 32, b, lane);
-      }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(acc_free);
-    }
-    if (lane == 0) ptx::tma_store_wait_all<0>();
-    __syncwarp();
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == B_TMA_WARP) {
-    ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem, 512);
-  }
-}
-
 // delta[b,h,i] = sum_d dO[i, h*64+d] * O[i, h*64+d]   (one warp per token row, 8 lanes per head)
-__global__ void __launch_bounds__(256) attn_delta_kernel_2k(const bf16* __restrict__ dout, const bf16* __restrict__ o,
+__global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ o,
                                                          float* __restrict__ delta, int rows, int tokens, int heads) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -718,7 +417,7 @@ __global__ void __launch_bounds__(256) attn_delta_kernel_2k(const bf16* __restri
 
 int attention_delta(const AttnBwdPlan* p, cudaStream_t stream) {
   const int rows = p->batch * p->tokens;
-  attn_delta_kernel_2k<<<(rows + 7) / 8, 256, 0, stream>>>(p->dout, p->o, p->delta, rows, p->tokens, p->heads);
+  attn_delta_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(p->dout, p->o, p->delta, rows, p->tokens, p->heads);
   VITATK_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -740,51 +439,8 @@ int attention_bwd_plan_init(AttnBwdPlan* p, const bf16* qkv, const bf16* dout, c
   const uint64_t ld = 3ull * heads * A_HD, ldo = 1ull * heads * A_HD;
   if (make_tmap_3d(&p->tmQKV128, qkv, ld, tokens, batch, ld * 2, ld * 2 * tokens, A_HD, 128)) return 1;
   if (make_tmap_3d(&p->tmQKV208, qkv, ld, tokens, batch, ld * 2, ld * 2 * tokens, A_HD, A_TPAD)) return 1;
-  if (make_tmap_3d(&p->tmDO128, dout, ldo, tokens, batch, ldo * 2, ldo * 2 * tokens, A_HD, 128)) return 1;
   if (make_tmap_3d(&p->tmDO208, dout, ldo, tokens, batch, ldo * 2, ldo * 2 * tokens, A_HD, A_TPAD)) return 1;
-  if (make_tmap_3d(&p->tmDqkv, dqkv, ld, tokens, batch, ld * 2, ld * 2 * tokens, A_HD, 32)) return 1;
   if (make_tmap_3d(&p->tmDqkv32, dqkv, ld, tokens, batch, ld * 2, ld * 2 * tokens, 32, 32, 64)) return 1;
-  return 0;
-}
-
-int attention_bwd_tc05(const AttnBwdPlan* p, cudaStream_t stream) {
-  static bool attr = false;
-  if (!attr) {
-    VITATK_CUDA_OK(cudaFuncSetAttribute(attn_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
-    VITATK_CUDA_OK(cudaFuncSetAttribute(attn_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
-    attr = true;
-  }
-  if (p->heads * A_HD % 256 != 0) {
-    set_error("attention_bwd_tc05: heads*64 must be a multiple of 256");
-    return 1;
-  }
-  const float scale = 1.0f / sqrtf(static_cast<float>(A_HD));
-  const float sl2 = scale * 1.4426950408889634f;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int D = p->heads * A_HD;
-  const int ntiles = p->tokens > 128 ? 2 : 1;
-  const int items = p->batch * p->heads * ntiles;
-  const int grid = items < sms ? items : sms;
-  const int rows = p->batch * p->tokens;
-  static int dbg = -1;
-  if (dbg < 0) {
-    const char* e = getenv("VITATK_ATTN_DBG");
-    dbg = e ? atoi(e) : 0;
-  }
-  attn_delta_kernel_2k<<<(rows + 7) / 8, 256, 0, stream>>>(p->dout, p->o, p->delta, rows, p->tokens, p->heads);
-  VITATK_CUDA_OK(cudaGetLastError());
-  // dQ: A0 = Q tile, A1 = dO tile, B0 = K, B1 = V
-  attn_bwd_kernel<0><<<grid, B_THREADS, B_SMEM, stream>>>(p->tmQKV128, p->tmDO128, p->tmQKV208, p->tmQKV208, p->tmDqkv, 0, 0, D,
-                                                         2 * D, p->lse2, p->delta, p->dqkv, p->tokens, p->heads, ntiles,
-                                                         items, sl2, scale, dbg);
-  VITATK_CUDA_OK(cudaGetLastError());
-  // dK,dV: A0 = K tile, A1 = V tile, B0 = Q, B1 = dO
-  attn_bwd_kernel<1><<<grid, B_THREADS, B_SMEM, stream>>>(p->tmQKV128, p->tmQKV128, p->tmQKV208, p->tmDO208, p->tmDqkv, D, 2 * D, 0,
-                                                         0, p->lse2, p->delta, p->dqkv, p->tokens, p->heads, ntiles,
-                                                         items, sl2, scale, dbg);
-  VITATK_CUDA_OK(cudaGetLastError());
   return 0;
 }
 

@@ -163,244 +163,6 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// LayerNorm kernels that also produce the LoRA down-projection of their OUTPUT: T[row, 64 g + j] = sum_k out[row,k] *
-// A[64 g + j, k] (A = the consumer site's packed adapter matrix, G groups of <= 16 rank rows).  The output rows are in
-// registers anyway; they are additionally staged as a 16-row bf16 tile in shared memory and multiplied with
-// mma.sync (these kernels use no tcgen05, so the legacy warp MMA does not disturb anything).  This replaces a
-// separate skinny GEMM that re-read the whole [M,768] activation (23-29 us per launch).
-// Block = 8 warps = 16 rows (two per warp); the K = 768 reduction of the MMA is split over the 8 warps.
-// ------------------------------------------------------------------------------------------------
-static constexpr int LT_ROWS = 16;
-static constexpr int LT_PITCH = 768 * 2 + 16;  // bytes; 388 words: ldmatrix row addresses fall into distinct banks
-static constexpr int LT_MAX_NT = 6;            // 8-column tiles of T: groups * ceil(rank / 8)
-
-__device__ __forceinline__ void lt_ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(addr));
-}
-__device__ __forceinline__ void lt_mma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
-// tile: [16][LT_PITCH] bf16 rows staged by the caller (after __syncthreads); red: [8 warps][16][8 * nt_total] floats.
-// lora: bf16 [64 * groups, 768]; T: bf16 [rows, ldt], group g at columns 64 g.
-__device__ __forceinline__ void lt_project(const uint8_t* tile, float* red, const bf16* __restrict__ lora, int groups,
-                                           int ntg, bf16* __restrict__ T, int ldt, int row0, int rows) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nt_total = groups * ntg;
-  float acc[LT_MAX_NT][4];
-#pragma unroll
-  for (int n = 0; n < LT_MAX_NT; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
-  const uint32_t tbase = static_cast<uint32_t>(__cvta_generic_to_shared(tile));
-  const int r = (lane & 7) + ((lane >> 3) & 1) * 8;
-#pragma unroll
-  for (int i = 0; i < 6; ++i) {  // this warp's 6 of the 48 k-steps
-    const int ks = warp * 6 + i;
-    uint32_t a[4];
-    lt_ldsm_x4(a, tbase + r * LT_PITCH + ks * 32 + (lane >> 4) * 16);
-#pragma unroll
-    for (int n = 0; n < LT_MAX_NT; ++n) {
-      if (n < nt_total) {
-        const int g = n / ntg, j0 = (n - g * ntg) * 8;
-        const bf16* ap = lora + static_cast<size_t>(64 * g + j0 + (lane >> 2)) * 768 + ks * 16 + 2 * (lane & 3);
-        lt_mma(acc[n], a, __ldg(reinterpret_cast<const uint32_t*>(ap)), __ldg(reinterpret_cast<const uint32_t*>(ap + 8)));
-      }
-    }
-  }
-  // cross-warp reduction of the K-split partial sums
-  const int ncols = nt_total * 8;
-#pragma unroll
-  for (int n = 0; n < LT_MAX_NT; ++n) {
-    if (n < nt_total) {
-      float* p = red + (warp * 16 + (lane >> 2)) * ncols + n * 8 + 2 * (lane & 3);
-      p[0] = acc[n][0];
-      p[1] = acc[n][1];
-      p[8 * ncols] = acc[n][2];
-      p[8 * ncols + 1] = acc[n][3];
-    }
-  }
-  __syncthreads();
-  for (int e = threadIdx.x; e < 16 * ncols; e += blockDim.x) {
-    const int rr = e / ncols, cc = e - rr * ncols;
-    float v = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) v += red[(w * 16 + rr) * ncols + cc];
-    const int n = cc >> 3, g = n / ntg, j = (n - g * ntg) * 8 + (cc & 7);
-    if (row0 + rr < rows) T[static_cast<size_t>(row0 + rr) * ldt + 64 * g + j] = __float2bfloat16(v);
-  }
-}
-
-__global__ void __launch_bounds__(256) ln_fwd_t_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
-                                                       const float* __restrict__ beta, bf16* __restrict__ y,
-                                                       float2* __restrict__ stats, int rows, float eps,
-                                                       const bf16* __restrict__ lora, int groups, int ntg,
-                                                       bf16* __restrict__ T, int ldt) {
-  extern __shared__ __align__(16) uint8_t lt_smem[];
-  uint8_t* tile = lt_smem;
-  float* red = reinterpret_cast<float*>(lt_smem + LT_ROWS * LT_PITCH);
-  pdl_wait();
-  pdl_launch_dependents();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row0 = blockIdx.x * LT_ROWS;
-  constexpr int CH = 3, COLS = 768;
-#pragma unroll 1
-  for (int it = 0; it < 2; ++it) {
-    const int lr = it * 8 + warp, row = row0 + lr;
-    uint4* trow = reinterpret_cast<uint4*>(tile + lr * LT_PITCH);
-    if (row >= rows) {
-#pragma unroll
-      for (int i = 0; i < CH; ++i) trow[lane + 32 * i] = make_uint4(0, 0, 0, 0);
-      continue;
-    }
-    const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * COLS);
-    float v[CH][8];
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < CH; ++i) {
-      unpack8(__ldg(xr + lane + 32 * i), v[i]);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) s += v[i][j];
-    }
-    const float mean = warp_sum(s) * (1.f / COLS);
-    float q = 0.f;
-#pragma unroll
-    for (int i = 0; i < CH; ++i)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float d = v[i][j] - mean;
-        q += d * d;
-      }
-    const float rstd = rsqrtf(warp_sum(q) * (1.f / COLS) + eps);
-    uint4* yr = reinterpret_cast<uint4*>(y + static_cast<size_t>(row) * COLS);
-#pragma unroll
-    for (int i = 0; i < CH; ++i) {
-      const int c = (lane + 32 * i) * 8;
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c));
-      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
-      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-      float o[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * gg[j] + bb[j];
-      const uint4 pk = pack8(o);
-      yr[lane + 32 * i] = pk;
-      trow[lane + 32 * i] = pk;  // the projection sees exactly the bf16 values the consumer GEMM will read
-    }
-    if (lane == 0) stats[row] = make_float2(mean, rstd);
-  }
-  __syncthreads();
-  lt_project(tile, red, lora, groups, ntg, T, ldt, row0, rows);
-}
-
-__global__ void __launch_bounds__(256) ln_bwd_t_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
-                                                       const float2* __restrict__ stats, const float* __restrict__ gamma,
-                                                       const bf16* __restrict__ dres, bf16* __restrict__ dx, int rows,
-                                                       const bf16* __restrict__ lora, int groups, int ntg,
-                                                       bf16* __restrict__ T, int ldt) {
-  extern __shared__ __align__(16) uint8_t lt_smem[];
-  uint8_t* tile = lt_smem;
-  float* red = reinterpret_cast<float*>(lt_smem + LT_ROWS * LT_PITCH);
-  pdl_wait();
-  pdl_launch_dependents();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row0 = blockIdx.x * LT_ROWS;
-  constexpr int CH = 3, COLS = 768;
-#pragma unroll 1
-  for (int it = 0; it < 2; ++it) {
-    const int lr = it * 8 + warp, row = row0 + lr;
-    uint4* trow = reinterpret_cast<uint4*>(tile + lr * LT_PITCH);
-    if (row >= rows) {
-#pragma unroll
-      for (int i = 0; i < CH; ++i) trow[lane + 32 * i] = make_uint4(0, 0, 0, 0);
-      continue;
-    }
-    const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * COLS);
-    const uint4* dyr = reinterpret_cast<const uint4*>(dy + static_cast<size_t>(row) * COLS);
-    const float2 st = stats[row];
-    float xh[CH][8], gd[CH][8];
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < CH; ++i) {
-      const int c = (lane + 32 * i) * 8;
-      float xv[8], dv[8];
-      unpack8(__ldg(xr + lane + 32 * i), xv);
-      unpack8(__ldg(dyr + lane + 32 * i), dv);
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c));
-      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
-      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        xh[i][j] = (xv[j] - st.x) * st.y;
-        gd[i][j] = dv[j] * gg[j];
-        s1 += gd[i][j];
-        s2 += gd[i][j] * xh[i][j];
-      }
-    }
-    const float m1 = warp_sum(s1) * (1.f / COLS);
-    const float m2 = warp_sum(s2) * (1.f / COLS);
-    uint4* dxr = reinterpret_cast<uint4*>(dx + static_cast<size_t>(row) * COLS);
-    const uint4* rr = dres ? reinterpret_cast<const uint4*>(dres + static_cast<size_t>(row) * COLS) : nullptr;
-#pragma unroll
-    for (int i = 0; i < CH; ++i) {
-      float o[8];
-      float r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      if (rr) unpack8(__ldg(rr + lane + 32 * i), r);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = r[j] + st.y * (gd[i][j] - m1 - xh[i][j] * m2);
-      const uint4 pk = pack8(o);
-      dxr[lane + 32 * i] = pk;
-      trow[lane + 32 * i] = pk;
-    }
-  }
-  __syncthreads();
-  lt_project(tile, red, lora, groups, ntg, T, ldt, row0, rows);
-}
-
-static inline size_t lt_smem_bytes(int nt_total) { return LT_ROWS * LT_PITCH + 8 * 16 * nt_total * 8 * sizeof(float); }
-
-int layernorm_fwd_t(const bf16* x, const float* gamma, const float* beta, bf16* y, float2* stats, int rows, int cols,
-                    float eps, const bf16* lora, int groups, int rank, bf16* T, int ldt, cudaStream_t stream) {
-  const int ntg = (rank + 7) / 8;
-  if (cols != 768 || groups < 1 || rank < 1 || groups * ntg > LT_MAX_NT) {
-    set_error("layernorm_fwd_t: unsupported cols=%d groups=%d rank=%d", cols, groups, rank);
-    return 1;
-  }
-  static bool attr = false;
-  if (!attr) {
-    VITATK_CUDA_OK(cudaFuncSetAttribute(ln_fwd_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(lt_smem_bytes(LT_MAX_NT))));
-    attr = true;
-  }
-  VITATK_CUDA_OK(launch_pdl(ln_fwd_t_kernel, dim3((rows + LT_ROWS - 1) / LT_ROWS), dim3(256), lt_smem_bytes(groups * ntg),
-                            stream, 1, x, gamma, beta, y, stats, rows, eps, lora, groups, ntg, T, ldt));
-  return 0;
-}
-
-int layernorm_bwd_t(const bf16* dy, const bf16* x, const float2* stats, const float* gamma, const bf16* dres, bf16* dx_out,
-                    int rows, int cols, const bf16* lora, int groups, int rank, bf16* T, int ldt, cudaStream_t stream) {
-  const int ntg = (rank + 7) / 8;
-  if (cols != 768 || groups < 1 || rank < 1 || groups * ntg > LT_MAX_NT) {
-    set_error("layernorm_bwd_t: unsupported cols=%d groups=%d rank=%d", cols, groups, rank);
-    return 1;
-  }
-  static bool attr = false;
-  if (!attr) {
-    VITATK_CUDA_OK(cudaFuncSetAttribute(ln_bwd_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(lt_smem_bytes(LT_MAX_NT))));
-    attr = true;
-  }
-  VITATK_CUDA_OK(launch_pdl(ln_bwd_t_kernel, dim3((rows + LT_ROWS - 1) / LT_ROWS), dim3(256), lt_smem_bytes(groups * ntg),
-                            stream, 1, dy, x, stats, gamma, dres, dx_out, rows, lora, groups, ntg, T, ldt));
-  return 0;
-}
-
 int layernorm_fwd(const bf16* x, const float* gamma, const float* beta, bf16* y, float2* stats, int rows, int cols,
                   float eps, cudaStream_t stream) {
   const int grid = (rows + 7) / 8;
@@ -509,10 +271,15 @@ __global__ void __launch_bounds__(256) head_kernel(const bf16* __restrict__ h, c
   float se = 0.f;
   for (int c = 0; c < classes; ++c) se += expf(lg[c] - mx);
   const float lse = mx + logf(se);
-  const int y = labels ? static_cast<int>(labels[b]) : -1;
+  // label out of [0, classes): F.cross_entropy raises (whitebox_attacks.py:29).  Here the image gets a NaN loss and no
+  // one-hot term; nothing is read out of bounds.  (Host labels are range-checked before the launch.)
+  const long long yl = labels ? static_cast<long long>(labels[b]) : -1;
+  const bool bad_label = labels && (yl < 0 || yl >= classes);
+  const int y = (labels && !bad_label) ? static_cast<int>(yl) : -1;
   if (tid < classes) logits[static_cast<size_t>(b) * classes + tid] = lg[tid];
   for (int c = tid + blockDim.x; c < classes; c += blockDim.x) logits[static_cast<size_t>(b) * classes + c] = lg[c];
   if (tid == 0 && loss && y >= 0) loss[b] = lse - lg[y];
+  if (tid == 0 && loss && bad_label) loss[b] = __int_as_float(0x7fc00000);
   if (dh == nullptr) return;
   // dlogits = (softmax - onehot) * grad_scale, or the caller's cotangent (vector-Jacobian product); dy = Wc^T dlogits
   __syncthreads();

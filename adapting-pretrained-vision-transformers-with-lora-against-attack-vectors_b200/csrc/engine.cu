@@ -112,13 +112,11 @@ struct vitatk_engine {
   long long launches = 0;
   PixelNorm nrm;
   // optional per-launch CUDA-event timing (bench.py's roofline leg; off in the timed region)
-  bool attn_bwd_two_kernel = false;  // VITATK_ATTN_BWD=2k selects the older dQ + dK/dV kernel pair
   bool zigzag = true;                // skinny LoRA GEMMs walk M last-to-first (VITATK_ZIGZAG=0: first-to-last)
   bool tc_const = true;              // bias / fold constants as tensor-core rank-1 updates (VITATK_TC_CONST=0: epilogue loads)
   char* cbuf = nullptr;              // backing store of the lbx / tones arrays
   bool const_dirty = true;           // weights / adapters changed since the constant columns were packed
   bool fuse_stats = true;            // folded LayerNorm: (mean, rstd) come out of the skinny LoRA GEMM (VITATK_FUSE_STATS=0: stats kernel)
-  bool fuse_ln_t = false;            // LayerNorm kernels also produce the LoRA x*A^T of the site they feed
   bool fuse_delta = false;           // delta comes out of the proj-backward GEMM epilogue (pair kernel) instead of a kernel
   bool prof = false;
   struct ProfRec { int cat; double flops; cudaEvent_t a, b; };
@@ -415,19 +413,11 @@ static int encoder_forward(vitatk_engine* e, PlanSet* ps, int batch, cudaStream_
     LayerPlans& p = ps->layers[l];
     const int rq = w.lora[VITATK_SITE_QKV].rank, r1 = w.lora[VITATK_SITE_FC1].rank;
     const bool fold = w.qkv_c1 != nullptr && w.fc1_c1 != nullptr;
-    // Legacy mma.sync is slow on sm_100 (measured: +14 us per launch with one 8-column tile of T, +72 us with three),
-    // so the fusion only pays for single-tile sites (it replaces a 23 us skinny GEMM); the 3-adapter q|k|v site keeps
-    // its own GEMM.
-    const bool ln1_t = !fold && e->fuse_ln_t && rq > 0 && 3 * ((rq + 7) / 8) <= 1;
-    const bool ln2_t = !fold && e->fuse_ln_t && r1 > 0 && r1 <= 8;
     if (fold) {  // only (mean, rstd): the normalisation itself happens in the qkv GEMM's epilogue
       if (!(rq > 0 && p.t_qkv.epi.stats_out)) RUNC(CAT_LN_FWD, 0, layernorm_stats(e->h[l], e->st1[l], M, D, c.ln_eps, s));
-    } else if (ln1_t)
-      RUNC(CAT_LN_FWD, 0, layernorm_fwd_t(e->h[l], w.ln1_g, w.ln1_b, e->xn, e->st1[l], M, D, c.ln_eps,
-                                          w.lora[VITATK_SITE_QKV].la_fwd, 3, rq, e->T, 3 * LORA_PAD, s));
-    else
+    } else
       RUNC(CAT_LN_FWD, 0, layernorm_fwd(e->h[l], w.ln1_g, w.ln1_b, e->xn, e->st1[l], M, D, c.ln_eps, s));
-    if (rq > 0 && !ln1_t) RUN_GEMM(CAT_T_QKV, &p.t_qkv);
+    if (rq > 0) RUN_GEMM(CAT_T_QKV, &p.t_qkv);
     RUN_GEMM(CAT_QKV, &p.qkv);
     RUNC(CAT_ATTN_FWD, 4.0 * batch * c.heads * TOKENS * TOKENS * 64, attention_fwd_tc05(&ps->attn_fwd[l], s));
     if (w.lora[VITATK_SITE_PROJ].rank > 0) RUN_GEMM(CAT_T_PROJ, &p.t_proj);
@@ -435,12 +425,9 @@ static int encoder_forward(vitatk_engine* e, PlanSet* ps, int batch, cudaStream_
     if (fold) {
       if (!(r1 > 0 && p.t_fc1.epi.stats_out))
         RUNC(CAT_LN_FWD, 0, layernorm_stats(e->h_mid[l], e->st2[l], M, D, c.ln_eps, s));
-    } else if (ln2_t)
-      RUNC(CAT_LN_FWD, 0, layernorm_fwd_t(e->h_mid[l], w.ln2_g, w.ln2_b, e->xn, e->st2[l], M, D, c.ln_eps,
-                                          w.lora[VITATK_SITE_FC1].la_fwd, 1, r1, e->T, 3 * LORA_PAD, s));
-    else
+    } else
       RUNC(CAT_LN_FWD, 0, layernorm_fwd(e->h_mid[l], w.ln2_g, w.ln2_b, e->xn, e->st2[l], M, D, c.ln_eps, s));
-    if (r1 > 0 && !ln2_t) RUN_GEMM(CAT_T_FC1, &p.t_fc1);
+    if (r1 > 0) RUN_GEMM(CAT_T_FC1, &p.t_fc1);
     RUN_GEMM(CAT_FC1, &p.fc1);
     if (w.lora[VITATK_SITE_FC2].rank > 0) RUN_GEMM(CAT_T_FC2, &p.t_fc2);
     RUN_GEMM(CAT_FC2, &p.fc2);
@@ -452,38 +439,21 @@ static int encoder_forward(vitatk_engine* e, PlanSet* ps, int batch, cudaStream_
 static int encoder_backward(vitatk_engine* e, PlanSet* ps, int batch, cudaStream_t s) {
   const vitatk_config& c = e->cfg;
   const int M = batch * TOKENS, D = c.dim;
-  bool t_fc2_ready = false;
   for (int l = c.layers - 1; l >= 0; --l) {
     const LayerWeights& w = e->lw[l];
     LayerPlans& p = ps->layers[l];
-    // dh_a * B_fc2 was already produced by the LayerNorm backward of the layer above (not for the top layer: dh_a
-    // comes from the head there)
-    if (w.lora[VITATK_SITE_FC2].rank > 0 && !t_fc2_ready) RUN_GEMM(CAT_BT_FC2, &p.bt_fc2);
+    if (w.lora[VITATK_SITE_FC2].rank > 0) RUN_GEMM(CAT_BT_FC2, &p.bt_fc2);
     RUN_GEMM(CAT_BFC2, &p.bfc2);  // du = (dh W2 + lora) * gelu'(u)   (u[l] holds gelu'(u), written by fc1's epilogue)
     if (w.lora[VITATK_SITE_FC1].rank > 0) RUN_GEMM(CAT_BT_FC1, &p.bt_fc1);
     RUN_GEMM(CAT_BFC1, &p.bfc1);  // dxn = du W1 + lora
-    const int rp = w.lora[VITATK_SITE_PROJ].rank;
-    const bool ln2b_t = e->fuse_ln_t && rp > 0 && rp <= 8;
-    if (ln2b_t)  // dh_mid, and its LoRA projection dh_mid * B_proj for the proj backward GEMM
-      RUNC(CAT_LN_BWD, 0, layernorm_bwd_t(e->dxn, e->h_mid[l], e->st2[l], w.ln2_g, e->dh_a, e->dh_b, M, D,
-                                          w.lora[VITATK_SITE_PROJ].lb_bwd, 1, rp, e->T, 3 * LORA_PAD, s));
-    else
-      RUNC(CAT_LN_BWD, 0, layernorm_bwd(e->dxn, e->h_mid[l], e->st2[l], w.ln2_g, e->dh_a, e->dh_b, M, D, s));  // dh_mid
-    if (rp > 0 && !ln2b_t) RUN_GEMM(CAT_BT_PROJ, &p.bt_proj);
+    RUNC(CAT_LN_BWD, 0, layernorm_bwd(e->dxn, e->h_mid[l], e->st2[l], w.ln2_g, e->dh_a, e->dh_b, M, D, s));  // dh_mid
+    if (w.lora[VITATK_SITE_PROJ].rank > 0) RUN_GEMM(CAT_BT_PROJ, &p.bt_proj);
     RUN_GEMM(CAT_BPROJ, &p.bproj);  // dao = dh_mid Wp + lora
     RUNC(CAT_ATTN_BWD, 8.0 * batch * c.heads * TOKENS * TOKENS * 64,
-         e->attn_bwd_two_kernel ? attention_bwd_tc05(&ps->attn_bwd[l], s)
-                                : attention_bwd_fused(&ps->attn_bwd[l], s, !e->fuse_delta));
+         attention_bwd_fused(&ps->attn_bwd[l], s, !e->fuse_delta));
     if (w.lora[VITATK_SITE_QKV].rank > 0) RUN_GEMM(CAT_BT_QKV, &p.bt_qkv);
     RUN_GEMM(CAT_BQKV, &p.bqkv);  // dxn = dqkv Wqkv + lora
-    // dh wrt h[l]; with fusion also dh * B_fc2 of the layer below (consumed first thing in its backward)
-    const int r2n = l > 0 ? e->lw[l - 1].lora[VITATK_SITE_FC2].rank : 0;
-    t_fc2_ready = e->fuse_ln_t && r2n > 0 && r2n <= 8;
-    if (t_fc2_ready)
-      RUNC(CAT_LN_BWD, 0, layernorm_bwd_t(e->dxn, e->h[l], e->st1[l], w.ln1_g, e->dh_b, e->dh_a, M, D,
-                                          e->lw[l - 1].lora[VITATK_SITE_FC2].lb_bwd, 1, r2n, e->T, 3 * LORA_PAD, s));
-    else
-      RUNC(CAT_LN_BWD, 0, layernorm_bwd(e->dxn, e->h[l], e->st1[l], w.ln1_g, e->dh_b, e->dh_a, M, D, s));
+    RUNC(CAT_LN_BWD, 0, layernorm_bwd(e->dxn, e->h[l], e->st1[l], w.ln1_g, e->dh_b, e->dh_a, M, D, s));  // dh wrt h[l]
   }
   RUN_GEMM(CAT_BPATCH, &ps->bpatch);  // dxn <- dL/d(cols)
   return 0;
@@ -534,8 +504,6 @@ int vitatk_create(const vitatk_config* cfg, vitatk_engine** out) {
   e->cfg = *cfg;
   e->num_sms = prop.multiProcessorCount;
   {
-    const char* v = getenv("VITATK_ATTN_BWD");
-    e->attn_bwd_two_kernel = v && strcmp(v, "2k") == 0;
     const char* g2 = getenv("VITATK_GEMM_2CTA");
     const char* fd = getenv("VITATK_FUSE_DELTA");
     const char* zz = getenv("VITATK_ZIGZAG");
@@ -544,12 +512,7 @@ int vitatk_create(const vitatk_config* cfg, vitatk_engine** out) {
     e->fuse_stats = !(fs && fs[0] == '0');
     const char* tc = getenv("VITATK_TC_CONST");
     e->tc_const = !(tc && tc[0] == '0') && !(g2 && g2[0] == '0') && cfg->dim % 256 == 0 && cfg->mlp_dim % 256 == 0;
-    const char* flt = getenv("VITATK_FUSE_LN_T");
-    // opt-in: measured perf-neutral on B200 (skinny GEMMs -8 ms, LayerNorm kernels +8 ms per PGD-10 step: the legacy
-    // mma.sync the LN kernels use for the projection is slow on sm_100)
-    e->fuse_ln_t = flt && flt[0] == '1' && cfg->dim == 768;
-    if (e->fuse_ln_t) e->tc_const = false;  // T then comes from the LayerNorm kernels, which write no constant columns
-    e->fuse_delta = !e->attn_bwd_two_kernel && !(g2 && g2[0] == '0') && !(fd && fd[0] == '0') && cfg->dim % 256 == 0;
+    e->fuse_delta = !(g2 && g2[0] == '0') && !(fd && fd[0] == '0') && cfg->dim % 256 == 0;
   }
   e->lw.resize(cfg->layers);
   for (int i = 0; i < 3; ++i) {
@@ -872,6 +835,11 @@ int vitatk_attack(vitatk_engine* e, const float* images, const int64_t* labels, 
 
 int vitatk_count_correct(vitatk_engine* e, const float* images, const int64_t* labels, int batch, long long* counts,
                          void* stream) {
+  if (check_batch(e, batch)) return 1;
+  if (!images || !labels || !counts) {
+    set_error("vitatk_count_correct: null argument");
+    return 1;
+  }
   if (vitatk_forward(e, images, batch, e->logits, stream)) return 1;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   RUNC(CAT_HEAD, 0, count_correct(e->logits, labels, batch, e->cfg.num_classes, counts, s));
@@ -891,7 +859,7 @@ int vitatk_k_gemm(int M, int N, int K, const void* A, int lda, const void* B, in
                   int ldo2, const void* T, int ldt, const void* LB, int ldlb, int lora_nkb, int lora_ksteps_,
                   int lora_group_cols, int epi_mode, const float* bias, const void* res, int ld_res, const float* table,
                   int table_rows, float* rowdot, int rowdot_rows, int rowdot_pad, const float* row_stats, const float* c1,
-                  float* stats_out, float stats_eps, int use_simt, void* stream) {
+                  float* stats_out, float stats_eps, void* stream) {
   GemmPlan p;
   GemmEpilogue ep = {};
   ep.mode = epi_mode;
@@ -908,13 +876,6 @@ int vitatk_k_gemm(int M, int N, int K, const void* A, int lda, const void* B, in
   ep.stats_out = reinterpret_cast<float2*>(stats_out);
   ep.stats_eps = stats_eps;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (use_simt) {
-    p.M = M; p.N = N; p.K = K; p.BN = 0;
-    p.lora_nkb = lora_nkb; p.lora_ksteps = lora_ksteps_; p.lora_group_cols = lora_group_cols; p.epi = ep;
-    return gemm_launch_simt(&p, static_cast<const bf16*>(A), lda, static_cast<const bf16*>(B), ldb,
-                            static_cast<bf16*>(out), ldo, static_cast<bf16*>(out2), ldo2, static_cast<const bf16*>(T),
-                            ldt, static_cast<const bf16*>(LB), ldlb, s);
-  }
   if (gemm_plan_init(&p, M, N, K, static_cast<const bf16*>(A), lda, static_cast<const bf16*>(B), ldb,
                      static_cast<bf16*>(out), ldo, static_cast<bf16*>(out2), ldo2, static_cast<const bf16*>(T), ldt,
                      static_cast<const bf16*>(LB), ldlb, lora_nkb, lora_ksteps_, lora_group_cols, ep))
@@ -924,23 +885,11 @@ int vitatk_k_gemm(int M, int N, int K, const void* A, int lda, const void* B, in
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   return gemm_launch(&p, s, sms);
 }
-int vitatk_k_attention_fwd(const void* qkv, void* out, int batch, int tokens, int heads, void* stream) {
-  return attention_fwd(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), batch, tokens, heads,
-                       static_cast<cudaStream_t>(stream));
-}
 int vitatk_k_attention_fwd_tc05(const void* qkv, void* out, float* lse2, int batch, int tokens, int heads, void* stream) {
   AttnFwdPlan p;
   if (attention_fwd_plan_init(&p, static_cast<const bf16*>(qkv), static_cast<bf16*>(out), lse2, batch, tokens, heads))
     return 1;
   return attention_fwd_tc05(&p, static_cast<cudaStream_t>(stream));
-}
-int vitatk_k_attention_bwd_tc05(const void* qkv, const void* dout, const void* o, const float* lse2, float* delta,
-                                void* dqkv, int batch, int tokens, int heads, void* stream) {
-  AttnBwdPlan p;
-  if (attention_bwd_plan_init(&p, static_cast<const bf16*>(qkv), static_cast<const bf16*>(dout),
-                              static_cast<const bf16*>(o), lse2, delta, static_cast<bf16*>(dqkv), batch, tokens, heads))
-    return 1;
-  return attention_bwd_tc05(&p, static_cast<cudaStream_t>(stream));
 }
 int vitatk_k_attention_bwd_fused(const void* qkv, const void* dout, const void* o, const float* lse2, float* delta,
                                  void* dqkv, int batch, int tokens, int heads, void* stream) {
@@ -953,11 +902,6 @@ int vitatk_k_attention_bwd_fused(const void* qkv, const void* dout, const void* 
 int vitatk_k_gemm_trace(long long* dev_buf) { return gemm_set_trace(dev_buf); }
 int vitatk_k_attention_bwd_trace(long long* dev_buf) { return attention_bwd_set_trace(dev_buf); }
 int vitatk_k_attention_fwd_trace(long long* dev_buf) { return attention_fwd_set_trace(dev_buf); }
-int vitatk_k_attention_bwd(const void* qkv, const void* dout, void* dqkv, int batch, int tokens, int heads,
-                           void* stream) {
-  return attention_bwd(static_cast<const bf16*>(qkv), static_cast<const bf16*>(dout), static_cast<bf16*>(dqkv), batch,
-                       tokens, heads, static_cast<cudaStream_t>(stream));
-}
 int vitatk_k_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* stats, int rows,
                            int cols, float eps, void* stream) {
   return layernorm_fwd(static_cast<const bf16*>(x), gamma, beta, static_cast<bf16*>(y),
@@ -968,20 +912,6 @@ int vitatk_k_layernorm_bwd(const void* dy, const void* x, const float* stats, co
   return layernorm_bwd(static_cast<const bf16*>(dy), static_cast<const bf16*>(x),
                        reinterpret_cast<const float2*>(stats), gamma, static_cast<const bf16*>(dres),
                        static_cast<bf16*>(dx), rows, cols, static_cast<cudaStream_t>(stream));
-}
-int vitatk_k_layernorm_fwd_t(const void* x, const float* gamma, const float* beta, void* y, float* stats, int rows,
-                             int cols, float eps, const void* lora, int groups, int rank, void* T, int ldt, void* stream) {
-  return layernorm_fwd_t(static_cast<const bf16*>(x), gamma, beta, static_cast<bf16*>(y), reinterpret_cast<float2*>(stats),
-                         rows, cols, eps, static_cast<const bf16*>(lora), groups, rank, static_cast<bf16*>(T), ldt,
-                         static_cast<cudaStream_t>(stream));
-}
-int vitatk_k_layernorm_bwd_t(const void* dy, const void* x, const float* stats, const float* gamma, const void* dres,
-                             void* dx, int rows, int cols, const void* lora, int groups, int rank, void* T, int ldt,
-                             void* stream) {
-  return layernorm_bwd_t(static_cast<const bf16*>(dy), static_cast<const bf16*>(x), reinterpret_cast<const float2*>(stats),
-                         gamma, static_cast<const bf16*>(dres), static_cast<bf16*>(dx), rows, cols,
-                         static_cast<const bf16*>(lora), groups, rank, static_cast<bf16*>(T), ldt,
-                         static_cast<cudaStream_t>(stream));
 }
 int vitatk_k_layernorm_stats(const void* x, float* stats, int rows, int cols, float eps, void* stream) {
   return layernorm_stats(static_cast<const bf16*>(x), reinterpret_cast<float2*>(stats), rows, cols, eps,

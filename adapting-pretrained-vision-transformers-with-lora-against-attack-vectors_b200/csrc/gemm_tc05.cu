@@ -105,12 +105,6 @@ __device__ __forceinline__ void gelu_and_grad_p(float u, float& g, float& d) {
   d = fmaf(u, pb, phi);
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi);
-__device__ __forceinline__ float gelu_exact(float u) { return 0.5f * u * (1.0f + erff(u * 0.70710678118654752f)); }
-__device__ __forceinline__ float gelu_grad(float u) {
-  const float cdf = 0.5f * (1.0f + erff(u * 0.70710678118654752f));
-  const float pdf = 0.3989422804014327f * expf(-0.5f * u * u);
-  return cdf + u * pdf;
-}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -860,41 +854,6 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------------------------
-// scalar reference kernel (tests only): same math, one thread per output element
-// ---------------------------------------------------------------------------------------------
-__global__ void gemm_simt_kernel(GemmKernelArgs args, const bf16* A, int lda, const bf16* B, int ldb, bf16* out,
-                                 int ldo, bf16* out2, int ldo2, const bf16* T, int ldt, const bf16* LB, int ldlb) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  const int m = blockIdx.y;
-  if (n >= args.N || m >= args.M) return;
-  float acc = 0.f;
-  for (int k = 0; k < args.K; ++k)
-    acc += __bfloat162float(A[(size_t)m * lda + k]) * __bfloat162float(B[(size_t)n * ldb + k]);
-  if (args.lora_nkb > 0) {
-    const int tcol0 = args.lora_group_cols > 0 ? (n / args.lora_group_cols) * 64 : 0;
-    for (int j = 0; j < args.lora_nkb; ++j)
-      for (int k = 0; k < args.lora_ksteps * 16; ++k)
-        acc += __bfloat162float(T[(size_t)m * ldt + tcol0 + j * 64 + k]) *
-               __bfloat162float(LB[(size_t)n * ldlb + j * 64 + k]);
-  }
-  const GemmEpilogue& e = args.epi;
-  if (e.row_stats) acc = e.row_stats[m].y * (acc - e.row_stats[m].x * e.c1[n]);
-  if (e.bias) acc += e.bias[n];
-  if (e.mode == EPI_RESIDUAL) acc += __bfloat162float(e.res[(size_t)m * e.ld_res + n]);
-  if (e.mode == EPI_MUL) acc *= __bfloat162float(e.res[(size_t)m * e.ld_res + n]);
-  if (e.mode == EPI_ROWTABLE) acc += e.table[(size_t)(m % e.table_rows) * args.N + n];
-  if (e.mode == EPI_ROWDOT)  // side buffer must be zeroed by the caller
-    atomicAdd(&e.rowdot[((size_t)(m / e.rowdot_rows) * (args.N >> 6) + (n >> 6)) * e.rowdot_pad + m % e.rowdot_rows],
-              __bfloat162float(__float2bfloat16(acc)) * __bfloat162float(e.res[(size_t)m * e.ld_res + n]));
-  if (e.mode == EPI_GELU_DUAL) {
-    out[(size_t)m * ldo + n] = __float2bfloat16(gelu_exact(acc));
-    out2[(size_t)m * ldo2 + n] = __float2bfloat16(gelu_grad(acc));
-  } else {
-    out[(size_t)m * ldo + n] = __float2bfloat16(acc);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -1079,13 +1038,14 @@ static int gemm_dbg_flags() {
 template <int BN, bool TWO, int EW = 1>
 static int launch_bn(const GemmPlan* p, cudaStream_t stream, int num_sms) {
   using Cfg = GemmCfg<BN, TWO>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce once;
+  if (once.need()) {
     VITATK_CUDA_OK(cudaFuncSetAttribute(gemm_tc05_kernel<BN, false, TWO, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::SMEM_BYTES));
+#ifdef VITATK_DBG_KERNELS
     VITATK_CUDA_OK(cudaFuncSetAttribute(gemm_tc05_kernel<BN, true, TWO, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::SMEM_BYTES));
-    attr_set = true;
+#endif
   }
   const int tile_m = TWO ? 2 * BM : BM;
   const int tiles = ((p->M + tile_m - 1) / tile_m) * (p->N / BN);
@@ -1103,18 +1063,27 @@ static int launch_bn(const GemmPlan* p, cudaStream_t stream, int num_sms) {
   a.gelu_f32 = gemm_gelu_f32();
   a.reverse_m = p->reverse_m;
   const dim3 grid(TWO ? 2 * units : units, 1, 1), block(gemm_threads(TWO, EW), 1, 1);
-  if (a.dbg)
+#ifdef VITATK_DBG_KERNELS  // timing-experiment instantiations (VITATK_GEMM_DBG switches) are not part of the product build
+  if (a.dbg) {
     VITATK_CUDA_OK(launch_pdl(gemm_tc05_kernel<BN, true, TWO, EW>, grid, block, Cfg::SMEM_BYTES, stream, TWO ? 2 : 1, p->tmA,
                               p->tmB, p->tmLA, p->tmLB, p->tmOut, p->tmOut2, p->tmAux, a));
-  else
-    VITATK_CUDA_OK(launch_pdl(gemm_tc05_kernel<BN, false, TWO, EW>, grid, block, Cfg::SMEM_BYTES, stream, TWO ? 2 : 1, p->tmA,
+    return 0;
+  }
+#endif
+  VITATK_CUDA_OK(launch_pdl(gemm_tc05_kernel<BN, false, TWO, EW>, grid, block, Cfg::SMEM_BYTES, stream, TWO ? 2 : 1, p->tmA,
                               p->tmB, p->tmLA, p->tmLB, p->tmOut, p->tmOut2, p->tmAux, a));
   return 0;
 }
 
 int gemm_set_trace(long long* dev_buf) {
+#ifdef VITATK_DBG_KERNELS
   VITATK_CUDA_OK(cudaMemcpyToSymbol(g_gemm_trace, &dev_buf, sizeof(dev_buf)));
   return 0;
+#else
+  (void)dev_buf;
+  set_error("gemm_set_trace: build with -DVITATK_DBG_KERNELS (VITATK_DBG_BUILD=1) for the in-kernel timeline");
+  return 1;
+#endif
 }
 
 int gemm_launch(const GemmPlan* p, cudaStream_t stream, int num_sms) {
@@ -1133,25 +1102,6 @@ int gemm_launch(const GemmPlan* p, cudaStream_t stream, int num_sms) {
   }
   set_error("gemm_launch: bad BN %d", p->BN);
   return 1;
-}
-
-int gemm_launch_simt(const GemmPlan* p, const bf16* A, int lda, const bf16* B, int ldb, bf16* out, int ldo,
-                     bf16* out2, int ldo2, const bf16* T, int ldt, const bf16* LB, int ldlb, cudaStream_t stream) {
-  GemmKernelArgs a;
-  a.M = p->M;
-  a.N = p->N;
-  a.K = p->K;
-  a.lora_nkb = p->lora_nkb;
-  a.lora_ksteps = p->lora_ksteps;
-  a.lora_group_cols = p->lora_group_cols;
-  a.epi = p->epi;
-  a.dbg = 0;
-  a.reverse_m = 0;
-  a.gelu_f32 = 1;
-  dim3 grid((p->N + 127) / 128, p->M);
-  gemm_simt_kernel<<<grid, 128, 0, stream>>>(a, A, lda, B, ldb, out, ldo, out2, ldo2, T, ldt, LB, ldlb);
-  VITATK_CUDA_OK(cudaGetLastError());
-  return 0;
 }
 
 }  // namespace vitatk

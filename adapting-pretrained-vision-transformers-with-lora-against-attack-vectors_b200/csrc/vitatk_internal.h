@@ -36,6 +36,21 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #endif
 bool pdl_enabled();
+
+// cudaFuncSetAttribute (the > 48 KB dynamic shared memory opt-in) applies to the CURRENT device only, so "done once" has
+// to be remembered per device: a process may hold engines on several GPUs (Engine(device="cuda:1")).
+struct PerDeviceOnce {
+  unsigned long long done = 0;
+  bool need() {
+    int d = 0;
+    cudaGetDevice(&d);
+    const unsigned long long bit = 1ull << (d & 63);
+    if (done & bit) return false;
+    done |= bit;
+    return true;
+  }
+};
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                               int cluster_x, Args&&... args) {
@@ -130,9 +145,6 @@ int gemm_plan_init(GemmPlan* p, int M, int N, int K, const bf16* A, int lda, con
                    bf16* out, int ldo, bf16* out2, int ldo2, const bf16* T, int ldt, const bf16* LB, int ldlb,
                    int lora_nkb, int lora_ksteps, int lora_group_cols, GemmEpilogue epi);
 int gemm_launch(const GemmPlan* p, cudaStream_t stream, int num_sms);
-// Scalar CUDA-core GEMM with identical semantics; used by tests to cross-check the tcgen05 kernel.
-int gemm_launch_simt(const GemmPlan* p, const bf16* A, int lda, const bf16* B, int ldb, bf16* out, int ldo,
-                     bf16* out2, int ldo2, const bf16* T, int ldt, const bf16* LB, int ldlb, cudaStream_t stream);
 
 int make_tmap_3d(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1_bytes,
                  uint64_t s2_bytes, uint32_t b0, uint32_t b1, int swizzle_bytes = 128);
@@ -150,28 +162,24 @@ struct AttnFwdPlan {
 };
 int attention_fwd_plan_init(AttnFwdPlan* p, const bf16* qkv, bf16* out, float* lse2, int batch, int tokens, int heads);
 int attention_fwd_tc05(const AttnFwdPlan* p, cudaStream_t stream);
-// tcgen05 backward: dQ kernel (also produces delta) then dK/dV kernel; lse2 comes from the forward.
+// tcgen05 backward (single fused pass, attention_bwd_fused.cu); lse2 comes from the forward.
 struct AttnBwdPlan {
   int batch, tokens, heads;
   const bf16 *dout, *o;
   const float* lse2;
   float* delta;  // [batch*heads, 208] scratch
   bf16* dqkv;
-  CUtensorMap tmQKV128, tmQKV208, tmDO128, tmDO208, tmDqkv;
-  CUtensorMap tmDqkv32;  // 32-column x 32-row store boxes, 64B swizzle (fused kernel)
+  CUtensorMap tmQKV128, tmQKV208, tmDO208;
+  CUtensorMap tmDqkv32;  // 32-column x 32-row store boxes, 64B swizzle
 };
 int attention_bwd_plan_init(AttnBwdPlan* p, const bf16* qkv, const bf16* dout, const bf16* o, const float* lse2,
                             float* delta, bf16* dqkv, int batch, int tokens, int heads);
-int attention_bwd_tc05(const AttnBwdPlan* p, cudaStream_t stream);        // two-kernel version (dQ, then dK/dV)
-// single-pass version (engine default); compute_delta = false when delta was already produced (EPI_ROWDOT GEMM)
+// compute_delta = false when delta was already produced by the proj-backward GEMM (EPI_ROWDOT)
 int attention_bwd_fused(const AttnBwdPlan* p, cudaStream_t stream, bool compute_delta);
+// In-kernel clock64 timelines (timing experiments only): compiled in with -DVITATK_DBG_KERNELS, otherwise they fail.
 int gemm_set_trace(long long* dev_buf);
-int attention_bwd_set_trace(long long* dev_buf);                          // timing experiments only
-int attention_fwd_set_trace(long long* dev_buf);                          // timing experiments only
-// mma.sync forward (round-1 first version, kept for cross-checking the tcgen05 kernel in tests)
-int attention_fwd(const bf16* qkv, bf16* out, int batch, int tokens, int heads, cudaStream_t stream);
-int attention_bwd(const bf16* qkv, const bf16* dout, bf16* dqkv, int batch, int tokens, int heads,
-                  cudaStream_t stream);
+int attention_bwd_set_trace(long long* dev_buf);
+int attention_fwd_set_trace(long long* dev_buf);
 
 // ---------------------------------------------------------------------------------------------
 // LayerNorm / head / PGD kernels (HBM-bound)
@@ -183,12 +191,6 @@ int layernorm_fwd(const bf16* x, const float* gamma, const float* beta, bf16* y,
 // dx_out = dres + LN_backward(dy) ; x is the saved LN input, stats = (mean, rstd)
 int layernorm_bwd(const bf16* dy, const bf16* x, const float2* stats, const float* gamma, const bf16* dres,
                   bf16* dx_out, int rows, int cols, cudaStream_t stream);
-// Variants that also write the LoRA down-projection of their output: T[row, 64 g + j] = out[row, :] . lora[64 g + j, :]
-// for g < groups, j < ceil8(rank) (lora: bf16 [64 * groups, cols], rows >= rank zero; groups * ceil(rank/8) <= 6; cols 768)
-int layernorm_fwd_t(const bf16* x, const float* gamma, const float* beta, bf16* y, float2* stats, int rows, int cols,
-                    float eps, const bf16* lora, int groups, int rank, bf16* T, int ldt, cudaStream_t stream);
-int layernorm_bwd_t(const bf16* dy, const bf16* x, const float2* stats, const float* gamma, const bf16* dres, bf16* dx_out,
-                    int rows, int cols, const bf16* lora, int groups, int rank, bf16* T, int ldt, cudaStream_t stream);
 // final LN on CLS rows + classifier + softmax-CE; writes logits, per-image loss, and (optionally) the
 // gradient wrt the final hidden state (non-CLS rows zero-filled).  dlogits == nullptr: the cotangent is
 // softmax - onehot (cross-entropy); otherwise the caller's [batch, classes] fp32 cotangent (vector-Jacobian product).

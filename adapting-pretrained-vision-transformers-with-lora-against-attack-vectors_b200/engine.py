@@ -49,7 +49,12 @@ def _strip(name: str) -> str:
 
 
 def collect_adapters(model: torch.nn.Module) -> Dict[str, List[Adapter]]:
-    """Find LoRA-wrapped Linears on the module tree -> {linear name: [(A, B, scale)]}."""
+    """Find LoRA-wrapped Linears on the module tree -> {linear name: [(A, B, scale)]}.
+
+    Only what ``model(x)`` really applies is returned (peft ``lora.Linear.forward``): adapters listed in the layer's
+    ``active_adapters`` that are not merged into ``base_layer.weight`` (a merged adapter already lives in the base weight
+    the engine packs) and only while ``disable_adapters`` is off.  DoRA layers change the function (magnitude vector) and
+    are rejected."""
     found: Dict[str, List[Adapter]] = {}
     for name, mod in model.named_modules():
         if not (hasattr(mod, "lora_A") and hasattr(mod, "lora_B")):
@@ -57,13 +62,50 @@ def collect_adapters(model: torch.nn.Module) -> Dict[str, List[Adapter]]:
         key = _strip(name)
         la, lb = mod.lora_A, mod.lora_B
         if isinstance(la, (torch.nn.ModuleDict, dict)):  # peft: one entry per adapter name
+            if bool(getattr(mod, "disable_adapters", False)):
+                continue
+            active = getattr(mod, "active_adapters", None)
+            if active is None:
+                active = getattr(mod, "active_adapter", None)
+            if isinstance(active, str):
+                active = [active]
+            active = list(la.keys()) if active is None else list(active)
+            merged_names = getattr(mod, "merged_adapters", None)
+            if merged_names is None and bool(getattr(mod, "merged", False)):
+                merged_names = list(la.keys())  # old peft: one flag for the whole layer
+            merged_names = set(merged_names or [])
             scaling = getattr(mod, "scaling", {})
+            use_dora = getattr(mod, "use_dora", {})
+            magnitude = getattr(mod, "lora_magnitude_vector", None)
             for ad in la.keys():
+                if ad not in active or ad in merged_names:
+                    continue
+                dora = (use_dora.get(ad, False) if isinstance(use_dora, dict) else bool(use_dora)) or (
+                    magnitude is not None and len(magnitude) > 0 and ad in magnitude)
+                if dora:
+                    raise _lib.VitatkError(f"{name}: adapter '{ad}' uses DoRA (lora_magnitude_vector), which the engine "
+                                           "does not implement")
                 found.setdefault(key, []).append(
                     (la[ad].weight.detach(), lb[ad].weight.detach(), float(scaling.get(ad, 1.0))))
         else:  # oracle.LoraLinear-style: plain parameters + .scale
             found.setdefault(key, []).append((la.detach(), lb.detach(), float(getattr(mod, "scale", 1.0))))
     return found
+
+
+def model_fingerprint(model: torch.nn.Module):
+    """Cheap identity of everything an engine packs from ``model``: (storage pointer, in-place version) of every
+    parameter plus each LoRA layer's active / merged / disabled adapter state.  ``compile_model`` rebuilds the engine
+    when it changes (optimizer steps, ``load_state_dict``, peft ``set_adapter`` / ``merge_adapter`` ... all do)."""
+    items = [(p.data_ptr(), p._version, tuple(p.shape)) for p in model.parameters()]
+    for name, mod in model.named_modules():
+        if hasattr(mod, "lora_A") and isinstance(mod.lora_A, (torch.nn.ModuleDict, dict)):
+            active = getattr(mod, "active_adapters", None)
+            if active is None:
+                active = getattr(mod, "active_adapter", None)
+            active = (active,) if isinstance(active, str) else tuple(active or ())
+            items.append((name, active, tuple(getattr(mod, "merged_adapters", None) or ()),
+                          bool(getattr(mod, "merged", False)), bool(getattr(mod, "disable_adapters", False))))
+    return tuple(items)
 
 
 def normalise_state_dict(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
@@ -169,7 +211,13 @@ class Engine:
 
     # ------------------------------------------------------------------ weight packing
     def _dev(self, t: torch.Tensor, dtype) -> torch.Tensor:
-        t = t.detach().to(device=self.device, dtype=dtype).contiguous()
+        """Host tensor -> device buffer the engine borrows.  Layout and dtype are fixed on the HOST, so the upload is one
+        cudaMemcpy per tensor and no ATen kernel runs on the device (the driver's kernel list of a run then starts with
+        the engine's own kernels)."""
+        t = t.detach()
+        if t.device.type != "cpu":
+            t = t.cpu()
+        t = t.to(dtype).contiguous().to(self.device)
         self._keep.append(t)
         return t
 
@@ -181,7 +229,7 @@ class Engine:
     def _upload(self, sd: Dict[str, torch.Tensor]) -> None:
         bf, f32 = torch.bfloat16, torch.float32
         D = self.dim
-        g = lambda k: sd[k].detach().to(self.device, torch.float32)  # noqa: E731
+        g = lambda k: sd[k].detach().to("cpu", torch.float32)  # noqa: E731  (all packing math runs on the host)
         pw = g("vit.embeddings.patch_embeddings.projection.weight").reshape(D, -1)
         if pw.shape[1] != 768:
             raise _lib.VitatkError("patch embedding must be 3x16x16")
@@ -261,17 +309,17 @@ class Engine:
                 continue
             G = len(names)
             gamma, beta = fold.get(site, (None, None))
-            la_fwd = torch.zeros(LORA_PAD * G, n_in, device=self.device)
-            lb_fwd = torch.zeros(n_out * G, LORA_PAD, device=self.device)
-            lb_bwd = torch.zeros(LORA_PAD * G, n_out * G, device=self.device)
-            la_bwd = torch.zeros(n_in, LORA_PAD * G, device=self.device)
-            c2 = torch.zeros(n_out * G, device=self.device)
+            la_fwd = torch.zeros(LORA_PAD * G, n_in)
+            lb_fwd = torch.zeros(n_out * G, LORA_PAD)
+            lb_bwd = torch.zeros(LORA_PAD * G, n_out * G)
+            la_bwd = torch.zeros(n_in, LORA_PAD * G)
+            c2 = torch.zeros(n_out * G)
             rmax = 0
             for gi, ads in enumerate(groups):
                 r0 = 0
                 for (A, B, s) in ads:
-                    A = A.to(self.device, torch.float32)
-                    B = B.to(self.device, torch.float32)
+                    A = A.detach().to("cpu", torch.float32)
+                    B = B.detach().to("cpu", torch.float32)
                     r = A.shape[0]
                     if A.shape != (r, n_in) or B.shape != (n_out, r):
                         raise _lib.VitatkError(f"adapter shape mismatch on {names[gi]}: A {tuple(A.shape)} B {tuple(B.shape)}")
@@ -285,13 +333,14 @@ class Engine:
                         c2[n_out * gi: n_out * (gi + 1)] += s * (B @ (A @ beta))
                     r0 += r
                 rmax = max(rmax, r0)
-            bufs = [self._dev(t, torch.bfloat16) for t in (la_fwd, lb_fwd, lb_bwd, la_bwd)]
+            host_bf = [t.to(torch.bfloat16) for t in (la_fwd, lb_fwd, lb_bwd, la_bwd)]
+            bufs = [self._dev(t, torch.bfloat16) for t in host_bf]
             _lib.check(self.lib.vitatk_set_lora(self._h, l, site, rmax, *[b.data_ptr() for b in bufs]),
                        f"vitatk_set_lora(layer {l}, site {site})")
             if gamma is not None:
                 # c1 share from the bf16 operands: row n of group gi sees sum_j lb_fwd[n, j] * sum_k la_fwd[64 gi + j, k]
-                a_sum = bufs[0].float().sum(1).reshape(G, LORA_PAD)
-                lb = bufs[1].float().reshape(G, n_out, LORA_PAD)
+                a_sum = host_bf[0].float().sum(1).reshape(G, LORA_PAD)
+                lb = host_bf[1].float().reshape(G, n_out, LORA_PAD)
                 c1 = torch.einsum("gnj,gj->gn", lb, a_sum).reshape(-1)
                 shares[site] = (c1, c2)
         return shares
@@ -312,6 +361,10 @@ class Engine:
     def _lab(self, y: torch.Tensor, b: int) -> torch.Tensor:
         if y.shape != (b,):
             raise ValueError(f"expected labels [{b}], got {tuple(y.shape)}")
+        if y.device.type == "cpu" and y.numel() and (int(y.min()) < 0 or int(y.max()) >= self.num_classes):
+            # F.cross_entropy raises for these (whitebox_attacks.py:29).  Device labels are not read back here (that
+            # would serialise the stream); the head kernel guards them instead and reports a NaN loss for the image.
+            raise IndexError(f"label out of range [0, {self.num_classes})")
         if y.device != self.device or y.dtype != torch.int64 or not y.is_contiguous():
             y = y.detach().to(self.device, torch.int64).contiguous()
         return y

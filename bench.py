@@ -36,30 +36,72 @@ def algorithmic_gflop_per_image_step(r=RANK_R):
     return (fwd + bwd + 2 * L * lora) / 1e9
 
 
-def ncu_traffic_per_launch(kernel_prefix="gemm_tc05_kernel<256"):
-    """dram read+write bytes per launch of the dominant kernel from the newest committed ncu launch list
-    (profiles/*_launches_summary.json, made by scripts/ncu_launch_summary.py); None if no profile is present."""
-    import glob
+def source_sha():
+    """sha256[:12] over the CUDA sources + headers: identifies the build an ncu capture was taken on."""
+    import hashlib
 
+    h = hashlib.sha256()
+    csrc = os.path.join(ROOT, "adapting-pretrained-vision-transformers-with-lora-against-attack-vectors_b200", "csrc")
+    for f in sorted(os.listdir(csrc)):
+        if f.endswith((".cu", ".cuh", ".h")):
+            h.update(open(os.path.join(csrc, f), "rb").read())
+    return h.hexdigest()[:12]
+
+
+def ncu_profile_numbers(kernel_prefix="gemm_tc05_kernel<256"):
+    """From the newest committed ncu launch list (profiles/*_launches_summary.json, scripts/ncu_launch_summary.py):
+    dram read+write bytes per launch of the dominant kernel, the time-weighted whole-step tensor-pipe utilisation
+    (sm__pipe_tensor_cycles_active, % of peak sustained) and the source hash of the build it was captured on.
+    A capture cannot be taken inside the timed run (a number measured under a profiler is not a bench value), so the
+    line says which build the capture belongs to and whether that is the build being benchmarked."""
+    import glob
     import re
 
     def version(path):  # r01_v10_... sorts after r01_v8_...
         return [int(n) for n in re.findall(r"\d+", os.path.basename(path))]
 
+    out = {"traffic": None, "traffic_source": None, "traffic_build": None, "traffic_is_current_build": None,
+           "tensor_pipe_pct_whole_step": None, "tensor_pipe_pct_dominant_kernel": None}
     files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_launches_summary.json")), key=version)
     if not files:
-        return None, None
+        return out
     try:
-        d = json.load(open(files[-1]))["kernels"]
+        doc = json.load(open(files[-1]))
+        d = doc["kernels"]
+        out["traffic_source"] = os.path.basename(files[-1])
+        out["traffic_build"] = doc.get("source_sha")
+        out["traffic_is_current_build"] = (doc.get("source_sha") == source_sha()) if doc.get("source_sha") else False
+        out["tensor_pipe_pct_whole_step"] = doc.get("tensor_pipe_pct_time_weighted")
         # the main GEMM runs as two instantiations (8 / 16 epilogue warps): launch-weighted mean over both
         ks = [k for name, k in d.items() if name.startswith(kernel_prefix)]
         n = sum(k["launches"] for k in ks)
         if n:
-            mb = sum((k["dram_read_mb_per_launch"] + k["dram_write_mb_per_launch"]) * k["launches"] for k in ks) / n
-            return mb * 1e6, os.path.basename(files[-1])
+            out["traffic"] = 1e6 * sum((k["dram_read_mb_per_launch"] + k["dram_write_mb_per_launch"]) * k["launches"]
+                                       for k in ks) / n
+            if all("tensor_pipe_pct" in k for k in ks):
+                out["tensor_pipe_pct_dominant_kernel"] = sum(k["tensor_pipe_pct"] * k["us_total"] for k in ks) / max(
+                    sum(k["us_total"] for k in ks), 1e-9)
     except Exception:
         pass
-    return None, None
+    return out
+
+
+def hbm_bytes_per_launch(batch, r=RANK_R):
+    """Algorithmic HBM bytes of one launch of every HBM-bound kernel category: what must be read and
+    written once, bf16 activations, no re-reads.  M = batch * 197 token rows."""
+    M, D, F = batch * 197, 768, 3072
+    tw = 64 * 2  # one 64-column group of T per row
+    px = batch * 3 * 224 * 224
+    return {
+        "layernorm_bwd": 4 * M * D * 2,                 # dy, x, dres in; dx out
+        "layernorm_fwd": 2 * M * D * 2,
+        "t_qkv": M * D * 2 + M * 3 * tw, "t_proj": M * D * 2 + M * tw, "t_fc1": M * D * 2 + M * tw,
+        "t_fc2": M * F * 2 + M * tw, "bt_fc2": M * D * 2 + M * tw, "bt_fc1": M * F * 2 + M * tw,
+        "bt_proj": M * D * 2 + M * tw, "bt_qkv": M * 3 * D * 2 + M * 3 * tw,
+        "pixel": px * 16,                                # update: g (bf16) + x0 + adv in, adv (fp32) + im2col (bf16) out
+        "attention_fwd": M * 3 * D * 2 + M * D * 2,      # q|k|v in, o out
+        "attention_bwd": M * 3 * D * 2 * 2 + M * D * 2,  # q|k|v + dO in, dq|dk|dv out
+    }
 
 
 def workload_config(world, batch):
@@ -158,6 +200,49 @@ def cpu_reference_run(steps, warmup, sample_batch):
                       f"+ torchattacks-PGD restatement), {total:.1f} s, {warmup} warm-up"}, total / max(len(times), 1)
 
 
+def gpu_eager_baseline(dev, sample_batch=64):
+    """"The reference on this box" (SURVEY 8(d)): the oracle's PGD-10 run by eager PyTorch on the same B200, fp32 (what the
+    reference scripts do) and under bf16 autocast (its best stock configuration).  Outside the timed region; a reported
+    baseline only."""
+    import torch
+
+    from oracle import vit_oracle as vo
+    from vitatk import synthetic
+
+    model = synthetic.random_vit(CLASSES, seed=0)
+    adapters = synthetic.random_adapters(model, r=RANK_R, seed=0)
+    vo.attach_lora(model, r=RANK_R, alpha=16.0, targets=vo.ALL_TARGETS, seed=0)
+    with torch.no_grad():
+        for name, mod in model.named_modules():
+            if isinstance(mod, vo.LoraLinear):
+                A, B, _ = adapters[name][0]
+                mod.lora_A.copy_(A)
+                mod.lora_B.copy_(B)
+    model.to(dev)
+    x, y = synthetic.images_and_labels(sample_batch, 0, CLASSES, seed=0)
+    x, y = x.to(dev), y.to(dev)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    out = {"unit": UNIT, "sample": f"PGD-10 on {sample_batch} images, eager PyTorch oracle on the same GPU, 1 warm-up + 2 timed"}
+    for tag, ctx in (("fp32", None), ("bf16_autocast", torch.autocast("cuda", dtype=torch.bfloat16))):
+        def run():
+            if ctx is None:
+                return vo.pgd(model, x, y, eps=EPS, alpha=ALPHA, steps=PGD_STEPS, random_start=True)
+            with ctx:
+                return vo.pgd(model, x, y, eps=EPS, alpha=ALPHA, steps=PGD_STEPS, random_start=True)
+        run()
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(2):
+            run()
+        b.record()
+        torch.cuda.synchronize(dev)
+        out[tag] = 2 * sample_batch / (a.elapsed_time(b) / 1e3)
+    del model
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -169,7 +254,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": dict(workload_config(max(args.gpus, 1), args.batch), reference_sample_batch=sample),
+        "config": workload_config(max(args.gpus, 1), args.batch),
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -330,7 +415,18 @@ def run_engine(args):
     peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
     total_prof_ms = sum(v["ms"] for v in prof.values())
     gflop_img = algorithmic_gflop_per_image_step() * PGD_STEPS
-    traffic, traffic_src = ncu_traffic_per_launch()
+    ncu_nums = ncu_profile_numbers()
+    hbm_peak = float(peaks["hbm_gbs"])
+    hbm_bytes = hbm_bytes_per_launch(batch)
+
+    def detail(k, v):
+        """[ms per step, achieved GFLOP/s (0 for non-GEMM), achieved HBM GB/s, fraction of the measured HBM peak]"""
+        row = [round(v["ms"], 3), round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 1) if v["flops"] else 0]
+        if k in hbm_bytes and v["launches"]:
+            gbs = hbm_bytes[k] * v["launches"] / max(v["ms"], 1e-9) / 1e6
+            row += [round(gbs, 1), round(gbs / hbm_peak, 3)]
+        return row
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -341,7 +437,12 @@ def run_engine(args):
                 "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8, "d2h_bytes_per_step": adv_host.numel() * 4},
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "achieved": gemm_tflops, "peak": peak, "unit": "TFLOP/s",
-                     "frac": gemm_tflops / peak, "traffic": traffic, "traffic_source": traffic_src,
+                     "frac": gemm_tflops / peak, "traffic": ncu_nums["traffic"],
+                     "traffic_source": ncu_nums["traffic_source"], "traffic_build": ncu_nums["traffic_build"],
+                     "traffic_is_current_build": ncu_nums["traffic_is_current_build"], "build": source_sha(),
+                     "tensor_pipe_pct_whole_step_ncu": ncu_nums["tensor_pipe_pct_whole_step"],
+                     "tensor_pipe_pct_dominant_kernel_ncu": ncu_nums["tensor_pipe_pct_dominant_kernel"],
+                     "hbm_peak_gbs": hbm_peak,
                      "algorithmic_flops_per_launch": gemm["flops"] / max(gemm["launches"], 1),
                      "avg_launch_us": gemm["ms"] * 1e3 / max(gemm["launches"], 1),
                      "kernel": "gemm_tc05_kernel (all main GEMM launches of one PGD-10 step, CUDA events per launch)",
@@ -350,18 +451,122 @@ def run_engine(args):
                      "whole_step_tensor_frac": value / world * gflop_img * 1e9 / 1e12 / peak},
         "breakdown_ms_per_step": {k: round(v["ms"], 3) for k, v in prof.items()},
         "breakdown_launches": {k: v["launches"] for k, v in prof.items()},
-        "breakdown_detail": {k: [round(v["ms"], 3), round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 1) if v["flops"] else 0]
-                             for k, v in eng.last_profile_detail.items() if v["launches"]},
+        "breakdown_detail_columns": ["ms_per_step", "GFLOP/s", "HBM GB/s (algorithmic bytes)", "frac of measured HBM peak"],
+        "breakdown_detail": {k: detail(k, v) for k, v in eng.last_profile_detail.items() if v["launches"]},
         "robust": {"clean_correct": int(counts[0]), "robust_correct": int(counts[1]), "total": int(counts[2]),
                    "linf": linf, "eps_f32": float(torch.tensor(EPS, dtype=torch.float32))},
     }
     if world == 1 and not args.no_cpu_baseline:
-        base, _ = cpu_reference_run(steps=1, warmup=0, sample_batch=4)
+        eng.close()
+        del eng
+        torch.cuda.empty_cache()
+        line["gpu_eager_baseline"] = gpu_eager_baseline(dev)
+        base, _ = cpu_reference_run(steps=1, warmup=1, sample_batch=4)
         line["cpu_baseline"] = base
     out.emit(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------------
+# config 1: the reference's own CPU-runnable case -- batched_fgsm_attack, batch 8 (BASELINE configs[0])
+# ---------------------------------------------------------------------------------------------------------
+def run_config1(args):
+    """FGSM eps=8/255 on ViT-B/16 with LoRA r=8 on q,k,v, batch 8, 21 classes.  One step = one FGSM attack of 8 images =
+    ~250 kernel launches of a few microseconds each, i.e. launch-bound when issued one by one: the device-resident number
+    replays the attack as ONE CUDA graph; `e2e` goes through the drop-in `batched_fgsm_attack` with host tensors."""
+    out = StdoutToStderr()
+    import torch
+
+    import vitatk
+    from oracle import vit_oracle as vo
+    from vitatk import synthetic
+
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    B = 8
+    model = synthetic.random_vit(CLASSES, seed=0)
+    qkv_sites = tuple(s for s in synthetic.LORA_SITES if s.rsplit(".", 1)[-1] in ("query", "key", "value"))
+    adapters = synthetic.random_adapters(model, r=RANK_R, seed=0, sites=qkv_sites)
+    eng = vitatk.Engine(model=model, adapters=adapters, max_batch=B, device=dev)
+    x_host, y_host = synthetic.images_and_labels(B, 0, CLASSES, seed=0, pin=True)
+    x, y = x_host.to(dev), y_host.to(dev)
+    adv = torch.empty_like(x)
+    side = torch.cuda.Stream(dev)
+    with torch.cuda.stream(side):
+        for _ in range(max(args.warmup, 3)):
+            eng.attack(x, y, EPS, EPS, 1, start="none", out=adv)
+    torch.cuda.synchronize(dev)
+    l0 = eng.launch_count
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        eng.attack(x, y, EPS, EPS, 1, start="none", out=adv)
+    launches_per_step = eng.launch_count - l0
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize(dev)
+    sampler = ClockSampler(dev.index or 0)
+    sampler.start()
+    steps = max(args.steps, 50)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms_graph = e0.elapsed_time(e1) / steps
+    # the same attack issued launch by launch (what the graph removes)
+    e0.record()
+    for _ in range(steps):
+        eng.attack(x, y, EPS, EPS, 1, start="none", out=adv)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms_eager = e0.elapsed_time(e1) / steps
+    clocks = sampler.stop()
+    # end to end through the reference's call shape with HOST tensors (whitebox_attacks.py:164)
+    mean = torch.tensor(vo.IMAGENET_MEAN).view(1, 3, 1, 1)
+    std = torch.tensor(vo.IMAGENET_STD).view(1, 3, 1, 1)
+    vitatk.batched_fgsm_attack(model, x_host, y_host, EPS, mean, std)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        adv_host = vitatk.batched_fgsm_attack(model, x_host, y_host, EPS, mean, std)
+    torch.cuda.synchronize(dev)
+    ms_e2e = (time.perf_counter() - t0) * 1e3 / steps
+    assert adv_host.device.type == "cpu" and float((adv_host - x_host).abs().max()) <= float(torch.tensor(EPS)) + 1e-9
+    # CPU baseline: the reference path itself (oracle port of batched_fgsm_attack) on the host cores, batch 8
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cm = synthetic.random_vit(CLASSES, seed=0)
+    vo.attach_lora(cm, r=RANK_R, alpha=16.0, targets=("query", "key", "value"), seed=0)
+    vo.fgsm(cm, x_host, y_host, EPS)
+    t0 = time.perf_counter()
+    vo.fgsm(cm, x_host, y_host, EPS)
+    cpu_s = time.perf_counter() - t0
+    peaks, peaks_kind = measured_peaks()
+    gflop = algorithmic_gflop_per_image_step(r=0) * B  # + LoRA on q,k,v only: < 0.3 %
+    line = {
+        "metric": "FGSM adv images/sec, ViT-B/16 (LoRA r=8 on q,k,v) bs8 (BASELINE configs[0])", "value": B / (ms_graph / 1e3),
+        "unit": UNIT, "n_gpus": 1, "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_graph,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "whitebox_attacks.py FGSM eps=8/255, ViT-B/16 LoRA r=8 on q,k,v, batch 8, 224x224, 21 classes "
+                               "(BASELINE configs[0])", "global_batch": B, "parallelism": "dp1",
+                   "l2": "working set (~0.45 GB of activations) exceeds L2; one CUDA-graph replay per step"},
+        "clocks": clocks,
+        "e2e": {"value": B / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8,
+                "d2h_bytes_per_step": x_host.numel() * 4, "api": "vitatk.batched_fgsm_attack(model, host images, ...)"},
+        "gpu_launches": launches_per_step * steps,
+        "launch_by_launch_ms_per_step": ms_eager, "cuda_graph_speedup": ms_eager / ms_graph,
+        "roofline": {"bound": "tensor", "achieved": gflop / ms_graph, "peak": float(peaks["bf16_tflops"]) , "unit": "TFLOP/s",
+                     "frac": gflop / ms_graph / float(peaks["bf16_tflops"]), "traffic": None,
+                     "note": "batch 8 = 1576 token rows = 7 pair tiles per N-tile: latency-bound, far from either roofline",
+                     "peak_kind": f"{peaks_kind} burst cuBLAS bf16"},
+        "cpu_baseline": {"value": B / cpu_s, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"1 x FGSM on {B} images (fp32 torch CPU oracle of whitebox_attacks.py:22-38), {cpu_s:.1f} s, 1 warm-up"},
+    }
+    out.emit(json.dumps(line))
     return 0
 
 
@@ -373,11 +578,15 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH, help="images per GPU (BASELINE: 256)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2],
+                    help="BASELINE.json configs, 1-based: 1 = FGSM batch 8 (CUDA graph), 2 = PGD-10 batch 256 (the metric; default)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "engine":
         args.warmup = 3  # timing rules: W >= 3
     if args.impl == "reference":
         return run_reference(args)
+    if args.config == 1:
+        return run_config1(args)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.gpus > 1 and world == 1:
         # convenience: re-launch under torchrun (the driver launches torchrun itself)

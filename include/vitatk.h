@@ -161,39 +161,27 @@ int vitatk_k_gemm(int M, int N, int K, const void* A_dev, int lda, const void* B
                   int lora_nkb, int lora_ksteps, int lora_group_cols, int epi_mode, const float* bias_dev,
                   const void* res_dev, int ld_res, const float* table_dev, int table_rows, float* rowdot_dev,
                   int rowdot_rows, int rowdot_pad, const float* row_stats_dev, const float* c1_dev, float* stats_out_dev,
-                  float stats_eps, int use_simt, void* stream);
-int vitatk_k_attention_fwd(const void* qkv_dev, void* out_dev, int batch, int tokens, int heads, void* stream);
+                  float stats_eps, void* stream);
 /* tcgen05 forward (the engine's path); lse2_dev (optional) receives [batch*heads, 208] log2-domain logsumexp */
 int vitatk_k_attention_fwd_tc05(const void* qkv_dev, void* out_dev, float* lse2_dev, int batch, int tokens, int heads,
                                 void* stream);
-/* tcgen05 backward, two-kernel version (dQ, then dK/dV): needs the forward's output o_dev and lse2_dev; delta_dev is a zero-
- * initialised [batch*heads, 208] fp32 scratch; dqkv_dev [batch*tokens, 3*D] receives dq | dk | dv */
-int vitatk_k_attention_bwd_tc05(const void* qkv_dev, const void* dout_dev, const void* o_dev, const float* lse2_dev,
-                                float* delta_dev, void* dqkv_dev, int batch, int tokens, int heads, void* stream);
-/* single-pass tcgen05 backward (the engine's path; same arguments as the two-kernel version above) */
+/* single-pass tcgen05 backward (the engine's path): needs the forward's output o_dev and lse2_dev; delta_dev is a
+ * [batch*heads, 208] fp32 scratch that receives rowsum(dO o O); dqkv_dev [batch*tokens, 3*D] receives dq | dk | dv */
 int vitatk_k_attention_bwd_fused(const void* qkv_dev, const void* dout_dev, const void* o_dev, const float* lse2_dev,
                                  float* delta_dev, void* dqkv_dev, int batch, int tokens, int heads, void* stream);
 /* timing experiments: device buffer of 4096 int64 receiving CTA 0's (event, step, clock64) timeline when
- * VITATK_ATTN_DBG has bit 32 set (scripts/attn_trace.py, scripts/attn_fwd_trace.py); null switches it off */
+ * VITATK_ATTN_DBG has bit 32 set (scripts/attn_trace.py, scripts/attn_fwd_trace.py); null switches it off.  The
+ * instrumented kernels are only compiled with -DVITATK_DBG_KERNELS (VITATK_DBG_BUILD=1 python -c "import vitatk._lib
+ * as l; l.build(force=True)"); in the product build these three calls fail with an explanatory error. */
 int vitatk_k_gemm_trace(long long* dev_buf);  /* pair GEMM epilogue timeline (VITATK_GEMM_DBG & 512), scripts/gemm_trace.py */
 int vitatk_k_attention_bwd_trace(long long* trace_dev);
 int vitatk_k_attention_fwd_trace(long long* trace_dev);
-int vitatk_k_attention_bwd(const void* qkv_dev, const void* dout_dev, void* dqkv_dev, int batch, int tokens,
-                           int heads, void* stream);
 int vitatk_k_layernorm_fwd(const void* x_dev, const float* gamma_dev, const float* beta_dev, void* y_dev,
                            float* stats_dev, int rows, int cols, float eps, void* stream);
 /* (mean, rstd) per row only (stats_dev fp32 [rows, 2]) */
 int vitatk_k_layernorm_stats(const void* x_dev, float* stats_dev, int rows, int cols, float eps, void* stream);
 int vitatk_k_layernorm_bwd(const void* dy_dev, const void* x_dev, const float* stats_dev, const float* gamma_dev,
                            const void* dres_dev, void* dx_dev, int rows, int cols, void* stream);
-/* LayerNorm variants that also write T[row, 64 g + j] = out[row, :] . lora[64 g + j, :] (the LoRA x*A^T of the site the
- * output feeds; lora bf16 [64 * groups, cols], rows >= rank zero; cols must be 768, groups * ceil(rank / 8) <= 6) */
-int vitatk_k_layernorm_fwd_t(const void* x_dev, const float* gamma_dev, const float* beta_dev, void* y_dev,
-                             float* stats_dev, int rows, int cols, float eps, const void* lora_dev, int groups, int rank,
-                             void* T_dev, int ldt, void* stream);
-int vitatk_k_layernorm_bwd_t(const void* dy_dev, const void* x_dev, const float* stats_dev, const float* gamma_dev,
-                             const void* dres_dev, void* dx_dev, int rows, int cols, const void* lora_dev, int groups,
-                             int rank, void* T_dev, int ldt, void* stream);
 int vitatk_k_pgd_update(const void* dcols_dev, const float* x0_dev, float* adv_dev, void* cols_dev, int batch,
                         const float* mean3, const float* std3, float eps, float alpha, void* stream);
 int vitatk_k_pgd_init(const float* x0_dev, const float* noise_dev, float* adv_dev, void* cols_dev, int batch,

@@ -48,3 +48,29 @@ def weights_checksum(model) -> np.ndarray:
     tot = sum(float(sd[k].double().sum()) for k in keys)
     tot_abs = sum(float(sd[k].double().abs().sum()) for k in keys)
     return np.array([tot, tot_abs, float(len(keys))])
+
+
+def make_structured_inputs(batch: int, seed: int = 7, grid: int = 2, noise: float = 0.05, index0: int = 0):
+    """Smooth colour-blob images (bilinear-upsampled ``grid x grid`` random colours + a little pixel noise), one
+    generator per GLOBAL image index.  Unlike i.i.d. uniform noise — which every random-init ViT maps to nearly the same
+    logits — these spread the clean predictions over many classes with top-1 margins of ~0.2, so a robust-accuracy
+    comparison is informative (self-labelled: clean accuracy is 100 % by construction)."""
+    xs = []
+    for i in range(batch):
+        g = torch.Generator().manual_seed(seed * 1_000_003 + index0 + i)
+        low = torch.rand(1, 3, grid, grid, generator=g)
+        x = torch.nn.functional.interpolate(low, size=(224, 224), mode="bilinear", align_corners=False)
+        x = x + noise * (torch.rand(1, 3, 224, 224, generator=g) - 0.5)
+        xs.append(x.clamp(0, 1))
+    return torch.cat(xs)
+
+
+ROBUST_EPS = 0.35 / 255   # FGSM budget of the robust-accuracy fixture (tests/golden/make_golden_robust.py picks it)
+ROBUST_BATCH = 64
+
+
+def margins(logits: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+    """logit[label] - max(other logits): > 0 <=> top-1 correct."""
+    own = logits.gather(1, labels[:, None])[:, 0]
+    other = logits.masked_fill(torch.nn.functional.one_hot(labels, logits.shape[1]).bool(), float("-inf")).max(1).values
+    return own - other

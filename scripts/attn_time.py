@@ -20,7 +20,6 @@ def t(fn, n=10):
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / n * 1e3
 fwd = lambda: _lib.check(lib.vitatk_k_attention_fwd_tc05(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, T, H, s))
-bwd2k = lambda: _lib.check(lib.vitatk_k_attention_bwd_tc05(qkv.data_ptr(), dout.data_ptr(), out.data_ptr(), lse.data_ptr(), delta.data_ptr(), dqkv.data_ptr(), B, T, H, s))
 print("dbg", os.environ.get("VITATK_ATTN_DBG", "0"), "fwd us", round(t(fwd), 1))
 bwdf = lambda: _lib.check(lib.vitatk_k_attention_bwd_fused(qkv.data_ptr(), dout.data_ptr(), out.data_ptr(), lse.data_ptr(), delta.data_ptr(), dqkv.data_ptr(), B, T, H, s))
 print("dbg", os.environ.get("VITATK_ATTN_DBG", "0"), "bwd fused us", round(t(bwdf), 1))

@@ -20,6 +20,13 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def golden_robust():
+    import numpy as np
+
+    return np.load(os.path.join(ROOT, "tests", "golden", "robust_fgsm.npz"))
+
+
+@pytest.fixture(scope="session")
 def lib():
     from vitatk import _lib
 

@@ -11,13 +11,18 @@ import torch
 pytestmark = pytest.mark.gpu
 
 RTOL_LOGITS = 2e-2   # ||logits - ref|| / ||ref||
-RTOL_GRAD = 5e-2     # ||grad - ref|| / ||ref||  (bf16 activations AND bf16 gradients through 12 layers)
+RTOL_GRAD = 2e-2     # ||grad - ref|| / ||ref||  (north_star: rtol 2e-2 for per-step input gradients)
 MIN_COS = 0.998
 MIN_SIGN_AGREE = 0.93
 
 
 def rel(a, b):
     return float((a.float() - b.float()).norm() / b.float().norm())
+
+
+def note(**kv):
+    """Measured values next to their gates (shown with pytest -s / -rA)."""
+    print("  measured: " + ", ".join(f"{k}={v:.5f}" if isinstance(v, float) else f"{k}={v}" for k, v in kv.items()))
 
 
 def cos(a, b):
@@ -52,6 +57,7 @@ def test_logits_and_grad_vs_oracle(setup, which):
     g, logits, loss = eng.input_grad(x, y)
     oloss, ologits, og = vo.input_grad(m, x, y)
     assert torch.isfinite(g).all() and torch.isfinite(logits).all()
+    note(which=which, rel_logits=rel(logits, ologits), rel_grad=rel(g, og), cos=cos(g, og))
     assert rel(logits, ologits) < RTOL_LOGITS, rel(logits, ologits)
     assert abs(float(loss.mean()) - float(oloss)) < 2e-2 * abs(float(oloss))
     assert rel(g, og) < RTOL_GRAD, rel(g, og)
@@ -118,6 +124,7 @@ def test_pgd_stepwise_parity_and_invariants(setup, golden):
     cur = x
     for step in range(3):
         g, _, loss = eng.input_grad(cur, y)
+        note(step=step, rel_grad=rel(g, tr["grads"][step]))
         assert rel(g, tr["grads"][step]) < RTOL_GRAD, (step, rel(g, tr["grads"][step]))
         assert abs(float(loss.mean()) - float(tr["losses"][step])) < 3e-2 * float(tr["losses"][step])
         cur = tr["advs"][step]
@@ -196,6 +203,161 @@ def test_robust_accuracy_counts(setup, golden):
     atk.set_normalization_used(vo.IMAGENET_MEAN, vo.IMAGENET_STD)
     counts = robust_accuracy_counts(eng, atk, x, y2).tolist()
     assert counts == golden["lora_counts_selflabel_pgd3"].tolist() == [4, 0, 4]
+
+
+def test_robust_accuracy_is_informative_and_matches_the_reference(golden_robust):
+    """Non-vacuous robust-accuracy gate (north_star: agree within 0.5 points).
+
+    (1) The committed fixture (tests/golden/robust_fgsm.npz) holds what the REFERENCE's own batched_fgsm_attack does to 64
+        self-labelled structured images at eps = 0.35/255: robust accuracy strictly inside (10 %, 90 %).  The engine must
+        reproduce the robust / broken verdict of every image whose margin is not within bf16 noise of zero.
+    (2) 0.5 points of 64 images is a third of an image, so the 0.5-point gate itself is evaluated on 4096 images against
+        the fp32 oracle run live on this GPU (same images, same labels, each side attacking with its own gradients)."""
+    import vitatk
+    from oracle import fixtures as fx
+    from oracle import vit_oracle as vo
+
+    m = fx.make_model(lora=True)
+    eng = vitatk.Engine(model=m, max_batch=256, device="cuda")
+    m.cuda()
+    eps = float(golden_robust["eps"])
+    assert eps == fx.ROBUST_EPS
+    gc = golden_robust["counts"].tolist()
+    assert gc[0] == gc[2] == fx.ROBUST_BATCH and 0.1 * gc[2] < gc[1] < 0.9 * gc[2], gc
+
+    def engine_side(x, y):
+        adv = eng.attack(x, y, eps, eps, 1, start="none")
+        assert float((adv - x).abs().max()) <= float(torch.tensor(eps, dtype=torch.float32))
+        return fx.margins(eng.logits(adv), y)
+
+    # ---- (1) the committed reference fixture ----
+    x = fx.make_structured_inputs(fx.ROBUST_BATCH).cuda()
+    y = torch.from_numpy(golden_robust["labels"]).cuda()
+    cm = torch.from_numpy(golden_robust["clean_margin"]).cuda()
+    clean_ok = eng.logits(x).argmax(-1) == y
+    assert bool(clean_ok[cm > 0.03].all()) and int((~clean_ok).sum()) <= 2, "clean top-1 must agree with the reference"
+    gm = torch.from_numpy(golden_robust["adv_margin"]).cuda()
+    em = engine_side(x, y)
+    clear = gm.abs() > 0.03  # ~4x the engine's absolute logit error on this model
+    n_eng = int((em > 0).sum())
+    note(golden_robust=gc[1], engine_robust=n_eng, clear_images=int(clear.sum()),
+         max_margin_err=float((em - gm).abs().max()))
+    assert int(clear.sum()) >= 45
+    assert torch.equal((em > 0)[clear], (gm > 0)[clear]), "robust / broken verdict differs on a clear-margin image"
+    assert abs(n_eng - gc[1]) <= int((~clear).sum())
+    assert float((em - gm).abs().max()) < 0.08
+    # ---- (2) 4096 images, engine vs fp32 oracle on this GPU ----
+    N, bs = 4096, 256
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    tot = rob_e = rob_o = clean_e = 0
+    for i0 in range(0, N, bs):
+        xb = fx.make_structured_inputs(bs, index0=1000 + i0).cuda()
+        with torch.no_grad():
+            yb = torch.cat([vo.logits_of(m, xb[j:j + 64]).argmax(-1) for j in range(0, bs, 64)])
+        clean_e += int((eng.logits(xb).argmax(-1) == yb).sum())
+        rob_e += int((engine_side(xb, yb) > 0).sum())
+        for j in range(0, bs, 64):
+            adv_o = vo.fgsm(m, xb[j:j + 64], yb[j:j + 64], eps)
+            with torch.no_grad():
+                rob_o += int((vo.logits_of(m, adv_o).argmax(-1) == yb[j:j + 64]).sum())
+        tot += bs
+    acc_e, acc_o = 100.0 * rob_e / tot, 100.0 * rob_o / tot
+    note(images=tot, robust_acc_engine=acc_e, robust_acc_oracle=acc_o, clean_acc_engine=100.0 * clean_e / tot)
+    assert 10.0 < acc_o < 90.0, acc_o
+    assert abs(acc_e - acc_o) <= 0.5, (acc_e, acc_o)
+    assert clean_e >= tot - 0.005 * tot  # clean top-1 agreement with the oracle's labels
+    eng.close()
+
+
+def test_full_batch_pgd10_random_start_rows_vs_oracle():
+    """BASELINE configs[1] shape: batch 256, PGD-10, eps 8/255, alpha 2/255, random start (shared noise).  At every one
+    of the 10 steps the gradient the engine used -- for 8 sampled rows of the 256 -- is compared with the fp32 oracle's
+    gradient AT THE SAME iterate (rtol 2e-2), and the engine's next iterate must be exactly the reference update
+    (sign step, projection, clamp) of its own gradient."""
+    import vitatk
+    from oracle import fixtures as fx
+    from oracle import vit_oracle as vo
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    m = fx.make_model(lora=True)
+    eng = vitatk.Engine(model=m, max_batch=256, device="cuda")
+    m.cuda()
+    g = torch.Generator().manual_seed(123)
+    x = torch.rand(256, 3, 224, 224, generator=g).cuda()
+    y = torch.randint(0, fx.NUM_CLASSES, (256,), generator=g).cuda()
+    noise = torch.empty(256, 3, 224, 224).uniform_(-fx.EPS, fx.EPS, generator=g).cuda()
+    rows = torch.tensor([0, 37, 64, 101, 128, 190, 222, 255], device="cuda")
+    eps32 = float(torch.tensor(fx.EPS, dtype=torch.float32))
+    cur = torch.clamp(x + noise, 0, 1)
+    worst = 0.0
+    for step in range(10):
+        nxt = eng.attack(x, y, fx.EPS, fx.ALPHA, step + 1, start="noise", noise=noise)  # iterate after step + 1 updates
+        if step == 0:  # the engine's random start is clamp(x + noise) up to the strict-ball ulp rule
+            first = eng.attack(x, y, fx.EPS, 0.0, 1, start="noise", noise=noise)
+            assert float((first - cur).abs().max()) <= 6e-8
+            cur = first
+        ge, _, _ = eng.input_grad(cur, y)  # the gradient the attack used at this iterate (deterministic kernels)
+        _, _, go = vo.input_grad(m, cur[rows], y[rows])
+        go = go * (rows.numel() / 256.0)  # mean CE over 8 rows -> mean over 256 (whitebox_attacks.py:29)
+        r = rel(ge[rows], go)
+        worst = max(worst, r)
+        assert r < RTOL_GRAD, (step, r)
+        stepped = cur + fx.ALPHA * ge.sign()
+        want = torch.clamp(x + torch.clamp(stepped - x, min=-fx.EPS, max=fx.EPS), 0, 1)
+        assert float((nxt - want).abs().max()) <= 6e-8, step  # one ulp: the strict-ball rule
+        assert float((nxt != want).float().mean()) < 0.05
+        assert float((nxt - x).abs().max()) <= eps32
+        cur = nxt
+    note(worst_rel_grad_over_10_steps=worst)
+    eng.close()
+
+
+def test_label_range_and_engines_on_two_devices():
+    """out-of-range labels must not read out of bounds (host labels raise like F.cross_entropy, device labels
+    give a NaN loss for that image only); and a second engine on another GPU of the same process gets its own
+    shared-memory opt-in."""
+    import vitatk
+    from oracle import fixtures as fx
+
+    m = fx.make_model(lora=True)
+    x, y = fx.make_inputs()
+    eng = vitatk.Engine(model=m, max_batch=4, device="cuda:0")
+    bad = y.clone()
+    bad[1] = fx.NUM_CLASSES
+    with pytest.raises(IndexError):
+        eng.input_grad(x.cuda(), bad)  # host labels: checked before the launch
+    g, _, loss = eng.input_grad(x.cuda(), bad.cuda())
+    assert torch.isnan(loss[1]) and torch.isfinite(loss[[0, 2, 3]]).all() and torch.isfinite(g).all()
+    g0, l0, _ = eng.input_grad(x.cuda(), y.cuda())
+    if torch.cuda.device_count() >= 2:
+        eng1 = vitatk.Engine(model=m, max_batch=4, device="cuda:1")
+        g1, l1, _ = eng1.input_grad(x.to("cuda:1"), y.to("cuda:1"))
+        assert torch.equal(l1.cpu(), l0.cpu()) and torch.equal(g1.cpu(), g0.cpu())
+        eng1.close()
+    eng.close()
+
+
+def test_engine_cache_follows_weight_updates():
+    """compile_model re-packs when the model changed (in-place parameter update) instead of attacking stale
+    weights."""
+    import vitatk
+    from oracle import fixtures as fx
+
+    m = fx.make_model(lora=True)
+    x, _ = fx.make_inputs()
+    x = x.cuda()
+    e1 = vitatk.compile_model(m, max_batch=4, device="cuda")
+    l1 = e1.logits(x)
+    assert vitatk.compile_model(m, max_batch=4) is e1  # unchanged model: cached
+    with torch.no_grad():
+        m.classifier.bias += 1.0
+    e2 = vitatk.compile_model(m, max_batch=4)
+    assert e2 is not e1
+    l2 = e2.logits(x)
+    assert float((l2 - l1 - 1.0).abs().max()) < 1e-5
+    vitatk.invalidate(m)
 
 
 def test_vjp_with_arbitrary_cotangent_vs_oracle_autograd(setup):
@@ -330,10 +492,11 @@ def test_tensor_core_constants_match_epilogue_constants(setup, monkeypatch):
     ref.close()
 
 
-@pytest.mark.parametrize("r", [4, 16, 28])
+@pytest.mark.parametrize("r", [4, 16, 28, 32])
 def test_other_lora_ranks_vs_oracle(r):
     """Ranks around the tensor-core-constants limits: r = 4 (generic column fill), r = 16 (constants spill into a second
-    k-step), r = 28 (r + 6 > 32: the engine falls back to epilogue-loaded constants)."""
+    k-step), r = 28 (r + 6 > 32: the engine falls back to epilogue-loaded constants), r = 32 (the largest rank the
+    reference trains, train_loras.py:441: two LoRA k-steps, no constant columns)."""
     import vitatk
     from oracle import fixtures as fx
     from oracle import vit_oracle as vo
@@ -345,8 +508,41 @@ def test_other_lora_ranks_vs_oracle(r):
     m.cuda()
     g, logits, _ = eng.input_grad(x, y)
     _, ol, og = vo.input_grad(m, x, y)
+    note(r=r, rel_logits=rel(logits, ol), rel_grad=rel(g, og))
     assert rel(logits, ol) < RTOL_LOGITS, (r, rel(logits, ol))
     assert rel(g, og) < RTOL_GRAD, (r, rel(g, og))
+    assert cos(g, og) > MIN_COS
+    eng.close()
+
+
+def test_stacked_adapters_total_rank_64_vs_oracle():
+    """eval_compose.py stacks adapters: two rank-32 adapters on every Linear run un-merged as ONE rank-64 adapter (the
+    padded maximum: four LoRA k-steps, constants loaded in the epilogue) and must match the fp32 oracle of the model with
+    both adapters applied."""
+    import vitatk
+    from oracle import fixtures as fx
+    from oracle import vit_oracle as vo
+    from vitatk.engine import collect_adapters
+
+    m1 = fx.make_model(lora=True, r=32)
+    m2 = fx.make_model(lora=False)
+    vo.attach_lora(m2, r=32, alpha=16.0, targets=vo.ALL_TARGETS, seed=31, b_std=0.02)
+    second = collect_adapters(m2)
+    eng = vitatk.Engine(model=m1, adapters=second, max_batch=4, device="cuda")
+    # oracle of the same function: merge the second adapter into the first model's base weights (fp32)
+    with torch.no_grad():
+        for name, ads in second.items():
+            mod = m1.get_submodule(name)
+            for (A, B, s) in ads:
+                mod.base.weight += s * (B @ A)
+    x, y = fx.make_inputs()
+    x, y = x.cuda(), y.cuda()
+    m1.cuda()
+    g, logits, _ = eng.input_grad(x, y)
+    _, ol, og = vo.input_grad(m1, x, y)
+    note(rel_logits=rel(logits, ol), rel_grad=rel(g, og))
+    assert rel(logits, ol) < RTOL_LOGITS, rel(logits, ol)
+    assert rel(g, og) < RTOL_GRAD, rel(g, og)
     assert cos(g, og) > MIN_COS
     eng.close()
 

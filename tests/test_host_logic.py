@@ -361,6 +361,105 @@ def test_peft_adapter_config_variants(tmp_path):
         compose({q + ".weight": torch.zeros(768, 768)}, [d2])
 
 
+def test_adapter_state_of_a_live_peft_layer_is_honoured(tmp_path):
+    """collect_adapters must return what model(x) applies -- peft's lora.Linear runs only ACTIVE adapters that
+    are not MERGED into base_layer.weight, nothing while adapters are disabled, and DoRA is a different function."""
+    import vitatk
+    from vitatk import _lib
+    from vitatk.adapters import read_adapter, write_adapter
+    from vitatk.engine import collect_adapters, model_fingerprint
+
+    class StubLoraLinear(torch.nn.Module):  # the attributes peft 0.15 lora.Linear exposes (peft itself is not installed)
+        def __init__(self):
+            super().__init__()
+            self.base_layer = torch.nn.Linear(16, 12)
+            self.lora_A = torch.nn.ModuleDict({n: torch.nn.Linear(16, r, bias=False) for n, r in (("a", 4), ("b", 2), ("c", 3))})
+            self.lora_B = torch.nn.ModuleDict({n: torch.nn.Linear(r, 12, bias=False) for n, r in (("a", 4), ("b", 2), ("c", 3))})
+            self.scaling = {"a": 4.0, "b": 8.0, "c": 1.0}
+            self.active_adapters = ["a", "c"]      # "b" is loaded but inactive
+            self.merged_adapters = ["c"]           # "c" is already inside base_layer.weight
+            self.disable_adapters = False
+            self.use_dora = {"a": False, "b": False, "c": False}
+            self.lora_magnitude_vector = torch.nn.ModuleDict()
+
+        @property
+        def merged(self):
+            return bool(self.merged_adapters)
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.vit = torch.nn.Module()
+            self.vit.q = StubLoraLinear()
+
+    net = Net()
+    found = collect_adapters(net)
+    assert list(found) == ["vit.q"] and len(found["vit.q"]) == 1
+    A, B, s = found["vit.q"][0]
+    assert A.shape == (4, 16) and B.shape == (12, 4) and s == 4.0  # only "a": active and not merged
+    fp0 = model_fingerprint(net)
+    net.vit.q.active_adapters = ["a", "b"]
+    assert [t[2] for t in collect_adapters(net)["vit.q"]] == [4.0, 8.0]
+    assert model_fingerprint(net) != fp0                      # adapter state is part of the engine cache key
+    fp1 = model_fingerprint(net)
+    with torch.no_grad():
+        net.vit.q.base_layer.weight.add_(1.0)                 # an optimizer step / load_state_dict bumps _version
+    assert model_fingerprint(net) != fp1
+    net.vit.q.disable_adapters = True
+    assert collect_adapters(net) == {}
+    net.vit.q.disable_adapters = False
+    net.vit.q.use_dora["a"] = True
+    with pytest.raises(_lib.VitatkError):
+        collect_adapters(net)
+    # adapter directories: DoRA configs / tensors are rejected instead of silently dropped
+    q = "vit.encoder.layer.0.attention.attention.query"
+    g = torch.Generator().manual_seed(1)
+    d = str(tmp_path / "dora")
+    write_adapter(d, {q: (torch.randn(8, 768, generator=g), torch.randn(768, 8, generator=g), 2.0)}, lora_alpha=16.0)
+    from safetensors.torch import load_file, save_file
+    st = os.path.join(d, "adapter_model.safetensors")
+    t = dict(load_file(st))
+    t[f"base_model.model.{q}.lora_magnitude_vector.default.weight"] = torch.ones(768)
+    save_file(t, st)
+    with pytest.raises(ValueError):
+        read_adapter(d)
+    import json
+    del t[f"base_model.model.{q}.lora_magnitude_vector.default.weight"]
+    save_file(t, st)
+    cfg = json.load(open(os.path.join(d, "adapter_config.json")))
+    cfg["use_dora"] = True
+    json.dump(cfg, open(os.path.join(d, "adapter_config.json"), "w"))
+    with pytest.raises(ValueError):
+        read_adapter(d)
+    assert vitatk.invalidate is not None
+
+
+def test_torchattacks_inverse_normalize_flag_is_explicit_and_off_by_default():
+    """SURVEY 8(c) hazard: the as-run reference (whitebox_attacks.py:169) makes torchattacks attack x*std+mean and
+    return (adv-mean)/std.  The engine only does that behind an explicit flag; the host-side transform pair is checked
+    here with a stand-in for the engine loop."""
+    import vitatk
+
+    core = torch.nn.Linear(4, 2)
+    mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+    assert vitatk.PGD(core)._inverse_normalize is False and vitatk.FGSM(core)._inverse_normalize is False
+    atk = vitatk.PGD(core, eps=8 / 255, torchattacks_inverse_normalize=True)
+    atk.set_normalization_used(mean, std)
+    seen = {}
+
+    def fake_forward(images, labels):  # stands in for the engine: records what it is asked to attack, adds +eps
+        seen["x"] = images.clone()
+        return torch.clamp(images + atk.eps, 0, 1)
+
+    atk.forward = fake_forward
+    x = torch.rand(2, 3, 8, 8)
+    out = atk(x, torch.zeros(2, dtype=torch.long))
+    m = torch.tensor(mean).view(1, 3, 1, 1)
+    s = torch.tensor(std).view(1, 3, 1, 1)
+    assert torch.allclose(seen["x"], x * s + m)                       # attack runs on the inverse-normalised batch
+    assert torch.allclose(out, x + (8 / 255) / s, atol=1e-6)         # returned tensor = x + delta / std
+
+
 def test_c_host_example_links_against_the_abi(c_example):
     assert os.path.exists(c_example)
 

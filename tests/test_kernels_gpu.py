@@ -27,7 +27,7 @@ def _dgelu(u):
 
 
 def run_gemm(lib, A, B, epi=EPI_PLAIN, bias=None, res=None, table=None, T=None, LB=None, nkb=0, ksteps=0,
-             group_cols=0, simt=False, rowdot=None, rowdot_rows=0, row_stats=None, c1=None, stats_out=None):
+             group_cols=0, rowdot=None, rowdot_rows=0, row_stats=None, c1=None, stats_out=None):
     from vitatk import _lib
 
     M, K = A.shape
@@ -39,7 +39,7 @@ def run_gemm(lib, A, B, epi=EPI_PLAIN, bias=None, res=None, table=None, T=None, 
                            group_cols, epi, _p(bias), _p(res), 0 if res is None else res.stride(0), _p(table),
                            0 if table is None else table.shape[0], _p(rowdot), rowdot_rows,
                            0 if rowdot is None else rowdot.shape[1], _p(row_stats), _p(c1), _p(stats_out), 1e-12,
-                           1 if simt else 0, _s())
+                           _s())
     _lib.check(rc, "vitatk_k_gemm")
     torch.cuda.synchronize()
     return out, out2
@@ -141,11 +141,6 @@ def test_gemm_tc05_vs_torch(lib, M, N, K, epi, lora):
     check_close(out, want, f"gemm {M}x{N}x{K} epi{epi}")
     if epi == EPI_GELU_DUAL:
         check_close(out2, want2, "gelu' output")
-    if M <= 2000:  # cross-check with the scalar CUDA-core kernel (bit-level agreement is not expected)
-        s_out, s_out2 = run_gemm(lib, A, B, epi, bias, res, table, T, LB, nkb, ksteps, gc, simt=True)
-        check_close(s_out, want, "simt gemm")
-        if epi == EPI_GELU_DUAL:
-            check_close(s_out2, want2, "simt gelu'")
 
 
 @pytest.mark.parametrize("images,tokens", [(8, 197), (3, 50), (256, 197)])
@@ -195,9 +190,6 @@ def test_gemm_layernorm_fold(lib, M, N, epi):
     else:
         check_close(out, ref, "ln-fold gemm")
     torch.testing.assert_close(stats[:, 0], h.float().mean(-1), rtol=1e-4, atol=1e-4)
-    if M <= 2000:
-        s_out, _ = run_gemm(lib, h, Wf, epi, c2.contiguous(), row_stats=stats, c1=c1.contiguous(), simt=True)
-        check_close(s_out, _gelu(ref) if epi == EPI_GELU_DUAL else ref, "ln-fold simt")
 
 
 @pytest.mark.parametrize("M,N", [(197, 64), (1576, 192), (50432, 64), (50432, 192)])
@@ -235,17 +227,10 @@ def test_attention_fwd_bwd_vs_torch(lib, batch, tokens):
     g = torch.Generator(device="cuda").manual_seed(batch * 100 + tokens)
     qkv = (torch.randn(batch * tokens, 3 * D, device="cuda", generator=g) * 1.5).to(torch.bfloat16)
     dout = torch.randn(batch * tokens, D, device="cuda", generator=g).to(torch.bfloat16)
-    out = torch.full((batch * tokens, D), float("nan"), device="cuda", dtype=torch.bfloat16)
-    dqkv = torch.full((batch * tokens, 3 * D), float("nan"), device="cuda", dtype=torch.bfloat16)
     out_tc = torch.full((batch * tokens, D), float("nan"), device="cuda", dtype=torch.bfloat16)
     lse2 = torch.zeros(batch * heads, 208, device="cuda")
-    _lib.check(lib.vitatk_k_attention_fwd(_p(qkv), _p(out), batch, tokens, heads, _s()), "attention_fwd")
     _lib.check(lib.vitatk_k_attention_fwd_tc05(_p(qkv), _p(out_tc), _p(lse2), batch, tokens, heads, _s()), "attention_fwd_tc05")
-    _lib.check(lib.vitatk_k_attention_bwd(_p(qkv), _p(dout), _p(dqkv), batch, tokens, heads, _s()), "attention_bwd")
-    dqkv_tc = torch.full((batch * tokens, 3 * D), float("nan"), device="cuda", dtype=torch.bfloat16)
     delta = torch.zeros(batch * heads, 208, device="cuda")
-    _lib.check(lib.vitatk_k_attention_bwd_tc05(_p(qkv), _p(dout), _p(out_tc), _p(lse2), _p(delta), _p(dqkv_tc), batch,
-                                               tokens, heads, _s()), "attention_bwd_tc05")
     dqkv_f = torch.full((batch * tokens, 3 * D), float("nan"), device="cuda", dtype=torch.bfloat16)
     _lib.check(lib.vitatk_k_attention_bwd_fused(_p(qkv), _p(dout), _p(out_tc), _p(lse2), _p(delta), _p(dqkv_f), batch,
                                                 tokens, heads, _s()), "attention_bwd_fused")
@@ -257,13 +242,10 @@ def test_attention_fwd_bwd_vs_torch(lib, batch, tokens):
     (gx,) = torch.autograd.grad(o, x, dout.float())
     gref = gx.permute(1, 3, 0, 2, 4).reshape(batch * tokens, 3 * D)
     # probabilities and dS are rounded to bf16 before the second GEMM of each chain (fp32 accumulate)
-    check_rel(out, o.detach(), "attention out", 8e-3, 2e-2)
     check_rel(out_tc, o.detach(), "attention out (tcgen05)", 8e-3, 2e-2)
     s_ref = (q @ k.transpose(-1, -2) / 8.0).detach()
     lse_ref = torch.logsumexp(s_ref, -1).reshape(batch * heads, tokens) * 1.4426950408889634
     torch.testing.assert_close(lse2[:, :tokens], lse_ref, rtol=1e-3, atol=2e-3)
-    check_rel(dqkv, gref, "attention dqkv", 1.5e-2, 3e-2)
-    check_rel(dqkv_tc, gref, "attention dqkv (tcgen05)", 1.5e-2, 3e-2)
     for name, sl in (("dq", slice(0, D)), ("dk", slice(D, 2 * D)), ("dv", slice(2 * D, 3 * D))):
         # per-slice check; a slice that is analytically zero (tokens == 1: dq = dk = 0) is compared on the scale of dv
         ref_s = gref[:, sl] if float(gref[:, sl].norm()) > 1e-3 * float(gref.norm()) else None
@@ -297,49 +279,6 @@ def test_layernorm_fwd_bwd_vs_torch(lib, rows):
     check_close(y, yr.detach(), "ln y")
     check_close(dx, gx + dres.float(), "ln dx")
     torch.testing.assert_close(stats[:, 0], x.float().mean(-1), rtol=1e-4, atol=1e-4)
-
-
-@pytest.mark.parametrize("rows,groups,rank", [(197, 1, 8), (1576, 3, 8), (1000, 1, 16), (50432, 3, 8)])
-def test_layernorm_with_lora_projection(lib, rows, groups, rank):
-    """LN forward / backward variants that also emit T = out * A^T for the LoRA site the output feeds."""
-    from vitatk import _lib
-
-    cols = 768
-    g = torch.Generator(device="cuda").manual_seed(rows + rank)
-    x = (torch.randn(rows, cols, device="cuda", generator=g) * 2 + 0.5).to(torch.bfloat16)
-    gamma = 1 + 0.1 * torch.randn(cols, device="cuda", generator=g)
-    beta = 0.1 * torch.randn(cols, device="cuda", generator=g)
-    dy = torch.randn(rows, cols, device="cuda", generator=g).to(torch.bfloat16)
-    dres = torch.randn(rows, cols, device="cuda", generator=g).to(torch.bfloat16)
-    lora = torch.zeros(64 * groups, cols, device="cuda")
-    for gi in range(groups):
-        lora[64 * gi: 64 * gi + rank] = torch.randn(rank, cols, device="cuda", generator=g) / math.sqrt(cols)
-    lora = lora.to(torch.bfloat16)
-    y, y0 = torch.empty_like(x), torch.empty_like(x)
-    stats, stats0 = torch.empty(rows, 2, device="cuda"), torch.empty(rows, 2, device="cuda")
-    dx, dx0 = torch.empty_like(x), torch.empty_like(x)
-    T = torch.full((rows, 192), 7.0, device="cuda", dtype=torch.bfloat16)
-    _lib.check(lib.vitatk_k_layernorm_fwd(_p(x), _p(gamma), _p(beta), _p(y0), _p(stats0), rows, cols, 1e-12, _s()), "ln")
-    _lib.check(lib.vitatk_k_layernorm_fwd_t(_p(x), _p(gamma), _p(beta), _p(y), _p(stats), rows, cols, 1e-12, _p(lora),
-                                            groups, rank, _p(T), 192, _s()), "ln_fwd_t")
-    torch.cuda.synchronize()
-    assert torch.equal(y, y0) and torch.equal(stats, stats0)  # same arithmetic as the plain kernel
-    r8 = (rank + 7) // 8 * 8
-    for gi in range(groups):
-        want = y.float() @ lora[64 * gi: 64 * gi + r8].float().t()
-        got = T[:, 64 * gi: 64 * gi + r8].float()
-        assert (got - want).abs().max() <= 1e-2 * want.abs().max() + 1e-3, (gi, (got - want).abs().max())
-        assert torch.equal(T[:, 64 * gi + r8: 64 * (gi + 1)], torch.full_like(T[:, 64 * gi + r8: 64 * (gi + 1)], 7.0))
-    T.fill_(7.0)
-    _lib.check(lib.vitatk_k_layernorm_bwd(_p(dy), _p(x), _p(stats), _p(gamma), _p(dres), _p(dx0), rows, cols, _s()), "lnb")
-    _lib.check(lib.vitatk_k_layernorm_bwd_t(_p(dy), _p(x), _p(stats), _p(gamma), _p(dres), _p(dx), rows, cols, _p(lora),
-                                            groups, rank, _p(T), 192, _s()), "ln_bwd_t")
-    torch.cuda.synchronize()
-    assert torch.equal(dx, dx0)
-    for gi in range(groups):
-        want = dx.float() @ lora[64 * gi: 64 * gi + r8].float().t()
-        got = T[:, 64 * gi: 64 * gi + r8].float()
-        assert (got - want).abs().max() <= 1e-2 * want.abs().max() + 1e-3, (gi, (got - want).abs().max())
 
 
 def _cols_from_image(img, mean, std):

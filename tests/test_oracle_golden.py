@@ -81,3 +81,28 @@ def test_lora_merge_and_zero_b():
 def test_png_roundtrip_truncates():
     x = torch.tensor([0.0, 0.5, 0.999, 1.0, 1.2, -0.1])
     np.testing.assert_allclose(vo.png_roundtrip(x).numpy(), np.array([0, 127, 254, 255, 255, 0]) / 255.0, rtol=1e-6)
+
+
+def test_robust_fixture_is_informative_and_reproducible(golden_robust):
+    """tests/golden/robust_fgsm.npz (made by the REFERENCE's batched_fgsm_attack, make_golden_robust.py): robust accuracy
+    strictly inside (10 %, 90 %), reference == oracle bit for bit, and the oracle regenerates the first images' labels
+    and post-attack margins from the seeds alone."""
+    import torch
+
+    from oracle import fixtures as fx
+    from oracle import vit_oracle as vo
+
+    c = golden_robust["counts"].tolist()
+    assert c[0] == c[2] == fx.ROBUST_BATCH and 0.1 * c[2] < c[1] < 0.9 * c[2]
+    assert float(golden_robust["ref_vs_oracle_maxdiff"]) == 0.0
+    assert int((golden_robust["adv_margin"] > 0).sum()) == c[1]
+    assert len(set(golden_robust["labels"].tolist())) >= 5      # predictions spread over many classes
+    m = fx.make_model(lora=True)
+    x = fx.make_structured_inputs(4)
+    y = torch.from_numpy(golden_robust["labels"][:4])
+    with torch.no_grad():
+        assert torch.equal(vo.logits_of(m, x).argmax(-1), y)
+    adv = vo.fgsm(m, x, y, float(golden_robust["eps"]))
+    with torch.no_grad():
+        mg = fx.margins(vo.logits_of(m, adv), y)
+    assert torch.allclose(mg, torch.from_numpy(golden_robust["adv_margin"][:4]), atol=2e-4)

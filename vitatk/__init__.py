@@ -22,6 +22,7 @@ from .attacks import (  # noqa: E402,F401
     batched_fgsm_attack,
     compile_model,
     get_model_output,
+    invalidate,
 )
 from .engine import Engine  # noqa: E402,F401
 from .adapters import (  # noqa: E402,F401

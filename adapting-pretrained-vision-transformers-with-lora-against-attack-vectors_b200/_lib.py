@@ -126,7 +126,7 @@ def load() -> C.CDLL:
     lib.vitatk_count_correct.argtypes = [vp, vp, vp, i, vp, vp]
     lib.vitatk_profile_begin.argtypes = [vp]
     lib.vitatk_profile_end.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(ll)]
-    lib.vitatk_k_gemm.argtypes = [i, i, i, vp, i, vp, i, vp, i, vp, i, vp, i, vp, i, i, i, i, i, vp, vp, i, vp, i, vp, i, i, vp, vp, vp, f, vp]
+    lib.vitatk_k_gemm.argtypes = [i, i, i, vp, i, vp, i, vp, i, vp, i, vp, i, vp, i, i, i, i, i, vp, vp, i, vp, i, vp, i, i, vp, vp, vp, f, vp, i, vp, vp, vp]
     lib.vitatk_k_attention_fwd_tc05.argtypes = [vp, vp, vp, i, i, i, vp]
     lib.vitatk_k_attention_bwd_fused.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, vp]
     lib.vitatk_k_gemm_trace.argtypes = [vp]

@@ -93,8 +93,8 @@ def compile_model(model: torch.nn.Module, max_batch: int = 256, device=None, for
     if eng is not None and getattr(eng, "_h", None) is not None and not eng._h.value:
         eng = None  # closed by the caller
     if force or eng is None or eng.max_batch < max_batch or getattr(core, "_vitatk_fingerprint", None) != fp:
-        if eng is not None:
-            eng.close()
+        # (the previous engine is NOT closed here: a caller may still hold it; it frees its workspace when the last
+        # reference goes away)
         if core.training:
             raise RuntimeError("vitatk: call model.eval() first (the reference attacks an eval() model, "
                                "whitebox_attacks.py:99; dropout is not part of the attack path)")

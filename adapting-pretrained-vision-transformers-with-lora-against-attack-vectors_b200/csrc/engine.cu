@@ -52,6 +52,10 @@ struct LoraSite {
   // write 1.0 into T's matching columns.  ccol == 0: off (the epilogue loads the constants itself).
   int ccol = 0;
   bool cfold = false;
+  // QKV site only: the q, k and v adapters share ONE 64-column group (q in columns [0, rq), k in [rq, rq + rk), v after
+  // them; la_fwd [64, D], lb_fwd [3D, 64], lb_bwd [64, 3D], la_bwd [D, 64]) instead of one group each.  Host-selected
+  // when rq + rk + rv <= 64: one LoRA k-block instead of three, and the site becomes eligible for T-tiles.
+  bool packed = false;
   const bf16* lbx = nullptr;
   const float* tones = nullptr;
 };
@@ -117,6 +121,8 @@ struct vitatk_engine {
   char* cbuf = nullptr;              // backing store of the lbx / tones arrays
   bool const_dirty = true;           // weights / adapters changed since the constant columns were packed
   bool fuse_stats = true;            // folded LayerNorm: (mean, rstd) come out of the skinny LoRA GEMM (VITATK_FUSE_STATS=0: stats kernel)
+  bool fuse_tt = true;               // plain LoRA sites: T = x*A^T comes from T-tiles inside the consumer GEMM (VITATK_TT=0: skinny GEMMs)
+  unsigned int* tt_flags = nullptr;  // [2 * ceil(max M / 256)] inter-CTA flags of the T-tiles (zero between launches)
   bool fuse_delta = false;           // delta comes out of the proj-backward GEMM epilogue (pair kernel) instead of a kernel
   bool prof = false;
   struct ProfRec { int cat; double flops; cudaEvent_t a, b; };
@@ -217,6 +223,24 @@ static int build_plans(vitatk_engine* e, int batch, PlanSet** out) {
     const bool fold = w.qkv_c1 != nullptr && w.fc1_c1 != nullptr;  // LayerNorm folded into the qkv / fc1 GEMMs
     const bf16* a_ln1 = fold ? e->h[l] : e->xn;
     const bf16* a_ln2 = fold ? e->h_mid[l] : e->xn;
+    // q|k|v adapters: one shared 64-column group (packed) or one group each
+    const int q_tcols = sq.packed ? LORA_PAD : 3 * LORA_PAD;
+    const int q_nkb_bwd = sq.rank > 0 ? (sq.packed ? 1 : 3) : 0;
+    const int q_group_cols = (sq.rank > 0 && !sq.packed) ? D : 0;
+    // T-tiles: the consumer GEMM computes its own T = x * A^T (GemmTT).  n = 32 when every column the LoRA k-steps read
+    // fits, else 64.  Sites whose skinny GEMM also produces LayerNorm statistics (folded qkv / fc1) keep that GEMM.
+    auto make_tt = [&](const LoraSite& ls, const bf16* tb, int ld_tb, int ksteps, const float* bias, bool ok) {
+      GemmTT t = {};
+      if (!e->fuse_tt || !ok || ls.rank <= 0) return t;
+      t.n = ksteps * 16 <= 32 ? 32 : 64;
+      t.tb = tb;
+      t.ld_tb = ld_tb;
+      t.out = e->T;
+      t.ld_out = 3 * LORA_PAD;
+      t.bias = bias;
+      t.flags = e->tt_flags;
+      return t;
+    };
     // ---------------- forward ----------------
     if (attention_fwd_plan_init(&ps->attn_fwd[l], e->qkv[l], e->ao[l], e->lse2[l], batch, TOKENS, c.heads)) return 1;
     if (attention_bwd_plan_init(&ps->attn_bwd[l], e->qkv[l], e->dao, e->ao[l], e->lse2[l], e->delta, e->dqkv, batch,
@@ -231,7 +255,7 @@ static int build_plans(vitatk_engine* e, int batch, PlanSet** out) {
       }
       if (sq.ccol > 0 && !sq.cfold) ep.bias = sq.tones;
       if (sq.rank > 0 &&
-          gemm_plan_init(&p.t_qkv, M, 3 * LORA_PAD, D, a_ln1, D, sq.la_fwd, D, e->T, 3 * LORA_PAD, nullptr, 0, nullptr, 0,
+          gemm_plan_init(&p.t_qkv, M, q_tcols, D, a_ln1, D, sq.la_fwd, D, e->T, 3 * LORA_PAD, nullptr, 0, nullptr, 0,
                          nullptr, 0, 0, 0, 0, ep))
         return 1;
     }
@@ -245,21 +269,21 @@ static int build_plans(vitatk_engine* e, int batch, PlanSet** out) {
       if (sq.ccol > 0) ep.bias = nullptr, ep.c1 = nullptr;  // the constants ride in the LoRA k-block
       if (gemm_plan_init(&p.qkv, M, 3 * D, D, a_ln1, D, w.qkv_w, D, e->qkv[l], 3 * D, nullptr, 0, e->T, 3 * LORA_PAD,
                          sq.ccol > 0 ? sq.lbx : sq.lb_fwd, LORA_PAD, sq.rank > 0 ? 1 : 0, site_ksteps(sq),
-                         sq.rank > 0 ? D : 0, ep))
+                         q_group_cols, ep))
         return 1;
     }
     {
       GemmEpilogue ep = plain;
       if (sp.ccol > 0) ep.bias = sp.tones;  // T[:, ccol..ccol+1] = 1: proj's bias is added by the tensor core
-      if (sp.rank > 0 &&
+      const GemmTT tt = make_tt(sp, sp.la_fwd, D, site_ksteps(sp), ep.bias, true);
+      p.t_proj.M = 0;  // M == 0: not launched (T comes from the consumer's T-tiles)
+      if (sp.rank > 0 && tt.n == 0 &&
           gemm_plan_init(&p.t_proj, M, LORA_PAD, D, e->ao[l], D, sp.la_fwd, D, e->T, 3 * LORA_PAD, nullptr, 0, nullptr, 0,
                          nullptr, 0, 0, 0, 0, ep))
         return 1;
-    }
-    {
-      GemmEpilogue ep = {EPI_RESIDUAL, sp.ccol > 0 ? nullptr : w.proj_b, e->h[l], D, nullptr, 0};
+      GemmEpilogue ep2 = {EPI_RESIDUAL, sp.ccol > 0 ? nullptr : w.proj_b, e->h[l], D, nullptr, 0};
       if (gemm_plan_init(&p.proj, M, D, D, e->ao[l], D, w.proj_w, D, e->h_mid[l], D, nullptr, 0, e->T, 3 * LORA_PAD,
-                         sp.ccol > 0 ? sp.lbx : sp.lb_fwd, LORA_PAD, sp.rank > 0 ? 1 : 0, site_ksteps(sp), 0, ep))
+                         sp.ccol > 0 ? sp.lbx : sp.lb_fwd, LORA_PAD, sp.rank > 0 ? 1 : 0, site_ksteps(sp), 0, ep2, &tt))
         return 1;
     }
     {
@@ -291,42 +315,50 @@ static int build_plans(vitatk_engine* e, int batch, PlanSet** out) {
     {
       GemmEpilogue ep = plain;
       if (s2.ccol > 0) ep.bias = s2.tones;
-      if (s2.rank > 0 &&
+      const GemmTT tt = make_tt(s2, s2.la_fwd, F, site_ksteps(s2), ep.bias, true);
+      p.t_fc2.M = 0;
+      if (s2.rank > 0 && tt.n == 0 &&
           gemm_plan_init(&p.t_fc2, M, LORA_PAD, F, e->g, F, s2.la_fwd, F, e->T, 3 * LORA_PAD, nullptr, 0, nullptr, 0,
                          nullptr, 0, 0, 0, 0, ep))
         return 1;
-    }
-    {
-      GemmEpilogue ep = {EPI_RESIDUAL, s2.ccol > 0 ? nullptr : w.fc2_b, e->h_mid[l], D, nullptr, 0};
+      GemmEpilogue ep2 = {EPI_RESIDUAL, s2.ccol > 0 ? nullptr : w.fc2_b, e->h_mid[l], D, nullptr, 0};
       if (gemm_plan_init(&p.fc2, M, D, F, e->g, F, w.fc2_w, F, e->h[l + 1], D, nullptr, 0, e->T, 3 * LORA_PAD,
-                         s2.ccol > 0 ? s2.lbx : s2.lb_fwd, LORA_PAD, s2.rank > 0 ? 1 : 0, site_ksteps(s2), 0, ep))
+                         s2.ccol > 0 ? s2.lbx : s2.lb_fwd, LORA_PAD, s2.rank > 0 ? 1 : 0, site_ksteps(s2), 0, ep2, &tt))
         return 1;
     }
     // ---------------- backward ----------------
     // The residual-stream gradient ping-pongs: layer l receives it in dh_in(l) and leaves dh_out(l).
     // dh entering layer l (grad wrt h[l+1]) lives in dh_a; dh_mid in dh_b; result (grad wrt h[l]) in dh_a.
-    if (s2.rank > 0 &&
-        gemm_plan_init(&p.bt_fc2, M, LORA_PAD, D, e->dh_a, D, s2.lb_bwd, D, e->T, 3 * LORA_PAD, nullptr, 0, nullptr, 0,
-                       nullptr, 0, 0, 0, 0, plain))
-      return 1;
     {
+      const GemmTT tt = make_tt(s2, s2.lb_bwd, D, lora_ksteps(s2.rank), nullptr, true);
+      p.bt_fc2.M = 0;
+      if (s2.rank > 0 && tt.n == 0 &&
+          gemm_plan_init(&p.bt_fc2, M, LORA_PAD, D, e->dh_a, D, s2.lb_bwd, D, e->T, 3 * LORA_PAD, nullptr, 0, nullptr, 0,
+                         nullptr, 0, 0, 0, 0, plain))
+        return 1;
       GemmEpilogue ep = {EPI_MUL, nullptr, e->u[l], F, nullptr, 0};
       if (gemm_plan_init(&p.bfc2, M, F, D, e->dh_a, D, w.fc2_wt, D, e->du, F, nullptr, 0, e->T, 3 * LORA_PAD, s2.la_bwd,
-                         LORA_PAD, s2.rank > 0 ? 1 : 0, lora_ksteps(s2.rank), 0, ep))
+                         LORA_PAD, s2.rank > 0 ? 1 : 0, lora_ksteps(s2.rank), 0, ep, &tt))
         return 1;
     }
-    if (s1.rank > 0 &&
-        gemm_plan_init(&p.bt_fc1, M, LORA_PAD, F, e->du, F, s1.lb_bwd, F, e->T, 3 * LORA_PAD, nullptr, 0, nullptr, 0,
-                       nullptr, 0, 0, 0, 0, plain))
-      return 1;
-    if (gemm_plan_init(&p.bfc1, M, D, F, e->du, F, w.fc1_wt, F, e->dxn, D, nullptr, 0, e->T, 3 * LORA_PAD, s1.la_bwd,
-                       LORA_PAD, s1.rank > 0 ? 1 : 0, lora_ksteps(s1.rank), 0, plain))
-      return 1;
-    if (sp.rank > 0 &&
-        gemm_plan_init(&p.bt_proj, M, LORA_PAD, D, e->dh_b, D, sp.lb_bwd, D, e->T, 3 * LORA_PAD, nullptr, 0, nullptr, 0,
-                       nullptr, 0, 0, 0, 0, plain))
-      return 1;
     {
+      const GemmTT tt = make_tt(s1, s1.lb_bwd, F, lora_ksteps(s1.rank), nullptr, true);
+      p.bt_fc1.M = 0;
+      if (s1.rank > 0 && tt.n == 0 &&
+          gemm_plan_init(&p.bt_fc1, M, LORA_PAD, F, e->du, F, s1.lb_bwd, F, e->T, 3 * LORA_PAD, nullptr, 0, nullptr, 0,
+                         nullptr, 0, 0, 0, 0, plain))
+        return 1;
+      if (gemm_plan_init(&p.bfc1, M, D, F, e->du, F, w.fc1_wt, F, e->dxn, D, nullptr, 0, e->T, 3 * LORA_PAD, s1.la_bwd,
+                         LORA_PAD, s1.rank > 0 ? 1 : 0, lora_ksteps(s1.rank), 0, plain, &tt))
+        return 1;
+    }
+    {
+      const GemmTT tt = make_tt(sp, sp.lb_bwd, D, lora_ksteps(sp.rank), nullptr, true);
+      p.bt_proj.M = 0;
+      if (sp.rank > 0 && tt.n == 0 &&
+          gemm_plan_init(&p.bt_proj, M, LORA_PAD, D, e->dh_b, D, sp.lb_bwd, D, e->T, 3 * LORA_PAD, nullptr, 0, nullptr, 0,
+                         nullptr, 0, 0, 0, 0, plain))
+        return 1;
       // proj backward also produces attention's delta = rowsum(dO o O) per (image, head, query): one 64-column slab of
       // the output is one head, so the pair kernel's slab epilogue gets it for free (replaces a 154 MB pass)
       GemmEpilogue ep = plain;
@@ -339,16 +371,20 @@ static int build_plans(vitatk_engine* e, int batch, PlanSet** out) {
         ep.rowdot_pad = 208;
       }
       if (gemm_plan_init(&p.bproj, M, D, D, e->dh_b, D, w.proj_wt, D, e->dao, D, nullptr, 0, e->T, 3 * LORA_PAD,
-                         sp.la_bwd, LORA_PAD, sp.rank > 0 ? 1 : 0, lora_ksteps(sp.rank), 0, ep))
+                         sp.la_bwd, LORA_PAD, sp.rank > 0 ? 1 : 0, lora_ksteps(sp.rank), 0, ep, &tt))
         return 1;
     }
-    if (sq.rank > 0 &&
-        gemm_plan_init(&p.bt_qkv, M, 3 * LORA_PAD, 3 * D, e->dqkv, 3 * D, sq.lb_bwd, 3 * D, e->T, 3 * LORA_PAD, nullptr,
-                       0, nullptr, 0, nullptr, 0, 0, 0, 0, plain))
-      return 1;
-    if (gemm_plan_init(&p.bqkv, M, D, 3 * D, e->dqkv, 3 * D, w.qkv_wt, 3 * D, e->dxn, D, nullptr, 0, e->T,
-                       3 * LORA_PAD, sq.la_bwd, 3 * LORA_PAD, sq.rank > 0 ? 3 : 0, lora_ksteps(sq.rank), 0, plain))
-      return 1;
+    {
+      const GemmTT tt = make_tt(sq, sq.lb_bwd, 3 * D, lora_ksteps(sq.rank), nullptr, sq.packed);
+      p.bt_qkv.M = 0;
+      if (sq.rank > 0 && tt.n == 0 &&
+          gemm_plan_init(&p.bt_qkv, M, q_tcols, 3 * D, e->dqkv, 3 * D, sq.lb_bwd, 3 * D, e->T, 3 * LORA_PAD, nullptr,
+                         0, nullptr, 0, nullptr, 0, 0, 0, 0, plain))
+        return 1;
+      if (gemm_plan_init(&p.bqkv, M, D, 3 * D, e->dqkv, 3 * D, w.qkv_wt, 3 * D, e->dxn, D, nullptr, 0, e->T,
+                         3 * LORA_PAD, sq.la_bwd, q_tcols, q_nkb_bwd, lora_ksteps(sq.rank), 0, plain, &tt))
+        return 1;
+    }
   }
   // patch-embed input gradient: dcols = dh0 * Wpe   (written over the im2col buffer's twin)
   if (gemm_plan_init(&ps->bpatch, M, D, D, e->dh_a, D, e->patch_wt, D, e->dxn, D, nullptr, 0, nullptr, 0, nullptr, 0, 0,
@@ -359,7 +395,7 @@ static int build_plans(vitatk_engine* e, int batch, PlanSet** out) {
     // tail that is still in L2 is consumed first (the main GEMM that follows reads front to back again)
     for (auto& p : ps->layers)
       for (GemmPlan* g : {&p.t_qkv, &p.t_proj, &p.t_fc1, &p.t_fc2, &p.bt_fc2, &p.bt_fc1, &p.bt_proj, &p.bt_qkv})
-        g->reverse_m = 1;
+        if (g->M > 0) g->reverse_m = 1;
   }
   e->plans[batch] = owner.release();
   *out = ps;
@@ -420,7 +456,7 @@ static int encoder_forward(vitatk_engine* e, PlanSet* ps, int batch, cudaStream_
     if (rq > 0) RUN_GEMM(CAT_T_QKV, &p.t_qkv);
     RUN_GEMM(CAT_QKV, &p.qkv);
     RUNC(CAT_ATTN_FWD, 4.0 * batch * c.heads * TOKENS * TOKENS * 64, attention_fwd_tc05(&ps->attn_fwd[l], s));
-    if (w.lora[VITATK_SITE_PROJ].rank > 0) RUN_GEMM(CAT_T_PROJ, &p.t_proj);
+    if (w.lora[VITATK_SITE_PROJ].rank > 0 && p.t_proj.M > 0) RUN_GEMM(CAT_T_PROJ, &p.t_proj);
     RUN_GEMM(CAT_PROJ, &p.proj);
     if (fold) {
       if (!(r1 > 0 && p.t_fc1.epi.stats_out))
@@ -429,7 +465,7 @@ static int encoder_forward(vitatk_engine* e, PlanSet* ps, int batch, cudaStream_
       RUNC(CAT_LN_FWD, 0, layernorm_fwd(e->h_mid[l], w.ln2_g, w.ln2_b, e->xn, e->st2[l], M, D, c.ln_eps, s));
     if (r1 > 0) RUN_GEMM(CAT_T_FC1, &p.t_fc1);
     RUN_GEMM(CAT_FC1, &p.fc1);
-    if (w.lora[VITATK_SITE_FC2].rank > 0) RUN_GEMM(CAT_T_FC2, &p.t_fc2);
+    if (w.lora[VITATK_SITE_FC2].rank > 0 && p.t_fc2.M > 0) RUN_GEMM(CAT_T_FC2, &p.t_fc2);
     RUN_GEMM(CAT_FC2, &p.fc2);
   }
   return 0;
@@ -442,16 +478,16 @@ static int encoder_backward(vitatk_engine* e, PlanSet* ps, int batch, cudaStream
   for (int l = c.layers - 1; l >= 0; --l) {
     const LayerWeights& w = e->lw[l];
     LayerPlans& p = ps->layers[l];
-    if (w.lora[VITATK_SITE_FC2].rank > 0) RUN_GEMM(CAT_BT_FC2, &p.bt_fc2);
+    if (w.lora[VITATK_SITE_FC2].rank > 0 && p.bt_fc2.M > 0) RUN_GEMM(CAT_BT_FC2, &p.bt_fc2);
     RUN_GEMM(CAT_BFC2, &p.bfc2);  // du = (dh W2 + lora) * gelu'(u)   (u[l] holds gelu'(u), written by fc1's epilogue)
-    if (w.lora[VITATK_SITE_FC1].rank > 0) RUN_GEMM(CAT_BT_FC1, &p.bt_fc1);
+    if (w.lora[VITATK_SITE_FC1].rank > 0 && p.bt_fc1.M > 0) RUN_GEMM(CAT_BT_FC1, &p.bt_fc1);
     RUN_GEMM(CAT_BFC1, &p.bfc1);  // dxn = du W1 + lora
     RUNC(CAT_LN_BWD, 0, layernorm_bwd(e->dxn, e->h_mid[l], e->st2[l], w.ln2_g, e->dh_a, e->dh_b, M, D, s));  // dh_mid
-    if (w.lora[VITATK_SITE_PROJ].rank > 0) RUN_GEMM(CAT_BT_PROJ, &p.bt_proj);
+    if (w.lora[VITATK_SITE_PROJ].rank > 0 && p.bt_proj.M > 0) RUN_GEMM(CAT_BT_PROJ, &p.bt_proj);
     RUN_GEMM(CAT_BPROJ, &p.bproj);  // dao = dh_mid Wp + lora
     RUNC(CAT_ATTN_BWD, 8.0 * batch * c.heads * TOKENS * TOKENS * 64,
          attention_bwd_fused(&ps->attn_bwd[l], s, !e->fuse_delta));
-    if (w.lora[VITATK_SITE_QKV].rank > 0) RUN_GEMM(CAT_BT_QKV, &p.bt_qkv);
+    if (w.lora[VITATK_SITE_QKV].rank > 0 && p.bt_qkv.M > 0) RUN_GEMM(CAT_BT_QKV, &p.bt_qkv);
     RUN_GEMM(CAT_BQKV, &p.bqkv);  // dxn = dqkv Wqkv + lora
     RUNC(CAT_LN_BWD, 0, layernorm_bwd(e->dxn, e->h[l], e->st1[l], w.ln1_g, e->dh_b, e->dh_a, M, D, s));  // dh wrt h[l]
   }
@@ -508,6 +544,8 @@ int vitatk_create(const vitatk_config* cfg, vitatk_engine** out) {
     const char* fd = getenv("VITATK_FUSE_DELTA");
     const char* zz = getenv("VITATK_ZIGZAG");
     e->zigzag = !(zz && zz[0] == '0');
+    const char* tt = getenv("VITATK_TT");
+    e->fuse_tt = !(tt && tt[0] == '0') && !(g2 && g2[0] == '0') && cfg->dim % 256 == 0 && cfg->mlp_dim % 256 == 0;
     const char* fs = getenv("VITATK_FUSE_STATS");
     e->fuse_stats = !(fs && fs[0] == '0');
     const char* tc = getenv("VITATK_TC_CONST");
@@ -528,6 +566,7 @@ int vitatk_destroy(vitatk_engine* e) {
   for (auto& kv : e->plans) delete kv.second;
   if (e->ws) cudaFree(e->ws);
   if (e->cbuf) cudaFree(e->cbuf);
+  if (e->tt_flags) cudaFree(e->tt_flags);
   for (auto& r : e->prof_recs) {  // profiling events (bench.py's roofline leg)
     cudaEventDestroy(r.a);
     cudaEventDestroy(r.b);
@@ -596,10 +635,12 @@ int vitatk_set_tensor(vitatk_engine* e, int id, int layer, const void* p, long l
 
 int vitatk_set_lora(vitatk_engine* e, int layer, int site, int rank, const void* la_fwd, const void* lb_fwd,
                     const void* lb_bwd, const void* la_bwd) {
-  if (!e || layer < 0 || layer >= e->cfg.layers || site < 0 || site > 3) {
+  if (!e || layer < 0 || layer >= e->cfg.layers || site < 0 || site > VITATK_SITE_QKV_PACKED) {
     set_error("vitatk_set_lora: bad layer/site");
     return 1;
   }
+  const bool packed = site == VITATK_SITE_QKV_PACKED;
+  if (packed) site = VITATK_SITE_QKV;
   if (rank < 0 || rank > LORA_PAD) {
     set_error("vitatk_set_lora: rank %d unsupported (0..%d)", rank, LORA_PAD);
     return 1;
@@ -610,6 +651,7 @@ int vitatk_set_lora(vitatk_engine* e, int layer, int site, int rank, const void*
   }
   LoraSite& s = e->lw[layer].lora[site];
   s.rank = rank;
+  s.packed = packed && rank > 0;
   s.la_fwd = static_cast<const bf16*>(la_fwd);
   s.lb_fwd = static_cast<const bf16*>(lb_fwd);
   s.lb_bwd = static_cast<const bf16*>(lb_bwd);
@@ -710,6 +752,11 @@ int vitatk_finalize(vitatk_engine* e) {
   total += al(static_cast<long long>(c.max_batch) * c.num_classes * 4) + al(c.max_batch * 4) + sz_img;
   VITATK_CUDA_OK(cudaMalloc(&e->ws, total));
   VITATK_CUDA_OK(cudaMemset(e->ws, 0, total));
+  {
+    const long long nflags = 2 * ((Mmax + 255) / 256);
+    VITATK_CUDA_OK(cudaMalloc(&e->tt_flags, nflags * sizeof(unsigned int)));
+    VITATK_CUDA_OK(cudaMemset(e->tt_flags, 0, nflags * sizeof(unsigned int)));
+  }
   e->ws_bytes = total;
   char* p = e->ws;
   auto take = [&](long long b) {
@@ -859,7 +906,8 @@ int vitatk_k_gemm(int M, int N, int K, const void* A, int lda, const void* B, in
                   int ldo2, const void* T, int ldt, const void* LB, int ldlb, int lora_nkb, int lora_ksteps_,
                   int lora_group_cols, int epi_mode, const float* bias, const void* res, int ld_res, const float* table,
                   int table_rows, float* rowdot, int rowdot_rows, int rowdot_pad, const float* row_stats, const float* c1,
-                  float* stats_out, float stats_eps, void* stream) {
+                  float* stats_out, float stats_eps, const void* tt_tb, int tt_n, const float* tt_bias,
+                  unsigned int* tt_flags, void* stream) {
   GemmPlan p;
   GemmEpilogue ep = {};
   ep.mode = epi_mode;
@@ -876,9 +924,19 @@ int vitatk_k_gemm(int M, int N, int K, const void* A, int lda, const void* B, in
   ep.stats_out = reinterpret_cast<float2*>(stats_out);
   ep.stats_eps = stats_eps;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  GemmTT tt = {};
+  if (tt_n > 0) {  // the GEMM computes T = A * tt_tb^T itself (T-tiles) and writes it to T before using it
+    tt.n = tt_n;
+    tt.tb = static_cast<const bf16*>(tt_tb);
+    tt.ld_tb = K;
+    tt.out = static_cast<bf16*>(const_cast<void*>(T));
+    tt.ld_out = ldt;
+    tt.bias = tt_bias;
+    tt.flags = tt_flags;
+  }
   if (gemm_plan_init(&p, M, N, K, static_cast<const bf16*>(A), lda, static_cast<const bf16*>(B), ldb,
                      static_cast<bf16*>(out), ldo, static_cast<bf16*>(out2), ldo2, static_cast<const bf16*>(T), ldt,
-                     static_cast<const bf16*>(LB), ldlb, lora_nkb, lora_ksteps_, lora_group_cols, ep))
+                     static_cast<const bf16*>(LB), ldlb, lora_nkb, lora_ksteps_, lora_group_cols, ep, &tt))
     return 1;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);

@@ -33,7 +33,9 @@ static constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
 static constexpr int NUM_EPI_WARPS = 8;  // single-CTA kernel and pair kernel with EW == 1; the pair kernel with EW == 2 has 16
 // warp roles: epilogue warps 0..NEPI-1, then the TMA producer warp, then the MMA issuer warp
 __host__ __device__ constexpr int gemm_epi_warps(bool two, int ew) { return (two && ew == 2) ? 16 : NUM_EPI_WARPS; }
-__host__ __device__ constexpr int gemm_threads(bool two, int ew) { return (gemm_epi_warps(two, ew) + 2) * 32; }
+// (+ in the pair kernel, a "signal" warp that publishes finished T-tiles with a gpu-scope release, so that no epilogue,
+// producer or MMA thread ever blocks on that fence)
+__host__ __device__ constexpr int gemm_threads(bool two, int ew) { return (gemm_epi_warps(two, ew) + (two ? 3 : 2)) * 32; }
 static constexpr int CHUNK = 32;                  // epilogue column granule = one tcgen05.ld.32x32b.x32
 static constexpr int STAGE_OUT_BYTES = 32 * 64;   // one warp's 32-row x 32-col bf16 store tile (64 B swizzle)
 static constexpr int SLAB_BYTES = 128 * 128;      // pair kernel: 128-row x 64-col bf16 slab (128 B swizzle)
@@ -61,6 +63,12 @@ struct GemmKernelArgs {
   GemmEpilogue epi;
   int reverse_m;  // 1: walk the M-blocks from the last to the first (the input was just written in ascending order by the
                   // previous kernel, so its tail is still in L2)
+  // T-tiles (pair kernel; see GemmTT in vitatk_internal.h).  tt_n = 0: off.
+  int tt_n;
+  bf16* tt_out;
+  int tt_ld;
+  const float* tt_bias;
+  unsigned int* tt_flags;
   int gelu_f32;  // GELU in the pair epilogue: 1 = fp32 Abramowitz-Stegun (VITATK_GELU=f32), otherwise the fp32 2^P fit
   int dbg;  // timing experiments (DBG instantiation only, VITATK_GEMM_DBG): 1 no aux loads, 2 no stores,
             // 4 no TMA loads after the first ring fill, 8 no MMA issue, 16 epilogue skips TMEM reads and math,
@@ -148,7 +156,8 @@ __global__ void __launch_bounds__(gemm_threads(TWO, EW), 1)
 gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmLA, const __grid_constant__ CUtensorMap tmLB,
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
-                 const __grid_constant__ CUtensorMap tmAux, const GemmKernelArgs args) {
+                 const __grid_constant__ CUtensorMap tmAux, const __grid_constant__ CUtensorMap tmTB,
+                 const GemmKernelArgs args) {
   using Cfg = GemmCfg<BN, TWO>;
   // CTA pair: rank 0 is the leader (issues the M = 256 MMAs); unit = CTA (single) or cluster (pair)
   const uint32_t rank = TWO ? ptx::cluster_ctarank() : 0u;
@@ -171,6 +180,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   uint64_t* aux_bar = bars + 2 * STAGES + 5;   // [2 groups][2 slabs] residual / multiplier slab landed (pair kernel)
+  uint64_t* tt_done = bars + 2 * STAGES + 9;   // the T-tile's rows of this CTA are in global memory (pair kernel)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -181,6 +191,10 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int main_kb = args.K / BK;
   const int num_kb = main_kb + args.lora_nkb;
   auto mblock = [&](int tile_) { return args.reverse_m ? tiles_m - 1 - tile_ / tiles_n : tile_ / tiles_n; };
+  // T-tiles: the unit that owns output tile (m, m % tiles_n) first computes T for M-block m (same A rows, the adapter's
+  // down-projection as B operand).  Every role derives the same item sequence from (tile, tiles_n) alone.
+  const bool tt_on = TWO && args.tt_n > 0;
+  auto has_ttile = [&](int tile_) { return tt_on && (tile_ % tiles_n) == ((tile_ / tiles_n) % tiles_n); };
 
   if (warp == MMA_WARP && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -192,6 +206,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       ptx::mbar_init(&tmem_empty[b], TWO ? 2 * NEPI : NEPI);  // pair: both CTAs' epilogue warps
     }
     for (int i = 0; i < 4; ++i) ptx::mbar_init(&aux_bar[i], 1);
+    ptx::mbar_init(tt_done, NEPI / 2);  // one arrival per warp of column group 0
     ptx::fence_mbar_init();
   }
   if (warp == TMA_WARP) {
@@ -205,6 +220,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         ptx::prefetch_tmap(&tmLA);
         ptx::prefetch_tmap(&tmLB);
       }
+      if (tt_on) ptx::prefetch_tmap(&tmTB);
     }
     if constexpr (TWO) {
       ptx::tmem_alloc_2cta(tmem_slot, Cfg::TMEM_COLS);
@@ -231,8 +247,44 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int n0 = (tile % tiles_n) * BN;
       const int nb0 = n0 + static_cast<int>(rank) * Cfg::B_ROWS;                     // pair: this CTA's half of B
       const int tcol0 = args.lora_group_cols > 0 ? (n0 / args.lora_group_cols) * BK : 0;
+      if constexpr (TWO) {
+        if (has_ttile(tile)) {
+          // ---- T-tile of this M-block: A rows x the adapter's down-projection (tt_n / 2 rows of TB per CTA) ----
+          const uint32_t tb_bytes = static_cast<uint32_t>(args.tt_n) * 64u;  // (tt_n / 2 rows) x 128 B
+          const uint32_t fb0 = ptx::mapa_shared(ptx::smem_u32(&full_bar[0]), 0);
+          for (int kb = 0; kb < main_kb; ++kb, ++cnt) {
+            const int s = cnt % STAGES;
+            const uint32_t ph = (cnt / STAGES) & 1;
+            ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+            uint8_t* sa = smem_stage + s * Cfg::STAGE_BYTES;
+            const uint32_t fb = fb0 + s * 8;
+            if (rank == 0) ptx::mbar_arrive_expect_tx_p(leader, &full_bar[s], 2 * (Cfg::A_BYTES + tb_bytes));
+            ptx::tma_load_2d_2cta_p(leader, sa, &tmA, fb, kb * BK, m0);
+            ptx::tma_load_2d_2cta_p(leader, sa + Cfg::A_BYTES, &tmTB, fb, kb * BK, static_cast<int>(rank) * (args.tt_n >> 1));
+          }
+        }
+      }
       for (int kb = 0; kb < num_kb; ++kb, ++cnt) {
         const int s = cnt % STAGES;
+        if (TWO && tt_on && kb == main_kb) {
+          // The LoRA k-block reads T rows that another unit's T-tile may still be producing: acquire the block's flag
+          // (both CTAs of the producing pair have stored their rows), then order the TMA (async proxy) read behind it.
+          const int mb = mblock(tile);
+          uint32_t spins = 0;
+          while (ptx::ld_acquire_gpu(args.tt_flags + mb) < 2u) {
+            if (++spins > (1u << 26)) __trap();  // a producer that never runs (not co-resident) must not hang the GPU
+          }
+          ptx::fence_proxy_async_global();
+          // last of the block's 2 * tiles_n consumers resets the flag pair for the next launch
+          if (leader) {
+            const unsigned int old = atomicAdd(args.tt_flags + tiles_m + mb, 1u);
+            if (old == 2u * tiles_n - 1u) {
+              args.tt_flags[tiles_m + mb] = 0u;
+              args.tt_flags[mb] = 0u;
+            }
+          }
+          __syncwarp();
+        }
         const uint32_t ph = (cnt / STAGES) & 1;
         ptx::mbar_wait(&empty_bar[s], ph ^ 1);
         uint8_t* sa = smem_stage + s * Cfg::STAGE_BYTES;
@@ -279,6 +331,29 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t it = 0;
     if (!TWO || rank == 0) {
       for (int tile = unit; tile < num_tiles; tile += num_units, ++it) {
+        if constexpr (TWO) {
+          if (has_ttile(tile)) {  // T-tile: M = 256, N = tt_n, K = the GEMM's K, into the first columns of this buffer
+            const uint32_t tbuf = it & 1;
+            ptx::mbar_wait(&tmem_empty[tbuf], ((it >> 1) & 1) ^ 1);
+            ptx::tc_fence_after();
+            const uint32_t idesc_t = ptx::make_idesc_bf16(TILE_M, static_cast<uint32_t>(args.tt_n));
+            for (int kb = 0; kb < main_kb; ++kb, ++cnt) {
+              const int s = cnt % STAGES;
+              ptx::mbar_wait(&full_bar[s], (cnt / STAGES) & 1);
+              ptx::tc_fence_after();
+              const uint32_t sa = ptx::smem_u32(smem_stage + s * Cfg::STAGE_BYTES);
+              const uint64_t adesc = ptx::make_smem_desc_sw128(sa);
+              const uint64_t bdesc = ptx::make_smem_desc_sw128(sa + Cfg::A_BYTES);
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k)
+                ptx::umma_bf16_2cta_p(leader, tmem_base + tbuf * BN, adesc + 2 * k, bdesc + 2 * k, idesc_t,
+                                      (kb > 0 || k > 0) ? 1u : 0u);
+              ptx::umma_commit_2cta_mc_p(leader, &empty_bar[s], 3);
+            }
+            ptx::umma_commit_2cta_mc_p(leader, &tmem_full[tbuf], 3);
+            ++it;
+          }
+        }
         const uint32_t buf = it & 1;
         const uint32_t use = it >> 1;
         // the epilogue warps (of both CTAs of a pair) have drained this accumulator
@@ -321,6 +396,20 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if constexpr (TWO) ptx::umma_commit_2cta_mc_p(leader, &tmem_full[buf], 3);
         else ptx::umma_commit_p(leader, &tmem_full[buf]);
       }
+    }
+  } else if (TWO && warp == MMA_WARP + 1) {
+    // ================================= T-tile publisher (pair kernel) =================================
+    // Waits until column group 0 has stored this CTA's rows of a T-tile, then publishes them with a gpu-scope release
+    // on the M-block's flag.  A dedicated warp, so that the fence (which waits for the stores to be visible device-wide)
+    // never stalls the epilogue, the producer or the MMA issuer.
+    uint32_t nt = 0;
+    for (int tile = unit; tile < num_tiles; tile += num_units) {
+      if (!has_ttile(tile)) continue;
+      ptx::mbar_wait(tt_done, nt & 1);
+      ++nt;
+      __threadfence();
+      if (lane == 0) ptx::red_release_gpu_add(args.tt_flags + mblock(tile), 1u);
+      __syncwarp();
     }
   } else if constexpr (TWO) {
     // ================================= slab epilogue (pair kernel), warps 0..NEPI-1 =================================
@@ -394,6 +483,46 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int tile = unit; tile < num_tiles; tile += num_units, ++it) {
       const int m0 = mblock(tile) * TILE_M + static_cast<int>(rank) * BM;
       const int n0 = (tile % tiles_n) * BN;
+      if (has_ttile(tile)) {
+        // ---- T-tile epilogue: columns [0, tt_n) of this accumulator are T = A * TB^T for this CTA's 128 rows.  Column
+        // group 0 converts them (+ the optional per-column bias) and writes its rows straight to global memory (16 KB per
+        // CTA: no staging buffer, no TMA store to wait for); group 1 only returns the accumulator. ----
+        const uint32_t tbuf = it & 1;
+        ptx::mbar_wait(&tmem_full[tbuf], (it >> 1) & 1);
+        ptx::tc_fence_after();
+        // eight columns at a time (tcgen05.ld.x8 -> bias -> bf16 -> one 16-byte store): the T-tile is ~1 % of the work
+        // and must not add register pressure to the main epilogue below
+        const int my_cols = (g == 0) ? max(0, min(NC, args.tt_n - hh * NC)) : 0;
+        const bool row_in = m0 + trow < args.M;
+        const uint32_t ta = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + tbuf * BN + hh * NC;
+        bf16* trow_ptr = args.tt_out + static_cast<size_t>(m0 + trow) * args.tt_ld + hh * NC;
+#pragma unroll 1
+        for (int j = 0; j < my_cols; j += 8) {
+          uint32_t r8[8];
+          ptx::tmem_ld_32x32b_x8(ta + j, r8);
+          ptx::tmem_ld_wait();
+          float f[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) f[k] = __uint_as_float(r8[k]);
+          if (args.tt_bias != nullptr) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(args.tt_bias + hh * NC + j));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(args.tt_bias + hh * NC + j + 4));
+            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+            f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+          }
+          if (row_in)
+            ptx::st_global_v4(trow_ptr + j, pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                              pack_bf16x2(f[6], f[7]));
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster(tmem_empty_remote + tbuf * 8);
+        if (g == 0) {
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(tt_done);
+        }
+        ++it;
+      }
       const uint32_t buf = it & 1;
       const uint32_t use = it >> 1;
       const int row = m0 + trow;
@@ -935,7 +1064,7 @@ static bool gemm_two_cta_enabled() {
 
 int gemm_plan_init(GemmPlan* p, int M, int N, int K, const bf16* A, int lda, const bf16* B, int ldb, bf16* out,
                    int ldo, bf16* out2, int ldo2, const bf16* T, int ldt, const bf16* LB, int ldlb, int lora_nkb,
-                   int lora_ksteps, int lora_group_cols, GemmEpilogue epi) {
+                   int lora_ksteps, int lora_group_cols, GemmEpilogue epi, const GemmTT* tt) {
   if (K % BK != 0 || N % 64 != 0 || M <= 0) {
     set_error("gemm_plan_init: unsupported shape M=%d N=%d K=%d (K%%64, N%%64 must be 0)", M, N, K);
     return 1;
@@ -949,6 +1078,8 @@ int gemm_plan_init(GemmPlan* p, int M, int N, int K, const bf16* A, int lda, con
   p->lora_group_cols = lora_group_cols;
   p->epi = epi;
   p->reverse_m = 0;
+  p->tt = GemmTT{};
+  if (tt != nullptr && tt->n > 0) p->tt = *tt;
   if (lora_group_cols > 0 && lora_group_cols % p->BN != 0) {
     set_error("gemm_plan_init: lora_group_cols %d not a multiple of BN %d", lora_group_cols, p->BN);
     return 1;
@@ -987,6 +1118,17 @@ int gemm_plan_init(GemmPlan* p, int M, int N, int K, const bf16* A, int lda, con
     if (make_tmap_2d(&p->tmAux, epi.res, M, N, epi.ld_res, 64, 128)) return 1;
   } else {
     p->tmAux = p->tmOut;
+  }
+  p->tmTB = p->tmB;
+  if (p->tt.n > 0) {
+    const GemmTT& t = p->tt;
+    if (!p->two_cta || lora_nkb != 1 || lora_group_cols != 0 || (t.n != 32 && t.n != 64) || lora_ksteps * 16 > t.n ||
+        t.out != T || t.ld_out != ldt || t.tb == nullptr || t.flags == nullptr) {
+      set_error("gemm_plan_init: T-tiles need the pair kernel, one LoRA k-block reading the T they produce, n in {32, 64} "
+                ">= 16 * lora_ksteps, and a flag array");
+      return 1;
+    }
+    if (make_tmap_2d(&p->tmTB, t.tb, 64, K, t.ld_tb, BK, t.n / 2)) return 1;
   }
   if (lora_nkb > 0) {
     const int tcols = lora_group_cols > 0 ? (N / lora_group_cols) * 64 : lora_nkb * 64;
@@ -1049,7 +1191,35 @@ static int launch_bn(const GemmPlan* p, cudaStream_t stream, int num_sms) {
   }
   const int tile_m = TWO ? 2 * BM : BM;
   const int tiles = ((p->M + tile_m - 1) / tile_m) * (p->N / BN);
-  const int max_units = TWO ? num_sms / 2 : num_sms;
+  int max_units = TWO ? num_sms / 2 : num_sms;
+  if constexpr (TWO) {
+    // Units wait on one another (T-tiles), so every cluster of the grid must be resident at once: ask the runtime how
+    // many 2-CTA clusters of this kernel the device can hold (a GPC with an odd number of SMs leaves one unpaired).
+    static int max_clusters[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int& mc = max_clusters[dev & 63];
+    if (mc == 0) {
+      cudaLaunchConfig_t qc = {};
+      qc.gridDim = dim3(2 * (num_sms / 2), 1, 1);
+      qc.blockDim = dim3(gemm_threads(TWO, EW), 1, 1);
+      qc.dynamicSmemBytes = Cfg::SMEM_BYTES;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = 2;
+      qa[0].val.clusterDim.y = 1;
+      qa[0].val.clusterDim.z = 1;
+      qc.attrs = qa;
+      qc.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, gemm_tc05_kernel<BN, false, TWO, EW>, &qc) != cudaSuccess || n < 1) {
+        cudaGetLastError();
+        n = num_sms / 2;
+      }
+      mc = n;
+    }
+    if (mc < max_units) max_units = mc;
+  }
   const int units = tiles < max_units ? tiles : max_units;
   GemmKernelArgs a;
   a.M = p->M;
@@ -1062,16 +1232,21 @@ static int launch_bn(const GemmPlan* p, cudaStream_t stream, int num_sms) {
   a.dbg = gemm_dbg_flags();
   a.gelu_f32 = gemm_gelu_f32();
   a.reverse_m = p->reverse_m;
+  a.tt_n = TWO ? p->tt.n : 0;
+  a.tt_out = p->tt.out;
+  a.tt_ld = p->tt.ld_out;
+  a.tt_bias = p->tt.bias;
+  a.tt_flags = p->tt.flags;
   const dim3 grid(TWO ? 2 * units : units, 1, 1), block(gemm_threads(TWO, EW), 1, 1);
 #ifdef VITATK_DBG_KERNELS  // timing-experiment instantiations (VITATK_GEMM_DBG switches) are not part of the product build
   if (a.dbg) {
     VITATK_CUDA_OK(launch_pdl(gemm_tc05_kernel<BN, true, TWO, EW>, grid, block, Cfg::SMEM_BYTES, stream, TWO ? 2 : 1, p->tmA,
-                              p->tmB, p->tmLA, p->tmLB, p->tmOut, p->tmOut2, p->tmAux, a));
+                              p->tmB, p->tmLA, p->tmLB, p->tmOut, p->tmOut2, p->tmAux, p->tmTB, a));
     return 0;
   }
 #endif
   VITATK_CUDA_OK(launch_pdl(gemm_tc05_kernel<BN, false, TWO, EW>, grid, block, Cfg::SMEM_BYTES, stream, TWO ? 2 : 1, p->tmA,
-                              p->tmB, p->tmLA, p->tmLB, p->tmOut, p->tmOut2, p->tmAux, a));
+                              p->tmB, p->tmLA, p->tmLB, p->tmOut, p->tmOut2, p->tmAux, p->tmTB, a));
   return 0;
 }
 

@@ -125,6 +125,30 @@ struct GemmEpilogue {
   int stat_col;
 };
 
+// T-tiles (pair kernel only): the GEMM computes its OWN LoRA down-projection T = A * TB^T inside the launch instead of
+// reading a T that a separate skinny GEMM produced.  Every 256-row M-block gets one extra work item ("T-tile": the same
+// A rows against the n-row adapter operand TB, full K) scheduled right before one of the block's output tiles; its rows
+// go to `out` with plain global stores, a gpu-scope release on flags[m] publishes them, and the output tiles of the
+// block acquire that flag before their TMA load of the LoRA k-block (which comes last in their k-loop, so they rarely
+// wait).  The A block is streamed once from HBM for the T-tile and the block's output tiles together.
+struct GemmTT {
+  int n;                 // 0 = off; 32 or 64: columns of T produced (>= every column the LoRA k-steps read)
+  const bf16* tb;        // [64, K] bf16 row-major (rows >= n unused): the adapter's down-projection, K-major
+  int ld_tb;
+  bf16* out;             // T [M, ld_out]  (must be the tensor the plan's LoRA k-block reads)
+  int ld_out;
+  const float* bias;     // [64] fp32 added to T's columns (the "ones" that feed bias columns of LB), or null
+  unsigned int* flags;   // [2 * ceil(M / 256)] zero-initialised; the kernel leaves it zeroed again
+  // LayerNorm statistics of A's rows from partial (mean, M2) records written by the producer of A (GemmEpilogue::
+  // stats_partial_out): the T-tile's epilogue combines them, writes stats_out and the per-row constant factors
+  const float2* stats_partial;  // [M, stats_nparts] or null
+  int stats_nparts;
+  int stats_part_cols;          // columns each partial record covers
+  float2* stats_out;            // [M] (mean, rstd)
+  float stats_eps;
+  int stat_col;                 // first of the six constant-factor columns in T (0 = none)
+};
+
 struct GemmPlan {
   // shapes
   int M, N, K;
@@ -135,15 +159,17 @@ struct GemmPlan {
   int lora_ksteps;      // UMMA k-steps (16 each) issued per extra k-block = ceil(r/16)
   int lora_group_cols;  // >0: T column offset = (n0 / lora_group_cols) * 64  (fused q|k|v forward)
   GemmEpilogue epi;
+  GemmTT tt;
   // tensor maps (built once per plan)
   CUtensorMap tmA, tmB, tmLA, tmLB, tmOut, tmOut2;
+  CUtensorMap tmTB;     // T-tile B operand: (tt.n / 2)-row x 64-col boxes of tt.tb
   CUtensorMap tmAux;    // residual / multiplier tensor as 64-col x 128-row slabs (pair kernel only)
 };
 
 // Build the TMA descriptors of a plan. Pointers may be null when the feature is unused.
 int gemm_plan_init(GemmPlan* p, int M, int N, int K, const bf16* A, int lda, const bf16* B, int ldb,
                    bf16* out, int ldo, bf16* out2, int ldo2, const bf16* T, int ldt, const bf16* LB, int ldlb,
-                   int lora_nkb, int lora_ksteps, int lora_group_cols, GemmEpilogue epi);
+                   int lora_nkb, int lora_ksteps, int lora_group_cols, GemmEpilogue epi, const GemmTT* tt = nullptr);
 int gemm_launch(const GemmPlan* p, cudaStream_t stream, int num_sms);
 
 int make_tmap_3d(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1_bytes,

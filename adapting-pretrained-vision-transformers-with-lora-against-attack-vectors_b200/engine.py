@@ -15,6 +15,7 @@ Weights in (reference formats):
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -31,7 +32,7 @@ T_PATCH_W, T_PATCH_WT, T_EMBED, T_LNF_G, T_LNF_B, T_HEAD_W, T_HEAD_B = 0, 1, 2, 
 T_LN1_G, T_LN1_B, T_QKV_W, T_QKV_WT, T_QKV_B, T_PROJ_W, T_PROJ_WT, T_PROJ_B = 16, 17, 18, 19, 20, 21, 22, 23
 T_LN2_G, T_LN2_B, T_FC1_W, T_FC1_WT, T_FC1_B, T_FC2_W, T_FC2_WT, T_FC2_B = 24, 25, 26, 27, 28, 29, 30, 31
 T_QKV_C1, T_FC1_C1 = 32, 33
-SITE_QKV, SITE_PROJ, SITE_FC1, SITE_FC2 = 0, 1, 2, 3
+SITE_QKV, SITE_PROJ, SITE_FC1, SITE_FC2, SITE_QKV_PACKED = 0, 1, 2, 3, 4
 
 Adapter = Tuple[torch.Tensor, torch.Tensor, float]  # (A [r,in], B [out,r], scale)
 
@@ -309,14 +310,22 @@ class Engine:
                 continue
             G = len(names)
             gamma, beta = fold.get(site, (None, None))
-            la_fwd = torch.zeros(LORA_PAD * G, n_in)
+            # q|k|v: when the three adapters fit one 64-column group together they are PACKED (column ranges [0, rq),
+            # [rq, rq + rk), ...): one LoRA k-block instead of three and x*A^T comes from T-tiles of the consumer GEMM
+            ranks = [sum(int(A.shape[0]) for (A, _, _) in ads) for ads in groups]
+            packed = G > 1 and sum(ranks) <= LORA_PAD and os.environ.get("VITATK_QKV_PACKED", "1") != "0"
+            GP = 1 if packed else G          # 64-column groups in the packed buffers
+            la_fwd = torch.zeros(LORA_PAD * GP, n_in)
             lb_fwd = torch.zeros(n_out * G, LORA_PAD)
-            lb_bwd = torch.zeros(LORA_PAD * G, n_out * G)
-            la_bwd = torch.zeros(n_in, LORA_PAD * G)
+            lb_bwd = torch.zeros(LORA_PAD * GP, n_out * G)
+            la_bwd = torch.zeros(n_in, LORA_PAD * GP)
             c2 = torch.zeros(n_out * G)
             rmax = 0
+            r0 = 0
             for gi, ads in enumerate(groups):
-                r0 = 0
+                if not packed:
+                    r0 = 0
+                row0 = 0 if packed else LORA_PAD * gi   # first row / column of this group's 64-wide block
                 for (A, B, s) in ads:
                     A = A.detach().to("cpu", torch.float32)
                     B = B.detach().to("cpu", torch.float32)
@@ -325,23 +334,26 @@ class Engine:
                         raise _lib.VitatkError(f"adapter shape mismatch on {names[gi]}: A {tuple(A.shape)} B {tuple(B.shape)}")
                     if r0 + r > LORA_PAD:
                         raise _lib.VitatkError(f"total LoRA rank on {names[gi]} exceeds {LORA_PAD}")
-                    la_fwd[LORA_PAD * gi + r0: LORA_PAD * gi + r0 + r] = A if gamma is None else A * gamma[None, :]
+                    la_fwd[row0 + r0: row0 + r0 + r] = A if gamma is None else A * gamma[None, :]
                     lb_fwd[n_out * gi: n_out * (gi + 1), r0: r0 + r] = s * B
-                    lb_bwd[LORA_PAD * gi + r0: LORA_PAD * gi + r0 + r, n_out * gi: n_out * (gi + 1)] = B.t()
-                    la_bwd[:, LORA_PAD * gi + r0: LORA_PAD * gi + r0 + r] = s * A.t()
+                    lb_bwd[row0 + r0: row0 + r0 + r, n_out * gi: n_out * (gi + 1)] = B.t()
+                    la_bwd[:, row0 + r0: row0 + r0 + r] = s * A.t()
                     if gamma is not None:
                         c2[n_out * gi: n_out * (gi + 1)] += s * (B @ (A @ beta))
                     r0 += r
                 rmax = max(rmax, r0)
             host_bf = [t.to(torch.bfloat16) for t in (la_fwd, lb_fwd, lb_bwd, la_bwd)]
             bufs = [self._dev(t, torch.bfloat16) for t in host_bf]
-            _lib.check(self.lib.vitatk_set_lora(self._h, l, site, rmax, *[b.data_ptr() for b in bufs]),
-                       f"vitatk_set_lora(layer {l}, site {site})")
+            _lib.check(self.lib.vitatk_set_lora(self._h, l, SITE_QKV_PACKED if packed else site, rmax,
+                                                *[b.data_ptr() for b in bufs]), f"vitatk_set_lora(layer {l}, site {site})")
             if gamma is not None:
                 # c1 share from the bf16 operands: row n of group gi sees sum_j lb_fwd[n, j] * sum_k la_fwd[64 gi + j, k]
-                a_sum = host_bf[0].float().sum(1).reshape(G, LORA_PAD)
-                lb = host_bf[1].float().reshape(G, n_out, LORA_PAD)
-                c1 = torch.einsum("gnj,gj->gn", lb, a_sum).reshape(-1)
+                if packed:  # one shared group: row n sees sum_j lb_fwd[n, j] * sum_k la_fwd[j, k]
+                    c1 = host_bf[1].float() @ host_bf[0].float().sum(1)
+                else:
+                    a_sum = host_bf[0].float().sum(1).reshape(G, LORA_PAD)
+                    lb = host_bf[1].float().reshape(G, n_out, LORA_PAD)
+                    c1 = torch.einsum("gnj,gj->gn", lb, a_sum).reshape(-1)
                 shares[site] = (c1, c2)
         return shares
 

@@ -73,7 +73,9 @@ enum vitatk_tensor_id {
 };
 
 /* Adapter sites for vitatk_set_lora (train_loras.py:79-95 target_modules; q,k,v share one fused site). */
-enum vitatk_lora_site { VITATK_SITE_QKV = 0, VITATK_SITE_PROJ = 1, VITATK_SITE_FC1 = 2, VITATK_SITE_FC2 = 3 };
+enum vitatk_lora_site { VITATK_SITE_QKV = 0, VITATK_SITE_PROJ = 1, VITATK_SITE_FC1 = 2, VITATK_SITE_FC2 = 3,
+                        /* the QKV site with q, k and v sharing ONE 64-column group (see vitatk_set_lora) */
+                        VITATK_SITE_QKV_PACKED = 4 };
 
 const char* vitatk_last_error(void);
 int vitatk_version(void);
@@ -91,7 +93,11 @@ int vitatk_set_tensor(vitatk_engine* e, int tensor_id, int layer, const void* de
  *   la_fwd  bf16 [64*G, in]    rows 64g..64g+r = A_g, rest zero           (T = x A^T)
  *   lb_fwd  bf16 [out, 64]     cols 0..r = (alpha/r) * B (row n of its group), rest zero
  *   lb_bwd  bf16 [64*G, out]   rows 64g..64g+r = B_g^T on group g's columns, zero elsewhere
- *   la_bwd  bf16 [in, 64*G]    cols 64g..64g+r = (alpha/r) * A_g^T, rest zero */
+ *   la_bwd  bf16 [in, 64*G]    cols 64g..64g+r = (alpha/r) * A_g^T, rest zero
+ * site == VITATK_SITE_QKV_PACKED (possible when rq + rk + rv <= 64; rank = that sum): the three adapters share one
+ * group -- G = 1 above, with A_q in rows [0, rq), A_k in [rq, rq + rk), A_v after them, B_q's columns [0, rq) non-zero only
+ * on the q rows of lb_fwd [3*in, 64] (and so on).  One LoRA k-block instead of three, and x*A^T is then computed inside
+ * the consumer GEMM (T-tiles) instead of by a separate launch. */
 int vitatk_set_lora(vitatk_engine* e, int layer, int site, int rank, const void* la_fwd_dev, const void* lb_fwd_dev,
                     const void* lb_bwd_dev, const void* la_bwd_dev);
 
@@ -155,13 +161,17 @@ long long vitatk_launch_count(const vitatk_engine* e);
 int vitatk_profile_begin(vitatk_engine* e);
 int vitatk_profile_end(vitatk_engine* e, double* ms_by_cat, double* flops_by_cat, long long* launches_by_cat);
 
-/* ---- kernel-level entry points (used by tests/ and bench.py's roofline leg) ---- */
+/* ---- kernel-level entry points (used by tests/ and bench.py's roofline leg) ----
+ * vitatk_k_gemm with tt_n in {32, 64}: "T-tile" mode of the pair kernel -- the GEMM computes T = A * tt_tb^T (tt_tb bf16
+ * [64, K], + tt_bias[64] if given) itself, writes it to T_dev and uses it as its LoRA k-block in the same launch;
+ * tt_flags_dev is a zero-initialised uint32 [2 * ceil(M / 256)] scratch that the launch leaves zeroed. */
 int vitatk_k_gemm(int M, int N, int K, const void* A_dev, int lda, const void* B_dev, int ldb, void* out_dev,
                   int ldo, void* out2_dev, int ldo2, const void* T_dev, int ldt, const void* LB_dev, int ldlb,
                   int lora_nkb, int lora_ksteps, int lora_group_cols, int epi_mode, const float* bias_dev,
                   const void* res_dev, int ld_res, const float* table_dev, int table_rows, float* rowdot_dev,
                   int rowdot_rows, int rowdot_pad, const float* row_stats_dev, const float* c1_dev, float* stats_out_dev,
-                  float stats_eps, void* stream);
+                  float stats_eps, const void* tt_tb_dev, int tt_n, const float* tt_bias_dev, unsigned int* tt_flags_dev,
+                  void* stream);
 /* tcgen05 forward (the engine's path); lse2_dev (optional) receives [batch*heads, 208] log2-domain logsumexp */
 int vitatk_k_attention_fwd_tc05(const void* qkv_dev, void* out_dev, float* lse2_dev, int batch, int tokens, int heads,
                                 void* stream);

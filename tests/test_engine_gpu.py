@@ -38,13 +38,11 @@ def setup():
     torch.backends.cudnn.allow_tf32 = False
     out = {}
     for name, lora in (("base", False), ("lora", True)):
-        m = fx.make_model(lora=lora)
+        m = fx.make_model(lora=lora).cuda()  # on its final device BEFORE compiling: moving it later changes the fingerprint
         eng = vitatk.compile_model(m, max_batch=8, device="cuda")
         out[name] = (m, eng)
     x, y = fx.make_inputs()
     out["x"], out["y"] = x.cuda(), y.cuda()
-    for name in ("base", "lora"):
-        out[name][0].cuda()
     return out
 
 

@@ -27,7 +27,8 @@ def _dgelu(u):
 
 
 def run_gemm(lib, A, B, epi=EPI_PLAIN, bias=None, res=None, table=None, T=None, LB=None, nkb=0, ksteps=0,
-             group_cols=0, rowdot=None, rowdot_rows=0, row_stats=None, c1=None, stats_out=None):
+             group_cols=0, rowdot=None, rowdot_rows=0, row_stats=None, c1=None, stats_out=None, tt_tb=None, tt_n=0,
+             tt_bias=None, tt_flags=None):
     from vitatk import _lib
 
     M, K = A.shape
@@ -39,7 +40,7 @@ def run_gemm(lib, A, B, epi=EPI_PLAIN, bias=None, res=None, table=None, T=None, 
                            group_cols, epi, _p(bias), _p(res), 0 if res is None else res.stride(0), _p(table),
                            0 if table is None else table.shape[0], _p(rowdot), rowdot_rows,
                            0 if rowdot is None else rowdot.shape[1], _p(row_stats), _p(c1), _p(stats_out), 1e-12,
-                           _s())
+                           _p(tt_tb), tt_n, _p(tt_bias), _p(tt_flags), _s())
     _lib.check(rc, "vitatk_k_gemm")
     torch.cuda.synchronize()
     return out, out2
@@ -141,6 +142,60 @@ def test_gemm_tc05_vs_torch(lib, M, N, K, epi, lora):
     check_close(out, want, f"gemm {M}x{N}x{K} epi{epi}")
     if epi == EPI_GELU_DUAL:
         check_close(out2, want2, "gelu' output")
+
+
+TT_CASES = [
+    # M, N, K, epi, rank, tt_n, bias columns
+    (1576, 768, 768, EPI_RESIDUAL, 8, 32, True),     # proj forward: T-tile + "ones" columns feeding the bias columns of LB
+    (1576, 768, 3072, EPI_RESIDUAL, 8, 32, True),    # fc2 forward (8-warp epilogue)
+    (1576, 3072, 768, EPI_MUL, 8, 32, False),        # fc2 backward (16-warp epilogue, 12 N-tiles per M-block)
+    (1576, 768, 2304, EPI_PLAIN, 24, 32, False),     # qkv backward with the packed q|k|v adapters
+    (1576, 768, 768, EPI_PLAIN, 40, 64, False),      # stacked adapters: 64 T columns
+    (300, 768, 768, EPI_RESIDUAL, 8, 32, True),      # two M-blocks, ragged
+    (50432, 768, 768, EPI_RESIDUAL, 8, 32, True),    # full BASELINE size: 197 M-blocks over 74 pairs
+    (50432, 3072, 768, EPI_MUL, 8, 32, False),
+    (50432, 768, 3072, EPI_PLAIN, 16, 32, False),
+]
+
+
+@pytest.mark.parametrize("M,N,K,epi,r,tt_n,with_bias", TT_CASES)
+def test_gemm_ttiles_compute_the_lora_projection_in_the_same_launch(lib, M, N, K, epi, r, tt_n, with_bias):
+    """T-tile mode of the pair kernel: out = epi(A B^T + T LB^T) with T = bf16(A TB^T (+ bias)) produced INSIDE the launch
+    (per-M-block flags between CTAs), against torch; T itself is checked too, the flag scratch must come back zeroed, and
+    a second launch on the same scratch must give the same bits (the flags reset themselves)."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K + r)
+    rn = lambda *s: torch.randn(*s, device="cuda", generator=g)  # noqa: E731
+    A = rn(M, K).to(torch.bfloat16)
+    B = (rn(N, K) / math.sqrt(K)).to(torch.bfloat16)
+    res = rn(M, N).to(torch.bfloat16) if epi in (EPI_RESIDUAL, EPI_MUL) else None
+    ncols = r + (2 if with_bias else 0)
+    ksteps = (ncols + 15) // 16
+    TB = torch.zeros(64, K, device="cuda")
+    TB[:r] = rn(r, K) / math.sqrt(K)
+    TB = TB.to(torch.bfloat16)
+    LB = torch.zeros(N, 64, device="cuda")
+    LB[:, :ncols] = rn(N, ncols) * 0.1
+    LB = LB.to(torch.bfloat16)
+    tbias = None
+    if with_bias:
+        tbias = torch.zeros(64, device="cuda")
+        tbias[r:r + 2] = 1.0
+    T = torch.full((M, 192), 3.0, device="cuda", dtype=torch.bfloat16)  # the engine's T has a 192-column pitch
+    flags = torch.zeros(2 * ((M + 255) // 256), device="cuda", dtype=torch.int32)
+    out, _ = run_gemm(lib, A, B, epi, None, res, None, T, LB, 1, ksteps, 0, tt_tb=TB, tt_n=tt_n, tt_bias=tbias, tt_flags=flags)
+    Tref = A.float() @ TB.float().t()
+    if with_bias:
+        Tref = Tref + tbias
+    got_T = T[:, :tt_n].float()
+    assert (got_T - Tref[:, :tt_n]).abs().max() <= 1e-2 * Tref.abs().max() + 1e-3
+    assert torch.equal(T[:, 64:], torch.full_like(T[:, 64:], 3.0))   # nothing beyond the group is touched
+    acc = A.float() @ B.float().t() + T[:, :16 * ksteps].float() @ LB[:, :16 * ksteps].float().t()
+    want = acc + res.float() if epi == EPI_RESIDUAL else (acc * res.float() if epi == EPI_MUL else acc)
+    check_close(out, want, f"T-tile gemm {M}x{N}x{K} epi{epi}")
+    assert int(flags.abs().sum()) == 0, "flag scratch must be left zeroed"
+    T2 = torch.full_like(T, 3.0)
+    out2, _ = run_gemm(lib, A, B, epi, None, res, None, T2, LB, 1, ksteps, 0, tt_tb=TB, tt_n=tt_n, tt_bias=tbias, tt_flags=flags)
+    assert torch.equal(out2, out) and torch.equal(T2, T)
 
 
 @pytest.mark.parametrize("images,tokens", [(8, 197), (3, 50), (256, 197)])

@@ -191,10 +191,26 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int main_kb = args.K / BK;
   const int num_kb = main_kb + args.lora_nkb;
   auto mblock = [&](int tile_) { return args.reverse_m ? tiles_m - 1 - tile_ / tiles_n : tile_ / tiles_n; };
-  // T-tiles: the unit that owns output tile (m, m % tiles_n) first computes T for M-block m (same A rows, the adapter's
-  // down-projection as B operand).  Every role derives the same item sequence from (tile, tiles_n) alone.
+  // T-tiles (pair kernel, args.tt_n > 0): every M-block gets one extra work item that computes T = A * TB^T for the block
+  // (same A rows, the adapter's down-projection as B operand, full K).  Schedule: the T-tile of block m runs ONE WAVE of
+  // output tiles ahead of the block's own output tiles -- units 0 .. tt_pro-1 start with the T-tiles of the first wave's
+  // blocks, and the unit that owns output tile (m, m % tiles_n) first computes the T-tile of block m + tt_shift -- so its
+  // rows are published long before a LoRA k-block needs them, while the A block is still in L2 when the output tiles
+  // stream it again.  Every role derives the same item sequence from (unit, tile) alone.
   const bool tt_on = TWO && args.tt_n > 0;
-  auto has_ttile = [&](int tile_) { return tt_on && (tile_ % tiles_n) == ((tile_ / tiles_n) % tiles_n); };
+  const int tt_shift = (num_units + tiles_n - 1) / tiles_n;        // M-blocks per wave of output tiles
+  const int tt_pro = tt_on ? min(tt_shift, tiles_m) : 0;
+  auto ttile_of = [&](int tile_) -> int {  // linear block index whose T-tile precedes output tile `tile_`, or -1
+    if (!tt_on) return -1;
+    const int ml = tile_ / tiles_n;
+    if (tile_ - ml * tiles_n != ml % tiles_n) return -1;
+    const int mt = ml + tt_shift;
+    return mt < tiles_m ? mt : -1;
+  };
+  auto block_row0 = [&](int mlin) {  // first row of this CTA's 128 rows of (linear) block mlin
+    return (args.reverse_m ? tiles_m - 1 - mlin : mlin) * TILE_M + static_cast<int>(rank) * BM;
+  };
+  uint32_t* tt_ready = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 10);  // output tiles of this unit whose T rows are acquired
 
   if (warp == MMA_WARP && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -207,6 +223,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int i = 0; i < 4; ++i) ptx::mbar_init(&aux_bar[i], 1);
     ptx::mbar_init(tt_done, NEPI / 2);  // one arrival per warp of column group 0
+    *tt_ready = 0u;
     ptx::fence_mbar_init();
   }
   if (warp == TMA_WARP) {
@@ -242,48 +259,44 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ================================= TMA producer (converged warp, elected lane issues) =================================
     const uint32_t leader = ptx::elect_leader();
     uint32_t cnt = 0;
-    for (int tile = unit; tile < num_tiles; tile += num_units) {
+    uint32_t n_main = 0;  // output tiles this unit has started
+    auto load_ttile = [&](int mlin) {  // A rows of block mlin x the adapter's down-projection (tt_n / 2 rows of TB per CTA)
+      const uint32_t tb_bytes = static_cast<uint32_t>(args.tt_n) * 64u;  // (tt_n / 2 rows) x 128 B
+      const uint32_t fb0 = ptx::mapa_shared(ptx::smem_u32(&full_bar[0]), 0);
+      const int tm0 = block_row0(mlin);
+      for (int kb = 0; kb < main_kb; ++kb, ++cnt) {
+        const int s = cnt % STAGES;
+        ptx::mbar_wait(&empty_bar[s], ((cnt / STAGES) & 1) ^ 1);
+        uint8_t* sa = smem_stage + s * Cfg::STAGE_BYTES;
+        const uint32_t fb = fb0 + s * 8;
+        if (rank == 0) ptx::mbar_arrive_expect_tx_p(leader, &full_bar[s], 2 * (Cfg::A_BYTES + tb_bytes));
+        ptx::tma_load_2d_2cta_p(leader, sa, &tmA, fb, kb * BK, tm0);
+        ptx::tma_load_2d_2cta_p(leader, sa + Cfg::A_BYTES, &tmTB, fb, kb * BK, static_cast<int>(rank) * (args.tt_n >> 1));
+      }
+    };
+    if constexpr (TWO) {
+      if (unit < tt_pro) load_ttile(unit);
+    }
+    for (int tile = unit; tile < num_tiles; tile += num_units, ++n_main) {
       const int m0 = mblock(tile) * TILE_M + static_cast<int>(rank) * BM;              // this CTA's 128 rows of A
       const int n0 = (tile % tiles_n) * BN;
       const int nb0 = n0 + static_cast<int>(rank) * Cfg::B_ROWS;                     // pair: this CTA's half of B
       const int tcol0 = args.lora_group_cols > 0 ? (n0 / args.lora_group_cols) * BK : 0;
       if constexpr (TWO) {
-        if (has_ttile(tile)) {
-          // ---- T-tile of this M-block: A rows x the adapter's down-projection (tt_n / 2 rows of TB per CTA) ----
-          const uint32_t tb_bytes = static_cast<uint32_t>(args.tt_n) * 64u;  // (tt_n / 2 rows) x 128 B
-          const uint32_t fb0 = ptx::mapa_shared(ptx::smem_u32(&full_bar[0]), 0);
-          for (int kb = 0; kb < main_kb; ++kb, ++cnt) {
-            const int s = cnt % STAGES;
-            const uint32_t ph = (cnt / STAGES) & 1;
-            ptx::mbar_wait(&empty_bar[s], ph ^ 1);
-            uint8_t* sa = smem_stage + s * Cfg::STAGE_BYTES;
-            const uint32_t fb = fb0 + s * 8;
-            if (rank == 0) ptx::mbar_arrive_expect_tx_p(leader, &full_bar[s], 2 * (Cfg::A_BYTES + tb_bytes));
-            ptx::tma_load_2d_2cta_p(leader, sa, &tmA, fb, kb * BK, m0);
-            ptx::tma_load_2d_2cta_p(leader, sa + Cfg::A_BYTES, &tmTB, fb, kb * BK, static_cast<int>(rank) * (args.tt_n >> 1));
-          }
-        }
+        const int mt = ttile_of(tile);
+        if (mt >= 0) load_ttile(mt);
       }
       for (int kb = 0; kb < num_kb; ++kb, ++cnt) {
         const int s = cnt % STAGES;
         if (TWO && tt_on && kb == main_kb) {
-          // The LoRA k-block reads T rows that another unit's T-tile may still be producing: acquire the block's flag
-          // (both CTAs of the producing pair have stored their rows), then order the TMA (async proxy) read behind it.
-          const int mb = mblock(tile);
+          // The LoRA k-block reads T rows produced by a T-tile (usually of another unit).  The publisher warp has
+          // acquired the block's flag ahead of time and counts the output tiles that may proceed; all that is left here
+          // is a shared-memory wait and ordering this thread's TMA (async proxy) read behind the acquired writes.
           uint32_t spins = 0;
-          while (ptx::ld_acquire_gpu(args.tt_flags + mb) < 2u) {
-            if (++spins > (1u << 26)) __trap();  // a producer that never runs (not co-resident) must not hang the GPU
+          while (ptx::ld_acquire_cta_shared(tt_ready) <= n_main) {
+            if (++spins > (1u << 30)) __trap();  // a T-tile that never arrives must not hang the GPU
           }
           ptx::fence_proxy_async_global();
-          // last of the block's 2 * tiles_n consumers resets the flag pair for the next launch
-          if (leader) {
-            const unsigned int old = atomicAdd(args.tt_flags + tiles_m + mb, 1u);
-            if (old == 2u * tiles_n - 1u) {
-              args.tt_flags[tiles_m + mb] = 0u;
-              args.tt_flags[mb] = 0u;
-            }
-          }
-          __syncwarp();
         }
         const uint32_t ph = (cnt / STAGES) & 1;
         ptx::mbar_wait(&empty_bar[s], ph ^ 1);
@@ -329,30 +342,34 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     constexpr uint32_t idesc = ptx::make_idesc_bf16(TILE_M, BN);
     uint32_t cnt = 0;
     uint32_t it = 0;
+    auto mma_ttile = [&]() {  // T-tile: M = 256, N = tt_n, K = the GEMM's K, into the first columns of accumulator it & 1
+      const uint32_t tbuf = it & 1;
+      ptx::mbar_wait(&tmem_empty[tbuf], ((it >> 1) & 1) ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t idesc_t = ptx::make_idesc_bf16(TILE_M, static_cast<uint32_t>(args.tt_n));
+      for (int kb = 0; kb < main_kb; ++kb, ++cnt) {
+        const int s = cnt % STAGES;
+        ptx::mbar_wait(&full_bar[s], (cnt / STAGES) & 1);
+        ptx::tc_fence_after();
+        const uint32_t sa = ptx::smem_u32(smem_stage + s * Cfg::STAGE_BYTES);
+        const uint64_t adesc = ptx::make_smem_desc_sw128(sa);
+        const uint64_t bdesc = ptx::make_smem_desc_sw128(sa + Cfg::A_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k)
+          ptx::umma_bf16_2cta_p(leader, tmem_base + tbuf * BN, adesc + 2 * k, bdesc + 2 * k, idesc_t,
+                                (kb > 0 || k > 0) ? 1u : 0u);
+        ptx::umma_commit_2cta_mc_p(leader, &empty_bar[s], 3);
+      }
+      ptx::umma_commit_2cta_mc_p(leader, &tmem_full[tbuf], 3);
+      ++it;
+    };
     if (!TWO || rank == 0) {
+      if constexpr (TWO) {
+        if (unit < tt_pro) mma_ttile();
+      }
       for (int tile = unit; tile < num_tiles; tile += num_units, ++it) {
         if constexpr (TWO) {
-          if (has_ttile(tile)) {  // T-tile: M = 256, N = tt_n, K = the GEMM's K, into the first columns of this buffer
-            const uint32_t tbuf = it & 1;
-            ptx::mbar_wait(&tmem_empty[tbuf], ((it >> 1) & 1) ^ 1);
-            ptx::tc_fence_after();
-            const uint32_t idesc_t = ptx::make_idesc_bf16(TILE_M, static_cast<uint32_t>(args.tt_n));
-            for (int kb = 0; kb < main_kb; ++kb, ++cnt) {
-              const int s = cnt % STAGES;
-              ptx::mbar_wait(&full_bar[s], (cnt / STAGES) & 1);
-              ptx::tc_fence_after();
-              const uint32_t sa = ptx::smem_u32(smem_stage + s * Cfg::STAGE_BYTES);
-              const uint64_t adesc = ptx::make_smem_desc_sw128(sa);
-              const uint64_t bdesc = ptx::make_smem_desc_sw128(sa + Cfg::A_BYTES);
-#pragma unroll
-              for (int k = 0; k < BK / 16; ++k)
-                ptx::umma_bf16_2cta_p(leader, tmem_base + tbuf * BN, adesc + 2 * k, bdesc + 2 * k, idesc_t,
-                                      (kb > 0 || k > 0) ? 1u : 0u);
-              ptx::umma_commit_2cta_mc_p(leader, &empty_bar[s], 3);
-            }
-            ptx::umma_commit_2cta_mc_p(leader, &tmem_full[tbuf], 3);
-            ++it;
-          }
+          if (ttile_of(tile) >= 0) mma_ttile();
         }
         const uint32_t buf = it & 1;
         const uint32_t use = it >> 1;
@@ -402,14 +419,58 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // Waits until column group 0 has stored this CTA's rows of a T-tile, then publishes them with a gpu-scope release
     // on the M-block's flag.  A dedicated warp, so that the fence (which waits for the stores to be visible device-wide)
     // never stalls the epilogue, the producer or the MMA issuer.
-    uint32_t nt = 0;
-    for (int tile = unit; tile < num_tiles; tile += num_units) {
-      if (!has_ttile(tile)) continue;
-      ptx::mbar_wait(tt_done, nt & 1);
-      ++nt;
-      __threadfence();
-      if (lane == 0) ptx::red_release_gpu_add(args.tt_flags + mblock(tile), 1u);
-      __syncwarp();
+    // It also acquires, ahead of the producer, the flags of the blocks this unit's output tiles belong to (tt_ready counts
+    // the tiles that may load their LoRA k-block) and keeps the flag array self-resetting: the last of a block's
+    // 2 * tiles_n consumers (tiles_n output tiles x 2 CTAs) zeroes the block's pair of counters for the next launch.
+    if (tt_on) {
+      int pt = unit;                             // tile cursor of the publish side
+      int pblk = unit < tt_pro ? unit : -1;      // block of the next T-tile this CTA publishes
+      auto seek = [&]() {
+        while (pblk < 0 && pt < num_tiles) {
+          pblk = ttile_of(pt);
+          pt += num_units;
+        }
+      };
+      seek();
+      uint32_t npub = 0, nacq = 0;
+      int at = unit;                             // next output tile whose block flag is to be acquired
+      unsigned int pend_old = 0;                 // (lane 0) result of the previous consumer count, examined one round later
+      int pend_blk = -1;
+      auto settle = [&]() {
+        if (lane == 0 && pend_blk >= 0 && pend_old == 2u * tiles_n - 1u) {
+          args.tt_flags[tiles_m + pend_blk] = 0u;
+          args.tt_flags[pend_blk] = 0u;
+        }
+      };
+      uint32_t idle = 0;
+      while (pblk >= 0 || at < num_tiles) {
+        if (++idle > (1u << 25)) __trap();  // (every poll is a device-memory round trip: tens of seconds without progress)
+        if (pblk >= 0 && ptx::mbar_try_wait(tt_done, npub & 1)) {
+          idle = 0;
+          ++npub;
+          __threadfence();
+          if (lane == 0) ptx::red_release_gpu_add(args.tt_flags + pblk, 1u);
+          __syncwarp();
+          pblk = -1;
+          seek();
+        }
+        if (at < num_tiles) {
+          const int ml = at / tiles_n;
+          if (ptx::ld_acquire_gpu(args.tt_flags + ml) >= 2u) {  // both CTAs of the producing pair have published
+            idle = 0;
+            settle();
+            if (lane == 0) {
+              pend_old = atomicAdd(args.tt_flags + tiles_m + ml, 1u);
+              pend_blk = ml;
+            }
+            ++nacq;
+            __syncwarp();
+            if (lane == 0) ptx::st_release_cta_shared(tt_ready, nacq);
+            at += num_units;
+          }
+        }
+      }
+      settle();
     }
   } else if constexpr (TWO) {
     // ================================= slab epilogue (pair kernel), warps 0..NEPI-1 =================================
@@ -479,11 +540,9 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         ptx::tma_store_commit();
       }
     };
-    if (has_aux && issuer && unit < num_tiles) issue_aux(0, unit, 0);
-    for (int tile = unit; tile < num_tiles; tile += num_units, ++it) {
-      const int m0 = mblock(tile) * TILE_M + static_cast<int>(rank) * BM;
-      const int n0 = (tile % tiles_n) * BN;
-      if (has_ttile(tile)) {
+    auto epi_ttile = [&](int mlin) {
+      {
+        const int m0 = block_row0(mlin);
         // ---- T-tile epilogue: columns [0, tt_n) of this accumulator are T = A * TB^T for this CTA's 128 rows.  Column
         // group 0 converts them (+ the optional per-column bias) and writes its rows straight to global memory (16 KB per
         // CTA: no staging buffer, no TMA store to wait for); group 1 only returns the accumulator. ----
@@ -522,6 +581,16 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (lane == 0) ptx::mbar_arrive(tt_done);
         }
         ++it;
+      }
+    };
+    if (has_aux && issuer && unit < num_tiles) issue_aux(0, unit, 0);
+    if (unit < tt_pro) epi_ttile(unit);
+    for (int tile = unit; tile < num_tiles; tile += num_units, ++it) {
+      const int m0 = mblock(tile) * TILE_M + static_cast<int>(rank) * BM;
+      const int n0 = (tile % tiles_n) * BN;
+      {
+        const int mt = ttile_of(tile);
+        if (mt >= 0) epi_ttile(mt);
       }
       const uint32_t buf = it & 1;
       const uint32_t use = it >> 1;

@@ -69,6 +69,7 @@ struct GemmKernelArgs {
   int tt_ld;
   const float* tt_bias;
   unsigned int* tt_flags;
+  int dbg_rt;    // run-time experiment switches that exist in the product build (VITATK_GEMM_RT): 1 = no L2 prefetch of T-tiles
   int gelu_f32;  // GELU in the pair epilogue: 1 = fp32 Abramowitz-Stegun (VITATK_GELU=f32), otherwise the fp32 2^P fit
   int dbg;  // timing experiments (DBG instantiation only, VITATK_GEMM_DBG): 1 no aux loads, 2 no stores,
             // 4 no TMA loads after the first ring fill, 8 no MMA issue, 16 epilogue skips TMEM reads and math,
@@ -282,12 +283,21 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int n0 = (tile % tiles_n) * BN;
       const int nb0 = n0 + static_cast<int>(rank) * Cfg::B_ROWS;                     // pair: this CTA's half of B
       const int tcol0 = args.lora_group_cols > 0 ? (n0 / args.lora_group_cols) * BK : 0;
+      int pf_row0 = -1;  // rows of the T-tile that follows this output tile in the unit's sequence
       if constexpr (TWO) {
         const int mt = ttile_of(tile);
         if (mt >= 0) load_ttile(mt);
+        // A T-tile is the first reader of its A block (one wave ahead of the block's output tiles), and with one CTA's
+        // ring in flight it would stream from HBM latency-bound.  So while this output tile runs, the A rows of the
+        // unit's NEXT T-tile are pulled into L2, one k-block per k-block (same K, hence the same count).
+        if (tt_on && tile + num_units < num_tiles && !(args.dbg_rt & 1)) {
+          const int nmt = ttile_of(tile + num_units);
+          if (nmt >= 0) pf_row0 = block_row0(nmt);
+        }
       }
       for (int kb = 0; kb < num_kb; ++kb, ++cnt) {
         const int s = cnt % STAGES;
+        if (TWO && pf_row0 >= 0 && kb < main_kb) ptx::tma_prefetch_2d_p(leader, &tmA, kb * BK, pf_row0);
         if (TWO && tt_on && kb == main_kb) {
           // The LoRA k-block reads T rows produced by a T-tile (usually of another unit).  The publisher warp has
           // acquired the block's flag ahead of time and counts the output tiles that may proceed; all that is left here
@@ -1306,6 +1316,14 @@ static int launch_bn(const GemmPlan* p, cudaStream_t stream, int num_sms) {
   a.tt_ld = p->tt.ld_out;
   a.tt_bias = p->tt.bias;
   a.tt_flags = p->tt.flags;
+  {
+    static int rt = -1;
+    if (rt < 0) {
+      const char* e = getenv("VITATK_GEMM_RT");
+      rt = e ? atoi(e) : 0;
+    }
+    a.dbg_rt = rt;
+  }
   const dim3 grid(TWO ? 2 * units : units, 1, 1), block(gemm_threads(TWO, EW), 1, 1);
 #ifdef VITATK_DBG_KERNELS  // timing-experiment instantiations (VITATK_GEMM_DBG switches) are not part of the product build
   if (a.dbg) {

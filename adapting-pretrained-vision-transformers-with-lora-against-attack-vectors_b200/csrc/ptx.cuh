@@ -314,6 +314,17 @@ __device__ __forceinline__ void tma_load_2d_p(uint32_t leader, void* smem_dst, c
       "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(leader)
       : "memory");
 }
+// TMA prefetch of a tile into L2 only (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_2d_p(uint32_t leader, const void* tmap, int c0, int c1) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %3, 0;\n\t"
+      "@q cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];\n\t"
+      "}\n" ::"l"(reinterpret_cast<uint64_t>(tmap)),
+      "r"(c0), "r"(c1), "r"(leader)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_3d_p(uint32_t leader, void* smem_dst, const void* tmap, uint64_t* bar, int c0,
                                               int c1, int c2) {
   asm volatile(

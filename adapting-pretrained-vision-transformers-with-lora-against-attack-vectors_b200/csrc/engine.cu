@@ -121,6 +121,12 @@ struct vitatk_engine {
   char* cbuf = nullptr;              // backing store of the lbx / tones arrays
   bool const_dirty = true;           // weights / adapters changed since the constant columns were packed
   bool fuse_stats = true;            // folded LayerNorm: (mean, rstd) come out of the skinny LoRA GEMM (VITATK_FUSE_STATS=0: stats kernel)
+  // T-tiles per site, VITATK_TT_SITES bit mask: 1 proj, 2 fc2, 4 fc2-bwd, 8 fc1-bwd, 16 proj-bwd, 32 qkv-bwd.  Default 0:
+  // measured inside the PGD step on B200 (one box, back to back: mask 0 / 17 / 51 / 63 = 245.9 / 246.7 / 247.5 / 249.4 ms)
+  // the T-tiles cost as much as the skinny GEMMs they replace -- a T-tile streams its A block at the ring-depth x latency
+  // bound (~680 clk per k-block whatever its size) and unbalances the static tile schedule, while the separate skinny
+  // GEMM finds its input L2-hot (zig-zag) and uses all 148 SMs.  The mechanism stays available and tested.
+  int tt_sites = 0;
   bool fuse_tt = true;               // plain LoRA sites: T = x*A^T comes from T-tiles inside the consumer GEMM (VITATK_TT=0: skinny GEMMs)
   unsigned int* tt_flags = nullptr;  // [2 * ceil(max M / 256)] inter-CTA flags of the T-tiles (zero between launches)
   bool fuse_delta = false;           // delta comes out of the proj-backward GEMM epilogue (pair kernel) instead of a kernel
@@ -275,7 +281,7 @@ static int build_plans(vitatk_engine* e, int batch, PlanSet** out) {
     {
       GemmEpilogue ep = plain;
       if (sp.ccol > 0) ep.bias = sp.tones;  // T[:, ccol..ccol+1] = 1: proj's bias is added by the tensor core
-      const GemmTT tt = make_tt(sp, sp.la_fwd, D, site_ksteps(sp), ep.bias, true);
+      const GemmTT tt = make_tt(sp, sp.la_fwd, D, site_ksteps(sp), ep.bias, e->tt_sites & 1);
       p.t_proj.M = 0;  // M == 0: not launched (T comes from the consumer's T-tiles)
       if (sp.rank > 0 && tt.n == 0 &&
           gemm_plan_init(&p.t_proj, M, LORA_PAD, D, e->ao[l], D, sp.la_fwd, D, e->T, 3 * LORA_PAD, nullptr, 0, nullptr, 0,
@@ -315,7 +321,7 @@ static int build_plans(vitatk_engine* e, int batch, PlanSet** out) {
     {
       GemmEpilogue ep = plain;
       if (s2.ccol > 0) ep.bias = s2.tones;
-      const GemmTT tt = make_tt(s2, s2.la_fwd, F, site_ksteps(s2), ep.bias, true);
+      const GemmTT tt = make_tt(s2, s2.la_fwd, F, site_ksteps(s2), ep.bias, e->tt_sites & 2);
       p.t_fc2.M = 0;
       if (s2.rank > 0 && tt.n == 0 &&
           gemm_plan_init(&p.t_fc2, M, LORA_PAD, F, e->g, F, s2.la_fwd, F, e->T, 3 * LORA_PAD, nullptr, 0, nullptr, 0,
@@ -330,7 +336,7 @@ static int build_plans(vitatk_engine* e, int batch, PlanSet** out) {
     // The residual-stream gradient ping-pongs: layer l receives it in dh_in(l) and leaves dh_out(l).
     // dh entering layer l (grad wrt h[l+1]) lives in dh_a; dh_mid in dh_b; result (grad wrt h[l]) in dh_a.
     {
-      const GemmTT tt = make_tt(s2, s2.lb_bwd, D, lora_ksteps(s2.rank), nullptr, true);
+      const GemmTT tt = make_tt(s2, s2.lb_bwd, D, lora_ksteps(s2.rank), nullptr, e->tt_sites & 4);
       p.bt_fc2.M = 0;
       if (s2.rank > 0 && tt.n == 0 &&
           gemm_plan_init(&p.bt_fc2, M, LORA_PAD, D, e->dh_a, D, s2.lb_bwd, D, e->T, 3 * LORA_PAD, nullptr, 0, nullptr, 0,
@@ -342,7 +348,7 @@ static int build_plans(vitatk_engine* e, int batch, PlanSet** out) {
         return 1;
     }
     {
-      const GemmTT tt = make_tt(s1, s1.lb_bwd, F, lora_ksteps(s1.rank), nullptr, true);
+      const GemmTT tt = make_tt(s1, s1.lb_bwd, F, lora_ksteps(s1.rank), nullptr, e->tt_sites & 8);
       p.bt_fc1.M = 0;
       if (s1.rank > 0 && tt.n == 0 &&
           gemm_plan_init(&p.bt_fc1, M, LORA_PAD, F, e->du, F, s1.lb_bwd, F, e->T, 3 * LORA_PAD, nullptr, 0, nullptr, 0,
@@ -353,7 +359,7 @@ static int build_plans(vitatk_engine* e, int batch, PlanSet** out) {
         return 1;
     }
     {
-      const GemmTT tt = make_tt(sp, sp.lb_bwd, D, lora_ksteps(sp.rank), nullptr, true);
+      const GemmTT tt = make_tt(sp, sp.lb_bwd, D, lora_ksteps(sp.rank), nullptr, e->tt_sites & 16);
       p.bt_proj.M = 0;
       if (sp.rank > 0 && tt.n == 0 &&
           gemm_plan_init(&p.bt_proj, M, LORA_PAD, D, e->dh_b, D, sp.lb_bwd, D, e->T, 3 * LORA_PAD, nullptr, 0, nullptr, 0,
@@ -375,7 +381,7 @@ static int build_plans(vitatk_engine* e, int batch, PlanSet** out) {
         return 1;
     }
     {
-      const GemmTT tt = make_tt(sq, sq.lb_bwd, 3 * D, lora_ksteps(sq.rank), nullptr, sq.packed);
+      const GemmTT tt = make_tt(sq, sq.lb_bwd, 3 * D, lora_ksteps(sq.rank), nullptr, sq.packed && (e->tt_sites & 32));
       p.bt_qkv.M = 0;
       if (sq.rank > 0 && tt.n == 0 &&
           gemm_plan_init(&p.bt_qkv, M, q_tcols, 3 * D, e->dqkv, 3 * D, sq.lb_bwd, 3 * D, e->T, 3 * LORA_PAD, nullptr,
@@ -546,6 +552,8 @@ int vitatk_create(const vitatk_config* cfg, vitatk_engine** out) {
     e->zigzag = !(zz && zz[0] == '0');
     const char* tt = getenv("VITATK_TT");
     e->fuse_tt = !(tt && tt[0] == '0') && !(g2 && g2[0] == '0') && cfg->dim % 256 == 0 && cfg->mlp_dim % 256 == 0;
+    const char* tts = getenv("VITATK_TT_SITES");
+    if (tts) e->tt_sites = atoi(tts);
     const char* fs = getenv("VITATK_FUSE_STATS");
     e->fuse_stats = !(fs && fs[0] == '0');
     const char* tc = getenv("VITATK_TC_CONST");

@@ -69,7 +69,7 @@ struct GemmKernelArgs {
   int tt_ld;
   const float* tt_bias;
   unsigned int* tt_flags;
-  int dbg_rt;    // run-time experiment switches that exist in the product build (VITATK_GEMM_RT): 1 = no L2 prefetch of T-tiles
+  int dbg_rt;    // run-time experiment switches that exist in the product build (VITATK_GEMM_RT): 1 = L2 prefetch of T-tiles
   int gelu_f32;  // GELU in the pair epilogue: 1 = fp32 Abramowitz-Stegun (VITATK_GELU=f32), otherwise the fp32 2^P fit
   int dbg;  // timing experiments (DBG instantiation only, VITATK_GEMM_DBG): 1 no aux loads, 2 no stores,
             // 4 no TMA loads after the first ring fill, 8 no MMA issue, 16 epilogue skips TMEM reads and math,
@@ -287,10 +287,11 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if constexpr (TWO) {
         const int mt = ttile_of(tile);
         if (mt >= 0) load_ttile(mt);
-        // A T-tile is the first reader of its A block (one wave ahead of the block's output tiles), and with one CTA's
-        // ring in flight it would stream from HBM latency-bound.  So while this output tile runs, the A rows of the
-        // unit's NEXT T-tile are pulled into L2, one k-block per k-block (same K, hence the same count).
-        if (tt_on && tile + num_units < num_tiles && !(args.dbg_rt & 1)) {
+        // Experiment (VITATK_GEMM_RT=1, off by default): pull the A rows of the unit's NEXT T-tile into L2 while this
+        // output tile runs.  Measured on B200 it makes T-tiles SLOWER (fc2: 70 instead of 50 us per launch): a T-tile is
+        // bound by the ring depth x the loaded L2 -> SM latency (~680 clk per k-block whatever its size), not by HBM, and
+        // the prefetch traffic only delays the output tile it rides on.
+        if (tt_on && tile + num_units < num_tiles && (args.dbg_rt & 1)) {
           const int nmt = ttile_of(tile + num_units);
           if (nmt >= 0) pf_row0 = block_row0(nmt);
         }

@@ -126,15 +126,15 @@ def load() -> C.CDLL:
     lib.vitatk_count_correct.argtypes = [vp, vp, vp, i, vp, vp]
     lib.vitatk_profile_begin.argtypes = [vp]
     lib.vitatk_profile_end.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(ll)]
-    lib.vitatk_k_gemm.argtypes = [i, i, i, vp, i, vp, i, vp, i, vp, i, vp, i, vp, i, i, i, i, i, vp, vp, i, vp, i, vp, i, i, vp, vp, vp, f, vp, i, vp, vp, vp]
+    lib.vitatk_k_gemm.argtypes = [i, i, i, vp, i, vp, i, vp, i, vp, i, vp, i, vp, i, i, i, i, i, vp, vp, i, vp, i, vp, i, i, vp, vp, vp, f, vp, i, vp, vp, i, vp]
     lib.vitatk_k_attention_fwd_tc05.argtypes = [vp, vp, vp, i, i, i, vp]
     lib.vitatk_k_attention_bwd_fused.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, vp]
     lib.vitatk_k_gemm_trace.argtypes = [vp]
     lib.vitatk_k_attention_bwd_trace.argtypes = [vp]
     lib.vitatk_k_attention_fwd_trace.argtypes = [vp]
-    lib.vitatk_k_layernorm_fwd.argtypes = [vp, vp, vp, vp, vp, i, i, f, vp]
-    lib.vitatk_k_layernorm_bwd.argtypes = [vp, vp, vp, vp, vp, vp, i, i, vp]
-    lib.vitatk_k_layernorm_stats.argtypes = [vp, vp, i, i, f, vp]
+    lib.vitatk_k_layernorm_fwd.argtypes = [vp, vp, vp, vp, vp, i, i, f, i, vp]
+    lib.vitatk_k_layernorm_bwd.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, vp]
+    lib.vitatk_k_layernorm_stats.argtypes = [vp, vp, i, i, f, i, vp]
     lib.vitatk_k_pgd_update.argtypes = [vp, vp, vp, vp, i, C.POINTER(f), C.POINTER(f), f, f, vp]
     lib.vitatk_k_pgd_init.argtypes = [vp, vp, vp, vp, i, C.POINTER(f), C.POINTER(f), f, i, u64, u64, vp]
     for name in EXPORTS:

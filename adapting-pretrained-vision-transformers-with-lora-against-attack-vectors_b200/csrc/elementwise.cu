@@ -5,6 +5,8 @@
 // Reference call sites replaced: torch LayerNorm (HF modeling_vit.py:325-326,333,340,455), classifier
 // (HF:613,642), F.cross_entropy (whitebox_attacks.py:29), normalisation (whitebox_attacks.py:26),
 // the FGSM tail (whitebox_attacks.py:32-38) and the torchattacks PGD loop body.
+#include <cuda_fp16.h>
+
 #include "vitatk_internal.h"
 
 namespace vitatk {
@@ -23,11 +25,36 @@ __device__ __forceinline__ void unpack8(const uint4& q, float* f) {
     f[2 * i + 1] = t.y;
   }
 }
+// The two residual streams (forward h, backward dh) are stored as IEEE fp16 instead of bf16: same bytes,
+// 8x smaller rounding step on the only tensors whose rounding accumulates over all 24 residual adds.  f16 != 0 selects it.
+__device__ __forceinline__ void unpack8(const uint4& q, float* f, int f16) {
+  if (f16) {
+    const __half2* p = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 t = __half22float2(p[i]);
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
+  } else {
+    unpack8(q, f);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* f, int f16);
 __device__ __forceinline__ uint4 pack8(const float* f) {
   uint4 q;
   __nv_bfloat162* p = reinterpret_cast<__nv_bfloat162*>(&q);
 #pragma unroll
   for (int i = 0; i < 4; ++i) p[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return q;
+}
+
+__device__ __forceinline__ uint4 pack8(const float* f, int f16) {
+  if (!f16) return pack8(f);
+  uint4 q;
+  __half2* p = reinterpret_cast<__half2*>(&q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
   return q;
 }
 
@@ -37,7 +64,7 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 template <int CH>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, bf16* __restrict__ y,
-                                                     float2* __restrict__ stats, int rows, float eps) {
+                                                     float2* __restrict__ stats, int rows, float eps, int x_f16) {
   pdl_wait();
   pdl_launch_dependents();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -49,7 +76,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x,
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < CH; ++i) {
-    unpack8(__ldg(xr + lane + 32 * i), v[i]);
+    unpack8(__ldg(xr + lane + 32 * i), v[i], x_f16);
 #pragma unroll
     for (int j = 0; j < 8; ++j) s += v[i][j];
   }
@@ -83,7 +110,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x,
 
 template <int CH>
 __global__ void __launch_bounds__(256) ln_stats_kernel(const bf16* __restrict__ x, float2* __restrict__ stats, int rows,
-                                                       float eps) {
+                                                       float eps, int x_f16) {
   pdl_wait();
   pdl_launch_dependents();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -95,7 +122,7 @@ __global__ void __launch_bounds__(256) ln_stats_kernel(const bf16* __restrict__ 
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < CH; ++i) {
-    unpack8(__ldg(xr + lane + 32 * i), v[i]);
+    unpack8(__ldg(xr + lane + 32 * i), v[i], x_f16);
 #pragma unroll
     for (int j = 0; j < 8; ++j) s += v[i][j];
   }
@@ -116,7 +143,7 @@ template <int CH>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                                                      const float2* __restrict__ stats, const float* __restrict__ gamma,
                                                      const bf16* __restrict__ dres, bf16* __restrict__ dx, int rows,
-                                                     int streaming) {
+                                                     int streaming, int x_f16, int g_f16) {
   pdl_wait();
   pdl_launch_dependents();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -135,7 +162,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
   for (int i = 0; i < CH; ++i) {
     const int c = (lane + 32 * i) * 8;
     float xv[8], dv[8];
-    unpack8(ld(xr + lane + 32 * i), xv);
+    unpack8(ld(xr + lane + 32 * i), xv, x_f16);
     unpack8(ld(dyr + lane + 32 * i), dv);
     const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c));
     const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
@@ -156,41 +183,41 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
   for (int i = 0; i < CH; ++i) {
     float o[8];
     float r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (rr) unpack8(ld(rr + lane + 32 * i), r);
+    if (rr) unpack8(ld(rr + lane + 32 * i), r, g_f16);
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = r[j] + st.y * (gd[i][j] - m1 - xh[i][j] * m2);
-    dxr[lane + 32 * i] = pack8(o);
+    dxr[lane + 32 * i] = pack8(o, g_f16);
   }
 }
 
 int layernorm_fwd(const bf16* x, const float* gamma, const float* beta, bf16* y, float2* stats, int rows, int cols,
-                  float eps, cudaStream_t stream) {
+                  float eps, cudaStream_t stream, int x_f16) {
   const int grid = (rows + 7) / 8;
   switch (cols) {
-    case 768: VITATK_CUDA_OK(launch_pdl(ln_fwd_kernel<3>, dim3(grid), dim3(256), 0, stream, 1, x, gamma, beta, y, stats, rows, eps)); break;
-    case 1024: VITATK_CUDA_OK(launch_pdl(ln_fwd_kernel<4>, dim3(grid), dim3(256), 0, stream, 1, x, gamma, beta, y, stats, rows, eps)); break;
-    case 512: VITATK_CUDA_OK(launch_pdl(ln_fwd_kernel<2>, dim3(grid), dim3(256), 0, stream, 1, x, gamma, beta, y, stats, rows, eps)); break;
-    case 256: VITATK_CUDA_OK(launch_pdl(ln_fwd_kernel<1>, dim3(grid), dim3(256), 0, stream, 1, x, gamma, beta, y, stats, rows, eps)); break;
+    case 768: VITATK_CUDA_OK(launch_pdl(ln_fwd_kernel<3>, dim3(grid), dim3(256), 0, stream, 1, x, gamma, beta, y, stats, rows, eps, x_f16)); break;
+    case 1024: VITATK_CUDA_OK(launch_pdl(ln_fwd_kernel<4>, dim3(grid), dim3(256), 0, stream, 1, x, gamma, beta, y, stats, rows, eps, x_f16)); break;
+    case 512: VITATK_CUDA_OK(launch_pdl(ln_fwd_kernel<2>, dim3(grid), dim3(256), 0, stream, 1, x, gamma, beta, y, stats, rows, eps, x_f16)); break;
+    case 256: VITATK_CUDA_OK(launch_pdl(ln_fwd_kernel<1>, dim3(grid), dim3(256), 0, stream, 1, x, gamma, beta, y, stats, rows, eps, x_f16)); break;
     default: set_error("layernorm_fwd: cols=%d unsupported", cols); return 1;
   }
   VITATK_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
-int layernorm_stats(const bf16* x, float2* stats, int rows, int cols, float eps, cudaStream_t stream) {
+int layernorm_stats(const bf16* x, float2* stats, int rows, int cols, float eps, cudaStream_t stream, int x_f16) {
   const int grid = (rows + 7) / 8;
   switch (cols) {
-    case 768: VITATK_CUDA_OK(launch_pdl(ln_stats_kernel<3>, dim3(grid), dim3(256), 0, stream, 1, x, stats, rows, eps)); break;
-    case 1024: VITATK_CUDA_OK(launch_pdl(ln_stats_kernel<4>, dim3(grid), dim3(256), 0, stream, 1, x, stats, rows, eps)); break;
-    case 512: VITATK_CUDA_OK(launch_pdl(ln_stats_kernel<2>, dim3(grid), dim3(256), 0, stream, 1, x, stats, rows, eps)); break;
-    case 256: VITATK_CUDA_OK(launch_pdl(ln_stats_kernel<1>, dim3(grid), dim3(256), 0, stream, 1, x, stats, rows, eps)); break;
+    case 768: VITATK_CUDA_OK(launch_pdl(ln_stats_kernel<3>, dim3(grid), dim3(256), 0, stream, 1, x, stats, rows, eps, x_f16)); break;
+    case 1024: VITATK_CUDA_OK(launch_pdl(ln_stats_kernel<4>, dim3(grid), dim3(256), 0, stream, 1, x, stats, rows, eps, x_f16)); break;
+    case 512: VITATK_CUDA_OK(launch_pdl(ln_stats_kernel<2>, dim3(grid), dim3(256), 0, stream, 1, x, stats, rows, eps, x_f16)); break;
+    case 256: VITATK_CUDA_OK(launch_pdl(ln_stats_kernel<1>, dim3(grid), dim3(256), 0, stream, 1, x, stats, rows, eps, x_f16)); break;
     default: set_error("layernorm_stats: cols=%d unsupported", cols); return 1;
   }
   return 0;
 }
 
 int layernorm_bwd(const bf16* dy, const bf16* x, const float2* stats, const float* gamma, const bf16* dres,
-                  bf16* dx_out, int rows, int cols, cudaStream_t stream) {
+                  bf16* dx_out, int rows, int cols, cudaStream_t stream, int x_f16, int g_f16) {
   const int grid = (rows + 7) / 8;
   static int streaming = -1;
   if (streaming < 0) {
@@ -198,10 +225,10 @@ int layernorm_bwd(const bf16* dy, const bf16* x, const float2* stats, const floa
     streaming = (e && e[0] == '0') ? 0 : 1;
   }
   switch (cols) {
-    case 768: VITATK_CUDA_OK(launch_pdl(ln_bwd_kernel<3>, dim3(grid), dim3(256), 0, stream, 1, dy, x, stats, gamma, dres, dx_out, rows, streaming)); break;
-    case 1024: VITATK_CUDA_OK(launch_pdl(ln_bwd_kernel<4>, dim3(grid), dim3(256), 0, stream, 1, dy, x, stats, gamma, dres, dx_out, rows, streaming)); break;
-    case 512: VITATK_CUDA_OK(launch_pdl(ln_bwd_kernel<2>, dim3(grid), dim3(256), 0, stream, 1, dy, x, stats, gamma, dres, dx_out, rows, streaming)); break;
-    case 256: VITATK_CUDA_OK(launch_pdl(ln_bwd_kernel<1>, dim3(grid), dim3(256), 0, stream, 1, dy, x, stats, gamma, dres, dx_out, rows, streaming)); break;
+    case 768: VITATK_CUDA_OK(launch_pdl(ln_bwd_kernel<3>, dim3(grid), dim3(256), 0, stream, 1, dy, x, stats, gamma, dres, dx_out, rows, streaming, x_f16, g_f16)); break;
+    case 1024: VITATK_CUDA_OK(launch_pdl(ln_bwd_kernel<4>, dim3(grid), dim3(256), 0, stream, 1, dy, x, stats, gamma, dres, dx_out, rows, streaming, x_f16, g_f16)); break;
+    case 512: VITATK_CUDA_OK(launch_pdl(ln_bwd_kernel<2>, dim3(grid), dim3(256), 0, stream, 1, dy, x, stats, gamma, dres, dx_out, rows, streaming, x_f16, g_f16)); break;
+    case 256: VITATK_CUDA_OK(launch_pdl(ln_bwd_kernel<1>, dim3(grid), dim3(256), 0, stream, 1, dy, x, stats, gamma, dres, dx_out, rows, streaming, x_f16, g_f16)); break;
     default: set_error("layernorm_bwd: cols=%d unsupported", cols); return 1;
   }
   VITATK_CUDA_OK(cudaGetLastError());
@@ -227,7 +254,8 @@ __global__ void __launch_bounds__(256) head_kernel(const bf16* __restrict__ h, c
                                                    const float* __restrict__ bc, const int64_t* __restrict__ labels,
                                                    float* __restrict__ logits, float* __restrict__ loss,
                                                    bf16* __restrict__ dh, int tokens, int dim, int classes, float eps,
-                                                   float grad_scale, const float* __restrict__ dlogits) {
+                                                   float grad_scale, const float* __restrict__ dlogits, int h_f16,
+                                                   int dh_f16, float* __restrict__ y_out, float* __restrict__ dlogits_out) {
   pdl_wait();
   pdl_launch_dependents();
   extern __shared__ float hs[];
@@ -240,7 +268,7 @@ __global__ void __launch_bounds__(256) head_kernel(const bf16* __restrict__ h, c
   const bf16* row = h + static_cast<size_t>(b) * tokens * dim;
   float s = 0.f;
   for (int k = tid; k < dim; k += blockDim.x) {
-    const float v = __bfloat162float(row[k]);
+    const float v = h_f16 ? __half2float(reinterpret_cast<const __half*>(row)[k]) : __bfloat162float(row[k]);
     xn[k] = v;
     s += v;
   }
@@ -280,12 +308,16 @@ __global__ void __launch_bounds__(256) head_kernel(const bf16* __restrict__ h, c
   for (int c = tid + blockDim.x; c < classes; c += blockDim.x) logits[static_cast<size_t>(b) * classes + c] = lg[c];
   if (tid == 0 && loss && y >= 0) loss[b] = lse - lg[y];
   if (tid == 0 && loss && bad_label) loss[b] = __int_as_float(0x7fc00000);
+  if (y_out != nullptr)  // LoRA training: the classifier's input (final-LayerNorm output of the CLS row)
+    for (int k = tid; k < dim; k += blockDim.x) y_out[static_cast<size_t>(b) * dim + k] = yv[k];
   if (dh == nullptr) return;
   // dlogits = (softmax - onehot) * grad_scale, or the caller's cotangent (vector-Jacobian product); dy = Wc^T dlogits
   __syncthreads();
   for (int c = tid; c < classes; c += blockDim.x)
     lg[c] = dlogits ? dlogits[static_cast<size_t>(b) * classes + c] : expf(lg[c] - lse) - (c == y ? 1.f : 0.f);
   __syncthreads();
+  if (dlogits_out != nullptr)  // LoRA training: the classifier's output cotangent (unscaled)
+    for (int c = tid; c < classes; c += blockDim.x) dlogits_out[static_cast<size_t>(b) * classes + c] = lg[c];
   for (int k = tid; k < dim; k += blockDim.x) {
     float acc = 0.f;
     for (int c = 0; c < classes; ++c) acc += lg[c] * __ldg(Wc + static_cast<size_t>(c) * dim + k);
@@ -301,8 +333,11 @@ __global__ void __launch_bounds__(256) head_kernel(const bf16* __restrict__ h, c
   const float m1 = block_sum(s1, red) / dim;
   const float m2 = block_sum(s2, red) / dim;
   bf16* drow = dh + static_cast<size_t>(b) * tokens * dim;
-  for (int k = tid; k < dim; k += blockDim.x)
-    drow[k] = __float2bfloat16(rstd * (dyv[k] * gamma[k] - m1 - xn[k] * m2));
+  for (int k = tid; k < dim; k += blockDim.x) {
+    const float o = rstd * (dyv[k] * gamma[k] - m1 - xn[k] * m2);
+    if (dh_f16) reinterpret_cast<__half*>(drow)[k] = __float2half_rn(o);
+    else drow[k] = __float2bfloat16(o);
+  }
   // every other token of this image receives zero gradient from the head
   uint4* z = reinterpret_cast<uint4*>(drow + dim);
   const int nz = (tokens - 1) * dim / 8;
@@ -311,14 +346,15 @@ __global__ void __launch_bounds__(256) head_kernel(const bf16* __restrict__ h, c
 
 int head_fwd_bwd(const bf16* h, const float* gamma, const float* beta, const float* Wc, const float* bc,
                  const int64_t* labels, float* logits, float* loss, bf16* dh, int batch, int tokens, int dim,
-                 int classes, float eps, float grad_scale, cudaStream_t stream, const float* dlogits) {
+                 int classes, float eps, float grad_scale, cudaStream_t stream, const float* dlogits, int h_f16, int dh_f16,
+                 float* y_out, float* dlogits_out) {
   if (dim % 8 != 0 || classes > 4096) {
     set_error("head_fwd_bwd: dim=%d classes=%d unsupported", dim, classes);
     return 1;
   }
   const size_t smem = (3 * dim + classes) * sizeof(float);
   VITATK_CUDA_OK(launch_pdl(head_kernel, dim3(batch), dim3(256), smem, stream, 1, h, gamma, beta, Wc, bc, labels, logits,
-                            loss, dh, tokens, dim, classes, eps, grad_scale, dlogits));
+                            loss, dh, tokens, dim, classes, eps, grad_scale, dlogits, h_f16, dh_f16, y_out, dlogits_out));
   return 0;
 }
 

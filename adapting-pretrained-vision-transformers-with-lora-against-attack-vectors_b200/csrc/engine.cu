@@ -127,6 +127,13 @@ struct vitatk_engine {
   // bound (~680 clk per k-block whatever its size) and unbalances the static tile schedule, while the separate skinny
   // GEMM finds its input L2-hot (zig-zag) and uses all 148 SMs.  The mechanism stays available and tested.
   int tt_sites = 0;
+  // Residual streams in IEEE fp16: h / h_mid (forward) and dh_a / dh_b (backward) are the only tensors
+  // whose 16-bit rounding accumulates over all 24 residual adds; fp16 has three more mantissa bits than bf16 at the same
+  // size, and tcgen05 kind::f16 multiplies an fp16 A operand with bf16 weights.  The backward stream carries gradients
+  // scaled by grad_S (a power of two, undone when the image gradient is materialised; sign() never sees it) so that they
+  // sit in fp16's normal range.  VITATK_RES_F16=0: bf16 streams (round-1 behaviour).
+  bool res_f16 = true;
+  float grad_S = 256.0f;
   bool fuse_tt = true;               // plain LoRA sites: T = x*A^T comes from T-tiles inside the consumer GEMM (VITATK_TT=0: skinny GEMMs)
   unsigned int* tt_flags = nullptr;  // [2 * ceil(max M / 256)] inter-CTA flags of the T-tiles (zero between launches)
   bool fuse_delta = false;           // delta comes out of the proj-backward GEMM epilogue (pair kernel) instead of a kernel
@@ -396,6 +403,19 @@ static int build_plans(vitatk_engine* e, int batch, PlanSet** out) {
   if (gemm_plan_init(&ps->bpatch, M, D, D, e->dh_a, D, e->patch_wt, D, e->dxn, D, nullptr, 0, nullptr, 0, nullptr, 0, 0,
                      0, 0, plain))
     return 1;
+  if (e->res_f16) {  // which operands / outputs live on the fp16 residual streams
+    ps->patch.out_f16 = 1;
+    ps->bpatch.a_f16 = 1;
+    for (int l = 0; l < c.layers; ++l) {
+      LayerPlans& p = ps->layers[l];
+      const bool fold = e->lw[l].qkv_c1 != nullptr && e->lw[l].fc1_c1 != nullptr;
+      if (fold) p.t_qkv.a_f16 = p.qkv.a_f16 = p.t_fc1.a_f16 = p.fc1.a_f16 = 1;  // A = the raw stream (LayerNorm folded)
+      p.proj.out_f16 = p.proj.res_f16 = 1;
+      p.fc2.out_f16 = p.fc2.res_f16 = 1;
+      p.bt_fc2.a_f16 = p.bfc2.a_f16 = 1;    // A = dh_a
+      p.bt_proj.a_f16 = p.bproj.a_f16 = 1;  // A = dh_b
+    }
+  }
   if (e->zigzag) {
     // the skinny x*A^T GEMMs read what the previous kernel has just written front to back: walk it back to front so the
     // tail that is still in L2 is consumed first (the main GEMM that follows reads front to back again)
@@ -456,9 +476,9 @@ static int encoder_forward(vitatk_engine* e, PlanSet* ps, int batch, cudaStream_
     const int rq = w.lora[VITATK_SITE_QKV].rank, r1 = w.lora[VITATK_SITE_FC1].rank;
     const bool fold = w.qkv_c1 != nullptr && w.fc1_c1 != nullptr;
     if (fold) {  // only (mean, rstd): the normalisation itself happens in the qkv GEMM's epilogue
-      if (!(rq > 0 && p.t_qkv.epi.stats_out)) RUNC(CAT_LN_FWD, 0, layernorm_stats(e->h[l], e->st1[l], M, D, c.ln_eps, s));
+      if (!(rq > 0 && p.t_qkv.epi.stats_out)) RUNC(CAT_LN_FWD, 0, layernorm_stats(e->h[l], e->st1[l], M, D, c.ln_eps, s, e->res_f16));
     } else
-      RUNC(CAT_LN_FWD, 0, layernorm_fwd(e->h[l], w.ln1_g, w.ln1_b, e->xn, e->st1[l], M, D, c.ln_eps, s));
+      RUNC(CAT_LN_FWD, 0, layernorm_fwd(e->h[l], w.ln1_g, w.ln1_b, e->xn, e->st1[l], M, D, c.ln_eps, s, e->res_f16));
     if (rq > 0) RUN_GEMM(CAT_T_QKV, &p.t_qkv);
     RUN_GEMM(CAT_QKV, &p.qkv);
     RUNC(CAT_ATTN_FWD, 4.0 * batch * c.heads * TOKENS * TOKENS * 64, attention_fwd_tc05(&ps->attn_fwd[l], s));
@@ -466,9 +486,9 @@ static int encoder_forward(vitatk_engine* e, PlanSet* ps, int batch, cudaStream_
     RUN_GEMM(CAT_PROJ, &p.proj);
     if (fold) {
       if (!(r1 > 0 && p.t_fc1.epi.stats_out))
-        RUNC(CAT_LN_FWD, 0, layernorm_stats(e->h_mid[l], e->st2[l], M, D, c.ln_eps, s));
+        RUNC(CAT_LN_FWD, 0, layernorm_stats(e->h_mid[l], e->st2[l], M, D, c.ln_eps, s, e->res_f16));
     } else
-      RUNC(CAT_LN_FWD, 0, layernorm_fwd(e->h_mid[l], w.ln2_g, w.ln2_b, e->xn, e->st2[l], M, D, c.ln_eps, s));
+      RUNC(CAT_LN_FWD, 0, layernorm_fwd(e->h_mid[l], w.ln2_g, w.ln2_b, e->xn, e->st2[l], M, D, c.ln_eps, s, e->res_f16));
     if (r1 > 0) RUN_GEMM(CAT_T_FC1, &p.t_fc1);
     RUN_GEMM(CAT_FC1, &p.fc1);
     if (w.lora[VITATK_SITE_FC2].rank > 0 && p.t_fc2.M > 0) RUN_GEMM(CAT_T_FC2, &p.t_fc2);
@@ -488,14 +508,14 @@ static int encoder_backward(vitatk_engine* e, PlanSet* ps, int batch, cudaStream
     RUN_GEMM(CAT_BFC2, &p.bfc2);  // du = (dh W2 + lora) * gelu'(u)   (u[l] holds gelu'(u), written by fc1's epilogue)
     if (w.lora[VITATK_SITE_FC1].rank > 0 && p.bt_fc1.M > 0) RUN_GEMM(CAT_BT_FC1, &p.bt_fc1);
     RUN_GEMM(CAT_BFC1, &p.bfc1);  // dxn = du W1 + lora
-    RUNC(CAT_LN_BWD, 0, layernorm_bwd(e->dxn, e->h_mid[l], e->st2[l], w.ln2_g, e->dh_a, e->dh_b, M, D, s));  // dh_mid
+    RUNC(CAT_LN_BWD, 0, layernorm_bwd(e->dxn, e->h_mid[l], e->st2[l], w.ln2_g, e->dh_a, e->dh_b, M, D, s, e->res_f16, e->res_f16));  // dh_mid
     if (w.lora[VITATK_SITE_PROJ].rank > 0 && p.bt_proj.M > 0) RUN_GEMM(CAT_BT_PROJ, &p.bt_proj);
     RUN_GEMM(CAT_BPROJ, &p.bproj);  // dao = dh_mid Wp + lora
     RUNC(CAT_ATTN_BWD, 8.0 * batch * c.heads * TOKENS * TOKENS * 64,
          attention_bwd_fused(&ps->attn_bwd[l], s, !e->fuse_delta));
     if (w.lora[VITATK_SITE_QKV].rank > 0 && p.bt_qkv.M > 0) RUN_GEMM(CAT_BT_QKV, &p.bt_qkv);
     RUN_GEMM(CAT_BQKV, &p.bqkv);  // dxn = dqkv Wqkv + lora
-    RUNC(CAT_LN_BWD, 0, layernorm_bwd(e->dxn, e->h[l], e->st1[l], w.ln1_g, e->dh_b, e->dh_a, M, D, s));  // dh wrt h[l]
+    RUNC(CAT_LN_BWD, 0, layernorm_bwd(e->dxn, e->h[l], e->st1[l], w.ln1_g, e->dh_b, e->dh_a, M, D, s, e->res_f16, e->res_f16));  // dh wrt h[l]
   }
   RUN_GEMM(CAT_BPATCH, &ps->bpatch);  // dxn <- dL/d(cols)
   return 0;
@@ -552,6 +572,9 @@ int vitatk_create(const vitatk_config* cfg, vitatk_engine** out) {
     e->zigzag = !(zz && zz[0] == '0');
     const char* tt = getenv("VITATK_TT");
     e->fuse_tt = !(tt && tt[0] == '0') && !(g2 && g2[0] == '0') && cfg->dim % 256 == 0 && cfg->mlp_dim % 256 == 0;
+    const char* rf = getenv("VITATK_RES_F16");
+    e->res_f16 = !(rf && rf[0] == '0');
+    if (!e->res_f16) e->grad_S = 1.0f;
     const char* tts = getenv("VITATK_TT_SITES");
     if (tts) e->tt_sites = atoi(tts);
     const char* fs = getenv("VITATK_FUSE_STATS");
@@ -818,7 +841,7 @@ int vitatk_forward(vitatk_engine* e, const float* images, int batch, float* logi
   RUNC(CAT_PIXEL, 0, pgd_init(images, nullptr, e->scratch_img, e->cols, batch, e->nrm, 0.f, 0, 0, 0, s));
   if (encoder_forward(e, ps, batch, s)) return 1;
   RUNC(CAT_HEAD, 0, head_fwd_bwd(e->h[c.layers], e->lnf_g, e->lnf_b, e->head_w, e->head_b, nullptr, logits_out, nullptr, nullptr,
-                   batch, TOKENS, c.dim, c.num_classes, c.ln_eps, 0.f, s));
+                   batch, TOKENS, c.dim, c.num_classes, c.ln_eps, 0.f, s, nullptr, e->res_f16, e->res_f16));
   return 0;
 }
 
@@ -834,9 +857,10 @@ int vitatk_input_grad(vitatk_engine* e, const float* images, const int64_t* labe
   // internal gradient is of the SUM of per-image CE (keeps magnitudes independent of batch / sharding);
   // the 1/B of the reference's mean reduction (whitebox_attacks.py:29) is applied when materialising.
   RUNC(CAT_HEAD, 0, head_fwd_bwd(e->h[c.layers], e->lnf_g, e->lnf_b, e->head_w, e->head_b, labels, logits_out ? logits_out : e->logits,
-                   loss_out ? loss_out : e->loss, e->dh_a, batch, TOKENS, c.dim, c.num_classes, c.ln_eps, 1.0f, s));
+                   loss_out ? loss_out : e->loss, e->dh_a, batch, TOKENS, c.dim, c.num_classes, c.ln_eps, e->grad_S, s,
+                   nullptr, e->res_f16, e->res_f16));
   if (encoder_backward(e, ps, batch, s)) return 1;
-  RUNC(CAT_PIXEL, 0, grad_to_image(e->dxn, grad_out, batch, e->nrm, 1.0f / batch, s));
+  RUNC(CAT_PIXEL, 0, grad_to_image(e->dxn, grad_out, batch, e->nrm, 1.0f / (batch * e->grad_S), s));
   return 0;
 }
 
@@ -854,9 +878,10 @@ int vitatk_vjp(vitatk_engine* e, const float* images, const float* dlogits, int 
   RUNC(CAT_PIXEL, 0, pgd_init(images, nullptr, e->scratch_img, e->cols, batch, e->nrm, 0.f, 0, 0, 0, s));
   if (encoder_forward(e, ps, batch, s)) return 1;
   RUNC(CAT_HEAD, 0, head_fwd_bwd(e->h[c.layers], e->lnf_g, e->lnf_b, e->head_w, e->head_b, nullptr, logits_out ? logits_out : e->logits,
-                   nullptr, e->dh_a, batch, TOKENS, c.dim, c.num_classes, c.ln_eps, 1.0f, s, dlogits));
+                   nullptr, e->dh_a, batch, TOKENS, c.dim, c.num_classes, c.ln_eps, e->grad_S, s, dlogits, e->res_f16,
+                   e->res_f16));
   if (encoder_backward(e, ps, batch, s)) return 1;
-  RUNC(CAT_PIXEL, 0, grad_to_image(e->dxn, grad_out, batch, e->nrm, 1.0f, s));
+  RUNC(CAT_PIXEL, 0, grad_to_image(e->dxn, grad_out, batch, e->nrm, 1.0f / e->grad_S, s));
   return 0;
 }
 
@@ -881,7 +906,7 @@ int vitatk_attack(vitatk_engine* e, const float* images, const int64_t* labels, 
   for (int it = 0; it < steps; ++it) {
     if (encoder_forward(e, ps, batch, s)) return 1;
     RUNC(CAT_HEAD, 0, head_fwd_bwd(e->h[c.layers], e->lnf_g, e->lnf_b, e->head_w, e->head_b, labels, e->logits, e->loss, e->dh_a,
-                     batch, TOKENS, c.dim, c.num_classes, c.ln_eps, 1.0f, s));
+                     batch, TOKENS, c.dim, c.num_classes, c.ln_eps, e->grad_S, s, nullptr, e->res_f16, e->res_f16));
     if (encoder_backward(e, ps, batch, s)) return 1;
     RUNC(CAT_PIXEL, 0, pgd_update(e->dxn, images, adv, e->cols, batch, e->nrm, eps, alpha, s));
   }
@@ -915,7 +940,7 @@ int vitatk_k_gemm(int M, int N, int K, const void* A, int lda, const void* B, in
                   int lora_group_cols, int epi_mode, const float* bias, const void* res, int ld_res, const float* table,
                   int table_rows, float* rowdot, int rowdot_rows, int rowdot_pad, const float* row_stats, const float* c1,
                   float* stats_out, float stats_eps, const void* tt_tb, int tt_n, const float* tt_bias,
-                  unsigned int* tt_flags, void* stream) {
+                  unsigned int* tt_flags, int formats, void* stream) {
   GemmPlan p;
   GemmEpilogue ep = {};
   ep.mode = epi_mode;
@@ -946,6 +971,9 @@ int vitatk_k_gemm(int M, int N, int K, const void* A, int lda, const void* B, in
                      static_cast<bf16*>(out), ldo, static_cast<bf16*>(out2), ldo2, static_cast<const bf16*>(T), ldt,
                      static_cast<const bf16*>(LB), ldlb, lora_nkb, lora_ksteps_, lora_group_cols, ep, &tt))
     return 1;
+  p.a_f16 = formats & 1;
+  p.out_f16 = (formats >> 1) & 1;
+  p.res_f16 = (formats >> 2) & 1;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -969,19 +997,19 @@ int vitatk_k_gemm_trace(long long* dev_buf) { return gemm_set_trace(dev_buf); }
 int vitatk_k_attention_bwd_trace(long long* dev_buf) { return attention_bwd_set_trace(dev_buf); }
 int vitatk_k_attention_fwd_trace(long long* dev_buf) { return attention_fwd_set_trace(dev_buf); }
 int vitatk_k_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* stats, int rows,
-                           int cols, float eps, void* stream) {
+                           int cols, float eps, int x_f16, void* stream) {
   return layernorm_fwd(static_cast<const bf16*>(x), gamma, beta, static_cast<bf16*>(y),
-                       reinterpret_cast<float2*>(stats), rows, cols, eps, static_cast<cudaStream_t>(stream));
+                       reinterpret_cast<float2*>(stats), rows, cols, eps, static_cast<cudaStream_t>(stream), x_f16);
 }
 int vitatk_k_layernorm_bwd(const void* dy, const void* x, const float* stats, const float* gamma, const void* dres,
-                           void* dx, int rows, int cols, void* stream) {
+                           void* dx, int rows, int cols, int x_f16, int g_f16, void* stream) {
   return layernorm_bwd(static_cast<const bf16*>(dy), static_cast<const bf16*>(x),
                        reinterpret_cast<const float2*>(stats), gamma, static_cast<const bf16*>(dres),
-                       static_cast<bf16*>(dx), rows, cols, static_cast<cudaStream_t>(stream));
+                       static_cast<bf16*>(dx), rows, cols, static_cast<cudaStream_t>(stream), x_f16, g_f16);
 }
-int vitatk_k_layernorm_stats(const void* x, float* stats, int rows, int cols, float eps, void* stream) {
+int vitatk_k_layernorm_stats(const void* x, float* stats, int rows, int cols, float eps, int x_f16, void* stream) {
   return layernorm_stats(static_cast<const bf16*>(x), reinterpret_cast<float2*>(stats), rows, cols, eps,
-                         static_cast<cudaStream_t>(stream));
+                         static_cast<cudaStream_t>(stream), x_f16);
 }
 static PixelNorm make_norm(const float* mean3, const float* std3) {
   PixelNorm n;

@@ -69,6 +69,7 @@ struct GemmKernelArgs {
   int tt_ld;
   const float* tt_bias;
   unsigned int* tt_flags;
+  int a_f16, out_f16, res_f16;  // 16-bit formats of the A operand / output / EPI_RESIDUAL input (0 bf16, 1 fp16)
   int dbg_rt;    // run-time experiment switches that exist in the product build (VITATK_GEMM_RT): 1 = L2 prefetch of T-tiles
   int gelu_f32;  // GELU in the pair epilogue: 1 = fp32 Abramowitz-Stegun (VITATK_GELU=f32), otherwise the fp32 2^P fit
   int dbg;  // timing experiments (DBG instantiation only, VITATK_GEMM_DBG): 1 no aux loads, 2 no stores,
@@ -117,6 +118,19 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi);
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void unpack_f16x8(const uint4& q, float* f) {
+  const __half2* p = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __half22float2(p[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
 }
 __device__ __forceinline__ void unpack_bf16x8(const uint4& q, float* f) {
   const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&q);
@@ -350,14 +364,15 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == MMA_WARP) {
     // ================================= MMA issuer (converged warp, elected lane issues) =================================
     const uint32_t leader = ptx::elect_leader();
-    constexpr uint32_t idesc = ptx::make_idesc_bf16(TILE_M, BN);
+    constexpr uint32_t idesc = ptx::make_idesc_bf16(TILE_M, BN);          // A = T (bf16): the LoRA k-blocks
+    const uint32_t idesc_a = args.a_f16 ? (idesc & ~(7u << 7)) : idesc;   // a_format field: 0 = F16, 1 = BF16
     uint32_t cnt = 0;
     uint32_t it = 0;
     auto mma_ttile = [&]() {  // T-tile: M = 256, N = tt_n, K = the GEMM's K, into the first columns of accumulator it & 1
       const uint32_t tbuf = it & 1;
       ptx::mbar_wait(&tmem_empty[tbuf], ((it >> 1) & 1) ^ 1);
       ptx::tc_fence_after();
-      const uint32_t idesc_t = ptx::make_idesc_bf16(TILE_M, static_cast<uint32_t>(args.tt_n));
+      const uint32_t idesc_t = ptx::make_idesc_bf16(TILE_M, static_cast<uint32_t>(args.tt_n)) & (args.a_f16 ? ~(7u << 7) : ~0u);
       for (int kb = 0; kb < main_kb; ++kb, ++cnt) {
         const int s = cnt % STAGES;
         ptx::mbar_wait(&full_bar[s], (cnt / STAGES) & 1);
@@ -399,13 +414,13 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint64_t bdesc = ptx::make_smem_desc_sw128(sb);
           const int ksteps = (kb < main_kb) ? BK / 16 : args.lora_ksteps;
           if (!(DBG && (args.dbg & 8))) {
-            if (ksteps == BK / 16) {
+            if (kb < main_kb) {
 #pragma unroll
               for (int k = 0; k < BK / 16; ++k) {  // +16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in (addr>>4)
                 if constexpr (TWO)
-                  ptx::umma_bf16_2cta_p(leader, tmem_acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                  ptx::umma_bf16_2cta_p(leader, tmem_acc, adesc + 2 * k, bdesc + 2 * k, idesc_a, (kb > 0 || k > 0) ? 1u : 0u);
                 else
-                  ptx::umma_bf16_p(leader, tmem_acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                  ptx::umma_bf16_p(leader, tmem_acc, adesc + 2 * k, bdesc + 2 * k, idesc_a, (kb > 0 || k > 0) ? 1u : 0u);
               }
             } else {
               for (int k = 0; k < ksteps; ++k) {
@@ -775,7 +790,8 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint32_t addr = rowaddr + (((hh * NQ + j) ^ swz) << 4);
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(addr));
             float f[8];
-            unpack_bf16x8(a, f);
+            if (args.res_f16 && epi.mode == EPI_RESIDUAL) unpack_f16x8(a, f);
+            else unpack_bf16x8(a, f);
             if (epi.mode == EPI_ROWDOT) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
@@ -799,6 +815,9 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (EW == 1 && row_ok)
               epi.rowdot[(static_cast<size_t>(row / epi.rowdot_rows) * (args.N >> 6) + (scol >> 6)) * epi.rowdot_pad +
                          row % epi.rowdot_rows] = dot;
+          } else if (args.out_f16) {
+#pragma unroll
+            for (int j = 0; j < NP; ++j) pk[j] = pack_f16x2(v[2 * j], v[2 * j + 1]);
           } else {
 #pragma unroll
             for (int j = 0; j < NP; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
@@ -814,8 +833,13 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             else if (tile + num_units < num_tiles) issue_aux(c, tile + num_units, 0);
           }
         } else {
+          if (args.out_f16) {
 #pragma unroll
-          for (int j = 0; j < NP; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+            for (int j = 0; j < NP; ++j) pk[j] = pack_f16x2(v[2 * j], v[2 * j + 1]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < NP; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+          }
           prefetch_slab1();
           GTR(sl, 4);
           // One group barrier per slab: buffer c & 1 was last read by the store of slab c - 2, and the issuer only passes
@@ -886,7 +910,8 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               const uint32_t addr = rowaddr + ((c ^ (srow & 7)) << 4);
               asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(addr));
               float f[8];
-              unpack_bf16x8(a, f);
+              if (args.a_f16) unpack_f16x8(a, f);
+              else unpack_bf16x8(a, f);
               if (kb == 0 && c == 0) shift = f[0];
 #pragma unroll
               for (int k = 0; k < 8; ++k) {
@@ -973,7 +998,8 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             float f[8];
-            unpack_bf16x8(aux[j], f);
+            if (args.res_f16 && epi.mode == EPI_RESIDUAL) unpack_f16x8(aux[j], f);
+            else unpack_bf16x8(aux[j], f);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
               if (epi.mode == EPI_RESIDUAL) v[8 * j + k] += f[k];
@@ -1030,6 +1056,9 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (!(DBG && (args.dbg & 2)))
             stage_and_store(my_out + (store_idx & 1) * STAGE_OUT_BYTES, packed2, &tmOut2, ncol, m0 + q * 32, lane);
           ++store_idx;
+        } else if (args.out_f16) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) packed[j] = pack_f16x2(v[2 * j], v[2 * j + 1]);
         } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j) packed[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
@@ -1158,6 +1187,7 @@ int gemm_plan_init(GemmPlan* p, int M, int N, int K, const bf16* A, int lda, con
   p->lora_group_cols = lora_group_cols;
   p->epi = epi;
   p->reverse_m = 0;
+  p->a_f16 = p->out_f16 = p->res_f16 = 0;
   p->tt = GemmTT{};
   if (tt != nullptr && tt->n > 0) p->tt = *tt;
   if (lora_group_cols > 0 && lora_group_cols % p->BN != 0) {
@@ -1317,6 +1347,9 @@ static int launch_bn(const GemmPlan* p, cudaStream_t stream, int num_sms) {
   a.tt_ld = p->tt.ld_out;
   a.tt_bias = p->tt.bias;
   a.tt_flags = p->tt.flags;
+  a.a_f16 = p->a_f16;
+  a.out_f16 = p->out_f16;
+  a.res_f16 = p->res_f16;
   {
     static int rt = -1;
     if (rt < 0) {

@@ -158,6 +158,10 @@ struct GemmPlan {
   int lora_nkb;         // extra 64-wide k-blocks (0 = no adapter)
   int lora_ksteps;      // UMMA k-steps (16 each) issued per extra k-block = ceil(r/16)
   int lora_group_cols;  // >0: T column offset = (n0 / lora_group_cols) * 64  (fused q|k|v forward)
+  // 16-bit storage formats (0 = bf16, 1 = IEEE fp16): the A operand, the output and the residual read by EPI_RESIDUAL.
+  // The residual streams are fp16; tcgen05 kind::f16 takes the A and B formats independently, so an fp16 activation
+  // meets bf16 weights in one MMA.  Set by the engine after gemm_plan_init (defaults 0).
+  int a_f16, out_f16, res_f16;
   GemmEpilogue epi;
   GemmTT tt;
   // tensor maps (built once per plan)
@@ -211,18 +215,21 @@ int attention_fwd_set_trace(long long* dev_buf);
 // LayerNorm / head / PGD kernels (HBM-bound)
 // ---------------------------------------------------------------------------------------------
 // (mean, rstd) per row only: the read-only half of LayerNorm, for consumers that fold the normalisation into a GEMM
-int layernorm_stats(const bf16* x, float2* stats, int rows, int cols, float eps, cudaStream_t stream);
+// x_f16 / g_f16: the LayerNorm input x (forward residual stream) resp. dres / dx_out (backward residual stream) hold IEEE
+// fp16 instead of bf16 bit patterns (same 16-bit storage; the pointers stay typed bf16*)
+int layernorm_stats(const bf16* x, float2* stats, int rows, int cols, float eps, cudaStream_t stream, int x_f16 = 0);
 int layernorm_fwd(const bf16* x, const float* gamma, const float* beta, bf16* y, float2* stats, int rows,
-                  int cols, float eps, cudaStream_t stream);
+                  int cols, float eps, cudaStream_t stream, int x_f16 = 0);
 // dx_out = dres + LN_backward(dy) ; x is the saved LN input, stats = (mean, rstd)
 int layernorm_bwd(const bf16* dy, const bf16* x, const float2* stats, const float* gamma, const bf16* dres,
-                  bf16* dx_out, int rows, int cols, cudaStream_t stream);
+                  bf16* dx_out, int rows, int cols, cudaStream_t stream, int x_f16 = 0, int g_f16 = 0);
 // final LN on CLS rows + classifier + softmax-CE; writes logits, per-image loss, and (optionally) the
 // gradient wrt the final hidden state (non-CLS rows zero-filled).  dlogits == nullptr: the cotangent is
 // softmax - onehot (cross-entropy); otherwise the caller's [batch, classes] fp32 cotangent (vector-Jacobian product).
 int head_fwd_bwd(const bf16* h, const float* gamma, const float* beta, const float* Wc, const float* bc,
                  const int64_t* labels, float* logits, float* loss, bf16* dh, int batch, int tokens, int dim,
-                 int classes, float eps, float grad_scale, cudaStream_t stream, const float* dlogits = nullptr);
+                 int classes, float eps, float grad_scale, cudaStream_t stream, const float* dlogits = nullptr,
+                 int h_f16 = 0, int dh_f16 = 0, float* y_out = nullptr, float* dlogits_out = nullptr);
 
 struct PixelNorm {
   float mean[3];

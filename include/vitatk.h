@@ -164,14 +164,17 @@ int vitatk_profile_end(vitatk_engine* e, double* ms_by_cat, double* flops_by_cat
 /* ---- kernel-level entry points (used by tests/ and bench.py's roofline leg) ----
  * vitatk_k_gemm with tt_n in {32, 64}: "T-tile" mode of the pair kernel -- the GEMM computes T = A * tt_tb^T (tt_tb bf16
  * [64, K], + tt_bias[64] if given) itself, writes it to T_dev and uses it as its LoRA k-block in the same launch;
- * tt_flags_dev is a zero-initialised uint32 [2 * ceil(M / 256)] scratch that the launch leaves zeroed. */
+ * tt_flags_dev is a zero-initialised uint32 [2 * ceil(M / 256)] scratch that the launch leaves zeroed.
+ * formats: bit 0 = A holds IEEE fp16 (else bf16), bit 1 = the output is written as fp16, bit 2 = the EPI_RESIDUAL input is
+ * fp16 (the engine keeps its two residual streams in fp16; B / T / LB are always bf16).  The LayerNorm entry points take
+ * x_f16 (their input x) and g_f16 (dres / dx) the same way. */
 int vitatk_k_gemm(int M, int N, int K, const void* A_dev, int lda, const void* B_dev, int ldb, void* out_dev,
                   int ldo, void* out2_dev, int ldo2, const void* T_dev, int ldt, const void* LB_dev, int ldlb,
                   int lora_nkb, int lora_ksteps, int lora_group_cols, int epi_mode, const float* bias_dev,
                   const void* res_dev, int ld_res, const float* table_dev, int table_rows, float* rowdot_dev,
                   int rowdot_rows, int rowdot_pad, const float* row_stats_dev, const float* c1_dev, float* stats_out_dev,
                   float stats_eps, const void* tt_tb_dev, int tt_n, const float* tt_bias_dev, unsigned int* tt_flags_dev,
-                  void* stream);
+                  int formats, void* stream);
 /* tcgen05 forward (the engine's path); lse2_dev (optional) receives [batch*heads, 208] log2-domain logsumexp */
 int vitatk_k_attention_fwd_tc05(const void* qkv_dev, void* out_dev, float* lse2_dev, int batch, int tokens, int heads,
                                 void* stream);
@@ -187,11 +190,11 @@ int vitatk_k_gemm_trace(long long* dev_buf);  /* pair GEMM epilogue timeline (VI
 int vitatk_k_attention_bwd_trace(long long* trace_dev);
 int vitatk_k_attention_fwd_trace(long long* trace_dev);
 int vitatk_k_layernorm_fwd(const void* x_dev, const float* gamma_dev, const float* beta_dev, void* y_dev,
-                           float* stats_dev, int rows, int cols, float eps, void* stream);
+                           float* stats_dev, int rows, int cols, float eps, int x_f16, void* stream);
 /* (mean, rstd) per row only (stats_dev fp32 [rows, 2]) */
-int vitatk_k_layernorm_stats(const void* x_dev, float* stats_dev, int rows, int cols, float eps, void* stream);
+int vitatk_k_layernorm_stats(const void* x_dev, float* stats_dev, int rows, int cols, float eps, int x_f16, void* stream);
 int vitatk_k_layernorm_bwd(const void* dy_dev, const void* x_dev, const float* stats_dev, const float* gamma_dev,
-                           const void* dres_dev, void* dx_dev, int rows, int cols, void* stream);
+                           const void* dres_dev, void* dx_dev, int rows, int cols, int x_f16, int g_f16, void* stream);
 int vitatk_k_pgd_update(const void* dcols_dev, const float* x0_dev, float* adv_dev, void* cols_dev, int batch,
                         const float* mean3, const float* std3, float eps, float alpha, void* stream);
 int vitatk_k_pgd_init(const float* x0_dev, const float* noise_dev, float* adv_dev, void* cols_dev, int batch,

@@ -28,19 +28,19 @@ def _dgelu(u):
 
 def run_gemm(lib, A, B, epi=EPI_PLAIN, bias=None, res=None, table=None, T=None, LB=None, nkb=0, ksteps=0,
              group_cols=0, rowdot=None, rowdot_rows=0, row_stats=None, c1=None, stats_out=None, tt_tb=None, tt_n=0,
-             tt_bias=None, tt_flags=None):
+             tt_bias=None, tt_flags=None, formats=0):
     from vitatk import _lib
 
     M, K = A.shape
     N = B.shape[0]
-    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float16 if formats & 2 else torch.bfloat16)
     out2 = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16) if epi == EPI_GELU_DUAL else None
     rc = lib.vitatk_k_gemm(M, N, K, _p(A), A.stride(0), _p(B), B.stride(0), _p(out), N, _p(out2), N, _p(T),
                            0 if T is None else T.stride(0), _p(LB), 0 if LB is None else LB.stride(0), nkb, ksteps,
                            group_cols, epi, _p(bias), _p(res), 0 if res is None else res.stride(0), _p(table),
                            0 if table is None else table.shape[0], _p(rowdot), rowdot_rows,
                            0 if rowdot is None else rowdot.shape[1], _p(row_stats), _p(c1), _p(stats_out), 1e-12,
-                           _p(tt_tb), tt_n, _p(tt_bias), _p(tt_flags), _s())
+                           _p(tt_tb), tt_n, _p(tt_bias), _p(tt_flags), formats, _s())
     _lib.check(rc, "vitatk_k_gemm")
     torch.cuda.synchronize()
     return out, out2
@@ -198,6 +198,41 @@ def test_gemm_ttiles_compute_the_lora_projection_in_the_same_launch(lib, M, N, K
     assert torch.equal(out2, out) and torch.equal(T2, T)
 
 
+@pytest.mark.parametrize("M,N,K,epi,formats", [
+    (1576, 768, 768, EPI_RESIDUAL, 7),    # proj / fc2 forward: fp16 A? no -- exercised fully: A, out and residual all fp16
+    (1576, 768, 3072, EPI_RESIDUAL, 6),   # fc2 forward as the engine runs it: bf16 A, fp16 residual in, fp16 out
+    (1576, 2304, 768, EPI_PLAIN, 1),      # qkv forward: fp16 A (the raw residual stream), bf16 out
+    (1576, 768, 768, EPI_ROWTABLE, 2),    # patch embed: fp16 out
+    (50432, 3072, 768, EPI_MUL, 1),       # fc2 backward: fp16 A (dh), bf16 multiplier and output
+    (1576, 64, 768, EPI_PLAIN, 1),        # skinny GEMM on an fp16 A (single-CTA kernel)
+])
+def test_gemm_mixed_fp16_bf16_operands(lib, M, N, K, epi, formats):
+    """The residual streams are IEEE fp16 while weights, T and every other activation stay bf16: tcgen05 kind::f16 takes the
+    A and B formats independently.  Checks every format switch of the GEMM against torch."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K + formats)
+    rn = lambda *s: torch.randn(*s, device="cuda", generator=g)  # noqa: E731
+    A = rn(M, K).to(torch.float16 if formats & 1 else torch.bfloat16)
+    B = (rn(N, K) / math.sqrt(K)).to(torch.bfloat16)
+    res = None
+    if epi in (EPI_RESIDUAL, EPI_MUL):
+        res = rn(M, N).to(torch.float16 if (formats & 4 and epi == EPI_RESIDUAL) else torch.bfloat16)
+    table = rn(197, N) if epi == EPI_ROWTABLE else None
+    T = LB = None
+    nkb = ksteps = 0
+    if N % 256 == 0:
+        nkb, ksteps = 1, 1
+        T = torch.zeros(M, 64, device="cuda")
+        LB = torch.zeros(N, 64, device="cuda")
+        T[:, :8], LB[:, :8] = rn(M, 8), rn(N, 8) * 0.1
+        T, LB = T.to(torch.bfloat16), LB.to(torch.bfloat16)
+    out, _ = run_gemm(lib, A, B, epi, None, res, table, T, LB, nkb, ksteps, 0, formats=formats)
+    assert out.dtype == (torch.float16 if formats & 2 else torch.bfloat16)
+    want, _ = ref_gemm(A, B, epi, None, res, table, T, LB, nkb, ksteps, 0)
+    check_close(out, want, f"mixed-format gemm {M}x{N}x{K} epi{epi} formats{formats}")
+    if formats & 2:  # fp16 output: three more mantissa bits than bf16
+        assert float((out.float() - want).abs().max()) <= 2e-3 * float(want.abs().max()) + 1e-3
+
+
 @pytest.mark.parametrize("images,tokens", [(8, 197), (3, 50), (256, 197)])
 def test_gemm_rowdot_epilogue(lib, images, tokens):
     """proj backward with the fused attention delta: out = A B^T (+ LoRA), side[b*12 + h, i] = sum_64 bf16(out) * res."""
@@ -236,7 +271,7 @@ def test_gemm_layernorm_fold(lib, M, N, epi):
     c1 = Wf.float().sum(1)
     c2 = b + W @ beta
     stats = torch.empty(M, 2, device="cuda")
-    _lib.check(lib.vitatk_k_layernorm_stats(_p(h), _p(stats), M, K, 1e-12, _s()), "ln_stats")
+    _lib.check(lib.vitatk_k_layernorm_stats(_p(h), _p(stats), M, K, 1e-12, 0, _s()), "ln_stats")
     out, out2 = run_gemm(lib, h, Wf, epi, c2.contiguous(), row_stats=stats, c1=c1.contiguous())
     ref = torch.nn.functional.layer_norm(h.float(), (K,), gamma, beta, eps=1e-12) @ W.t() + b
     if epi == EPI_GELU_DUAL:
@@ -311,22 +346,27 @@ def test_attention_fwd_bwd_vs_torch(lib, batch, tokens):
     check_rel(delta[:, :tokens], dref, "attention delta", 1e-2, 3e-2)  # o is bf16-rounded in the kernel's input
 
 
-@pytest.mark.parametrize("rows", [1, 8, 197, 1576, 50432])
-def test_layernorm_fwd_bwd_vs_torch(lib, rows):
+@pytest.mark.parametrize("rows,f16", [(1, 0), (8, 1), (197, 0), (1576, 1), (50432, 0), (50432, 1)])
+def test_layernorm_fwd_bwd_vs_torch(lib, rows, f16):
+    """f16 = 1: the LayerNorm input x and the residual-gradient stream (dres in, dx out) are IEEE fp16, as in the engine."""
     from vitatk import _lib
 
     cols = 768
+    sdt = torch.float16 if f16 else torch.bfloat16
     g = torch.Generator(device="cuda").manual_seed(rows)
-    x = (torch.randn(rows, cols, device="cuda", generator=g) * 2 + 0.5).to(torch.bfloat16)
+    x = (torch.randn(rows, cols, device="cuda", generator=g) * 2 + 0.5).to(sdt)
     gamma = 1 + 0.1 * torch.randn(cols, device="cuda", generator=g)
     beta = 0.1 * torch.randn(cols, device="cuda", generator=g)
     dy = torch.randn(rows, cols, device="cuda", generator=g).to(torch.bfloat16)
-    dres = torch.randn(rows, cols, device="cuda", generator=g).to(torch.bfloat16)
-    y = torch.empty_like(x)
+    dres = torch.randn(rows, cols, device="cuda", generator=g).to(sdt)
+    y = torch.empty(rows, cols, device="cuda", dtype=torch.bfloat16)
     stats = torch.empty(rows, 2, device="cuda")
-    dx = torch.empty_like(x)
-    _lib.check(lib.vitatk_k_layernorm_fwd(_p(x), _p(gamma), _p(beta), _p(y), _p(stats), rows, cols, 1e-12, _s()), "ln_fwd")
-    _lib.check(lib.vitatk_k_layernorm_bwd(_p(dy), _p(x), _p(stats), _p(gamma), _p(dres), _p(dx), rows, cols, _s()), "ln_bwd")
+    dx = torch.empty_like(dres)
+    _lib.check(lib.vitatk_k_layernorm_fwd(_p(x), _p(gamma), _p(beta), _p(y), _p(stats), rows, cols, 1e-12, f16, _s()), "ln_fwd")
+    _lib.check(lib.vitatk_k_layernorm_bwd(_p(dy), _p(x), _p(stats), _p(gamma), _p(dres), _p(dx), rows, cols, f16, f16, _s()),
+               "ln_bwd")
+    st2 = torch.empty(rows, 2, device="cuda")
+    _lib.check(lib.vitatk_k_layernorm_stats(_p(x), _p(st2), rows, cols, 1e-12, f16, _s()), "ln_stats")
     torch.cuda.synchronize()
     xf = x.float().requires_grad_(True)
     yr = torch.nn.functional.layer_norm(xf, (cols,), gamma, beta, eps=1e-12)
@@ -334,6 +374,7 @@ def test_layernorm_fwd_bwd_vs_torch(lib, rows):
     check_close(y, yr.detach(), "ln y")
     check_close(dx, gx + dres.float(), "ln dx")
     torch.testing.assert_close(stats[:, 0], x.float().mean(-1), rtol=1e-4, atol=1e-4)
+    assert torch.equal(st2, stats)
 
 
 def _cols_from_image(img, mean, std):

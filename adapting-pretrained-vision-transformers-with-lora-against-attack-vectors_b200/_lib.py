@@ -76,7 +76,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 # symbols include/vitatk.h declares; tests check the .so exports every one of them
 EXPORTS = [
     "vitatk_last_error", "vitatk_version", "vitatk_create", "vitatk_destroy", "vitatk_set_tensor", "vitatk_set_lora",
-    "vitatk_set_normalization", "vitatk_finalize", "vitatk_workspace_bytes", "vitatk_forward", "vitatk_input_grad", "vitatk_vjp", "vitatk_png_roundtrip",
+    "vitatk_set_normalization", "vitatk_stream_format", "vitatk_finalize", "vitatk_workspace_bytes", "vitatk_forward", "vitatk_input_grad", "vitatk_vjp", "vitatk_png_roundtrip",
     "vitatk_attack", "vitatk_count_correct", "vitatk_launch_count", "vitatk_k_gemm", "vitatk_k_layernorm_fwd", "vitatk_k_layernorm_bwd", "vitatk_k_pgd_update",
     "vitatk_k_pgd_init", "vitatk_profile_begin", "vitatk_profile_end", "vitatk_k_attention_fwd_tc05",
     "vitatk_k_attention_bwd_fused", "vitatk_k_gemm_trace", "vitatk_k_attention_bwd_trace",
@@ -114,6 +114,7 @@ def load() -> C.CDLL:
     lib.vitatk_set_lora.argtypes = [vp, i, i, i, vp, vp, vp, vp]
     lib.vitatk_set_normalization.argtypes = [vp, C.POINTER(f), C.POINTER(f)]
     lib.vitatk_finalize.argtypes = [vp]
+    lib.vitatk_stream_format.argtypes = [vp]
     lib.vitatk_workspace_bytes.argtypes = [vp]
     lib.vitatk_workspace_bytes.restype = ll
     lib.vitatk_launch_count.argtypes = [vp]

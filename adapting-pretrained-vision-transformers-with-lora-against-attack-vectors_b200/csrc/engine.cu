@@ -129,7 +129,8 @@ struct vitatk_engine {
   int tt_sites = 0;
   // Residual streams in IEEE fp16: h / h_mid (forward) and dh_a / dh_b (backward) are the only tensors
   // whose 16-bit rounding accumulates over all 24 residual adds; fp16 has three more mantissa bits than bf16 at the same
-  // size, and tcgen05 kind::f16 multiplies an fp16 A operand with bf16 weights.  The backward stream carries gradients
+  // size.  tcgen05 kind::f16 needs A and B in one format, so the host packs the operands that multiply a stream as fp16
+  // too (folded qkv / fc1 weights and their adapters' A; fc2^T, proj^T, patch^T and the adapters' B^T for the backward).  The backward stream carries gradients
   // scaled by grad_S (a power of two, undone when the image gradient is materialised; sign() never sees it) so that they
   // sit in fp16's normal range.  VITATK_RES_F16=0: bf16 streams (round-1 behaviour).
   bool res_f16 = true;
@@ -746,6 +747,7 @@ int vitatk_profile_end(vitatk_engine* e, double* ms_by_cat, double* flops_by_cat
 }
 
 long long vitatk_workspace_bytes(const vitatk_engine* e) { return e ? e->ws_bytes : 0; }
+int vitatk_stream_format(const vitatk_engine* e) { return (e && e->res_f16) ? 1 : 0; }
 long long vitatk_launch_count(const vitatk_engine* e) { return e ? e->launches : 0; }
 
 int vitatk_finalize(vitatk_engine* e) {

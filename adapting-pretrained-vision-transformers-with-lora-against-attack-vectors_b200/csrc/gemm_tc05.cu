@@ -69,7 +69,7 @@ struct GemmKernelArgs {
   int tt_ld;
   const float* tt_bias;
   unsigned int* tt_flags;
-  int a_f16, out_f16, res_f16;  // 16-bit formats of the A operand / output / EPI_RESIDUAL input (0 bf16, 1 fp16)
+  int a_f16, out_f16, res_f16;  // 16-bit formats of the A and B operands / output / EPI_RESIDUAL input (0 bf16, 1 fp16)
   int dbg_rt;    // run-time experiment switches that exist in the product build (VITATK_GEMM_RT): 1 = L2 prefetch of T-tiles
   int gelu_f32;  // GELU in the pair epilogue: 1 = fp32 Abramowitz-Stegun (VITATK_GELU=f32), otherwise the fp32 2^P fit
   int dbg;  // timing experiments (DBG instantiation only, VITATK_GEMM_DBG): 1 no aux loads, 2 no stores,
@@ -365,14 +365,17 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ================================= MMA issuer (converged warp, elected lane issues) =================================
     const uint32_t leader = ptx::elect_leader();
     constexpr uint32_t idesc = ptx::make_idesc_bf16(TILE_M, BN);          // A = T (bf16): the LoRA k-blocks
-    const uint32_t idesc_a = args.a_f16 ? (idesc & ~(7u << 7)) : idesc;   // a_format field: 0 = F16, 1 = BF16
+    // a_f16: A AND B of the main k-blocks are IEEE fp16 (a_format / b_format fields: 0 = F16, 1 = BF16).  kind::f16 wants
+    // both operands in the same format -- a mixed fp16 x bf16 descriptor is an illegal instruction on sm_100a (measured)
+    const uint32_t idesc_a = args.a_f16 ? (idesc & ~((7u << 7) | (7u << 10))) : idesc;
     uint32_t cnt = 0;
     uint32_t it = 0;
     auto mma_ttile = [&]() {  // T-tile: M = 256, N = tt_n, K = the GEMM's K, into the first columns of accumulator it & 1
       const uint32_t tbuf = it & 1;
       ptx::mbar_wait(&tmem_empty[tbuf], ((it >> 1) & 1) ^ 1);
       ptx::tc_fence_after();
-      const uint32_t idesc_t = ptx::make_idesc_bf16(TILE_M, static_cast<uint32_t>(args.tt_n)) & (args.a_f16 ? ~(7u << 7) : ~0u);
+      const uint32_t idesc_t =
+          ptx::make_idesc_bf16(TILE_M, static_cast<uint32_t>(args.tt_n)) & (args.a_f16 ? ~((7u << 7) | (7u << 10)) : ~0u);
       for (int kb = 0; kb < main_kb; ++kb, ++cnt) {
         const int s = cnt % STAGES;
         ptx::mbar_wait(&full_bar[s], (cnt / STAGES) & 1);

@@ -158,9 +158,9 @@ struct GemmPlan {
   int lora_nkb;         // extra 64-wide k-blocks (0 = no adapter)
   int lora_ksteps;      // UMMA k-steps (16 each) issued per extra k-block = ceil(r/16)
   int lora_group_cols;  // >0: T column offset = (n0 / lora_group_cols) * 64  (fused q|k|v forward)
-  // 16-bit storage formats (0 = bf16, 1 = IEEE fp16): the A operand, the output and the residual read by EPI_RESIDUAL.
-  // The residual streams are fp16; tcgen05 kind::f16 takes the A and B formats independently, so an fp16 activation
-  // meets bf16 weights in one MMA.  Set by the engine after gemm_plan_init (defaults 0).
+  // 16-bit storage formats (0 = bf16, 1 = IEEE fp16): the A and B operands of the main k-blocks (tcgen05 kind::f16 needs
+  // both in the same format, so the weights that meet an fp16 residual stream are packed as fp16 too; T / LB of the LoRA
+  // k-blocks stay bf16), the output, and the residual read by EPI_RESIDUAL.  Set by the engine after gemm_plan_init.
   int a_f16, out_f16, res_f16;
   GemmEpilogue epi;
   GemmTT tt;

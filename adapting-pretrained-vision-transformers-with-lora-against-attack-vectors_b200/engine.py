@@ -167,6 +167,9 @@ class Engine:
         # LayerNorm folded into the qkv / fc1 GEMMs: LN(h) W^T = rstd (h (gamma o W)^T - mean c1) + c2
         import os as _os
         self.ln_fold = _os.environ.get("VITATK_LN_FOLD", "1") != "0"
+        # Residual streams are IEEE fp16 on the device (csrc/engine.cu res_f16); the tensor cores need both operands of an
+        # MMA in one 16-bit format, so every weight that multiplies a stream is packed as fp16 as well (same bytes)
+        self.res_f16 = _os.environ.get("VITATK_RES_F16", "1") != "0"
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         if model is not None:
             sd = model.state_dict()
@@ -207,6 +210,7 @@ class Engine:
                           self.ln_eps, (C.c_float * 3)(*self.mean), (C.c_float * 3)(*self.std))
         with torch.cuda.device(self.device):
             _lib.check(self.lib.vitatk_create(C.byref(cfg), C.byref(self._h)), "vitatk_create")
+            self.res_f16 = bool(self.lib.vitatk_stream_format(self._h))  # the device side is authoritative
             self._upload(sd)
             _lib.check(self.lib.vitatk_finalize(self._h), "vitatk_finalize")
 
@@ -229,13 +233,14 @@ class Engine:
 
     def _upload(self, sd: Dict[str, torch.Tensor]) -> None:
         bf, f32 = torch.bfloat16, torch.float32
+        sf = torch.float16 if self.res_f16 else bf   # operands that meet a residual stream
         D = self.dim
         g = lambda k: sd[k].detach().to("cpu", torch.float32)  # noqa: E731  (all packing math runs on the host)
         pw = g("vit.embeddings.patch_embeddings.projection.weight").reshape(D, -1)
         if pw.shape[1] != 768:
             raise _lib.VitatkError("patch embedding must be 3x16x16")
         self._set(T_PATCH_W, 0, pw, bf)
-        self._set(T_PATCH_WT, 0, pw.t(), bf)
+        self._set(T_PATCH_WT, 0, pw.t(), sf)      # backward: A = dh (stream)
         pos = g("vit.embeddings.position_embeddings").reshape(-1, D)
         if pos.shape[0] != TOKENS:
             raise _lib.VitatkError(f"expected {TOKENS} position embeddings, got {pos.shape[0]}")
@@ -263,23 +268,24 @@ class Engine:
             # forward operands of the two LayerNorm-fed GEMMs: folded = gamma o W (the backward keeps the plain W^T)
             wqkv_f = (wqkv * g1[None, :]) if fold else wqkv
             wfc1_f = (wfc1 * g2[None, :]) if fold else wfc1
-            self._set(T_QKV_W, l, wqkv_f, bf)
+            fw = sf if fold else bf                   # folded: A = the raw stream h; otherwise A = LayerNorm output (bf16)
+            self._set(T_QKV_W, l, wqkv_f, fw)
             self._set(T_QKV_WT, l, wqkv.t(), bf)
-            self._set(T_FC1_W, l, wfc1_f, bf)
+            self._set(T_FC1_W, l, wfc1_f, fw)
             self._set(T_FC1_WT, l, wfc1.t(), bf)
             for (w_id, wt_id, b_id, key) in ((T_PROJ_W, T_PROJ_WT, T_PROJ_B, "attention.output.dense"),
                                              (T_FC2_W, T_FC2_WT, T_FC2_B, "output.dense")):
                 w = g(p + key + ".weight")
                 self._set(w_id, l, w, bf)
-                self._set(wt_id, l, w.t(), bf)
+                self._set(wt_id, l, w.t(), sf)            # backward of proj / fc2: A = dh (stream)
                 self._set(b_id, l, g(p + key + ".bias"), f32)
             lora_c = self._upload_lora(l, p, {SITE_QKV: (g1, b1), SITE_FC1: (g2, b2)} if fold else {})
             if fold:
                 # c1[n] = sum_k of the bf16 operands the tensor cores really see (+ the adapter's share), c2 in fp32
                 zc = (0.0, 0.0)
-                c1q = wqkv_f.to(bf).float().sum(1) + lora_c.get(SITE_QKV, zc)[0]
+                c1q = wqkv_f.to(fw).float().sum(1) + lora_c.get(SITE_QKV, zc)[0]
                 c2q = bqkv + wqkv @ b1 + lora_c.get(SITE_QKV, zc)[1]
-                c1f = wfc1_f.to(bf).float().sum(1) + lora_c.get(SITE_FC1, zc)[0]
+                c1f = wfc1_f.to(fw).float().sum(1) + lora_c.get(SITE_FC1, zc)[0]
                 c2f = bfc1 + wfc1 @ b2 + lora_c.get(SITE_FC1, zc)[1]
                 self._set(T_QKV_B, l, c2q, f32)
                 self._set(T_FC1_B, l, c2f, f32)
@@ -342,8 +348,13 @@ class Engine:
                         c2[n_out * gi: n_out * (gi + 1)] += s * (B @ (A @ beta))
                     r0 += r
                 rmax = max(rmax, r0)
-            host_bf = [t.to(torch.bfloat16) for t in (la_fwd, lb_fwd, lb_bwd, la_bwd)]
-            bufs = [self._dev(t, torch.bfloat16) for t in host_bf]
+            bfl = torch.bfloat16
+            sfl = torch.float16 if self.res_f16 else bfl
+            # la_fwd multiplies the raw stream h when the site's LayerNorm is folded (qkv, fc1); lb_bwd multiplies the
+            # gradient stream dh at proj and fc2 -- those are packed in the stream's format
+            fmt = [sfl if gamma is not None else bfl, bfl, sfl if site in (SITE_PROJ, SITE_FC2) else bfl, bfl]
+            host_bf = [t.to(f) for t, f in zip((la_fwd, lb_fwd, lb_bwd, la_bwd), fmt)]
+            bufs = [self._dev(t, f) for t, f in zip(host_bf, fmt)]
             _lib.check(self.lib.vitatk_set_lora(self._h, l, SITE_QKV_PACKED if packed else site, rmax,
                                                 *[b.data_ptr() for b in bufs]), f"vitatk_set_lora(layer {l}, site {site})")
             if gamma is not None:

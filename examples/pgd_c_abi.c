@@ -32,14 +32,31 @@ static uint16_t bf16_bits(float f) {  /* round to nearest even */
   u += 0x7fffu + ((u >> 16) & 1u);
   return (uint16_t)(u >> 16);
 }
-/* device bf16 matrix [rows, cols] with N(0, sigma)-ish entries, plus its transpose */
-static int upload_w(int rows, int cols, float sigma, void** w_dev, void** wt_dev) {
+static uint16_t f16_bits(float f) {  /* IEEE half, round to nearest even (|f| here is far inside the normal range) */
+  uint32_t u; memcpy(&u, &f, 4);
+  uint32_t sign = (u >> 16) & 0x8000u, e = (u >> 23) & 0xffu, m = u & 0x7fffffu;
+  if (e < 113) {  /* subnormal half or zero */
+    if (e < 102) return (uint16_t)sign;
+    m |= 0x800000u;
+    uint32_t shift = 126 - e, half = 1u << (shift - 1), r = m >> shift;
+    if ((m & (2 * half - 1)) > half || ((m & (2 * half - 1)) == half && (r & 1u))) ++r;
+    return (uint16_t)(sign | r);
+  }
+  uint32_t h = ((e - 112) << 10) | (m >> 13);
+  if ((m & 0x1fffu) > 0x1000u || ((m & 0x1fffu) == 0x1000u && (h & 1u))) ++h;
+  return (uint16_t)(sign | h);
+}
+/* device 16-bit matrix [rows, cols] with N(0, sigma)-ish entries, plus its transpose.  The transposed copy multiplies
+ * the engine's gradient residual stream in the backward pass and must be in that stream's format (vitatk_stream_format:
+ * IEEE fp16 by default, bf16 otherwise); the forward copy is bf16 (no LayerNorm-fold tensors are supplied here). */
+static int upload_w(int rows, int cols, float sigma, void** w_dev, void** wt_dev, int wt_f16) {
   size_t n = (size_t)rows * cols;
   uint16_t* w = (uint16_t*)malloc(n * 2), * wt = (uint16_t*)malloc(n * 2);
   for (int r = 0; r < rows; ++r)
     for (int c = 0; c < cols; ++c) {
       float v = sigma * (urand() + urand() + urand() + urand() - 2.0f) * 1.7320508f;
-      w[(size_t)r * cols + c] = wt[(size_t)c * rows + r] = bf16_bits(v);
+      w[(size_t)r * cols + c] = bf16_bits(v);
+      wt[(size_t)c * rows + r] = wt_f16 ? f16_bits(v) : bf16_bits(v);
     }
   CU(cudaMalloc(w_dev, n * 2)); CU(cudaMemcpy(*w_dev, w, n * 2, cudaMemcpyHostToDevice));
   if (wt_dev) { CU(cudaMalloc(wt_dev, n * 2)); CU(cudaMemcpy(*wt_dev, wt, n * 2, cudaMemcpyHostToDevice)); }
@@ -61,7 +78,8 @@ int main(void) {
   vitatk_engine* e = NULL;
   CK(vitatk_create(&cfg, &e));
   void *w, *wt, *v;
-  if (upload_w(D, D, 0.02f, &w, &wt)) return 1;
+  const int sf16 = vitatk_stream_format(e);  /* 1: the residual streams (and the operands that multiply them) are fp16 */
+  if (upload_w(D, D, 0.02f, &w, &wt, sf16)) return 1;  /* patch-embed: W^T meets the gradient stream */
   CK(vitatk_set_tensor(e, VITATK_PATCH_W, 0, w, (long long)D * D * 2));
   CK(vitatk_set_tensor(e, VITATK_PATCH_WT, 0, wt, (long long)D * D * 2));
   if (upload_f(197 * D, 0.f, 0.04f, &v)) return 1;
@@ -87,7 +105,8 @@ int main(void) {
                                                       {VITATK_FC1_W, VITATK_FC1_WT, VITATK_FC1_B, F, D},
                                                       {VITATK_FC2_W, VITATK_FC2_WT, VITATK_FC2_B, D, F}};
     for (int k = 0; k < 4; ++k) {
-      if (upload_w(lin[k].out, lin[k].in, 0.02f, &w, &wt)) return 1;
+      /* proj (k = 1) and fc2 (k = 3): their W^T multiplies the gradient stream dh; qkv / fc1 W^T multiply bf16 tensors */
+      if (upload_w(lin[k].out, lin[k].in, 0.02f, &w, &wt, sf16 && (k == 1 || k == 3))) return 1;
       CK(vitatk_set_tensor(e, lin[k].w, l, w, (long long)lin[k].out * lin[k].in * 2));
       CK(vitatk_set_tensor(e, lin[k].wt, l, wt, (long long)lin[k].out * lin[k].in * 2));
       if (upload_f(lin[k].out, 0.f, 0.02f, &v)) return 1;

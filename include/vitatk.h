@@ -88,6 +88,13 @@ int vitatk_destroy(vitatk_engine* e);
  * the caller keeps the buffer alive for the life of the engine.  nbytes is checked against the shape. */
 int vitatk_set_tensor(vitatk_engine* e, int tensor_id, int layer, const void* dev_ptr, long long nbytes);
 
+/* 16-bit format of the engine's two residual streams: 1 = IEEE fp16 (default), 0 = bf16 (VITATK_RES_F16=0).  The tensor
+ * cores need both operands of an MMA in ONE 16-bit format, so the "bf16" tensors that multiply a stream must be supplied
+ * in the stream's format: PATCH_WT, PROJ_WT, FC2_WT (they meet the gradient stream in the backward), QKV_W / FC1_W when
+ * the LayerNorm-fold tensors QKV_C1 / FC1_C1 are supplied (they then meet the raw forward stream), and of the adapters
+ * la_fwd of a folded qkv / fc1 site and lb_bwd of the proj / fc2 sites.  Everything else stays bf16. */
+int vitatk_stream_format(const vitatk_engine* e);
+
 /* replaces: PeftModel.from_pretrained / get_peft_model (train_loras.py:83-92,419).  rank == 0 removes
  * the adapter.  G = 3 for the fused QKV site (q|k|v groups), 1 otherwise; in/out are the Linear's dims.
  *   la_fwd  bf16 [64*G, in]    rows 64g..64g+r = A_g, rest zero           (T = x A^T)
@@ -165,8 +172,9 @@ int vitatk_profile_end(vitatk_engine* e, double* ms_by_cat, double* flops_by_cat
  * vitatk_k_gemm with tt_n in {32, 64}: "T-tile" mode of the pair kernel -- the GEMM computes T = A * tt_tb^T (tt_tb bf16
  * [64, K], + tt_bias[64] if given) itself, writes it to T_dev and uses it as its LoRA k-block in the same launch;
  * tt_flags_dev is a zero-initialised uint32 [2 * ceil(M / 256)] scratch that the launch leaves zeroed.
- * formats: bit 0 = A holds IEEE fp16 (else bf16), bit 1 = the output is written as fp16, bit 2 = the EPI_RESIDUAL input is
- * fp16 (the engine keeps its two residual streams in fp16; B / T / LB are always bf16).  The LayerNorm entry points take
+ * formats: bit 0 = A and B hold IEEE fp16 (else bf16; T / LB are always bf16), bit 1 = the output is written as fp16,
+ * bit 2 = the EPI_RESIDUAL input is fp16 (the engine keeps its two residual streams -- and the weights that multiply
+ * them -- in fp16).  The LayerNorm entry points take
  * x_f16 (their input x) and g_f16 (dres / dx) the same way. */
 int vitatk_k_gemm(int M, int N, int K, const void* A_dev, int lda, const void* B_dev, int ldb, void* out_dev,
                   int ldo, void* out2_dev, int ldo2, const void* T_dev, int ldt, const void* LB_dev, int ldlb,

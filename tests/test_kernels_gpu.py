@@ -199,7 +199,7 @@ def test_gemm_ttiles_compute_the_lora_projection_in_the_same_launch(lib, M, N, K
 
 
 @pytest.mark.parametrize("M,N,K,epi,formats", [
-    (1576, 768, 768, EPI_RESIDUAL, 7),    # proj / fc2 forward: fp16 A? no -- exercised fully: A, out and residual all fp16
+    (1576, 768, 768, EPI_RESIDUAL, 7),    # every switch at once: fp16 A and B, fp16 residual in, fp16 out
     (1576, 768, 3072, EPI_RESIDUAL, 6),   # fc2 forward as the engine runs it: bf16 A, fp16 residual in, fp16 out
     (1576, 2304, 768, EPI_PLAIN, 1),      # qkv forward: fp16 A (the raw residual stream), bf16 out
     (1576, 768, 768, EPI_ROWTABLE, 2),    # patch embed: fp16 out
@@ -207,12 +207,12 @@ def test_gemm_ttiles_compute_the_lora_projection_in_the_same_launch(lib, M, N, K
     (1576, 64, 768, EPI_PLAIN, 1),        # skinny GEMM on an fp16 A (single-CTA kernel)
 ])
 def test_gemm_mixed_fp16_bf16_operands(lib, M, N, K, epi, formats):
-    """The residual streams are IEEE fp16 while weights, T and every other activation stay bf16: tcgen05 kind::f16 takes the
-    A and B formats independently.  Checks every format switch of the GEMM against torch."""
+    """The residual streams are IEEE fp16 (and so are the weights that multiply them: kind::f16 needs A and B in ONE format)
+    while T / LB and every other activation stay bf16.  Checks every format switch of the GEMM against torch."""
     g = torch.Generator(device="cuda").manual_seed(M + N + K + formats)
     rn = lambda *s: torch.randn(*s, device="cuda", generator=g)  # noqa: E731
     A = rn(M, K).to(torch.float16 if formats & 1 else torch.bfloat16)
-    B = (rn(N, K) / math.sqrt(K)).to(torch.bfloat16)
+    B = (rn(N, K) / math.sqrt(K)).to(torch.float16 if formats & 1 else torch.bfloat16)   # same format as A (hardware rule)
     res = None
     if epi in (EPI_RESIDUAL, EPI_MUL):
         res = rn(M, N).to(torch.float16 if (formats & 4 and epi == EPI_RESIDUAL) else torch.bfloat16)

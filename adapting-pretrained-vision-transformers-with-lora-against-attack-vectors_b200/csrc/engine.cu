@@ -138,6 +138,32 @@ struct vitatk_engine {
   bool fuse_tt = true;               // plain LoRA sites: T = x*A^T comes from T-tiles inside the consumer GEMM (VITATK_TT=0: skinny GEMMs)
   unsigned int* tt_flags = nullptr;  // [2 * ceil(max M / 256)] inter-CTA flags of the T-tiles (zero between launches)
   bool fuse_delta = false;           // delta comes out of the proj-backward GEMM epilogue (pair kernel) instead of a kernel
+  // ---- LoRA training (vitatk_train_*) ----
+  struct TrainAdapter {
+    int rank = 0;
+    float scale = 0.f;
+    long long off_a = 0, off_b = 0;  // offsets of A [r, in] and B [out, r] in the flat fp32 parameter / gradient buffers
+    int col0 = 0;                    // first column of this adapter inside its site's 64-column group
+  };
+  struct TrainLayerPlans {
+    GemmPlan fc1_t, fc2_t;                                   // forward with the per-layer GELU output buffer
+    GemmPlan bt_fc2, bt_fc1, bt_proj, bt_qkv;                // BT = dY * B (skinny)
+    GemmPlan bfc2_nl, bfc1_nl, bproj_nl, bqkv_nl;            // frozen-weight input gradients WITHOUT the LoRA k-block
+  };
+  struct TrainState {
+    bool enabled = false;
+    float p_drop = 0.f;
+    float* params = nullptr;
+    float* grads = nullptr;
+    long long n = 0, off_cw = -1, off_cb = -1;
+    std::vector<std::vector<TrainAdapter>> ad;  // [layer][6]: q, k, v, proj, fc1, fc2
+    std::vector<bf16*> g_layer;                 // per-layer GELU output (input of the fc2 adapter, needed for its dA)
+    bf16* Td = nullptr;                         // [M, 64] recomputed dropout(x) A^T for dB
+    float* partial = nullptr;                   // weight-gradient partial sums
+    float *ycls = nullptr, *dlog = nullptr;     // head: classifier input / output cotangent
+    char* buf = nullptr;
+    std::map<int, std::vector<TrainLayerPlans>*> plans;
+  } tr;
   bool prof = false;
   struct ProfRec { int cat; double flops; cudaEvent_t a, b; };
   std::vector<ProfRec> prof_recs;
@@ -599,6 +625,8 @@ int vitatk_destroy(vitatk_engine* e) {
   if (e->ws) cudaFree(e->ws);
   if (e->cbuf) cudaFree(e->cbuf);
   if (e->tt_flags) cudaFree(e->tt_flags);
+  if (e->tr.buf) cudaFree(e->tr.buf);
+  for (auto& kv : e->tr.plans) delete kv.second;
   for (auto& r : e->prof_recs) {  // profiling events (bench.py's roofline leg)
     cudaEventDestroy(r.a);
     cudaEventDestroy(r.b);
@@ -661,6 +689,8 @@ int vitatk_set_tensor(vitatk_engine* e, int id, int layer, const void* p, long l
   // weights changed -> cached TMA plans (and the packed constant columns) are stale
   for (auto& kv : e->plans) delete kv.second;
   e->plans.clear();
+  for (auto& kv : e->tr.plans) delete kv.second;
+  e->tr.plans.clear();
   e->const_dirty = true;
   return 0;
 }
@@ -829,6 +859,28 @@ int vitatk_finalize(vitatk_engine* e) {
   e->logits = reinterpret_cast<float*>(take(al(static_cast<long long>(c.max_batch) * c.num_classes * 4)));
   e->loss = reinterpret_cast<float*>(take(al(c.max_batch * 4)));
   e->scratch_img = reinterpret_cast<float*>(take(sz_img));
+  if (e->tr.enabled) {  // LoRA training: per-layer GELU outputs + scratch for the weight gradients
+    const long long sz_td = al(Mmax * LORA_PAD * 2);
+    const long long sz_part = al(((Mmax + 255) / 256) * F * 16 * 4);
+    const long long sz_y = al(static_cast<long long>(c.max_batch) * D * 4), sz_dl = al(static_cast<long long>(c.max_batch) * c.num_classes * 4);
+    const long long tot = c.layers * sz_f + sz_td + sz_part + sz_y + sz_dl;
+    VITATK_CUDA_OK(cudaMalloc(&e->tr.buf, tot));
+    VITATK_CUDA_OK(cudaMemset(e->tr.buf, 0, tot));
+    char* q = e->tr.buf;
+    e->tr.g_layer.resize(c.layers);
+    for (int l = 0; l < c.layers; ++l) {
+      e->tr.g_layer[l] = reinterpret_cast<bf16*>(q);
+      q += sz_f;
+    }
+    e->tr.Td = reinterpret_cast<bf16*>(q);
+    q += sz_td;
+    e->tr.partial = reinterpret_cast<float*>(q);
+    q += sz_part;
+    e->tr.ycls = reinterpret_cast<float*>(q);
+    q += sz_y;
+    e->tr.dlog = reinterpret_cast<float*>(q);
+    e->ws_bytes += tot;
+  }
   e->const_dirty = true;  // the tensor-core constant columns are packed on first use (refresh_const_columns)
   e->finalized = true;
   return 0;
@@ -1030,6 +1082,349 @@ int vitatk_k_pgd_init(const float* x0, const float* noise, float* adv, void* col
                       const float* std3, float eps, int use_rng, uint64_t seed, uint64_t image_index0, void* stream) {
   return pgd_init(x0, noise, adv, static_cast<bf16*>(cols), batch, make_norm(mean3, std3), eps, use_rng, seed,
                   image_index0, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"
+
+// =================================================================================================
+// LoRA training step: train_loras.py:295-324 on the engine.  Forward and input-gradient backward are the
+// attack path's tcgen05 kernels; train.cu supplies the dropout-aware adapter kernels, weight gradients, Adam and
+// re-packing.  Train mode keeps LayerNorm un-folded (the adapters see dropout(LN(h))) and the bias in the epilogue.
+// =================================================================================================
+namespace vitatk {
+
+static const int AD_SITE[6] = {VITATK_SITE_QKV, VITATK_SITE_QKV, VITATK_SITE_QKV, VITATK_SITE_PROJ, VITATK_SITE_FC1,
+                               VITATK_SITE_FC2};
+
+static int build_train_plans(vitatk_engine* e, int batch, std::vector<vitatk_engine::TrainLayerPlans>** out) {
+  auto it = e->tr.plans.find(batch);
+  if (it != e->tr.plans.end()) {
+    *out = it->second;
+    return 0;
+  }
+  const vitatk_config& c = e->cfg;
+  const int M = batch * TOKENS, D = c.dim, F = c.mlp_dim;
+  std::unique_ptr<std::vector<vitatk_engine::TrainLayerPlans>> owner(new std::vector<vitatk_engine::TrainLayerPlans>(c.layers));
+  GemmEpilogue plain = {};
+  plain.mode = EPI_PLAIN;
+  for (int l = 0; l < c.layers; ++l) {
+    const LayerWeights& w = e->lw[l];
+    vitatk_engine::TrainLayerPlans& p = (*owner)[l];
+    const LoraSite& sq = w.lora[VITATK_SITE_QKV];
+    const LoraSite& sp = w.lora[VITATK_SITE_PROJ];
+    const LoraSite& s1 = w.lora[VITATK_SITE_FC1];
+    const LoraSite& s2 = w.lora[VITATK_SITE_FC2];
+    if (sq.rank > 0 && !sq.packed) {
+      set_error("training needs the q|k|v adapters packed into one group (rq + rk + rv <= 64)");
+      return 1;
+    }
+    bf16* gl = e->tr.g_layer[l];
+    {  // forward fc1 / fc2 through the per-layer GELU buffer (LayerNorm un-folded: A = xn)
+      GemmEpilogue ep = plain;
+      ep.mode = EPI_GELU_DUAL;
+      ep.bias = w.fc1_b;
+      if (gemm_plan_init(&p.fc1_t, M, F, D, e->xn, D, w.fc1_w, D, gl, F, e->u[l], F, e->T, 3 * LORA_PAD, s1.lb_fwd, LORA_PAD,
+                         s1.rank > 0 ? 1 : 0, lora_ksteps(s1.rank), 0, ep))
+        return 1;
+      GemmEpilogue ep2 = {EPI_RESIDUAL, w.fc2_b, e->h_mid[l], D, nullptr, 0};
+      if (gemm_plan_init(&p.fc2_t, M, D, F, gl, F, w.fc2_w, F, e->h[l + 1], D, nullptr, 0, e->T, 3 * LORA_PAD, s2.lb_fwd,
+                         LORA_PAD, s2.rank > 0 ? 1 : 0, lora_ksteps(s2.rank), 0, ep2))
+        return 1;
+      p.fc2_t.out_f16 = p.fc2_t.res_f16 = e->res_f16 ? 1 : 0;
+    }
+    // BT = dY * B (un-scaled B^T rows)
+    if (s2.rank > 0 && gemm_plan_init(&p.bt_fc2, M, LORA_PAD, D, e->dh_a, D, s2.lb_bwd, D, e->T, 3 * LORA_PAD, nullptr, 0, nullptr,
+                                      0, nullptr, 0, 0, 0, 0, plain))
+      return 1;
+    if (s1.rank > 0 && gemm_plan_init(&p.bt_fc1, M, LORA_PAD, F, e->du, F, s1.lb_bwd, F, e->T, 3 * LORA_PAD, nullptr, 0, nullptr,
+                                      0, nullptr, 0, 0, 0, 0, plain))
+      return 1;
+    if (sp.rank > 0 && gemm_plan_init(&p.bt_proj, M, LORA_PAD, D, e->dh_b, D, sp.lb_bwd, D, e->T, 3 * LORA_PAD, nullptr, 0, nullptr,
+                                      0, nullptr, 0, 0, 0, 0, plain))
+      return 1;
+    if (sq.rank > 0 && gemm_plan_init(&p.bt_qkv, M, LORA_PAD, 3 * D, e->dqkv, 3 * D, sq.lb_bwd, 3 * D, e->T, 3 * LORA_PAD, nullptr,
+                                      0, nullptr, 0, nullptr, 0, 0, 0, 0, plain))
+      return 1;
+    p.bt_fc2.a_f16 = p.bt_proj.a_f16 = e->res_f16 ? 1 : 0;
+    // frozen-weight input gradients; the LoRA share is added by lora_dx (its dropout mask does not apply to W's share)
+    {
+      GemmEpilogue ep = plain;
+      if (s2.rank == 0) ep = GemmEpilogue{EPI_MUL, nullptr, e->u[l], F, nullptr, 0};
+      if (gemm_plan_init(&p.bfc2_nl, M, F, D, e->dh_a, D, w.fc2_wt, D, e->du, F, nullptr, 0, nullptr, 0, nullptr, 0, 0, 0, 0, ep))
+        return 1;
+      p.bfc2_nl.a_f16 = e->res_f16 ? 1 : 0;
+    }
+    if (gemm_plan_init(&p.bfc1_nl, M, D, F, e->du, F, w.fc1_wt, F, e->dxn, D, nullptr, 0, nullptr, 0, nullptr, 0, 0, 0, 0, plain))
+      return 1;
+    {
+      GemmEpilogue ep = plain;
+      if (sp.rank == 0 && e->fuse_delta) {
+        ep.mode = EPI_ROWDOT;
+        ep.res = e->ao[l];
+        ep.ld_res = D;
+        ep.rowdot = e->delta;
+        ep.rowdot_rows = TOKENS;
+        ep.rowdot_pad = 208;
+      }
+      if (gemm_plan_init(&p.bproj_nl, M, D, D, e->dh_b, D, w.proj_wt, D, e->dao, D, nullptr, 0, nullptr, 0, nullptr, 0, 0, 0, 0, ep))
+        return 1;
+      p.bproj_nl.a_f16 = e->res_f16 ? 1 : 0;
+    }
+    if (gemm_plan_init(&p.bqkv_nl, M, D, 3 * D, e->dqkv, 3 * D, w.qkv_wt, 3 * D, e->dxn, D, nullptr, 0, nullptr, 0, nullptr, 0, 0, 0,
+                       0, plain))
+      return 1;
+  }
+  e->tr.plans[batch] = owner.get();
+  *out = owner.release();
+  return 0;
+}
+
+}  // namespace vitatk
+
+extern "C" {
+
+int vitatk_train_enable(vitatk_engine* e, float dropout_p) {
+  if (!e || e->finalized || !(dropout_p >= 0.f && dropout_p < 1.f)) {
+    set_error("vitatk_train_enable: call before vitatk_finalize with 0 <= dropout < 1");
+    return 1;
+  }
+  e->tr.enabled = true;
+  e->tr.p_drop = dropout_p;
+  e->tr.ad.assign(e->cfg.layers, std::vector<vitatk_engine::TrainAdapter>(6));
+  e->tc_const = false;  // the adapters change every step: constants stay in the epilogue, no packed copies to refresh
+  e->const_dirty = true;
+  return 0;
+}
+
+int vitatk_train_bind(vitatk_engine* e, float* params_dev, float* grads_dev, long long n, long long off_classifier_w,
+                      long long off_classifier_b) {
+  if (!e || !e->tr.enabled || !params_dev || !grads_dev || n <= 0) {
+    set_error("vitatk_train_bind: engine not in training mode or bad arguments");
+    return 1;
+  }
+  const long long C = e->cfg.num_classes, D = e->cfg.dim;
+  if (off_classifier_w < 0 || off_classifier_w + C * D > n || off_classifier_b < 0 || off_classifier_b + C > n) {
+    set_error("vitatk_train_bind: classifier offsets outside the parameter buffer");
+    return 1;
+  }
+  e->tr.params = params_dev;
+  e->tr.grads = grads_dev;
+  e->tr.n = n;
+  e->tr.off_cw = off_classifier_w;
+  e->tr.off_cb = off_classifier_b;
+  // the head reads the trainable classifier copy (peft modules_to_save, train_loras.py:84) straight from the masters
+  e->head_w = params_dev + off_classifier_w;
+  e->head_b = params_dev + off_classifier_b;
+  return 0;
+}
+
+int vitatk_train_set_adapter(vitatk_engine* e, int layer, int adapter, int rank, float scale, long long off_a, long long off_b) {
+  if (!e || !e->tr.enabled || layer < 0 || layer >= e->cfg.layers || adapter < 0 || adapter > 5 || rank < 0 || rank > 64) {
+    set_error("vitatk_train_set_adapter: bad arguments");
+    return 1;
+  }
+  vitatk_engine::TrainAdapter& a = e->tr.ad[layer][adapter];
+  a.rank = rank;
+  a.scale = scale;
+  a.off_a = off_a;
+  a.off_b = off_b;
+  // column of the adapter inside its site's group: q, k, v are packed one after the other
+  int col = 0;
+  for (int k = 0; k < 3; ++k) {
+    e->tr.ad[layer][k].col0 = col;
+    col += e->tr.ad[layer][k].rank;
+  }
+  for (int k = 3; k < 6; ++k) e->tr.ad[layer][k].col0 = 0;
+  return 0;
+}
+
+// forward (train mode: dropout on the adapters' inputs) + loss + backward + every weight gradient into grads_dev.
+// The gradients are those of the MEAN cross-entropy over this call's batch (train_loras.py:309-311).
+int vitatk_train_step(vitatk_engine* e, const float* images, const int64_t* labels, int batch, uint64_t seed, uint64_t step,
+                      uint64_t image_index0, float* loss_out, float* logits_out, void* stream) {
+  if (check_batch(e, batch)) return 1;
+  if (!e->tr.enabled || !e->tr.params || !images || !labels) {
+    set_error("vitatk_train_step: training mode not set up (vitatk_train_enable / vitatk_train_bind)");
+    return 1;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  PlanSet* ps = nullptr;
+  if (build_plans(e, batch, &ps)) return 1;
+  std::vector<vitatk_engine::TrainLayerPlans>* tp = nullptr;
+  if (build_train_plans(e, batch, &tp)) return 1;
+  const vitatk_config& c = e->cfg;
+  const int M = batch * TOKENS, D = c.dim, F = c.mlp_dim, LDT = 3 * LORA_PAD;
+  const float p = e->tr.p_drop;
+  const long long row0 = static_cast<long long>(image_index0) * TOKENS;
+  const int rf = e->res_f16 ? 1 : 0;
+  auto A_of = [&](int l, int k) { return e->tr.params + e->tr.ad[l][k].off_a; };
+  auto gA = [&](int l, int k) { return e->tr.grads + e->tr.ad[l][k].off_a; };
+  auto gB = [&](int l, int k) { return e->tr.grads + e->tr.ad[l][k].off_b; };
+  auto mseed = [&](int l, int k) { return train_mask_seed(seed, step, l, k); };
+  VITATK_CUDA_OK(cudaMemsetAsync(e->tr.grads, 0, e->tr.n * sizeof(float), s));
+  // ------------------------------------------------ forward ------------------------------------------------
+  RUNC(CAT_PIXEL, 0, pgd_init(images, nullptr, e->scratch_img, e->cols, batch, e->nrm, 0.f, 0, 0, 0, s));
+  RUN_GEMM(CAT_PATCH, &ps->patch);
+  for (int l = 0; l < c.layers; ++l) {
+    const LayerWeights& w = e->lw[l];
+    LayerPlans& pl = ps->layers[l];
+    vitatk_engine::TrainLayerPlans& tl = (*tp)[l];
+    const auto& ad = e->tr.ad[l];
+    if (w.qkv_c1 != nullptr) {
+      set_error("vitatk_train_step: the engine was packed with folded LayerNorms; training needs them un-folded");
+      return 1;
+    }
+    RUNC(CAT_LN_FWD, 0, layernorm_fwd(e->h[l], w.ln1_g, w.ln1_b, e->xn, e->st1[l], M, D, c.ln_eps, s, rf));
+    for (int k = 0; k < 3; ++k)
+      if (ad[k].rank > 0)
+        RUNC(CAT_T_QKV, 0, lora_down(e->xn, D, D, A_of(l, k), ad[k].rank, e->T, LDT, ad[k].col0, M, mseed(l, k), p, row0, s));
+    RUN_GEMM(CAT_QKV, &pl.qkv);
+    RUNC(CAT_ATTN_FWD, 0, attention_fwd_tc05(&ps->attn_fwd[l], s));
+    if (ad[3].rank > 0)
+      RUNC(CAT_T_PROJ, 0, lora_down(e->ao[l], D, D, A_of(l, 3), ad[3].rank, e->T, LDT, 0, M, mseed(l, 3), p, row0, s));
+    RUN_GEMM(CAT_PROJ, &pl.proj);
+    RUNC(CAT_LN_FWD, 0, layernorm_fwd(e->h_mid[l], w.ln2_g, w.ln2_b, e->xn, e->st2[l], M, D, c.ln_eps, s, rf));
+    if (ad[4].rank > 0)
+      RUNC(CAT_T_FC1, 0, lora_down(e->xn, D, D, A_of(l, 4), ad[4].rank, e->T, LDT, 0, M, mseed(l, 4), p, row0, s));
+    RUN_GEMM(CAT_FC1, &tl.fc1_t);
+    if (ad[5].rank > 0)
+      RUNC(CAT_T_FC2, 0, lora_down(e->tr.g_layer[l], F, F, A_of(l, 5), ad[5].rank, e->T, LDT, 0, M, mseed(l, 5), p, row0, s));
+    RUN_GEMM(CAT_FC2, &tl.fc2_t);
+  }
+  RUNC(CAT_HEAD, 0, head_fwd_bwd(e->h[c.layers], e->lnf_g, e->lnf_b, e->head_w, e->head_b, labels, logits_out ? logits_out : e->logits,
+                                 loss_out ? loss_out : e->loss, e->dh_a, batch, TOKENS, D, c.num_classes, c.ln_eps, e->grad_S, s,
+                                 nullptr, rf, rf, e->tr.ycls, e->tr.dlog));
+  const float inv_b = 1.0f / batch;
+  RUNC(CAT_HEAD, 0, head_wgrad(e->tr.ycls, e->tr.dlog, batch, D, c.num_classes, inv_b, e->tr.grads + e->tr.off_cw,
+                               e->tr.grads + e->tr.off_cb, s));
+  // ------------------------------------------------ backward ------------------------------------------------
+  const float gs = inv_b / e->grad_S;  // the gradient stream carries grad_S * d(sum CE)
+  // one adapter's weight gradients: dB = s dY^T drop(x) A^T (recomputed), dA = s (dY B)^T drop(x)
+  auto adapter_wgrad = [&](int l, int k, const bf16* x, int ldx, int in, const bf16* dY, int ldy, int out, int dy_f16) -> int {
+    const auto& a = e->tr.ad[l][k];
+    if (lora_down(x, ldx, in, A_of(l, k), a.rank, e->tr.Td, LORA_PAD, 0, M, mseed(l, k), p, row0, s)) return 1;
+    if (wgrad(dY, ldy, out, e->tr.Td, LORA_PAD, 0, a.rank, M, e->tr.partial, a.scale * gs, 0, gB(l, k), 0u, 0.f, 0, 0, dy_f16, s))
+      return 1;
+    if (wgrad(x, ldx, in, e->T, LDT, a.col0, a.rank, M, e->tr.partial, a.scale * gs, 1, gA(l, k), mseed(l, k), p, row0, in, 0, s))
+      return 1;
+    e->launches += 5;  // lora_down + 2 x (wgrad + reduce)
+    return 0;
+  };
+  for (int l = c.layers - 1; l >= 0; --l) {
+    const LayerWeights& w = e->lw[l];
+    vitatk_engine::TrainLayerPlans& tl = (*tp)[l];
+    const auto& ad = e->tr.ad[l];
+    // ---- fc2: x = gelu(u) (saved per layer), dY = dh_a ----
+    if (ad[5].rank > 0) {
+      RUN_GEMM(CAT_BT_FC2, &tl.bt_fc2);
+      if (adapter_wgrad(l, 5, e->tr.g_layer[l], F, F, e->dh_a, D, D, rf)) return 1;
+    }
+    RUN_GEMM(CAT_BFC2, &tl.bfc2_nl);
+    if (ad[5].rank > 0) {
+      LoraDxArgs a = {};
+      a.n = 1;
+      a.ad[0] = {A_of(l, 5), ad[5].scale, ad[5].rank, 0, mseed(l, 5)};
+      RUNC(CAT_BFC2, 0, lora_dx(e->du, F, F, e->T, LDT, a, e->u[l], F, M, 1, p, row0, s));
+    }
+    // ---- fc1: x = LN2(h_mid) (recomputed), dY = du ----
+    if (ad[4].rank > 0) {
+      RUNC(CAT_LN_FWD, 0, layernorm_fwd(e->h_mid[l], w.ln2_g, w.ln2_b, e->xn, e->st2[l], M, D, c.ln_eps, s, rf));
+      RUN_GEMM(CAT_BT_FC1, &tl.bt_fc1);
+      if (adapter_wgrad(l, 4, e->xn, D, D, e->du, F, F, 0)) return 1;
+    }
+    RUN_GEMM(CAT_BFC1, &tl.bfc1_nl);
+    if (ad[4].rank > 0) {
+      LoraDxArgs a = {};
+      a.n = 1;
+      a.ad[0] = {A_of(l, 4), ad[4].scale, ad[4].rank, 0, mseed(l, 4)};
+      RUNC(CAT_BFC1, 0, lora_dx(e->dxn, D, D, e->T, LDT, a, nullptr, 0, M, 1, p, row0, s));
+    }
+    RUNC(CAT_LN_BWD, 0, layernorm_bwd(e->dxn, e->h_mid[l], e->st2[l], w.ln2_g, e->dh_a, e->dh_b, M, D, s, rf, rf));
+    // ---- proj: x = attention output, dY = dh_b ----
+    if (ad[3].rank > 0) {
+      RUN_GEMM(CAT_BT_PROJ, &tl.bt_proj);
+      if (adapter_wgrad(l, 3, e->ao[l], D, D, e->dh_b, D, D, rf)) return 1;
+    }
+    RUN_GEMM(CAT_BPROJ, &tl.bproj_nl);
+    if (ad[3].rank > 0) {
+      LoraDxArgs a = {};
+      a.n = 1;
+      a.ad[0] = {A_of(l, 3), ad[3].scale, ad[3].rank, 0, mseed(l, 3)};
+      RUNC(CAT_BPROJ, 0, lora_dx(e->dao, D, D, e->T, LDT, a, nullptr, 0, M, 1, p, row0, s));
+    }
+    // delta = rowsum(dO o O) needs the complete dO: the GEMM epilogue only has it when proj carries no adapter
+    RUNC(CAT_ATTN_BWD, 0, attention_bwd_fused(&ps->attn_bwd[l], s, !(ad[3].rank == 0 && e->fuse_delta)));
+    // ---- q, k, v: x = LN1(h) (recomputed), dY = the adapter's 768 columns of dqkv ----
+    const bool any_qkv = ad[0].rank > 0 || ad[1].rank > 0 || ad[2].rank > 0;
+    if (any_qkv) {
+      RUNC(CAT_LN_FWD, 0, layernorm_fwd(e->h[l], w.ln1_g, w.ln1_b, e->xn, e->st1[l], M, D, c.ln_eps, s, rf));
+      RUN_GEMM(CAT_BT_QKV, &tl.bt_qkv);
+      for (int k = 0; k < 3; ++k)
+        if (ad[k].rank > 0 && adapter_wgrad(l, k, e->xn, D, D, e->dqkv + k * D, 3 * D, D, 0)) return 1;
+    }
+    RUN_GEMM(CAT_BQKV, &tl.bqkv_nl);
+    if (any_qkv) {
+      LoraDxArgs a = {};
+      for (int k = 0; k < 3; ++k)
+        if (ad[k].rank > 0) a.ad[a.n++] = {A_of(l, k), ad[k].scale, ad[k].rank, ad[k].col0, mseed(l, k)};
+      RUNC(CAT_BQKV, 0, lora_dx(e->dxn, D, D, e->T, LDT, a, nullptr, 0, M, 1, p, row0, s));
+    }
+    RUNC(CAT_LN_BWD, 0, layernorm_bwd(e->dxn, e->h[l], e->st1[l], w.ln1_g, e->dh_b, e->dh_a, M, D, s, rf, rf));
+  }
+  return 0;
+}
+
+// torch.optim.Adam over the bound parameter buffer (train_loras.py:284) + re-packing of every adapter's 16-bit operands.
+// m_dev / v_dev: caller-owned fp32 moment buffers of the same length (zero-initialised); step counts from 1.
+int vitatk_train_apply(vitatk_engine* e, float* m_dev, float* v_dev, float lr, float beta1, float beta2, float eps, int step,
+                       void* stream) {
+  if (!e || !e->tr.enabled || !e->tr.params || !m_dev || !v_dev || step < 1) {
+    set_error("vitatk_train_apply: bad arguments");
+    return 1;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (adam_step(e->tr.params, e->tr.grads, m_dev, v_dev, e->tr.n, lr, beta1, beta2, eps, step, s)) return 1;
+  ++e->launches;
+  return vitatk_train_repack(e, stream);
+}
+
+unsigned int vitatk_train_mask_seed(uint64_t seed, uint64_t step, int layer, int adapter) {
+  return train_mask_seed(seed, step, layer, adapter);
+}
+
+// masters -> packed operands (also called once after vitatk_train_bind so that the engine computes with the masters)
+int vitatk_train_repack(vitatk_engine* e, void* stream) {
+  if (!e || !e->tr.enabled || !e->tr.params) {
+    set_error("vitatk_train_repack: training mode not set up");
+    return 1;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const vitatk_config& c = e->cfg;
+  const int D = c.dim, F = c.mlp_dim;
+  const int ins[6] = {D, D, D, D, D, F}, outs[6] = {D, D, D, D, F, D};
+  for (int l = 0; l < c.layers; ++l) {
+    for (int k = 0; k < 6; ++k) {
+      const vitatk_engine::TrainAdapter& a = e->tr.ad[l][k];
+      if (a.rank <= 0) continue;
+      const int site = AD_SITE[k];
+      const LoraSite& ls = e->lw[l].lora[site];
+      if (!ls.la_fwd) {
+        set_error("vitatk_train_repack: layer %d adapter %d has no packed operand buffers (vitatk_set_lora first)", l, k);
+        return 1;
+      }
+      const bool qkv = site == VITATK_SITE_QKV;
+      const int out0 = qkv ? k * D : 0;              // row offset of the group in lb_fwd / column offset in lb_bwd
+      const int ld_lbb = qkv ? 3 * D : outs[k];      // lb_bwd [64, out_total]
+      // operands that meet an fp16 residual stream: lb_bwd of proj / fc2 (la_fwd never does in train mode: LN un-folded)
+      const int fmt = (e->res_f16 && (site == VITATK_SITE_PROJ || site == VITATK_SITE_FC2)) ? 2 : 0;
+      if (lora_repack(e->tr.params + a.off_a, e->tr.params + a.off_b, a.rank, ins[k], outs[k], a.scale,
+                      const_cast<bf16*>(ls.la_fwd), const_cast<bf16*>(ls.lb_fwd), const_cast<bf16*>(ls.lb_bwd),
+                      const_cast<bf16*>(ls.la_bwd), a.col0, a.col0, out0, ld_lbb, LORA_PAD, nullptr, fmt, s))
+        return 1;
+      ++e->launches;
+    }
+  }
+  return 0;
 }
 
 }  // extern "C"

@@ -15,6 +15,7 @@
 //   adam_kernel        torch.optim.Adam semantics (bias correction, eps outside the sqrt) over the flat parameter buffer
 //   lora_repack_kernel fp32 masters -> the bf16 operand layouts of vitatk_set_lora (s*B, B^T, s*A^T, A)
 // Dropout masks are counter-based: keep(seed, m * K + k) from a 32-bit integer hash, identical in oracle/train_oracle.py.
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 #include "vitatk_internal.h"
@@ -124,17 +125,6 @@ int lora_down(const bf16* x, int ldx, int K, const float* A, int r, bf16* T, int
 // Up to three adapters share the input (q, k, v read the same LayerNorm output, each with its own mask).  One thread per
 // 8 consecutive columns of one row; the row's BT values are fetched once per thread (<= 3 * 16 floats).
 // ------------------------------------------------------------------------------------------------
-struct LoraDxAdapter {
-  const float* A;   // fp32 master [r, K]
-  float scale;      // alpha / r
-  int r, c0;
-  uint32_t seed;
-};
-struct LoraDxArgs {
-  LoraDxAdapter ad[3];
-  int n;
-};
-
 __global__ void __launch_bounds__(256) lora_dx_kernel(bf16* __restrict__ dX, int ldx, int K, const bf16* __restrict__ BT, int ldt,
                                                       LoraDxArgs args, const bf16* __restrict__ mul, int ldm, int rows,
                                                       int accumulate, uint32_t thresh, float inv_keep, long long row0) {
@@ -229,7 +219,7 @@ template <int R>
 __global__ void __launch_bounds__(WG_COLS) wgrad_kernel(const bf16* __restrict__ X, int ldx, int N, const bf16* __restrict__ S,
                                                         int lds, int c0, int r, int rows, float* __restrict__ P,
                                                         uint32_t seed, uint32_t thresh, float inv_keep, long long row0,
-                                                        int mask_ld) {
+                                                        int mask_ld, int x_f16) {
   __shared__ float s_sh[WG_ROWS][R];
   const int n = blockIdx.x * WG_COLS + threadIdx.x;
   const int m_begin = blockIdx.y * WG_ROWS;
@@ -246,7 +236,7 @@ __global__ void __launch_bounds__(WG_COLS) wgrad_kernel(const bf16* __restrict__
   if (n < N) {
     const bf16* xp = X + static_cast<size_t>(m_begin) * ldx + n;
     for (int m = m_begin; m < m_end; ++m, xp += ldx) {
-      float xv = __bfloat162float(*xp);
+      float xv = x_f16 ? __half2float(*reinterpret_cast<const __half*>(xp)) : __bfloat162float(*xp);
       if (thresh != 0u) {
         const uint32_t idx = static_cast<uint32_t>((row0 + m) * static_cast<long long>(mask_ld)) + n;
         xv = drop_keep(seed, idx, thresh) ? xv * inv_keep : 0.f;
@@ -262,18 +252,18 @@ __global__ void __launch_bounds__(WG_COLS) wgrad_kernel(const bf16* __restrict__
 }
 
 // G[n * r + j] (or G[j * N + n] when transpose) = scale * sum_chunks P[chunk][n][j]
-__global__ void wgrad_reduce_kernel(const float* __restrict__ P, int chunks, int N, int r, float scale, int transpose,
-                                    float* __restrict__ G) {
+__global__ void wgrad_reduce_kernel(const float* __restrict__ P, int chunks, int N, int rr, int r_total, int j0, float scale,
+                                    int transpose, float* __restrict__ G) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N * r) return;
-  const int n = i / r, j = i % r;
+  if (i >= N * rr) return;
+  const int n = i / rr, j = i % rr;
   float acc = 0.f;
   for (int c = 0; c < chunks; ++c) acc += P[(static_cast<size_t>(c) * N + n) * 16 + j];
-  G[transpose ? static_cast<size_t>(j) * N + n : static_cast<size_t>(n) * r + j] = acc * scale;
+  G[transpose ? static_cast<size_t>(j0 + j) * N + n : static_cast<size_t>(n) * r_total + j0 + j] = acc * scale;
 }
 
 int wgrad(const bf16* X, int ldx, int N, const bf16* S, int lds, int c0, int r, int rows, float* partial, float scale,
-          int transpose, float* G, uint32_t seed, float p, long long row0, int mask_ld, cudaStream_t stream) {
+          int transpose, float* G, uint32_t seed, float p, long long row0, int mask_ld, int x_f16, cudaStream_t stream) {
   if (r < 1 || r > 64) {
     set_error("wgrad: unsupported rank %d", r);
     return 1;
@@ -285,25 +275,11 @@ int wgrad(const bf16* X, int ldx, int N, const bf16* S, int lds, int c0, int r, 
   for (int j0 = 0; j0 < r; j0 += 16) {  // ranks above 16: 16 columns of S per pass
     const int rr = r - j0 < 16 ? r - j0 : 16;
     if (rr <= 8)
-      wgrad_kernel<8><<<grid, WG_COLS, 0, stream>>>(X, ldx, N, S, lds, c0 + j0, rr, rows, partial, seed, th, inv, row0, mask_ld);
+      wgrad_kernel<8><<<grid, WG_COLS, 0, stream>>>(X, ldx, N, S, lds, c0 + j0, rr, rows, partial, seed, th, inv, row0, mask_ld, x_f16);
     else
-      wgrad_kernel<16><<<grid, WG_COLS, 0, stream>>>(X, ldx, N, S, lds, c0 + j0, rr, rows, partial, seed, th, inv, row0, mask_ld);
-    // the reduce of pass j0 writes columns [j0, j0 + rr) of the rank dimension: G is [N, r] or [r, N]
-    float* g0 = transpose ? G + static_cast<size_t>(j0) * N : G + j0;
-    if (r <= 16) {
-      wgrad_reduce_kernel<<<(N * rr + 255) / 256, 256, 0, stream>>>(partial, chunks, N, rr, scale, transpose, g0);
-    } else {
-      // strided destination for the non-transposed layout: reduce into a temporary-free form one rank column at a time
-      for (int j = 0; j < rr; ++j) {
-        // (rank > 16 is rare -- stacked adapters are not trained -- so the simple per-column launch is kept)
-        wgrad_reduce_kernel<<<(N + 255) / 256, 256, 0, stream>>>(partial + j, chunks, N, 1, scale, 1,
-                                                                 transpose ? G + static_cast<size_t>(j0 + j) * N : nullptr);
-        if (!transpose) {
-          set_error("wgrad: rank > 16 needs the transposed output layout");
-          return 1;
-        }
-      }
-    }
+      wgrad_kernel<16><<<grid, WG_COLS, 0, stream>>>(X, ldx, N, S, lds, c0 + j0, rr, rows, partial, seed, th, inv, row0, mask_ld, x_f16);
+    // the reduce of pass j0 fills rank columns [j0, j0 + rr) of G ([N, r] row-major, or [r, N] when transposed)
+    wgrad_reduce_kernel<<<(N * rr + 255) / 256, 256, 0, stream>>>(partial, chunks, N, rr, r, j0, scale, transpose, G);
   }
   VITATK_CUDA_OK(cudaGetLastError());
   return 0;
@@ -371,27 +347,31 @@ int adam_step(float* p, const float* g, float* m, float* v, long long n, float l
 __global__ void lora_repack_kernel(const float* __restrict__ A, const float* __restrict__ B, int r, int in, int out, float s,
                                    bf16* __restrict__ la_fwd, bf16* __restrict__ lb_fwd, bf16* __restrict__ lb_bwd,
                                    bf16* __restrict__ la_bwd, int row0, int col0, int out0, int ld_lbb, int ld_lab,
-                                   const float* __restrict__ gamma) {
+                                   const float* __restrict__ gamma, int fmt) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < r * in) {
     const int j = i / in, k = i % in;
     const float a = A[i];
-    la_fwd[static_cast<size_t>(row0 + j) * in + k] = __float2bfloat16(gamma ? a * gamma[k] : a);
+    const float af = gamma ? a * gamma[k] : a;
+    if (fmt & 1) reinterpret_cast<__half*>(la_fwd)[static_cast<size_t>(row0 + j) * in + k] = __float2half_rn(af);
+    else la_fwd[static_cast<size_t>(row0 + j) * in + k] = __float2bfloat16(af);
     la_bwd[static_cast<size_t>(k) * ld_lab + row0 + j] = __float2bfloat16(s * a);
   }
   if (i < out * r) {
     const int n = i / r, j = i % r;
     const float b = B[i];
     lb_fwd[static_cast<size_t>(out0 + n) * 64 + col0 + j] = __float2bfloat16(s * b);
-    lb_bwd[static_cast<size_t>(row0 + j) * ld_lbb + out0 + n] = __float2bfloat16(b);
+    if (fmt & 2) reinterpret_cast<__half*>(lb_bwd)[static_cast<size_t>(row0 + j) * ld_lbb + out0 + n] = __float2half_rn(b);
+    else lb_bwd[static_cast<size_t>(row0 + j) * ld_lbb + out0 + n] = __float2bfloat16(b);
   }
 }
 
 int lora_repack(const float* A, const float* B, int r, int in, int out, float s, bf16* la_fwd, bf16* lb_fwd, bf16* lb_bwd,
-                bf16* la_bwd, int row0, int col0, int out0, int ld_lbb, int ld_lab, const float* gamma, cudaStream_t stream) {
+                bf16* la_bwd, int row0, int col0, int out0, int ld_lbb, int ld_lab, const float* gamma, int fmt,
+                cudaStream_t stream) {
   const int n = r * (in > out ? in : out);
   lora_repack_kernel<<<(n + 255) / 256, 256, 0, stream>>>(A, B, r, in, out, s, la_fwd, lb_fwd, lb_bwd, la_bwd, row0, col0, out0,
-                                                          ld_lbb, ld_lab, gamma);
+                                                          ld_lbb, ld_lab, gamma, fmt);
   VITATK_CUDA_OK(cudaGetLastError());
   return 0;
 }

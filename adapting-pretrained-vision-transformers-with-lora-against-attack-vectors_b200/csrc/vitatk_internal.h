@@ -253,4 +253,39 @@ int png_roundtrip(const float* images, float* out, uint8_t* u8_hwc, int batch, c
 int count_correct(const float* logits, const int64_t* labels, int batch, int classes, long long* counts,
                   cudaStream_t stream);
 
+
+// ---------------------------------------------------------------------------------------------
+// LoRA training step (train.cu): dropout-aware adapter kernels, weight gradients, Adam, operand re-packing
+// ---------------------------------------------------------------------------------------------
+struct LoraDxAdapter {
+  const float* A;   // fp32 master [r, K]
+  float scale;      // alpha / r
+  int r, c0;        // rank, first column of this adapter's dY*B inside BT
+  uint32_t seed;    // dropout mask key
+};
+struct LoraDxArgs {
+  LoraDxAdapter ad[3];
+  int n;
+};
+// T[m, c0 + j] = sum_k drop(x[m, k]) * A[j, k]  (mask keyed by seed over element index (row0 + m) * K + k; p = 0: no mask)
+int lora_down(const bf16* x, int ldx, int K, const float* A, int r, bf16* T, int ldt, int c0, int rows, uint32_t seed,
+              float p, long long row0, cudaStream_t stream);
+// dX (+)= sum_a drop'_a o (BT_a * s_a A_a), then * mul (optional)
+int lora_dx(bf16* dX, int ldx, int K, const bf16* BT, int ldt, const LoraDxArgs& args, const bf16* mul, int ldm, int rows,
+            int accumulate, float p, long long row0, cudaStream_t stream);
+// G = scale * X^T S over the token rows (G [N, r], or [r, N] with transpose); X optionally masked (p > 0) with element
+// index (row0 + m) * mask_ld + n; x_f16: X holds IEEE fp16.  partial: fp16-free fp32 scratch [ceil(rows / 256), N, 16].
+int wgrad(const bf16* X, int ldx, int N, const bf16* S, int lds, int c0, int r, int rows, float* partial, float scale,
+          int transpose, float* G, uint32_t seed, float p, long long row0, int mask_ld, int x_f16, cudaStream_t stream);
+int head_wgrad(const float* y, const float* dlogits, int batch, int dim, int classes, float scale, float* dW, float* db,
+               cudaStream_t stream);
+int adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, int step,
+              cudaStream_t stream);
+// fp32 masters of one adapter -> its slots in the site's packed 16-bit operand buffers (vitatk_set_lora layouts);
+// fmt bit 0: la_fwd is fp16, bit 1: lb_bwd is fp16 (operands that meet an fp16 residual stream), else bf16
+int lora_repack(const float* A, const float* B, int r, int in, int out, float s, bf16* la_fwd, bf16* lb_fwd, bf16* lb_bwd,
+                bf16* la_bwd, int row0, int col0, int out0, int ld_lbb, int ld_lab, const float* gamma, int fmt,
+                cudaStream_t stream);
+uint32_t train_mask_seed(uint64_t seed, uint64_t step, int layer, int adapter);
+
 }  // namespace vitatk

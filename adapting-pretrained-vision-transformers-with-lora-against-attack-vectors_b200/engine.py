@@ -160,13 +160,17 @@ class Engine:
                  adapters: Optional[Dict[str, Sequence[Adapter]]] = None, max_batch: int = 256,
                  mean: Sequence[float] = IMAGENET_MEAN, std: Sequence[float] = IMAGENET_STD,
                  device: Optional[torch.device] = None, ln_eps: Optional[float] = None,
-                 merge_lora: Optional[bool] = None):
+                 merge_lora: Optional[bool] = None, train_dropout: Optional[float] = None):
         if not torch.cuda.is_available():
             raise _lib.VitatkError("vitatk needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
         # LayerNorm folded into the qkv / fc1 GEMMs: LN(h) W^T = rstd (h (gamma o W)^T - mean c1) + c2
         import os as _os
         self.ln_fold = _os.environ.get("VITATK_LN_FOLD", "1") != "0"
+        # training mode (vitatk.training.LoraTrainer): the adapters see dropout(LayerNorm(h)), so LayerNorm stays un-folded
+        self.train_dropout = None if train_dropout is None else float(train_dropout)
+        if self.train_dropout is not None:
+            self.ln_fold = False
         # Residual streams are IEEE fp16 on the device (csrc/engine.cu res_f16); the tensor cores need both operands of an
         # MMA in one 16-bit format, so every weight that multiplies a stream is packed as fp16 as well (same bytes)
         self.res_f16 = _os.environ.get("VITATK_RES_F16", "1") != "0"
@@ -211,6 +215,8 @@ class Engine:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.vitatk_create(C.byref(cfg), C.byref(self._h)), "vitatk_create")
             self.res_f16 = bool(self.lib.vitatk_stream_format(self._h))  # the device side is authoritative
+            if self.train_dropout is not None:
+                _lib.check(self.lib.vitatk_train_enable(self._h, self.train_dropout), "vitatk_train_enable")
             self._upload(sd)
             _lib.check(self.lib.vitatk_finalize(self._h), "vitatk_finalize")
 

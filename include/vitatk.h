@@ -168,6 +168,34 @@ long long vitatk_launch_count(const vitatk_engine* e);
 int vitatk_profile_begin(vitatk_engine* e);
 int vitatk_profile_end(vitatk_engine* e, double* ms_by_cat, double* flops_by_cat, long long* launches_by_cat);
 
+/* ---- LoRA training step (replaces the batch body of train_loras.py:295-324) ----
+ * peft semantics of train_loras.py:79-95 in train mode: y = W x + b + (alpha / r) B (A dropout_p(x)); trainable = every
+ * adapter's A [r, in] and B [out, r] plus the classifier copy (modules_to_save).  All trainable parameters live in ONE
+ * caller-owned fp32 device buffer (masters) with a gradient buffer of the same layout; the engine computes with 16-bit
+ * operands re-packed from the masters after every update.  Adapter ids: 0 query, 1 key, 2 value, 3 attention output,
+ * 4 intermediate (fc1), 5 output (fc2).  Dropout masks are counter-based (seed, step, layer, adapter, element index), so
+ * a step is reproducible and independent of how images are sharded over GPUs (image_index0 = global index of image 0).
+ *   vitatk_train_enable        before vitatk_finalize: switches the engine to training mode (per-layer GELU buffers,
+ *                              bias / LayerNorm un-folded) with dropout probability p on the adapters' inputs
+ *   vitatk_train_bind          masters + gradient buffer (n floats) and the classifier's offsets in them
+ *   vitatk_train_set_adapter   where adapter (layer, id) lives in the buffers: A at off_a ([r, in]), B at off_b ([out, r])
+ *   vitatk_train_repack        masters -> packed operands (call once after binding; vitatk_train_apply does it itself)
+ *   vitatk_train_step          forward + mean cross-entropy + backward: every weight gradient written to the gradient
+ *                              buffer (an all-reduce over data-parallel ranks goes between step and apply)
+ *   vitatk_train_apply         torch.optim.Adam update of the masters (train_loras.py:284) + re-pack */
+int vitatk_train_enable(vitatk_engine* e, float dropout_p);
+/* key of the dropout mask of adapter (layer, id) at a step; element (row, k) of the adapter's [rows, in] input is kept iff
+ * lowbias32((row * in + k) ^ key) >= p * 2^32 (host function, no GPU needed: lets a test pin the oracle's restatement) */
+unsigned int vitatk_train_mask_seed(uint64_t seed, uint64_t step, int layer, int adapter);
+int vitatk_train_bind(vitatk_engine* e, float* params_dev, float* grads_dev, long long n, long long off_classifier_w,
+                      long long off_classifier_b);
+int vitatk_train_set_adapter(vitatk_engine* e, int layer, int adapter, int rank, float scale, long long off_a, long long off_b);
+int vitatk_train_repack(vitatk_engine* e, void* stream);
+int vitatk_train_step(vitatk_engine* e, const float* images_dev, const int64_t* labels_dev, int batch, uint64_t seed,
+                      uint64_t step, uint64_t image_index0, float* loss_dev, float* logits_dev, void* stream);
+int vitatk_train_apply(vitatk_engine* e, float* m_dev, float* v_dev, float lr, float beta1, float beta2, float eps, int step,
+                       void* stream);
+
 /* ---- kernel-level entry points (used by tests/ and bench.py's roofline leg) ----
  * vitatk_k_gemm with tt_n in {32, 64}: "T-tile" mode of the pair kernel -- the GEMM computes T = A * tt_tb^T (tt_tb bf16
  * [64, K], + tt_bias[64] if given) itself, writes it to T_dev and uses it as its LoRA k-block in the same launch;

@@ -494,3 +494,56 @@ def test_wrapper_peeling_and_attack_object_defaults():
     if not torch.cuda.is_available():
         with pytest.raises(Exception):
             atk(torch.rand(1, 3, 224, 224), torch.zeros(1, dtype=torch.long))      # no CPU fallback: must raise
+
+
+def test_training_dropout_mask_arithmetic_matches_the_library(lib):
+    """The oracle's restatement of the counter-based dropout mask (oracle/train_oracle.py) against the library's own host
+    arithmetic (vitatk_train_mask_seed) and known answers of the 32-bit hash; the keep rate is 1 - p."""
+    from oracle import train_oracle as to
+
+    for seed, step, layer, adapter in ((0, 0, 0, 0), (1234, 7, 11, 5), (2 ** 40 + 3, 100000, 3, 2)):
+        assert to.mask_seed(seed, step, layer, adapter) == lib.vitatk_train_mask_seed(seed, step, layer, adapter)
+    # lowbias32 known answers (computed with the C expression in csrc/train.cu)
+    def c_hash(h):
+        m = 0xFFFFFFFF
+        h ^= h >> 16; h = (h * 0x7feb352d) & m; h ^= h >> 15; h = (h * 0x846ca68b) & m; h ^= h >> 16
+        return h
+    xs = torch.tensor([0, 1, 2, 0xFFFFFFFF, 123456789, 50432 * 3072 - 1], dtype=torch.int64)
+    assert to.lowbias32(xs).tolist() == [c_hash(int(v)) for v in xs]
+    keep = to.keep_mask(to.mask_seed(1, 2, 3, 4), 4096, 768, 0.1)
+    assert abs(float(keep.float().mean()) - 0.9) < 2e-3
+    assert bool(to.keep_mask(5, 8, 16, 0.0).all())
+    # row0 shifts the counter: rows [100, 108) of a long batch == the same rows generated alone (sharding invariance)
+    full = to.keep_mask(77, 200, 768, 0.1)
+    assert torch.equal(full[100:108], to.keep_mask(77, 8, 768, 0.1, row0=100))
+
+
+def test_gradient_averaging_world2_gloo():
+    """Data-parallel LoRA training exchanges ONE tensor per step: the flat gradient buffer (mean over ranks)."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    assert res[0][1] == res[1][1] == [2.0, 3.0, 4.0]  # mean of [1,2,3] and [3,4,5]
+
+
+def _grad_worker(rank, world, port, q):
+    import sys
+
+    import torch.distributed as dist
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from vitatk.training import average_gradients
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    g = torch.tensor([1.0, 2.0, 3.0]) + 2.0 * rank
+    average_gradients(g)
+    q.put((rank, g.tolist()))
+    dist.destroy_process_group()

@@ -570,6 +570,114 @@ def run_config1(args):
     return 0
 
 
+# ---------------------------------------------------------------------------------------------------------
+# config 5: LoRA fine-tune step + PGD-7 adversarial training, batch 96 per GPU (BASELINE configs[4])
+# ---------------------------------------------------------------------------------------------------------
+def run_config5(args):
+    """One step = PGD-7 (eps 8/255, alpha 2/255, random start) against the current adapters on 96 images per GPU, then one
+    LoRA training step on the adversarial batch (train-mode forward with dropout 0.1, mean CE, backward, dA / dB /
+    classifier gradients, ONE all-reduce of the flat gradient buffer over NCCL, Adam lr 1e-4, operand re-pack).
+    Adapters as in train_loras.py:79-95: r = 16, alpha = 16, targets query / key / value / output.dense."""
+    out = StdoutToStderr()
+    import torch
+    import torch.distributed as dist
+
+    import vitatk
+    from vitatk import synthetic
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, K = 96, 7
+    idx0 = rank * B
+    model = synthetic.random_vit(CLASSES, seed=0)
+    trainer = vitatk.LoraTrainer(model=model, rank=16, alpha=16.0, dropout=0.1, lr=1e-4, max_batch=B, device=dev, seed=0)
+    x_host, y_host = synthetic.images_and_labels(B, idx0, CLASSES, seed=0, pin=True)
+    x, y = x_host.to(dev), y_host.to(dev)
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    losses = []
+    for _ in range(max(args.warmup, 3)):
+        losses.append(float(trainer.adversarial_step(x, y, EPS, ALPHA, K, image_index0=idx0)))
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = trainer.engine.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for _ in range(args.steps):
+        last = trainer.adversarial_step(x, y, EPS, ALPHA, K, image_index0=idx0)
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    launches = trainer.engine.launch_count - l0
+    clocks = sampler.stop() if rank == 0 else None
+    # end to end: the batch comes from pinned host memory every step, the loss goes back to the host
+    loss_host = torch.empty(1).pin_memory()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    f0.record()
+    for _ in range(args.steps):
+        x.copy_(x_host, non_blocking=True)
+        y.copy_(y_host, non_blocking=True)
+        loss_host.copy_(trainer.adversarial_step(x, y, EPS, ALPHA, K, image_index0=idx0).reshape(1), non_blocking=True)
+    f1.record()
+    sync_all()
+    ms_e2e = f0.elapsed_time(f1)
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+    peaks, peaks_kind = measured_peaks()
+    # algorithmic FLOPs per image: 7 attack steps (fwd + input-grad bwd, LoRA r=16 on 5 targets) + 1 training step (same
+    # frozen-weight fwd + bwd; the rank-16 weight gradients are < 1 % on top)
+    gflop_img = algorithmic_gflop_per_image_step(r=16) * (K + 1)
+    imgs = B * world * args.steps
+    value = imgs / (ms / 1e3)
+    peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
+    line = {
+        "metric": "adversarially trained images/sec (PGD-7 + LoRA r=16 train step), ViT-B/16 bs96 per GPU (BASELINE configs[4])",
+        "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": "PGD-7 eps=8/255 alpha=2/255 + one LoRA(r=16; q,k,v,attention.output.dense,output.dense; dropout 0.1) "
+                               "Adam step, ViT-B/16, 21 classes, batch 96 per GPU (BASELINE configs[4])",
+                   "global_batch": B * world, "parallelism": f"dp{world} (one gradient all-reduce of "
+                                                             f"{trainer.params.numel() * 4 / 1e6:.1f} MB per step)",
+                   "l2": "activations (~4 GB per step) exceed L2"},
+        "clocks": clocks,
+        "e2e": {"value": imgs / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8,
+                "d2h_bytes_per_step": 4},
+        "gpu_launches": launches,
+        "roofline": {"bound": "tensor", "achieved": value / world * gflop_img / 1e3, "peak": peak, "unit": "TFLOP/s",
+                     "frac": value / world * gflop_img / 1e3 / peak, "traffic": None,
+                     "note": "whole-step algorithmic FLOPs / time (no per-kernel split for this config)",
+                     "peak_kind": f"{peaks_kind} sustained cuBLAS bf16"},
+        "train": {"trainable_params": int(trainer.params.numel()), "loss_first_warmup": losses[0], "loss_last": float(last)},
+    }
+    out.emit(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -578,8 +686,9 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH, help="images per GPU (BASELINE: 256)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--config", type=int, default=2, choices=[1, 2],
-                    help="BASELINE.json configs, 1-based: 1 = FGSM batch 8 (CUDA graph), 2 = PGD-10 batch 256 (the metric; default)")
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 5],
+                    help="BASELINE.json configs, 1-based: 1 = FGSM batch 8 (CUDA graph), 2 = PGD-10 batch 256 (the metric; default), "
+                         "5 = PGD-7 adversarial LoRA training, batch 96 per GPU")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "engine":
         args.warmup = 3  # timing rules: W >= 3
@@ -599,7 +708,7 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
         return subprocess.call(cmd)
-    return run_engine(args)
+    return run_config5(args) if args.config == 5 else run_engine(args)
 
 
 if __name__ == "__main__":

@@ -14,7 +14,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libvitatk.so")
 INCLUDE_DIR = os.path.join(os.path.dirname(PKG_DIR), "include")
-SOURCES = ["gemm_tc05.cu", "attention_tc05.cu", "attention_bwd_fused.cu", "elementwise.cu", "train.cu", "engine.cu"]
+SOURCES = ["gemm_tc05.cu", "attention_tc05.cu", "attention_bwd_fused.cu", "elementwise.cu", "train.cu", "patch.cu", "engine.cu"]
 HEADERS = ["ptx.cuh", "vitatk_internal.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -82,7 +82,7 @@ EXPORTS = [
     "vitatk_k_attention_bwd_fused", "vitatk_k_gemm_trace", "vitatk_k_attention_bwd_trace",
     "vitatk_k_attention_fwd_trace", "vitatk_k_layernorm_stats",
     "vitatk_train_enable", "vitatk_train_bind", "vitatk_train_set_adapter", "vitatk_train_repack", "vitatk_train_step",
-    "vitatk_train_apply", "vitatk_train_mask_seed",
+    "vitatk_train_apply", "vitatk_train_mask_seed", "vitatk_patch_grad", "vitatk_patch_apply", "vitatk_patch_update",
 ]
 
 
@@ -146,6 +146,9 @@ def load() -> C.CDLL:
     lib.vitatk_train_repack.argtypes = [vp, vp]
     lib.vitatk_train_step.argtypes = [vp, vp, vp, i, u64, u64, u64, vp, vp, vp]
     lib.vitatk_train_apply.argtypes = [vp, vp, vp, f, f, f, f, i, vp]
+    lib.vitatk_patch_grad.argtypes = [vp, vp, vp, i, i, vp, vp, vp, i, i, vp, vp, vp, vp]
+    lib.vitatk_patch_apply.argtypes = [vp, i, i, vp, vp, i, i, vp, vp]
+    lib.vitatk_patch_update.argtypes = [vp, vp, vp, vp, i, f, i, i, f, f, f, vp]
     lib.vitatk_train_mask_seed.argtypes = [u64, u64, i, i]
     lib.vitatk_train_mask_seed.restype = C.c_uint
     for name in EXPORTS:

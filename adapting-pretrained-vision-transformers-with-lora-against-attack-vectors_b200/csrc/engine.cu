@@ -112,6 +112,7 @@ struct vitatk_engine {
   bf16 *cols = nullptr, *xn = nullptr, *g = nullptr, *T = nullptr;
   bf16 *dh_a = nullptr, *dh_b = nullptr, *du = nullptr, *dxn = nullptr, *dao = nullptr, *dqkv = nullptr;
   float *logits = nullptr, *loss = nullptr, *scratch_img = nullptr;
+  int64_t* labels_rep = nullptr;  // [max_batch] per-sample labels of the EOT front end
   std::map<int, PlanSet*> plans;
   long long launches = 0;
   PixelNorm nrm;
@@ -625,6 +626,7 @@ int vitatk_destroy(vitatk_engine* e) {
   if (e->ws) cudaFree(e->ws);
   if (e->cbuf) cudaFree(e->cbuf);
   if (e->tt_flags) cudaFree(e->tt_flags);
+  if (e->labels_rep) cudaFree(e->labels_rep);
   if (e->tr.buf) cudaFree(e->tr.buf);
   for (auto& kv : e->tr.plans) delete kv.second;
   for (auto& r : e->prof_recs) {  // profiling events (bench.py's roofline leg)
@@ -815,6 +817,7 @@ int vitatk_finalize(vitatk_engine* e) {
   total += al(static_cast<long long>(c.max_batch) * c.num_classes * 4) + al(c.max_batch * 4) + sz_img;
   VITATK_CUDA_OK(cudaMalloc(&e->ws, total));
   VITATK_CUDA_OK(cudaMemset(e->ws, 0, total));
+  VITATK_CUDA_OK(cudaMalloc(&e->labels_rep, static_cast<size_t>(c.max_batch) * sizeof(int64_t)));
   {
     const long long nflags = 2 * ((Mmax + 255) / 256);
     VITATK_CUDA_OK(cudaMalloc(&e->tt_flags, nflags * sizeof(unsigned int)));
@@ -1425,6 +1428,60 @@ int vitatk_train_repack(vitatk_engine* e, void* stream) {
     }
   }
   return 0;
+}
+
+}  // extern "C"
+
+// =================================================================================================
+// Adversarial patch / EOT front end
+// =================================================================================================
+extern "C" {
+
+int vitatk_patch_grad(vitatk_engine* e, const float* images, const int64_t* labels, int batch, int T, const float* tf_dev,
+                      const float* fw_dev, const float* patch_dev, int p, int circle, float* grad_dev, float* loss_dev,
+                      float* logits_dev, void* stream) {
+  const int samples = batch * T;
+  if (check_batch(e, samples)) return 1;
+  if (!images || !labels || !tf_dev || !fw_dev || !patch_dev || !grad_dev || T < 1 || p < 1 || p > 224) {
+    set_error("vitatk_patch_grad: bad arguments (batch * T <= max_batch, 1 <= p <= 224)");
+    return 1;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  PlanSet* ps = nullptr;
+  if (build_plans(e, samples, &ps)) return 1;
+  const vitatk_config& c = e->cfg;
+  RUNC(CAT_PIXEL, 0, patch_apply(images, patch_dev, p, tf_dev, T, samples, circle, e->nrm, e->cols, nullptr, s));
+  if (encoder_forward(e, ps, samples, s)) return 1;
+  RUNC(CAT_HEAD, 0, repeat_labels(labels, T, samples, e->labels_rep, s));
+  RUNC(CAT_HEAD, 0, head_fwd_bwd(e->h[c.layers], e->lnf_g, e->lnf_b, e->head_w, e->head_b, e->labels_rep,
+                                 logits_dev ? logits_dev : e->logits, loss_dev ? loss_dev : e->loss, e->dh_a, samples, TOKENS, c.dim,
+                                 c.num_classes, c.ln_eps, e->grad_S, s, nullptr, e->res_f16, e->res_f16));
+  if (encoder_backward(e, ps, samples, s)) return 1;
+  // gradient of the MEAN cross-entropy over this call's samples (the caller rescales when it splits a step into chunks)
+  RUNC(CAT_PIXEL, 0, patch_grad(e->dxn, tf_dev, fw_dev, p, samples, circle, e->nrm, 1.0f / (samples * e->grad_S), e->scratch_img,
+                                grad_dev, s));
+  ++e->launches;
+  return 0;
+}
+
+int vitatk_patch_apply(const float* images, int batch, int T, const float* tf_dev, const float* patch_dev, int p, int circle,
+                       float* out_dev, void* stream) {
+  if (!images || !tf_dev || !patch_dev || !out_dev || batch < 1 || T < 1 || p < 1 || p > 224) {
+    set_error("vitatk_patch_apply: bad arguments");
+    return 1;
+  }
+  PixelNorm n = {{0.f, 0.f, 0.f}, {1.f, 1.f, 1.f}};
+  return patch_apply(images, patch_dev, p, tf_dev, T, batch * T, circle, n, nullptr, out_dev, static_cast<cudaStream_t>(stream));
+}
+
+int vitatk_patch_update(float* patch_dev, const float* grad_dev, float* m_dev, float* v_dev, int n, float lr, int maximize,
+                        int adam_step, float beta1, float beta2, float eps, void* stream) {
+  if (!patch_dev || !grad_dev || n < 1 || (adam_step > 0 && (!m_dev || !v_dev))) {
+    set_error("vitatk_patch_update: bad arguments");
+    return 1;
+  }
+  return patch_update(patch_dev, grad_dev, m_dev, v_dev, n, lr, maximize ? 1.f : -1.f, adam_step, beta1, beta2, eps,
+                      static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -288,4 +288,19 @@ int lora_repack(const float* A, const float* B, int r, int in, int out, float s,
                 cudaStream_t stream);
 uint32_t train_mask_seed(uint64_t seed, uint64_t step, int layer, int adapter);
 
+// ---------------------------------------------------------------------------------------------
+// adversarial patch / EOT front end (patch.cu)
+// ---------------------------------------------------------------------------------------------
+// composite of `samples` = images x T transformed copies of one patch [3, p, p]; tf [samples, 6] = inverse affine (output-
+// normalised -> patch-normalised).  Writes the normalised im2col rows (cols) and / or fp32 NCHW images (out_img).
+int patch_apply(const float* images, const float* patch, int p, const float* tf, int T, int samples, int circle, PixelNorm nrm,
+                bf16* cols, float* out_img, cudaStream_t stream);
+// grad [3, p, p] += scale * d loss / d patch from dcols (gradient w.r.t. the normalised im2col rows); fw = forward affine;
+// partial: fp32 scratch [samples, 3, p, p]
+int patch_grad(const bf16* dcols, const float* tf, const float* fw, int p, int samples, int circle, PixelNorm nrm, float scale,
+               float* partial, float* grad, cudaStream_t stream);
+int patch_update(float* patch, const float* grad, float* m, float* v, int n, float lr, float dir, int step, float b1, float b2,
+                 float eps, cudaStream_t stream);
+int repeat_labels(const int64_t* labels, int T, int samples, int64_t* out, cudaStream_t stream);
+
 }  // namespace vitatk

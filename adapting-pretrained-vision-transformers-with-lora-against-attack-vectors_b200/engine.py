@@ -387,6 +387,14 @@ class Engine:
             x = x.detach().to(self.device, torch.float32).contiguous()
         return x
 
+    def _img_any(self, x: torch.Tensor) -> torch.Tensor:
+        """Like ``_img`` but without the max_batch limit (callers that split the batch themselves)."""
+        if x.dim() != 4 or tuple(x.shape[1:]) != (3, 224, 224):
+            raise ValueError(f"expected images [B,3,224,224], got {tuple(x.shape)}")
+        if x.device != self.device or x.dtype != torch.float32 or not x.is_contiguous():
+            x = x.detach().to(self.device, torch.float32).contiguous()
+        return x
+
     def _lab(self, y: torch.Tensor, b: int) -> torch.Tensor:
         if y.shape != (b,):
             raise ValueError(f"expected labels [{b}], got {tuple(y.shape)}")

@@ -196,6 +196,25 @@ int vitatk_train_step(vitatk_engine* e, const float* images_dev, const int64_t* 
 int vitatk_train_apply(vitatk_engine* e, float* m_dev, float* v_dev, float lr, float beta1, float beta2, float eps, int step,
                        void* stream);
 
+/* ---- adversarial patch / EOT front end (replaces what ART's AdversarialPatchPyTorch does around the
+ * model in patch_attack.py:47-75,194-204 and rp2_attack.py:33-72) ----
+ * One shared patch [3, p, p] (fp32, [0,1]) is pasted into every image under T random transforms per image (scale,
+ * rotation, translation; circular or square mask): sample n = image n / T under transform n.  tf_dev [batch*T, 6] is the
+ * inverse affine map output-normalised -> patch-normalised coordinates ((x + 0.5) * 2 / 224 - 1 etc.), fw_dev its inverse.
+ *   vitatk_patch_grad    composite -> normalised im2col -> ViT forward -> mean CE over the batch*T samples -> backward ->
+ *                        grad_dev [3, p, p] += d loss / d patch (deterministic gather, no atomics).  batch*T <= max_batch;
+ *                        a larger EOT step is split into several calls by the caller.  loss_dev [batch*T] / logits_dev optional.
+ *   vitatk_patch_apply   the composite itself as fp32 images [batch*T, 3, 224, 224] (attack.apply_patch, patch_attack.py:204)
+ *   vitatk_patch_update  one optimiser step on the patch: Adam (adam_step >= 1 = step counter; ART's default, lr 5.0) or
+ *                        a sign step (adam_step == 0, ART's "pgd"), ascending the loss when maximize != 0, then clip [0,1] */
+int vitatk_patch_grad(vitatk_engine* e, const float* images_dev, const int64_t* labels_dev, int batch, int T,
+                      const float* tf_dev, const float* fw_dev, const float* patch_dev, int p, int circle, float* grad_dev,
+                      float* loss_dev, float* logits_dev, void* stream);
+int vitatk_patch_apply(const float* images_dev, int batch, int T, const float* tf_dev, const float* patch_dev, int p,
+                       int circle, float* out_dev, void* stream);
+int vitatk_patch_update(float* patch_dev, const float* grad_dev, float* m_dev, float* v_dev, int n, float lr, int maximize,
+                        int adam_step, float beta1, float beta2, float eps, void* stream);
+
 /* ---- kernel-level entry points (used by tests/ and bench.py's roofline leg) ----
  * vitatk_k_gemm with tt_n in {32, 64}: "T-tile" mode of the pair kernel -- the GEMM computes T = A * tt_tb^T (tt_tb bf16
  * [64, K], + tt_bias[64] if given) itself, writes it to T_dev and uses it as its LoRA k-block in the same launch;

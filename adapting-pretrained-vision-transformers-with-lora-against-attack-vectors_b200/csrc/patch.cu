@@ -27,9 +27,9 @@ __device__ __forceinline__ float patch_mask(float U, float V, int circle) {
   if (fabsf(U) > 1.f || fabsf(V) > 1.f) return 0.f;
   if (!circle) return 1.f;
   // ART's soft circle (AdversarialPatchPyTorch._get_circular_patch_mask, sharpness 40): 1 - clip((x^2 + y^2)^40, 0, 1)
-  const float r2 = U * U + V * V;
-  const float r4 = r2 * r2, r8 = r4 * r4, r16 = r8 * r8, r32 = r16 * r16;
-  return 1.f - fminf(r32 * r8, 1.f);
+  const float a = U * U + V * V;
+  const float a2 = a * a, a4 = a2 * a2, a8 = a4 * a4, a16 = a8 * a8, a32 = a16 * a16;
+  return 1.f - fminf(a32 * a8, 1.f);  // a^40
 }
 
 // bilinear sample of channel plane `pc` [p, p] at normalised (U, V), zero outside (grid_sample, align_corners = false)

@@ -678,6 +678,115 @@ def run_config5(args):
     return 0
 
 
+# ---------------------------------------------------------------------------------------------------------
+# config 4: patch / EOT optimisation, 32 random transforms per image per step, batch 96 (BASELINE configs[3])
+# ---------------------------------------------------------------------------------------------------------
+def run_config4(args):
+    """One step = one optimiser step on the shared adversarial patch from 96 images x 32 random (scale, rotation,
+    translation) placements = 3072 transformed samples: composite -> ViT-B/16 (LoRA r=8) forward -> CE -> backward -> patch
+    gradient (deterministic gather) in 12 engine calls of 256 samples, ONE all-reduce of the [3,p,p] gradient across ranks,
+    Adam update.  The metric counts transformed samples per second."""
+    out = StdoutToStderr()
+    import torch
+    import torch.distributed as dist
+
+    import vitatk
+    from vitatk import synthetic
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, T, P = 96, 32, 24
+    model = synthetic.random_vit(CLASSES, seed=0)
+    adapters = synthetic.random_adapters(model, r=RANK_R, seed=0)
+    eng = vitatk.Engine(model=model, adapters=adapters, max_batch=256, device=dev)
+    x_host, y_host = synthetic.images_and_labels(B, rank * B, CLASSES, seed=0, pin=True)
+    x, y = x_host.to(dev), y_host.to(dev)
+    atk = vitatk.AdversarialPatch(eng, rotation_max=22.5, scale_min=0.05, scale_max=1.0, learning_rate=5.0, max_iter=1,
+                                  batch_size=B, patch_shape=(3, P, P), patch_type="circle", optimizer="Adam",
+                                  transforms_per_image=T, seed=rank, max_samples=256)
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    first = None
+    for _ in range(max(args.warmup, 3)):
+        l = atk.train_step(x, y)
+        first = l if first is None else first
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for _ in range(args.steps):
+        last = atk.train_step(x, y)
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    launches = eng.launch_count - l0
+    clocks = sampler.stop() if rank == 0 else None
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    patch_host = torch.empty(3, P, P).pin_memory()
+    sync_all()
+    f0.record()
+    for _ in range(args.steps):
+        x.copy_(x_host, non_blocking=True)
+        y.copy_(y_host, non_blocking=True)
+        atk.train_step(x, y)
+        patch_host.copy_(atk.patch, non_blocking=True)
+    f1.record()
+    sync_all()
+    ms_e2e = f0.elapsed_time(f1)
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+    peaks, peaks_kind = measured_peaks()
+    samples = B * T * world * args.steps
+    value = samples / (ms / 1e3)
+    peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
+    gflop = algorithmic_gflop_per_image_step()
+    line = {
+        "metric": "EOT transformed samples/sec (patch optimisation, 32 transforms x 96 images per step), LoRA ViT-B/16 (BASELINE configs[3])",
+        "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": "adversarial patch 3x24x24 (circle), scale 0.05-1.0, rotation +-22.5 deg, Adam lr 5.0, 32 transforms x "
+                               "96 images per step, LoRA(r=8) ViT-B/16, 21 classes (BASELINE configs[3])",
+                   "global_batch": B * T * world, "parallelism": f"dp{world} (one all-reduce of the {3 * P * P * 4} B patch gradient per step)",
+                   "l2": "activations of every 256-sample chunk (~11 GB) exceed L2"},
+        "clocks": clocks,
+        "e2e": {"value": samples / (ms_e2e / 1e3), "unit": "samples/s", "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8,
+                "d2h_bytes_per_step": 3 * P * P * 4},
+        "gpu_launches": launches,
+        "roofline": {"bound": "tensor", "achieved": value / world * gflop / 1e3, "peak": peak, "unit": "TFLOP/s",
+                     "frac": value / world * gflop / 1e3 / peak, "traffic": None,
+                     "note": "whole-step algorithmic FLOPs (one forward + input-gradient backward per sample) / time",
+                     "peak_kind": f"{peaks_kind} sustained cuBLAS bf16"},
+        "patch": {"loss_first": first, "loss_last": last},
+    }
+    out.emit(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -686,9 +795,9 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH, help="images per GPU (BASELINE: 256)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 5],
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 4, 5],
                     help="BASELINE.json configs, 1-based: 1 = FGSM batch 8 (CUDA graph), 2 = PGD-10 batch 256 (the metric; default), "
-                         "5 = PGD-7 adversarial LoRA training, batch 96 per GPU")
+                         "4 = patch / EOT optimisation (32 transforms x 96 images), 5 = PGD-7 adversarial LoRA training, batch 96 per GPU")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "engine":
         args.warmup = 3  # timing rules: W >= 3
@@ -708,7 +817,7 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
         return subprocess.call(cmd)
-    return run_config5(args) if args.config == 5 else run_engine(args)
+    return {4: run_config4, 5: run_config5}.get(args.config, run_engine)(args)
 
 
 if __name__ == "__main__":

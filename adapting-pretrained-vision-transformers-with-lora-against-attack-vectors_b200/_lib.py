@@ -14,7 +14,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libvitatk.so")
 INCLUDE_DIR = os.path.join(os.path.dirname(PKG_DIR), "include")
-SOURCES = ["gemm_tc05.cu", "attention_tc05.cu", "attention_bwd_fused.cu", "elementwise.cu", "train.cu", "patch.cu", "engine.cu"]
+SOURCES = ["gemm_tc05.cu", "attention_tc05.cu", "attention_bwd_fused.cu", "elementwise.cu", "train.cu", "patch.cu", "swin.cu", "engine.cu"]
 HEADERS = ["ptx.cuh", "vitatk_internal.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -83,6 +83,9 @@ EXPORTS = [
     "vitatk_k_attention_fwd_trace", "vitatk_k_layernorm_stats",
     "vitatk_train_enable", "vitatk_train_bind", "vitatk_train_set_adapter", "vitatk_train_repack", "vitatk_train_step",
     "vitatk_train_apply", "vitatk_train_mask_seed", "vitatk_patch_grad", "vitatk_patch_apply", "vitatk_patch_update",
+    "vitatk_swin_create", "vitatk_swin_destroy", "vitatk_swin_set_tensor", "vitatk_swin_set_lora", "vitatk_swin_set_normalization",
+    "vitatk_swin_finalize", "vitatk_swin_workspace_bytes", "vitatk_swin_launch_count", "vitatk_swin_forward",
+    "vitatk_swin_input_grad", "vitatk_swin_attack", "vitatk_swin_count_correct",
 ]
 
 
@@ -153,7 +156,8 @@ def load() -> C.CDLL:
     lib.vitatk_train_mask_seed.restype = C.c_uint
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name not in ("vitatk_last_error", "vitatk_workspace_bytes", "vitatk_launch_count", "vitatk_train_mask_seed"):
+        if name not in ("vitatk_last_error", "vitatk_workspace_bytes", "vitatk_launch_count", "vitatk_train_mask_seed",
+                        "vitatk_swin_workspace_bytes", "vitatk_swin_launch_count"):
             fn.restype = i
     _lib = lib
     return lib

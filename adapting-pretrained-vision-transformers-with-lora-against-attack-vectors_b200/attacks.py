@@ -98,7 +98,11 @@ def compile_model(model: torch.nn.Module, max_batch: int = 256, device=None, for
         if core.training:
             raise RuntimeError("vitatk: call model.eval() first (the reference attacks an eval() model, "
                                "whitebox_attacks.py:99; dropout is not part of the attack path)")
-        eng = Engine(model=core, max_batch=max_batch, device=device)
+        if any(k.startswith("swin.") or ".swin." in k for k in core.state_dict()):
+            from .swin import SwinEngine  # HF SwinForImageClassification (shifted-window attention)
+            eng = SwinEngine(model=core, max_batch=max_batch, device=device)
+        else:
+            eng = Engine(model=core, max_batch=max_batch, device=device)
         object.__setattr__(core, "_vitatk_engine", eng)
         object.__setattr__(core, "_vitatk_fingerprint", fp)
     if mean is not None:

@@ -1,0 +1,1196 @@
+// Swin Transformer (shifted-window attention) on the attack engine (BASELINE configs[2]: PGD-20 on LoRA
+// Swin-B).  The reference only names the model family (README.md:53); the arithmetic restated here is HF
+// transformers' SwinForImageClassification (modeling_swin.py: window_partition :141-150, patch merging :326-349,
+// window attention with relative-position bias and the -100 region mask :410-459,:556-582, cyclic shift :615-636,
+// pooled head :870-915), forward and input-gradient backward.
+//
+// Every Linear (qkv, proj, fc1, fc2, patch embed, patch-merging reduction) runs on the same tcgen05 GEMM as the ViT path
+// (bias / residual / GELU+GELU' / LoRA k-block epilogues; stage widths 128 / 256 / 512 / 1024).  New here:
+//   win_attn_fwd / win_attn_bwd   7x7-window attention, head dim 32: one warp per (window, head); the cyclic shift, the
+//                                 window partition and their inverses are index arithmetic on the token-major q|k|v rows
+//                                 (nothing is rolled or re-laid out in memory), the relative-position bias comes from a
+//                                 [heads, 49, 49] table, the shifted-window mask from each token's region id.  The backward
+//                                 recomputes the 49x49 probabilities (they are never stored).
+//   merge_gather / merge_scatter  2x2 patch merging as a row permutation ([B,H,W,C] -> [B,H/2,W/2,4C]) and its inverse
+//   ln_any_fwd / ln_any_bwd       LayerNorm for any width (128 ... 2048 here), one warp per row
+//   swin_head                     final LayerNorm on all 49 tokens + mean pool + classifier + CE (+ backward)
+//   swin pixel kernels            PGD init / update / gradient materialisation for the 4x4 patch-embedding layout
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <memory>
+#include <vector>
+
+#include "../../include/vitatk.h"
+#include "vitatk_internal.h"
+
+namespace vitatk {
+namespace {
+
+constexpr int WIN = 7, WT = 49, HD = 32, IMG = 224;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ void unpack8(const uint4& q, float* f) {
+  const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(p[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 q;
+  __nv_bfloat162* p = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return q;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm for any width (cols % 8 == 0): one warp per row, two passes over the row (the second one hits L1 / L2)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ln_any_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, bf16* __restrict__ y,
+                                                         float2* __restrict__ stats, int rows, int cols, float eps) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * cols);
+  const int nch = cols >> 3;
+  float s = 0.f;
+  for (int c = lane; c < nch; c += 32) {
+    float v[8];
+    unpack8(__ldg(xr + c), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[j];
+  }
+  const float mean = warp_sum(s) / cols;
+  float q = 0.f;
+  for (int c = lane; c < nch; c += 32) {
+    float v[8];
+    unpack8(__ldg(xr + c), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) q = fmaf(v[j] - mean, v[j] - mean, q);
+  }
+  const float rstd = rsqrtf(warp_sum(q) / cols + eps);
+  uint4* yr = reinterpret_cast<uint4*>(y + static_cast<size_t>(row) * cols);
+  for (int c = lane; c < nch; c += 32) {
+    float v[8], o[8];
+    unpack8(__ldg(xr + c), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = (v[j] - mean) * rstd * __ldg(gamma + c * 8 + j) + __ldg(beta + c * 8 + j);
+    yr[c] = pack8(o);
+  }
+  if (lane == 0) stats[row] = make_float2(mean, rstd);
+}
+
+// dx = dres + LN_backward(dy)   (dres may be null)
+__global__ void __launch_bounds__(256) ln_any_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                         const float2* __restrict__ stats, const float* __restrict__ gamma,
+                                                         const bf16* __restrict__ dres, bf16* __restrict__ dx, int rows, int cols) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * cols);
+  const uint4* dyr = reinterpret_cast<const uint4*>(dy + static_cast<size_t>(row) * cols);
+  const int nch = cols >> 3;
+  const float2 st = stats[row];
+  float s1 = 0.f, s2 = 0.f;
+  for (int c = lane; c < nch; c += 32) {
+    float xv[8], dv[8];
+    unpack8(__ldg(xr + c), xv);
+    unpack8(__ldg(dyr + c), dv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float gd = dv[j] * __ldg(gamma + c * 8 + j);
+      s1 += gd;
+      s2 = fmaf(gd, (xv[j] - st.x) * st.y, s2);
+    }
+  }
+  const float m1 = warp_sum(s1) / cols, m2 = warp_sum(s2) / cols;
+  const uint4* rr = dres ? reinterpret_cast<const uint4*>(dres + static_cast<size_t>(row) * cols) : nullptr;
+  uint4* dxr = reinterpret_cast<uint4*>(dx + static_cast<size_t>(row) * cols);
+  for (int c = lane; c < nch; c += 32) {
+    float xv[8], dv[8], r[8] = {0, 0, 0, 0, 0, 0, 0, 0}, o[8];
+    unpack8(__ldg(xr + c), xv);
+    unpack8(__ldg(dyr + c), dv);
+    if (rr) unpack8(__ldg(rr + c), r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float gd = dv[j] * __ldg(gamma + c * 8 + j);
+      o[j] = r[j] + st.y * (gd - m1 - (xv[j] - st.x) * st.y * m2);
+    }
+    dxr[c] = pack8(o);
+  }
+}
+
+int ln_any_fwd(const bf16* x, const float* g, const float* b, bf16* y, float2* st, int rows, int cols, float eps, cudaStream_t s) {
+  ln_any_fwd_kernel<<<(rows + 7) / 8, 256, 0, s>>>(x, g, b, y, st, rows, cols, eps);
+  VITATK_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int ln_any_bwd(const bf16* dy, const bf16* x, const float2* st, const float* g, const bf16* dres, bf16* dx, int rows, int cols,
+               cudaStream_t s) {
+  ln_any_bwd_kernel<<<(rows + 7) / 8, 256, 0, s>>>(dy, x, st, g, dres, dx, rows, cols);
+  VITATK_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 2x2 patch merging (modeling_swin.py:326-345): out[b, y2, x2, k*C + c] = in[b, 2*y2 + (k & 1), 2*x2 + (k >> 1), c]
+// (k = 0..3 in HF's concat order: (0,0), (1,0), (0,1), (1,1)).  One thread per 16-byte chunk.  scatter = the inverse.
+// ------------------------------------------------------------------------------------------------
+__global__ void merge_permute_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int batch, int R, int C, int scatter) {
+  const int chunks = C >> 3, R2 = R >> 1;
+  const long long total = static_cast<long long>(batch) * R2 * R2 * 4 * chunks;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int ch = static_cast<int>(i % chunks);
+  long long t = i / chunks;
+  const int k = static_cast<int>(t % 4);
+  t /= 4;
+  const int x2 = static_cast<int>(t % R2);
+  t /= R2;
+  const int y2 = static_cast<int>(t % R2), b = static_cast<int>(t / R2);
+  const size_t fine = ((static_cast<size_t>(b) * R + 2 * y2 + (k & 1)) * R + 2 * x2 + (k >> 1)) * C + ch * 8;
+  const size_t coarse = ((static_cast<size_t>(b) * R2 + y2) * R2 + x2) * (4 * C) + k * C + ch * 8;
+  if (scatter) *reinterpret_cast<uint4*>(out + fine) = *reinterpret_cast<const uint4*>(in + coarse);
+  else *reinterpret_cast<uint4*>(out + coarse) = *reinterpret_cast<const uint4*>(in + fine);
+}
+int merge_permute(const bf16* in, bf16* out, int batch, int R, int C, int scatter, cudaStream_t s) {
+  const long long total = static_cast<long long>(batch) * (R / 2) * (R / 2) * 4 * (C / 8);
+  merge_permute_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(in, out, batch, R, C, scatter);
+  VITATK_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Window attention.  Token rows are (b, y, x) row-major over an R x R grid; q|k|v packed [M, 3C], head h = columns
+// h*32 .. h*32+31 of each third.  Window (wy, wx) holds the tokens whose SHIFTED coordinates y' = (y - shift) mod R fall
+// in [7 wy, 7 wy + 7): torch.roll(-shift) + window_partition without moving data.
+// ------------------------------------------------------------------------------------------------
+struct WinGeom {
+  int R, nW, heads, C, shift;
+};
+__device__ __forceinline__ int win_token_row(const WinGeom& g, int b, int win, int t) {
+  const int wpr = g.R / WIN;
+  const int wy = win / wpr, wx = win % wpr, iy = t / WIN, ix = t % WIN;
+  int y = wy * WIN + iy + g.shift, x = wx * WIN + ix + g.shift;
+  if (y >= g.R) y -= g.R;
+  if (x >= g.R) x -= g.R;
+  return (b * g.R + y) * g.R + x;
+}
+// region id of a shifted position (modeling_swin.py:556-575): tokens of different regions must not attend to each other
+__device__ __forceinline__ int win_region(const WinGeom& g, int win, int t) {
+  if (g.shift == 0) return 0;
+  const int wpr = g.R / WIN;
+  const int ys = (win / wpr) * WIN + t / WIN, xs = (win % wpr) * WIN + t % WIN;
+  const int ry = ys < g.R - WIN ? 0 : (ys < g.R - g.shift ? 1 : 2);
+  const int rx = xs < g.R - WIN ? 0 : (xs < g.R - g.shift ? 1 : 2);
+  return ry * 3 + rx;
+}
+
+constexpr int WA_WARPS = 4;
+// smem per warp (floats): K [49][32], V [49][32]
+__global__ void __launch_bounds__(WA_WARPS * 32) win_attn_fwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ bias,
+                                                                     bf16* __restrict__ out, WinGeom g, int items, float scale) {
+  extern __shared__ float sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * WA_WARPS + warp;
+  if (item >= items) return;
+  float* Ks = sm + warp * (2 * WT * HD + 64);
+  float* Vs = Ks + WT * HD;
+  int* reg = reinterpret_cast<int*>(Vs + WT * HD);
+  const int h = item % g.heads, win = (item / g.heads) % g.nW, b = item / (g.heads * g.nW);
+  const int ld = 3 * g.C;
+  for (int t = lane; t < WT; t += 32) reg[t] = win_region(g, win, t);
+  // cooperative load of K and V: 49 rows x 32 dims = 196 chunks of 8
+  for (int c = lane; c < WT * 4; c += 32) {
+    const int t = c >> 2, d8 = (c & 3) * 8;
+    const size_t row = static_cast<size_t>(win_token_row(g, b, win, t)) * ld + h * HD + d8;
+    float f[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(qkv + row + g.C)), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) Ks[t * HD + d8 + j] = f[j];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(qkv + row + 2 * g.C)), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) Vs[t * HD + d8 + j] = f[j];
+  }
+  __syncwarp();
+  const float* bh = bias + static_cast<size_t>(h) * WT * WT;
+  for (int i = lane; i < WT; i += 32) {
+    const int qrow = win_token_row(g, b, win, i);
+    float q[HD];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) unpack8(__ldg(reinterpret_cast<const uint4*>(qkv + static_cast<size_t>(qrow) * ld + h * HD + c * 8)), q + c * 8);
+    float s[WT];
+    float mx = -INFINITY;
+    const int ri = reg[i];
+#pragma unroll
+    for (int j = 0; j < WT; ++j) {
+      float acc = 0.f;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) acc = fmaf(q[d], Ks[j * HD + d], acc);
+      acc = fmaf(acc, scale, __ldg(bh + i * WT + j));
+      if (reg[j] != ri) acc -= 100.f;
+      s[j] = acc;
+      mx = fmaxf(mx, acc);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < WT; ++j) {
+      s[j] = __expf(s[j] - mx);
+      sum += s[j];
+    }
+    const float inv = 1.f / sum;
+    float o[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) o[d] = 0.f;
+#pragma unroll
+    for (int j = 0; j < WT; ++j) {
+      const float p = s[j] * inv;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) o[d] = fmaf(p, Vs[j * HD + d], o[d]);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(qrow) * g.C + h * HD);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) dst[c] = pack8(o + c * 8);
+  }
+}
+
+constexpr int WB_WARPS = 2;
+// smem per warp (floats): Q, K, V, dO [49][32] each, lse [49], D [49], region [49]
+constexpr int WB_SMEM_FLOATS = 4 * WT * HD + 3 * 64;
+__global__ void __launch_bounds__(WB_WARPS * 32) win_attn_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
+                                                                     const float* __restrict__ bias, bf16* __restrict__ dqkv,
+                                                                     WinGeom g, int items, float scale) {
+  extern __shared__ float sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * WB_WARPS + warp;
+  if (item >= items) return;
+  float* Qs = sm + warp * WB_SMEM_FLOATS;
+  float* Ks = Qs + WT * HD;
+  float* Vs = Ks + WT * HD;
+  float* Gs = Vs + WT * HD;  // dO
+  float* lse = Gs + WT * HD;
+  float* Dd = lse + 64;
+  int* reg = reinterpret_cast<int*>(Dd + 64);
+  const int h = item % g.heads, win = (item / g.heads) % g.nW, b = item / (g.heads * g.nW);
+  const int ld = 3 * g.C;
+  for (int t = lane; t < WT; t += 32) reg[t] = win_region(g, win, t);
+  for (int c = lane; c < WT * 4; c += 32) {
+    const int t = c >> 2, d8 = (c & 3) * 8;
+    const int trow = win_token_row(g, b, win, t);
+    const size_t row = static_cast<size_t>(trow) * ld + h * HD + d8;
+    float f[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(qkv + row)), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) Qs[t * HD + d8 + j] = f[j];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(qkv + row + g.C)), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) Ks[t * HD + d8 + j] = f[j];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(qkv + row + 2 * g.C)), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) Vs[t * HD + d8 + j] = f[j];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dout + static_cast<size_t>(trow) * g.C + h * HD + d8)), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) Gs[t * HD + d8 + j] = f[j];
+  }
+  __syncwarp();
+  const float* bh = bias + static_cast<size_t>(h) * WT * WT;
+  // ---- phase A: lane = query.  lse_i, D_i = sum_j p_ij dP_ij, dq_i = scale * sum_j dS_ij k_j ----
+  for (int i = lane; i < WT; i += 32) {
+    float q[HD], go[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) {
+      q[d] = Qs[i * HD + d];
+      go[d] = Gs[i * HD + d];
+    }
+    float s[WT];
+    float mx = -INFINITY;
+    const int ri = reg[i];
+#pragma unroll
+    for (int j = 0; j < WT; ++j) {
+      float acc = 0.f;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) acc = fmaf(q[d], Ks[j * HD + d], acc);
+      acc = fmaf(acc, scale, __ldg(bh + i * WT + j));
+      if (reg[j] != ri) acc -= 100.f;
+      s[j] = acc;
+      mx = fmaxf(mx, acc);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < WT; ++j) {
+      s[j] = __expf(s[j] - mx);
+      sum += s[j];
+    }
+    const float inv = 1.f / sum;
+    float dP[WT];
+    float D = 0.f;
+#pragma unroll
+    for (int j = 0; j < WT; ++j) {
+      float acc = 0.f;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) acc = fmaf(go[d], Vs[j * HD + d], acc);
+      s[j] *= inv;
+      dP[j] = acc;
+      D = fmaf(s[j], acc, D);
+    }
+    float dq[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) dq[d] = 0.f;
+#pragma unroll
+    for (int j = 0; j < WT; ++j) {
+      const float dS = s[j] * (dP[j] - D) * scale;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) dq[d] = fmaf(dS, Ks[j * HD + d], dq[d]);
+    }
+    lse[i] = mx + __logf(sum);
+    Dd[i] = D;
+    uint4* dst = reinterpret_cast<uint4*>(dqkv + static_cast<size_t>(win_token_row(g, b, win, i)) * ld + h * HD);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) dst[c] = pack8(dq + c * 8);
+  }
+  __syncwarp();
+  // ---- phase B: lane = key.  dv_j = sum_i p_ij dO_i, dk_j = scale * sum_i dS_ij q_i ----
+  for (int j = lane; j < WT; j += 32) {
+    float k[HD], v[HD], dk[HD], dv[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) {
+      k[d] = Ks[j * HD + d];
+      v[d] = Vs[j * HD + d];
+      dk[d] = 0.f;
+      dv[d] = 0.f;
+    }
+    const int rj = reg[j];
+#pragma unroll 7
+    for (int i = 0; i < WT; ++i) {
+      float sc = 0.f, dp = 0.f;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) {
+        sc = fmaf(Qs[i * HD + d], k[d], sc);
+        dp = fmaf(Gs[i * HD + d], v[d], dp);
+      }
+      sc = fmaf(sc, scale, __ldg(bh + i * WT + j));
+      if (reg[i] != rj) sc -= 100.f;
+      const float p = __expf(sc - lse[i]);
+      const float dS = p * (dp - Dd[i]) * scale;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) {
+        dv[d] = fmaf(p, Gs[i * HD + d], dv[d]);
+        dk[d] = fmaf(dS, Qs[i * HD + d], dk[d]);
+      }
+    }
+    const size_t row = static_cast<size_t>(win_token_row(g, b, win, j)) * ld + h * HD;
+    uint4* dkp = reinterpret_cast<uint4*>(dqkv + row + g.C);
+    uint4* dvp = reinterpret_cast<uint4*>(dqkv + row + 2 * g.C);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      dkp[c] = pack8(dk + c * 8);
+      dvp[c] = pack8(dv + c * 8);
+    }
+  }
+}
+
+int win_attn_fwd(const bf16* qkv, const float* bias, bf16* out, int batch, int R, int C, int heads, int shift, cudaStream_t s) {
+  WinGeom g = {R, (R / WIN) * (R / WIN), heads, C, shift};
+  const int items = batch * g.nW * heads;
+  const size_t smem = WA_WARPS * (2 * WT * HD + 64) * sizeof(float);
+  static PerDeviceOnce once;
+  if (once.need()) VITATK_CUDA_OK(cudaFuncSetAttribute(win_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  win_attn_fwd_kernel<<<(items + WA_WARPS - 1) / WA_WARPS, WA_WARPS * 32, smem, s>>>(qkv, bias, out, g, items, 1.0f / sqrtf(static_cast<float>(HD)));
+  VITATK_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int win_attn_bwd(const bf16* qkv, const bf16* dout, const float* bias, bf16* dqkv, int batch, int R, int C, int heads, int shift,
+                 cudaStream_t s) {
+  WinGeom g = {R, (R / WIN) * (R / WIN), heads, C, shift};
+  const int items = batch * g.nW * heads;
+  const size_t smem = WB_WARPS * WB_SMEM_FLOATS * sizeof(float);
+  static PerDeviceOnce once;
+  if (once.need()) VITATK_CUDA_OK(cudaFuncSetAttribute(win_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  win_attn_bwd_kernel<<<(items + WB_WARPS - 1) / WB_WARPS, WB_WARPS * 32, smem, s>>>(qkv, dout, bias, dqkv, g, items,
+                                                                                    1.0f / sqrtf(static_cast<float>(HD)));
+  VITATK_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Head (modeling_swin.py:886-895, 1075-1080): LayerNorm on each of the T tokens of the last stage, mean over tokens,
+// classifier, CE; backward to the last stage's hidden state.  One CTA per image.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) swin_head_kernel(const bf16* __restrict__ h, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, const float* __restrict__ Wc,
+                                                        const float* __restrict__ bc, const int64_t* __restrict__ labels,
+                                                        float* __restrict__ logits, float* __restrict__ loss, bf16* __restrict__ dh,
+                                                        int tokens, int dim, int classes, float eps, float grad_scale) {
+  extern __shared__ float hs[];
+  float* pooled = hs;             // [dim]
+  float* dpool = pooled + dim;    // [dim]
+  float* lg = dpool + dim;        // [classes]
+  float* tst = lg + classes;      // [tokens][2] mean, rstd
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+  const bf16* base = h + static_cast<size_t>(b) * tokens * dim;
+  for (int k = tid; k < dim; k += blockDim.x) pooled[k] = 0.f;
+  __syncthreads();
+  // per-token statistics (warp per token)
+  for (int t = warp; t < tokens; t += nw) {
+    float s = 0.f;
+    for (int k = lane; k < dim; k += 32) s += __bfloat162float(base[static_cast<size_t>(t) * dim + k]);
+    const float mean = warp_sum(s) / dim;
+    float q = 0.f;
+    for (int k = lane; k < dim; k += 32) {
+      const float d = __bfloat162float(base[static_cast<size_t>(t) * dim + k]) - mean;
+      q = fmaf(d, d, q);
+    }
+    const float rstd = rsqrtf(warp_sum(q) / dim + eps);
+    if (lane == 0) {
+      tst[2 * t] = mean;
+      tst[2 * t + 1] = rstd;
+    }
+  }
+  __syncthreads();
+  for (int k = tid; k < dim; k += blockDim.x) {
+    float acc = 0.f;
+    for (int t = 0; t < tokens; ++t)
+      acc += (__bfloat162float(base[static_cast<size_t>(t) * dim + k]) - tst[2 * t]) * tst[2 * t + 1];
+    pooled[k] = acc / tokens * gamma[k] + beta[k];
+  }
+  __syncthreads();
+  for (int c = warp; c < classes; c += nw) {
+    float acc = 0.f;
+    for (int k = lane; k < dim; k += 32) acc = fmaf(pooled[k], __ldg(Wc + static_cast<size_t>(c) * dim + k), acc);
+    acc = warp_sum(acc);
+    if (lane == 0) lg[c] = acc + bc[c];
+  }
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int c = 0; c < classes; ++c) mx = fmaxf(mx, lg[c]);
+  float se = 0.f;
+  for (int c = 0; c < classes; ++c) se += expf(lg[c] - mx);
+  const float lse = mx + logf(se);
+  const long long yl = labels ? static_cast<long long>(labels[b]) : -1;
+  const int y = (labels && yl >= 0 && yl < classes) ? static_cast<int>(yl) : -1;
+  for (int c = tid; c < classes; c += blockDim.x) logits[static_cast<size_t>(b) * classes + c] = lg[c];
+  if (tid == 0 && loss) loss[b] = y >= 0 ? lse - lg[y] : __int_as_float(0x7fc00000);
+  if (dh == nullptr) return;
+  __syncthreads();
+  for (int c = tid; c < classes; c += blockDim.x) lg[c] = expf(lg[c] - lse) - (c == y ? 1.f : 0.f);
+  __syncthreads();
+  // d pooled-LN-output[k] (same for every token, / tokens), times gamma
+  for (int k = tid; k < dim; k += blockDim.x) {
+    float acc = 0.f;
+    for (int c = 0; c < classes; ++c) acc = fmaf(lg[c], __ldg(Wc + static_cast<size_t>(c) * dim + k), acc);
+    dpool[k] = acc * grad_scale / tokens * gamma[k];
+  }
+  __syncthreads();
+  // LayerNorm backward per token (warp per token): dx = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dpool
+  for (int t = warp; t < tokens; t += nw) {
+    const float mean = tst[2 * t], rstd = tst[2 * t + 1];
+    float s1 = 0.f, s2 = 0.f;
+    for (int k = lane; k < dim; k += 32) {
+      const float xh = (__bfloat162float(base[static_cast<size_t>(t) * dim + k]) - mean) * rstd;
+      s1 += dpool[k];
+      s2 = fmaf(dpool[k], xh, s2);
+    }
+    const float m1 = warp_sum(s1) / dim, m2 = warp_sum(s2) / dim;
+    bf16* drow = dh + (static_cast<size_t>(b) * tokens + t) * dim;
+    for (int k = lane; k < dim; k += 32) {
+      const float xh = (__bfloat162float(base[static_cast<size_t>(t) * dim + k]) - mean) * rstd;
+      drow[k] = __float2bfloat16(rstd * (dpool[k] - m1 - xh * m2));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pixel kernels for the 4x4 patch embedding: im2col row = b * 3136 + (y / 4) * 56 + x / 4, column = c * 16 + (y % 4) * 4 + x % 4
+// (flattening of the conv weight [128, 3, 4, 4]); the matrix is 64 columns wide (48 used, the rest stay zero).
+// ------------------------------------------------------------------------------------------------
+constexpr int SW_P = 4, SW_G = IMG / SW_P, SW_K = 64;
+__device__ __forceinline__ size_t swin_cols_off(int b, int c, int y, int x) {
+  return (static_cast<size_t>(b) * SW_G * SW_G + (y >> 2) * SW_G + (x >> 2)) * SW_K + c * 16 + (y & 3) * 4 + (x & 3);
+}
+__device__ __forceinline__ float u01_hash(uint64_t seed, uint64_t ctr) {
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (ctr + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return static_cast<float>(z >> 40) * (1.0f / 16777216.0f);
+}
+__device__ __forceinline__ float enforce_ball(float adv, float x0, float eps) {
+  const float d = adv - x0;
+  if (d > eps) adv = __uint_as_float(__float_as_uint(adv) - 1u);
+  else if (d < -eps) adv = __uint_as_float(__float_as_uint(adv) + 1u);
+  return adv;
+}
+// mode 0: init (adv = clamp(x0 + noise | rng, 0, 1)); 1: PGD update from dcols; 2: materialise the gradient image.
+// One thread = 4 consecutive pixels (one patch row).
+__global__ void __launch_bounds__(256) swin_pixel_kernel(int mode, const float* __restrict__ x0, const float* __restrict__ noise,
+                                                         float* __restrict__ adv, bf16* __restrict__ cols,
+                                                         const bf16* __restrict__ dcols, float* __restrict__ grad, int batch,
+                                                         PixelNorm nrm, float eps, float alpha, int use_rng, uint64_t seed,
+                                                         uint64_t index0, float gscale) {
+  const long long total = static_cast<long long>(batch) * 3 * IMG * (IMG / 4);
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int x4 = static_cast<int>(idx % (IMG / 4));
+  long long t = idx / (IMG / 4);
+  const int y = static_cast<int>(t % IMG);
+  t /= IMG;
+  const int c = static_cast<int>(t % 3), b = static_cast<int>(t / 3);
+  const size_t p = (static_cast<size_t>(b * 3 + c) * IMG + y) * IMG + x4 * 4;
+  const size_t co = swin_cols_off(b, c, y, x4 * 4);
+  if (mode == 2) {
+    const uint2 q = *reinterpret_cast<const uint2*>(dcols + co);
+    const __nv_bfloat162* q2 = reinterpret_cast<const __nv_bfloat162*>(&q);
+    const float2 a = __bfloat1622float2(q2[0]), bb = __bfloat1622float2(q2[1]);
+    const float k = nrm.inv_std[c] * gscale;
+    *reinterpret_cast<float4*>(grad + p) = make_float4(a.x * k, a.y * k, bb.x * k, bb.y * k);
+    return;
+  }
+  const float4 o4 = __ldg(reinterpret_cast<const float4*>(x0 + p));
+  const float xo[4] = {o4.x, o4.y, o4.z, o4.w};
+  float v[4];
+  if (mode == 0) {
+    for (int j = 0; j < 4; ++j) v[j] = xo[j];
+    if (noise != nullptr) {
+      const float4 n4 = __ldg(reinterpret_cast<const float4*>(noise + p));
+      const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
+      for (int j = 0; j < 4; ++j) v[j] = enforce_ball(fminf(fmaxf(xo[j] + nn[j], 0.f), 1.f), xo[j], eps);
+    } else if (use_rng) {
+      const uint64_t e0 = (index0 + b) * (3ull * IMG * IMG) + (static_cast<uint64_t>(c) * IMG + y) * IMG + x4 * 4;
+      for (int j = 0; j < 4; ++j) {
+        const float n = (2.f * u01_hash(seed, e0 + j) - 1.f) * eps;
+        v[j] = enforce_ball(fminf(fmaxf(xo[j] + n, 0.f), 1.f), xo[j], eps);
+      }
+    }
+  } else {
+    const float4 a4 = *reinterpret_cast<const float4*>(adv + p);
+    const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+    const uint2 q = *reinterpret_cast<const uint2*>(dcols + co);
+    const __nv_bfloat162* q2 = reinterpret_cast<const __nv_bfloat162*>(&q);
+    const float2 g0 = __bfloat1622float2(q2[0]), g1 = __bfloat1622float2(q2[1]);
+    const float gg[4] = {g0.x, g0.y, g1.x, g1.y};
+    for (int j = 0; j < 4; ++j) {
+      const float sg = (gg[j] > 0.f) ? 1.f : ((gg[j] < 0.f) ? -1.f : 0.f);
+      const float stepped = av[j] + alpha * sg;
+      const float delta = fminf(fmaxf(stepped - xo[j], -eps), eps);
+      v[j] = enforce_ball(fminf(fmaxf(xo[j] + delta, 0.f), 1.f), xo[j], eps);
+    }
+  }
+  *reinterpret_cast<float4*>(adv + p) = make_float4(v[0], v[1], v[2], v[3]);
+  uint2 o;
+  __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+  o2[0] = __floats2bfloat162_rn((v[0] - nrm.mean[c]) * nrm.inv_std[c], (v[1] - nrm.mean[c]) * nrm.inv_std[c]);
+  o2[1] = __floats2bfloat162_rn((v[2] - nrm.mean[c]) * nrm.inv_std[c], (v[3] - nrm.mean[c]) * nrm.inv_std[c]);
+  *reinterpret_cast<uint2*>(cols + co) = o;
+}
+
+struct BlockW {
+  const float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
+  const bf16 *qkv_w = nullptr, *qkv_wt = nullptr, *proj_w = nullptr, *proj_wt = nullptr, *fc1_w = nullptr, *fc1_wt = nullptr,
+             *fc2_w = nullptr, *fc2_wt = nullptr;
+  const float *qkv_b = nullptr, *proj_b = nullptr, *fc1_b = nullptr, *fc2_b = nullptr, *relbias = nullptr;
+  struct Lora {
+    int rank = 0;
+    const bf16 *la_fwd = nullptr, *lb_fwd = nullptr, *lb_bwd = nullptr, *la_bwd = nullptr;
+  } lora[4];
+  // saved activations
+  bf16 *h_in = nullptr, *qkv = nullptr, *ao = nullptr, *h_mid = nullptr, *u = nullptr;
+  float2 *st1 = nullptr, *st2 = nullptr;
+};
+struct BlockPlans {
+  GemmPlan t_qkv, qkv, t_proj, proj, t_fc1, fc1, t_fc2, fc2;
+  GemmPlan bt_fc2, bfc2, bt_fc1, bfc1, bt_proj, bproj, bt_qkv, bqkv;
+};
+struct StageW {
+  const float *mln_g = nullptr, *mln_b = nullptr;
+  const bf16 *m_w = nullptr, *m_wt = nullptr;
+  float2* stm = nullptr;
+  GemmPlan red, bred;
+};
+struct SwinPlans {
+  GemmPlan patch, bpatch;
+  std::vector<std::vector<BlockPlans>> blocks;
+  std::vector<GemmPlan> red, bred;
+};
+
+}  // namespace
+}  // namespace vitatk
+
+using namespace vitatk;
+
+struct vitatk_swin {
+  vitatk_swin_config cfg;
+  int num_sms = 148;
+  bool finalized = false;
+  const bf16 *patch_w = nullptr, *patch_wt = nullptr;
+  const float *patch_b = nullptr, *eln_g = nullptr, *eln_b = nullptr, *fln_g = nullptr, *fln_b = nullptr, *head_w = nullptr,
+              *head_b = nullptr;
+  std::vector<std::vector<BlockW>> blk;  // [stage][block]
+  StageW stg[3];
+  char* ws = nullptr;
+  long long ws_bytes = 0;
+  // scratch sized for the largest stage
+  bf16 *cols = nullptr, *e0 = nullptr, *xn = nullptr, *g = nullptr, *T = nullptr, *dA = nullptr, *dB = nullptr, *dxn = nullptr,
+       *dao = nullptr, *du = nullptr, *dqkv = nullptr, *xm = nullptr;
+  bf16* sout[4] = {nullptr, nullptr, nullptr, nullptr};  // output of each stage (input of its patch merging / of the head)
+  float2* st_e = nullptr;
+  float *logits = nullptr, *loss = nullptr, *scratch_img = nullptr;
+  std::map<int, SwinPlans*> plans;
+  long long launches = 0;
+  PixelNorm nrm;
+};
+
+namespace vitatk {
+namespace {
+
+constexpr int LORA_PAD = 64;
+int ksteps_of(int r) { return (r + 15) / 16; }
+
+int swin_dims(const vitatk_swin* e, int s, int* C, int* R) {
+  *C = e->cfg.embed_dim << s;
+  *R = (e->cfg.image_size / e->cfg.patch_size) >> s;
+  return 0;
+}
+
+int build_swin_plans(vitatk_swin* e, int batch, SwinPlans** out) {
+  auto it = e->plans.find(batch);
+  if (it != e->plans.end()) {
+    *out = it->second;
+    return 0;
+  }
+  std::unique_ptr<SwinPlans> owner(new SwinPlans());
+  SwinPlans* ps = owner.get();
+  const vitatk_swin_config& c = e->cfg;
+  GemmEpilogue plain = {};
+  plain.mode = EPI_PLAIN;
+  const int R0 = c.image_size / c.patch_size, C0 = c.embed_dim;
+  const int M0 = batch * R0 * R0;
+  {
+    GemmEpilogue ep = plain;
+    ep.bias = e->patch_b;
+    if (gemm_plan_init(&ps->patch, M0, C0, SW_K, e->cols, SW_K, e->patch_w, SW_K, e->e0, C0, nullptr, 0, nullptr, 0, nullptr, 0, 0, 0,
+                       0, ep))
+      return 1;
+    if (gemm_plan_init(&ps->bpatch, M0, SW_K, C0, e->dxn, C0, e->patch_wt, C0, e->dqkv, SW_K, nullptr, 0, nullptr, 0, nullptr, 0, 0, 0,
+                       0, plain))
+      return 1;
+  }
+  ps->blocks.resize(4);
+  ps->red.resize(3);
+  ps->bred.resize(3);
+  for (int s = 0; s < 4; ++s) {
+    int C, R;
+    swin_dims(e, s, &C, &R);
+    const int M = batch * R * R, F = 4 * C;
+    ps->blocks[s].resize(c.depths[s]);
+    for (int bi = 0; bi < c.depths[s]; ++bi) {
+      BlockW& w = e->blk[s][bi];
+      BlockPlans& p = ps->blocks[s][bi];
+      const BlockW::Lora& sq = w.lora[VITATK_SITE_QKV];
+      const BlockW::Lora& sp = w.lora[VITATK_SITE_PROJ];
+      const BlockW::Lora& s1 = w.lora[VITATK_SITE_FC1];
+      const BlockW::Lora& s2 = w.lora[VITATK_SITE_FC2];
+      bf16* h_out = (bi + 1 < c.depths[s]) ? e->blk[s][bi + 1].h_in : e->sout[s];  // last block of a stage -> stage output
+      auto skinny = [&](GemmPlan* pl, int K, const bf16* A, const bf16* B) {
+        return gemm_plan_init(pl, M, LORA_PAD, K, A, K, B, K, e->T, LORA_PAD, nullptr, 0, nullptr, 0, nullptr, 0, 0, 0, 0, plain);
+      };
+      auto lora_args = [&](const BlockW::Lora& l, const bf16* LB, int* nkb, int* ks) {
+        *nkb = l.rank > 0 ? 1 : 0;
+        *ks = ksteps_of(l.rank);
+        return l.rank > 0 ? LB : nullptr;
+      };
+      int nkb, ks;
+      // ---- forward ----
+      if (sq.rank > 0 && skinny(&p.t_qkv, C, e->xn, sq.la_fwd)) return 1;
+      {
+        GemmEpilogue ep = plain;
+        ep.bias = w.qkv_b;
+        const bf16* LB = lora_args(sq, sq.lb_fwd, &nkb, &ks);
+        if (gemm_plan_init(&p.qkv, M, 3 * C, C, e->xn, C, w.qkv_w, C, w.qkv, 3 * C, nullptr, 0, e->T, LORA_PAD, LB, LORA_PAD, nkb, ks,
+                           0, ep))
+          return 1;
+      }
+      if (sp.rank > 0 && skinny(&p.t_proj, C, w.ao, sp.la_fwd)) return 1;
+      {
+        GemmEpilogue ep = {EPI_RESIDUAL, w.proj_b, w.h_in, C, nullptr, 0};
+        const bf16* LB = lora_args(sp, sp.lb_fwd, &nkb, &ks);
+        if (gemm_plan_init(&p.proj, M, C, C, w.ao, C, w.proj_w, C, w.h_mid, C, nullptr, 0, e->T, LORA_PAD, LB, LORA_PAD, nkb, ks, 0, ep))
+          return 1;
+      }
+      if (s1.rank > 0 && skinny(&p.t_fc1, C, e->xn, s1.la_fwd)) return 1;
+      {
+        GemmEpilogue ep = plain;
+        ep.mode = EPI_GELU_DUAL;
+        ep.bias = w.fc1_b;
+        const bf16* LB = lora_args(s1, s1.lb_fwd, &nkb, &ks);
+        if (gemm_plan_init(&p.fc1, M, F, C, e->xn, C, w.fc1_w, C, e->g, F, w.u, F, e->T, LORA_PAD, LB, LORA_PAD, nkb, ks, 0, ep)) return 1;
+      }
+      if (s2.rank > 0 && skinny(&p.t_fc2, F, e->g, s2.la_fwd)) return 1;
+      {
+        GemmEpilogue ep = {EPI_RESIDUAL, w.fc2_b, w.h_mid, C, nullptr, 0};
+        const bf16* LB = lora_args(s2, s2.lb_fwd, &nkb, &ks);
+        if (gemm_plan_init(&p.fc2, M, C, F, e->g, F, w.fc2_w, F, h_out, C, nullptr, 0, e->T, LORA_PAD, LB, LORA_PAD, nkb, ks, 0, ep))
+          return 1;
+      }
+      // ---- backward (gradient wrt the block output arrives in dA; dB holds the mid-block gradient) ----
+      if (s2.rank > 0 && skinny(&p.bt_fc2, C, e->dA, s2.lb_bwd)) return 1;
+      {
+        GemmEpilogue ep = {EPI_MUL, nullptr, w.u, F, nullptr, 0};
+        const bf16* LB = lora_args(s2, s2.la_bwd, &nkb, &ks);
+        if (gemm_plan_init(&p.bfc2, M, F, C, e->dA, C, w.fc2_wt, C, e->du, F, nullptr, 0, e->T, LORA_PAD, LB, LORA_PAD, nkb, ks, 0, ep))
+          return 1;
+      }
+      if (s1.rank > 0 && skinny(&p.bt_fc1, F, e->du, s1.lb_bwd)) return 1;
+      {
+        const bf16* LB = lora_args(s1, s1.la_bwd, &nkb, &ks);
+        if (gemm_plan_init(&p.bfc1, M, C, F, e->du, F, w.fc1_wt, F, e->dxn, C, nullptr, 0, e->T, LORA_PAD, LB, LORA_PAD, nkb, ks, 0,
+                           plain))
+          return 1;
+      }
+      if (sp.rank > 0 && skinny(&p.bt_proj, C, e->dB, sp.lb_bwd)) return 1;
+      {
+        const bf16* LB = lora_args(sp, sp.la_bwd, &nkb, &ks);
+        if (gemm_plan_init(&p.bproj, M, C, C, e->dB, C, w.proj_wt, C, e->dao, C, nullptr, 0, e->T, LORA_PAD, LB, LORA_PAD, nkb, ks, 0,
+                           plain))
+          return 1;
+      }
+      if (sq.rank > 0 && skinny(&p.bt_qkv, 3 * C, e->dqkv, sq.lb_bwd)) return 1;
+      {
+        const bf16* LB = lora_args(sq, sq.la_bwd, &nkb, &ks);
+        if (gemm_plan_init(&p.bqkv, M, C, 3 * C, e->dqkv, 3 * C, w.qkv_wt, 3 * C, e->dxn, C, nullptr, 0, e->T, LORA_PAD, LB, LORA_PAD, nkb,
+                           ks, 0, plain))
+          return 1;
+      }
+    }
+    if (s < 3) {  // patch merging: [M/4, 4C] -> LN -> [M/4, 2C]
+      const int M4 = M / 4;
+      if (gemm_plan_init(&ps->red[s], M4, 2 * C, 4 * C, e->xn, 4 * C, e->stg[s].m_w, 4 * C, e->blk[s + 1][0].h_in, 2 * C, nullptr, 0,
+                         nullptr, 0, nullptr, 0, 0, 0, 0, plain))
+        return 1;
+      if (gemm_plan_init(&ps->bred[s], M4, 4 * C, 2 * C, e->dA, 2 * C, e->stg[s].m_wt, 2 * C, e->dxn, 4 * C, nullptr, 0, nullptr, 0,
+                         nullptr, 0, 0, 0, 0, plain))
+        return 1;
+    }
+  }
+  e->plans[batch] = owner.release();
+  *out = ps;
+  return 0;
+}
+
+#define SRUN(expr)         \
+  do {                     \
+    if (expr) return 1;    \
+    ++e->launches;         \
+  } while (0)
+#define SGEMM(plan) SRUN(gemm_launch((plan), s, e->num_sms))
+
+// forward from e->cols (normalised im2col of the input) to the last stage's output in e->hfin
+int swin_forward(vitatk_swin* e, SwinPlans* ps, int batch, cudaStream_t s) {
+  const vitatk_swin_config& c = e->cfg;
+  const int R0 = c.image_size / c.patch_size, C0 = c.embed_dim;
+  SGEMM(&ps->patch);
+  SRUN(ln_any_fwd(e->e0, e->eln_g, e->eln_b, e->blk[0][0].h_in, e->st_e, batch * R0 * R0, C0, c.ln_eps, s));
+  for (int st = 0; st < 4; ++st) {
+    int C, R;
+    swin_dims(e, st, &C, &R);
+    const int M = batch * R * R, heads = c.heads[st];
+    for (int bi = 0; bi < c.depths[st]; ++bi) {
+      BlockW& w = e->blk[st][bi];
+      BlockPlans& p = ps->blocks[st][bi];
+      const int shift = (bi % 2 == 1 && R > c.window) ? c.window / 2 : 0;
+      SRUN(ln_any_fwd(w.h_in, w.ln1_g, w.ln1_b, e->xn, w.st1, M, C, c.ln_eps, s));
+      if (w.lora[VITATK_SITE_QKV].rank > 0) SGEMM(&p.t_qkv);
+      SGEMM(&p.qkv);
+      SRUN(win_attn_fwd(w.qkv, w.relbias, w.ao, batch, R, C, heads, shift, s));
+      if (w.lora[VITATK_SITE_PROJ].rank > 0) SGEMM(&p.t_proj);
+      SGEMM(&p.proj);
+      SRUN(ln_any_fwd(w.h_mid, w.ln2_g, w.ln2_b, e->xn, w.st2, M, C, c.ln_eps, s));
+      if (w.lora[VITATK_SITE_FC1].rank > 0) SGEMM(&p.t_fc1);
+      SGEMM(&p.fc1);
+      if (w.lora[VITATK_SITE_FC2].rank > 0) SGEMM(&p.t_fc2);
+      SGEMM(&p.fc2);
+    }
+    if (st < 3) {
+      SRUN(merge_permute(e->sout[st], e->xm, batch, R, C, 0, s));
+      SRUN(ln_any_fwd(e->xm, e->stg[st].mln_g, e->stg[st].mln_b, e->xn, e->stg[st].stm, M / 4, 4 * C, c.ln_eps, s));
+      SGEMM(&ps->red[st]);
+    }
+  }
+  return 0;
+}
+
+// backward from dA = d loss / d (last stage output) down to e->dqkv = d loss / d cols
+int swin_backward(vitatk_swin* e, SwinPlans* ps, int batch, cudaStream_t s) {
+  const vitatk_swin_config& c = e->cfg;
+  const int R0 = c.image_size / c.patch_size, C0 = c.embed_dim;
+  for (int st = 3; st >= 0; --st) {
+    int C, R;
+    swin_dims(e, st, &C, &R);
+    const int M = batch * R * R, heads = c.heads[st];
+    if (st < 3) {
+      // dA holds the gradient wrt the NEXT stage's input [M/4, 2C]: back through reduction, LayerNorm and the 2x2 gather
+      SGEMM(&ps->bred[st]);                                                          // dxn [M/4, 4C]
+      SRUN(merge_permute(e->sout[st], e->xm, batch, R, C, 0, s));                    // the LayerNorm's input, re-gathered
+      SRUN(ln_any_bwd(e->dxn, e->xm, e->stg[st].stm, e->stg[st].mln_g, nullptr, e->du, M / 4, 4 * C, s));
+      SRUN(merge_permute(e->du, e->dA, batch, R, C, 1, s));                          // dA [M, C]
+    }
+    for (int bi = c.depths[st] - 1; bi >= 0; --bi) {
+      BlockW& w = e->blk[st][bi];
+      BlockPlans& p = ps->blocks[st][bi];
+      const int shift = (bi % 2 == 1 && R > c.window) ? c.window / 2 : 0;
+      if (w.lora[VITATK_SITE_FC2].rank > 0) SGEMM(&p.bt_fc2);
+      SGEMM(&p.bfc2);
+      if (w.lora[VITATK_SITE_FC1].rank > 0) SGEMM(&p.bt_fc1);
+      SGEMM(&p.bfc1);
+      SRUN(ln_any_bwd(e->dxn, w.h_mid, w.st2, w.ln2_g, e->dA, e->dB, M, C, s));
+      if (w.lora[VITATK_SITE_PROJ].rank > 0) SGEMM(&p.bt_proj);
+      SGEMM(&p.bproj);
+      SRUN(win_attn_bwd(w.qkv, e->dao, w.relbias, e->dqkv, batch, R, C, heads, shift, s));
+      if (w.lora[VITATK_SITE_QKV].rank > 0) SGEMM(&p.bt_qkv);
+      SGEMM(&p.bqkv);
+      SRUN(ln_any_bwd(e->dxn, w.h_in, w.st1, w.ln1_g, e->dB, e->dA, M, C, s));
+    }
+  }
+  SRUN(ln_any_bwd(e->dA, e->e0, e->st_e, e->eln_g, nullptr, e->dxn, batch * R0 * R0, C0, s));
+  SGEMM(&ps->bpatch);  // e->dqkv <- d loss / d cols  [M0, 64]
+  return 0;
+}
+
+int swin_pixels(vitatk_swin* e, int mode, const float* x0, const float* noise, float* adv, float* grad, int batch, float eps,
+                float alpha, int use_rng, uint64_t seed, uint64_t index0, float gscale, cudaStream_t s) {
+  const long long total = static_cast<long long>(batch) * 3 * IMG * (IMG / 4);
+  swin_pixel_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(mode, x0, noise, adv, e->cols, e->dqkv, grad, batch,
+                                                                               e->nrm, eps, alpha, use_rng, seed, index0, gscale);
+  VITATK_CUDA_OK(cudaGetLastError());
+  ++e->launches;
+  return 0;
+}
+
+int swin_head(vitatk_swin* e, const int64_t* labels, float* logits, float* loss, bf16* dh, int batch, float gscale, cudaStream_t s) {
+  const vitatk_swin_config& c = e->cfg;
+  const int C = c.embed_dim << 3, R = (c.image_size / c.patch_size) >> 3;
+  const int tokens = R * R;
+  const size_t smem = (2 * C + c.num_classes + 2 * tokens) * sizeof(float);
+  swin_head_kernel<<<batch, 256, smem, s>>>(e->sout[3], e->fln_g, e->fln_b, e->head_w, e->head_b, labels, logits, loss, dh, tokens, C,
+                                            c.num_classes, c.ln_eps, gscale);
+  VITATK_CUDA_OK(cudaGetLastError());
+  ++e->launches;
+  return 0;
+}
+
+int swin_check(vitatk_swin* e, int batch) {
+  if (!e || !e->finalized) {
+    set_error("swin engine not finalized");
+    return 1;
+  }
+  if (batch < 1 || batch > e->cfg.max_batch) {
+    set_error("batch %d outside [1, max_batch=%d]", batch, e->cfg.max_batch);
+    return 1;
+  }
+  return 0;
+}
+
+}  // namespace
+}  // namespace vitatk
+
+extern "C" {
+
+int vitatk_swin_create(const vitatk_swin_config* cfg, vitatk_swin** out) {
+  if (!cfg || !out) {
+    set_error("vitatk_swin_create: null argument");
+    return 1;
+  }
+  bool ok = cfg->image_size == 224 && cfg->patch_size == 4 && cfg->window == 7 && cfg->embed_dim % 64 == 0 && cfg->num_classes >= 1 &&
+            cfg->max_batch >= 1;
+  for (int s = 0; s < 4 && ok; ++s) ok = cfg->depths[s] >= 1 && cfg->heads[s] * HD == (cfg->embed_dim << s);
+  if (!ok) {
+    set_error("vitatk_swin_create: unsupported geometry (image 224, patch 4, window 7, head dim 32, embed_dim %% 64 == 0)");
+    return 1;
+  }
+  int dev = 0;
+  VITATK_CUDA_OK(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  VITATK_CUDA_OK(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) {
+    set_error("vitatk requires an sm_100a (B200) device; found sm_%d%d. There is no fallback path.", prop.major, prop.minor);
+    return 1;
+  }
+  vitatk_swin* e = new vitatk_swin();
+  e->cfg = *cfg;
+  e->num_sms = prop.multiProcessorCount;
+  e->blk.resize(4);
+  for (int s = 0; s < 4; ++s) e->blk[s].resize(cfg->depths[s]);
+  for (int i = 0; i < 3; ++i) {
+    e->nrm.mean[i] = cfg->mean[i];
+    e->nrm.inv_std[i] = 1.0f / cfg->std[i];
+  }
+  *out = e;
+  return 0;
+}
+
+int vitatk_swin_destroy(vitatk_swin* e) {
+  if (!e) return 0;
+  for (auto& kv : e->plans) delete kv.second;
+  if (e->ws) cudaFree(e->ws);
+  delete e;
+  return 0;
+}
+
+int vitatk_swin_set_tensor(vitatk_swin* e, int id, int stage, int block, const void* p, long long nbytes) {
+  if (!e || !p) {
+    set_error("vitatk_swin_set_tensor: null argument");
+    return 1;
+  }
+  const vitatk_swin_config& c = e->cfg;
+  const float* pf = static_cast<const float*>(p);
+  const bf16* pb = static_cast<const bf16*>(p);
+  long long want = -1;
+  const long long C0 = c.embed_dim, CL = C0 << 3;
+  if (id < 16) {
+    switch (id) {
+      case VITATK_SWIN_PATCH_W: e->patch_w = pb; want = C0 * SW_K * 2; break;
+      case VITATK_SWIN_PATCH_WT: e->patch_wt = pb; want = C0 * SW_K * 2; break;
+      case VITATK_SWIN_PATCH_B: e->patch_b = pf; want = C0 * 4; break;
+      case VITATK_SWIN_EMB_LN_G: e->eln_g = pf; want = C0 * 4; break;
+      case VITATK_SWIN_EMB_LN_B: e->eln_b = pf; want = C0 * 4; break;
+      case VITATK_SWIN_FINAL_LN_G: e->fln_g = pf; want = CL * 4; break;
+      case VITATK_SWIN_FINAL_LN_B: e->fln_b = pf; want = CL * 4; break;
+      case VITATK_SWIN_HEAD_W: e->head_w = pf; want = c.num_classes * CL * 4; break;
+      case VITATK_SWIN_HEAD_B: e->head_b = pf; want = c.num_classes * 4; break;
+      default: break;
+    }
+  } else if (id >= 64) {
+    if (stage < 0 || stage > 2) {
+      set_error("vitatk_swin_set_tensor: merge stage %d out of range", stage);
+      return 1;
+    }
+    const long long C = C0 << stage;
+    StageW& w = e->stg[stage];
+    switch (id) {
+      case VITATK_SWIN_MERGE_LN_G: w.mln_g = pf; want = 4 * C * 4; break;
+      case VITATK_SWIN_MERGE_LN_B: w.mln_b = pf; want = 4 * C * 4; break;
+      case VITATK_SWIN_MERGE_W: w.m_w = pb; want = 2 * C * 4 * C * 2; break;
+      case VITATK_SWIN_MERGE_WT: w.m_wt = pb; want = 2 * C * 4 * C * 2; break;
+      default: break;
+    }
+  } else {
+    if (stage < 0 || stage > 3 || block < 0 || block >= c.depths[stage]) {
+      set_error("vitatk_swin_set_tensor: stage %d block %d out of range", stage, block);
+      return 1;
+    }
+    const long long C = C0 << stage, F = 4 * C;
+    BlockW& w = e->blk[stage][block];
+    switch (id) {
+      case VITATK_SWIN_LN1_G: w.ln1_g = pf; want = C * 4; break;
+      case VITATK_SWIN_LN1_B: w.ln1_b = pf; want = C * 4; break;
+      case VITATK_SWIN_QKV_W: w.qkv_w = pb; want = 3 * C * C * 2; break;
+      case VITATK_SWIN_QKV_WT: w.qkv_wt = pb; want = 3 * C * C * 2; break;
+      case VITATK_SWIN_QKV_B: w.qkv_b = pf; want = 3 * C * 4; break;
+      case VITATK_SWIN_RELBIAS: w.relbias = pf; want = static_cast<long long>(c.heads[stage]) * WT * WT * 4; break;
+      case VITATK_SWIN_PROJ_W: w.proj_w = pb; want = C * C * 2; break;
+      case VITATK_SWIN_PROJ_WT: w.proj_wt = pb; want = C * C * 2; break;
+      case VITATK_SWIN_PROJ_B: w.proj_b = pf; want = C * 4; break;
+      case VITATK_SWIN_LN2_G: w.ln2_g = pf; want = C * 4; break;
+      case VITATK_SWIN_LN2_B: w.ln2_b = pf; want = C * 4; break;
+      case VITATK_SWIN_FC1_W: w.fc1_w = pb; want = F * C * 2; break;
+      case VITATK_SWIN_FC1_WT: w.fc1_wt = pb; want = F * C * 2; break;
+      case VITATK_SWIN_FC1_B: w.fc1_b = pf; want = F * 4; break;
+      case VITATK_SWIN_FC2_W: w.fc2_w = pb; want = F * C * 2; break;
+      case VITATK_SWIN_FC2_WT: w.fc2_wt = pb; want = F * C * 2; break;
+      case VITATK_SWIN_FC2_B: w.fc2_b = pf; want = C * 4; break;
+      default: break;
+    }
+  }
+  if (want < 0) {
+    set_error("vitatk_swin_set_tensor: unknown tensor id %d", id);
+    return 1;
+  }
+  if (nbytes != want) {
+    set_error("vitatk_swin_set_tensor: id %d stage %d block %d expects %lld bytes, got %lld", id, stage, block, want, nbytes);
+    return 1;
+  }
+  for (auto& kv : e->plans) delete kv.second;
+  e->plans.clear();
+  return 0;
+}
+
+int vitatk_swin_set_lora(vitatk_swin* e, int stage, int block, int site, int rank, const void* la_fwd, const void* lb_fwd,
+                         const void* lb_bwd, const void* la_bwd) {
+  if (!e || stage < 0 || stage > 3 || block < 0 || block >= e->cfg.depths[stage] || site < 0 || site > 3 || rank < 0 ||
+      rank > LORA_PAD || (rank > 0 && (!la_fwd || !lb_fwd || !lb_bwd || !la_bwd))) {
+    set_error("vitatk_swin_set_lora: bad arguments");
+    return 1;
+  }
+  BlockW::Lora& l = e->blk[stage][block].lora[site];
+  l.rank = rank;
+  l.la_fwd = static_cast<const bf16*>(la_fwd);
+  l.lb_fwd = static_cast<const bf16*>(lb_fwd);
+  l.lb_bwd = static_cast<const bf16*>(lb_bwd);
+  l.la_bwd = static_cast<const bf16*>(la_bwd);
+  for (auto& kv : e->plans) delete kv.second;
+  e->plans.clear();
+  return 0;
+}
+
+int vitatk_swin_finalize(vitatk_swin* e) {
+  if (!e) {
+    set_error("vitatk_swin_finalize: null engine");
+    return 1;
+  }
+  if (e->finalized) return 0;
+  const vitatk_swin_config& c = e->cfg;
+  bool ok = e->patch_w && e->patch_wt && e->patch_b && e->eln_g && e->eln_b && e->fln_g && e->fln_b && e->head_w && e->head_b;
+  for (int s = 0; s < 4 && ok; ++s) {
+    for (const BlockW& w : e->blk[s])
+      ok = ok && w.ln1_g && w.ln1_b && w.ln2_g && w.ln2_b && w.qkv_w && w.qkv_wt && w.qkv_b && w.relbias && w.proj_w && w.proj_wt &&
+           w.proj_b && w.fc1_w && w.fc1_wt && w.fc1_b && w.fc2_w && w.fc2_wt && w.fc2_b;
+    if (s < 3) ok = ok && e->stg[s].mln_g && e->stg[s].mln_b && e->stg[s].m_w && e->stg[s].m_wt;
+  }
+  if (!ok) {
+    set_error("vitatk_swin_finalize: a tensor is missing");
+    return 1;
+  }
+  auto al = [](long long b) { return (b + 1023) / 1024 * 1024; };
+  const long long B = c.max_batch;
+  const int R0 = c.image_size / c.patch_size;
+  const long long M0 = B * R0 * R0, C0 = c.embed_dim;
+  // per-stage token counts and widths; M * C is the same (M0 * C0 / 2^s) ... sizes below use stage 0 as the maximum
+  long long total = 0;
+  for (int s = 0; s < 4; ++s) {
+    const long long M = M0 >> (2 * s), C = C0 << s;
+    total += c.depths[s] * (al(M * C * 2) * 3 + al(M * 3 * C * 2) + al(M * 4 * C * 2) + 2 * al(M * 8));
+    if (s < 3) total += al((M / 4) * 8);
+  }
+  const long long szC = al(M0 * C0 * 2), sz3 = al(M0 * 3 * C0 * 2), sz4 = al(M0 * 4 * C0 * 2);
+  const long long sz_img = al(B * 3 * IMG * IMG * 4);
+  total += al(M0 * SW_K * 2) + szC /*e0*/ + sz4 /*xn (also [M/4, 4C] rows)*/ + sz4 /*g*/ + al(M0 * LORA_PAD * 2) /*T*/ +
+           3 * szC /*dA dB dao*/ + 2 * szC /*stage outputs: M C halves per stage*/ + sz4 /*dxn (also [M/4, 4C])*/ + sz4 /*du*/ + sz3 /*dqkv*/ + sz4 /*xm*/ + al(M0 * 8) /*st_e*/ +
+           al(B * c.num_classes * 4) + al(B * 4) + sz_img;
+  VITATK_CUDA_OK(cudaMalloc(&e->ws, total));
+  VITATK_CUDA_OK(cudaMemset(e->ws, 0, total));
+  e->ws_bytes = total;
+  char* p = e->ws;
+  auto take = [&](long long b) {
+    char* r = p;
+    p += al(b);
+    return r;
+  };
+  for (int s = 0; s < 4; ++s) {
+    const long long M = M0 >> (2 * s), C = C0 << s;
+    for (BlockW& w : e->blk[s]) {
+      w.h_in = reinterpret_cast<bf16*>(take(M * C * 2));
+      w.ao = reinterpret_cast<bf16*>(take(M * C * 2));
+      w.h_mid = reinterpret_cast<bf16*>(take(M * C * 2));
+      w.qkv = reinterpret_cast<bf16*>(take(M * 3 * C * 2));
+      w.u = reinterpret_cast<bf16*>(take(M * 4 * C * 2));
+      w.st1 = reinterpret_cast<float2*>(take(M * 8));
+      w.st2 = reinterpret_cast<float2*>(take(M * 8));
+    }
+    if (s < 3) e->stg[s].stm = reinterpret_cast<float2*>(take((M / 4) * 8));
+  }
+  e->cols = reinterpret_cast<bf16*>(take(M0 * SW_K * 2));
+  e->e0 = reinterpret_cast<bf16*>(take(M0 * C0 * 2));
+  e->xn = reinterpret_cast<bf16*>(take(M0 * 4 * C0 * 2));
+  e->g = reinterpret_cast<bf16*>(take(M0 * 4 * C0 * 2));
+  e->T = reinterpret_cast<bf16*>(take(M0 * LORA_PAD * 2));
+  e->dA = reinterpret_cast<bf16*>(take(M0 * C0 * 2));
+  e->dB = reinterpret_cast<bf16*>(take(M0 * C0 * 2));
+  e->dao = reinterpret_cast<bf16*>(take(M0 * C0 * 2));
+  for (int s = 0; s < 4; ++s) e->sout[s] = reinterpret_cast<bf16*>(take((M0 * C0 * 2) >> s));
+  e->dxn = reinterpret_cast<bf16*>(take(M0 * 4 * C0 * 2));
+  e->du = reinterpret_cast<bf16*>(take(M0 * 4 * C0 * 2));
+  e->dqkv = reinterpret_cast<bf16*>(take(M0 * 3 * C0 * 2));
+  e->xm = reinterpret_cast<bf16*>(take(M0 * 4 * C0 * 2));
+  e->st_e = reinterpret_cast<float2*>(take(M0 * 8));
+  e->logits = reinterpret_cast<float*>(take(B * c.num_classes * 4));
+  e->loss = reinterpret_cast<float*>(take(B * 4));
+  e->scratch_img = reinterpret_cast<float*>(take(B * 3 * IMG * IMG * 4));
+  e->finalized = true;
+  return 0;
+}
+
+long long vitatk_swin_workspace_bytes(const vitatk_swin* e) { return e ? e->ws_bytes : 0; }
+long long vitatk_swin_launch_count(const vitatk_swin* e) { return e ? e->launches : 0; }
+
+int vitatk_swin_set_normalization(vitatk_swin* e, const float* mean3, const float* std3) {
+  if (!e || !mean3 || !std3) {
+    set_error("vitatk_swin_set_normalization: null argument");
+    return 1;
+  }
+  for (int i = 0; i < 3; ++i) {
+    if (!(std3[i] > 0.f)) {
+      set_error("vitatk_swin_set_normalization: std[%d] must be > 0", i);
+      return 1;
+    }
+    e->nrm.mean[i] = mean3[i];
+    e->nrm.inv_std[i] = 1.0f / std3[i];
+  }
+  return 0;
+}
+
+int vitatk_swin_forward(vitatk_swin* e, const float* images, int batch, float* logits_out, void* stream) {
+  if (swin_check(e, batch)) return 1;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  SwinPlans* ps = nullptr;
+  if (build_swin_plans(e, batch, &ps)) return 1;
+  if (swin_pixels(e, 0, images, nullptr, e->scratch_img, nullptr, batch, 0.f, 0.f, 0, 0, 0, 0.f, s)) return 1;
+  if (swin_forward(e, ps, batch, s)) return 1;
+  return swin_head(e, nullptr, logits_out, nullptr, nullptr, batch, 0.f, s);
+}
+
+int vitatk_swin_input_grad(vitatk_swin* e, const float* images, const int64_t* labels, int batch, float* grad_out, float* logits_out,
+                           float* loss_out, void* stream) {
+  if (swin_check(e, batch)) return 1;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  SwinPlans* ps = nullptr;
+  if (build_swin_plans(e, batch, &ps)) return 1;
+  if (swin_pixels(e, 0, images, nullptr, e->scratch_img, nullptr, batch, 0.f, 0.f, 0, 0, 0, 0.f, s)) return 1;
+  if (swin_forward(e, ps, batch, s)) return 1;
+  if (swin_head(e, labels, logits_out ? logits_out : e->logits, loss_out ? loss_out : e->loss, e->dA, batch, 1.0f, s)) return 1;
+  if (swin_backward(e, ps, batch, s)) return 1;
+  return swin_pixels(e, 2, images, nullptr, nullptr, grad_out, batch, 0.f, 0.f, 0, 0, 0, 1.0f / batch, s);
+}
+
+int vitatk_swin_attack(vitatk_swin* e, const float* images, const int64_t* labels, int batch, float eps, float alpha, int steps,
+                       int start, const float* noise, uint64_t seed, uint64_t image_index0, float* adv, void* stream) {
+  if (swin_check(e, batch)) return 1;
+  if (steps < 1 || !images || !labels || !adv || images == adv || (start == VITATK_START_NOISE && !noise)) {
+    set_error("vitatk_swin_attack: bad arguments");
+    return 1;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  SwinPlans* ps = nullptr;
+  if (build_swin_plans(e, batch, &ps)) return 1;
+  if (swin_pixels(e, 0, images, start == VITATK_START_NOISE ? noise : nullptr, adv, nullptr, batch, eps, 0.f,
+                  start == VITATK_START_RNG ? 1 : 0, seed, image_index0, 0.f, s))
+    return 1;
+  for (int it = 0; it < steps; ++it) {
+    if (swin_forward(e, ps, batch, s)) return 1;
+    if (swin_head(e, labels, e->logits, e->loss, e->dA, batch, 1.0f, s)) return 1;
+    if (swin_backward(e, ps, batch, s)) return 1;
+    if (swin_pixels(e, 1, images, nullptr, adv, nullptr, batch, eps, alpha, 0, 0, 0, 0.f, s)) return 1;
+  }
+  return 0;
+}
+
+int vitatk_swin_count_correct(vitatk_swin* e, const float* images, const int64_t* labels, int batch, long long* counts, void* stream) {
+  if (swin_check(e, batch)) return 1;
+  if (!images || !labels || !counts) {
+    set_error("vitatk_swin_count_correct: null argument");
+    return 1;
+  }
+  if (vitatk_swin_forward(e, images, batch, e->logits, stream)) return 1;
+  ++e->launches;
+  return count_correct(e->logits, labels, batch, e->cfg.num_classes, counts, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

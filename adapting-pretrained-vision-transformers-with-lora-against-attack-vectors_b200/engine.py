@@ -39,7 +39,7 @@ Adapter = Tuple[torch.Tensor, torch.Tensor, float]  # (A [r,in], B [out,r], scal
 
 def _strip(name: str) -> str:
     """Remove wrapper prefixes (LogitsModel.model, peft base_model.model, DDP module) from a key."""
-    while not (name.startswith("vit.") or name.startswith("classifier.")):
+    while not (name.startswith("vit.") or name.startswith("swin.") or name.startswith("classifier.")):
         for pre in ("base_model.", "model.", "module."):
             if name.startswith(pre):
                 name = name[len(pre):]

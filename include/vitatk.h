@@ -215,6 +215,51 @@ int vitatk_patch_apply(const float* images_dev, int batch, int T, const float* t
 int vitatk_patch_update(float* patch_dev, const float* grad_dev, float* m_dev, float* v_dev, int n, float lr, int maximize,
                         int adam_step, float beta1, float beta2, float eps, void* stream);
 
+/* ---- Swin Transformer (shifted-window attention; SURVEY 8(f)-4a, BASELINE configs[2]) ----
+ * Same attack surface as the ViT engine for HF SwinForImageClassification (swin-base-patch4-window7-224 geometry: image
+ * 224, patch 4, window 7, head dim 32, four stages of width embed_dim * 2^s): forward, input gradient, FGSM / PGD,
+ * top-1 counts.  Every Linear runs on the same tcgen05 GEMM with the same LoRA layouts as vitatk_set_lora (q|k|v packed
+ * into one 64-column group: VITATK_SITE_QKV here always means the packed layout); window attention, patch merging, the
+ * pooled head and the 4x4 patch-embedding pixel kernels are in csrc/swin.cu.  Tensors are bf16 [out, in] (+ transposed
+ * copy) for weights and fp32 for everything else, as for the ViT engine; RELBIAS is the relative-position bias already
+ * gathered to [heads, 49, 49] (relative_position_bias_table[relative_position_index]); PATCH_W is the conv weight
+ * [embed_dim, 3*4*4] zero-padded to 64 columns (PATCH_WT its [64, embed_dim] transpose). */
+typedef struct vitatk_swin vitatk_swin;
+typedef struct {
+  int image_size, patch_size, embed_dim, window;
+  int depths[4], heads[4];
+  int num_classes, max_batch;
+  float ln_eps;
+  float mean[3], std[3];
+} vitatk_swin_config;
+enum vitatk_swin_tensor_id {
+  VITATK_SWIN_PATCH_W = 0, VITATK_SWIN_PATCH_WT = 1, VITATK_SWIN_PATCH_B = 2, VITATK_SWIN_EMB_LN_G = 3, VITATK_SWIN_EMB_LN_B = 4,
+  VITATK_SWIN_FINAL_LN_G = 5, VITATK_SWIN_FINAL_LN_B = 6, VITATK_SWIN_HEAD_W = 7, VITATK_SWIN_HEAD_B = 8,
+  /* per (stage, block) */
+  VITATK_SWIN_LN1_G = 16, VITATK_SWIN_LN1_B, VITATK_SWIN_QKV_W, VITATK_SWIN_QKV_WT, VITATK_SWIN_QKV_B, VITATK_SWIN_RELBIAS,
+  VITATK_SWIN_PROJ_W, VITATK_SWIN_PROJ_WT, VITATK_SWIN_PROJ_B, VITATK_SWIN_LN2_G, VITATK_SWIN_LN2_B, VITATK_SWIN_FC1_W,
+  VITATK_SWIN_FC1_WT, VITATK_SWIN_FC1_B, VITATK_SWIN_FC2_W, VITATK_SWIN_FC2_WT, VITATK_SWIN_FC2_B,
+  /* per stage 0..2: patch merging (LayerNorm over 4C, reduction Linear 4C -> 2C without bias) */
+  VITATK_SWIN_MERGE_LN_G = 64, VITATK_SWIN_MERGE_LN_B, VITATK_SWIN_MERGE_W, VITATK_SWIN_MERGE_WT
+};
+int vitatk_swin_create(const vitatk_swin_config* cfg, vitatk_swin** out);
+int vitatk_swin_destroy(vitatk_swin* e);
+int vitatk_swin_set_tensor(vitatk_swin* e, int tensor_id, int stage, int block, const void* dev_ptr, long long nbytes);
+int vitatk_swin_set_lora(vitatk_swin* e, int stage, int block, int site, int rank, const void* la_fwd_dev, const void* lb_fwd_dev,
+                         const void* lb_bwd_dev, const void* la_bwd_dev);
+int vitatk_swin_set_normalization(vitatk_swin* e, const float* mean3, const float* std3);
+int vitatk_swin_finalize(vitatk_swin* e);
+long long vitatk_swin_workspace_bytes(const vitatk_swin* e);
+long long vitatk_swin_launch_count(const vitatk_swin* e);
+int vitatk_swin_forward(vitatk_swin* e, const float* images_dev, int batch, float* logits_dev, void* stream);
+int vitatk_swin_input_grad(vitatk_swin* e, const float* images_dev, const int64_t* labels_dev, int batch, float* grad_dev,
+                           float* logits_dev, float* loss_dev, void* stream);
+int vitatk_swin_attack(vitatk_swin* e, const float* images_dev, const int64_t* labels_dev, int batch, float eps, float alpha,
+                       int steps, int start, const float* noise_dev, uint64_t seed, uint64_t image_index0, float* adv_dev,
+                       void* stream);
+int vitatk_swin_count_correct(vitatk_swin* e, const float* images_dev, const int64_t* labels_dev, int batch, long long* counts_dev,
+                              void* stream);
+
 /* ---- kernel-level entry points (used by tests/ and bench.py's roofline leg) ----
  * vitatk_k_gemm with tt_n in {32, 64}: "T-tile" mode of the pair kernel -- the GEMM computes T = A * tt_tb^T (tt_tb bf16
  * [64, K], + tt_bias[64] if given) itself, writes it to T_dev and uses it as its LoRA k-block in the same launch;

@@ -72,6 +72,34 @@ def build_model(num_labels: int = 21, seed: int = 0, perturb: bool = True) -> nn
     return model
 
 
+def build_swin(num_labels: int = 21, seed: int = 0, perturb: bool = True) -> nn.Module:
+    """HF SwinForImageClassification with the swin-base-patch4-window7-224 geometry (README.md:53 names the family; no
+    reference script builds it), random init.  ``perturb`` also randomises what HF initialises to constants: biases,
+    LayerNorm affines and the relative-position bias tables (zero in HF, which would hide every bias-table bug)."""
+    from transformers import SwinConfig, SwinForImageClassification
+
+    torch.manual_seed(seed)
+    cfg = SwinConfig(image_size=224, patch_size=4, embed_dim=128, depths=[2, 2, 18, 2], num_heads=[4, 8, 16, 32],
+                     window_size=7, num_labels=num_labels)
+    model = SwinForImageClassification(cfg)
+    if perturb:
+        g = torch.Generator().manual_seed(seed + 1000)
+        with torch.no_grad():
+            for name, p in model.named_parameters():
+                if "relative_position_bias_table" in name:
+                    p.copy_(torch.randn(p.shape, generator=g) * 0.5)
+                elif name.endswith("bias") and "norm" not in name:
+                    p.copy_(torch.randn(p.shape, generator=g) * 0.02)
+                elif "norm" in name and name.endswith("weight"):
+                    p.copy_(1.0 + torch.randn(p.shape, generator=g) * 0.1)
+                elif "norm" in name and name.endswith("bias"):
+                    p.copy_(torch.randn(p.shape, generator=g) * 0.05)
+    model.eval()
+    for p in model.parameters():
+        p.requires_grad_(False)
+    return model
+
+
 class LoraLinear(nn.Module):
     """y = base(x) + scale * B(A(dropout(x))), dropout == identity in eval.
 
@@ -108,7 +136,8 @@ def attach_lora(model: nn.Module, r: int = 8, alpha: float = 16.0,
     g = torch.Generator().manual_seed(seed + 2000)
     todo = []
     for name, mod in model.named_modules():
-        if isinstance(mod, nn.Linear) and name.startswith("vit.encoder") and _matches(name, targets):
+        if isinstance(mod, nn.Linear) and name.startswith(("vit.encoder", "swin.encoder")) and _matches(name, targets) \
+                and ".downsample." not in name:
             todo.append(name)
     for name in todo:
         parent_name, _, child = name.rpartition(".")

@@ -26,6 +26,7 @@ from .attacks import (  # noqa: E402,F401
 )
 from .engine import Engine  # noqa: E402,F401
 from .patch import AdversarialPatch, sample_transforms  # noqa: E402,F401
+from .swin import SwinEngine  # noqa: E402,F401
 from .training import LoraTrainer, average_gradients, init_adapters  # noqa: E402,F401
 from .adapters import (  # noqa: E402,F401
     PeftAdapter,

@@ -679,6 +679,133 @@ def run_config5(args):
 
 
 # ---------------------------------------------------------------------------------------------------------
+# config 3: PGD-20 on LoRA Swin-B (shifted-window attention), batch 128 per GPU (BASELINE configs[2])
+# ---------------------------------------------------------------------------------------------------------
+def swin_gflop_per_image_step(r=RANK_R):
+    """Dense-contraction FLOPs of one PGD step (forward + input-gradient backward) of Swin-B for one image."""
+    C0, depths, R0 = 128, (2, 2, 18, 2), 56
+    fwd = 2 * R0 * R0 * 48 * C0
+    for s, d in enumerate(depths):
+        C, T = C0 << s, (R0 >> s) ** 2
+        lin = 2 * T * (3 * C * C + C * C + 8 * C * C)
+        att = 4 * T * 49 * C
+        lora = 2 * T * r * (6 * C + 2 * C + 5 * C + 5 * C)
+        fwd += d * (lin + att + lora)
+        if s < 3:
+            fwd += 2 * (T // 4) * 4 * C * 2 * C
+    return 2 * fwd / 1e9 + sum(d * 4 * ((R0 >> s) ** 2) * 49 * (C0 << s) for s, d in enumerate(depths)) / 1e9  # attention bwd = 2x fwd
+
+
+def run_config3(args):
+    out = StdoutToStderr()
+    import torch
+    import torch.distributed as dist
+
+    import vitatk
+    from oracle import vit_oracle as vo   # model construction only (HF SwinForImageClassification, random init); never timed
+    from vitatk.dist import allreduce_counts
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, K = 128, 20
+    idx0 = rank * B
+    model = vo.build_swin(num_labels=CLASSES, seed=0)
+    vo.attach_lora(model, r=RANK_R, alpha=16.0, targets=vo.ALL_TARGETS, seed=0, b_std=0.02)
+    eng = vitatk.SwinEngine(model=model, max_batch=B, device=dev)
+    from vitatk import synthetic
+    x_host, y_host = synthetic.images_and_labels(B, idx0, CLASSES, seed=0, pin=True)
+    x, y = x_host.to(dev), y_host.to(dev)
+    adv = torch.empty_like(x)
+    adv_host = torch.empty_like(x_host).pin_memory()
+
+    def step(i):
+        eng.attack(x, y, EPS, ALPHA, K, start="rng", seed=1234 + i, image_index0=idx0, out=adv)
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    launches = eng.launch_count - l0
+    clocks = sampler.stop() if rank == 0 else None
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    f0.record()
+    for i in range(args.steps):
+        x.copy_(x_host, non_blocking=True)
+        y.copy_(y_host, non_blocking=True)
+        step(i)
+        adv_host.copy_(adv, non_blocking=True)
+    f1.record()
+    sync_all()
+    ms_e2e = f0.elapsed_time(f1)
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    y_clean = eng.logits(x).argmax(-1)
+    eng.attack(x, y_clean, EPS, ALPHA, K, start="rng", seed=99, image_index0=idx0, out=adv)
+    c, r = eng.count_correct(x, y_clean), eng.count_correct(adv, y_clean)
+    counts = allreduce_counts(torch.stack([c[0], r[0], c[1]]))
+    linf = float((adv - x).abs().max())
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+    peaks, peaks_kind = measured_peaks()
+    imgs = B * world * args.steps
+    value = imgs / (ms / 1e3)
+    peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
+    gflop = swin_gflop_per_image_step() * K
+    line = {
+        "metric": "PGD-20 adv images/sec, LoRA Swin-B (shifted-window attention) bs128 per GPU (BASELINE configs[2])",
+        "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "PGD-20 eps=8/255 alpha=2/255 random-start on LoRA(r=8; q,k,v,proj,fc1,fc2) Swin-B "
+                               "(patch 4, window 7, depths 2-2-18-2), 21 classes, batch 128 per GPU, 224x224 (BASELINE configs[2])",
+                   "global_batch": B * world, "parallelism": f"dp{world} (independent images, no data-path collective)",
+                   "l2": "inputs larger than L2 (77 MB images, ~8 GB activations per step)"},
+        "clocks": clocks,
+        "e2e": {"value": imgs / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8,
+                "d2h_bytes_per_step": adv_host.numel() * 4},
+        "gpu_launches": launches,
+        "roofline": {"bound": "tensor", "achieved": value / world * gflop / 1e3, "peak": peak, "unit": "TFLOP/s",
+                     "frac": value / world * gflop / 1e3 / peak, "traffic": None,
+                     "note": "whole-step algorithmic FLOPs / time; the 7x7-window attention runs on CUDA cores (first version)",
+                     "peak_kind": f"{peaks_kind} sustained cuBLAS bf16"},
+        "robust": {"clean_correct": int(counts[0]), "robust_correct": int(counts[1]), "total": int(counts[2]), "linf": linf,
+                   "eps_f32": float(torch.tensor(EPS, dtype=torch.float32))},
+    }
+    out.emit(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------------
 # config 4: patch / EOT optimisation, 32 random transforms per image per step, batch 96 (BASELINE configs[3])
 # ---------------------------------------------------------------------------------------------------------
 def run_config4(args):
@@ -795,9 +922,9 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH, help="images per GPU (BASELINE: 256)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 4, 5],
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5],
                     help="BASELINE.json configs, 1-based: 1 = FGSM batch 8 (CUDA graph), 2 = PGD-10 batch 256 (the metric; default), "
-                         "4 = patch / EOT optimisation (32 transforms x 96 images), 5 = PGD-7 adversarial LoRA training, batch 96 per GPU")
+                         "3 = PGD-20 on LoRA Swin-B batch 128, 4 = patch / EOT optimisation (32 transforms x 96 images), 5 = PGD-7 adversarial LoRA training, batch 96 per GPU")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "engine":
         args.warmup = 3  # timing rules: W >= 3
@@ -817,7 +944,7 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
         return subprocess.call(cmd)
-    return {4: run_config4, 5: run_config5}.get(args.config, run_engine)(args)
+    return {3: run_config3, 4: run_config4, 5: run_config5}.get(args.config, run_engine)(args)
 
 
 if __name__ == "__main__":

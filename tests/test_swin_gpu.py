@@ -48,7 +48,7 @@ def test_swin_logits_and_grad_vs_hf_oracle(swin, which):
     assert torch.isfinite(g).all() and torch.isfinite(logits).all()
     assert rel(logits, ologits) < 2e-2
     assert abs(float(loss.mean()) - float(oloss)) < 2e-2 * abs(float(oloss))
-    assert rel(g, og) < 3e-2, rel(g, og)   # 24 blocks of bf16 residual stream (the ViT path keeps its streams in fp16)
+    assert rel(g, og) < 2e-2, rel(g, og)
     assert c > 0.999
     assert torch.equal(eng.logits(x), logits)
     # batch independence (windows / shifts never mix images)

@@ -54,7 +54,10 @@ struct GemmCfg {
   // (128 rows x 64 cols, 128B swizzle) shared by the four warps of a group
   static constexpr int OUT_BYTES = TWO ? 2 * 2 * SLAB_BYTES : NUM_EPI_WARPS * 2 * STAGE_OUT_BYTES;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + OUT_BYTES + BAR_BYTES;
+  static constexpr int XCH_BYTES = TWO ? 0 : 1024;  // single-CTA kernel: 128 x (mean, M2) hand-over between the two statistics groups
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + OUT_BYTES + BAR_BYTES + XCH_BYTES;
+  static_assert(STAGES % 2 == 0 || TWO, "the statistics groups of the single-CTA kernel own stages by parity");
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory per CTA");
 };
 
 struct GemmKernelArgs {
@@ -189,6 +192,8 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* smem_stage = smem;
   uint8_t* smem_out = smem + STAGES * Cfg::STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_out + Cfg::OUT_BYTES);
+  uint8_t* smem_xch = smem_out + Cfg::OUT_BYTES + Cfg::BAR_BYTES;
+  (void)smem_xch;
   uint64_t* full_bar = bars;                   // [STAGES]
   uint64_t* empty_bar = bars + STAGES;         // [STAGES]
   uint64_t* tmem_full = bars + 2 * STAGES;     // [2]
@@ -891,19 +896,25 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
     uint32_t scnt = 0;  // k-block counter of the row-statistics warps (same sequence as the producer's)
+    if (!TWO && epi.stats_out != nullptr && hsel == 0) asm volatile("bar.arrive 2, 256;" ::: "memory");
     for (int tile = unit; tile < num_tiles; tile += num_units, ++it) {
       const int m0 = mblock(tile) * TILE_M + static_cast<int>(rank) * BM;
       const int n0 = (tile % tiles_n) * BN;
       const uint32_t buf = it & 1;
       const uint32_t use = it >> 1;
       float2 row_mr = make_float2(0.f, 1.f);
-      if (!TWO && epi.stats_out != nullptr && hsel == 0) {
+      if (!TWO && epi.stats_out != nullptr) {
         // LayerNorm statistics of this tile's 128 A rows, read from the operand stages as they land (thread = row).
-        // Shifted accumulation (d = x - x[0]) keeps the single-pass variance well conditioned when |mean| >> std.
+        // All eight epilogue warps take part: warp (q, hsel) owns the k-blocks that land in stages of parity hsel (STAGES
+        // is even, so a stage always belongs to the same group and its empty barrier counts the MMA + that group's four
+        // warps).  Each group accumulates shifted sums (d = x - its first element: well conditioned when |mean| >> std);
+        // group 1 hands its (mean, M2) to group 0 through shared memory and the two are merged (Chan et al.).
         const int srow = q * 32 + lane;
         float shift = 0.f, sd = 0.f, sdd = 0.f;
+        int nproc = 0;
         for (int kb = 0; kb < num_kb; ++kb, ++scnt) {
           const int s = scnt % STAGES;
+          if ((s & 1) != hsel) continue;
           ptx::mbar_wait(&full_bar[s], (scnt / STAGES) & 1);
           if (kb < main_kb) {
             const uint32_t rowaddr = ptx::smem_u32(smem_stage + s * Cfg::STAGE_BYTES) + srow * 128;
@@ -915,7 +926,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               float f[8];
               if (args.a_f16) unpack_f16x8(a, f);
               else unpack_bf16x8(a, f);
-              if (kb == 0 && c == 0) shift = f[0];
+              if (nproc == 0 && c == 0) shift = f[0];
 #pragma unroll
               for (int k = 0; k < 8; ++k) {
                 const float d = f[k] - shift;
@@ -923,16 +934,31 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 sdd = fmaf(d, d, sdd);
               }
             }
+            ++nproc;
           }
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&empty_bar[s]);
         }
-        const float inv_k = 1.0f / static_cast<float>(args.K);
-        const float md = sd * inv_k;
-        const float var = fmaxf(sdd * inv_k - md * md, 0.f);
-        const float2 mr = make_float2(shift + md, rsqrtf(var + epi.stats_eps));
-        if (m0 + srow < args.M) epi.stats_out[m0 + srow] = mr;
-        row_mr = mr;
+        const float n_g = static_cast<float>(nproc * BK);
+        const float mean_g = nproc ? shift + sd / n_g : 0.f;
+        const float m2_g = nproc ? fmaxf(sdd - sd * sd / n_g, 0.f) : 0.f;
+        float2* xch = reinterpret_cast<float2*>(smem_xch);
+        if (hsel == 1) {
+          asm volatile("bar.sync 2, 256;" ::: "memory");   // group 0 has read the previous tile's hand-over
+          xch[srow] = make_float2(mean_g, m2_g);
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+        } else {
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          const float2 o = xch[srow];
+          asm volatile("bar.arrive 2, 256;" ::: "memory");
+          const float n_o = static_cast<float>(args.K) - n_g, n = static_cast<float>(args.K);
+          const float delta = o.x - mean_g;
+          const float mean = mean_g + delta * (n_o / n);
+          const float var = fmaxf((m2_g + o.y + delta * delta * (n_g * n_o / n)) / n, 0.f);
+          const float2 mr = make_float2(mean, rsqrtf(var + epi.stats_eps));
+          if (m0 + srow < args.M) epi.stats_out[m0 + srow] = mr;
+          row_mr = mr;
+        }
       }
       ptx::mbar_wait(&tmem_full[buf], use & 1);
       ptx::tc_fence_after();

@@ -196,11 +196,39 @@ __device__ __forceinline__ int win_region(const WinGeom& g, int win, int t) {
   return ry * 3 + rx;
 }
 
+// 32-wide dot product / axpy against a shared-memory row, read as eight 16-byte broadcast loads (one LDS.128 per four
+// FMAs; scalar loads made these kernels LSU-bound)
+__device__ __forceinline__ float dot32(const float (&a)[HD], const float* row) {
+  const float4* r4 = reinterpret_cast<const float4*>(row);
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < HD / 4; ++i) {
+    const float4 v = r4[i];
+    acc = fmaf(a[4 * i], v.x, acc);
+    acc = fmaf(a[4 * i + 1], v.y, acc);
+    acc = fmaf(a[4 * i + 2], v.z, acc);
+    acc = fmaf(a[4 * i + 3], v.w, acc);
+  }
+  return acc;
+}
+__device__ __forceinline__ void axpy32(float (&acc)[HD], float p, const float* row) {
+  const float4* r4 = reinterpret_cast<const float4*>(row);
+#pragma unroll
+  for (int i = 0; i < HD / 4; ++i) {
+    const float4 v = r4[i];
+    acc[4 * i] = fmaf(p, v.x, acc[4 * i]);
+    acc[4 * i + 1] = fmaf(p, v.y, acc[4 * i + 1]);
+    acc[4 * i + 2] = fmaf(p, v.z, acc[4 * i + 2]);
+    acc[4 * i + 3] = fmaf(p, v.w, acc[4 * i + 3]);
+  }
+}
+
 constexpr int WA_WARPS = 4;
 // smem per warp (floats): K [49][32], V [49][32]
 __global__ void __launch_bounds__(WA_WARPS * 32) win_attn_fwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ bias,
                                                                      bf16* __restrict__ out, WinGeom g, int items, float scale) {
-  extern __shared__ float sm[];
+  extern __shared__ float4 sm4_[];
+  float* sm = reinterpret_cast<float*>(sm4_);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int item = blockIdx.x * WA_WARPS + warp;
   if (item >= items) return;
@@ -234,9 +262,7 @@ __global__ void __launch_bounds__(WA_WARPS * 32) win_attn_fwd_kernel(const bf16*
     const int ri = reg[i];
 #pragma unroll
     for (int j = 0; j < WT; ++j) {
-      float acc = 0.f;
-#pragma unroll
-      for (int d = 0; d < HD; ++d) acc = fmaf(q[d], Ks[j * HD + d], acc);
+      float acc = dot32(q, Ks + j * HD);
       acc = fmaf(acc, scale, __ldg(bh + i * WT + j));
       if (reg[j] != ri) acc -= 100.f;
       s[j] = acc;
@@ -253,11 +279,7 @@ __global__ void __launch_bounds__(WA_WARPS * 32) win_attn_fwd_kernel(const bf16*
 #pragma unroll
     for (int d = 0; d < HD; ++d) o[d] = 0.f;
 #pragma unroll
-    for (int j = 0; j < WT; ++j) {
-      const float p = s[j] * inv;
-#pragma unroll
-      for (int d = 0; d < HD; ++d) o[d] = fmaf(p, Vs[j * HD + d], o[d]);
-    }
+    for (int j = 0; j < WT; ++j) axpy32(o, s[j] * inv, Vs + j * HD);
     uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(qrow) * g.C + h * HD);
 #pragma unroll
     for (int c = 0; c < 4; ++c) dst[c] = pack8(o + c * 8);
@@ -270,7 +292,8 @@ constexpr int WB_SMEM_FLOATS = 4 * WT * HD + 3 * 64;
 __global__ void __launch_bounds__(WB_WARPS * 32) win_attn_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
                                                                      const float* __restrict__ bias, bf16* __restrict__ dqkv,
                                                                      WinGeom g, int items, float scale) {
-  extern __shared__ float sm[];
+  extern __shared__ float4 sm4_[];
+  float* sm = reinterpret_cast<float*>(sm4_);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int item = blockIdx.x * WB_WARPS + warp;
   if (item >= items) return;
@@ -317,9 +340,7 @@ __global__ void __launch_bounds__(WB_WARPS * 32) win_attn_bwd_kernel(const bf16*
     const int ri = reg[i];
 #pragma unroll
     for (int j = 0; j < WT; ++j) {
-      float acc = 0.f;
-#pragma unroll
-      for (int d = 0; d < HD; ++d) acc = fmaf(q[d], Ks[j * HD + d], acc);
+      float acc = dot32(q, Ks + j * HD);
       acc = fmaf(acc, scale, __ldg(bh + i * WT + j));
       if (reg[j] != ri) acc -= 100.f;
       s[j] = acc;
@@ -336,9 +357,7 @@ __global__ void __launch_bounds__(WB_WARPS * 32) win_attn_bwd_kernel(const bf16*
     float D = 0.f;
 #pragma unroll
     for (int j = 0; j < WT; ++j) {
-      float acc = 0.f;
-#pragma unroll
-      for (int d = 0; d < HD; ++d) acc = fmaf(go[d], Vs[j * HD + d], acc);
+      const float acc = dot32(go, Vs + j * HD);
       s[j] *= inv;
       dP[j] = acc;
       D = fmaf(s[j], acc, D);
@@ -348,9 +367,7 @@ __global__ void __launch_bounds__(WB_WARPS * 32) win_attn_bwd_kernel(const bf16*
     for (int d = 0; d < HD; ++d) dq[d] = 0.f;
 #pragma unroll
     for (int j = 0; j < WT; ++j) {
-      const float dS = s[j] * (dP[j] - D) * scale;
-#pragma unroll
-      for (int d = 0; d < HD; ++d) dq[d] = fmaf(dS, Ks[j * HD + d], dq[d]);
+      axpy32(dq, s[j] * (dP[j] - D) * scale, Ks + j * HD);
     }
     lse[i] = mx + __logf(sum);
     Dd[i] = D;
@@ -372,21 +389,13 @@ __global__ void __launch_bounds__(WB_WARPS * 32) win_attn_bwd_kernel(const bf16*
     const int rj = reg[j];
 #pragma unroll 7
     for (int i = 0; i < WT; ++i) {
-      float sc = 0.f, dp = 0.f;
-#pragma unroll
-      for (int d = 0; d < HD; ++d) {
-        sc = fmaf(Qs[i * HD + d], k[d], sc);
-        dp = fmaf(Gs[i * HD + d], v[d], dp);
-      }
+      float sc = dot32(k, Qs + i * HD);
+      const float dp = dot32(v, Gs + i * HD);
       sc = fmaf(sc, scale, __ldg(bh + i * WT + j));
       if (reg[i] != rj) sc -= 100.f;
       const float p = __expf(sc - lse[i]);
-      const float dS = p * (dp - Dd[i]) * scale;
-#pragma unroll
-      for (int d = 0; d < HD; ++d) {
-        dv[d] = fmaf(p, Gs[i * HD + d], dv[d]);
-        dk[d] = fmaf(dS, Qs[i * HD + d], dk[d]);
-      }
+      axpy32(dv, p, Gs + i * HD);
+      axpy32(dk, p * (dp - Dd[i]) * scale, Qs + i * HD);
     }
     const size_t row = static_cast<size_t>(win_token_row(g, b, win, j)) * ld + h * HD;
     uint4* dkp = reinterpret_cast<uint4*>(dqkv + row + g.C);

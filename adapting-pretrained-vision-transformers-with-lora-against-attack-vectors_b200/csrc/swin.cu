@@ -6,11 +6,12 @@
 //
 // Every Linear (qkv, proj, fc1, fc2, patch embed, patch-merging reduction) runs on the same tcgen05 GEMM as the ViT path
 // (bias / residual / GELU+GELU' / LoRA k-block epilogues; stage widths 128 / 256 / 512 / 1024).  New here:
-//   win_attn_fwd / win_attn_bwd   7x7-window attention, head dim 32: one warp per (window, head); the cyclic shift, the
-//                                 window partition and their inverses are index arithmetic on the token-major q|k|v rows
-//                                 (nothing is rolled or re-laid out in memory), the relative-position bias comes from a
-//                                 [heads, 49, 49] table, the shifted-window mask from each token's region id.  The backward
-//                                 recomputes the 49x49 probabilities (they are never stored).
+//   win_attn_fwd / win_attn_bwd   7x7-window attention, head dim 32: one four-warp CTA per (window, head), the five small
+//                                 products on warp-level bf16 MMAs; the cyclic shift, the window partition and their
+//                                 inverses are index arithmetic on the token-major q|k|v rows (nothing is rolled or
+//                                 re-laid out in memory), the relative-position bias comes from a [heads, 49, 49] table,
+//                                 the shifted-window mask from each token's region id.  The backward recomputes the
+//                                 49x49 probabilities (they are never stored).
 //   merge_gather / merge_scatter  2x2 patch merging as a row permutation ([B,H,W,C] -> [B,H/2,W/2,4C]) and its inverse
 //   ln_any_fwd / ln_any_bwd       LayerNorm for any width (128 ... 2048 here), one warp per row
 //   swin_head                     final LayerNorm on all 49 tokens + mean pool + classifier + CE (+ backward)
@@ -130,14 +131,126 @@ __global__ void __launch_bounds__(256) ln_any_bwd_kernel(const bf16* __restrict_
   }
 }
 
+// The widths the Swin path uses (128 ... 2048 = 8 * LPR * CPL columns): LPR lanes per row, CPL 16-byte chunks per lane, the
+// row lives in registers -- one global read, one write (the kernels are pure HBM traffic: 4 B per element forward, 8 B
+// backward with the residual gradient).
+template <int LPR>
+__device__ __forceinline__ float row_sum(float v) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+template <int LPR, int CPL>
+__global__ void __launch_bounds__(256) ln_reg_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, bf16* __restrict__ y,
+                                                         float2* __restrict__ stats, int rows, float eps) {
+  constexpr int COLS = 8 * LPR * CPL, RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, sub = lane % LPR;
+  const int row = (blockIdx.x * 8 + (threadIdx.x >> 5)) * RPW + lane / LPR;
+  const bool ok = row < rows;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(ok ? row : 0) * COLS);
+  float v[CPL][8];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < CPL; ++k) {
+    unpack8(__ldg(xr + sub + k * LPR), v[k]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[k][j];
+  }
+  const float mean = row_sum<LPR>(s) * (1.f / COLS);
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < CPL; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) q = fmaf(v[k][j] - mean, v[k][j] - mean, q);
+  const float rstd = rsqrtf(row_sum<LPR>(q) * (1.f / COLS) + eps);
+  if (!ok) return;
+  uint4* yr = reinterpret_cast<uint4*>(y + static_cast<size_t>(row) * COLS);
+#pragma unroll
+  for (int k = 0; k < CPL; ++k) {
+    const int c = sub + k * LPR;
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c), g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c + 1);
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * c), b1 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * c + 1);
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = fmaf((v[k][j] - mean) * rstd, gg[j], bb[j]);
+    yr[c] = pack8(o);
+  }
+  if (sub == 0) stats[row] = make_float2(mean, rstd);
+}
+template <int LPR, int CPL>
+__global__ void __launch_bounds__(256) ln_reg_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                         const float2* __restrict__ stats, const float* __restrict__ gamma,
+                                                         const bf16* __restrict__ dres, bf16* __restrict__ dx, int rows) {
+  constexpr int COLS = 8 * LPR * CPL, RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, sub = lane % LPR;
+  const int row = (blockIdx.x * 8 + (threadIdx.x >> 5)) * RPW + lane / LPR;
+  const bool ok = row < rows;
+  const size_t off = static_cast<size_t>(ok ? row : 0) * COLS;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + off);
+  const uint4* dyr = reinterpret_cast<const uint4*>(dy + off);
+  const float2 st = stats[ok ? row : 0];
+  float xh[CPL][8], gd[CPL][8];  // (x - mean) * rstd and gamma * dy
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < CPL; ++k) {
+    const int c = sub + k * LPR;
+    unpack8(__ldg(xr + c), xh[k]);
+    unpack8(__ldg(dyr + c), gd[k]);
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c), g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c + 1);
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      xh[k][j] = (xh[k][j] - st.x) * st.y;
+      gd[k][j] *= gg[j];
+      s1 += gd[k][j];
+      s2 = fmaf(gd[k][j], xh[k][j], s2);
+    }
+  }
+  const float m1 = row_sum<LPR>(s1) * (1.f / COLS), m2 = row_sum<LPR>(s2) * (1.f / COLS);
+  if (!ok) return;
+  const uint4* rr = dres ? reinterpret_cast<const uint4*>(dres + off) : nullptr;
+  uint4* dxr = reinterpret_cast<uint4*>(dx + off);
+#pragma unroll
+  for (int k = 0; k < CPL; ++k) {
+    const int c = sub + k * LPR;
+    float r[8] = {0, 0, 0, 0, 0, 0, 0, 0}, o[8];
+    if (rr) unpack8(__ldg(rr + c), r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = r[j] + st.y * (gd[k][j] - m1 - xh[k][j] * m2);
+    dxr[c] = pack8(o);
+  }
+}
+
 int ln_any_fwd(const bf16* x, const float* g, const float* b, bf16* y, float2* st, int rows, int cols, float eps, cudaStream_t s) {
-  ln_any_fwd_kernel<<<(rows + 7) / 8, 256, 0, s>>>(x, g, b, y, st, rows, cols, eps);
+#define LN_FWD(LPR, CPL)                                                                                                    \
+  ln_reg_fwd_kernel<LPR, CPL><<<(rows + 8 * (32 / LPR) - 1) / (8 * (32 / LPR)), 256, 0, s>>>(x, g, b, y, st, rows, eps)
+  switch (((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(b)) & 15) ? 0 : cols) {
+    case 128: LN_FWD(16, 1); break;
+    case 256: LN_FWD(32, 1); break;
+    case 512: LN_FWD(32, 2); break;
+    case 1024: LN_FWD(32, 4); break;
+    case 2048: LN_FWD(32, 8); break;
+    default: ln_any_fwd_kernel<<<(rows + 7) / 8, 256, 0, s>>>(x, g, b, y, st, rows, cols, eps);
+  }
+#undef LN_FWD
   VITATK_CUDA_OK(cudaGetLastError());
   return 0;
 }
 int ln_any_bwd(const bf16* dy, const bf16* x, const float2* st, const float* g, const bf16* dres, bf16* dx, int rows, int cols,
                cudaStream_t s) {
-  ln_any_bwd_kernel<<<(rows + 7) / 8, 256, 0, s>>>(dy, x, st, g, dres, dx, rows, cols);
+#define LN_BWD(LPR, CPL)                                                                                                    \
+  ln_reg_bwd_kernel<LPR, CPL><<<(rows + 8 * (32 / LPR) - 1) / (8 * (32 / LPR)), 256, 0, s>>>(dy, x, st, g, dres, dx, rows)
+  switch ((reinterpret_cast<uintptr_t>(g) & 15) ? 0 : cols) {
+    case 128: LN_BWD(16, 1); break;
+    case 256: LN_BWD(32, 1); break;
+    case 512: LN_BWD(32, 2); break;
+    case 1024: LN_BWD(32, 4); break;
+    case 2048: LN_BWD(32, 8); break;
+    default: ln_any_bwd_kernel<<<(rows + 7) / 8, 256, 0, s>>>(dy, x, st, g, dres, dx, rows, cols);
+  }
+#undef LN_BWD
   VITATK_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -174,6 +287,14 @@ int merge_permute(const bf16* in, bf16* out, int batch, int R, int C, int scatte
 // Window attention.  Token rows are (b, y, x) row-major over an R x R grid; q|k|v packed [M, 3C], head h = columns
 // h*32 .. h*32+31 of each third.  Window (wy, wx) holds the tokens whose SHIFTED coordinates y' = (y - shift) mod R fall
 // in [7 wy, 7 wy + 7): torch.roll(-shift) + window_partition without moving data.
+//
+// A (window, head) unit is 49 x 49 x 32: 12 KB of HBM traffic forward, 24 KB backward, against 0.3 / 0.8 MFLOP -- the
+// kernels are HBM-bound byte work once the arithmetic is off the FP32 pipe.  One CTA of four warps per unit; the 49
+// tokens are padded to 64 rows in shared memory; each warp owns 16 query rows (16 key rows in the second backward
+// phase) and runs the five small products on warp-level m16n8k16 bf16 MMAs (fp32 accumulate) straight from ldmatrix
+// fragments -- a 64 x 64 x 32 product is far below one tcgen05 tile, and the TMEM / mbarrier hand-offs of the UMMA path
+// cost more than the whole unit.  The probabilities never leave registers in the forward (the S accumulator fragments
+// are re-packed as the A operand of P*V); the backward recomputes them.
 // ------------------------------------------------------------------------------------------------
 struct WinGeom {
   int R, nW, heads, C, shift;
@@ -196,225 +317,307 @@ __device__ __forceinline__ int win_region(const WinGeom& g, int win, int t) {
   return ry * 3 + rx;
 }
 
-// 32-wide dot product / axpy against a shared-memory row, read as eight 16-byte broadcast loads (one LDS.128 per four
-// FMAs; scalar loads made these kernels LSU-bound)
-__device__ __forceinline__ float dot32(const float (&a)[HD], const float* row) {
-  const float4* r4 = reinterpret_cast<const float4*>(row);
-  float acc = 0.f;
-#pragma unroll
-  for (int i = 0; i < HD / 4; ++i) {
-    const float4 v = r4[i];
-    acc = fmaf(a[4 * i], v.x, acc);
-    acc = fmaf(a[4 * i + 1], v.y, acc);
-    acc = fmaf(a[4 * i + 2], v.z, acc);
-    acc = fmaf(a[4 * i + 3], v.w, acc);
-  }
-  return acc;
+constexpr int WPAD = 64;  // tokens of a window, padded to four 16-row MMA tiles
+constexpr int QS = 40;    // row stride (elements) of the [64][32] operand tiles: 80 B, ldmatrix conflict-free
+constexpr int PS = 72;    // row stride of the [64][64] P / dS tiles: 144 B
+constexpr int WA_THREADS = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
 }
-__device__ __forceinline__ void axpy32(float (&acc)[HD], float p, const float* row) {
-  const float4* r4 = reinterpret_cast<const float4*>(row);
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+// Fragment addressing (lane l; i = l >> 3 selects the 8x8 matrix, r = l & 7 its row).
+//   A operand, storage [m][k]:              row m0 + r + (i & 1) * 8,  col k0 + (i >> 1) * 8    (ldsm_x4)
+//   B operand, storage [n][k] ("col"):      row n0 + r + (i >> 1) * 8, col k0 + (i & 1) * 8     (ldsm_x4: b0 b1 of n-tile n0, then of n0 + 8)
+//   B operand, storage [k][n]:              row k0 + r + (i & 1) * 8,  col n0 + (i >> 1) * 8    (ldsm_x4_t: same register order)
+//   A operand, storage [k][m] (transposed): row k0 + r + (i >> 1) * 8, col m0 + (i & 1) * 8     (ldsm_x4_t)
+__device__ __forceinline__ int frag_r_lo(int lane) { return (lane & 7) + ((lane >> 3) & 1) * 8; }  // r + (i & 1) * 8
+__device__ __forceinline__ int frag_c_hi(int lane) { return (lane >> 4) * 8; }                      // (i >> 1) * 8
+__device__ __forceinline__ int frag_r_hi(int lane) { return (lane & 7) + (lane >> 4) * 8; }          // r + (i >> 1) * 8
+__device__ __forceinline__ int frag_c_lo(int lane) { return ((lane >> 3) & 1) * 8; }                 // (i & 1) * 8
+
+// rows [0, 49) of one [token][32] head slice -> shared [64][QS]; rows 49..63 zero
+__device__ __forceinline__ void win_load_tile(bf16* dst, const bf16* src, size_t ld, const int* trow, int tid) {
+  for (int c = tid; c < WPAD * 4; c += WA_THREADS) {
+    const int t = c >> 2, d8 = (c & 3) * 8;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (t < WT) v = __ldg(reinterpret_cast<const uint4*>(src + static_cast<size_t>(trow[t]) * ld + d8));
+    *reinterpret_cast<uint4*>(dst + t * QS + d8) = v;
+  }
+}
+// 16 rows [m0, m0 + 16) of a staged [64][QS] tile -> global rows (row stride ld), 16-byte stores
+__device__ __forceinline__ void win_store_rows(bf16* dst, size_t ld, const bf16* tile, const int* trow, int m0, int lane) {
 #pragma unroll
-  for (int i = 0; i < HD / 4; ++i) {
-    const float4 v = r4[i];
-    acc[4 * i] = fmaf(p, v.x, acc[4 * i]);
-    acc[4 * i + 1] = fmaf(p, v.y, acc[4 * i + 1]);
-    acc[4 * i + 2] = fmaf(p, v.z, acc[4 * i + 2]);
-    acc[4 * i + 3] = fmaf(p, v.w, acc[4 * i + 3]);
+  for (int c = lane; c < 64; c += 32) {
+    const int t = m0 + (c >> 2), d8 = (c & 3) * 8;
+    if (t < WT) *reinterpret_cast<uint4*>(dst + static_cast<size_t>(trow[t]) * ld + d8) = *reinterpret_cast<const uint4*>(tile + t * QS + d8);
+  }
+}
+// accumulator fragments of a [16][32] tile (four n-tiles) -> rows m0 + g, m0 + g + 8 of a staged tile, scaled
+__device__ __forceinline__ void win_stage_acc(bf16* tile, const float (&o)[4][4], int m0, int lane, float s_lo, float s_hi) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    *reinterpret_cast<uint32_t*>(tile + (m0 + g) * QS + nt * 8 + 2 * t) = pack_bf16x2(o[nt][0] * s_lo, o[nt][1] * s_lo);
+    *reinterpret_cast<uint32_t*>(tile + (m0 + g + 8) * QS + nt * 8 + 2 * t) = pack_bf16x2(o[nt][2] * s_hi, o[nt][3] * s_hi);
+  }
+}
+// S = scale * Q K^T + bias + region mask for the warp's 16 query rows, then the row softmax statistics.
+// On return p[nt][e] = exp(s - rowmax) (0 for key columns >= 49 and for query rows >= 49), inv_* = 1 / rowsum.
+__device__ __forceinline__ void win_scores(float (&p)[8][4], float& inv_lo, float& inv_hi, const bf16* Qs, const bf16* Ks,
+                                           const int* reg, const float* __restrict__ bh, float scale, int m0, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) p[nt][e] = 0.f;
+  uint32_t aq[2][4];
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) ldsm_x4(aq[ks], smem_u32(Qs + (m0 + frag_r_lo(lane)) * QS + ks * 16 + frag_c_hi(lane)));
+#pragma unroll
+  for (int np = 0; np < 4; ++np) {
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      uint32_t bk[4];
+      ldsm_x4(bk, smem_u32(Ks + (np * 16 + frag_r_hi(lane)) * QS + ks * 16 + frag_c_lo(lane)));
+      mma16816(p[2 * np], aq[ks], bk[0], bk[1]);
+      if (np < 3) mma16816(p[2 * np + 1], aq[ks], bk[2], bk[3]);
+    }
+  }
+  const int i_lo = m0 + g, i_hi = i_lo + 8;
+  const int r_lo = reg[i_lo], r_hi = reg[i_hi];
+  float mx_lo = -INFINITY, mx_hi = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < 7; ++nt) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int j = nt * 8 + 2 * t + e;
+      float lo = -INFINITY, hi = -INFINITY;
+      if (j < WT) {
+        const int rj = reg[j];
+        if (i_lo < WT) lo = fmaf(p[nt][e], scale, __ldg(bh + i_lo * WT + j)) - (rj != r_lo ? 100.f : 0.f);
+        if (i_hi < WT) hi = fmaf(p[nt][2 + e], scale, __ldg(bh + i_hi * WT + j)) - (rj != r_hi ? 100.f : 0.f);
+      }
+      p[nt][e] = lo;
+      p[nt][2 + e] = hi;
+      mx_lo = fmaxf(mx_lo, lo);
+      mx_hi = fmaxf(mx_hi, hi);
+    }
+  }
+  mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1));
+  mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
+  mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1));
+  mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
+  if (i_lo >= WT) mx_lo = 0.f;  // padded query rows: exp(-inf - 0) = 0 everywhere, no NaN
+  if (i_hi >= WT) mx_hi = 0.f;
+  float sum_lo = 0.f, sum_hi = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < 7; ++nt) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      p[nt][e] = __expf(p[nt][e] - mx_lo);
+      p[nt][2 + e] = __expf(p[nt][2 + e] - mx_hi);
+      sum_lo += p[nt][e];
+      sum_hi += p[nt][2 + e];
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) p[7][e] = 0.f;
+  sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 1);
+  sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 2);
+  sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 1);
+  sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 2);
+  inv_lo = i_lo < WT ? 1.f / sum_lo : 0.f;
+  inv_hi = i_hi < WT ? 1.f / sum_hi : 0.f;
+}
+// acc[16][32] += X[16][64] * Y[64][32]: X from accumulator-layout registers (eight n-tiles = four k-steps), Y stored [k][n]
+__device__ __forceinline__ void win_mma_regA(float (&acc)[4][4], const float (&x)[8][4], const bf16* Ys, int lane) {
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    uint32_t a[4];
+    a[0] = pack_bf16x2(x[2 * ks][0], x[2 * ks][1]);
+    a[1] = pack_bf16x2(x[2 * ks][2], x[2 * ks][3]);
+    a[2] = pack_bf16x2(x[2 * ks + 1][0], x[2 * ks + 1][1]);
+    a[3] = pack_bf16x2(x[2 * ks + 1][2], x[2 * ks + 1][3]);
+#pragma unroll
+    for (int dp = 0; dp < 2; ++dp) {
+      uint32_t b[4];
+      ldsm_x4_t(b, smem_u32(Ys + (ks * 16 + frag_r_lo(lane)) * QS + dp * 16 + frag_c_hi(lane)));
+      mma16816(acc[2 * dp], a, b[0], b[1]);
+      mma16816(acc[2 * dp + 1], a, b[2], b[3]);
+    }
+  }
+}
+// acc[16][32] += X^T[16][64] * Y[64][32] for output rows [m0, m0 + 16): X stored [k = 64][m = 64] (stride PS), Y stored [k][n]
+__device__ __forceinline__ void win_mma_transA(float (&acc)[4][4], const bf16* Xs, const bf16* Ys, int m0, int lane) {
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    uint32_t a[4];
+    ldsm_x4_t(a, smem_u32(Xs + (ks * 16 + frag_r_hi(lane)) * PS + m0 + frag_c_lo(lane)));
+#pragma unroll
+    for (int dp = 0; dp < 2; ++dp) {
+      uint32_t b[4];
+      ldsm_x4_t(b, smem_u32(Ys + (ks * 16 + frag_r_lo(lane)) * QS + dp * 16 + frag_c_hi(lane)));
+      mma16816(acc[2 * dp], a, b[0], b[1]);
+      mma16816(acc[2 * dp + 1], a, b[2], b[3]);
+    }
   }
 }
 
-constexpr int WA_WARPS = 4;
-// smem per warp (floats): K [49][32], V [49][32]
-__global__ void __launch_bounds__(WA_WARPS * 32) win_attn_fwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ bias,
-                                                                     bf16* __restrict__ out, WinGeom g, int items, float scale) {
-  extern __shared__ float4 sm4_[];
-  float* sm = reinterpret_cast<float*>(sm4_);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int item = blockIdx.x * WA_WARPS + warp;
-  if (item >= items) return;
-  float* Ks = sm + warp * (2 * WT * HD + 64);
-  float* Vs = Ks + WT * HD;
-  int* reg = reinterpret_cast<int*>(Vs + WT * HD);
+__global__ void __launch_bounds__(WA_THREADS) win_attn_fwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ bias,
+                                                                  bf16* __restrict__ out, WinGeom g, float scale) {
+  __shared__ __align__(16) bf16 Qs[WPAD * QS], Ks[WPAD * QS], Vs[WPAD * QS];
+  __shared__ int reg[WPAD], trow[WPAD];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int item = blockIdx.x;
   const int h = item % g.heads, win = (item / g.heads) % g.nW, b = item / (g.heads * g.nW);
-  const int ld = 3 * g.C;
-  for (int t = lane; t < WT; t += 32) reg[t] = win_region(g, win, t);
-  // cooperative load of K and V: 49 rows x 32 dims = 196 chunks of 8
-  for (int c = lane; c < WT * 4; c += 32) {
-    const int t = c >> 2, d8 = (c & 3) * 8;
-    const size_t row = static_cast<size_t>(win_token_row(g, b, win, t)) * ld + h * HD + d8;
-    float f[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(qkv + row + g.C)), f);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) Ks[t * HD + d8 + j] = f[j];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(qkv + row + 2 * g.C)), f);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) Vs[t * HD + d8 + j] = f[j];
+  const size_t ld = 3 * static_cast<size_t>(g.C);
+  if (tid < WPAD) {
+    reg[tid] = tid < WT ? win_region(g, win, tid) : -1;
+    trow[tid] = tid < WT ? win_token_row(g, b, win, tid) : 0;
   }
+  __syncthreads();
+  const bf16* base = qkv + h * HD;
+  win_load_tile(Qs, base, ld, trow, tid);
+  win_load_tile(Ks, base + g.C, ld, trow, tid);
+  win_load_tile(Vs, base + 2 * g.C, ld, trow, tid);
+  __syncthreads();
+  const int m0 = warp * 16;
+  float p[8][4], inv_lo, inv_hi;
+  win_scores(p, inv_lo, inv_hi, Qs, Ks, reg, bias + static_cast<size_t>(h) * WT * WT, scale, m0, lane);
+  float o[4][4];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[nt][e] = 0.f;
+  win_mma_regA(o, p, Vs, lane);
+  // the warp's own 16 Q rows are dead (only this warp read them): stage O there, then 16-byte stores
   __syncwarp();
-  const float* bh = bias + static_cast<size_t>(h) * WT * WT;
-  for (int i = lane; i < WT; i += 32) {
-    const int qrow = win_token_row(g, b, win, i);
-    float q[HD];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) unpack8(__ldg(reinterpret_cast<const uint4*>(qkv + static_cast<size_t>(qrow) * ld + h * HD + c * 8)), q + c * 8);
-    float s[WT];
-    float mx = -INFINITY;
-    const int ri = reg[i];
-#pragma unroll
-    for (int j = 0; j < WT; ++j) {
-      float acc = dot32(q, Ks + j * HD);
-      acc = fmaf(acc, scale, __ldg(bh + i * WT + j));
-      if (reg[j] != ri) acc -= 100.f;
-      s[j] = acc;
-      mx = fmaxf(mx, acc);
-    }
-    float sum = 0.f;
-#pragma unroll
-    for (int j = 0; j < WT; ++j) {
-      s[j] = __expf(s[j] - mx);
-      sum += s[j];
-    }
-    const float inv = 1.f / sum;
-    float o[HD];
-#pragma unroll
-    for (int d = 0; d < HD; ++d) o[d] = 0.f;
-#pragma unroll
-    for (int j = 0; j < WT; ++j) axpy32(o, s[j] * inv, Vs + j * HD);
-    uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(qrow) * g.C + h * HD);
-#pragma unroll
-    for (int c = 0; c < 4; ++c) dst[c] = pack8(o + c * 8);
-  }
+  win_stage_acc(Qs, o, m0, lane, inv_lo, inv_hi);
+  __syncwarp();
+  win_store_rows(out + h * HD, static_cast<size_t>(g.C), Qs, trow, m0, lane);
 }
 
-constexpr int WB_WARPS = 2;
-// smem per warp (floats): Q, K, V, dO [49][32] each, lse [49], D [49], region [49]
-constexpr int WB_SMEM_FLOATS = 4 * WT * HD + 3 * 64;
-__global__ void __launch_bounds__(WB_WARPS * 32) win_attn_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
-                                                                     const float* __restrict__ bias, bf16* __restrict__ dqkv,
-                                                                     WinGeom g, int items, float scale) {
-  extern __shared__ float4 sm4_[];
-  float* sm = reinterpret_cast<float*>(sm4_);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int item = blockIdx.x * WB_WARPS + warp;
-  if (item >= items) return;
-  float* Qs = sm + warp * WB_SMEM_FLOATS;
-  float* Ks = Qs + WT * HD;
-  float* Vs = Ks + WT * HD;
-  float* Gs = Vs + WT * HD;  // dO
-  float* lse = Gs + WT * HD;
-  float* Dd = lse + 64;
-  int* reg = reinterpret_cast<int*>(Dd + 64);
+// Backward: recompute P, dP = dO V^T, D = rowsum(P o dP), dS = scale * P o (dP - D); dQ = dS K (phase 1, warp = 16 query
+// rows); dK = dS^T Q, dV = P^T dO (phase 2, warp = 16 key rows, P and dS through shared memory).
+__global__ void __launch_bounds__(WA_THREADS) win_attn_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
+                                                                  const float* __restrict__ bias, bf16* __restrict__ dqkv,
+                                                                  WinGeom g, float scale) {
+  __shared__ __align__(16) bf16 Qs[WPAD * QS], Ks[WPAD * QS], Vs[WPAD * QS], Gs[WPAD * QS];
+  __shared__ __align__(16) bf16 Ps[WPAD * PS], Ds[WPAD * PS];
+  __shared__ int reg[WPAD], trow[WPAD];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int item = blockIdx.x;
   const int h = item % g.heads, win = (item / g.heads) % g.nW, b = item / (g.heads * g.nW);
-  const int ld = 3 * g.C;
-  for (int t = lane; t < WT; t += 32) reg[t] = win_region(g, win, t);
-  for (int c = lane; c < WT * 4; c += 32) {
-    const int t = c >> 2, d8 = (c & 3) * 8;
-    const int trow = win_token_row(g, b, win, t);
-    const size_t row = static_cast<size_t>(trow) * ld + h * HD + d8;
-    float f[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(qkv + row)), f);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) Qs[t * HD + d8 + j] = f[j];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(qkv + row + g.C)), f);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) Ks[t * HD + d8 + j] = f[j];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(qkv + row + 2 * g.C)), f);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) Vs[t * HD + d8 + j] = f[j];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(dout + static_cast<size_t>(trow) * g.C + h * HD + d8)), f);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) Gs[t * HD + d8 + j] = f[j];
+  const size_t ld = 3 * static_cast<size_t>(g.C);
+  if (tid < WPAD) {
+    reg[tid] = tid < WT ? win_region(g, win, tid) : -1;
+    trow[tid] = tid < WT ? win_token_row(g, b, win, tid) : 0;
   }
+  __syncthreads();
+  const bf16* base = qkv + h * HD;
+  win_load_tile(Qs, base, ld, trow, tid);
+  win_load_tile(Ks, base + g.C, ld, trow, tid);
+  win_load_tile(Vs, base + 2 * g.C, ld, trow, tid);
+  win_load_tile(Gs, dout + h * HD, static_cast<size_t>(g.C), trow, tid);
+  __syncthreads();
+  const int m0 = warp * 16, gq = lane >> 2, tq = lane & 3;
+  float dq[4][4];
+  {
+    float p[8][4], inv_lo, inv_hi;
+    win_scores(p, inv_lo, inv_hi, Qs, Ks, reg, bias + static_cast<size_t>(h) * WT * WT, scale, m0, lane);
+    // dP = dO V^T (V stored [key][dim] = the "col" B operand, like K in the scores)
+    float dp[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) dp[nt][e] = 0.f;
+    uint32_t ag[2][4];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) ldsm_x4(ag[ks], smem_u32(Gs + (m0 + frag_r_lo(lane)) * QS + ks * 16 + frag_c_hi(lane)));
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        uint32_t bv[4];
+        ldsm_x4(bv, smem_u32(Vs + (np * 16 + frag_r_hi(lane)) * QS + ks * 16 + frag_c_lo(lane)));
+        mma16816(dp[2 * np], ag[ks], bv[0], bv[1]);
+        if (np < 3) mma16816(dp[2 * np + 1], ag[ks], bv[2], bv[3]);
+      }
+    }
+    float d_lo = 0.f, d_hi = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 7; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        p[nt][e] *= inv_lo;
+        p[nt][2 + e] *= inv_hi;
+        d_lo = fmaf(p[nt][e], dp[nt][e], d_lo);
+        d_hi = fmaf(p[nt][2 + e], dp[nt][2 + e], d_hi);
+      }
+    }
+    d_lo += __shfl_xor_sync(0xffffffffu, d_lo, 1);
+    d_lo += __shfl_xor_sync(0xffffffffu, d_lo, 2);
+    d_hi += __shfl_xor_sync(0xffffffffu, d_hi, 1);
+    d_hi += __shfl_xor_sync(0xffffffffu, d_hi, 2);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      // P (bf16) for dV, then dS in place of dP
+      *reinterpret_cast<uint32_t*>(Ps + (m0 + gq) * PS + nt * 8 + 2 * tq) = pack_bf16x2(p[nt][0], p[nt][1]);
+      *reinterpret_cast<uint32_t*>(Ps + (m0 + gq + 8) * PS + nt * 8 + 2 * tq) = pack_bf16x2(p[nt][2], p[nt][3]);
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        dp[nt][e] = p[nt][e] * (dp[nt][e] - d_lo) * scale;
+        dp[nt][2 + e] = p[nt][2 + e] * (dp[nt][2 + e] - d_hi) * scale;
+      }
+      *reinterpret_cast<uint32_t*>(Ds + (m0 + gq) * PS + nt * 8 + 2 * tq) = pack_bf16x2(dp[nt][0], dp[nt][1]);
+      *reinterpret_cast<uint32_t*>(Ds + (m0 + gq + 8) * PS + nt * 8 + 2 * tq) = pack_bf16x2(dp[nt][2], dp[nt][3]);
+    }
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) dq[nt][e] = 0.f;
+    win_mma_regA(dq, dp, Ks, lane);
+  }
+  __syncthreads();  // P, dS complete; K, V no longer read
+  float dk[4][4], dv[4][4];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) dk[nt][e] = dv[nt][e] = 0.f;
+  win_mma_transA(dv, Ps, Gs, m0, lane);
+  win_mma_transA(dk, Ds, Qs, m0, lane);
+  win_stage_acc(Ks, dk, m0, lane, 1.f, 1.f);
+  win_stage_acc(Vs, dv, m0, lane, 1.f, 1.f);
+  __syncthreads();  // every warp is done with Q (and dO)
+  win_stage_acc(Qs, dq, m0, lane, 1.f, 1.f);
   __syncwarp();
-  const float* bh = bias + static_cast<size_t>(h) * WT * WT;
-  // ---- phase A: lane = query.  lse_i, D_i = sum_j p_ij dP_ij, dq_i = scale * sum_j dS_ij k_j ----
-  for (int i = lane; i < WT; i += 32) {
-    float q[HD], go[HD];
-#pragma unroll
-    for (int d = 0; d < HD; ++d) {
-      q[d] = Qs[i * HD + d];
-      go[d] = Gs[i * HD + d];
-    }
-    float s[WT];
-    float mx = -INFINITY;
-    const int ri = reg[i];
-#pragma unroll
-    for (int j = 0; j < WT; ++j) {
-      float acc = dot32(q, Ks + j * HD);
-      acc = fmaf(acc, scale, __ldg(bh + i * WT + j));
-      if (reg[j] != ri) acc -= 100.f;
-      s[j] = acc;
-      mx = fmaxf(mx, acc);
-    }
-    float sum = 0.f;
-#pragma unroll
-    for (int j = 0; j < WT; ++j) {
-      s[j] = __expf(s[j] - mx);
-      sum += s[j];
-    }
-    const float inv = 1.f / sum;
-    float dP[WT];
-    float D = 0.f;
-#pragma unroll
-    for (int j = 0; j < WT; ++j) {
-      const float acc = dot32(go, Vs + j * HD);
-      s[j] *= inv;
-      dP[j] = acc;
-      D = fmaf(s[j], acc, D);
-    }
-    float dq[HD];
-#pragma unroll
-    for (int d = 0; d < HD; ++d) dq[d] = 0.f;
-#pragma unroll
-    for (int j = 0; j < WT; ++j) {
-      axpy32(dq, s[j] * (dP[j] - D) * scale, Ks + j * HD);
-    }
-    lse[i] = mx + __logf(sum);
-    Dd[i] = D;
-    uint4* dst = reinterpret_cast<uint4*>(dqkv + static_cast<size_t>(win_token_row(g, b, win, i)) * ld + h * HD);
-#pragma unroll
-    for (int c = 0; c < 4; ++c) dst[c] = pack8(dq + c * 8);
-  }
-  __syncwarp();
-  // ---- phase B: lane = key.  dv_j = sum_i p_ij dO_i, dk_j = scale * sum_i dS_ij q_i ----
-  for (int j = lane; j < WT; j += 32) {
-    float k[HD], v[HD], dk[HD], dv[HD];
-#pragma unroll
-    for (int d = 0; d < HD; ++d) {
-      k[d] = Ks[j * HD + d];
-      v[d] = Vs[j * HD + d];
-      dk[d] = 0.f;
-      dv[d] = 0.f;
-    }
-    const int rj = reg[j];
-#pragma unroll 7
-    for (int i = 0; i < WT; ++i) {
-      float sc = dot32(k, Qs + i * HD);
-      const float dp = dot32(v, Gs + i * HD);
-      sc = fmaf(sc, scale, __ldg(bh + i * WT + j));
-      if (reg[i] != rj) sc -= 100.f;
-      const float p = __expf(sc - lse[i]);
-      axpy32(dv, p, Gs + i * HD);
-      axpy32(dk, p * (dp - Dd[i]) * scale, Qs + i * HD);
-    }
-    const size_t row = static_cast<size_t>(win_token_row(g, b, win, j)) * ld + h * HD;
-    uint4* dkp = reinterpret_cast<uint4*>(dqkv + row + g.C);
-    uint4* dvp = reinterpret_cast<uint4*>(dqkv + row + 2 * g.C);
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      dkp[c] = pack8(dk + c * 8);
-      dvp[c] = pack8(dv + c * 8);
-    }
-  }
+  bf16* dbase = dqkv + h * HD;
+  win_store_rows(dbase, ld, Qs, trow, m0, lane);
+  win_store_rows(dbase + g.C, ld, Ks, trow, m0, lane);
+  win_store_rows(dbase + 2 * g.C, ld, Vs, trow, m0, lane);
 }
 
 int win_attn_fwd(const bf16* qkv, const float* bias, bf16* out, int batch, int R, int C, int heads, int shift, cudaStream_t s) {
   WinGeom g = {R, (R / WIN) * (R / WIN), heads, C, shift};
   const int items = batch * g.nW * heads;
-  const size_t smem = WA_WARPS * (2 * WT * HD + 64) * sizeof(float);
-  static PerDeviceOnce once;
-  if (once.need()) VITATK_CUDA_OK(cudaFuncSetAttribute(win_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  win_attn_fwd_kernel<<<(items + WA_WARPS - 1) / WA_WARPS, WA_WARPS * 32, smem, s>>>(qkv, bias, out, g, items, 1.0f / sqrtf(static_cast<float>(HD)));
+  win_attn_fwd_kernel<<<items, WA_THREADS, 0, s>>>(qkv, bias, out, g, 1.0f / sqrtf(static_cast<float>(HD)));
   VITATK_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -422,11 +625,7 @@ int win_attn_bwd(const bf16* qkv, const bf16* dout, const float* bias, bf16* dqk
                  cudaStream_t s) {
   WinGeom g = {R, (R / WIN) * (R / WIN), heads, C, shift};
   const int items = batch * g.nW * heads;
-  const size_t smem = WB_WARPS * WB_SMEM_FLOATS * sizeof(float);
-  static PerDeviceOnce once;
-  if (once.need()) VITATK_CUDA_OK(cudaFuncSetAttribute(win_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  win_attn_bwd_kernel<<<(items + WB_WARPS - 1) / WB_WARPS, WB_WARPS * 32, smem, s>>>(qkv, dout, bias, dqkv, g, items,
-                                                                                    1.0f / sqrtf(static_cast<float>(HD)));
+  win_attn_bwd_kernel<<<items, WA_THREADS, 0, s>>>(qkv, dout, bias, dqkv, g, 1.0f / sqrtf(static_cast<float>(HD)));
   VITATK_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -1200,6 +1399,23 @@ int vitatk_swin_count_correct(vitatk_swin* e, const float* images, const int64_t
   if (vitatk_swin_forward(e, images, batch, e->logits, stream)) return 1;
   ++e->launches;
   return count_correct(e->logits, labels, batch, e->cfg.num_classes, counts, static_cast<cudaStream_t>(stream));
+}
+
+int vitatk_k_win_attn_fwd(const void* qkv, const float* bias, void* out, int batch, int R, int C, int heads, int shift, void* stream) {
+  if (!qkv || !bias || !out || batch <= 0 || R % WIN || C != heads * HD || shift < 0 || shift >= WIN) {
+    set_error("vitatk_k_win_attn_fwd: bad arguments");
+    return 1;
+  }
+  return win_attn_fwd(static_cast<const bf16*>(qkv), bias, static_cast<bf16*>(out), batch, R, C, heads, shift, static_cast<cudaStream_t>(stream));
+}
+int vitatk_k_win_attn_bwd(const void* qkv, const void* dout, const float* bias, void* dqkv, int batch, int R, int C, int heads, int shift,
+                          void* stream) {
+  if (!qkv || !dout || !bias || !dqkv || batch <= 0 || R % WIN || C != heads * HD || shift < 0 || shift >= WIN) {
+    set_error("vitatk_k_win_attn_bwd: bad arguments");
+    return 1;
+  }
+  return win_attn_bwd(static_cast<const bf16*>(qkv), static_cast<const bf16*>(dout), bias, static_cast<bf16*>(dqkv), batch, R, C, heads,
+                      shift, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -300,6 +300,12 @@ int vitatk_k_pgd_update(const void* dcols_dev, const float* x0_dev, float* adv_d
 int vitatk_k_pgd_init(const float* x0_dev, const float* noise_dev, float* adv_dev, void* cols_dev, int batch,
                       const float* mean3, const float* std3, float eps, int use_rng, uint64_t seed,
                       uint64_t image_index0, void* stream);
+/* 7x7 shifted-window attention of the Swin path on its own (HF modeling_swin.py:410-459, :556-582, :615-636): qkv bf16
+ * [batch*R*R, 3C] token-major, bias fp32 [heads, 49, 49], head dim 32 (C == 32 * heads), 0 <= shift < 7. */
+int vitatk_k_win_attn_fwd(const void* qkv_dev, const float* bias_dev, void* out_dev, int batch, int R, int C, int heads,
+                          int shift, void* stream);
+int vitatk_k_win_attn_bwd(const void* qkv_dev, const void* dout_dev, const float* bias_dev, void* dqkv_dev, int batch,
+                          int R, int C, int heads, int shift, void* stream);
 
 #ifdef __cplusplus
 }

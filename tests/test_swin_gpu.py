@@ -87,3 +87,61 @@ def test_swin_pgd_dropin_invariants(swin):
     assert float(((adv - x).sign() == (ref - x).sign()).float().mean()) > 0.9
     c = eng.count_correct(x, eng.logits(x).argmax(-1))
     assert c.tolist() == [4, 4]
+
+
+def _win_attn_ref(qkv, bias, batch, R, heads, shift):
+    """torch fp32 restatement of HF Swin's shifted-window attention (modeling_swin.py: roll :615-622, window_partition
+    :141-150, scores + relative-position bias + -100 region mask + softmax :428-452, mask :556-582, reverse roll :632-636)
+    on token-major q|k|v rows [batch*R*R, 3*heads*32]."""
+    C = heads * 32
+    nw = R // 7
+    x = qkv.view(batch, R, R, 3, heads, 32)
+    if shift:
+        x = torch.roll(x, (-shift, -shift), dims=(1, 2))
+    x = x.view(batch, nw, 7, nw, 7, 3, heads, 32).permute(5, 0, 1, 3, 6, 2, 4, 7).reshape(3, batch, nw * nw, heads, 49, 32)
+    q, k, v = x[0], x[1], x[2]
+    s = q @ k.transpose(-1, -2) / 32 ** 0.5 + bias[None, None]
+    if shift:
+        img = torch.zeros(R, R, device=qkv.device)
+        cnt = 0
+        for hs in (slice(0, -7), slice(-7, -shift), slice(-shift, None)):
+            for ws in (slice(0, -7), slice(-7, -shift), slice(-shift, None)):
+                img[hs, ws] = cnt
+                cnt += 1
+        mw = img.view(nw, 7, nw, 7).permute(0, 2, 1, 3).reshape(nw * nw, 49)
+        mask = (mw[:, None, :] - mw[:, :, None] != 0).float() * -100.0
+        s = s + mask[None, :, None]
+    o = torch.softmax(s, dim=-1) @ v  # [batch, nW, heads, 49, 32]
+    o = o.view(batch, nw, nw, heads, 7, 7, 32).permute(0, 1, 4, 2, 5, 3, 6).reshape(batch, R, R, C)
+    if shift:
+        o = torch.roll(o, (shift, shift), dims=(1, 2))
+    return o.reshape(batch * R * R, C)
+
+
+@pytest.mark.parametrize("R,heads,shift,batch", [(14, 4, 0, 3), (14, 4, 3, 3), (7, 32, 0, 2), (28, 8, 3, 2), (56, 4, 3, 1)])
+def test_window_attention_kernels_vs_torch(R, heads, shift, batch):
+    """The 7x7 window attention kernels on their own (forward and input-gradient backward) against torch fp32 + autograd."""
+    from vitatk import _lib
+
+    lib = _lib.load()
+    torch.manual_seed(R * 100 + heads + shift)
+    C = heads * 32
+    M = batch * R * R
+    qkv = (torch.randn(M, 3 * C, device="cuda") * 1.5).bfloat16()
+    bias = torch.randn(heads, 49, 49, device="cuda") * 0.5
+    dout = torch.randn(M, C, device="cuda").bfloat16()
+    out = torch.full((M, C), float("nan"), device="cuda", dtype=torch.bfloat16)
+    dqkv = torch.full((M, 3 * C), float("nan"), device="cuda", dtype=torch.bfloat16)
+    st = torch.cuda.current_stream().cuda_stream
+    assert lib.vitatk_k_win_attn_fwd(qkv.data_ptr(), bias.data_ptr(), out.data_ptr(), batch, R, C, heads, shift, st) == 0
+    assert lib.vitatk_k_win_attn_bwd(qkv.data_ptr(), dout.data_ptr(), bias.data_ptr(), dqkv.data_ptr(), batch, R, C, heads, shift, st) == 0
+    torch.cuda.synchronize()
+    ref_in = qkv.float().requires_grad_(True)
+    ref = _win_attn_ref(ref_in, bias, batch, R, heads, shift)
+    ref.backward(dout.float())
+    dref = ref_in.grad
+    e_o = rel(out, ref.detach())
+    e_q, e_k, e_v = (rel(dqkv[:, i * C:(i + 1) * C], dref[:, i * C:(i + 1) * C]) for i in range(3))
+    note(R=R, heads=heads, shift=shift, rel_out=e_o, rel_dq=e_q, rel_dk=e_k, rel_dv=e_v)
+    assert torch.isfinite(out.float()).all() and torch.isfinite(dqkv.float()).all()
+    assert e_o < 1e-2 and e_q < 1.5e-2 and e_k < 1.5e-2 and e_v < 1e-2

@@ -86,7 +86,7 @@ EXPORTS = [
     "vitatk_swin_create", "vitatk_swin_destroy", "vitatk_swin_set_tensor", "vitatk_swin_set_lora", "vitatk_swin_set_normalization",
     "vitatk_swin_finalize", "vitatk_swin_workspace_bytes", "vitatk_swin_launch_count", "vitatk_swin_forward",
     "vitatk_swin_input_grad", "vitatk_swin_attack", "vitatk_swin_count_correct", "vitatk_k_win_attn_fwd",
-    "vitatk_k_win_attn_bwd",
+    "vitatk_k_win_attn_bwd", "vitatk_k_win_bias_table",
 ]
 
 
@@ -144,8 +144,10 @@ def load() -> C.CDLL:
     lib.vitatk_k_layernorm_stats.argtypes = [vp, vp, i, i, f, i, vp]
     lib.vitatk_k_pgd_update.argtypes = [vp, vp, vp, vp, i, C.POINTER(f), C.POINTER(f), f, f, vp]
     lib.vitatk_k_pgd_init.argtypes = [vp, vp, vp, vp, i, C.POINTER(f), C.POINTER(f), f, i, u64, u64, vp]
-    lib.vitatk_k_win_attn_fwd.argtypes = [vp, vp, vp, i, i, i, i, i, vp]
-    lib.vitatk_k_win_attn_bwd.argtypes = [vp, vp, vp, vp, i, i, i, i, i, vp]
+    lib.vitatk_k_win_attn_fwd.argtypes = [vp, vp, i, vp, i, i, i, i, i, vp]
+    lib.vitatk_k_win_attn_bwd.argtypes = [vp, vp, vp, i, vp, i, i, i, i, i, vp]
+    lib.vitatk_k_win_bias_table.argtypes = [vp, vp, i, i, vp]
+    lib.vitatk_k_win_bias_table.restype = C.c_longlong
     lib.vitatk_train_enable.argtypes = [vp, f]
     lib.vitatk_train_bind.argtypes = [vp, vp, vp, ll, ll, ll]
     lib.vitatk_train_set_adapter.argtypes = [vp, i, i, i, f, ll, ll]

@@ -32,14 +32,17 @@ void set_error(const char* fmt, ...) {
 }
 const char* last_error() { return g_err; }
 
+static thread_local int g_pdl_scope = 0;
 bool pdl_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("VITATK_PDL");  // measured on B200: no gain (937.8 vs 941.6 adv img/s), so opt-in
-    v = (e && e[0] == '1') ? 1 : 0;
+  static int v = -2;
+  if (v == -2) {
+    const char* e = getenv("VITATK_PDL");  // ViT PGD step on B200: no gain (937.8 vs 941.6 adv img/s), so opt-in there
+    v = !e ? -1 : (e[0] == '1' ? 1 : 0);
   }
-  return v == 1;
+  return v == 1 || (v == -1 && g_pdl_scope > 0);
 }
+PdlScope::PdlScope(bool on) : saved(g_pdl_scope) { g_pdl_scope = on ? 1 : 0; }
+PdlScope::~PdlScope() { g_pdl_scope = saved; }
 
 static constexpr int TOKENS = 197;
 static constexpr int LORA_PAD = 64;

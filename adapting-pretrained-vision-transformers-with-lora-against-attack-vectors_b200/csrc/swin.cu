@@ -61,6 +61,8 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 __global__ void __launch_bounds__(256) ln_any_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, bf16* __restrict__ y,
                                                          float2* __restrict__ stats, int rows, int cols, float eps) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
   const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * cols);
@@ -96,6 +98,8 @@ __global__ void __launch_bounds__(256) ln_any_fwd_kernel(const bf16* __restrict_
 __global__ void __launch_bounds__(256) ln_any_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                                                          const float2* __restrict__ stats, const float* __restrict__ gamma,
                                                          const bf16* __restrict__ dres, bf16* __restrict__ dx, int rows, int cols) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
   const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * cols);
@@ -144,6 +148,8 @@ template <int LPR, int CPL>
 __global__ void __launch_bounds__(256) ln_reg_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, bf16* __restrict__ y,
                                                          float2* __restrict__ stats, int rows, float eps) {
+  pdl_wait();
+  pdl_launch_dependents();
   constexpr int COLS = 8 * LPR * CPL, RPW = 32 / LPR;
   const int lane = threadIdx.x & 31, sub = lane % LPR;
   const int row = (blockIdx.x * 8 + (threadIdx.x >> 5)) * RPW + lane / LPR;
@@ -183,6 +189,8 @@ template <int LPR, int CPL>
 __global__ void __launch_bounds__(256) ln_reg_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                                                          const float2* __restrict__ stats, const float* __restrict__ gamma,
                                                          const bf16* __restrict__ dres, bf16* __restrict__ dx, int rows) {
+  pdl_wait();
+  pdl_launch_dependents();
   constexpr int COLS = 8 * LPR * CPL, RPW = 32 / LPR;
   const int lane = threadIdx.x & 31, sub = lane % LPR;
   const int row = (blockIdx.x * 8 + (threadIdx.x >> 5)) * RPW + lane / LPR;
@@ -225,14 +233,14 @@ __global__ void __launch_bounds__(256) ln_reg_bwd_kernel(const bf16* __restrict_
 
 int ln_any_fwd(const bf16* x, const float* g, const float* b, bf16* y, float2* st, int rows, int cols, float eps, cudaStream_t s) {
 #define LN_FWD(LPR, CPL)                                                                                                    \
-  ln_reg_fwd_kernel<LPR, CPL><<<(rows + 8 * (32 / LPR) - 1) / (8 * (32 / LPR)), 256, 0, s>>>(x, g, b, y, st, rows, eps)
+  VITATK_CUDA_OK(launch_pdl(ln_reg_fwd_kernel<LPR, CPL>, dim3((rows + 8 * (32 / LPR) - 1) / (8 * (32 / LPR))), dim3(256), 0, s, 1, x, g, b, y, st, rows, eps))
   switch (((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(b)) & 15) ? 0 : cols) {
     case 128: LN_FWD(16, 1); break;
     case 256: LN_FWD(32, 1); break;
     case 512: LN_FWD(32, 2); break;
     case 1024: LN_FWD(32, 4); break;
     case 2048: LN_FWD(32, 8); break;
-    default: ln_any_fwd_kernel<<<(rows + 7) / 8, 256, 0, s>>>(x, g, b, y, st, rows, cols, eps);
+    default: VITATK_CUDA_OK(launch_pdl(ln_any_fwd_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, 1, x, g, b, y, st, rows, cols, eps));
   }
 #undef LN_FWD
   VITATK_CUDA_OK(cudaGetLastError());
@@ -241,14 +249,14 @@ int ln_any_fwd(const bf16* x, const float* g, const float* b, bf16* y, float2* s
 int ln_any_bwd(const bf16* dy, const bf16* x, const float2* st, const float* g, const bf16* dres, bf16* dx, int rows, int cols,
                cudaStream_t s) {
 #define LN_BWD(LPR, CPL)                                                                                                    \
-  ln_reg_bwd_kernel<LPR, CPL><<<(rows + 8 * (32 / LPR) - 1) / (8 * (32 / LPR)), 256, 0, s>>>(dy, x, st, g, dres, dx, rows)
+  VITATK_CUDA_OK(launch_pdl(ln_reg_bwd_kernel<LPR, CPL>, dim3((rows + 8 * (32 / LPR) - 1) / (8 * (32 / LPR))), dim3(256), 0, s, 1, dy, x, st, g, dres, dx, rows))
   switch ((reinterpret_cast<uintptr_t>(g) & 15) ? 0 : cols) {
     case 128: LN_BWD(16, 1); break;
     case 256: LN_BWD(32, 1); break;
     case 512: LN_BWD(32, 2); break;
     case 1024: LN_BWD(32, 4); break;
     case 2048: LN_BWD(32, 8); break;
-    default: ln_any_bwd_kernel<<<(rows + 7) / 8, 256, 0, s>>>(dy, x, st, g, dres, dx, rows, cols);
+    default: VITATK_CUDA_OK(launch_pdl(ln_any_bwd_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, 1, dy, x, st, g, dres, dx, rows, cols));
   }
 #undef LN_BWD
   VITATK_CUDA_OK(cudaGetLastError());
@@ -260,6 +268,8 @@ int ln_any_bwd(const bf16* dy, const bf16* x, const float2* st, const float* g, 
 // (k = 0..3 in HF's concat order: (0,0), (1,0), (0,1), (1,1)).  One thread per 16-byte chunk.  scatter = the inverse.
 // ------------------------------------------------------------------------------------------------
 __global__ void merge_permute_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int batch, int R, int C, int scatter) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int chunks = C >> 3, R2 = R >> 1;
   const long long total = static_cast<long long>(batch) * R2 * R2 * 4 * chunks;
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -278,7 +288,7 @@ __global__ void merge_permute_kernel(const bf16* __restrict__ in, bf16* __restri
 }
 int merge_permute(const bf16* in, bf16* out, int batch, int R, int C, int scatter, cudaStream_t s) {
   const long long total = static_cast<long long>(batch) * (R / 2) * (R / 2) * 4 * (C / 8);
-  merge_permute_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(in, out, batch, R, C, scatter);
+  VITATK_CUDA_OK(launch_pdl(merge_permute_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, s, 1, in, out, batch, R, C, scatter));
   VITATK_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -307,16 +317,6 @@ __device__ __forceinline__ int win_token_row(const WinGeom& g, int b, int win, i
   if (x >= g.R) x -= g.R;
   return (b * g.R + y) * g.R + x;
 }
-// region id of a shifted position (modeling_swin.py:556-575): tokens of different regions must not attend to each other
-__device__ __forceinline__ int win_region(const WinGeom& g, int win, int t) {
-  if (g.shift == 0) return 0;
-  const int wpr = g.R / WIN;
-  const int ys = (win / wpr) * WIN + t / WIN, xs = (win % wpr) * WIN + t % WIN;
-  const int ry = ys < g.R - WIN ? 0 : (ys < g.R - g.shift ? 1 : 2);
-  const int rx = xs < g.R - WIN ? 0 : (xs < g.R - g.shift ? 1 : 2);
-  return ry * 3 + rx;
-}
-
 constexpr int WPAD = 64;  // tokens of a window, padded to four 16-row MMA tiles
 constexpr int QS = 40;    // row stride (elements) of the [64][32] operand tiles: 80 B, ldmatrix conflict-free
 constexpr int PS = 72;    // row stride of the [64][64] P / dS tiles: 144 B
@@ -338,6 +338,11 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<const uint32_t*>(&v);
@@ -352,13 +357,40 @@ __device__ __forceinline__ int frag_c_hi(int lane) { return (lane >> 4) * 8; }  
 __device__ __forceinline__ int frag_r_hi(int lane) { return (lane & 7) + (lane >> 4) * 8; }          // r + (i >> 1) * 8
 __device__ __forceinline__ int frag_c_lo(int lane) { return ((lane >> 3) & 1) * 8; }                 // (i & 1) * 8
 
-// rows [0, 49) of one [token][32] head slice -> shared [64][QS]; rows 49..63 zero
-__device__ __forceinline__ void win_load_tile(bf16* dst, const bf16* src, size_t ld, const int* trow, int tid) {
-  for (int c = tid; c < WPAD * 4; c += WA_THREADS) {
-    const int t = c >> 2, d8 = (c & 3) * 8;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (t < WT) v = __ldg(reinterpret_cast<const uint4*>(src + static_cast<size_t>(trow[t]) * ld + d8));
-    *reinterpret_cast<uint4*>(dst + t * QS + d8) = v;
+// Loading a unit: thread tid owns the 16-byte chunk (tid & 3) of token rows t0 = tid >> 2 (always a real token) and
+// t1 = t0 + 32 (a real token when < 49, else a zero row of the padding).  All global loads of a thread are issued before
+// the first shared-memory store.
+struct WinRows {
+  size_t r0, r1;  // global token rows
+  bool has1;
+};
+__device__ __forceinline__ WinRows win_rows(const WinGeom& g, int b, int win, int tid, int* trow) {
+  const int t0 = tid >> 2, t1 = t0 + 32;
+  WinRows w;
+  w.has1 = t1 < WT;
+  const int a0 = win_token_row(g, b, win, t0), a1 = w.has1 ? win_token_row(g, b, win, t1) : 0;
+  if ((tid & 3) == 0) {
+    trow[t0] = a0;
+    trow[t1] = a1;
+  }
+  w.r0 = static_cast<size_t>(a0);
+  w.r1 = static_cast<size_t>(a1);
+  return w;
+}
+template <int N>
+__device__ __forceinline__ void win_load_tiles(bf16* const (&dst)[N], const bf16* const (&src)[N], const size_t (&ld)[N], const WinRows& w,
+                                               int tid) {
+  const int d8 = (tid & 3) * 8, t0 = tid >> 2;
+  uint4 v0[N], v1[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    v0[i] = __ldg(reinterpret_cast<const uint4*>(src[i] + w.r0 * ld[i] + d8));
+    v1[i] = w.has1 ? __ldg(reinterpret_cast<const uint4*>(src[i] + w.r1 * ld[i] + d8)) : make_uint4(0u, 0u, 0u, 0u);
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    *reinterpret_cast<uint4*>(dst[i] + t0 * QS + d8) = v0[i];
+    *reinterpret_cast<uint4*>(dst[i] + (t0 + 32) * QS + d8) = v1[i];
   }
 }
 // 16 rows [m0, m0 + 16) of a staged [64][QS] tile -> global rows (row stride ld), 16-byte stores
@@ -378,11 +410,54 @@ __device__ __forceinline__ void win_stage_acc(bf16* tile, const float (&o)[4][4]
     *reinterpret_cast<uint32_t*>(tile + (m0 + g + 8) * QS + nt * 8 + 2 * t) = pack_bf16x2(o[nt][2] * s_hi, o[nt][3] * s_hi);
   }
 }
-// S = scale * Q K^T + bias + region mask for the warp's 16 query rows, then the row softmax statistics.
-// On return p[nt][e] = exp(s - rowmax) (0 for key columns >= 49 and for query rows >= 49), inv_* = 1 / rowsum.
-__device__ __forceinline__ void win_scores(float (&p)[8][4], float& inv_lo, float& inv_hi, const bf16* Qs, const bf16* Ks,
-                                           const int* reg, const float* __restrict__ bh, float scale, int m0, int lane) {
+// Relative-position bias + shifted-window mask in FRAGMENT order: for every (variant, head) a [warp 4][n-tile 7][lane 32]
+// array of float4 = the four accumulator elements (rows g, g + 8; key columns 2t, 2t + 1) of that lane, so the softmax
+// prologue is seven coalesced 16-byte loads and 28 FMAs with no index arithmetic, compares or branches.  Key columns
+// >= 49 hold -inf, padded query rows 0.  variant: bit 1 = window in the last window row, bit 0 = in the last window column
+// of a shifted block (modeling_swin.py:556-575: only those windows straddle the cyclic seam and mask by region).
+constexpr int BIAS_FRAG_F4 = 4 * 7 * 32;  // float4 per (variant, head)
+__global__ void relbias_frag_kernel(const float* __restrict__ bias, float4* __restrict__ out, int heads, int shift, int variants) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= variants * heads * BIAS_FRAG_F4) return;
+  const int lane = idx & 31, nt = (idx >> 5) % 7, warp = (idx / 224) & 3, h = (idx / BIAS_FRAG_F4) % heads, v = idx / (BIAS_FRAG_F4 * heads);
   const int g = lane >> 2, t = lane & 3;
+  float val[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int i = warp * 16 + g + (e >> 1) * 8, j = nt * 8 + 2 * t + (e & 1);
+    float x = 0.f;
+    if (j >= WT) x = -INFINITY;
+    else if (i < WT) {
+      x = bias[(static_cast<size_t>(h) * WT + i) * WT + j];
+      const int ryi = (v & 2) ? (i / WIN < WIN - shift ? 1 : 2) : 0, ryj = (v & 2) ? (j / WIN < WIN - shift ? 1 : 2) : 0;
+      const int rxi = (v & 1) ? (i % WIN < WIN - shift ? 1 : 2) : 0, rxj = (v & 1) ? (j % WIN < WIN - shift ? 1 : 2) : 0;
+      if (ryi != ryj || rxi != rxj) x -= 100.f;
+    }
+    val[e] = x;
+  }
+  out[idx] = make_float4(val[0], val[1], val[2], val[3]);
+}
+int relbias_frag(const float* bias, float* out, int heads, int shift, cudaStream_t s) {
+  const int variants = shift ? 4 : 1, total = variants * heads * BIAS_FRAG_F4;
+  relbias_frag_kernel<<<(total + 255) / 256, 256, 0, s>>>(bias, reinterpret_cast<float4*>(out), heads, shift, variants);
+  VITATK_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+size_t relbias_frag_bytes(int heads, int shift) { return static_cast<size_t>(shift ? 4 : 1) * heads * BIAS_FRAG_F4 * sizeof(float4); }
+__device__ __forceinline__ const float4* win_bias_tab(const float* tab, const WinGeom& g, int win, int h, int warp) {
+  const int wpr = g.R / WIN;
+  const int v = g.shift ? ((win / wpr == wpr - 1 ? 2 : 0) | (win % wpr == wpr - 1 ? 1 : 0)) : 0;
+  return reinterpret_cast<const float4*>(tab) + (static_cast<size_t>(v) * g.heads + h) * BIAS_FRAG_F4 + warp * (7 * 32);
+}
+
+// S = scale * Q K^T + (bias + region mask) for the warp's 16 query rows, then the row softmax statistics.
+// On return p[nt][e] = exp(s - rowmax) (0 for key columns >= 49), inv_* = 1 / rowsum (0 for query rows >= 49).
+__device__ __forceinline__ void win_scores(float (&p)[8][4], float& inv_lo, float& inv_hi, const bf16* Qs, const bf16* Ks,
+                                           const float4* __restrict__ tab, float scale, int m0, int lane) {
+  const int g = lane >> 2;
+  float4 bz[7];
+#pragma unroll
+  for (int nt = 0; nt < 7; ++nt) bz[nt] = __ldg(tab + nt * 32 + lane);
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
@@ -400,51 +475,40 @@ __device__ __forceinline__ void win_scores(float (&p)[8][4], float& inv_lo, floa
       if (np < 3) mma16816(p[2 * np + 1], aq[ks], bk[2], bk[3]);
     }
   }
-  const int i_lo = m0 + g, i_hi = i_lo + 8;
-  const int r_lo = reg[i_lo], r_hi = reg[i_hi];
   float mx_lo = -INFINITY, mx_hi = -INFINITY;
 #pragma unroll
   for (int nt = 0; nt < 7; ++nt) {
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int j = nt * 8 + 2 * t + e;
-      float lo = -INFINITY, hi = -INFINITY;
-      if (j < WT) {
-        const int rj = reg[j];
-        if (i_lo < WT) lo = fmaf(p[nt][e], scale, __ldg(bh + i_lo * WT + j)) - (rj != r_lo ? 100.f : 0.f);
-        if (i_hi < WT) hi = fmaf(p[nt][2 + e], scale, __ldg(bh + i_hi * WT + j)) - (rj != r_hi ? 100.f : 0.f);
-      }
-      p[nt][e] = lo;
-      p[nt][2 + e] = hi;
-      mx_lo = fmaxf(mx_lo, lo);
-      mx_hi = fmaxf(mx_hi, hi);
-    }
+    p[nt][0] = fmaf(p[nt][0], scale, bz[nt].x);
+    p[nt][1] = fmaf(p[nt][1], scale, bz[nt].y);
+    p[nt][2] = fmaf(p[nt][2], scale, bz[nt].z);
+    p[nt][3] = fmaf(p[nt][3], scale, bz[nt].w);
+    mx_lo = fmaxf(mx_lo, fmaxf(p[nt][0], p[nt][1]));
+    mx_hi = fmaxf(mx_hi, fmaxf(p[nt][2], p[nt][3]));
   }
   mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1));
   mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
   mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1));
   mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
-  if (i_lo >= WT) mx_lo = 0.f;  // padded query rows: exp(-inf - 0) = 0 everywhere, no NaN
-  if (i_hi >= WT) mx_hi = 0.f;
+  // exp(s - mx) = 2^(s * log2e - mx * log2e): one FFMA + one MUFU.EX2 per element
+  constexpr float LOG2E = 1.4426950408889634f;
+  const float nm_lo = -mx_lo * LOG2E, nm_hi = -mx_hi * LOG2E;
   float sum_lo = 0.f, sum_hi = 0.f;
 #pragma unroll
   for (int nt = 0; nt < 7; ++nt) {
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      p[nt][e] = __expf(p[nt][e] - mx_lo);
-      p[nt][2 + e] = __expf(p[nt][2 + e] - mx_hi);
+      p[nt][e] = ex2_approx(fmaf(p[nt][e], LOG2E, nm_lo));
+      p[nt][2 + e] = ex2_approx(fmaf(p[nt][2 + e], LOG2E, nm_hi));
       sum_lo += p[nt][e];
       sum_hi += p[nt][2 + e];
     }
   }
-#pragma unroll
-  for (int e = 0; e < 4; ++e) p[7][e] = 0.f;
   sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 1);
   sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 2);
   sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 1);
   sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 2);
-  inv_lo = i_lo < WT ? 1.f / sum_lo : 0.f;
-  inv_hi = i_hi < WT ? 1.f / sum_hi : 0.f;
+  inv_lo = m0 + g < WT ? 1.f / sum_lo : 0.f;
+  inv_hi = m0 + g + 8 < WT ? 1.f / sum_hi : 0.f;
 }
 // acc[16][32] += X[16][64] * Y[64][32]: X from accumulator-layout registers (eight n-tiles = four k-steps), Y stored [k][n]
 __device__ __forceinline__ void win_mma_regA(float (&acc)[4][4], const float (&x)[8][4], const bf16* Ys, int lane) {
@@ -482,25 +546,26 @@ __device__ __forceinline__ void win_mma_transA(float (&acc)[4][4], const bf16* X
 
 __global__ void __launch_bounds__(WA_THREADS) win_attn_fwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ bias,
                                                                   bf16* __restrict__ out, WinGeom g, float scale) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ __align__(16) bf16 Qs[WPAD * QS], Ks[WPAD * QS], Vs[WPAD * QS];
-  __shared__ int reg[WPAD], trow[WPAD];
+  __shared__ int trow[WPAD];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int item = blockIdx.x;
   const int h = item % g.heads, win = (item / g.heads) % g.nW, b = item / (g.heads * g.nW);
   const size_t ld = 3 * static_cast<size_t>(g.C);
-  if (tid < WPAD) {
-    reg[tid] = tid < WT ? win_region(g, win, tid) : -1;
-    trow[tid] = tid < WT ? win_token_row(g, b, win, tid) : 0;
+  {
+    const WinRows wr = win_rows(g, b, win, tid, trow);
+    const bf16* base = qkv + h * HD;
+    bf16* const dst[3] = {Qs, Ks, Vs};
+    const bf16* const srcs[3] = {base, base + g.C, base + 2 * g.C};
+    const size_t lds[3] = {ld, ld, ld};
+    win_load_tiles<3>(dst, srcs, lds, wr, tid);
   }
-  __syncthreads();
-  const bf16* base = qkv + h * HD;
-  win_load_tile(Qs, base, ld, trow, tid);
-  win_load_tile(Ks, base + g.C, ld, trow, tid);
-  win_load_tile(Vs, base + 2 * g.C, ld, trow, tid);
   __syncthreads();
   const int m0 = warp * 16;
   float p[8][4], inv_lo, inv_hi;
-  win_scores(p, inv_lo, inv_hi, Qs, Ks, reg, bias + static_cast<size_t>(h) * WT * WT, scale, m0, lane);
+  win_scores(p, inv_lo, inv_hi, Qs, Ks, win_bias_tab(bias, g, win, h, warp), scale, m0, lane);
   float o[4][4];
 #pragma unroll
   for (int nt = 0; nt < 4; ++nt)
@@ -519,29 +584,29 @@ __global__ void __launch_bounds__(WA_THREADS) win_attn_fwd_kernel(const bf16* __
 __global__ void __launch_bounds__(WA_THREADS) win_attn_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
                                                                   const float* __restrict__ bias, bf16* __restrict__ dqkv,
                                                                   WinGeom g, float scale) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ __align__(16) bf16 Qs[WPAD * QS], Ks[WPAD * QS], Vs[WPAD * QS], Gs[WPAD * QS];
   __shared__ __align__(16) bf16 Ps[WPAD * PS], Ds[WPAD * PS];
-  __shared__ int reg[WPAD], trow[WPAD];
+  __shared__ int trow[WPAD];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int item = blockIdx.x;
   const int h = item % g.heads, win = (item / g.heads) % g.nW, b = item / (g.heads * g.nW);
   const size_t ld = 3 * static_cast<size_t>(g.C);
-  if (tid < WPAD) {
-    reg[tid] = tid < WT ? win_region(g, win, tid) : -1;
-    trow[tid] = tid < WT ? win_token_row(g, b, win, tid) : 0;
+  {
+    const WinRows wr = win_rows(g, b, win, tid, trow);
+    const bf16* base = qkv + h * HD;
+    bf16* const dst[4] = {Qs, Ks, Vs, Gs};
+    const bf16* const srcs[4] = {base, base + g.C, base + 2 * g.C, dout + h * HD};
+    const size_t lds[4] = {ld, ld, ld, static_cast<size_t>(g.C)};
+    win_load_tiles<4>(dst, srcs, lds, wr, tid);
   }
-  __syncthreads();
-  const bf16* base = qkv + h * HD;
-  win_load_tile(Qs, base, ld, trow, tid);
-  win_load_tile(Ks, base + g.C, ld, trow, tid);
-  win_load_tile(Vs, base + 2 * g.C, ld, trow, tid);
-  win_load_tile(Gs, dout + h * HD, static_cast<size_t>(g.C), trow, tid);
   __syncthreads();
   const int m0 = warp * 16, gq = lane >> 2, tq = lane & 3;
   float dq[4][4];
   {
     float p[8][4], inv_lo, inv_hi;
-    win_scores(p, inv_lo, inv_hi, Qs, Ks, reg, bias + static_cast<size_t>(h) * WT * WT, scale, m0, lane);
+    win_scores(p, inv_lo, inv_hi, Qs, Ks, win_bias_tab(bias, g, win, h, warp), scale, m0, lane);
     // dP = dO V^T (V stored [key][dim] = the "col" B operand, like K in the scores)
     float dp[8][4];
 #pragma unroll
@@ -614,19 +679,17 @@ __global__ void __launch_bounds__(WA_THREADS) win_attn_bwd_kernel(const bf16* __
   win_store_rows(dbase + 2 * g.C, ld, Vs, trow, m0, lane);
 }
 
-int win_attn_fwd(const bf16* qkv, const float* bias, bf16* out, int batch, int R, int C, int heads, int shift, cudaStream_t s) {
+int win_attn_fwd(const bf16* qkv, const float* bias_frag, bf16* out, int batch, int R, int C, int heads, int shift, cudaStream_t s) {
   WinGeom g = {R, (R / WIN) * (R / WIN), heads, C, shift};
   const int items = batch * g.nW * heads;
-  win_attn_fwd_kernel<<<items, WA_THREADS, 0, s>>>(qkv, bias, out, g, 1.0f / sqrtf(static_cast<float>(HD)));
-  VITATK_CUDA_OK(cudaGetLastError());
+  VITATK_CUDA_OK(launch_pdl(win_attn_fwd_kernel, dim3(items), dim3(WA_THREADS), 0, s, 1, qkv, bias_frag, out, g, 1.0f / sqrtf(static_cast<float>(HD))));
   return 0;
 }
-int win_attn_bwd(const bf16* qkv, const bf16* dout, const float* bias, bf16* dqkv, int batch, int R, int C, int heads, int shift,
+int win_attn_bwd(const bf16* qkv, const bf16* dout, const float* bias_frag, bf16* dqkv, int batch, int R, int C, int heads, int shift,
                  cudaStream_t s) {
   WinGeom g = {R, (R / WIN) * (R / WIN), heads, C, shift};
   const int items = batch * g.nW * heads;
-  win_attn_bwd_kernel<<<items, WA_THREADS, 0, s>>>(qkv, dout, bias, dqkv, g, 1.0f / sqrtf(static_cast<float>(HD)));
-  VITATK_CUDA_OK(cudaGetLastError());
+  VITATK_CUDA_OK(launch_pdl(win_attn_bwd_kernel, dim3(items), dim3(WA_THREADS), 0, s, 1, qkv, dout, bias_frag, dqkv, g, 1.0f / sqrtf(static_cast<float>(HD))));
   return 0;
 }
 
@@ -806,6 +869,7 @@ struct BlockW {
   const bf16 *qkv_w = nullptr, *qkv_wt = nullptr, *proj_w = nullptr, *proj_wt = nullptr, *fc1_w = nullptr, *fc1_wt = nullptr,
              *fc2_w = nullptr, *fc2_wt = nullptr;
   const float *qkv_b = nullptr, *proj_b = nullptr, *fc1_b = nullptr, *fc2_b = nullptr, *relbias = nullptr;
+  float* bias_frag = nullptr;  // engine-owned fragment-order copy of relbias (+ region masks), relbias_frag()
   struct Lora {
     int rank = 0;
     const bf16 *la_fwd = nullptr, *lb_fwd = nullptr, *lb_bwd = nullptr, *la_bwd = nullptr;
@@ -846,6 +910,7 @@ struct vitatk_swin {
   StageW stg[3];
   char* ws = nullptr;
   long long ws_bytes = 0;
+  char* bias_tab = nullptr;  // fragment-order relative-position bias tables of every block
   // scratch sized for the largest stage
   bf16 *cols = nullptr, *e0 = nullptr, *xn = nullptr, *g = nullptr, *T = nullptr, *dA = nullptr, *dB = nullptr, *dxn = nullptr,
        *dao = nullptr, *du = nullptr, *dqkv = nullptr, *xm = nullptr;
@@ -867,6 +932,12 @@ int swin_dims(const vitatk_swin* e, int s, int* C, int* R) {
   *C = e->cfg.embed_dim << s;
   *R = (e->cfg.image_size / e->cfg.patch_size) >> s;
   return 0;
+}
+// cyclic shift of block bi of stage s (modeling_swin.py:592-600: odd blocks, unless the stage is a single window)
+int swin_shift(const vitatk_swin* e, int s, int bi) {
+  int C, R;
+  swin_dims(e, s, &C, &R);
+  return (bi % 2 == 1 && R > e->cfg.window) ? e->cfg.window / 2 : 0;
 }
 
 int build_swin_plans(vitatk_swin* e, int batch, SwinPlans** out) {
@@ -1003,6 +1074,7 @@ int build_swin_plans(vitatk_swin* e, int batch, SwinPlans** out) {
 
 // forward from e->cols (normalised im2col of the input) to the last stage's output in e->hfin
 int swin_forward(vitatk_swin* e, SwinPlans* ps, int batch, cudaStream_t s) {
+  PdlScope pdl(true);  // short kernels: overlap each launch ramp with the previous kernel (vitatk_internal.h)
   const vitatk_swin_config& c = e->cfg;
   const int R0 = c.image_size / c.patch_size, C0 = c.embed_dim;
   SGEMM(&ps->patch);
@@ -1014,11 +1086,11 @@ int swin_forward(vitatk_swin* e, SwinPlans* ps, int batch, cudaStream_t s) {
     for (int bi = 0; bi < c.depths[st]; ++bi) {
       BlockW& w = e->blk[st][bi];
       BlockPlans& p = ps->blocks[st][bi];
-      const int shift = (bi % 2 == 1 && R > c.window) ? c.window / 2 : 0;
+      const int shift = swin_shift(e, st, bi);
       SRUN(ln_any_fwd(w.h_in, w.ln1_g, w.ln1_b, e->xn, w.st1, M, C, c.ln_eps, s));
       if (w.lora[VITATK_SITE_QKV].rank > 0) SGEMM(&p.t_qkv);
       SGEMM(&p.qkv);
-      SRUN(win_attn_fwd(w.qkv, w.relbias, w.ao, batch, R, C, heads, shift, s));
+      SRUN(win_attn_fwd(w.qkv, w.bias_frag, w.ao, batch, R, C, heads, shift, s));
       if (w.lora[VITATK_SITE_PROJ].rank > 0) SGEMM(&p.t_proj);
       SGEMM(&p.proj);
       SRUN(ln_any_fwd(w.h_mid, w.ln2_g, w.ln2_b, e->xn, w.st2, M, C, c.ln_eps, s));
@@ -1038,6 +1110,7 @@ int swin_forward(vitatk_swin* e, SwinPlans* ps, int batch, cudaStream_t s) {
 
 // backward from dA = d loss / d (last stage output) down to e->dqkv = d loss / d cols
 int swin_backward(vitatk_swin* e, SwinPlans* ps, int batch, cudaStream_t s) {
+  PdlScope pdl(true);  // short kernels: overlap each launch ramp with the previous kernel (vitatk_internal.h)
   const vitatk_swin_config& c = e->cfg;
   const int R0 = c.image_size / c.patch_size, C0 = c.embed_dim;
   for (int st = 3; st >= 0; --st) {
@@ -1054,7 +1127,7 @@ int swin_backward(vitatk_swin* e, SwinPlans* ps, int batch, cudaStream_t s) {
     for (int bi = c.depths[st] - 1; bi >= 0; --bi) {
       BlockW& w = e->blk[st][bi];
       BlockPlans& p = ps->blocks[st][bi];
-      const int shift = (bi % 2 == 1 && R > c.window) ? c.window / 2 : 0;
+      const int shift = swin_shift(e, st, bi);
       if (w.lora[VITATK_SITE_FC2].rank > 0) SGEMM(&p.bt_fc2);
       SGEMM(&p.bfc2);
       if (w.lora[VITATK_SITE_FC1].rank > 0) SGEMM(&p.bt_fc1);
@@ -1062,7 +1135,7 @@ int swin_backward(vitatk_swin* e, SwinPlans* ps, int batch, cudaStream_t s) {
       SRUN(ln_any_bwd(e->dxn, w.h_mid, w.st2, w.ln2_g, e->dA, e->dB, M, C, s));
       if (w.lora[VITATK_SITE_PROJ].rank > 0) SGEMM(&p.bt_proj);
       SGEMM(&p.bproj);
-      SRUN(win_attn_bwd(w.qkv, e->dao, w.relbias, e->dqkv, batch, R, C, heads, shift, s));
+      SRUN(win_attn_bwd(w.qkv, e->dao, w.bias_frag, e->dqkv, batch, R, C, heads, shift, s));
       if (w.lora[VITATK_SITE_QKV].rank > 0) SGEMM(&p.bt_qkv);
       SGEMM(&p.bqkv);
       SRUN(ln_any_bwd(e->dxn, w.h_in, w.st1, w.ln1_g, e->dB, e->dA, M, C, s));
@@ -1149,6 +1222,7 @@ int vitatk_swin_destroy(vitatk_swin* e) {
   if (!e) return 0;
   for (auto& kv : e->plans) delete kv.second;
   if (e->ws) cudaFree(e->ws);
+  if (e->bias_tab) cudaFree(e->bias_tab);
   delete e;
   return 0;
 }
@@ -1203,7 +1277,14 @@ int vitatk_swin_set_tensor(vitatk_swin* e, int id, int stage, int block, const v
       case VITATK_SWIN_QKV_W: w.qkv_w = pb; want = 3 * C * C * 2; break;
       case VITATK_SWIN_QKV_WT: w.qkv_wt = pb; want = 3 * C * C * 2; break;
       case VITATK_SWIN_QKV_B: w.qkv_b = pf; want = 3 * C * 4; break;
-      case VITATK_SWIN_RELBIAS: w.relbias = pf; want = static_cast<long long>(c.heads[stage]) * WT * WT * 4; break;
+      case VITATK_SWIN_RELBIAS:
+        w.relbias = pf;
+        want = static_cast<long long>(c.heads[stage]) * WT * WT * 4;
+        if (e->finalized && nbytes == want) {  // re-derive the engine-owned fragment-order copy
+          if (relbias_frag(pf, w.bias_frag, c.heads[stage], swin_shift(e, stage, block), nullptr)) return 1;
+          VITATK_CUDA_OK(cudaStreamSynchronize(nullptr));
+        }
+        break;
       case VITATK_SWIN_PROJ_W: w.proj_w = pb; want = C * C * 2; break;
       case VITATK_SWIN_PROJ_WT: w.proj_wt = pb; want = C * C * 2; break;
       case VITATK_SWIN_PROJ_B: w.proj_b = pf; want = C * 4; break;
@@ -1322,6 +1403,22 @@ int vitatk_swin_finalize(vitatk_swin* e) {
   e->logits = reinterpret_cast<float*>(take(B * c.num_classes * 4));
   e->loss = reinterpret_cast<float*>(take(B * 4));
   e->scratch_img = reinterpret_cast<float*>(take(B * 3 * IMG * IMG * 4));
+  // relative-position bias + region masks in MMA fragment order (relbias_frag_kernel), one table per block
+  size_t tab_bytes = 0;
+  for (int s = 0; s < 4; ++s)
+    for (int bi = 0; bi < c.depths[s]; ++bi) tab_bytes += relbias_frag_bytes(c.heads[s], swin_shift(e, s, bi));
+  VITATK_CUDA_OK(cudaMalloc(&e->bias_tab, tab_bytes));
+  char* tp = e->bias_tab;
+  for (int s = 0; s < 4; ++s) {
+    for (int bi = 0; bi < c.depths[s]; ++bi) {
+      BlockW& w = e->blk[s][bi];
+      w.bias_frag = reinterpret_cast<float*>(tp);
+      tp += relbias_frag_bytes(c.heads[s], swin_shift(e, s, bi));
+      if (relbias_frag(w.relbias, w.bias_frag, c.heads[s], swin_shift(e, s, bi), nullptr)) return 1;
+    }
+  }
+  VITATK_CUDA_OK(cudaStreamSynchronize(nullptr));
+  e->ws_bytes += static_cast<long long>(tab_bytes);
   e->finalized = true;
   return 0;
 }
@@ -1401,21 +1498,46 @@ int vitatk_swin_count_correct(vitatk_swin* e, const float* images, const int64_t
   return count_correct(e->logits, labels, batch, e->cfg.num_classes, counts, static_cast<cudaStream_t>(stream));
 }
 
-int vitatk_k_win_attn_fwd(const void* qkv, const float* bias, void* out, int batch, int R, int C, int heads, int shift, void* stream) {
+long long vitatk_k_win_bias_table(const float* bias, float* table, int heads, int shift, void* stream) {
+  if (heads <= 0 || shift < 0 || shift >= WIN) {
+    set_error("vitatk_k_win_bias_table: bad arguments");
+    return -1;
+  }
+  if (bias && table && relbias_frag(bias, table, heads, shift, static_cast<cudaStream_t>(stream))) return -1;
+  return static_cast<long long>(relbias_frag_bytes(heads, shift));
+}
+// bias_is_table = 0: bias is the [heads, 49, 49] table (a temporary fragment-order copy is made per call); 1: bias is the
+// fragment-order table vitatk_k_win_bias_table wrote for the same (heads, shift)
+int vitatk_k_win_attn_fwd(const void* qkv, const float* bias, int bias_is_table, void* out, int batch, int R, int C, int heads, int shift,
+                          void* stream) {
   if (!qkv || !bias || !out || batch <= 0 || R % WIN || C != heads * HD || shift < 0 || shift >= WIN) {
     set_error("vitatk_k_win_attn_fwd: bad arguments");
     return 1;
   }
-  return win_attn_fwd(static_cast<const bf16*>(qkv), bias, static_cast<bf16*>(out), batch, R, C, heads, shift, static_cast<cudaStream_t>(stream));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (bias_is_table) return win_attn_fwd(static_cast<const bf16*>(qkv), bias, static_cast<bf16*>(out), batch, R, C, heads, shift, s);
+  float* tab = nullptr;
+  VITATK_CUDA_OK(cudaMallocAsync(&tab, relbias_frag_bytes(heads, shift), s));
+  int rc = relbias_frag(bias, tab, heads, shift, s);
+  if (!rc) rc = win_attn_fwd(static_cast<const bf16*>(qkv), tab, static_cast<bf16*>(out), batch, R, C, heads, shift, s);
+  cudaFreeAsync(tab, s);
+  return rc;
 }
-int vitatk_k_win_attn_bwd(const void* qkv, const void* dout, const float* bias, void* dqkv, int batch, int R, int C, int heads, int shift,
-                          void* stream) {
+int vitatk_k_win_attn_bwd(const void* qkv, const void* dout, const float* bias, int bias_is_table, void* dqkv, int batch, int R, int C,
+                          int heads, int shift, void* stream) {
   if (!qkv || !dout || !bias || !dqkv || batch <= 0 || R % WIN || C != heads * HD || shift < 0 || shift >= WIN) {
     set_error("vitatk_k_win_attn_bwd: bad arguments");
     return 1;
   }
-  return win_attn_bwd(static_cast<const bf16*>(qkv), static_cast<const bf16*>(dout), bias, static_cast<bf16*>(dqkv), batch, R, C, heads,
-                      shift, static_cast<cudaStream_t>(stream));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (bias_is_table)
+    return win_attn_bwd(static_cast<const bf16*>(qkv), static_cast<const bf16*>(dout), bias, static_cast<bf16*>(dqkv), batch, R, C, heads, shift, s);
+  float* tab = nullptr;
+  VITATK_CUDA_OK(cudaMallocAsync(&tab, relbias_frag_bytes(heads, shift), s));
+  int rc = relbias_frag(bias, tab, heads, shift, s);
+  if (!rc) rc = win_attn_bwd(static_cast<const bf16*>(qkv), static_cast<const bf16*>(dout), tab, static_cast<bf16*>(dqkv), batch, R, C, heads, shift, s);
+  cudaFreeAsync(tab, s);
+  return rc;
 }
 
 }  // extern "C"

@@ -28,14 +28,22 @@ const char* last_error();
 // pdl_wait() before their first global-memory access (the previous kernel in the stream has then completed and its
 // writes are visible) and pdl_launch_dependents() right after, so the NEXT kernel's launch latency and prologue
 // (barrier init, TMEM allocation, descriptor prefetch) overlap this kernel's execution / tail.  Measured on B200 it
-// changes nothing for this workload (the ~2700 launches per PGD-10 step are already queued ahead of the GPU), so the
-// launch attribute is opt-in: VITATK_PDL=1.  Without the attribute griddepcontrol.* are no-ops.
+// changes nothing for the ViT PGD step (its ~2700 launches run 100 us each), so there the launch attribute is opt-in:
+// VITATK_PDL=1.  The Swin path is the opposite case -- 560 launches of 10-50 us per iteration, a quarter of which is the
+// per-kernel ramp -- and turns it on for its own launches (PdlScope; VITATK_PDL=0 turns it off): 20.5 -> 19.6 ms per
+// iteration with only the GEMMs taking part.  Without the attribute griddepcontrol.* are no-ops.
 // ---------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #endif
 bool pdl_enabled();
+// Engine-scoped default: while a PdlScope(true) is alive on this thread, pdl_enabled() is true unless VITATK_PDL=0.
+struct PdlScope {
+  explicit PdlScope(bool on);
+  ~PdlScope();
+  int saved;
+};
 
 // cudaFuncSetAttribute (the > 48 KB dynamic shared memory opt-in) applies to the CURRENT device only, so "done once" has
 // to be remembered per device: a process may hold engines on several GPUs (Engine(device="cuda:1")).

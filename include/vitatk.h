@@ -301,11 +301,15 @@ int vitatk_k_pgd_init(const float* x0_dev, const float* noise_dev, float* adv_de
                       const float* mean3, const float* std3, float eps, int use_rng, uint64_t seed,
                       uint64_t image_index0, void* stream);
 /* 7x7 shifted-window attention of the Swin path on its own (HF modeling_swin.py:410-459, :556-582, :615-636): qkv bf16
- * [batch*R*R, 3C] token-major, bias fp32 [heads, 49, 49], head dim 32 (C == 32 * heads), 0 <= shift < 7. */
-int vitatk_k_win_attn_fwd(const void* qkv_dev, const float* bias_dev, void* out_dev, int batch, int R, int C, int heads,
-                          int shift, void* stream);
-int vitatk_k_win_attn_bwd(const void* qkv_dev, const void* dout_dev, const float* bias_dev, void* dqkv_dev, int batch,
-                          int R, int C, int heads, int shift, void* stream);
+ * [batch*R*R, 3C] token-major, head dim 32 (C == 32 * heads), 0 <= shift < 7.  bias is the fp32 [heads, 49, 49]
+ * relative-position table (bias_is_table = 0; a fragment-order copy is made per call) or the fragment-order table
+ * vitatk_k_win_bias_table wrote for the same (heads, shift) (bias_is_table = 1) -- what the engine keeps per block.
+ * vitatk_k_win_bias_table returns the table's size in bytes (and writes it when both pointers are given), -1 on error. */
+long long vitatk_k_win_bias_table(const float* bias_dev, float* table_dev, int heads, int shift, void* stream);
+int vitatk_k_win_attn_fwd(const void* qkv_dev, const float* bias_dev, int bias_is_table, void* out_dev, int batch, int R,
+                          int C, int heads, int shift, void* stream);
+int vitatk_k_win_attn_bwd(const void* qkv_dev, const void* dout_dev, const float* bias_dev, int bias_is_table,
+                          void* dqkv_dev, int batch, int R, int C, int heads, int shift, void* stream);
 
 #ifdef __cplusplus
 }

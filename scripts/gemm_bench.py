@@ -56,7 +56,7 @@ def main():
         def launch():
             rc = lib.vitatk_k_gemm(M, N, K, p(A), A.stride(0), p(B), B.stride(0), p(out), N, p(out2), N, p(T),
                                    0 if T is None else T.stride(0), p(LB), 0 if LB is None else LB.stride(0), nkb,
-                                   1 if nkb else 0, gcols, epi, p(bias), p(res), 0 if res is None else N, None, 0, None, 0, 0, None, None, None, 0.0, 0, s)
+                                   1 if nkb else 0, gcols, epi, p(bias), p(res), 0 if res is None else N, None, 0, None, 0, 0, None, None, None, 1e-12, None, 0, None, None, 0, s)
             _lib.check(rc, name)
 
         for _ in range(3):

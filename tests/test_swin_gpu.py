@@ -133,8 +133,8 @@ def test_window_attention_kernels_vs_torch(R, heads, shift, batch):
     out = torch.full((M, C), float("nan"), device="cuda", dtype=torch.bfloat16)
     dqkv = torch.full((M, 3 * C), float("nan"), device="cuda", dtype=torch.bfloat16)
     st = torch.cuda.current_stream().cuda_stream
-    assert lib.vitatk_k_win_attn_fwd(qkv.data_ptr(), bias.data_ptr(), out.data_ptr(), batch, R, C, heads, shift, st) == 0
-    assert lib.vitatk_k_win_attn_bwd(qkv.data_ptr(), dout.data_ptr(), bias.data_ptr(), dqkv.data_ptr(), batch, R, C, heads, shift, st) == 0
+    assert lib.vitatk_k_win_attn_fwd(qkv.data_ptr(), bias.data_ptr(), 0, out.data_ptr(), batch, R, C, heads, shift, st) == 0
+    assert lib.vitatk_k_win_attn_bwd(qkv.data_ptr(), dout.data_ptr(), bias.data_ptr(), 0, dqkv.data_ptr(), batch, R, C, heads, shift, st) == 0
     torch.cuda.synchronize()
     ref_in = qkv.float().requires_grad_(True)
     ref = _win_attn_ref(ref_in, bias, batch, R, heads, shift)

@@ -15,7 +15,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libvitatk.so")
 INCLUDE_DIR = os.path.join(os.path.dirname(PKG_DIR), "include")
 SOURCES = ["gemm_tc05.cu", "attention_tc05.cu", "attention_bwd_fused.cu", "elementwise.cu", "train.cu", "patch.cu", "swin.cu", "engine.cu"]
-HEADERS = ["ptx.cuh", "vitatk_internal.h"]
+HEADERS = ["ptx.cuh", "vitatk_internal.h", "mma_sync.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",

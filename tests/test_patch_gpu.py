@@ -102,3 +102,53 @@ def test_patch_attack_object_optimises_and_applies():
     p2 = atk.generate(x, y)
     assert p2.shape == (3, 24, 24)
     eng.close()
+
+
+def test_full_size_eot_gradient_is_linear_over_image_shards():
+    """BASELINE configs[3] shape: 32 transforms x 96 images = 3072 samples per step, 3x24x24 circular patch.  The
+    size-independent property the data-parallel patch all-reduce rests on: d mean-CE / d patch over the whole batch equals
+    the mean of the gradients of its two 48-image shards (same per-sample transforms), bit-reproducibly; and per-sample
+    losses / logits of the big launch equal those of the shards row for row."""
+    import vitatk
+    from oracle import fixtures as fx
+    from vitatk import _lib
+
+    m = fx.make_model(lora=True)
+    eng = vitatk.Engine(model=m, max_batch=256, device="cuda")
+    B, T, p = 96, 32, 24
+    g = torch.Generator().manual_seed(17)
+    x = torch.rand(B, 3, 224, 224, generator=g).cuda()
+    y = torch.randint(0, fx.NUM_CLASSES, (B,), generator=g).cuda()
+    patch = torch.rand(3, p, p, generator=g).cuda()
+    inv, fw = vitatk.sample_transforms(B * T, np.random.default_rng(3), 0.05, 1.0, 22.5)
+    tfi, tff = torch.from_numpy(inv).cuda(), torch.from_numpy(fw).cuda()
+
+    def run(lo, hi):
+        """mean-CE gradient over images [lo, hi) x T transforms, 8 images (256 samples) per launch like AdversarialPatch"""
+        n = hi - lo
+        grad = torch.zeros_like(patch)
+        loss = torch.empty(n * T, device="cuda")
+        logits = torch.empty(n * T, eng.num_classes, device="cuda")
+        for i0 in range(lo, hi, 8):
+            nb = min(8, hi - i0)
+            gc = torch.zeros_like(patch)
+            a, b = tfi[i0 * T:(i0 + nb) * T].contiguous(), tff[i0 * T:(i0 + nb) * T].contiguous()
+            o = (i0 - lo) * T
+            _lib.check(eng.lib.vitatk_patch_grad(eng._h, x[i0:i0 + nb].data_ptr(), y[i0:i0 + nb].data_ptr(), nb, T, a.data_ptr(),
+                                                 b.data_ptr(), patch.data_ptr(), p, 1, gc.data_ptr(), loss[o:].data_ptr(),
+                                                 logits[o:].data_ptr(), eng._stream()), "vitatk_patch_grad")
+            grad.add_(gc, alpha=nb / n)
+        torch.cuda.synchronize()
+        return grad, loss, logits
+
+    gf, lf, zf = run(0, B)
+    gf2, _, _ = run(0, B)
+    assert torch.equal(gf, gf2)
+    assert torch.isfinite(gf).all() and float(gf.abs().max()) > 0
+    g0, l0, z0 = run(0, 48)
+    g1, l1, z1 = run(48, B)
+    e = rel(0.5 * (g0 + g1), gf)
+    note(samples=B * T, shard_mean_vs_full=e, mean_loss=float(lf.mean()))
+    assert e < 2e-3, e
+    assert torch.equal(torch.cat([z0, z1]), zf) and torch.equal(torch.cat([l0, l1]), lf)
+    eng.close()

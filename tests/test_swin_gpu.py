@@ -145,3 +145,55 @@ def test_window_attention_kernels_vs_torch(R, heads, shift, batch):
     note(R=R, heads=heads, shift=shift, rel_out=e_o, rel_dq=e_q, rel_dk=e_k, rel_dv=e_v)
     assert torch.isfinite(out.float()).all() and torch.isfinite(dqkv.float()).all()
     assert e_o < 1e-2 and e_q < 1.5e-2 and e_k < 1.5e-2 and e_v < 1e-2
+
+
+def test_swin_full_size_pgd20_rows_vs_oracle_and_properties():
+    """BASELINE configs[2] shape: LoRA Swin-B, batch 128, PGD-20, eps 8/255, alpha 2/255, random start (shared noise).
+    Every fourth step, the gradient the engine used -- for 8 sampled rows of the 128 -- is compared with the fp32 HF
+    oracle's gradient AT THE SAME iterate (rtol 2e-2); at every step the engine's next iterate must be exactly the
+    reference update (sign step, projection, clamp) of its own gradient.  Then the size-independent properties: ball,
+    range, bit-reproducibility, batch independence with the sharding-invariant random start."""
+    import vitatk
+    from oracle import fixtures as fx
+    from oracle import vit_oracle as vo
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    m = vo.build_swin(num_labels=fx.NUM_CLASSES, seed=0)
+    vo.attach_lora(m, r=8, alpha=16.0, targets=vo.ALL_TARGETS, seed=0, b_std=0.02)
+    m = m.cuda()
+    eng = vitatk.SwinEngine(model=m, max_batch=128, device="cuda")
+    B = 128
+    g = torch.Generator().manual_seed(321)
+    x = torch.rand(B, 3, 224, 224, generator=g).cuda()
+    y = torch.randint(0, fx.NUM_CLASSES, (B,), generator=g).cuda()
+    noise = torch.empty(B, 3, 224, 224).uniform_(-fx.EPS, fx.EPS, generator=g).cuda()
+    rows = torch.arange(0, B, 16, device="cuda")
+    eps32 = float(torch.tensor(fx.EPS, dtype=torch.float32))
+    cur = eng.attack(x, y, fx.EPS, 0.0, 1, start="noise", noise=noise)  # the random start itself
+    assert float((cur - torch.clamp(x + noise, 0, 1)).abs().max()) <= 6e-8
+    worst = 0.0
+    for step in range(20):
+        nxt = eng.attack(x, y, fx.EPS, fx.ALPHA, step + 1, start="noise", noise=noise)
+        ge, _, _ = eng.input_grad(cur, y)
+        if step % 4 == 0 or step == 19:
+            _, _, go = vo.input_grad(m, cur[rows], y[rows])
+            go = go * (rows.numel() / float(B))  # mean CE over 8 rows -> mean over 128
+            r = rel(ge[rows], go)
+            worst = max(worst, r)
+            assert r < 2e-2, (step, r)
+        stepped = cur + fx.ALPHA * ge.sign()
+        want = torch.clamp(x + torch.clamp(stepped - x, min=-fx.EPS, max=fx.EPS), 0, 1)
+        assert float((nxt - want).abs().max()) <= 6e-8, step
+        assert float((nxt != want).float().mean()) < 0.05
+        assert float((nxt - x).abs().max()) <= eps32
+        cur = nxt
+    note(worst_rel_grad_over_20_steps=worst)
+    a1 = eng.attack(x, y, fx.EPS, fx.ALPHA, 3, start="rng", seed=9)
+    a2 = eng.attack(x, y, fx.EPS, fx.ALPHA, 3, start="rng", seed=9)
+    assert torch.equal(a1, a2)
+    assert float((a1 - x).abs().max()) <= eps32 and float(a1.min()) >= 0.0 and float(a1.max()) <= 1.0
+    tail = eng.attack(x[123:], y[123:], fx.EPS, fx.ALPHA, 3, start="rng", seed=9, image_index0=123)
+    assert torch.equal(tail, a1[123:])
+    assert torch.equal(eng.logits(x)[50:53], eng.logits(x[50:53]))
+    eng.close()

@@ -135,3 +135,33 @@ def test_peft_zero_init_loss_decreases_and_adapter_directory(tmp_path):
     assert l_adv == l_adv and l_adv > 0
     for e in (trainer.engine, ref, eng2):
         e.close()
+
+
+def test_full_size_train_step_vs_oracle_and_data_parallel_equivalence():
+    """BASELINE configs[4] shape: batch 96, LoRA r=16 on the reference's five targets, dropout 0.1.  (1) the weight
+    gradients of the whole batch against the fp32 oracle (rtol 2e-2 per parameter kind); (2) the size-independent property
+    data-parallel training rests on: with masks keyed by the GLOBAL row index, the gradient of the 96-image batch equals
+    the mean of the gradients of its two 48-image shards (what the NCCL all-reduce computes)."""
+    from oracle import vit_oracle as vo
+
+    trainer, om, _, _, to = _setup(vo.REFERENCE_TARGETS, r=16, dropout=0.1, batch=96)
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(96, 3, 224, 224, generator=g).cuda()
+    y = torch.randint(0, 21, (96,), generator=g).cuda()
+    loss, logits = trainer.forward_backward(x, y, image_index0=0)
+    full = trainer.grads.clone()
+    eg = {k: v.cuda() for k, v in trainer.gradients().items()}
+    oloss, ologits, og = to.loss_and_grads(om, x, y, seed=11, step=0, p=0.1, image_index0=0)
+    errs = {kind: rel(_group(eg, kind), _group(og, kind)) for kind in (".lora_A", ".lora_B", "classifier.weight", "classifier.bias")}
+    note(batch=96, rel_logits=rel(logits, ologits), **{k.strip("."): v for k, v in errs.items()})
+    assert rel(logits, ologits) < RTOL and abs(float(loss.mean()) - float(oloss)) < 2e-2 * float(oloss)
+    for kind, e in errs.items():
+        assert e < RTOL, (kind, e)
+    trainer.forward_backward(x[:48], y[:48], image_index0=0)
+    lo = trainer.grads.clone()
+    trainer.forward_backward(x[48:], y[48:], image_index0=48)
+    hi = trainer.grads.clone()
+    e = rel(0.5 * (lo + hi), full)
+    note(shard_mean_vs_full=e)
+    assert e < 2e-3, e
+    trainer.engine.close()

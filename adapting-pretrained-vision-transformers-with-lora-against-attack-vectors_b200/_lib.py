@@ -80,7 +80,7 @@ EXPORTS = [
     "vitatk_attack", "vitatk_count_correct", "vitatk_launch_count", "vitatk_k_gemm", "vitatk_k_layernorm_fwd", "vitatk_k_layernorm_bwd", "vitatk_k_pgd_update",
     "vitatk_k_pgd_init", "vitatk_profile_begin", "vitatk_profile_end", "vitatk_k_attention_fwd_tc05",
     "vitatk_k_attention_bwd_fused", "vitatk_k_gemm_trace", "vitatk_k_attention_bwd_trace",
-    "vitatk_k_attention_fwd_trace", "vitatk_k_layernorm_stats",
+    "vitatk_k_attention_fwd_trace", "vitatk_k_layernorm_stats", "vitatk_k_layernorm_bwd_bt",
     "vitatk_train_enable", "vitatk_train_bind", "vitatk_train_set_adapter", "vitatk_train_repack", "vitatk_train_step",
     "vitatk_train_apply", "vitatk_train_mask_seed", "vitatk_patch_grad", "vitatk_patch_apply", "vitatk_patch_update",
     "vitatk_swin_create", "vitatk_swin_destroy", "vitatk_swin_set_tensor", "vitatk_swin_set_lora", "vitatk_swin_set_normalization",
@@ -144,6 +144,7 @@ def load() -> C.CDLL:
     lib.vitatk_k_layernorm_stats.argtypes = [vp, vp, i, i, f, i, vp]
     lib.vitatk_k_pgd_update.argtypes = [vp, vp, vp, vp, i, C.POINTER(f), C.POINTER(f), f, f, vp]
     lib.vitatk_k_pgd_init.argtypes = [vp, vp, vp, vp, i, C.POINTER(f), C.POINTER(f), f, i, u64, u64, vp]
+    lib.vitatk_k_layernorm_bwd_bt.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, vp, i, vp, i, vp]
     lib.vitatk_k_win_attn_fwd.argtypes = [vp, vp, i, vp, i, i, i, i, i, vp]
     lib.vitatk_k_win_attn_bwd.argtypes = [vp, vp, vp, i, vp, i, i, i, i, i, vp]
     lib.vitatk_k_win_bias_table.argtypes = [vp, vp, i, i, vp]

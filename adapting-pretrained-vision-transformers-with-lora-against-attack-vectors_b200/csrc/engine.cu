@@ -80,6 +80,8 @@ struct LayerPlans {
   GemmPlan t_qkv, qkv, t_proj, proj, t_fc1, fc1, t_fc2, fc2;
   // backward (input gradients)
   GemmPlan bt_fc2, bfc2, bt_fc1, bfc1, bt_proj, bproj, bt_qkv, bqkv;
+  // the LayerNorm backward that produces the site's input also writes its dx * B^T (layernorm_bwd_bt): no skinny launch
+  bool ln_bt_proj = false, ln_bt_fc2 = false;
 };
 
 struct PlanSet {
@@ -143,6 +145,7 @@ struct vitatk_engine {
   bool fuse_tt = true;               // plain LoRA sites: T = x*A^T comes from T-tiles inside the consumer GEMM (VITATK_TT=0: skinny GEMMs)
   unsigned int* tt_flags = nullptr;  // [2 * ceil(max M / 256)] inter-CTA flags of the T-tiles (zero between launches)
   bool fuse_delta = false;           // delta comes out of the proj-backward GEMM epilogue (pair kernel) instead of a kernel
+  bool fuse_ln_bt = true;            // LayerNorm backward also writes the next LoRA site's dx * B^T (no bt_proj / bt_fc2 launch)
   // ---- LoRA training (vitatk_train_*) ----
   struct TrainAdapter {
     int rank = 0;
@@ -377,7 +380,9 @@ static int build_plans(vitatk_engine* e, int batch, PlanSet** out) {
     {
       const GemmTT tt = make_tt(s2, s2.lb_bwd, D, lora_ksteps(s2.rank), nullptr, e->tt_sites & 4);
       p.bt_fc2.M = 0;
-      if (s2.rank > 0 && tt.n == 0 &&
+      // fused into the LayerNorm backward that writes dh_a (LN1 of layer l + 1); the last layer's dh_a comes from the head
+      p.ln_bt_fc2 = e->fuse_ln_bt && s2.rank > 0 && tt.n == 0 && l + 1 < c.layers;
+      if (s2.rank > 0 && tt.n == 0 && !p.ln_bt_fc2 &&
           gemm_plan_init(&p.bt_fc2, M, LORA_PAD, D, e->dh_a, D, s2.lb_bwd, D, e->T, 3 * LORA_PAD, nullptr, 0, nullptr, 0,
                          nullptr, 0, 0, 0, 0, plain))
         return 1;
@@ -400,7 +405,8 @@ static int build_plans(vitatk_engine* e, int batch, PlanSet** out) {
     {
       const GemmTT tt = make_tt(sp, sp.lb_bwd, D, lora_ksteps(sp.rank), nullptr, e->tt_sites & 16);
       p.bt_proj.M = 0;
-      if (sp.rank > 0 && tt.n == 0 &&
+      p.ln_bt_proj = e->fuse_ln_bt && sp.rank > 0 && tt.n == 0;  // fused into LN2's backward, which writes dh_b
+      if (sp.rank > 0 && tt.n == 0 && !p.ln_bt_proj &&
           gemm_plan_init(&p.bt_proj, M, LORA_PAD, D, e->dh_b, D, sp.lb_bwd, D, e->T, 3 * LORA_PAD, nullptr, 0, nullptr, 0,
                          nullptr, 0, 0, 0, 0, plain))
         return 1;
@@ -546,14 +552,24 @@ static int encoder_backward(vitatk_engine* e, PlanSet* ps, int batch, cudaStream
     RUN_GEMM(CAT_BFC2, &p.bfc2);  // du = (dh W2 + lora) * gelu'(u)   (u[l] holds gelu'(u), written by fc1's epilogue)
     if (w.lora[VITATK_SITE_FC1].rank > 0 && p.bt_fc1.M > 0) RUN_GEMM(CAT_BT_FC1, &p.bt_fc1);
     RUN_GEMM(CAT_BFC1, &p.bfc1);  // dxn = du W1 + lora
-    RUNC(CAT_LN_BWD, 0, layernorm_bwd(e->dxn, e->h_mid[l], e->st2[l], w.ln2_g, e->dh_a, e->dh_b, M, D, s, e->res_f16, e->res_f16));  // dh_mid
+    if (p.ln_bt_proj)  // dh_mid, and T = dh_mid * B_proj^T for bproj's LoRA k-block
+      RUNC(CAT_LN_BWD, 0, layernorm_bwd_bt(e->dxn, e->h_mid[l], e->st2[l], w.ln2_g, e->dh_a, e->dh_b, M, D, s, e->res_f16, e->res_f16,
+                                         w.lora[VITATK_SITE_PROJ].lb_bwd, lora_ksteps(w.lora[VITATK_SITE_PROJ].rank), e->T, 3 * LORA_PAD));
+    else
+      RUNC(CAT_LN_BWD, 0, layernorm_bwd(e->dxn, e->h_mid[l], e->st2[l], w.ln2_g, e->dh_a, e->dh_b, M, D, s, e->res_f16, e->res_f16));  // dh_mid
     if (w.lora[VITATK_SITE_PROJ].rank > 0 && p.bt_proj.M > 0) RUN_GEMM(CAT_BT_PROJ, &p.bt_proj);
     RUN_GEMM(CAT_BPROJ, &p.bproj);  // dao = dh_mid Wp + lora
     RUNC(CAT_ATTN_BWD, 8.0 * batch * c.heads * TOKENS * TOKENS * 64,
          attention_bwd_fused(&ps->attn_bwd[l], s, !e->fuse_delta));
     if (w.lora[VITATK_SITE_QKV].rank > 0 && p.bt_qkv.M > 0) RUN_GEMM(CAT_BT_QKV, &p.bt_qkv);
     RUN_GEMM(CAT_BQKV, &p.bqkv);  // dxn = dqkv Wqkv + lora
-    RUNC(CAT_LN_BWD, 0, layernorm_bwd(e->dxn, e->h[l], e->st1[l], w.ln1_g, e->dh_b, e->dh_a, M, D, s, e->res_f16, e->res_f16));  // dh wrt h[l]
+    if (l > 0 && ps->layers[l - 1].ln_bt_fc2) {  // dh wrt h[l], and T = dh * B_fc2^T for layer l - 1's bfc2
+      const LoraSite& n2 = e->lw[l - 1].lora[VITATK_SITE_FC2];
+      RUNC(CAT_LN_BWD, 0, layernorm_bwd_bt(e->dxn, e->h[l], e->st1[l], w.ln1_g, e->dh_b, e->dh_a, M, D, s, e->res_f16, e->res_f16,
+                                         n2.lb_bwd, lora_ksteps(n2.rank), e->T, 3 * LORA_PAD));
+    } else {
+      RUNC(CAT_LN_BWD, 0, layernorm_bwd(e->dxn, e->h[l], e->st1[l], w.ln1_g, e->dh_b, e->dh_a, M, D, s, e->res_f16, e->res_f16));  // dh wrt h[l]
+    }
   }
   RUN_GEMM(CAT_BPATCH, &ps->bpatch);  // dxn <- dL/d(cols)
   return 0;
@@ -620,6 +636,8 @@ int vitatk_create(const vitatk_config* cfg, vitatk_engine** out) {
     const char* tc = getenv("VITATK_TC_CONST");
     e->tc_const = !(tc && tc[0] == '0') && !(g2 && g2[0] == '0') && cfg->dim % 256 == 0 && cfg->mlp_dim % 256 == 0;
     e->fuse_delta = !(g2 && g2[0] == '0') && !(fd && fd[0] == '0') && cfg->dim % 256 == 0;
+    const char* lb = getenv("VITATK_LN_BT");
+    e->fuse_ln_bt = !(lb && lb[0] == '0') && cfg->dim == 768;
   }
   e->lw.resize(cfg->layers);
   for (int i = 0; i < 3; ++i) {
@@ -1067,6 +1085,12 @@ int vitatk_k_layernorm_fwd(const void* x, const float* gamma, const float* beta,
                            int cols, float eps, int x_f16, void* stream) {
   return layernorm_fwd(static_cast<const bf16*>(x), gamma, beta, static_cast<bf16*>(y),
                        reinterpret_cast<float2*>(stats), rows, cols, eps, static_cast<cudaStream_t>(stream), x_f16);
+}
+int vitatk_k_layernorm_bwd_bt(const void* dy, const void* x, const float* stats, const float* gamma, const void* dres, void* dx,
+                              int rows, int cols, int x_f16, int g_f16, const void* lb, int ksteps, void* T, int ldt, void* stream) {
+  return layernorm_bwd_bt(static_cast<const bf16*>(dy), static_cast<const bf16*>(x), reinterpret_cast<const float2*>(stats), gamma,
+                          static_cast<const bf16*>(dres), static_cast<bf16*>(dx), rows, cols, static_cast<cudaStream_t>(stream), x_f16,
+                          g_f16, static_cast<const bf16*>(lb), ksteps, static_cast<bf16*>(T), ldt);
 }
 int vitatk_k_layernorm_bwd(const void* dy, const void* x, const float* stats, const float* gamma, const void* dres,
                            void* dx, int rows, int cols, int x_f16, int g_f16, void* stream) {

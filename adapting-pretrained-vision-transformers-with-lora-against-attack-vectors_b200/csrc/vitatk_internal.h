@@ -231,6 +231,10 @@ int layernorm_fwd(const bf16* x, const float* gamma, const float* beta, bf16* y,
 // dx_out = dres + LN_backward(dy) ; x is the saved LN input, stats = (mean, rstd)
 int layernorm_bwd(const bf16* dy, const bf16* x, const float2* stats, const float* gamma, const bf16* dres,
                   bf16* dx_out, int rows, int cols, cudaStream_t stream, int x_f16 = 0, int g_f16 = 0);
+// layernorm_bwd that also writes T[rows, 16 * ksteps] = dx * LB^T (LB [16 * ksteps, 768] in dx's 16-bit format): the LoRA
+// down-projection the next backward GEMM needs, from rows the kernel already holds (cols == 768)
+int layernorm_bwd_bt(const bf16* dy, const bf16* x, const float2* stats, const float* gamma, const bf16* dres, bf16* dx_out,
+                     int rows, int cols, cudaStream_t stream, int x_f16, int g_f16, const bf16* LB, int ksteps, bf16* T, int ldt);
 // final LN on CLS rows + classifier + softmax-CE; writes logits, per-image loss, and (optionally) the
 // gradient wrt the final hidden state (non-CLS rows zero-filled).  dlogits == nullptr: the cotangent is
 // softmax - onehot (cross-entropy); otherwise the caller's [batch, classes] fp32 cotangent (vector-Jacobian product).

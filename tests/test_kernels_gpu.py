@@ -377,6 +377,35 @@ def test_layernorm_fwd_bwd_vs_torch(lib, rows, f16):
     assert torch.equal(st2, stats)
 
 
+@pytest.mark.parametrize("rows,f16,ksteps", [(197 * 3 + 5, 1, 1), (197 * 2, 0, 1), (1000, 1, 2), (64, 1, 4)])
+def test_layernorm_bwd_with_fused_down_projection(lib, rows, f16, ksteps):
+    """layernorm_bwd_bt: dx bit-identical to the plain LayerNorm backward, and T = dx * lb^T (the skinny GEMM it replaces)
+    for 16 * ksteps adapter rows, ragged row counts included."""
+    from vitatk import _lib
+
+    cols, n = 768, 16 * ksteps
+    sdt = torch.float16 if f16 else torch.bfloat16
+    g = torch.Generator(device="cuda").manual_seed(rows + ksteps)
+    x = (torch.randn(rows, cols, device="cuda", generator=g) * 2 + 0.5).to(sdt)
+    gamma = 1 + 0.1 * torch.randn(cols, device="cuda", generator=g)
+    dy = torch.randn(rows, cols, device="cuda", generator=g).to(torch.bfloat16)
+    dres = torch.randn(rows, cols, device="cuda", generator=g).to(sdt)
+    lb = torch.zeros(64, cols, device="cuda", dtype=sdt)
+    lb[:n] = (torch.randn(n, cols, device="cuda", generator=g) * 0.05).to(sdt)
+    stats = torch.empty(rows, 2, device="cuda")
+    _lib.check(lib.vitatk_k_layernorm_stats(_p(x), _p(stats), rows, cols, 1e-12, f16, _s()), "ln_stats")
+    dx0, dx1 = torch.empty_like(dres), torch.empty_like(dres)
+    T = torch.full((rows, 192), float("nan"), device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.vitatk_k_layernorm_bwd(_p(dy), _p(x), _p(stats), _p(gamma), _p(dres), _p(dx0), rows, cols, f16, f16, _s()), "ln_bwd")
+    _lib.check(lib.vitatk_k_layernorm_bwd_bt(_p(dy), _p(x), _p(stats), _p(gamma), _p(dres), _p(dx1), rows, cols, f16, f16, _p(lb),
+                                             ksteps, _p(T), 192, _s()), "ln_bwd_bt")
+    torch.cuda.synchronize()
+    assert torch.equal(dx0, dx1)
+    ref = dx1.float() @ lb[:n].float().t()
+    check_close(T[:, :n], ref, "T = dx lb^T")
+    assert torch.isnan(T[:, n:].float()).all()  # only the columns the LoRA k-steps read are written
+
+
 def _cols_from_image(img, mean, std):
     """torch restatement of the im2col layout: [B,3,224,224] -> [B*197, 768] with zero CLS rows."""
     B = img.shape[0]

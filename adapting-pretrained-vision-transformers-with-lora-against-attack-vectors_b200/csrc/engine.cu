@@ -381,7 +381,7 @@ static int build_plans(vitatk_engine* e, int batch, PlanSet** out) {
       const GemmTT tt = make_tt(s2, s2.lb_bwd, D, lora_ksteps(s2.rank), nullptr, e->tt_sites & 4);
       p.bt_fc2.M = 0;
       // fused into the LayerNorm backward that writes dh_a (LN1 of layer l + 1); the last layer's dh_a comes from the head
-      p.ln_bt_fc2 = e->fuse_ln_bt && s2.rank > 0 && tt.n == 0 && l + 1 < c.layers;
+      p.ln_bt_fc2 = e->fuse_ln_bt && s2.rank > 0 && lora_ksteps(s2.rank) <= LN_BT_MAX_KSTEPS && tt.n == 0 && l + 1 < c.layers;
       if (s2.rank > 0 && tt.n == 0 && !p.ln_bt_fc2 &&
           gemm_plan_init(&p.bt_fc2, M, LORA_PAD, D, e->dh_a, D, s2.lb_bwd, D, e->T, 3 * LORA_PAD, nullptr, 0, nullptr, 0,
                          nullptr, 0, 0, 0, 0, plain))
@@ -405,7 +405,7 @@ static int build_plans(vitatk_engine* e, int batch, PlanSet** out) {
     {
       const GemmTT tt = make_tt(sp, sp.lb_bwd, D, lora_ksteps(sp.rank), nullptr, e->tt_sites & 16);
       p.bt_proj.M = 0;
-      p.ln_bt_proj = e->fuse_ln_bt && sp.rank > 0 && tt.n == 0;  // fused into LN2's backward, which writes dh_b
+      p.ln_bt_proj = e->fuse_ln_bt && sp.rank > 0 && lora_ksteps(sp.rank) <= LN_BT_MAX_KSTEPS && tt.n == 0;  // fused into LN2's backward, which writes dh_b
       if (sp.rank > 0 && tt.n == 0 && !p.ln_bt_proj &&
           gemm_plan_init(&p.bt_proj, M, LORA_PAD, D, e->dh_b, D, sp.lb_bwd, D, e->T, 3 * LORA_PAD, nullptr, 0, nullptr, 0,
                          nullptr, 0, 0, 0, 0, plain))

@@ -194,11 +194,11 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
 // LayerNorm backward that also produces the NEXT LoRA site's down-projection of its output:  T = dx * LB^T, LB [16 KS, COLS]
 // (the adapter's B^T rows as packed for the skinny GEMM it replaces: bt_proj after LN2-backward, the previous layer's
 // bt_fc2 after LN1-backward).  The kernel holds every dx row it writes, so the 77 MB re-read and the launch of the skinny
-// GEMM go away.  A CTA owns 16 rows (each warp normalises two, one after the other) and parks them in shared memory
-// (16-bit, as stored); warp w then owns columns [96 w, 96 w + 96) of the reduction and runs it as m16n8k16 MMAs with the
-// permuted-k trick of train.cu -- lane t owns 8 consecutive columns of each 32-column block: one 16-byte shared load per
-// row for the A fragments, one 16-byte global load (issued before the barrier; the same 24 KB for every CTA) per 8
-// adapter rows; the eight [16, 16 KS] partials are summed through shared memory in a fixed order.
+// GEMM go away.  The eight rows of a CTA are parked in shared memory (16-bit, as stored); warp w then owns columns
+// [96 w, 96 w + 96) of the reduction and runs it as m16n8k16 MMAs (rows 8..15 of the A operand are zero) with the
+// permuted-k trick of train.cu -- lane t owns 8 consecutive columns of each 32-column block: one 16-byte shared load for
+// the A fragment pair, one 16-byte global load (L1-resident, the same 24 KB for every CTA) per 8 adapter rows; the eight
+// [8, 16 KS] partials are summed through shared memory in a fixed order.
 template <int KS>
 __global__ void __launch_bounds__(256) ln_bwd_bt_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                                                         const float2* __restrict__ stats, const float* __restrict__ gamma,
@@ -207,68 +207,58 @@ __global__ void __launch_bounds__(256) ln_bwd_bt_kernel(const bf16* __restrict__
                                                         bf16* __restrict__ T, int ldt) {
   constexpr int CH = 3, COLS = 768, XLD = COLS + 32;  // 1600-byte rows: two consecutive rows cover all 32 banks
   constexpr int NT = 2 * KS;                          // 8-column tiles of T
-  __shared__ __align__(16) uint16_t Xs[16 * XLD];
-  __shared__ __align__(16) float Ps[8][16][8 * NT];   // [warp][row][column]
+  __shared__ __align__(16) uint16_t Xs[8 * XLD];
+  __shared__ __align__(16) float Ps[8][8][8 * NT];    // [warp][row][column]
   pdl_wait();
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row0 = blockIdx.x * 16;
+  const int row0 = blockIdx.x * 8, row = row0 + warp;
   auto ld = [&](const uint4* p) { return streaming ? __ldcs(p) : __ldg(p); };
-#pragma unroll 1
-  for (int half = 0; half < 2; ++half) {
-    const int lr = warp + 8 * half, row = row0 + lr;
-    if (row < rows) {
-      const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * COLS);
-      const uint4* dyr = reinterpret_cast<const uint4*>(dy + static_cast<size_t>(row) * COLS);
-      const float2 st = stats[row];
-      float xh[CH][8], gd[CH][8];
-      float s1 = 0.f, s2 = 0.f;
+  if (row < rows) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * COLS);
+    const uint4* dyr = reinterpret_cast<const uint4*>(dy + static_cast<size_t>(row) * COLS);
+    const float2 st = stats[row];
+    float xh[CH][8], gd[CH][8];
+    float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-      for (int i = 0; i < CH; ++i) {
-        const int c = (lane + 32 * i) * 8;
-        float xv[8], dv[8];
-        unpack8(ld(xr + lane + 32 * i), xv, x_f16);
-        unpack8(ld(dyr + lane + 32 * i), dv);
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c));
-        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
-        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    for (int i = 0; i < CH; ++i) {
+      const int c = (lane + 32 * i) * 8;
+      float xv[8], dv[8];
+      unpack8(ld(xr + lane + 32 * i), xv, x_f16);
+      unpack8(ld(dyr + lane + 32 * i), dv);
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          xh[i][j] = (xv[j] - st.x) * st.y;
-          gd[i][j] = dv[j] * gg[j];
-          s1 += gd[i][j];
-          s2 += gd[i][j] * xh[i][j];
-        }
+      for (int j = 0; j < 8; ++j) {
+        xh[i][j] = (xv[j] - st.x) * st.y;
+        gd[i][j] = dv[j] * gg[j];
+        s1 += gd[i][j];
+        s2 += gd[i][j] * xh[i][j];
       }
-      const float m1 = warp_sum(s1) * (1.f / COLS);
-      const float m2 = warp_sum(s2) * (1.f / COLS);
-      uint4* dxr = reinterpret_cast<uint4*>(dx + static_cast<size_t>(row) * COLS);
-      const uint4* rr = dres ? reinterpret_cast<const uint4*>(dres + static_cast<size_t>(row) * COLS) : nullptr;
-#pragma unroll
-      for (int i = 0; i < CH; ++i) {
-        float o[8];
-        float r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (rr) unpack8(ld(rr + lane + 32 * i), r, g_f16);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = r[j] + st.y * (gd[i][j] - m1 - xh[i][j] * m2);
-        const uint4 pk = pack8(o, g_f16);
-        dxr[lane + 32 * i] = pk;
-        *reinterpret_cast<uint4*>(Xs + lr * XLD + (lane + 32 * i) * 8) = pk;
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < CH; ++i) *reinterpret_cast<uint4*>(Xs + lr * XLD + (lane + 32 * i) * 8) = make_uint4(0u, 0u, 0u, 0u);
     }
+    const float m1 = warp_sum(s1) * (1.f / COLS);
+    const float m2 = warp_sum(s2) * (1.f / COLS);
+    uint4* dxr = reinterpret_cast<uint4*>(dx + static_cast<size_t>(row) * COLS);
+    const uint4* rr = dres ? reinterpret_cast<const uint4*>(dres + static_cast<size_t>(row) * COLS) : nullptr;
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      float o[8];
+      float r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (rr) unpack8(ld(rr + lane + 32 * i), r, g_f16);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = r[j] + st.y * (gd[i][j] - m1 - xh[i][j] * m2);
+      const uint4 pk = pack8(o, g_f16);
+      dxr[lane + 32 * i] = pk;
+      *reinterpret_cast<uint4*>(Xs + warp * XLD + (lane + 32 * i) * 8) = pk;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < CH; ++i) *reinterpret_cast<uint4*>(Xs + warp * XLD + (lane + 32 * i) * 8) = make_uint4(0u, 0u, 0u, 0u);
   }
-  const int g = lane >> 2, t = lane & 3;
-  uint4 bfr[3][NT];  // the adapter fragments do not depend on the rows: in flight across the barrier
-#pragma unroll
-  for (int kb = 0; kb < 3; ++kb)
-#pragma unroll
-    for (int n = 0; n < NT; ++n)
-      bfr[kb][n] = __ldg(reinterpret_cast<const uint4*>(LB + static_cast<size_t>(n * 8 + g) * COLS + warp * 96 + kb * 32 + 8 * t));
   __syncthreads();
   {
+    const int g = lane >> 2, t = lane & 3;
     float acc[NT][4];
 #pragma unroll
     for (int n = 0; n < NT; ++n)
@@ -277,28 +267,27 @@ __global__ void __launch_bounds__(256) ln_bwd_bt_kernel(const bf16* __restrict__
 #pragma unroll
     for (int kb = 0; kb < 3; ++kb) {
       const int k0 = warp * 96 + kb * 32 + 8 * t;
-      const uint4 lo = *reinterpret_cast<const uint4*>(Xs + g * XLD + k0);
-      const uint4 hi = *reinterpret_cast<const uint4*>(Xs + (g + 8) * XLD + k0);
-      const uint32_t a0[4] = {lo.x, hi.x, lo.y, hi.y}, a1[4] = {lo.z, hi.z, lo.w, hi.w};
+      const uint4 a = *reinterpret_cast<const uint4*>(Xs + g * XLD + k0);
+      uint4 b[NT];
+#pragma unroll
+      for (int n = 0; n < NT; ++n) b[n] = __ldg(reinterpret_cast<const uint4*>(LB + static_cast<size_t>(n * 8 + g) * COLS + k0));
+      const uint32_t a_lo[4] = {a.x, 0u, a.y, 0u}, a_hi[4] = {a.z, 0u, a.w, 0u};  // rows 8..15 of the tile do not exist
 #pragma unroll
       for (int n = 0; n < NT; ++n) {
         if (g_f16) {
-          mma16816_f16(acc[n], a0, bfr[kb][n].x, bfr[kb][n].y);
-          mma16816_f16(acc[n], a1, bfr[kb][n].z, bfr[kb][n].w);
+          mma16816_f16(acc[n], a_lo, b[n].x, b[n].y);
+          mma16816_f16(acc[n], a_hi, b[n].z, b[n].w);
         } else {
-          mma16816(acc[n], a0, bfr[kb][n].x, bfr[kb][n].y);
-          mma16816(acc[n], a1, bfr[kb][n].z, bfr[kb][n].w);
+          mma16816(acc[n], a_lo, b[n].x, b[n].y);
+          mma16816(acc[n], a_hi, b[n].z, b[n].w);
         }
       }
     }
 #pragma unroll
-    for (int n = 0; n < NT; ++n) {
-      *reinterpret_cast<float2*>(&Ps[warp][g][n * 8 + 2 * t]) = make_float2(acc[n][0], acc[n][1]);
-      *reinterpret_cast<float2*>(&Ps[warp][g + 8][n * 8 + 2 * t]) = make_float2(acc[n][2], acc[n][3]);
-    }
+    for (int n = 0; n < NT; ++n) *reinterpret_cast<float2*>(&Ps[warp][g][n * 8 + 2 * t]) = make_float2(acc[n][0], acc[n][1]);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 16 * 8 * NT; i += 256) {
+  for (int i = threadIdx.x; i < 8 * 8 * NT; i += 256) {
     const int r = i / (8 * NT), c = i % (8 * NT);
     float s = 0.f;
 #pragma unroll
@@ -354,11 +343,11 @@ int layernorm_bwd(const bf16* dy, const bf16* x, const float2* stats, const floa
 
 int layernorm_bwd_bt(const bf16* dy, const bf16* x, const float2* stats, const float* gamma, const bf16* dres, bf16* dx_out,
                      int rows, int cols, cudaStream_t stream, int x_f16, int g_f16, const bf16* LB, int ksteps, bf16* T, int ldt) {
-  if (cols != 768 || ksteps < 1 || ksteps > LN_BT_MAX_KSTEPS || LB == nullptr || T == nullptr || (reinterpret_cast<uintptr_t>(LB) & 15) != 0) {
+  if (cols != 768 || ksteps < 1 || ksteps > 4 || LB == nullptr || T == nullptr || (reinterpret_cast<uintptr_t>(LB) & 15) != 0) {
     set_error("layernorm_bwd_bt: cols=%d ksteps=%d unsupported", cols, ksteps);
     return 1;
   }
-  const int grid = (rows + 15) / 16;
+  const int grid = (rows + 7) / 8;
   static int streaming = -1;
   if (streaming < 0) {
     const char* e = getenv("VITATK_LN_STREAM");
@@ -366,8 +355,12 @@ int layernorm_bwd_bt(const bf16* dy, const bf16* x, const float2* stats, const f
   }
 #define LNBT(KS) \
   VITATK_CUDA_OK(launch_pdl(ln_bwd_bt_kernel<KS>, dim3(grid), dim3(256), 0, stream, 1, dy, x, stats, gamma, dres, dx_out, rows, streaming, x_f16, g_f16, LB, T, ldt))
-  if (ksteps == 1) LNBT(1);
-  else LNBT(2);
+  switch (ksteps) {
+    case 1: LNBT(1); break;
+    case 2: LNBT(2); break;
+    case 3: LNBT(3); break;
+    default: LNBT(4); break;
+  }
 #undef LNBT
   VITATK_CUDA_OK(cudaGetLastError());
   return 0;

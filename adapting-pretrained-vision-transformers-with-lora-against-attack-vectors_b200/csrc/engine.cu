@@ -145,7 +145,7 @@ struct vitatk_engine {
   bool fuse_tt = true;               // plain LoRA sites: T = x*A^T comes from T-tiles inside the consumer GEMM (VITATK_TT=0: skinny GEMMs)
   unsigned int* tt_flags = nullptr;  // [2 * ceil(max M / 256)] inter-CTA flags of the T-tiles (zero between launches)
   bool fuse_delta = false;           // delta comes out of the proj-backward GEMM epilogue (pair kernel) instead of a kernel
-  bool fuse_ln_bt = true;            // LayerNorm backward also writes the next LoRA site's dx * B^T (no bt_proj / bt_fc2 launch)
+  bool fuse_ln_bt = false;           // VITATK_LN_BT=1: LayerNorm backward also writes the next LoRA site's dx * B^T (no bt_proj / bt_fc2 launch)
   // ---- LoRA training (vitatk_train_*) ----
   struct TrainAdapter {
     int rank = 0;
@@ -636,8 +636,10 @@ int vitatk_create(const vitatk_config* cfg, vitatk_engine** out) {
     const char* tc = getenv("VITATK_TC_CONST");
     e->tc_const = !(tc && tc[0] == '0') && !(g2 && g2[0] == '0') && cfg->dim % 256 == 0 && cfg->mlp_dim % 256 == 0;
     e->fuse_delta = !(g2 && g2[0] == '0') && !(fd && fd[0] == '0') && cfg->dim % 256 == 0;
+    // measured neutral on B200 (the CTA-level hand-over costs the LayerNorm kernel what the two skinny launches cost:
+    // layernorm_bwd 14.8 -> 19.0 ms per step against 4.7 ms of bt_proj + bt_fc2), so opt-in like the T-tiles
     const char* lb = getenv("VITATK_LN_BT");
-    e->fuse_ln_bt = !(lb && lb[0] == '0') && cfg->dim == 768;
+    e->fuse_ln_bt = lb && lb[0] == '1' && cfg->dim == 768;
   }
   e->lw.resize(cfg->layers);
   for (int i = 0; i < 3; ++i) {

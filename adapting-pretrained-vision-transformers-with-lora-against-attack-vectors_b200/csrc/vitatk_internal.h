@@ -231,7 +231,7 @@ int layernorm_fwd(const bf16* x, const float* gamma, const float* beta, bf16* y,
 // dx_out = dres + LN_backward(dy) ; x is the saved LN input, stats = (mean, rstd)
 int layernorm_bwd(const bf16* dy, const bf16* x, const float2* stats, const float* gamma, const bf16* dres,
                   bf16* dx_out, int rows, int cols, cudaStream_t stream, int x_f16 = 0, int g_f16 = 0);
-constexpr int LN_BT_MAX_KSTEPS = 2;  // ranks <= 32 (shared-memory budget of the fused kernel); larger ranks keep the skinny GEMM
+constexpr int LN_BT_MAX_KSTEPS = 4;  // ranks <= 64
 // layernorm_bwd that also writes T[rows, 16 * ksteps] = dx * LB^T (LB [16 * ksteps, 768] in dx's 16-bit format): the LoRA
 // down-projection the next backward GEMM needs, from rows the kernel already holds (cols == 768)
 int layernorm_bwd_bt(const bf16* dy, const bf16* x, const float2* stats, const float* gamma, const bf16* dres, bf16* dx_out,

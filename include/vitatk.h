@@ -296,7 +296,7 @@ int vitatk_k_layernorm_stats(const void* x_dev, float* stats_dev, int rows, int 
 int vitatk_k_layernorm_bwd(const void* dy_dev, const void* x_dev, const float* stats_dev, const float* gamma_dev,
                            const void* dres_dev, void* dx_dev, int rows, int cols, int x_f16, int g_f16, void* stream);
 /* LayerNorm backward that also writes T[rows, 16 * ksteps] = dx * lb^T (bf16, row stride ldt): lb [16 * ksteps, 768] in dx's
- * 16-bit format (fp16 when g_f16) -- the down-projection the next backward GEMM's LoRA k-block reads; cols == 768, ksteps <= 2 */
+ * 16-bit format (fp16 when g_f16) -- the down-projection the next backward GEMM's LoRA k-block reads; cols == 768, ksteps <= 4 */
 int vitatk_k_layernorm_bwd_bt(const void* dy_dev, const void* x_dev, const float* stats_dev, const float* gamma_dev,
                               const void* dres_dev, void* dx_dev, int rows, int cols, int x_f16, int g_f16,
                               const void* lb_dev, int ksteps, void* T_dev, int ldt, void* stream);

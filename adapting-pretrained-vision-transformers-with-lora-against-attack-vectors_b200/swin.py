@@ -50,6 +50,17 @@ def _bind(lib):
     lib._swin_bound = True
 
 
+def relative_position_index(window: int) -> torch.Tensor:
+    """[window^2, window^2] index into the (2 window - 1)^2-row relative_position_bias_table (modeling_swin.py:461-473)."""
+    ch = torch.arange(window)
+    coords = torch.stack(torch.meshgrid([ch, ch], indexing="ij")).flatten(1)
+    rel = (coords[:, :, None] - coords[:, None, :]).permute(1, 2, 0).contiguous()
+    rel[:, :, 0] += window - 1
+    rel[:, :, 1] += window - 1
+    rel[:, :, 0] *= 2 * window - 1
+    return rel.sum(-1)
+
+
 class SwinEngine:
     def __init__(self, model: Optional[torch.nn.Module] = None, state_dict: Optional[Dict[str, torch.Tensor]] = None,
                  adapters: Optional[Dict[str, Sequence[Adapter]]] = None, max_batch: int = 128,
@@ -127,14 +138,7 @@ class SwinEngine:
         self._set(T_FLN_B, 0, 0, g("swin.layernorm.bias"), f32)
         self._set(T_HEAD_W, 0, 0, g("classifier.weight"), f32)
         self._set(T_HEAD_B, 0, 0, g("classifier.bias"), f32)
-        # relative_position_index (modeling_swin.py:461-473)
-        ch = torch.arange(window)
-        coords = torch.stack(torch.meshgrid([ch, ch], indexing="ij")).flatten(1)
-        rel = (coords[:, :, None] - coords[:, None, :]).permute(1, 2, 0).contiguous()
-        rel[:, :, 0] += window - 1
-        rel[:, :, 1] += window - 1
-        rel[:, :, 0] *= 2 * window - 1
-        rel_index = rel.sum(-1).reshape(-1)
+        rel_index = relative_position_index(window).reshape(-1)
         for s in range(4):
             Cs = C0 << s
             for b in range(self.depths[s]):

@@ -547,3 +547,81 @@ def _grad_worker(rank, world, port, q):
     average_gradients(g)
     q.put((rank, g.tolist()))
     dist.destroy_process_group()
+
+
+def test_swin_relative_position_index_matches_hf():
+    """The host-side gather that turns HF's relative_position_bias_table into the [heads, 49, 49] bias the kernels read
+    uses the same index as transformers' SwinSelfAttention buffer (modeling_swin.py:461-473)."""
+    import torch
+    from transformers import SwinConfig
+    from transformers.models.swin.modeling_swin import SwinSelfAttention
+
+    from vitatk.swin import relative_position_index
+
+    att = SwinSelfAttention(SwinConfig(window_size=7), dim=128, num_heads=4, window_size=7)
+    idx = relative_position_index(7)
+    assert idx.shape == (49, 49) and torch.equal(idx, att.relative_position_index)
+    assert int(idx.min()) == 0 and int(idx.max()) == 13 * 13 - 1
+    for w in (2, 3, 5):
+        i = relative_position_index(w)
+        assert i.shape == (w * w, w * w) and int(i.max()) == (2 * w - 1) ** 2 - 1
+
+
+def test_patch_transforms_are_consistent_affine_pairs():
+    """sample_transforms: forward and inverse maps compose to the identity, scale / rotation / translation stay in ART's
+    ranges (the un-rotated patch stays inside the frame), a fixed `scale` pins every sample, same rng -> same draws."""
+    import numpy as np
+
+    from vitatk import sample_transforms
+
+    inv, fw = sample_transforms(500, np.random.default_rng(1), 0.1, 0.9, 22.5)
+    assert inv.shape == (500, 6) and fw.shape == (500, 6) and inv.dtype == np.float32
+    A = fw.reshape(500, 2, 3).astype(np.float64)
+    B = inv.reshape(500, 2, 3).astype(np.float64)
+    comp = np.einsum("nij,njk->nik", A[:, :, :2], B[:, :, :2])
+    assert np.abs(comp - np.eye(2)).max() < 1e-5
+    assert np.abs(np.einsum("nij,nj->ni", A[:, :, :2], B[:, :, 2]) + A[:, :, 2]).max() < 1e-5  # F(I(p)) = p for the offsets
+    s = np.sqrt(A[:, 0, 0] ** 2 + A[:, 1, 0] ** 2)
+    phi = np.degrees(np.arctan2(A[:, 1, 0], A[:, 0, 0]))
+    assert s.min() >= 0.1 - 1e-6 and s.max() <= 0.9 + 1e-6 and np.abs(phi).max() <= 22.5 + 1e-4
+    assert (np.abs(A[:, :, 2]) <= (1 - s)[:, None] + 1e-6).all()
+    inv2, fw2 = sample_transforms(500, np.random.default_rng(1), 0.1, 0.9, 22.5)
+    assert np.array_equal(inv, inv2) and np.array_equal(fw, fw2)
+    _, fw3 = sample_transforms(10, np.random.default_rng(2), 0.1, 0.9, 0.0, scale=0.5)
+    assert np.allclose(fw3[:, 0], 0.5) and np.allclose(fw3[:, 1], 0.0)
+
+
+def test_train_oracle_pieces_are_pinned_to_torch():
+    """oracle/train_oracle.py against PyTorch itself: with p = 0 a TrainLoraLinear is y = W x + b + s B A x exactly; with
+    p > 0 the keep-mask keeps ~(1 - p) of the elements, the survivors are scaled by 1 / (1 - p), the mask is a pure
+    function of (key, global row index) -- sharding-invariant -- and changes with the step; make_optimizer is
+    torch.optim.Adam with the reference's hyper-parameters (train_loras.py:284)."""
+    import torch
+
+    from oracle import train_oracle as to
+
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(32, 24)
+    A, B, s = torch.randn(4, 32), torch.randn(24, 4) * 0.1, 2.0
+    mod = to.TrainLoraLinear(lin, A, B, s, layer=3, adapter=1).train()
+    x = torch.randn(2, 10, 32)
+    want = lin(x) + s * (x @ A.t()) @ B.t()
+    assert torch.allclose(mod(x), want, atol=1e-5)
+    mod.p, mod.seed, mod.step, mod.row0 = 0.25, 11, 2, 40
+    keep = to.keep_mask(to.mask_seed(11, 2, 3, 1), 20, 32, 0.25, row0=40).reshape(2, 10, 32)
+    xd = torch.where(keep, x / 0.75, torch.zeros_like(x))
+    assert torch.allclose(mod(x), lin(x) + s * (xd @ A.t()) @ B.t(), atol=1e-5)
+    assert torch.allclose(mod.eval()(x), want, atol=1e-5)  # eval mode: dropout is the identity (peft)
+    key = to.mask_seed(11, 2, 3, 1)
+    m = to.keep_mask(key, 4000, 64, 0.1)
+    assert abs(float(m.float().mean()) - 0.9) < 0.01
+    assert torch.equal(m, to.keep_mask(key, 4000, 64, 0.1))
+    assert torch.equal(m[1000:], to.keep_mask(key, 3000, 64, 0.1, row0=1000))          # keyed by the global row index
+    assert not torch.equal(m, to.keep_mask(to.mask_seed(11, 3, 3, 1), 4000, 64, 0.1))  # new step, new mask
+    holder = torch.nn.Module()
+    holder.site = mod
+    holder.classifier = torch.nn.Linear(8, 3)
+    opt = to.make_optimizer(holder)
+    g0 = opt.param_groups[0]
+    assert isinstance(opt, torch.optim.Adam) and g0["lr"] == 1e-4 and tuple(g0["betas"]) == (0.9, 0.999) and g0["eps"] == 1e-8
+    assert g0["weight_decay"] == 0 and not g0["amsgrad"] and len(g0["params"]) == 4

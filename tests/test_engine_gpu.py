@@ -492,8 +492,8 @@ def test_tensor_core_constants_match_epilogue_constants(setup, monkeypatch):
 
 def test_layernorm_backward_down_projection_fusion_is_equivalent(setup, monkeypatch):
     """VITATK_LN_BT=1 (opt-in): the LayerNorm backward kernels also write the next LoRA site's dx * B^T instead of a
-    skinny GEMM launch.  Same 16-bit inputs, fp32 accumulation in a different order: logits identical, input gradient
-    equal to the default engine's up to bf16 rounding of T, and within the contract against the oracle."""
+    skinny GEMM launch.  Logits identical (forward untouched), 23 launches fewer per backward, input gradient within the
+    contract against the oracle and not less accurate than the default engine's."""
     import vitatk
     from oracle import vit_oracle as vo
 
@@ -502,15 +502,19 @@ def test_layernorm_backward_down_projection_fusion_is_equivalent(setup, monkeypa
     monkeypatch.setenv("VITATK_LN_BT", "1")
     fused = vitatk.Engine(model=m, max_batch=8, device="cuda")
     monkeypatch.delenv("VITATK_LN_BT")
-    n0, n1 = eng.launch_count(), fused.launch_count()
+    n0, n1 = eng.launch_count, fused.launch_count
     g0, l0, _ = eng.input_grad(x, y)
     g1, l1, _ = fused.input_grad(x, y)
-    d0, d1 = eng.launch_count() - n0, fused.launch_count() - n1
+    d0, d1 = eng.launch_count - n0, fused.launch_count - n1
     _, _, og = vo.input_grad(m, x, y)
     note(launches_default=d0, launches_fused=d1, rel_fused_vs_default=rel(g1, g0), rel_fused_vs_oracle=rel(g1, og))
     assert d1 == d0 - 23  # bt_proj of 12 layers + bt_fc2 of 11 (the last layer's input gradient comes from the head)
     assert torch.equal(l0, l1)
-    assert rel(g1, g0) < 5e-3 and rel(g1, og) < RTOL_GRAD
+    # T is summed in a different order and rounded to bf16 again, so the two engines differ from each other by about as
+    # much as each differs from the fp32 oracle (as in the tensor-core-constants test above)
+    e0, e1 = rel(g0, og), rel(g1, og)
+    assert e1 < RTOL_GRAD and e1 < 1.5 * e0 + 2e-3, (e0, e1)
+    assert rel(g1, g0) < RTOL_GRAD and cos(g1, g0) > MIN_COS
     fused.close()
 
 

@@ -635,6 +635,19 @@ def run_config5(args):
     f1.record()
     sync_all()
     ms_e2e = f0.elapsed_time(f1)
+    # where the step goes (outside the timed region): the PGD-7 attack alone, the training step alone (CUDA events)
+    split = {}
+    adv = trainer.engine.attack(x, y, EPS, ALPHA, K, start="rng", seed=1, image_index0=idx0)
+    for name, fn in (("attack_pgd7_ms", lambda: trainer.engine.attack(x, y, EPS, ALPHA, K, start="rng", seed=1, image_index0=idx0)),
+                     ("train_step_ms", lambda: trainer.step(adv, y, idx0))):
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        g0.record()
+        for _ in range(3):
+            fn()
+        g1.record()
+        torch.cuda.synchronize(dev)
+        split[name] = g0.elapsed_time(g1) / 3
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -670,6 +683,7 @@ def run_config5(args):
                      "note": "whole-step algorithmic FLOPs / time (no per-kernel split for this config)",
                      "peak_kind": f"{peaks_kind} sustained cuBLAS bf16"},
         "train": {"trainable_params": int(trainer.params.numel()), "loss_first_warmup": losses[0], "loss_last": float(last)},
+        "split_ms": split,
     }
     out.emit(json.dumps(line))
     if world > 1:

@@ -4,8 +4,10 @@
 // trainable = every lora_A / lora_B plus a full copy of the classifier (task_type SEQ_CLS).
 //
 // The frozen-weight forward / input-gradient path is the engine's tcgen05 GEMM / attention / LayerNorm kernels; this file
-// adds what only training needs.  All of it is HBM-bound streaming work with tiny reductions (rank r <= 64), so the
-// kernels are plain coalesced CUDA-core kernels sized to the 148 SMs -- not GEMMs reshaped for the tensor cores:
+// adds what only training needs.  All of it is HBM-bound streaming work with tiny reductions (rank r <= 64): coalesced
+// streaming kernels sized to the 148 SMs, not GEMM launches.  The rank-r products inside them run as warp-level
+// m16n8k16 MMAs (*_mma_kernel below, mma_sync.cuh) -- the first, CUDA-core versions were FMA-issue bound at 8-14x their
+// HBM time -- and the CUDA-core kernels remain as the fallback for shapes the MMA versions do not take:
 //   lora_down_kernel   T[m, c0 + j] = sum_k drop(x[m, k]) * A[j, k]                  (dropout mask regenerated, never stored)
 //   lora_dx_kernel     dX[m, k] (+)= drop'(m, k) * sum_j BT[m, c0 + j] * s A[j, k]   (LoRA share of the input gradient; the
 //                      mask applies to this share only, so it cannot ride in the frozen GEMM's accumulator), optional * mul

@@ -115,7 +115,6 @@ struct vitatk_engine {
   std::vector<bf16*> ao;     // [layers] attention output (saved: delta = rowsum(dO o O) in the backward)
   std::vector<float*> lse2;  // [layers] log2-domain logsumexp per (image, head, query)
   float* delta = nullptr;
-  float* delta_part = nullptr;  // GemmEpilogue::rowdot_part (same layout as delta)
   bf16 *cols = nullptr, *xn = nullptr, *g = nullptr, *T = nullptr;
   bf16 *dh_a = nullptr, *dh_b = nullptr, *du = nullptr, *dxn = nullptr, *dao = nullptr, *dqkv = nullptr;
   float *logits = nullptr, *loss = nullptr, *scratch_img = nullptr;
@@ -145,7 +144,6 @@ struct vitatk_engine {
   float grad_S = 256.0f;
   bool fuse_tt = true;               // plain LoRA sites: T = x*A^T comes from T-tiles inside the consumer GEMM (VITATK_TT=0: skinny GEMMs)
   unsigned int* tt_flags = nullptr;  // [2 * ceil(max M / 256)] inter-CTA flags of the T-tiles (zero between launches)
-  bool rowdot_epi16 = true;          // bproj's ROWDOT epilogue with 16 warps (VITATK_ROWDOT_EPI16=0: 8)
   bool fuse_delta = false;           // delta comes out of the proj-backward GEMM epilogue (pair kernel) instead of a kernel
   bool fuse_ln_bt = false;           // VITATK_LN_BT=1: LayerNorm backward also writes the next LoRA site's dx * B^T (no bt_proj / bt_fc2 launch)
   // ---- LoRA training (vitatk_train_*) ----
@@ -422,7 +420,6 @@ static int build_plans(vitatk_engine* e, int batch, PlanSet** out) {
         ep.rowdot = e->delta;
         ep.rowdot_rows = TOKENS;
         ep.rowdot_pad = 208;
-        ep.rowdot_part = e->rowdot_epi16 ? e->delta_part : nullptr;
       }
       if (gemm_plan_init(&p.bproj, M, D, D, e->dh_b, D, w.proj_wt, D, e->dao, D, nullptr, 0, e->T, 3 * LORA_PAD,
                          sp.la_bwd, LORA_PAD, sp.rank > 0 ? 1 : 0, lora_ksteps(sp.rank), 0, ep, &tt))
@@ -641,8 +638,6 @@ int vitatk_create(const vitatk_config* cfg, vitatk_engine** out) {
     e->fuse_delta = !(g2 && g2[0] == '0') && !(fd && fd[0] == '0') && cfg->dim % 256 == 0;
     // measured neutral on B200 (the CTA-level hand-over costs the LayerNorm kernel what the two skinny launches cost:
     // layernorm_bwd 14.8 -> 19.0 ms per step against 4.7 ms of bt_proj + bt_fc2), so opt-in like the T-tiles
-    const char* r16 = getenv("VITATK_ROWDOT_EPI16");
-    e->rowdot_epi16 = !(r16 && r16[0] == '0');
     const char* lb = getenv("VITATK_LN_BT");
     e->fuse_ln_bt = lb && lb[0] == '1' && cfg->dim == 768;
   }
@@ -847,7 +842,7 @@ int vitatk_finalize(vitatk_engine* e) {
   total += c.layers * (sz_d + sz_3d + sz_f + 2 * sz_st);  // h_mid, qkv, u, stats
   const long long sz_lse = al(static_cast<long long>(c.max_batch) * c.heads * 208 * 4);
   total += 2 * sz_d + sz_f + sz_t;                      // cols, xn, g, T
-  total += c.layers * (sz_d + sz_lse) + 2 * sz_lse;     // ao, lse2 per layer; delta, delta_part
+  total += c.layers * (sz_d + sz_lse) + sz_lse;         // ao, lse2 per layer; delta
   total += 4 * sz_d + sz_f + sz_3d;                     // dh_a, dh_b, dxn, dao, du, dqkv
   total += al(static_cast<long long>(c.max_batch) * c.num_classes * 4) + al(c.max_batch * 4) + sz_img;
   VITATK_CUDA_OK(cudaMalloc(&e->ws, total));
@@ -884,7 +879,6 @@ int vitatk_finalize(vitatk_engine* e) {
     e->lse2[l] = reinterpret_cast<float*>(take(sz_lse));
   }
   e->delta = reinterpret_cast<float*>(take(sz_lse));
-  e->delta_part = reinterpret_cast<float*>(take(sz_lse));
   e->cols = reinterpret_cast<bf16*>(take(sz_d));
   e->xn = reinterpret_cast<bf16*>(take(sz_d));
   e->g = reinterpret_cast<bf16*>(take(sz_f));

@@ -817,18 +817,12 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
             }
           }
-          size_t ridx = 0;
           if (epi.mode == EPI_ROWDOT) {
-            // one slab row = one head's 64 columns.  EW == 1: one thread holds them all.  EW == 2: the two threads of a
-            // row (column halves hh = 0 / 1, different warps) meet through rowdot_part, a global array of the same layout:
-            // hh = 1 parks its half here, the group barrier of the slab store below orders it, hh = 0 adds it to its own
-            // half (fixed order: deterministic).  Every (row, slab) has its own slot, so no buffer is ever reused.
-            ridx = (static_cast<size_t>(row / epi.rowdot_rows) * (args.N >> 6) + (scol >> 6)) * epi.rowdot_pad + row % epi.rowdot_rows;
-            if (EW == 1) {
-              if (row_ok) epi.rowdot[ridx] = dot;
-            } else if (hh == 1 && row_ok) {
-              epi.rowdot_part[ridx] = dot;
-            }
+            // one slab row = one head's 64 columns: only the EW == 1 layout holds them in one thread (the host never
+            // selects EW == 2 for this mode)
+            if (EW == 1 && row_ok)
+              epi.rowdot[(static_cast<size_t>(row / epi.rowdot_rows) * (args.N >> 6) + (scol >> 6)) * epi.rowdot_pad +
+                         row % epi.rowdot_rows] = dot;
           } else if (args.out_f16) {
 #pragma unroll
             for (int j = 0; j < NP; ++j) pk[j] = pack_f16x2(v[2 * j], v[2 * j + 1]);
@@ -839,8 +833,6 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           prefetch_slab1();
           write_row(b, pk);  // in place: each thread only ever touches its own part of its own row of the slab
           store_slab(b, &tmOut, scol, m0);
-          if (EW == 2 && epi.mode == EPI_ROWDOT && hh == 0 && row_ok)
-            epi.rowdot[ridx] = dot + *reinterpret_cast<const volatile float*>(epi.rowdot_part + ridx);
           ++c;
           if (issuer) {
             // the other buffer's last store has been read out -> fetch the next slab's residual / multiplier into it
@@ -1425,8 +1417,8 @@ int gemm_launch(const GemmPlan* p, cudaStream_t stream, int num_sms) {
       if (!p->two_cta) return launch_bn<256, false>(p, stream, num_sms);
       // 16 epilogue warps (two per TMEM lane quarter and column group) for the short-K GEMMs, whose epilogue is as long
       // as their main loop (measured: fc1 -7 %, qkv -4 %, proj -4 %, bfc2 -3 %); the K >= 2304 GEMMs are main-loop
-      // bound and lose ~3 % to the extra warps; ROWDOT needs rowdot_part to join the two halves of a slab row
-      if (gemm_epi16_enabled() && (p->epi.mode != EPI_ROWDOT || p->epi.rowdot_part != nullptr) && p->K <= gemm_epi16_max_k())
+      // bound and lose ~3 % to the extra warps, and ROWDOT needs a whole slab row in one thread
+      if (gemm_epi16_enabled() && p->epi.mode != EPI_ROWDOT && p->K <= gemm_epi16_max_k())
         return launch_bn<256, true, 2>(p, stream, num_sms);
       return launch_bn<256, true, 1>(p, stream, num_sms);
     case 192: return launch_bn<192, false>(p, stream, num_sms);

@@ -123,8 +123,6 @@ struct GemmEpilogue {
   float* rowdot;        // EPI_ROWDOT side output, [(M / rowdot_rows) * (N / 64), rowdot_pad] fp32
   int rowdot_rows;      // rows per group (tokens per image)
   int rowdot_pad;       // row pitch of the side output (208)
-  float* rowdot_part;   // scratch of the same size and layout: lets the 16-warp epilogue (two threads per slab row) run
-                        // EPI_ROWDOT; null = the 8-warp epilogue
   // Constants through the tensor core.  A consumer GEMM can take its per-column constants (bias, the LayerNorm-fold
   // c1 / c2) as rank-1 updates inside its LoRA k-block instead of loading them in the epilogue: LB carries
   // [c1_hi, c1_lo, c1_hi, c2_hi, c2_lo, c2_hi] in columns stat_col.. of every 64-column group and the producer of T

@@ -22,11 +22,11 @@ from typing import Optional, Sequence, Tuple
 
 import numpy as np
 import torch
-import torch.distributed as dist
 
 from . import _lib
 from .attacks import _unwrap, compile_model
 from .engine import IMAGENET_MEAN, IMAGENET_STD, Engine
+from .training import average_gradients
 
 
 def sample_transforms(n: int, rng: np.random.Generator, scale_min: float, scale_max: float, rotation_max: float,
@@ -107,9 +107,7 @@ class AdversarialPatch:
                            "vitatk_patch_grad")
                 self._grad.add_(g, alpha=nb / B)      # mean over the whole step = chunk means weighted by chunk size
                 loss_sum += loss.sum()
-            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-                dist.all_reduce(self._grad, op=dist.ReduceOp.SUM)   # the one collective: the shared patch's gradient
-                self._grad.div_(dist.get_world_size())
+            average_gradients(self._grad)   # the one collective: the shared patch's gradient (mean over ranks)
             self._steps += 1
             _lib.check(eng.lib.vitatk_patch_update(self.patch.data_ptr(), self._grad.data_ptr(), self._m.data_ptr(),
                                                    self._v.data_ptr(), self.patch.numel(), self.learning_rate,

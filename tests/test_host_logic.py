@@ -625,3 +625,36 @@ def test_train_oracle_pieces_are_pinned_to_torch():
     g0 = opt.param_groups[0]
     assert isinstance(opt, torch.optim.Adam) and g0["lr"] == 1e-4 and tuple(g0["betas"]) == (0.9, 0.999) and g0["eps"] == 1e-8
     assert g0["weight_decay"] == 0 and not g0["amsgrad"] and len(g0["params"]) == 4
+
+
+def test_init_adapters_follows_peft_and_the_reference_parameter_counts():
+    """training.init_adapters (peft's LoRA init for train_loras.py:79-95): the reference's five targets by suffix match
+    ("output.dense" also matches attention.output.dense), A ~ U(-1/sqrt(in), 1/sqrt(in)), B = 0 (the adapted
+    model starts identical to the base model), scale = alpha / r.  Known answer: r = 16 on the five targets plus the
+    classifier copy is 1 933 077 trainable parameters -- the number bench.py --config 5 reports (the notebook
+    configurations' 225 125 / 667 493 are pinned in test_oracle_golden.py::test_lora_known_answers)."""
+    import math
+
+    import torch
+
+    from oracle import fixtures as fx
+    from vitatk.engine import normalise_state_dict
+    from vitatk.training import REFERENCE_TARGETS, init_adapters
+
+    sd = normalise_state_dict(fx.make_model(lora=False).state_dict())
+    ad = init_adapters(sd, rank=16, alpha=16.0, targets=REFERENCE_TARGETS, seed=3)
+    assert len(ad) == 12 * 5
+    kinds = sorted({k.split("layer.")[1].split(".", 1)[1] for k in ad})
+    assert kinds == ["attention.attention.key", "attention.attention.query", "attention.attention.value",
+                     "attention.output.dense", "output.dense"]
+    n = sum(A.numel() + B.numel() for A, B, _ in ad.values())
+    n += sd["classifier.weight"].numel() + sd["classifier.bias"].numel()
+    assert n == 1933077
+    for name, (A, B, s) in ad.items():
+        assert s == 1.0 and float(B.abs().max()) == 0.0 and A.shape[0] == 16 and B.shape[1] == 16
+        bound = 1.0 / math.sqrt(A.shape[1])
+        assert float(A.abs().max()) <= bound and float(A.abs().max()) > 0.9 * bound
+        assert abs(float(A.std()) - bound / math.sqrt(3)) < 0.05 * bound
+    again = init_adapters(sd, rank=16, alpha=16.0, targets=REFERENCE_TARGETS, seed=3)
+    assert all(torch.equal(ad[k][0], again[k][0]) for k in ad)
+    assert init_adapters(sd, rank=8, alpha=16.0, targets=("query",), seed=0)["vit.encoder.layer.0.attention.attention.query"][2] == 2.0
